@@ -1,0 +1,135 @@
+"""Pin the C oracle (oracle/zs_oracle.c) against the committed cv2 golden vectors (CPU only)."""
+import numpy as np
+import pytest
+
+import oracle
+
+
+def test_pyramid_levels_and_planes(golden):
+    g = golden("pyramid")
+    L = g["L"]
+    h, w = L.shape
+    assert oracle.pyramid_num_levels(w, h, (15, 15), 3) == int(g["cv_levels_w15"])
+    assert oracle.pyramid_num_levels(w, h, (31, 31), 3) == int(g["cv_levels_w31"])
+    assert oracle.pyramid_num_levels(w, h, (63, 63), 4) == int(g["cv_levels_w63"])
+    P = oracle.Pyramid(L, (15, 15), 3)
+    assert P.levels == int(g["cv_levels_w15"])
+    for l in range(P.levels):
+        assert np.array_equal(P.image(l), g[f"cv_pyr_img{l}"])
+        assert np.array_equal(P.deriv(l), g[f"cv_pyr_der{l}"])
+
+
+@pytest.mark.parametrize("thr", [1, 10, 40])
+def test_fast_full_frame(golden, thr):
+    g = golden("detect")
+    x, y, s = oracle.fast_detect(g["L"], thr)
+    assert np.array_equal(x, g[f"cv_fast_t{thr}_x"])
+    assert np.array_equal(y, g[f"cv_fast_t{thr}_y"])
+    assert np.array_equal(s, g[f"cv_fast_t{thr}_r"])
+
+
+@pytest.mark.parametrize("name", ["L", "Lq"])
+@pytest.mark.parametrize("cell,thr", [((16, 16), 10), ((32, 32), 10), ((64, 64), 1), ((24, 16), 5)])
+def test_grid_detect(golden, name, cell, thr):
+    g = golden("detect")
+    x, y, s = oracle.grid_detect(g[name], cell, thr)
+    k = f"cv_grid_{name}_c{cell[0]}x{cell[1]}_t{thr}"
+    assert np.array_equal(x, g[k + "_x"]) and np.array_equal(y, g[k + "_y"]) and np.array_equal(s, g[k + "_r"])
+
+
+def test_grid_detect_occupancy(golden):
+    g = golden("detect")
+    x, y, s = oracle.grid_detect(g["L"], (16, 16), 10, g["occ"])
+    assert np.array_equal(x, g["cv_grid_occ_x"]) and np.array_equal(y, g["cv_grid_occ_y"])
+    assert np.array_equal(s, g["cv_grid_occ_r"])
+
+
+def test_orb_blur_and_descriptors(golden):
+    g = golden("detect")
+    L = g["L"]
+    assert np.array_equal(oracle.orb_blur(L), g["cv_orb_blur"])
+    x, y, _ = oracle.grid_detect(L, (16, 16), 10)
+    kept, desc = oracle.orb_compute(L, x, y)
+    assert np.array_equal(x[kept].astype(np.float32), g["cv_orb_kx"])
+    assert np.array_equal(y[kept].astype(np.float32), g["cv_orb_ky"])
+    assert np.array_equal(desc, g["cv_orb_desc"])
+
+
+def test_orb_rotated_subpixel(golden):
+    g = golden("detect")
+    kept, desc = oracle.orb_compute(g["L"], g["orb_in_x"], g["orb_in_y"], g["orb_in_a"])
+    assert np.array_equal(g["orb_in_x"][kept], g["cv_orb_rot_kx"])
+    assert np.array_equal(g["orb_in_y"][kept], g["cv_orb_rot_ky"])
+    assert np.array_equal(desc, g["cv_orb_rot_desc"])
+
+
+@pytest.mark.parametrize("nm,qk,tk", [("orb", "dl", "dr"), ("b16", "q16", "t16"), ("one", "dl", "dr")])
+def test_hamming_matching(golden, nm, qk, tk):
+    g = golden("match")
+    q, t = g[qk], g[tk]
+    if nm == "one":
+        t = t[:1]
+    idx, dist = oracle.match_hamming_knn2(q, t)
+    assert np.array_equal(idx, g[f"cv_knn_{nm}_idx"])
+    valid = idx >= 0
+    assert np.array_equal(dist.astype(np.float32)[valid], g[f"cv_knn_{nm}_dist"][valid])
+    oq, ot, od = oracle.match_hamming_cross(q, t)
+    assert np.array_equal(oq, g[f"cv_cross_{nm}_q"]) and np.array_equal(ot, g[f"cv_cross_{nm}_t"])
+    assert np.array_equal(od.astype(np.float32), g[f"cv_cross_{nm}_d"])
+    rq, rt, rd = oracle.ratio_test(idx, dist.astype(np.float32), 0.8)
+    assert np.array_equal(rq, g[f"cv_ratio_{nm}_q"]) and np.array_equal(rt, g[f"cv_ratio_{nm}_t"])
+    assert np.array_equal(rd, g[f"cv_ratio_{nm}_d"])
+
+
+def test_l2_matching_sift(golden):
+    g = golden("match")
+    q, t = g["sift0"].astype(np.float32), g["sift1"].astype(np.float32)
+    idx, dist = oracle.match_l2_knn2(q, t)
+    assert np.array_equal(idx, g["cv_knn_sift_idx"])
+    assert np.array_equal(dist, g["cv_knn_sift_dist"])          # bit-exact distances
+    oq, ot, od = oracle.match_l2_cross(q, t)
+    assert np.array_equal(oq, g["cv_cross_sift_q"]) and np.array_equal(ot, g["cv_cross_sift_t"])
+    assert np.array_equal(od, g["cv_cross_sift_d"])
+    rq, rt, rd = oracle.ratio_test(idx, dist, 0.8)
+    assert np.array_equal(rq, g["cv_ratio_sift_q"]) and np.array_equal(rt, g["cv_ratio_sift_t"])
+
+
+LK_CASES = [((15, 15), 3), ((21, 21), 2), ((31, 31), 3), ((31, 31), 0), ((63, 63), 3), ((31, 21), 3)]
+LK_TOL = 0.01   # px, the north-star tolerance; status flags must be identical
+
+
+@pytest.mark.parametrize("win,ml", LK_CASES)
+@pytest.mark.parametrize("init", [False, True])
+def test_lk(golden, win, ml, init):
+    g = golden("klt")
+    PA, PB = oracle.Pyramid(g["A"], win, ml), oracle.Pyramid(g["B"], win, ml)
+    k = f"{'cv_lki' if init else 'cv_lk'}_w{win[0]}x{win[1]}_l{ml}"
+    flags = oracle.LK_GET_MIN_EIGENVALS | (oracle.LK_USE_INITIAL_FLOW if init else 0)
+    p1, st, err = oracle.lk_track(PA, PB, g["pts"], g["init"] if init else None, win, ml, flags=flags)
+    assert np.array_equal(st, g[k + "_st"])
+    ok = st > 0
+    assert np.abs(p1 - g[k + "_p1"])[ok].max() < LK_TOL
+    assert np.allclose(err, g[k + "_err"], rtol=1e-4, atol=1e-6)
+
+
+def test_fb_gate(golden):
+    g = golden("klt")
+    win, ml = (31, 31), 3
+    PA, PB = oracle.Pyramid(g["A"], win, ml), oracle.Pyramid(g["B"], win, ml)
+    p1, st, _ = oracle.lk_track(PA, PB, g["pts"], None, win, ml)
+    pb, sb, _ = oracle.lk_track(PB, PA, p1, None, win, ml)
+    keep = oracle.fb_check(g["pts"], pb, st, sb, 1.0)
+    assert np.array_equal(keep, g["cv_fb_keep"])
+    assert np.abs(p1 - g["cv_fb_p1"])[keep].max() < LK_TOL
+
+
+def test_empty_inputs():
+    idx, dist = oracle.match_hamming_knn2(np.zeros((0, 32), np.uint8), np.zeros((5, 32), np.uint8))
+    assert idx.shape == (0, 2)
+    oq, _, _ = oracle.match_hamming_cross(np.zeros((3, 32), np.uint8), np.zeros((0, 32), np.uint8))
+    assert len(oq) == 0
+    x, y, s = oracle.grid_detect(np.full((64, 64), 7, np.uint8), (16, 16), 10)
+    assert len(x) == 0
+    P = oracle.Pyramid(np.zeros((64, 64), np.uint8), (15, 15), 3)
+    p1, st, err = oracle.lk_track(P, P, np.zeros((0, 2), np.float32))
+    assert p1.shape == (0, 2)
