@@ -1,0 +1,240 @@
+/*
+ * zenslam_cuda.h -- C ABI of libzenslam_cuda.so, the B200 (sm_100a) backend for ZenSLAM's
+ * per-frame stereo front-end: optical-flow pyramids, FAST/grid detection, ORB description,
+ * brute-force matching and pyramidal KLT.
+ *
+ * The reference (vinodkhare/zenslam) has no C ABI: its seams are C++ virtual interfaces over
+ * OpenCV types.  Every entry point below names the reference interface it stands behind
+ * (file:line relative to the reference root); the C++ adapter in zenslam_cuda/ converts
+ * cv::Mat / std::vector to these calls, exactly as zenslam_metal/ does for Metal
+ * (zenslam_metal/source/pyr_lk_factory.cpp:7-49).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns zs_status (0 = ok, < 0 = error),
+ *     never throws, never allocates caller-visible memory;
+ *   - `_host` functions take HOST pointers, perform the H2D/D2H copies themselves and return
+ *     when the results are in the caller's buffers (drop-in semantics of the reference calls);
+ *   - all other functions take DEVICE pointers, enqueue work on the context's stream and
+ *     return without synchronising;
+ *   - there is no CPU fallback: without a usable sm_100 device zs_context_create fails.
+ */
+#ifndef ZENSLAM_CUDA_H
+#define ZENSLAM_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZS_API __attribute__((visibility("default")))
+
+typedef int zs_status;
+enum {
+    ZS_OK = 0,
+    ZS_ERR_NO_DEVICE = -1,     /* no CUDA device / not an sm_100 part */
+    ZS_ERR_INVALID = -2,       /* bad argument */
+    ZS_ERR_CUDA = -3,          /* CUDA runtime error; see zs_last_error_string */
+    ZS_ERR_CAPACITY = -4,      /* caller buffer too small */
+    ZS_ERR_UNSUPPORTED = -5    /* valid in the reference but outside this backend (e.g. non-integer L2 input) */
+};
+
+/* cv::OPTFLOW_* values the reference passes (keypoint_tracker.cpp:153,390) */
+#define ZS_LK_USE_INITIAL_FLOW 4
+#define ZS_LK_GET_MIN_EIGENVALS 8
+
+typedef struct zs_context zs_context;    /* device + stream + scratch */
+typedef struct zs_pyramid zs_pyramid;    /* S image slots, each a padded optical-flow pyramid in HBM */
+typedef struct zs_frontend zs_frontend;  /* batched stereo front-end (native per-frame pipeline) */
+
+/* ---- availability / context ---------------------------------------------------------------
+ * cf. zenslam::metal::is_available() (zenslam_metal/include/zenslam_metal/pyr_lk.h:9) and the
+ * factory that returns an empty pointer when the backend is absent (pyr_lk_factory.cpp:41-49). */
+ZS_API int zs_is_available(void);
+ZS_API const char* zs_version(void);
+ZS_API const char* zs_status_string(zs_status s);
+ZS_API const char* zs_last_error_string(void);
+
+/* stream: a cudaStream_t to enqueue on, or NULL to let the context create its own. */
+ZS_API zs_status zs_context_create(int device, void* stream, zs_context** out);
+ZS_API void zs_context_destroy(zs_context* ctx);
+ZS_API zs_status zs_context_synchronize(zs_context* ctx);
+ZS_API void* zs_context_stream(zs_context* ctx);
+/* number of kernels this library has launched on the context since creation */
+ZS_API uint64_t zs_context_launch_count(const zs_context* ctx);
+
+/* ---- pyramids: cv::buildOpticalFlowPyramid(img, pyr, win, maxLevel, withDerivatives=true) ----
+ * utils::pyramid (zenslam_core/source/utils/utils_opencv.cpp:525-530; called processor.cpp:37,53).
+ * One zs_pyramid holds `slots` images of identical size.  Level l of slot s is an image plane
+ * padded REFLECT_101 by the window plus a zero-padded (dx,dy) int16 Scharr plane. */
+ZS_API zs_status zs_pyramid_create(zs_context* ctx, int width, int height, int slots,
+                                   int win_w, int win_h, int max_level, zs_pyramid** out);
+ZS_API void zs_pyramid_destroy(zs_pyramid* p);
+ZS_API int zs_pyramid_levels(const zs_pyramid* p);
+ZS_API zs_status zs_pyramid_level_size(const zs_pyramid* p, int level, int* width, int* height);
+/* copy `count` images into level 0 of slots first..first+count-1 (slot index taken modulo slots).
+ * src_is_host selects cudaMemcpy kind; pitch = bytes per row, stride = bytes per image. */
+ZS_API zs_status zs_pyramid_upload(zs_context* ctx, zs_pyramid* p, const uint8_t* src, size_t pitch,
+                                   size_t stride, int first, int count, int src_is_host);
+/* build levels 1.. and all derivative planes for slots first..first+count-1 (modulo slots) */
+ZS_API zs_status zs_pyramid_build(zs_context* ctx, zs_pyramid* p, int first, int count);
+/* test access: copy one un-padded level image (u8, w*h) / derivative plane (int16, w*h*2) to host */
+ZS_API zs_status zs_pyramid_download_image(zs_context* ctx, const zs_pyramid* p, int slot, int level, uint8_t* dst);
+ZS_API zs_status zs_pyramid_download_deriv(zs_context* ctx, const zs_pyramid* p, int slot, int level, int16_t* dst);
+
+/* ---- detection: keypoint_detector_grid::detect_keypoints -----------------------------------
+ * (zenslam_core/source/detection/keypoint_detector_grid.cpp:39-150; interface keypoint_detector.h:8-14)
+ * Per unoccupied cell: cv::FAST(threshold, NMS, TYPE_9_16) on the cell ROI, first maximum-response
+ * corner, cell row-major order.  Works on level 0 of slots first..first+count-1.
+ * d_occupied: [count][grid_h*grid_w] bytes or NULL.  Outputs are [count][cap] device arrays
+ * (cap >= grid_w*grid_h; d_xy is [count][cap][2], x,y interleaved like cv::KeyPoint::pt) plus d_count[count]. */
+ZS_API zs_status zs_fast_grid_detect(zs_context* ctx, const zs_pyramid* p, int first, int count,
+                                     int cell_w, int cell_h, int threshold, const uint8_t* d_occupied,
+                                     float* d_xy, float* d_response, int* d_count, int cap);
+
+/* full-frame cv::FAST(img, threshold, true) for keypoint_detector_simple
+ * (zenslam_core/source/detection/keypoint_detector_simple.cpp:38-63): raster order, optional mask
+ * d_mask [count][height][width] (0 = rejected), cap entries per image; d_count receives the true
+ * number found (may exceed cap, in which case only the first cap are stored). */
+ZS_API zs_status zs_fast_detect(zs_context* ctx, const zs_pyramid* p, int first, int count, int threshold,
+                                const uint8_t* d_mask, float* d_xy, float* d_response,
+                                int* d_count, int cap);
+
+/* ---- description: cv::ORB::create()->compute(image, keypoints, descriptors) ----------------
+ * (keypoint_detector_grid.cpp:138).  Drops keypoints outside the 31-px border keeping order,
+ * blurs (7x7 sigma 2, float32), 256 rBRIEF tests rotated by the keypoint angle (degrees; NULL = -1,
+ * what FAST keypoints carry).  In/out arrays are [count][cap]; d_src_index (optional) receives the
+ * input row each surviving keypoint came from. */
+ZS_API zs_status zs_orb_compute(zs_context* ctx, const zs_pyramid* p, int first, int count,
+                                const float* d_xy_in, const float* d_resp_in,
+                                const float* d_angle_in, const int* d_count_in, int cap,
+                                float* d_xy, float* d_resp, int* d_src_index, int* d_count,
+                                uint8_t* d_desc /* [count][cap][32] */);
+/* test access: the blurred level-0 image ORB samples from (u8, w*h) */
+ZS_API zs_status zs_orb_download_blur(zs_context* ctx, const zs_pyramid* p, int slot, uint8_t* dst);
+
+/* ---- matching: cv::BFMatcher as used by zenslam::matcher --------------------------------------
+ * (zenslam_core/source/matching/matcher.cpp:60-80; utils::create_matcher matching_utils.cpp:63-95)
+ * `pairs` independent problems; problem k matches queries d_q + k*q_stride (nq[k] rows) against
+ * train d_t + k*t_stride (nt[k] rows); strides are in elements of the pointer type (bytes for Hamming,
+ * floats for L2).  Descriptors are 32-byte rows (Hamming) or `dim` floats (L2).
+ * knn2: per query the two nearest (ties -> smaller train index): d_idx [pairs][cap_q][2] (-1 = none),
+ * d_dist [pairs][cap_q][2] (Hamming: popcount as float; L2: sqrtf of the exact integer distance),
+ * d_pass [pairs][cap_q]: Lowe ratio gate of matcher.cpp:70 ((double)d0 < ratio*(double)d1, two neighbours).
+ * cross: BFMatcher(crossCheck=true).match: d_idx [pairs][cap_q] = train index or -1, d_dist likewise. */
+ZS_API zs_status zs_match_hamming_knn2(zs_context* ctx, const uint8_t* d_q, const int* d_nq, size_t q_stride,
+                                       const uint8_t* d_t, const int* d_nt, size_t t_stride, int pairs,
+                                       int cap_q, int cap_t, double ratio,
+                                       int* d_idx, float* d_dist, uint8_t* d_pass);
+ZS_API zs_status zs_match_hamming_cross(zs_context* ctx, const uint8_t* d_q, const int* d_nq, size_t q_stride,
+                                        const uint8_t* d_t, const int* d_nt, size_t t_stride, int pairs,
+                                        int cap_q, int cap_t, int* d_idx, float* d_dist);
+/* L2 on integer-valued float descriptors (cv::SIFT, values 0..255): exact; runs the
+ * -2 A.B^T contraction on the tcgen05 tensor cores in bf16.  dim must be a multiple of 64. */
+ZS_API zs_status zs_match_l2_knn2(zs_context* ctx, const float* d_q, const int* d_nq, size_t q_stride,
+                                  const float* d_t, const int* d_nt, size_t t_stride, int pairs,
+                                  int cap_q, int cap_t, int dim, double ratio,
+                                  int* d_idx, float* d_dist, uint8_t* d_pass);
+ZS_API zs_status zs_match_l2_cross(zs_context* ctx, const float* d_q, const int* d_nq, size_t q_stride,
+                                   const float* d_t, const int* d_nt, size_t t_stride, int pairs,
+                                   int cap_q, int cap_t, int dim, int* d_idx, float* d_dist);
+
+/* ---- KLT: pyr_lk::calc_optical_flow_pyr_lk == cv::calcOpticalFlowPyrLK ----------------------
+ * (zenslam_core/include/zenslam/tracking/pyr_lk.h:15-26; zenslam_core/source/tracking/pyr_lk.cpp:25)
+ * `jobs` independent calls: job j tracks d_count[j] points from slot d_prev_slot[j] to slot
+ * d_next_slot[j] of the same zs_pyramid.  Point arrays are [jobs][cap] float2 (x,y interleaved);
+ * d_next_pts is read when flags has ZS_LK_USE_INITIAL_FLOW.  flags must include
+ * ZS_LK_GET_MIN_EIGENVALS (the only mode the reference uses), so err = min-eigenvalue. */
+typedef struct {
+    int win_w, win_h;        /* tracking.klt_window_size */
+    int max_level;           /* tracking.klt_max_level */
+    int max_iters;           /* TermCriteria.maxCount (99) */
+    double epsilon;          /* TermCriteria.epsilon (0.001) */
+    int flags;
+    double min_eig_threshold;/* 1e-4 */
+} zs_lk_params;
+
+ZS_API zs_status zs_klt_track(zs_context* ctx, const zs_pyramid* p, const int* d_prev_slot, const int* d_next_slot,
+                              const float* d_prev_pts, float* d_next_pts, const int* d_count, int jobs, int cap,
+                              const zs_lk_params* params, uint8_t* d_status, float* d_err);
+
+/* forward + backward LK and the forward-backward gate of keypoint_tracker::track_keypoints
+ * (zenslam_core/source/tracking/keypoint_tracker.cpp:129-197, 343-434): d_keep[j][i] =
+ * status && status_back && ||p0_back - p0|| < klt_threshold.  d_next_pts holds the forward result. */
+ZS_API zs_status zs_klt_track_fb(zs_context* ctx, const zs_pyramid* p, const int* d_prev_slot, const int* d_next_slot,
+                                 const float* d_prev_pts, float* d_next_pts, const int* d_count, int jobs, int cap,
+                                 const zs_lk_params* params, double klt_threshold,
+                                 uint8_t* d_status, float* d_err, uint8_t* d_keep);
+
+/* ---- host-pointer mirrors of the reference calls (single image, synchronous) ----------------- */
+
+/* pyr_lk::calc_optical_flow_pyr_lk with level-0 images (pyramids are rebuilt on the device:
+ * identical to what the reference's processor builds, utils_opencv.cpp:525-530). */
+ZS_API zs_status zs_calc_optical_flow_pyr_lk_host(zs_context* ctx,
+                                                  const uint8_t* prev_img, const uint8_t* next_img,
+                                                  int width, int height, size_t pitch,
+                                                  const float* prev_pts, float* next_pts, int n,
+                                                  uint8_t* status, float* err, const zs_lk_params* params);
+/* keypoint_detector_grid::detect_keypoints: occupied [grid_h*grid_w] or NULL; outputs sized
+ * grid_w*grid_h (x, y, response) and *32 (desc); *n_out = keypoints that survive ORB's border filter. */
+ZS_API zs_status zs_detect_keypoints_grid_host(zs_context* ctx, const uint8_t* img, int width, int height,
+                                               size_t pitch, int cell_w, int cell_h, int threshold,
+                                               const uint8_t* occupied, float* x, float* y, float* response,
+                                               uint8_t* desc, int* n_out);
+/* matcher::match_keypoints descriptor stage: mode 0 = KNN (ratio), 1 = BRUTE (cross-check);
+ * norm 0 = Hamming (32-byte rows), 1 = L2 (dim floats).  Outputs sized nq; *n_out matches. */
+ZS_API zs_status zs_match_host(zs_context* ctx, const void* q, int nq, const void* t, int nt, int dim,
+                               int norm, int mode, double ratio, int* query_idx, int* train_idx, float* distance,
+                               int* n_out);
+
+/* ---- batched stereo front-end ------------------------------------------------------------------
+ * The per-frame call pattern of keypoint_tracker::track (keypoint_tracker.cpp:41-105) restated for
+ * a batch of B consecutive stereo frames: per frame 2 pyramids, 2 grid detections + ORB, 1 stereo
+ * kNN-ratio match, 4 forward+backward KLT pairs (temporal L, temporal R from the previous frame's
+ * keypoints; stereo L->R, R->L).  The previous frame of the first batch element is carried from
+ * the preceding call.  Field names follow options.yaml. */
+typedef struct {
+    int width, height, batch;
+    int cell_w, cell_h;            /* slam.detection.cell_size */
+    int fast_threshold;            /* slam.detection.fast_threshold */
+    int klt_win_w, klt_win_h;      /* slam.tracking.klt_window_size */
+    int klt_max_level;             /* slam.tracking.klt_max_level */
+    double klt_threshold;          /* slam.tracking.klt_threshold */
+    double matcher_ratio;          /* slam.matcher_ratio */
+    int max_iters; double epsilon; double min_eig_threshold;
+} zs_frontend_options;
+
+typedef struct {               /* per-frame result views, all HOST pointers, [batch][cap] rows */
+    int cap;                   /* = grid_w*grid_h */
+    int* n_left; int* n_right;                 /* [batch] keypoints after ORB's border filter */
+    float* kp_left; float* kp_right;           /* [batch][cap][2] x,y */
+    float* resp_left; float* resp_right;       /* [batch][cap] */
+    uint8_t* desc_left; uint8_t* desc_right;   /* [batch][cap][32] */
+    int* match_idx; float* match_dist; uint8_t* match_pass;  /* stereo kNN: [batch][cap][2], [batch][cap][2], [batch][cap] */
+    /* KLT pairs, kind 0 temporal-L, 1 temporal-R, 2 stereo L->R, 3 stereo R->L */
+    float* track_pts;          /* [4][batch][cap][2] forward result */
+    uint8_t* track_keep;       /* [4][batch][cap] FB gate */
+    int* track_n;              /* [4][batch] number of points tracked */
+} zs_frontend_results;
+
+ZS_API zs_status zs_frontend_create(zs_context* ctx, const zs_frontend_options* opt, zs_frontend** out);
+ZS_API void zs_frontend_destroy(zs_frontend* fe);
+ZS_API int zs_frontend_capacity(const zs_frontend* fe);
+ZS_API size_t zs_frontend_h2d_bytes(const zs_frontend* fe);
+ZS_API size_t zs_frontend_d2h_bytes(const zs_frontend* fe);
+/* stage B stereo frames (left/right [batch][height][pitch]) into the device ring; host or device source */
+ZS_API zs_status zs_frontend_upload(zs_frontend* fe, const uint8_t* left, const uint8_t* right, size_t pitch,
+                                    size_t stride, int src_is_host);
+/* run the whole hot path on the staged batch (asynchronous) */
+ZS_API zs_status zs_frontend_run(zs_frontend* fe);
+/* copy results to host (synchronises) */
+ZS_API zs_status zs_frontend_download(zs_frontend* fe, const zs_frontend_results* res);
+/* upload + run + download with host buffers: the end-to-end call */
+ZS_API zs_status zs_frontend_process_host(zs_frontend* fe, const uint8_t* left, const uint8_t* right,
+                                          size_t pitch, size_t stride, const zs_frontend_results* res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZENSLAM_CUDA_H */

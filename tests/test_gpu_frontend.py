@@ -1,0 +1,172 @@
+"""GPU: the reference-interface mirrors (detector / matcher / pyr_lk) and the batched front-end vs the oracle."""
+import numpy as np
+import pytest
+
+import oracle
+from zenslam_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from zenslam_b200.runtime import Context
+    c = Context()
+    yield c
+    c.close()
+
+
+def oracle_detect(img, cell, thr, occ=None):
+    x, y, s = oracle.grid_detect(img, cell, thr, occ)
+    kept, desc = oracle.orb_compute(img, x, y)
+    return np.stack([x[kept], y[kept]], 1).astype(np.float32), s[kept].astype(np.float32), desc
+
+
+def test_keypoint_detector_grid_mirror(ctx):
+    from zenslam_b200 import detection_options, keypoint
+    from zenslam_b200.detection import keypoint_detector_grid
+    L, R = syn.stereo_pair(752, 480, 1001)
+    det = keypoint_detector_grid(detection_options(), ctx)
+    keypoint.index_next = 100
+    kps = det.detect_keypoints(L, {})
+    xy, resp, desc = oracle_detect(L, (16, 16), 10)
+    assert len(kps) == len(xy) and [k.index for k in kps] == list(range(100, 100 + len(kps)))
+    assert np.array_equal(np.array([k.pt for k in kps], np.float32), xy)
+    assert np.array_equal(np.array([k.response for k in kps], np.float32), resp)
+    assert np.array_equal(np.stack([k.descriptor for k in kps]), desc)
+    assert all(k.size == 7.0 and k.angle == -1.0 and k.octave == 0 and k.class_id == -1 for k in kps)
+    # occupancy from existing keypoints (keypoint_detector_grid.cpp:48-63)
+    existing = {k.index: k for k in kps[::3]}
+    kps2 = det.detect_keypoints(L, existing)
+    occ = np.zeros((480 // 16, 752 // 16), np.uint8)
+    for k in existing.values():
+        occ[int(k.pt[1]) // 16, int(k.pt[0]) // 16] = 1
+    xy2, _, desc2 = oracle_detect(L, (16, 16), 10, occ)
+    assert np.array_equal(np.array([k.pt for k in kps2], np.float32), xy2)
+    assert np.array_equal(np.stack([k.descriptor for k in kps2]), desc2)
+
+
+def test_keypoint_detector_simple_mirror(ctx):
+    from zenslam_b200 import detection_options
+    from zenslam_b200.detection import keypoint_detector_simple
+    L, _ = syn.stereo_pair(320, 240, 1002)
+    det = keypoint_detector_simple(detection_options(fast_threshold=20), ctx)
+    kps = det.detect_keypoints(L, {})
+    x, y, s = oracle.fast_detect(L, 20)
+    kept, desc = oracle.orb_compute(L, x, y)
+    assert len(kps) == len(kept)
+    assert np.array_equal(np.array([k.pt for k in kps], np.float32), np.stack([x[kept], y[kept]], 1).astype(np.float32))
+    assert np.array_equal(np.stack([k.descriptor for k in kps]), desc)
+    # mask: discs of radius min(cell)/2 around existing keypoints (keypoint_detector_simple.cpp:41-45)
+    existing = kps[::5]
+    kps2 = det.detect_keypoints(L, existing)
+    r = 8
+    drop = np.zeros(len(x), bool)
+    for k in existing:
+        cx, cy = int(round(k.pt[0])), int(round(k.pt[1]))
+        drop |= (x - cx) ** 2 + (y - cy) ** 2 <= r * r
+    kept2, desc2 = oracle.orb_compute(L, x[~drop], y[~drop])
+    assert len(kps2) == len(kept2)
+    assert np.array_equal(np.stack([k.descriptor for k in kps2]), desc2) if len(kept2) else True
+
+
+@pytest.mark.parametrize("mode", ["KNN", "BRUTE"])
+def test_matcher_mirror(ctx, mode):
+    from zenslam_b200 import detection_options, keypoint, slam_options
+    from zenslam_b200.detection import keypoint_detector_grid
+    from zenslam_b200.matching import matcher
+    L, R = syn.stereo_pair(752, 480, 1003)
+    det = keypoint_detector_grid(detection_options(), ctx)
+    keypoint.index_next = 0
+    k0 = det.detect_keypoints(L, {}); k1 = det.detect_keypoints(R, {})
+    m = matcher(slam_options(matcher=mode, matcher_ratio=0.8), True, ctx)
+    got = m.match_keypoints(k0, k1)
+    d0 = np.stack([k.descriptor for k in k0]); d1 = np.stack([k.descriptor for k in k1])
+    if mode == "KNN":
+        idx, dist = oracle.match_hamming_knn2(d0, d1)
+        q, t, d = oracle.ratio_test(idx, dist.astype(np.float32), 0.8)
+    else:
+        q, t, d = oracle.match_hamming_cross(d0, d1)
+    assert len(got) == len(q) and len(got) > 100
+    assert [g.queryIdx for g in got] == [k0[i].index for i in q]
+    assert [g.trainIdx for g in got] == [k1[i].index for i in t]
+    assert np.array_equal(np.array([g.distance for g in got], np.float32), d.astype(np.float32))
+    # map overload: keypoints whose index exists in the other set are skipped (matcher.cpp:21-53)
+    m0 = {k.index: k for k in k0}; m1 = {k.index: k for k in k1}
+    shared = k0[5]
+    m1[shared.index] = shared
+    got2 = m.match_keypoints(m0, m1)
+    assert all(g.queryIdx != shared.index and g.trainIdx != shared.index for g in got2)
+    assert m.match_keypoints([], k1) == [] and m.match_keypoints({}, m1) == []
+
+
+def test_pyr_lk_mirror_and_fb(ctx):
+    from zenslam_b200 import keypoint, tracking_options
+    from zenslam_b200.tracking import create_cuda_pyr_lk, track_keypoints
+    lk = create_cuda_pyr_lk(ctx)
+    assert lk is not None
+    seq, _ = syn.stereo_sequence(752, 480, 2, 1004, subpixel=True)
+    A, B = seq[0, 0], seq[1, 0]
+    rng = np.random.default_rng(2)
+    pts = np.stack([rng.uniform(-5, 757, 500), rng.uniform(-5, 485, 500)], 1).astype(np.float32)
+    p1, st, err = lk.calc_optical_flow_pyr_lk([A], [B], pts, None, (31, 31), 3, (99, 0.001), 8, 1e-4)
+    PA, PB = oracle.Pyramid(A, (31, 31), 3), oracle.Pyramid(B, (31, 31), 3)
+    o1, os_, oe = oracle.lk_track(PA, PB, pts, None)
+    assert np.array_equal(st, os_) and np.array_equal(p1, o1) and np.array_equal(err, oe)
+    kps = [keypoint(pt=(float(x), float(y)), index=i) for i, (x, y) in enumerate(pts)]
+    tracked = track_keypoints(lk, A, B, kps, tracking_options())
+    ob, osb, _ = oracle.lk_track(PB, PA, o1, None)
+    keep = oracle.fb_check(pts, ob, os_, osb, 1.0)
+    assert [k.index for k in tracked] == list(np.nonzero(keep)[0])
+    assert np.array_equal(np.array([k.pt for k in tracked], np.float32), o1[keep])
+    # empty input (keypoint_tracker.cpp:122)
+    assert track_keypoints(lk, A, B, [], tracking_options()) == []
+    e1, es, ee = lk.calc_optical_flow_pyr_lk(A, B, np.zeros((0, 2), np.float32), None, (31, 31), 3)
+    assert e1.shape == (0, 2)
+
+
+@pytest.mark.parametrize("w,h,B,cell", [(752, 480, 3, (16, 16)), (640, 400, 2, (32, 32))])
+def test_frontend_batches_vs_oracle(ctx, w, h, B, cell):
+    from zenslam_b200 import detection_options, slam_options, tracking_options
+    from zenslam_b200.frontend import StereoFrontend
+    opts = slam_options(matcher="KNN", matcher_ratio=0.8, detection=detection_options(cell_size=cell),
+                        tracking=tracking_options())
+    fe = StereoFrontend(ctx, w, h, B, opts)
+    nb = 2
+    seq, _ = syn.stereo_sequence(w, h, nb * B, 5000 + w, subpixel=True)
+    win, ml = (31, 31), 3
+    prev = None     # (imgL, imgR, kpL, kpR)
+    for b in range(nb):
+        chunk = seq[b * B:(b + 1) * B]
+        res = fe.process(np.ascontiguousarray(chunk[:, 0]), np.ascontiguousarray(chunk[:, 1]))
+        for k in range(B):
+            L, R = chunk[k, 0], chunk[k, 1]
+            xyl, rl, dl = oracle_detect(L, cell, 10)
+            xyr, rr, dr = oracle_detect(R, cell, 10)
+            nl, nr = res["n_left"][k], res["n_right"][k]
+            assert nl == len(xyl) and nr == len(xyr)
+            assert np.array_equal(res["kp_left"][k, :nl], xyl) and np.array_equal(res["kp_right"][k, :nr], xyr)
+            assert np.array_equal(res["resp_left"][k, :nl], rl) and np.array_equal(res["desc_left"][k, :nl], dl)
+            assert np.array_equal(res["desc_right"][k, :nr], dr)
+            oi, od = oracle.match_hamming_knn2(dl, dr)
+            assert np.array_equal(res["match_idx"][k, :nl], oi)
+            assert np.array_equal(res["match_dist"][k, :nl], od.astype(np.float32))
+            rq, _, _ = oracle.ratio_test(oi, od.astype(np.float32), 0.8)
+            assert np.array_equal(np.nonzero(res["match_pass"][k, :nl])[0], rq)
+            PL, PR = oracle.Pyramid(L, win, ml), oracle.Pyramid(R, win, ml)
+            jobs = []
+            if prev is not None:
+                jobs += [(0, prev[0], PL, prev[2]), (1, prev[1], PR, prev[3])]
+            else:
+                assert res["track_n"][0, k] == 0 and res["track_n"][1, k] == 0
+            jobs += [(2, PL, PR, xyl), (3, PR, PL, xyr)]
+            for kind, P0, P1, pts in jobs:
+                n = len(pts)
+                assert res["track_n"][kind, k] == n
+                o1, os_, _ = oracle.lk_track(P0, P1, pts, None, win, ml)
+                ob, osb, _ = oracle.lk_track(P1, P0, o1, None, win, ml)
+                keep = oracle.fb_check(pts, ob, os_, osb, 1.0)
+                assert np.array_equal(res["track_pts"][kind, k, :n], o1), (b, k, kind)
+                assert np.array_equal(res["track_keep"][kind, k, :n].astype(bool), keep)
+            prev = (PL, PR, xyl, xyr)
+    fe.close()

@@ -1,0 +1,374 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the committed cv2 golden vectors.
+Bit-exact for pyramids, keypoints, descriptors, match indices/distances; KLT within 0.01 px with identical status."""
+import numpy as np
+import pytest
+
+import oracle
+from zenslam_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+LK_TOL = 0.01
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from zenslam_b200.runtime import Context
+    c = Context()
+    yield c
+    c.close()
+
+
+def dev(ctx, a, dtype=None):
+    import torch
+    return ctx.to_device(np.ascontiguousarray(a), dtype)
+
+
+# ---------------------------------------------------------------------------------------------
+# pyramid
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,h,win,ml", [(256, 192, (15, 15), 3), (752, 480, (31, 31), 3), (752, 480, (63, 63), 4),
+                                        (321, 243, (21, 21), 5), (1280, 720, (31, 21), 3)])
+def test_pyramid_vs_oracle(ctx, w, h, win, ml):
+    from zenslam_b200.runtime import Pyramid
+    imgs = np.stack([syn.stereo_pair(w, h, 10 + w)[0], syn.stereo_pair(w, h, 11 + w)[1],
+                     np.random.default_rng(w).integers(0, 256, (h, w), dtype=np.uint8)])
+    p = Pyramid(ctx, w, h, 3, win, ml)
+    p.upload(imgs, 0)
+    p.build(0, 3)
+    for s in range(3):
+        P = oracle.Pyramid(imgs[s], win, ml)
+        assert p.levels == P.levels
+        for l in range(P.levels):
+            assert p.level_size(l) == P.level_size(l)
+            assert np.array_equal(p.image(s, l), P.image(l)), (s, l)
+            assert np.array_equal(p.deriv(s, l), P.deriv(l)), (s, l)
+
+
+def test_pyramid_golden(ctx, golden):
+    from zenslam_b200.runtime import Pyramid
+    g = golden("pyramid")
+    L = g["L"]
+    h, w = L.shape
+    p = Pyramid(ctx, w, h, 2, (15, 15), 3)
+    p.upload(L, 1)        # slot 1: exercises the slot offset
+    p.build(1, 1)
+    assert p.levels == int(g["cv_levels_w15"])
+    for l in range(p.levels):
+        assert np.array_equal(p.image(1, l), g[f"cv_pyr_img{l}"])
+        assert np.array_equal(p.deriv(1, l), g[f"cv_pyr_der{l}"])
+
+
+# ---------------------------------------------------------------------------------------------
+# detection
+# ---------------------------------------------------------------------------------------------
+def _grid(ctx, imgs, cell, thr, occ=None):
+    from zenslam_b200.runtime import Pyramid, fast_grid_detect
+    n, h, w = imgs.shape
+    p = Pyramid(ctx, w, h, n, (16, 16), 0)
+    p.upload(imgs, 0)
+    p.build(0, n)
+    xy, resp, cnt = fast_grid_detect(p, 0, n, cell, thr, occ)
+    return p, xy, resp, cnt
+
+
+@pytest.mark.parametrize("name", ["L", "Lq"])
+@pytest.mark.parametrize("cell,thr", [((16, 16), 10), ((32, 32), 10), ((64, 64), 1), ((24, 16), 5)])
+def test_grid_detect_golden(ctx, golden, name, cell, thr):
+    g = golden("detect")
+    _, xy, resp, cnt = _grid(ctx, g[name][None], cell, thr)
+    k = f"cv_grid_{name}_c{cell[0]}x{cell[1]}_t{thr}"
+    n = int(cnt[0])
+    assert n == len(g[k + "_x"])
+    xy = xy[0, :n].cpu().numpy()
+    assert np.array_equal(xy[:, 0], g[k + "_x"]) and np.array_equal(xy[:, 1], g[k + "_y"])
+    assert np.array_equal(resp[0, :n].cpu().numpy(), g[k + "_r"])
+
+
+def test_grid_detect_occupancy_golden(ctx, golden):
+    g = golden("detect")
+    _, xy, resp, cnt = _grid(ctx, g["L"][None], (16, 16), 10, g["occ"][None])
+    n = int(cnt[0])
+    xy = xy[0, :n].cpu().numpy()
+    assert np.array_equal(xy[:, 0], g["cv_grid_occ_x"]) and np.array_equal(xy[:, 1], g["cv_grid_occ_y"])
+    assert np.array_equal(resp[0, :n].cpu().numpy(), g["cv_grid_occ_r"])
+
+
+@pytest.mark.parametrize("w,h,cell,thr", [(752, 480, (16, 16), 10), (752, 480, (16, 16), 1), (1280, 1024, (32, 32), 10),
+                                          (752, 480, (64, 64), 1), (640, 400, (20, 28), 7)])
+def test_grid_detect_batch_vs_oracle(ctx, w, h, cell, thr):
+    seq, _ = syn.stereo_sequence(w, h, 3, 2000 + w, subpixel=True)
+    imgs = seq.reshape(-1, h, w)
+    imgs[1] = imgs[1] // 8 * 8           # heavy ties
+    _, xy, resp, cnt = _grid(ctx, imgs, cell, thr)
+    for i in range(len(imgs)):
+        ox, oy, osc = oracle.grid_detect(imgs[i], cell, thr)
+        n = int(cnt[i])
+        assert n == len(ox)
+        a = xy[i, :n].cpu().numpy()
+        assert np.array_equal(a[:, 0], ox) and np.array_equal(a[:, 1], oy)
+        assert np.array_equal(resp[i, :n].cpu().numpy(), osc)
+
+
+@pytest.mark.parametrize("thr", [1, 10, 40])
+def test_fast_full_frame_golden(ctx, golden, thr):
+    from zenslam_b200.runtime import Pyramid, fast_detect
+    g = golden("detect")
+    L = g["L"]
+    h, w = L.shape
+    p = Pyramid(ctx, w, h, 1, (16, 16), 0)
+    p.upload(L, 0); p.build(0, 1)
+    xy, resp, cnt = fast_detect(p, 0, 1, thr, None, 65536)
+    n = int(cnt[0])
+    assert n == len(g[f"cv_fast_t{thr}_x"])
+    a = xy[0, :n].cpu().numpy()
+    assert np.array_equal(a[:, 0], g[f"cv_fast_t{thr}_x"]) and np.array_equal(a[:, 1], g[f"cv_fast_t{thr}_y"])
+    assert np.array_equal(resp[0, :n].cpu().numpy(), g[f"cv_fast_t{thr}_r"])
+
+
+# ---------------------------------------------------------------------------------------------
+# ORB
+# ---------------------------------------------------------------------------------------------
+def test_orb_golden(ctx, golden):
+    from zenslam_b200.runtime import orb_compute
+    g = golden("detect")
+    L = g["L"]
+    p, xy, resp, cnt = _grid(ctx, L[None], (16, 16), 10)
+    oxy, oresp, src, on, desc = orb_compute(p, 0, 1, xy, resp, cnt)
+    assert np.array_equal(p.blur(0), g["cv_orb_blur"])
+    n = int(on[0])
+    assert n == len(g["cv_orb_kx"])
+    a = oxy[0, :n].cpu().numpy()
+    assert np.array_equal(a[:, 0], g["cv_orb_kx"]) and np.array_equal(a[:, 1], g["cv_orb_ky"])
+    assert np.array_equal(desc[0, :n].cpu().numpy(), g["cv_orb_desc"])
+
+
+def test_orb_rotated_subpixel_golden(ctx, golden):
+    import torch
+    from zenslam_b200.runtime import Pyramid, orb_compute
+    g = golden("detect")
+    L = g["L"]
+    h, w = L.shape
+    p = Pyramid(ctx, w, h, 1, (16, 16), 0)
+    p.upload(L, 0); p.build(0, 1)
+    xy = dev(ctx, np.stack([g["orb_in_x"], g["orb_in_y"]], 1)[None])
+    n = dev(ctx, np.array([len(g["orb_in_x"])], np.int32))
+    resp = dev(ctx, np.zeros((1, len(g["orb_in_x"])), np.float32))
+    ang = dev(ctx, g["orb_in_a"][None])
+    oxy, _, src, on, desc = orb_compute(p, 0, 1, xy, resp, n, ang)
+    k = int(on[0])
+    assert k == len(g["cv_orb_rot_kx"])
+    a = oxy[0, :k].cpu().numpy()
+    assert np.array_equal(a[:, 0], g["cv_orb_rot_kx"]) and np.array_equal(a[:, 1], g["cv_orb_rot_ky"])
+    assert np.array_equal(desc[0, :k].cpu().numpy(), g["cv_orb_rot_desc"])
+
+
+@pytest.mark.parametrize("w,h,cell", [(752, 480, (16, 16)), (1280, 720, (32, 32))])
+def test_orb_batch_vs_oracle(ctx, w, h, cell):
+    from zenslam_b200.runtime import orb_compute
+    seq, _ = syn.stereo_sequence(w, h, 2, 3000 + w)
+    imgs = seq.reshape(-1, h, w)
+    p, xy, resp, cnt = _grid(ctx, imgs, cell, 10)
+    oxy, oresp, src, on, desc = orb_compute(p, 0, len(imgs), xy, resp, cnt)
+    for i in range(len(imgs)):
+        assert np.array_equal(p.blur(i), oracle.orb_blur(imgs[i]))
+        ox, oy, osc = oracle.grid_detect(imgs[i], cell, 10)
+        kept, odesc = oracle.orb_compute(imgs[i], ox, oy)
+        n = int(on[i])
+        assert n == len(kept)
+        a = oxy[i, :n].cpu().numpy()
+        assert np.array_equal(a[:, 0], ox[kept]) and np.array_equal(a[:, 1], oy[kept])
+        assert np.array_equal(src[i, :n].cpu().numpy(), kept)
+        assert np.array_equal(oresp[i, :n].cpu().numpy(), osc[kept])
+        assert np.array_equal(desc[i, :n].cpu().numpy(), odesc)
+
+
+# ---------------------------------------------------------------------------------------------
+# matching
+# ---------------------------------------------------------------------------------------------
+def _pad(descs, cap, dtype):
+    out = np.zeros((len(descs), cap) + descs[0].shape[1:], dtype)
+    for i, d in enumerate(descs):
+        out[i, :len(d)] = d
+    return out
+
+
+@pytest.mark.parametrize("nm,qk,tk", [("orb", "dl", "dr"), ("b16", "q16", "t16"), ("one", "dl", "dr")])
+def test_hamming_golden(ctx, golden, nm, qk, tk):
+    from zenslam_b200.runtime import match_hamming_cross, match_hamming_knn2
+    g = golden("match")
+    q, t = g[qk], g[tk]
+    if nm == "one":
+        t = t[:1]
+    dq, dt = dev(ctx, q[None]), dev(ctx, t[None])
+    nq, nt = dev(ctx, np.array([len(q)], np.int32)), dev(ctx, np.array([len(t)], np.int32))
+    idx, dist, ps = match_hamming_knn2(ctx, dq, nq, dt, nt, 0.8)
+    idx, dist, ps = idx[0].cpu().numpy(), dist[0].cpu().numpy(), ps[0].cpu().numpy()
+    assert np.array_equal(idx, g[f"cv_knn_{nm}_idx"])
+    valid = idx >= 0
+    assert np.array_equal(dist[valid], g[f"cv_knn_{nm}_dist"][valid])
+    assert np.array_equal(np.nonzero(ps)[0], g[f"cv_ratio_{nm}_q"])
+    cidx, cdist = match_hamming_cross(ctx, dq, nq, dt, nt)
+    cidx, cdist = cidx[0].cpu().numpy(), cdist[0].cpu().numpy()
+    keep = np.nonzero(cidx >= 0)[0]
+    assert np.array_equal(keep, g[f"cv_cross_{nm}_q"]) and np.array_equal(cidx[keep], g[f"cv_cross_{nm}_t"])
+    assert np.array_equal(cdist[keep], g[f"cv_cross_{nm}_d"])
+
+
+def test_hamming_batch_ragged_vs_oracle(ctx):
+    from zenslam_b200.runtime import match_hamming_cross, match_hamming_knn2
+    rng = np.random.default_rng(5)
+    sizes = [(1100, 1000), (0, 50), (37, 0), (1, 1), (300, 1411), (129, 128)]
+    qs = [rng.integers(0, 256, (a, 32), dtype=np.uint8) for a, _ in sizes]
+    ts = [rng.integers(0, 256, (b, 32), dtype=np.uint8) for _, b in sizes]
+    ts[0][:40] = qs[0][100:140]; ts[0][500] = ts[0][3]           # duplicates -> ties
+    qs[4][:, 2:] = 0; ts[4][:, 2:] = 0                           # 16-bit descriptors: massive ties
+    cap_q, cap_t = 1100, 1411
+    dq, dt = dev(ctx, _pad(qs, cap_q, np.uint8)), dev(ctx, _pad(ts, cap_t, np.uint8))
+    nq = dev(ctx, np.array([a for a, _ in sizes], np.int32)); nt = dev(ctx, np.array([b for _, b in sizes], np.int32))
+    idx, dist, ps = match_hamming_knn2(ctx, dq, nq, dt, nt, 0.8)
+    cidx, cdist = match_hamming_cross(ctx, dq, nq, dt, nt)
+    idx, dist, ps, cidx, cdist = [a.cpu().numpy() for a in (idx, dist, ps, cidx, cdist)]
+    for k, (a, b) in enumerate(sizes):
+        oi, od = oracle.match_hamming_knn2(qs[k], ts[k])
+        assert np.array_equal(idx[k, :a], oi)
+        assert np.array_equal(dist[k, :a][oi >= 0], od.astype(np.float32)[oi >= 0])
+        rq, _, _ = oracle.ratio_test(oi, od.astype(np.float32), 0.8)
+        assert np.array_equal(np.nonzero(ps[k, :a])[0], rq)
+        assert not ps[k, a:].any() and (idx[k, a:] == -1).all()
+        oq, ot, odd = oracle.match_hamming_cross(qs[k], ts[k])
+        keep = np.nonzero(cidx[k, :a] >= 0)[0]
+        assert np.array_equal(keep, oq) and np.array_equal(cidx[k, keep], ot)
+        assert np.array_equal(cdist[k, keep], odd.astype(np.float32))
+
+
+def test_l2_golden_sift(ctx, golden):
+    from zenslam_b200.runtime import match_l2_cross, match_l2_knn2
+    g = golden("match")
+    q, t = g["sift0"].astype(np.float32), g["sift1"].astype(np.float32)
+    dq, dt = dev(ctx, q[None]), dev(ctx, t[None])
+    nq, nt = dev(ctx, np.array([len(q)], np.int32)), dev(ctx, np.array([len(t)], np.int32))
+    idx, dist, ps = match_l2_knn2(ctx, dq, nq, dt, nt, 0.8)
+    idx, dist, ps = idx[0].cpu().numpy(), dist[0].cpu().numpy(), ps[0].cpu().numpy()
+    assert np.array_equal(idx, g["cv_knn_sift_idx"])
+    assert np.array_equal(dist, g["cv_knn_sift_dist"])
+    assert np.array_equal(np.nonzero(ps)[0], g["cv_ratio_sift_q"])
+    cidx, cdist = match_l2_cross(ctx, dq, nq, dt, nt)
+    cidx, cdist = cidx[0].cpu().numpy(), cdist[0].cpu().numpy()
+    keep = np.nonzero(cidx >= 0)[0]
+    assert np.array_equal(keep, g["cv_cross_sift_q"]) and np.array_equal(cidx[keep], g["cv_cross_sift_t"])
+    assert np.array_equal(cdist[keep], g["cv_cross_sift_d"])
+
+
+def test_l2_rejects_non_integer(ctx):
+    from zenslam_b200 import ZenslamCudaError
+    from zenslam_b200.runtime import match_l2_knn2
+    q = np.random.default_rng(0).random((1, 8, 128), dtype=np.float32)
+    n = dev(ctx, np.array([8], np.int32))
+    with pytest.raises(ZenslamCudaError):
+        match_l2_knn2(ctx, dev(ctx, q), n, dev(ctx, q), n, 0.8)
+
+
+@pytest.mark.parametrize("nq,nt", [(2000, 2000), (517, 1033), (1, 300), (256, 128)])
+def test_l2_sift_like_vs_oracle(ctx, nq, nt):
+    from zenslam_b200.runtime import match_l2_cross, match_l2_knn2
+    rng = np.random.default_rng(nq)
+    # SIFT-like: integer-valued, row norm ~512, clipped at 255; planted duplicates for ties
+    def mk(n):
+        a = rng.gamma(0.6, 40.0, (n, 128))
+        a = a / np.linalg.norm(a, axis=1, keepdims=True) * 512
+        return np.clip(np.rint(a), 0, 255).astype(np.float32)
+    q, t = mk(nq), mk(nt)
+    if nt > 40 and nq > 10:
+        t[7] = q[3]; t[31] = q[3]; t[5] = t[6]
+    dq, dt = dev(ctx, q[None]), dev(ctx, t[None])
+    dnq, dnt = dev(ctx, np.array([nq], np.int32)), dev(ctx, np.array([nt], np.int32))
+    idx, dist, ps = match_l2_knn2(ctx, dq, dnq, dt, dnt, 0.8)
+    oi, od = oracle.match_l2_knn2(q, t)
+    assert np.array_equal(idx[0].cpu().numpy(), oi)
+    assert np.array_equal(dist[0].cpu().numpy()[oi >= 0], od[oi >= 0])
+    cidx, cdist = match_l2_cross(ctx, dq, dnq, dt, dnt)
+    cidx, cdist = cidx[0].cpu().numpy(), cdist[0].cpu().numpy()
+    oq, ot, odd = oracle.match_l2_cross(q, t)
+    keep = np.nonzero(cidx >= 0)[0]
+    assert np.array_equal(keep, oq) and np.array_equal(cidx[keep], ot) and np.array_equal(cdist[keep], odd)
+
+
+# ---------------------------------------------------------------------------------------------
+# KLT
+# ---------------------------------------------------------------------------------------------
+LK_CASES = [((15, 15), 3), ((21, 21), 2), ((31, 31), 3), ((31, 31), 0), ((63, 63), 3), ((31, 21), 3)]
+
+
+def _klt(ctx, A, B, pts, init, win, ml, fb=None):
+    from zenslam_b200 import LK_GET_MIN_EIGENVALS, LK_USE_INITIAL_FLOW
+    from zenslam_b200.runtime import LK, Pyramid, klt_track
+    h, w = A.shape
+    p = Pyramid(ctx, w, h, 2, win, ml)
+    p.upload(np.stack([A, B]), 0); p.build(0, 2)
+    n = len(pts)
+    lk = LK(win, ml, 99, 0.001, LK_GET_MIN_EIGENVALS | (LK_USE_INITIAL_FLOW if init is not None else 0), 1e-4)
+    out = klt_track(p, dev(ctx, np.array([0], np.int32)), dev(ctx, np.array([1], np.int32)), dev(ctx, pts[None]),
+                    dev(ctx, np.array([n], np.int32)), lk, None if init is None else dev(ctx, init[None].copy()), fb)
+    return [o[0].cpu().numpy() for o in out]
+
+
+@pytest.mark.parametrize("win,ml", LK_CASES)
+@pytest.mark.parametrize("init", [False, True])
+def test_klt_golden(ctx, golden, win, ml, init):
+    g = golden("klt")
+    k = f"{'cv_lki' if init else 'cv_lk'}_w{win[0]}x{win[1]}_l{ml}"
+    p1, st, err = _klt(ctx, g["A"], g["B"], g["pts"], g["init"] if init else None, win, ml)
+    assert np.array_equal(st, g[k + "_st"])
+    ok = st > 0
+    assert np.abs(p1 - g[k + "_p1"])[ok].max() < LK_TOL
+    assert np.allclose(err, g[k + "_err"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("win,ml", LK_CASES)
+@pytest.mark.parametrize("init", [False, True])
+def test_klt_bit_exact_vs_oracle(ctx, golden, win, ml, init):
+    """The CUDA kernel and the C oracle implement the same exact-integer arithmetic: identical bits."""
+    g = golden("klt")
+    PA, PB = oracle.Pyramid(g["A"], win, ml), oracle.Pyramid(g["B"], win, ml)
+    flags = oracle.LK_GET_MIN_EIGENVALS | (oracle.LK_USE_INITIAL_FLOW if init else 0)
+    o1, os_, oe = oracle.lk_track(PA, PB, g["pts"], g["init"] if init else None, win, ml, flags=flags)
+    p1, st, err = _klt(ctx, g["A"], g["B"], g["pts"], g["init"] if init else None, win, ml)
+    assert np.array_equal(st, os_)
+    assert np.array_equal(p1, o1)
+    assert np.array_equal(err, oe)
+
+
+def test_klt_fb_gate_golden(ctx, golden):
+    g = golden("klt")
+    p1, st, err, keep = _klt(ctx, g["A"], g["B"], g["pts"], None, (31, 31), 3, fb=1.0)
+    assert np.array_equal(keep.astype(bool), g["cv_fb_keep"])
+    assert np.abs(p1 - g["cv_fb_p1"])[g["cv_fb_keep"]].max() < LK_TOL
+
+
+def test_klt_multi_job_752(ctx):
+    """C2-shaped: 4 jobs over a 4-slot pyramid (temporal L/R, stereo both ways), ragged counts."""
+    from zenslam_b200 import LK_GET_MIN_EIGENVALS
+    from zenslam_b200.runtime import LK, Pyramid, klt_track
+    w, h, win, ml = 752, 480, (31, 31), 3
+    seq, _ = syn.stereo_sequence(w, h, 2, 4000, subpixel=True)
+    imgs = seq.reshape(4, h, w)          # slots: 0 = L0, 1 = R0, 2 = L1, 3 = R1
+    p = Pyramid(ctx, w, h, 4, win, ml)
+    p.upload(imgs, 0); p.build(0, 4)
+    rng = np.random.default_rng(1)
+    cap = 1200
+    counts = np.array([1200, 800, 0, 37], np.int32)
+    pts = np.stack([rng.uniform(0, w, (4, cap)), rng.uniform(0, h, (4, cap))], -1).astype(np.float32)
+    prev = np.array([0, 1, 2, 3], np.int32); nxt = np.array([2, 3, 3, 2], np.int32)
+    lk = LK(win, ml, 99, 0.001, LK_GET_MIN_EIGENVALS, 1e-4)
+    p1, st, err, keep = klt_track(p, dev(ctx, prev), dev(ctx, nxt), dev(ctx, pts), dev(ctx, counts), lk, None, 1.0)
+    p1, st, err, keep = [a.cpu().numpy() for a in (p1, st, err, keep)]
+    pyr = [oracle.Pyramid(imgs[i], win, ml) for i in range(4)]
+    for j in range(4):
+        n = counts[j]
+        o1, os_, oe = oracle.lk_track(pyr[prev[j]], pyr[nxt[j]], pts[j, :n], None, win, ml)
+        ob, osb, _ = oracle.lk_track(pyr[nxt[j]], pyr[prev[j]], o1, None, win, ml)
+        okeep = oracle.fb_check(pts[j, :n], ob, os_, osb, 1.0)
+        assert np.array_equal(st[j, :n], os_) and np.array_equal(p1[j, :n], o1) and np.array_equal(err[j, :n], oe)
+        assert np.array_equal(keep[j, :n].astype(bool), okeep)
+        assert okeep.mean() > 0.5 if n > 100 else True

@@ -1,0 +1,89 @@
+// zs_common.cuh -- shared declarations of libzenslam_cuda.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/zenslam_cuda.h"
+
+#define ZS_MAX_LEVELS 8
+
+// Device-side view of a zs_pyramid: S slots, `levels` levels.  Level l image plane of slot s starts at
+// img[l] + s*img_slot[l]; interior pixel (x,y) at + (y + pad_y)*pitch[l] + pad_x + x.  The derivative
+// plane has the same geometry with 4-byte (dx,dy int16) elements: der[l] + s*der_slot[l] (in elements).
+struct zs_pyr_view {
+    int levels, slots;
+    int pad_x, pad_y;            // pad_x = win_w rounded up to 16 (keeps interiors 16-byte aligned)
+    int w[ZS_MAX_LEVELS], h[ZS_MAX_LEVELS];
+    int pitch[ZS_MAX_LEVELS];    // bytes per padded image row (= elements per padded derivative row)
+    size_t slot_stride[ZS_MAX_LEVELS];   // elements per slot plane (pitch * padded height)
+    uint8_t* img[ZS_MAX_LEVELS];
+    short2* der[ZS_MAX_LEVELS];
+    // blurred level-0 image for ORB (un-padded, pitch blur_pitch)
+    uint8_t* blur; int blur_pitch; size_t blur_slot;
+};
+
+struct zs_context {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int sm_count;
+    uint64_t launches;
+    // growable device scratch (single-stream use)
+    void* scratch; size_t scratch_bytes;
+    // pinned host staging for the _host entry points
+    void* pinned; size_t pinned_bytes;
+    // cached pyramids for the single-image host mirrors: [0] LK (2 slots), [1] detection (1 slot)
+    zs_pyramid* host_pyr[2];
+};
+
+struct zs_pyramid {
+    zs_context* ctx;
+    int width, height, slots, win_w, win_h, max_level;
+    zs_pyr_view v;
+    void* block;        // one allocation backing every plane
+    size_t block_bytes;
+};
+
+void zs_set_error(const char* fmt, ...);
+zs_status zs_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define ZS_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) return zs_cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define ZS_LAUNCH_CHECK(ctx)                                                 \
+    do {                                                                     \
+        (ctx)->launches++;                                                   \
+        cudaError_t e__ = cudaGetLastError();                                \
+        if (e__ != cudaSuccess) return zs_cuda_fail(e__, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+#define ZS_REQUIRE(cond, msg)                                                \
+    do {                                                                     \
+        if (!(cond)) { zs_set_error("%s:%d: %s", __FILE__, __LINE__, msg); return ZS_ERR_INVALID; } \
+    } while (0)
+
+zs_status zs_scratch(zs_context* ctx, size_t bytes, void** out);
+zs_status zs_pinned(zs_context* ctx, size_t bytes, void** out);
+
+static inline int zs_div_up(int a, int b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ int zs_reflect101(int p, int n)
+{
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p;
+    return p;
+}
+
+__device__ __forceinline__ int zs_slot(int first, int i, int slots) { return (first + i) % slots; }
+
+// internal launchers (defined in the per-stage .cu files)
+zs_status zs_launch_orb_blur(zs_context* ctx, const zs_pyramid* p, int first, int count);
+zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_slot, const int* d_next_slot,
+                        const float* d_prev_pts, float* d_next_pts, const int* d_count, const int* d_pts_row, int jobs, int cap,
+                        const zs_lk_params* prm, uint8_t* d_status, float* d_err, int fb, double fb_thr, uint8_t* d_keep);

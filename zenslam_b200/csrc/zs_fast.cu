@@ -1,0 +1,353 @@
+// zs_fast.cu -- FAST-9-16 + score + 3x3 NMS, per grid cell (keypoint_detector_grid) and full frame
+// (keypoint_detector_simple).
+//
+// Reference: zenslam_core/source/detection/keypoint_detector_grid.cpp:39-120 (cells, first-max per cell,
+// row-major order) over cv::FastFeatureDetector (keypoint_detector_grid.cpp:15,90); semantics in SURVEY A.1.
+//
+// Grid kernel: one warp per cell.  The cell ROI is staged in shared memory with coalesced loads, a cheap
+// 16-bit ring-mask test finds the (few) corners, those are compacted with a ballot and scored densely
+// (one lane per corner), NMS and the first-maximum selection run on the shared score tile.  Integer only.
+// HBM traffic: each image byte is read once (cells never overlap) + 16 B per cell written.
+#include "zs_common.cuh"
+
+#define FAST_WARPS 8
+
+// does a 16-bit circular mask contain 9 contiguous set bits?
+__device__ __forceinline__ bool has_run9(uint32_t m16)
+{
+    uint32_t m = m16 | (m16 << 16);
+    uint32_t r = m & (m >> 1);       // runs of 2
+    r &= r >> 2;                     // runs of 4
+    r &= r >> 4;                     // runs of 8
+    r &= m >> 8;                     // runs of 9
+    return (r & 0xffffu) != 0;
+}
+
+// Ring test on a shared-memory tile: returns true if pixel (x,y) passes FAST-9 at threshold t.
+__device__ __forceinline__ bool fast_is_corner(const uint8_t* tile, int tp, int x, int y, int t, int d[16])
+{
+    const int v = tile[y * tp + x];
+    uint32_t dark = 0, bright = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        // ring offsets are compile-time after unrolling
+        const int dx = (k == 0 || k == 8) ? 0 : (k == 1 || k == 7) ? 1 : (k == 2 || k == 6) ? 2 : (k >= 3 && k <= 5) ? 3
+                       : (k == 9 || k == 15) ? -1 : (k == 10 || k == 14) ? -2 : -3;
+        const int dy = (k == 4 || k == 12) ? 0 : (k == 3 || k == 13) ? 1 : (k == 2 || k == 14) ? 2 : (k <= 1 || k == 15) ? 3
+                       : (k == 5 || k == 11) ? -1 : (k == 6 || k == 10) ? -2 : -3;
+        d[k] = v - (int)tile[(y + dy) * tp + (x + dx)];
+        dark |= (uint32_t)(d[k] > t) << k;
+        bright |= (uint32_t)(d[k] < -t) << k;
+    }
+    return has_run9(dark) || has_run9(bright);
+}
+
+// s = max over 16 arcs of 9 of min(d) (dark) / min(-d) (bright); score = s - 1
+__device__ __forceinline__ int fast_score(const int d[16])
+{
+    int best = -256;
+    // sliding minimum / maximum over windows of 9 by doubling: m2, m4, m8, then one more
+    int mn2[16], mx2[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { mn2[k] = min(d[k], d[(k + 1) & 15]); mx2[k] = max(d[k], d[(k + 1) & 15]); }
+    int mn4[16], mx4[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
+        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
+        best = max(best, max(mn9, -mx9));
+    }
+    return best - 1;
+}
+
+struct fast_grid_args {
+    zs_pyr_view v;
+    int first, count;
+    int cw, ch, gw, gh, threshold;
+    const uint8_t* occupied;     // [count][gh*gw] or null
+    // per-cell candidates: [count][gh*gw]
+    int* cand;                   // packed: (score << 20) | (y_in_cell << 10) | x_in_cell, or -1
+};
+
+// grid: (ceil(cells / FAST_WARPS), count); dynamic smem = FAST_WARPS * (tile + score tile + corner list)
+__global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_grid(fast_grid_args a)
+{
+    extern __shared__ uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cells = a.gw * a.gh;
+    const int cell = blockIdx.x * FAST_WARPS + warp;
+    if (cell >= cells) return;
+    const int img = blockIdx.y;
+    int* cand = a.cand + (size_t)img * cells + cell;
+    if (a.occupied && a.occupied[(size_t)img * cells + cell]) { if (lane == 0) *cand = -1; return; }
+
+    const int tp = (a.cw + 3) & ~3;                        // tile pitch
+    const int tile_bytes = tp * a.ch;
+    const int list_cap = (a.cw - 6) * (a.ch - 6);
+    uint8_t* tile = smem + (size_t)warp * (2 * tile_bytes + 2 * ((list_cap + 1) & ~1));
+    uint8_t* score = tile + tile_bytes;
+    uint16_t* list = (uint16_t*)(score + tile_bytes);
+
+    const int gx = cell % a.gw, gy = cell / a.gw;
+    const int slot = zs_slot(a.first, img, a.v.slots);
+    const int pitch = a.v.pitch[0];
+    const uint8_t* src = a.v.img[0] + (size_t)slot * a.v.slot_stride[0] + (size_t)(a.v.pad_y + gy * a.ch) * pitch
+                         + a.v.pad_x + gx * a.cw;
+
+    // stage the cell (the reference clips cells to the image, but with integer-division grids every cell
+    // is full-size: keypoint_detector_grid.cpp:42,79-85)
+    if ((a.cw & 3) == 0) {
+        const int wpr = a.cw >> 2;                          // words per row; src is 4-byte aligned
+        for (int i = lane; i < wpr * a.ch; i += 32) {
+            const int r = i / wpr, c = i - r * wpr;
+            ((uint32_t*)(tile + r * tp))[c] = *(const uint32_t*)(src + (size_t)r * pitch + 4 * c);
+        }
+    } else {
+        for (int i = lane; i < a.cw * a.ch; i += 32) {
+            const int r = i / a.cw, c = i - r * a.cw;
+            tile[r * tp + c] = src[(size_t)r * pitch + c];
+        }
+    }
+    for (int i = lane; i < tile_bytes / 4; i += 32) ((uint32_t*)score)[i] = 0;
+    __syncwarp();
+
+    // pass 1: ring-mask test over the interior, compact corners
+    const int iw = a.cw - 6, ih = a.ch - 6;
+    const int npx = iw * ih;
+    int ncorners = 0;
+    int d[16];
+    for (int base = 0; base < npx; base += 32) {
+        const int i = base + lane;
+        bool corner = false;
+        int x = 0, y = 0;
+        if (i < npx) {
+            y = i / iw; x = i - y * iw; x += 3; y += 3;
+            corner = fast_is_corner(tile, tp, x, y, a.threshold, d);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, corner);
+        if (corner) list[ncorners + __popc(m & ((1u << lane) - 1))] = (uint16_t)(y * a.cw + x);
+        ncorners += __popc(m);
+    }
+    if (ncorners == 0) { if (lane == 0) *cand = -1; return; }
+    __syncwarp();
+
+    // pass 2: score the corners densely
+    for (int base = 0; base < ncorners; base += 32) {
+        const int i = base + lane;
+        if (i < ncorners) {
+            const int p = list[i], y = p / a.cw, x = p - y * a.cw;
+            fast_is_corner(tile, tp, x, y, a.threshold, d);
+            score[y * tp + x] = (uint8_t)fast_score(d);
+        }
+    }
+    __syncwarp();
+
+    // pass 3: NMS (strictly greater than all 8 neighbours) + first maximum in raster order
+    unsigned best = 0;     // key = (score + 1) << 20 | (0xfffff - raster); 0 = none
+    for (int base = 0; base < ncorners; base += 32) {
+        const int i = base + lane;
+        if (i < ncorners) {
+            const int p = list[i], y = p / a.cw, x = p - y * a.cw;
+            const int s = score[y * tp + x];
+            const uint8_t* r0 = score + (y - 1) * tp + x;
+            const uint8_t* r1 = r0 + tp; const uint8_t* r2 = r1 + tp;
+            const bool keep = s > r0[-1] && s > r0[0] && s > r0[1] && s > r1[-1] && s > r1[1] && s > r2[-1] && s > r2[0] &&
+                              s > r2[1];
+            if (keep) best = max(best, ((unsigned)(s + 1) << 20) | (0xfffffu - (unsigned)p));
+        }
+    }
+    best = __reduce_max_sync(0xffffffffu, best);
+    if (lane == 0) {
+        if (best == 0) *cand = -1;
+        else {
+            const int s = (int)(best >> 20) - 1;
+            const int p = 0xfffff - (int)(best & 0xfffffu);
+            const int y = p / a.cw, x = p - y * a.cw;
+            *cand = (s << 20) | (y << 10) | x;
+        }
+    }
+}
+
+// Compaction in cell row-major order: one block per image, block-wide exclusive scan over the cells.
+__global__ void __launch_bounds__(1024) k_grid_compact(const int* __restrict__ cand, int cells, int gw, int cw, int ch,
+                                                       float2* __restrict__ oxy,
+                                                       float* __restrict__ oresp, int* __restrict__ ocount, int cap)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int img = blockIdx.x;
+    const int* c = cand + (size_t)img * cells;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < cells; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = (i < cells) ? c[i] : -1;
+        const int f = v >= 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, f);
+        const int wpre = __popc(m & ((1u << lane) - 1));
+        if (lane == 0) warp_sums[warp] = __popc(m);
+        __syncthreads();
+        int woff = 0, total = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { const int s = warp_sums[k]; if (k < warp) woff += s; total += s; }
+        const int pos = carry + woff + wpre;
+        if (f && pos < cap) {
+            const int gx = i % gw, gy = i / gw;
+            oxy[(size_t)img * cap + pos] = make_float2((float)(gx * cw + (v & 1023)), (float)(gy * ch + ((v >> 10) & 1023)));
+            oresp[(size_t)img * cap + pos] = (float)(v >> 20);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ocount[img] = min(carry, cap);
+}
+
+extern "C" zs_status zs_fast_grid_detect(zs_context* ctx, const zs_pyramid* p, int first, int count, int cell_w,
+                                         int cell_h, int threshold, const uint8_t* d_occupied, float* d_xy,
+                                         float* d_response, int* d_count, int cap)
+{
+    ZS_REQUIRE(ctx && p && d_xy && d_response && d_count, "null argument");
+    ZS_REQUIRE(count >= 0 && count <= p->slots && first >= 0, "bad slot range");
+    ZS_REQUIRE(cell_w >= 7 && cell_h >= 7 && cell_w <= 256 && cell_h <= 256, "cell size must be within 7..256");
+    const int gw = p->width / cell_w, gh = p->height / cell_h;
+    const int cells = gw * gh;
+    ZS_REQUIRE(cap >= cells || cells == 0, "cap < number of cells");
+    if (count == 0) return ZS_OK;
+    if (cells == 0) { ZS_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int) * count, ctx->stream)); return ZS_OK; }
+    threshold = threshold < 0 ? 0 : threshold > 255 ? 255 : threshold;
+    void* scratch;
+    zs_status st = zs_scratch(ctx, sizeof(int) * (size_t)cells * count, &scratch);
+    if (st != ZS_OK) return st;
+    fast_grid_args a;
+    a.v = p->v; a.first = first; a.count = count; a.cw = cell_w; a.ch = cell_h; a.gw = gw; a.gh = gh;
+    a.threshold = threshold; a.occupied = d_occupied; a.cand = (int*)scratch;
+    const int tp = (cell_w + 3) & ~3;
+    const int list_cap = (cell_w - 6) * (cell_h - 6);
+    const size_t smem = (size_t)FAST_WARPS * (2 * tp * cell_h + 2 * ((list_cap + 1) & ~1));
+    ZS_REQUIRE(smem <= 220 * 1024, "cell too large for the shared-memory tile");
+    if (smem > 48 * 1024)
+        ZS_CUDA(cudaFuncSetAttribute(k_fast_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fast_grid<<<dim3(zs_div_up(cells, FAST_WARPS), count), FAST_WARPS * 32, smem, ctx->stream>>>(a);
+    ZS_LAUNCH_CHECK(ctx);
+    k_grid_compact<<<count, 1024, 0, ctx->stream>>>(a.cand, cells, gw, cell_w, cell_h, (float2*)d_xy, d_response, d_count, cap);
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Full-frame FAST for keypoint_detector_simple (zenslam_core/source/detection/keypoint_detector_simple.cpp:38-63):
+// cv::FAST(img, threshold, true) + mask, raster order.
+//   k_fast_score_map   score (s-1, 0 = not a corner) for every pixel of the frame
+//   k_fast_nms_rows    per row: NMS + mask -> (count pass) row counts / (write pass) compacted output
+//   k_row_scan         exclusive scan of the row counts, one block per image
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fast_score_map(zs_pyr_view v, int first, int threshold, uint8_t* __restrict__ score)
+{
+    const int w = v.w[0], h = v.h[0], pitch = v.pitch[0];
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= w || y >= h) return;
+    const int slot = zs_slot(first, blockIdx.z, v.slots);
+    uint8_t out = 0;
+    if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {
+        const uint8_t* img = v.img[0] + (size_t)slot * v.slot_stride[0] + (size_t)v.pad_y * pitch + v.pad_x;
+        int d[16];
+        if (fast_is_corner(img, pitch, x, y, threshold, d)) out = (uint8_t)fast_score(d);
+    }
+    score[((size_t)blockIdx.z * h + y) * w + x] = out;
+}
+
+// one warp per row; pass 0 counts, pass 1 writes
+__global__ void __launch_bounds__(256) k_fast_nms_rows(const uint8_t* __restrict__ score, const uint8_t* __restrict__ mask,
+                                                       int w, int h, int write, int* __restrict__ row_count,
+                                                       const int* __restrict__ row_off, float2* __restrict__ oxy,
+                                                       float* __restrict__ oresp, int cap)
+{
+    const int lane = threadIdx.x & 31;
+    const int y = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int img = blockIdx.y;
+    if (y >= h) return;
+    int n = 0;
+    if (y >= 3 && y < h - 3) {
+        const uint8_t* r1 = score + ((size_t)img * h + y) * w;
+        const uint8_t* r0 = r1 - w; const uint8_t* r2 = r1 + w;
+        const int base_out = write ? row_off[(size_t)img * h + y] : 0;
+        for (int x0 = 0; x0 < w; x0 += 32) {
+            const int x = x0 + lane;
+            bool keep = false;
+            int s = 0;
+            if (x >= 3 && x < w - 3) {
+                s = r1[x];
+                keep = s > 0 && s > r0[x - 1] && s > r0[x] && s > r0[x + 1] && s > r1[x - 1] && s > r1[x + 1] && s > r2[x - 1] &&
+                       s > r2[x] && s > r2[x + 1];
+                if (keep && mask) keep = mask[((size_t)img * h + y) * w + x] != 0;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (write && keep) {
+                const int pos = base_out + n + __popc(m & ((1u << lane) - 1));
+                if (pos < cap) {
+                    oxy[(size_t)img * cap + pos] = make_float2((float)x, (float)y);
+                    oresp[(size_t)img * cap + pos] = (float)s;
+                }
+            }
+            n += __popc(m);
+        }
+    }
+    if (!write && lane == 0) row_count[(size_t)img * h + y] = n;
+}
+
+__global__ void __launch_bounds__(1024) k_row_scan(const int* __restrict__ row_count, int h, int* __restrict__ row_off,
+                                                   int* __restrict__ total)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int img = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < h; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < h ? row_count[(size_t)img * h + i] : 0;
+        int s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+        if (lane == 31) warp_sums[warp] = s;
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int k = 0; k < 32; ++k) { const int ws = warp_sums[k]; if (k < warp) woff += ws; tot += ws; }
+        if (i < h) row_off[(size_t)img * h + i] = carry + woff + s - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[img] = carry;
+}
+
+extern "C" zs_status zs_fast_detect(zs_context* ctx, const zs_pyramid* p, int first, int count, int threshold,
+                                    const uint8_t* d_mask, float* d_xy, float* d_response, int* d_count, int cap)
+{
+    ZS_REQUIRE(ctx && p && d_xy && d_response && d_count, "null argument");
+    ZS_REQUIRE(count >= 0 && count <= p->slots && first >= 0 && cap > 0, "bad range");
+    if (count == 0) return ZS_OK;
+    threshold = threshold < 0 ? 0 : threshold > 255 ? 255 : threshold;
+    const int w = p->width, h = p->height;
+    const size_t plane = ((size_t)count * w * h + 255) / 256 * 256;
+    void* s;
+    zs_status st = zs_scratch(ctx, plane + sizeof(int) * 2 * (size_t)count * h, &s);
+    if (st != ZS_OK) return st;
+    uint8_t* score = (uint8_t*)s;
+    int* row_count = (int*)(score + plane);
+    int* row_off = row_count + (size_t)count * h;
+    k_fast_score_map<<<dim3(zs_div_up(w, 32), zs_div_up(h, 8), count), 256, 0, ctx->stream>>>(p->v, first, threshold, score);
+    ZS_LAUNCH_CHECK(ctx);
+    k_fast_nms_rows<<<dim3(zs_div_up(h, 8), count), 256, 0, ctx->stream>>>(score, d_mask, w, h, 0, row_count, nullptr, nullptr,
+                                                                          nullptr, cap);
+    ZS_LAUNCH_CHECK(ctx);
+    k_row_scan<<<count, 1024, 0, ctx->stream>>>(row_count, h, row_off, d_count);
+    ZS_LAUNCH_CHECK(ctx);
+    k_fast_nms_rows<<<dim3(zs_div_up(h, 8), count), 256, 0, ctx->stream>>>(score, d_mask, w, h, 1, nullptr, row_off, (float2*)d_xy,
+                                                                          d_response, cap);
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}

@@ -1,0 +1,211 @@
+// zs_frontend.cu -- the batched stereo front-end: the per-frame call pattern of keypoint_tracker::track
+// (zenslam_core/source/tracking/keypoint_tracker.cpp:41-105) + processor's pyramid builds (processor.cpp:37,53)
+// for B consecutive stereo frames per launch sequence.
+//
+// Slot layout of the single zs_pyramid (2B + 2 slots):   0 = carried left frame, 1 = carried right frame,
+//   2 .. B+1 = left frames of the batch, B+2 .. 2B+1 = right frames.  Keypoint arrays use the same rows.
+// Per batch (all on one stream, 2B images / 4B KLT jobs per launch):
+//   upload -> pyramid build -> grid FAST -> ORB (blur, filter, rBRIEF) -> stereo Hamming kNN + ratio
+//   -> fused forward+backward KLT with FB gate for {temporal L, temporal R, stereo L->R, stereo R->L}
+//   -> carry the last frame (pyramid planes + keypoints) into slots 0/1.
+#include <stdlib.h>
+
+#include "zs_common.cuh"
+
+struct zs_frontend {
+    zs_context* ctx;
+    zs_frontend_options opt;
+    int B, cap, gw, gh, slots;
+    zs_pyramid* pyr;
+    uint8_t* dev; size_t dev_bytes;
+    // device arrays (rows = slots unless noted)
+    float* raw_xy; float* raw_resp; int* raw_n;          // [2B][cap]: grid candidates before ORB's border filter
+    float* xy; float* resp; int* n; uint8_t* desc;       // [slots][cap]
+    int* m_idx; float* m_dist; uint8_t* m_pass;          // [B][cap]
+    int* job_prev; int* job_next; int* job_row;          // [4B]
+    float* t_pts; uint8_t* t_status; float* t_err; uint8_t* t_keep;   // [4B][cap]
+    int* t_n;                                            // [4B] points tracked per job
+    bool have_carry;
+    // pinned host staging for process_host
+    uint8_t* pin; size_t pin_bytes;
+};
+
+static inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+
+// t_n[j] = n[row[j]]
+__global__ void k_gather_counts(const int* __restrict__ n, const int* __restrict__ row, int jobs, int* __restrict__ out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < jobs) out[j] = n[row[j]];
+}
+
+extern "C" zs_status zs_frontend_create(zs_context* ctx, const zs_frontend_options* opt, zs_frontend** out)
+{
+    ZS_REQUIRE(ctx && opt && out, "null argument");
+    ZS_REQUIRE(opt->width > 0 && opt->height > 0 && opt->batch > 0, "bad geometry");
+    ZS_REQUIRE(opt->cell_w >= 7 && opt->cell_h >= 7, "cell size must be at least 7");
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    zs_frontend* fe = (zs_frontend*)calloc(1, sizeof(zs_frontend));
+    fe->ctx = ctx; fe->opt = *opt; fe->B = opt->batch;
+    fe->gw = opt->width / opt->cell_w; fe->gh = opt->height / opt->cell_h;
+    fe->cap = fe->gw * fe->gh;
+    if (fe->cap < 1) { free(fe); zs_set_error("image smaller than one cell"); return ZS_ERR_INVALID; }
+    fe->slots = 2 * fe->B + 2;
+    zs_status st = zs_pyramid_create(ctx, opt->width, opt->height, fe->slots, opt->klt_win_w, opt->klt_win_h,
+                                     opt->klt_max_level, &fe->pyr);
+    if (st != ZS_OK) { free(fe); return st; }
+    const size_t B = fe->B, cap = fe->cap, S = fe->slots, J = 4 * B;
+    size_t off = 0;
+#define CARVE(field, type, count) const size_t o_##field = off; off += al256(sizeof(type) * (count));
+    CARVE(raw_xy, float, 2 * (2 * B) * cap) CARVE(raw_resp, float, 2 * B * cap) CARVE(raw_n, int, 2 * B)
+    CARVE(xy, float, 2 * S * cap) CARVE(resp, float, S * cap) CARVE(n, int, S) CARVE(desc, uint8_t, S * cap * 32)
+    CARVE(m_idx, int, 2 * B * cap) CARVE(m_dist, float, 2 * B * cap) CARVE(m_pass, uint8_t, B * cap)
+    CARVE(job_prev, int, J) CARVE(job_next, int, J) CARVE(job_row, int, J)
+    CARVE(t_pts, float, 2 * J * cap) CARVE(t_status, uint8_t, J * cap) CARVE(t_err, float, J * cap)
+    CARVE(t_keep, uint8_t, J * cap) CARVE(t_n, int, J)
+#undef CARVE
+    cudaError_t e = cudaMalloc((void**)&fe->dev, off);
+    if (e != cudaSuccess) { zs_pyramid_destroy(fe->pyr); free(fe); return zs_cuda_fail(e, "cudaMalloc(frontend)", __FILE__, __LINE__); }
+    fe->dev_bytes = off;
+    cudaMemsetAsync(fe->dev, 0, off, ctx->stream);
+#define BIND(field, type) fe->field = (type*)(fe->dev + o_##field);
+    BIND(raw_xy, float) BIND(raw_resp, float) BIND(raw_n, int) BIND(xy, float) BIND(resp, float) BIND(n, int)
+    BIND(desc, uint8_t) BIND(m_idx, int) BIND(m_dist, float) BIND(m_pass, uint8_t) BIND(job_prev, int) BIND(job_next, int)
+    BIND(job_row, int) BIND(t_pts, float) BIND(t_status, uint8_t) BIND(t_err, float) BIND(t_keep, uint8_t) BIND(t_n, int)
+#undef BIND
+    // job tables: kind-major [4][B]
+    int* h = (int*)malloc(sizeof(int) * 3 * J);
+    int *hp = h, *hn = h + J, *hr = h + 2 * J;
+    for (size_t k = 0; k < B; ++k) {
+        const int L = 2 + (int)k, R = (int)B + 2 + (int)k;
+        const int Lp = k == 0 ? 0 : L - 1, Rp = k == 0 ? 1 : R - 1;
+        hp[0 * B + k] = Lp; hn[0 * B + k] = L; hr[0 * B + k] = Lp;      // temporal left: previous frame's keypoints
+        hp[1 * B + k] = Rp; hn[1 * B + k] = R; hr[1 * B + k] = Rp;      // temporal right
+        hp[2 * B + k] = L;  hn[2 * B + k] = R; hr[2 * B + k] = L;       // stereo L -> R
+        hp[3 * B + k] = R;  hn[3 * B + k] = L; hr[3 * B + k] = R;       // stereo R -> L
+    }
+    e = cudaMemcpyAsync(fe->job_prev, hp, sizeof(int) * J, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(fe->job_next, hn, sizeof(int) * J, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(fe->job_row, hr, sizeof(int) * J, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    free(h);
+    if (e != cudaSuccess) { zs_frontend_destroy(fe); return zs_cuda_fail(e, "frontend job tables", __FILE__, __LINE__); }
+    *out = fe;
+    return ZS_OK;
+}
+
+extern "C" void zs_frontend_destroy(zs_frontend* fe)
+{
+    if (!fe) return;
+    cudaSetDevice(fe->ctx->device);
+    cudaStreamSynchronize(fe->ctx->stream);
+    if (fe->pyr) zs_pyramid_destroy(fe->pyr);
+    if (fe->dev) cudaFree(fe->dev);
+    if (fe->pin) cudaFreeHost(fe->pin);
+    free(fe);
+}
+
+extern "C" int zs_frontend_capacity(const zs_frontend* fe) { return fe ? fe->cap : 0; }
+
+extern "C" size_t zs_frontend_h2d_bytes(const zs_frontend* fe)
+{
+    return fe ? (size_t)2 * fe->B * fe->opt.width * fe->opt.height : 0;
+}
+
+extern "C" size_t zs_frontend_d2h_bytes(const zs_frontend* fe)
+{
+    if (!fe) return 0;
+    const size_t B = fe->B, cap = fe->cap;
+    // counts + keypoints + responses + descriptors (both cameras) + match idx/dist/pass + tracks pts/keep/n
+    return 2 * B * 4 + 2 * B * cap * (8 + 4 + 32) + B * cap * (8 + 8 + 1) + 4 * B * cap * (8 + 1) + 4 * B * 4;
+}
+
+extern "C" zs_status zs_frontend_upload(zs_frontend* fe, const uint8_t* left, const uint8_t* right, size_t pitch, size_t stride,
+                                        int src_is_host)
+{
+    ZS_REQUIRE(fe && left && right, "null argument");
+    zs_status st = zs_pyramid_upload(fe->ctx, fe->pyr, left, pitch, stride, 2, fe->B, src_is_host);
+    if (st != ZS_OK) return st;
+    return zs_pyramid_upload(fe->ctx, fe->pyr, right, pitch, stride, fe->B + 2, fe->B, src_is_host);
+}
+
+extern "C" zs_status zs_frontend_run(zs_frontend* fe)
+{
+    ZS_REQUIRE(fe, "null argument");
+    zs_context* ctx = fe->ctx;
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    const int B = fe->B, cap = fe->cap;
+    const zs_frontend_options& o = fe->opt;
+    zs_status st;
+    // 1. pyramids of the 2B new images (utils::pyramid, processor.cpp:37,53)
+    if ((st = zs_pyramid_build(ctx, fe->pyr, 2, 2 * B)) != ZS_OK) return st;
+    if (!fe->have_carry) {
+        // very first batch of a sequence: there is no previous frame; slots 0/1 stay empty (n = 0), so the
+        // temporal jobs of frame 0 track zero points
+        ZS_CUDA(cudaMemsetAsync(fe->n, 0, sizeof(int) * 2, ctx->stream));
+    }
+    // 2. detection (keypoint_tracker.cpp:53,69 -> keypoint_detector_grid.cpp:39-150), no occupancy: every cell is searched
+    if ((st = zs_fast_grid_detect(ctx, fe->pyr, 2, 2 * B, o.cell_w, o.cell_h, o.fast_threshold, nullptr, fe->raw_xy, fe->raw_resp,
+                                  fe->raw_n, cap)) != ZS_OK) return st;
+    // 3. ORB::compute (keypoint_detector_grid.cpp:138)
+    if ((st = zs_orb_compute(ctx, fe->pyr, 2, 2 * B, fe->raw_xy, fe->raw_resp, nullptr, fe->raw_n, cap, fe->xy + (size_t)2 * cap * 2,
+                             fe->resp + (size_t)2 * cap, nullptr, fe->n + 2, fe->desc + (size_t)2 * cap * 32)) != ZS_OK) return st;
+    // 4. stereo kNN + ratio (matcher.cpp:60-75), left = query, right = train
+    if ((st = zs_match_hamming_knn2(ctx, fe->desc + (size_t)2 * cap * 32, fe->n + 2, (size_t)cap * 32,
+                                    fe->desc + (size_t)(B + 2) * cap * 32, fe->n + B + 2, (size_t)cap * 32, B, cap, cap,
+                                    o.matcher_ratio, fe->m_idx, fe->m_dist, fe->m_pass)) != ZS_OK) return st;
+    // 5. four forward+backward KLT pairs per frame (keypoint_tracker.cpp:47,50,60-67,76-83)
+    zs_lk_params prm;
+    prm.win_w = o.klt_win_w; prm.win_h = o.klt_win_h; prm.max_level = o.klt_max_level; prm.max_iters = o.max_iters;
+    prm.epsilon = o.epsilon; prm.flags = ZS_LK_GET_MIN_EIGENVALS; prm.min_eig_threshold = o.min_eig_threshold;
+    if ((st = zs_klt_launch(ctx, fe->pyr, fe->job_prev, fe->job_next, fe->xy, fe->t_pts, fe->n, fe->job_row, 4 * B, cap, &prm,
+                            fe->t_status, fe->t_err, 1, o.klt_threshold, fe->t_keep)) != ZS_OK) return st;
+    k_gather_counts<<<zs_div_up(4 * B, 256), 256, 0, ctx->stream>>>(fe->n, fe->job_row, 4 * B, fe->t_n);
+    ZS_LAUNCH_CHECK(ctx);
+    // 6. carry the last stereo frame into slots 0/1 (pyramid planes and keypoints)
+    const zs_pyr_view& v = fe->pyr->v;
+    for (int cam = 0; cam < 2; ++cam) {
+        const int src = cam == 0 ? B + 1 : 2 * B + 1, dst = cam;
+        for (int l = 0; l < v.levels; ++l) {
+            ZS_CUDA(cudaMemcpyAsync(v.img[l] + (size_t)dst * v.slot_stride[l], v.img[l] + (size_t)src * v.slot_stride[l],
+                                    v.slot_stride[l], cudaMemcpyDeviceToDevice, ctx->stream));
+            ZS_CUDA(cudaMemcpyAsync(v.der[l] + (size_t)dst * v.slot_stride[l], v.der[l] + (size_t)src * v.slot_stride[l],
+                                    v.slot_stride[l] * sizeof(short2), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        ZS_CUDA(cudaMemcpyAsync(fe->xy + (size_t)dst * cap * 2, fe->xy + (size_t)src * cap * 2, sizeof(float) * 2 * cap,
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+        ZS_CUDA(cudaMemcpyAsync(fe->n + dst, fe->n + src, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    fe->have_carry = true;
+    return ZS_OK;
+}
+
+extern "C" zs_status zs_frontend_download(zs_frontend* fe, const zs_frontend_results* r)
+{
+    ZS_REQUIRE(fe && r, "null argument");
+    ZS_REQUIRE(r->cap == fe->cap, "results.cap must equal zs_frontend_capacity()");
+    zs_context* ctx = fe->ctx;
+    const size_t B = fe->B, cap = fe->cap;
+    const cudaMemcpyKind k = cudaMemcpyDeviceToHost;
+#define DL(dst, src, bytes) if (dst) ZS_CUDA(cudaMemcpyAsync(dst, src, bytes, k, ctx->stream));
+    DL(r->n_left, fe->n + 2, sizeof(int) * B) DL(r->n_right, fe->n + B + 2, sizeof(int) * B)
+    DL(r->kp_left, fe->xy + 2 * cap * 2, sizeof(float) * 2 * B * cap) DL(r->kp_right, fe->xy + (B + 2) * cap * 2, sizeof(float) * 2 * B * cap)
+    DL(r->resp_left, fe->resp + 2 * cap, sizeof(float) * B * cap) DL(r->resp_right, fe->resp + (B + 2) * cap, sizeof(float) * B * cap)
+    DL(r->desc_left, fe->desc + 2 * cap * 32, B * cap * 32) DL(r->desc_right, fe->desc + (B + 2) * cap * 32, B * cap * 32)
+    DL(r->match_idx, fe->m_idx, sizeof(int) * 2 * B * cap) DL(r->match_dist, fe->m_dist, sizeof(float) * 2 * B * cap)
+    DL(r->match_pass, fe->m_pass, B * cap)
+    DL(r->track_pts, fe->t_pts, sizeof(float) * 2 * 4 * B * cap) DL(r->track_keep, fe->t_keep, 4 * B * cap)
+    DL(r->track_n, fe->t_n, sizeof(int) * 4 * B)
+#undef DL
+    ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZS_OK;
+}
+
+extern "C" zs_status zs_frontend_process_host(zs_frontend* fe, const uint8_t* left, const uint8_t* right, size_t pitch,
+                                              size_t stride, const zs_frontend_results* res)
+{
+    zs_status st = zs_frontend_upload(fe, left, right, pitch, stride, 1);
+    if (st != ZS_OK) return st;
+    if ((st = zs_frontend_run(fe)) != ZS_OK) return st;
+    return zs_frontend_download(fe, res);
+}

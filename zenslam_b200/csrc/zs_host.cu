@@ -1,0 +1,165 @@
+// zs_host.cu -- host-pointer mirrors of the reference's calls (single image, synchronous): what the C++
+// adapter in zenslam_cuda/ binds for drop-in use.  They stage through the context's device scratch, run the
+// same kernels as the batched path with batch 1, and copy the results back.
+#include "zs_common.cuh"
+
+static zs_status host_pyramid(zs_context* ctx, int which, int w, int h, int slots, int win_w, int win_h, int max_level,
+                              zs_pyramid** out)
+{
+    zs_pyramid* p = ctx->host_pyr[which];
+    if (p && (p->width != w || p->height != h || p->slots != slots || p->win_w != win_w || p->win_h != win_h ||
+              p->max_level != max_level)) {
+        zs_pyramid_destroy(p);
+        p = ctx->host_pyr[which] = nullptr;
+    }
+    if (!p) {
+        zs_status st = zs_pyramid_create(ctx, w, h, slots, win_w, win_h, max_level, &p);
+        if (st != ZS_OK) return st;
+        ctx->host_pyr[which] = p;
+    }
+    *out = p;
+    return ZS_OK;
+}
+
+static inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+
+extern "C" zs_status zs_calc_optical_flow_pyr_lk_host(zs_context* ctx, const uint8_t* prev_img, const uint8_t* next_img,
+                                                      int width, int height, size_t pitch, const float* prev_pts,
+                                                      float* next_pts, int n, uint8_t* status, float* err,
+                                                      const zs_lk_params* prm)
+{
+    ZS_REQUIRE(ctx && prev_img && next_img && prm, "null argument");
+    ZS_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return ZS_OK;
+    ZS_REQUIRE(prev_pts && next_pts && status && err, "null argument");
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    zs_pyramid* p;
+    zs_status st = host_pyramid(ctx, 0, width, height, 2, prm->win_w, prm->win_h, prm->max_level, &p);
+    if (st != ZS_OK) return st;
+    if ((st = zs_pyramid_upload(ctx, p, prev_img, pitch, pitch * height, 0, 1, 1)) != ZS_OK) return st;
+    if ((st = zs_pyramid_upload(ctx, p, next_img, pitch, pitch * height, 1, 1, 1)) != ZS_OK) return st;
+    if ((st = zs_pyramid_build(ctx, p, 0, 2)) != ZS_OK) return st;
+    // scratch: [slots(2) count(1)] | prev n*2 f | next n*2 f | err n f | status n
+    const size_t o_prev = 256, o_next = o_prev + al256(sizeof(float) * 2 * n), o_err = o_next + al256(sizeof(float) * 2 * n),
+                 o_st = o_err + al256(sizeof(float) * n), total = o_st + al256(n);
+    // the KLT kernel itself uses no context scratch, so one block serves the whole call
+    void* s;
+    if ((st = zs_scratch(ctx, total, &s)) != ZS_OK) return st;
+    uint8_t* base = (uint8_t*)s;
+    const int hdr[3] = { 0, 1, n };
+    ZS_CUDA(cudaMemcpyAsync(base, hdr, sizeof(hdr), cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(base + o_prev, prev_pts, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (prm->flags & ZS_LK_USE_INITIAL_FLOW)
+        ZS_CUDA(cudaMemcpyAsync(base + o_next, next_pts, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    st = zs_klt_track(ctx, p, (const int*)base, (const int*)base + 1, (const float*)(base + o_prev), (float*)(base + o_next),
+                      (const int*)base + 2, 1, n, prm, base + o_st, (float*)(base + o_err));
+    if (st != ZS_OK) return st;
+    ZS_CUDA(cudaMemcpyAsync(next_pts, base + o_next, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(status, base + o_st, n, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(err, base + o_err, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZS_OK;
+}
+
+extern "C" zs_status zs_detect_keypoints_grid_host(zs_context* ctx, const uint8_t* img, int width, int height, size_t pitch,
+                                                   int cell_w, int cell_h, int threshold, const uint8_t* occupied, float* x,
+                                                   float* y, float* response, uint8_t* desc, int* n_out)
+{
+    ZS_REQUIRE(ctx && img && x && y && response && desc && n_out, "null argument");
+    ZS_REQUIRE(cell_w > 0 && cell_h > 0, "bad cell size");
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    *n_out = 0;
+    const int gw = width / cell_w, gh = height / cell_h, cells = gw * gh;
+    if (cells == 0) return ZS_OK;
+    zs_pyramid* p;
+    zs_status st = host_pyramid(ctx, 1, width, height, 1, 16, 16, 0, &p);
+    if (st != ZS_OK) return st;
+    if ((st = zs_pyramid_upload(ctx, p, img, pitch, pitch * height, 0, 1, 1)) != ZS_OK) return st;
+    if ((st = zs_pyramid_build(ctx, p, 0, 1)) != ZS_OK) return st;      // fills the reflect padding ORB's blur reads
+    // This call's buffers come from cudaMallocAsync rather than the context scratch, because the detection
+    // kernels use that scratch themselves.
+    const size_t o_occ = 0, o_xy0 = al256(cells), o_r0 = o_xy0 + al256(sizeof(float) * 2 * cells),
+                 o_n0 = o_r0 + al256(sizeof(float) * cells), o_xy = o_n0 + 256, o_r = o_xy + al256(sizeof(float) * 2 * cells),
+                 o_n = o_r + al256(sizeof(float) * cells), o_desc = o_n + 256, total = o_desc + al256((size_t)cells * 32);
+    uint8_t* base;
+    ZS_CUDA(cudaMallocAsync((void**)&base, total, ctx->stream));
+    if (occupied) ZS_CUDA(cudaMemcpyAsync(base + o_occ, occupied, cells, cudaMemcpyHostToDevice, ctx->stream));
+    st = zs_fast_grid_detect(ctx, p, 0, 1, cell_w, cell_h, threshold, occupied ? base + o_occ : nullptr, (float*)(base + o_xy0),
+                             (float*)(base + o_r0), (int*)(base + o_n0), cells);
+    if (st == ZS_OK)
+        st = zs_orb_compute(ctx, p, 0, 1, (const float*)(base + o_xy0), (const float*)(base + o_r0), nullptr,
+                            (const int*)(base + o_n0), cells, (float*)(base + o_xy), (float*)(base + o_r), nullptr,
+                            (int*)(base + o_n), base + o_desc);
+    if (st != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+    int n = 0;
+    ZS_CUDA(cudaMemcpyAsync(&n, base + o_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n > 0) {
+        void* pin;
+        if ((st = zs_pinned(ctx, sizeof(float) * 2 * n, &pin)) != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+        ZS_CUDA(cudaMemcpyAsync(pin, base + o_xy, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        ZS_CUDA(cudaMemcpyAsync(response, base + o_r, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        ZS_CUDA(cudaMemcpyAsync(desc, base + o_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+        const float* xy = (const float*)pin;
+        for (int i = 0; i < n; ++i) { x[i] = xy[2 * i]; y[i] = xy[2 * i + 1]; }
+    }
+    ZS_CUDA(cudaFreeAsync(base, ctx->stream));
+    *n_out = n;
+    return ZS_OK;
+}
+
+extern "C" zs_status zs_match_host(zs_context* ctx, const void* q, int nq, const void* t, int nt, int dim, int norm, int mode,
+                                   double ratio, int* query_idx, int* train_idx, float* distance, int* n_out)
+{
+    ZS_REQUIRE(ctx && n_out, "null argument");
+    *n_out = 0;
+    if (nq <= 0 || nt <= 0) return ZS_OK;     // matcher.cpp:55-56,120-123: empty in, empty out
+    ZS_REQUIRE(q && t && query_idx && train_idx && distance, "null argument");
+    ZS_REQUIRE(norm == 0 || norm == 1, "norm must be 0 (Hamming) or 1 (L2)");
+    ZS_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (KNN + ratio) or 1 (BRUTE cross-check)");
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    const size_t row = norm == 0 ? 32 : sizeof(float) * (size_t)dim;
+    if (norm == 0) ZS_REQUIRE(dim == 32 || dim == 256 || dim == 0, "Hamming descriptors are 32-byte rows");
+    const size_t o_q = 256, o_t = o_q + al256(row * nq), o_idx = o_t + al256(row * nt), o_dist = o_idx + al256(sizeof(int) * 2 * nq),
+                 o_pass = o_dist + al256(sizeof(float) * 2 * nq), total = o_pass + al256(nq);
+    uint8_t* base;
+    ZS_CUDA(cudaMallocAsync((void**)&base, total, ctx->stream));
+    const int hdr[2] = { nq, nt };
+    ZS_CUDA(cudaMemcpyAsync(base, hdr, sizeof(hdr), cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(base + o_q, q, row * nq, cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(base + o_t, t, row * nt, cudaMemcpyHostToDevice, ctx->stream));
+    zs_status st;
+    const int* d_nq = (const int*)base; const int* d_nt = d_nq + 1;
+    int* d_idx = (int*)(base + o_idx); float* d_dist = (float*)(base + o_dist); uint8_t* d_pass = base + o_pass;
+    if (norm == 0) {
+        if (mode == 0) st = zs_match_hamming_knn2(ctx, base + o_q, d_nq, 0, base + o_t, d_nt, 0, 1, nq, nt, ratio, d_idx, d_dist, d_pass);
+        else st = zs_match_hamming_cross(ctx, base + o_q, d_nq, 0, base + o_t, d_nt, 0, 1, nq, nt, d_idx, d_dist);
+    } else {
+        if (mode == 0) st = zs_match_l2_knn2(ctx, (const float*)(base + o_q), d_nq, 0, (const float*)(base + o_t), d_nt, 0, 1, nq, nt, dim, ratio, d_idx, d_dist, d_pass);
+        else st = zs_match_l2_cross(ctx, (const float*)(base + o_q), d_nq, 0, (const float*)(base + o_t), d_nt, 0, 1, nq, nt, dim, d_idx, d_dist);
+    }
+    if (st != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+    void* pin;
+    const size_t hb = sizeof(int) * 2 * nq + sizeof(float) * 2 * nq + nq;
+    if ((st = zs_pinned(ctx, hb, &pin)) != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+    int* h_idx = (int*)pin; float* h_dist = (float*)(h_idx + 2 * nq); uint8_t* h_pass = (uint8_t*)(h_dist + 2 * nq);
+    const int per = mode == 0 ? 2 : 1;
+    ZS_CUDA(cudaMemcpyAsync(h_idx, d_idx, sizeof(int) * per * nq, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(h_dist, d_dist, sizeof(float) * per * nq, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mode == 0) ZS_CUDA(cudaMemcpyAsync(h_pass, d_pass, nq, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ZS_CUDA(cudaFreeAsync(base, ctx->stream));
+    int m = 0;
+    for (int i = 0; i < nq; ++i) {
+        if (mode == 0) {
+            if (!h_pass[i]) continue;
+            query_idx[m] = i; train_idx[m] = h_idx[2 * i]; distance[m] = h_dist[2 * i]; ++m;
+        } else {
+            if (h_idx[i] < 0) continue;
+            query_idx[m] = i; train_idx[m] = h_idx[i]; distance[m] = h_dist[i]; ++m;
+        }
+    }
+    *n_out = m;
+    return ZS_OK;
+}

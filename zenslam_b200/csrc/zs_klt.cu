@@ -1,0 +1,260 @@
+// zs_klt.cu -- pyramidal Lucas-Kanade: pyr_lk::calc_optical_flow_pyr_lk == cv::calcOpticalFlowPyrLK
+// (zenslam_core/include/zenslam/tracking/pyr_lk.h:15-26, zenslam_core/source/tracking/pyr_lk.cpp:25) and the
+// forward-backward gate of keypoint_tracker::track_keypoints (keypoint_tracker.cpp:129-197, 343-434).
+// Arithmetic follows SURVEY A.8: 14-bit fixed-point bilinear weights, integer template (I, Ix, Iy) and
+// mismatch sums accumulated EXACTLY in integers, one conversion to float32, float32 2x2 solve with the
+// reference's operation order (compiled with -fmad=false; every product/sum below is a separate rounding).
+//
+// One warp per feature; all pyramid levels and all Gauss-Newton iterations run inside the kernel (no
+// per-level launch).  The template patch lives in shared memory; the warp sweeps the window with its 32
+// lanes, control flow (early exits, iteration counts) is warp-uniform so divergence is across warps only.
+#include "zs_common.cuh"
+
+#define KLT_WARPS 8
+
+struct klt_args {
+    zs_pyr_view v;
+    const int* prev_slot; const int* next_slot;
+    const float2* prev_pts; float2* next_pts; const int* count;
+    const int* pts_row;      // optional: row of prev_pts / count each job reads (null: row = job)
+    int cap, win_w, win_h, max_level, max_iters, flags;
+    double eps2, min_eig;
+    uint8_t* status; float* err;
+    int fb; double fb_thr; uint8_t* keep;
+};
+
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int lo = __shfl_xor_sync(0xffffffffu, (int)(v & 0xffffffffll), o);
+        const int hi = __shfl_xor_sync(0xffffffffu, (int)(v >> 32), o);
+        v += ((long long)hi << 32) | (unsigned int)lo;
+    }
+    return v;
+}
+
+__device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01, int& w10, int& w11)
+{
+    const float na = __fsub_rn(1.f, a), nb = __fsub_rn(1.f, b);
+    w00 = __float2int_rn(__fmul_rn(__fmul_rn(na, nb), 16384.f));
+    w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, nb), 16384.f));
+    w10 = __float2int_rn(__fmul_rn(__fmul_rn(na, b), 16384.f));
+    w11 = 16384 - w00 - w01 - w10;
+}
+
+struct lk_result { float x, y; int status; float err; };
+
+// Track one point from plane set (I, dI) to J over all levels.  Warp-uniform.
+template <bool BIG>
+__device__ __forceinline__ lk_result lk_track_point(const klt_args& a, int slot_i, int slot_j, float2 prev, float2 init,
+                                                     bool use_init, short* sI, short2* sD, int lane)
+{
+    const zs_pyr_view& v = a.v;
+    const int ww = a.win_w, wh = a.win_h, npx = ww * wh;
+    const float hwx = __fmul_rn((float)(ww - 1), 0.5f), hwy = __fmul_rn((float)(wh - 1), 0.5f);
+    const float FLT_SCALE = 1.f / (float)(1 << 20);
+    lk_result r; r.status = 1; r.err = 0.f; r.x = 0.f; r.y = 0.f;
+    float outx = 0.f, outy = 0.f;
+    const int top = min(a.max_level, v.levels - 1);
+
+    for (int level = top; level >= 0; --level) {
+        const int cols = v.w[level], rows = v.h[level], pitch = v.pitch[level];
+        const size_t org = (size_t)v.pad_y * pitch + v.pad_x;
+        const uint8_t* I = v.img[level] + (size_t)slot_i * v.slot_stride[level] + org;
+        const short2* dI = v.der[level] + (size_t)slot_i * v.slot_stride[level] + org;
+        const uint8_t* J = v.img[level] + (size_t)slot_j * v.slot_stride[level] + org;
+        const float scale = 1.f / (float)(1 << level);
+        float px = __fmul_rn(prev.x, scale), py = __fmul_rn(prev.y, scale);
+        float nx, ny;
+        if (level == top) {
+            if (use_init) { nx = __fmul_rn(init.x, scale); ny = __fmul_rn(init.y, scale); }
+            else { nx = px; ny = py; }
+        } else { nx = __fmul_rn(outx, 2.f); ny = __fmul_rn(outy, 2.f); }
+        outx = nx; outy = ny;
+
+        px = __fsub_rn(px, hwx); py = __fsub_rn(py, hwy);
+        const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
+        if (ipx < -ww || ipx >= cols || ipy < -wh || ipy >= rows) {
+            if (level == 0) { r.status = 0; r.err = 0.f; }
+            continue;
+        }
+        int w00, w01, w10, w11;
+        lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
+
+        // ---- template: I, Ix, Iy over the window; A = sum of gradient products
+        long long sA11 = 0, sA12 = 0, sA22 = 0;
+        {
+            int pA11 = 0, pA12 = 0, pA22 = 0;
+            int x = lane, y = 0;
+            while (x >= ww) { x -= ww; ++y; }
+            const uint8_t* Ib = I + (ptrdiff_t)ipy * pitch + ipx;
+            const short2* dIb = dI + (ptrdiff_t)ipy * pitch + ipx;
+            for (int idx = lane; idx < npx; idx += 32) {
+                const uint8_t* s0 = Ib + y * pitch + x;
+                const short2* d0 = dIb + y * pitch + x;
+                const int ival = ((int)s0[0] * w00 + (int)s0[1] * w01 + (int)s0[pitch] * w10 + (int)s0[pitch + 1] * w11 + (1 << 8)) >> 9;
+                const short2 a00 = d0[0], a01 = d0[1], a10 = d0[pitch], a11 = d0[pitch + 1];
+                const int ixv = ((int)a00.x * w00 + (int)a01.x * w01 + (int)a10.x * w10 + (int)a11.x * w11 + (1 << 13)) >> 14;
+                const int iyv = ((int)a00.y * w00 + (int)a01.y * w01 + (int)a10.y * w10 + (int)a11.y * w11 + (1 << 13)) >> 14;
+                sI[idx] = (short)ival;
+                sD[idx] = make_short2((short)ixv, (short)iyv);
+                if (BIG) { sA11 += ixv * ixv; sA12 += ixv * iyv; sA22 += iyv * iyv; }
+                else { pA11 += ixv * ixv; pA12 += ixv * iyv; pA22 += iyv * iyv; }
+                x += 32;
+                while (x >= ww) { x -= ww; ++y; }
+            }
+            if (!BIG) { sA11 = pA11; sA12 = pA12; sA22 = pA22; }
+        }
+        sA11 = warp_sum_ll(sA11); sA12 = warp_sum_ll(sA12); sA22 = warp_sum_ll(sA22);
+        __syncwarp();
+        const float A11 = __fmul_rn(__ll2float_rn(sA11), FLT_SCALE), A12 = __fmul_rn(__ll2float_rn(sA12), FLT_SCALE),
+                    A22 = __fmul_rn(__ll2float_rn(sA22), FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dA = __fsub_rn(A11, A22);
+        const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * ww * wh));
+        if (a.flags & ZS_LK_GET_MIN_EIGENVALS) r.err = minEig;
+        if ((double)minEig < a.min_eig || D < 1.1920929e-07f) {
+            if (level == 0) r.status = 0;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+        nx = __fsub_rn(nx, hwx); ny = __fsub_rn(ny, hwy);
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < a.max_iters; ++j) {
+            const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
+            if (inx < -ww || inx >= cols || iny < -wh || iny >= rows) {
+                if (level == 0) r.status = 0;
+                break;
+            }
+            lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
+            long long sb1 = 0, sb2 = 0;
+            {
+                int pb1 = 0, pb2 = 0;
+                int x = lane, y = 0;
+                while (x >= ww) { x -= ww; ++y; }
+                const uint8_t* Jb = J + (ptrdiff_t)iny * pitch + inx;
+                for (int idx = lane; idx < npx; idx += 32) {
+                    const uint8_t* j0 = Jb + y * pitch + x;
+                    const int diff = (((int)j0[0] * w00 + (int)j0[1] * w01 + (int)j0[pitch] * w10 + (int)j0[pitch + 1] * w11 + (1 << 8)) >> 9)
+                                     - (int)sI[idx];
+                    const short2 g = sD[idx];
+                    if (BIG) { sb1 += diff * (int)g.x; sb2 += diff * (int)g.y; }
+                    else { pb1 += diff * (int)g.x; pb2 += diff * (int)g.y; }
+                    x += 32;
+                    while (x >= ww) { x -= ww; ++y; }
+                }
+                if (!BIG) { sb1 = pb1; sb2 = pb2; }
+            }
+            sb1 = warp_sum_ll(sb1); sb2 = warp_sum_ll(sb2);
+            const float b1 = __fmul_rn(__ll2float_rn(sb1), FLT_SCALE), b2 = __fmul_rn(__ll2float_rn(sb2), FLT_SCALE);
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+            nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
+            outx = __fadd_rn(nx, hwx); outy = __fadd_rn(ny, hwy);
+            if ((double)dx * (double)dx + (double)dy * (double)dy <= a.eps2) break;
+            if (j > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
+                outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f)); outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        __syncwarp();
+    }
+    r.x = outx; r.y = outy;
+    return r;
+}
+
+// grid: (ceil(cap / KLT_WARPS), jobs); dynamic smem = KLT_WARPS * per-warp template bytes
+template <bool BIG>
+__global__ void __launch_bounds__(KLT_WARPS * 32) k_klt_track(klt_args a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int job = blockIdx.y;
+    const int i = blockIdx.x * KLT_WARPS + warp;
+    const int in_row = a.pts_row ? a.pts_row[job] : job;
+    if (i >= min(a.count[in_row], a.cap)) return;
+    const int npx = a.win_w * a.win_h;
+    const size_t per_warp = (size_t)((npx + 1) & ~1) * 2 + (size_t)npx * 4;
+    short* sI = (short*)(smem + warp * per_warp);
+    short2* sD = (short2*)(smem + warp * per_warp + (size_t)((npx + 1) & ~1) * 2);
+    const size_t o = (size_t)job * a.cap + i;
+    const float2 p0 = a.prev_pts[(size_t)in_row * a.cap + i];
+    const bool use_init = (a.flags & ZS_LK_USE_INITIAL_FLOW) != 0;
+    float2 init = make_float2(0.f, 0.f);
+    if (use_init) init = a.next_pts[o];
+    const int si = a.prev_slot[job], sj = a.next_slot[job];
+    const lk_result f = lk_track_point<BIG>(a, si, sj, p0, init, use_init, sI, sD, lane);
+    if (lane == 0) {
+        a.next_pts[o] = make_float2(f.x, f.y);
+        a.status[o] = (uint8_t)f.status;
+        a.err[o] = f.err;
+    }
+    if (a.fb) {
+        // backward call (keypoint_tracker.cpp:156-170): from the forward result, no initial flow
+        const lk_result b = lk_track_point<BIG>(a, sj, si, make_float2(f.x, f.y), init, false, sI, sD, lane);
+        if (lane == 0) {
+            // cv::norm(Point2f) -> sqrt((double)dx*dx + (double)dy*dy) < klt_threshold (keypoint_tracker.cpp:180)
+            const float dx = __fsub_rn(b.x, p0.x), dy = __fsub_rn(b.y, p0.y);
+            const double nrm = sqrt((double)dx * (double)dx + (double)dy * (double)dy);
+            a.keep[o] = (uint8_t)(f.status && b.status && nrm < a.fb_thr);
+        }
+    }
+}
+
+zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_slot, const int* d_next_slot,
+                        const float* d_prev_pts, float* d_next_pts, const int* d_count, const int* d_pts_row, int jobs, int cap,
+                        const zs_lk_params* prm, uint8_t* d_status, float* d_err, int fb, double fb_thr, uint8_t* d_keep)
+{
+    ZS_REQUIRE(ctx && p && d_prev_slot && d_next_slot && d_prev_pts && d_next_pts && d_count && prm && d_status && d_err,
+               "null argument");
+    ZS_REQUIRE(jobs >= 0 && cap > 0, "bad sizes");
+    ZS_REQUIRE(prm->win_w == p->win_w && prm->win_h == p->win_h,
+               "LK window must equal the window the pyramid was padded for (reference: both are klt_window_size)");
+    ZS_REQUIRE(prm->flags & ZS_LK_GET_MIN_EIGENVALS, "only OPTFLOW_LK_GET_MIN_EIGENVALS mode is implemented (the reference's)");
+    ZS_REQUIRE(prm->max_level >= 0, "max_level < 0");
+    if (jobs == 0) return ZS_OK;
+    klt_args a;
+    a.v = p->v; a.prev_slot = d_prev_slot; a.next_slot = d_next_slot;
+    a.prev_pts = (const float2*)d_prev_pts; a.next_pts = (float2*)d_next_pts; a.count = d_count; a.pts_row = d_pts_row;
+    a.cap = cap; a.win_w = prm->win_w; a.win_h = prm->win_h; a.max_level = prm->max_level;
+    int mi = prm->max_iters; mi = mi < 0 ? 0 : mi > 100 ? 100 : mi;          // cv: clamp(maxCount, 0, 100)
+    double eps = prm->epsilon; eps = eps < 0 ? 0 : eps > 10. ? 10. : eps;   // cv: clamp(epsilon, 0, 10)
+    a.max_iters = mi; a.eps2 = eps * eps; a.flags = prm->flags; a.min_eig = prm->min_eig_threshold;
+    a.status = d_status; a.err = d_err; a.fb = fb; a.fb_thr = fb_thr; a.keep = d_keep;
+    const int npx = a.win_w * a.win_h;
+    const size_t per_warp = (size_t)((npx + 1) & ~1) * 2 + (size_t)npx * 4;
+    const size_t smem = per_warp * KLT_WARPS;
+    ZS_REQUIRE(smem <= 227 * 1024, "window too large for the shared-memory template");
+    const bool big = (npx + 31) / 32 > 60;      // int32 lane partials hold 64 pixels (|diff*Ix| < 2^25)
+    const dim3 grid(zs_div_up(cap, KLT_WARPS), jobs);
+    if (big) {
+        if (smem > 48 * 1024) ZS_CUDA(cudaFuncSetAttribute(k_klt_track<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_klt_track<true><<<grid, KLT_WARPS * 32, smem, ctx->stream>>>(a);
+    } else {
+        if (smem > 48 * 1024) ZS_CUDA(cudaFuncSetAttribute(k_klt_track<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_klt_track<false><<<grid, KLT_WARPS * 32, smem, ctx->stream>>>(a);
+    }
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}
+
+extern "C" zs_status zs_klt_track(zs_context* ctx, const zs_pyramid* p, const int* d_prev_slot, const int* d_next_slot,
+                                  const float* d_prev_pts, float* d_next_pts, const int* d_count, int jobs, int cap,
+                                  const zs_lk_params* params, uint8_t* d_status, float* d_err)
+{
+    return zs_klt_launch(ctx, p, d_prev_slot, d_next_slot, d_prev_pts, d_next_pts, d_count, nullptr, jobs, cap, params,
+                         d_status, d_err, 0, 0.0, nullptr);
+}
+
+extern "C" zs_status zs_klt_track_fb(zs_context* ctx, const zs_pyramid* p, const int* d_prev_slot, const int* d_next_slot,
+                                     const float* d_prev_pts, float* d_next_pts, const int* d_count, int jobs, int cap,
+                                     const zs_lk_params* params, double klt_threshold, uint8_t* d_status, float* d_err,
+                                     uint8_t* d_keep)
+{
+    ZS_REQUIRE(d_keep, "d_keep is null");
+    return zs_klt_launch(ctx, p, d_prev_slot, d_next_slot, d_prev_pts, d_next_pts, d_count, nullptr, jobs, cap, params,
+                         d_status, d_err, 1, klt_threshold, d_keep);
+}

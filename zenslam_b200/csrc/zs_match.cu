@@ -1,0 +1,316 @@
+// zs_match.cu -- brute-force descriptor matching: cv::BFMatcher knnMatch(k=2) + Lowe ratio, and
+// match() with crossCheck=true, Hamming norm.
+// Reference: zenslam::matcher (zenslam_core/source/matching/matcher.cpp:60-80) and utils::create_matcher
+// (zenslam_core/source/matching/matching_utils.cpp:63-95); tie rules in SURVEY A.5.
+//
+// Popcount tiles: one thread owns a query descriptor in registers (8 x u32); the block stages tiles of
+// train descriptors in shared memory and every thread sweeps the tile with broadcast 128-bit reads,
+// XOR + POPC, keeping a running top-2.  Train indices are visited in ascending order with strict '<'
+// updates, which is exactly OpenCV's stable tie rule (smaller train index wins).  Integer-ALU bound.
+#include "zs_common.cuh"
+
+#define MATCH_THREADS 128
+#define MATCH_TILE 128
+
+struct top2 { int d0, d1, i0, i1; };
+
+__device__ __forceinline__ void top2_update(top2& t, int d, int j)
+{
+    if (d < t.d0) { t.d1 = t.d0; t.i1 = t.i0; t.d0 = d; t.i0 = j; }
+    else if (d < t.d1) { t.d1 = d; t.i1 = j; }
+}
+
+// grid: (ceil(cap_q / 128), pairs)
+__global__ void __launch_bounds__(MATCH_THREADS) k_hamming_top2(
+    const uint8_t* __restrict__ q, const int* __restrict__ nq, size_t q_stride,
+    const uint8_t* __restrict__ t, const int* __restrict__ nt, size_t t_stride,
+    int* __restrict__ o_idx, int* __restrict__ o_dist, int out_stride /* ints per pair */)
+{
+    __shared__ uint4 tile[MATCH_TILE * 2];
+    const int pair = blockIdx.y;
+    const int n_q = nq[pair], n_t = nt[pair];
+    const int qi = blockIdx.x * MATCH_THREADS + threadIdx.x;
+    if (blockIdx.x * MATCH_THREADS >= n_q) return;
+    const uint4* qp = (const uint4*)(q + (size_t)pair * q_stride);
+    const uint4* tp = (const uint4*)(t + (size_t)pair * t_stride);
+    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+    if (qi < n_q) { qa = qp[2 * qi]; qb = qp[2 * qi + 1]; }
+    top2 best = { 0x7fffffff, 0x7fffffff, -1, -1 };
+    for (int base = 0; base < n_t; base += MATCH_TILE) {
+        const int m = min(MATCH_TILE, n_t - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * m; i += MATCH_THREADS) tile[i] = tp[2 * base + i];
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < m; ++j) {
+            const uint4 a = tile[2 * j], b = tile[2 * j + 1];
+            const int d = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) +
+                          __popc(qb.x ^ b.x) + __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
+            top2_update(best, d, base + j);
+        }
+    }
+    if (qi < n_q) {
+        int* oi = o_idx + (size_t)pair * out_stride + 2 * qi;
+        int* od = o_dist + (size_t)pair * out_stride + 2 * qi;
+        oi[0] = best.i0; oi[1] = best.i1; od[0] = best.d0; od[1] = best.d1;
+    }
+}
+
+// knn2 epilogue: int distances -> float, ratio gate of matcher.cpp:70
+__global__ void k_knn2_finish(const int* __restrict__ idx_in, const int* __restrict__ dist_in, const int* __restrict__ nq,
+                              int cap_q, double ratio, int l2, int* __restrict__ idx, float* __restrict__ dist,
+                              uint8_t* __restrict__ pass)
+{
+    const int pair = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap_q) return;
+    const size_t o = (size_t)pair * cap_q + i;
+    if (i >= nq[pair]) {
+        idx[2 * o] = idx[2 * o + 1] = -1; dist[2 * o] = dist[2 * o + 1] = 0.f;
+        if (pass) pass[o] = 0;
+        return;
+    }
+    const int i0 = idx_in[2 * o], i1 = idx_in[2 * o + 1];
+    float d0 = 0.f, d1 = 0.f;
+    if (i0 >= 0) d0 = l2 ? sqrtf((float)dist_in[2 * o]) : (float)dist_in[2 * o];
+    if (i1 >= 0) d1 = l2 ? sqrtf((float)dist_in[2 * o + 1]) : (float)dist_in[2 * o + 1];
+    idx[2 * o] = i0; idx[2 * o + 1] = i1; dist[2 * o] = d0; dist[2 * o + 1] = d1;
+    if (pass) pass[o] = (i0 >= 0 && i1 >= 0 && (double)d0 < ratio * (double)d1) ? 1 : 0;
+}
+
+// cross-check epilogue: keep (i, fwd[i]) iff bwd[fwd[i]] == i
+__global__ void k_cross_finish(const int* __restrict__ fwd_idx, const int* __restrict__ fwd_dist,
+                               const int* __restrict__ bwd_idx, const int* __restrict__ nq, int cap_q, int cap_t, int l2,
+                               int* __restrict__ idx, float* __restrict__ dist)
+{
+    const int pair = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap_q) return;
+    const size_t o = (size_t)pair * cap_q + i;
+    int out = -1; float d = 0.f;
+    if (i < nq[pair]) {
+        const int f = fwd_idx[2 * o];
+        if (f >= 0 && bwd_idx[2 * ((size_t)pair * cap_t + f)] == i) {
+            out = f;
+            d = l2 ? sqrtf((float)fwd_dist[2 * o]) : (float)fwd_dist[2 * o];
+        }
+    }
+    idx[o] = out; dist[o] = d;
+}
+
+// L2 top-2 on integer-valued descriptors stored as u8 (dim bytes per row, dim % 4 == 0, dim <= 128).
+// d2 = sum (a-b)^2 computed exactly in int32 with dp4a: |a|^2 + |b|^2 - 2 a.b.
+// (CUDA-core form; the tcgen05 kernel in zs_match_l2.cu is the production path for large problems.)
+template <int NW>
+__global__ void __launch_bounds__(MATCH_THREADS) k_l2u8_top2(
+    const uint8_t* __restrict__ q, const int* __restrict__ nq, size_t q_stride,
+    const uint8_t* __restrict__ t, const int* __restrict__ nt, size_t t_stride,
+    int* __restrict__ o_idx, int* __restrict__ o_dist, int out_stride)
+{
+    constexpr int TILE = 32;
+    __shared__ uint32_t tile[TILE * NW];
+    __shared__ int tnorm[TILE];
+    const int pair = blockIdx.y;
+    const int n_q = nq[pair], n_t = nt[pair];
+    const int qi = blockIdx.x * MATCH_THREADS + threadIdx.x;
+    if (blockIdx.x * MATCH_THREADS >= n_q) return;
+    const uint32_t* qp = (const uint32_t*)(q + (size_t)pair * q_stride);
+    const uint32_t* tp = (const uint32_t*)(t + (size_t)pair * t_stride);
+    uint32_t qr[NW];
+    int qn = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { qr[w] = (qi < n_q) ? qp[(size_t)qi * NW + w] : 0u; qn = (int)__dp4a(qr[w], qr[w], (unsigned)qn); }
+    top2 best = { 0x7fffffff, 0x7fffffff, -1, -1 };
+    for (int base = 0; base < n_t; base += TILE) {
+        const int m = min(TILE, n_t - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < m * NW; i += MATCH_THREADS) tile[i] = tp[(size_t)base * NW + i];
+        __syncthreads();
+        if (threadIdx.x < m) {
+            int s = 0;
+            for (int w = 0; w < NW; ++w) { const uint32_t v = tile[threadIdx.x * NW + w]; s = (int)__dp4a(v, v, (unsigned)s); }
+            tnorm[threadIdx.x] = s;
+        }
+        __syncthreads();
+        for (int j = 0; j < m; ++j) {
+            int dot = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) dot = (int)__dp4a(qr[w], tile[j * NW + w], (unsigned)dot);
+            top2_update(best, qn + tnorm[j] - 2 * dot, base + j);
+        }
+    }
+    if (qi < n_q) {
+        int* oi = o_idx + (size_t)pair * out_stride + 2 * qi;
+        int* od = o_dist + (size_t)pair * out_stride + 2 * qi;
+        oi[0] = best.i0; oi[1] = best.i1; od[0] = best.d0; od[1] = best.d1;
+    }
+}
+
+// float (integer-valued, 0..255) -> u8, flagging anything else
+__global__ void k_f32_to_u8(const float* __restrict__ src, const int* __restrict__ n, size_t src_stride, int cap, int dim,
+                            uint8_t* __restrict__ dst, int* __restrict__ bad)
+{
+    const int pair = blockIdx.y;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)min(n[pair], cap) * dim) return;
+    const float v = src[(size_t)pair * src_stride + i];
+    const int r = __float2int_rn(v);
+    if ((float)r != v || r < 0 || r > 255) atomicExch(bad, 1);
+    dst[(size_t)pair * cap * dim + i] = (uint8_t)r;
+}
+
+static zs_status hamming_top2(zs_context* ctx, const uint8_t* q, const int* nq, size_t qs, const uint8_t* t, const int* nt,
+                              size_t ts, int pairs, int cap_q, int* idx, int* dist)
+{
+    k_hamming_top2<<<dim3(zs_div_up(cap_q, MATCH_THREADS), pairs), MATCH_THREADS, 0, ctx->stream>>>(
+        q, nq, qs, t, nt, ts, idx, dist, 2 * cap_q);
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}
+
+extern "C" zs_status zs_match_hamming_knn2(zs_context* ctx, const uint8_t* d_q, const int* d_nq, size_t q_stride,
+                                           const uint8_t* d_t, const int* d_nt, size_t t_stride, int pairs, int cap_q,
+                                           int cap_t, double ratio, int* d_idx, float* d_dist, uint8_t* d_pass)
+{
+    ZS_REQUIRE(ctx && d_q && d_nq && d_t && d_nt && d_idx && d_dist, "null argument");
+    ZS_REQUIRE(pairs >= 0 && cap_q > 0 && cap_t > 0, "bad sizes");
+    ZS_REQUIRE(((uintptr_t)d_q % 16) == 0 && ((uintptr_t)d_t % 16) == 0 && q_stride % 16 == 0 && t_stride % 16 == 0,
+               "descriptor arrays must be 16-byte aligned");
+    if (pairs == 0) return ZS_OK;
+    void* s;
+    zs_status st = zs_scratch(ctx, sizeof(int) * 4 * (size_t)cap_q * pairs, &s);
+    if (st != ZS_OK) return st;
+    int* ti = (int*)s; int* td = ti + 2 * (size_t)cap_q * pairs;
+    st = hamming_top2(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, ti, td);
+    if (st != ZS_OK) return st;
+    k_knn2_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(ti, td, d_nq, cap_q, ratio, 0, d_idx, d_dist, d_pass);
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}
+
+extern "C" zs_status zs_match_hamming_cross(zs_context* ctx, const uint8_t* d_q, const int* d_nq, size_t q_stride,
+                                            const uint8_t* d_t, const int* d_nt, size_t t_stride, int pairs, int cap_q,
+                                            int cap_t, int* d_idx, float* d_dist)
+{
+    ZS_REQUIRE(ctx && d_q && d_nq && d_t && d_nt && d_idx && d_dist, "null argument");
+    ZS_REQUIRE(pairs >= 0 && cap_q > 0 && cap_t > 0, "bad sizes");
+    ZS_REQUIRE(((uintptr_t)d_q % 16) == 0 && ((uintptr_t)d_t % 16) == 0 && q_stride % 16 == 0 && t_stride % 16 == 0,
+               "descriptor arrays must be 16-byte aligned");
+    if (pairs == 0) return ZS_OK;
+    void* s;
+    zs_status st = zs_scratch(ctx, sizeof(int) * 4 * ((size_t)cap_q + cap_t) * pairs, &s);
+    if (st != ZS_OK) return st;
+    int* fi = (int*)s; int* fd = fi + 2 * (size_t)cap_q * pairs;
+    int* bi = fd + 2 * (size_t)cap_q * pairs; int* bd = bi + 2 * (size_t)cap_t * pairs;
+    st = hamming_top2(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, fi, fd);
+    if (st != ZS_OK) return st;
+    st = hamming_top2(ctx, d_t, d_nt, t_stride, d_q, d_nq, q_stride, pairs, cap_t, bi, bd);
+    if (st != ZS_OK) return st;
+    k_cross_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(fi, fd, bi, d_nq, cap_q, cap_t, 0, d_idx, d_dist);
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}
+
+// ---- L2 (integer-valued float descriptors) -----------------------------------------------------------
+zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, const uint8_t* t8, const int* nt, int pairs,
+                            int cap_q, int cap_t, int dim, int* idx, int* dist);   // zs_match_l2.cu
+
+static zs_status l2_prepare(zs_context* ctx, const float* d_q, const int* d_nq, size_t q_stride, const float* d_t,
+                            const int* d_nt, size_t t_stride, int pairs, int cap_q, int cap_t, int dim, size_t extra_ints,
+                            uint8_t** q8, uint8_t** t8, int** extra)
+{
+    ZS_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 128, "dim must be a multiple of 4, at most 128");
+    const size_t qb = ((size_t)pairs * cap_q * dim + 255) / 256 * 256, tb = ((size_t)pairs * cap_t * dim + 255) / 256 * 256;
+    void* s;
+    zs_status st = zs_scratch(ctx, qb + tb + 256 + extra_ints * sizeof(int), &s);
+    if (st != ZS_OK) return st;
+    *q8 = (uint8_t*)s; *t8 = *q8 + qb;
+    int* bad = (int*)(*t8 + tb);
+    *extra = bad + 64;
+    ZS_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+    k_f32_to_u8<<<dim3(zs_div_up(cap_q * dim, 256), pairs), 256, 0, ctx->stream>>>(d_q, d_nq, q_stride, cap_q, dim, *q8, bad);
+    ZS_LAUNCH_CHECK(ctx);
+    k_f32_to_u8<<<dim3(zs_div_up(cap_t * dim, 256), pairs), 256, 0, ctx->stream>>>(d_t, d_nt, t_stride, cap_t, dim, *t8, bad);
+    ZS_LAUNCH_CHECK(ctx);
+    int h_bad = 0;
+    ZS_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h_bad) {
+        zs_set_error("L2 matching is exact only for integer-valued descriptors in 0..255 (cv::SIFT); got other values");
+        return ZS_ERR_UNSUPPORTED;
+    }
+    return ZS_OK;
+}
+
+static zs_status l2_top2(zs_context* ctx, const uint8_t* q8, const int* nq, const uint8_t* t8, const int* nt, int pairs,
+                         int cap_q, int cap_t, int dim, int* idx, int* dist)
+{
+    if (dim == 128) return zs_l2_tensor_top2(ctx, q8, nq, t8, nt, pairs, cap_q, cap_t, dim, idx, dist);
+    const dim3 grid(zs_div_up(cap_q, MATCH_THREADS), pairs);
+#define L2_CASE(NW)                                                                                          \
+    case NW:                                                                                                 \
+        k_l2u8_top2<NW><<<grid, MATCH_THREADS, 0, ctx->stream>>>(q8, nq, (size_t)cap_q * dim, t8, nt,         \
+                                                                 (size_t)cap_t * dim, idx, dist, 2 * cap_q); \
+        break;
+    switch (dim / 4) {
+        L2_CASE(1) L2_CASE(2) L2_CASE(4) L2_CASE(8) L2_CASE(16) L2_CASE(32)
+    default:
+        zs_set_error("L2 descriptor dim %d not supported (4, 8, 16, 32, 64, 128)", dim);
+        return ZS_ERR_UNSUPPORTED;
+    }
+#undef L2_CASE
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}
+
+// CUDA-core L2 top-2, exported for tests that cross-check the tensor-core kernel
+zs_status zs_l2_cuda_core_top2(zs_context* ctx, const uint8_t* q8, const int* nq, const uint8_t* t8, const int* nt, int pairs,
+                               int cap_q, int cap_t, int dim, int* idx, int* dist)
+{
+    ZS_REQUIRE(dim == 128, "dim");
+    k_l2u8_top2<32><<<dim3(zs_div_up(cap_q, MATCH_THREADS), pairs), MATCH_THREADS, 0, ctx->stream>>>(
+        q8, nq, (size_t)cap_q * dim, t8, nt, (size_t)cap_t * dim, idx, dist, 2 * cap_q);
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}
+
+extern "C" zs_status zs_match_l2_knn2(zs_context* ctx, const float* d_q, const int* d_nq, size_t q_stride, const float* d_t,
+                                      const int* d_nt, size_t t_stride, int pairs, int cap_q, int cap_t, int dim,
+                                      double ratio, int* d_idx, float* d_dist, uint8_t* d_pass)
+{
+    ZS_REQUIRE(ctx && d_q && d_nq && d_t && d_nt && d_idx && d_dist, "null argument");
+    ZS_REQUIRE(pairs >= 0 && cap_q > 0 && cap_t > 0, "bad sizes");
+    if (pairs == 0) return ZS_OK;
+    uint8_t *q8, *t8; int* ex;
+    zs_status st = l2_prepare(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, cap_t, dim,
+                              4 * (size_t)cap_q * pairs, &q8, &t8, &ex);
+    if (st != ZS_OK) return st;
+    int* ti = ex; int* td = ti + 2 * (size_t)cap_q * pairs;
+    st = l2_top2(ctx, q8, d_nq, t8, d_nt, pairs, cap_q, cap_t, dim, ti, td);
+    if (st != ZS_OK) return st;
+    k_knn2_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(ti, td, d_nq, cap_q, ratio, 1, d_idx, d_dist, d_pass);
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}
+
+extern "C" zs_status zs_match_l2_cross(zs_context* ctx, const float* d_q, const int* d_nq, size_t q_stride, const float* d_t,
+                                       const int* d_nt, size_t t_stride, int pairs, int cap_q, int cap_t, int dim,
+                                       int* d_idx, float* d_dist)
+{
+    ZS_REQUIRE(ctx && d_q && d_nq && d_t && d_nt && d_idx && d_dist, "null argument");
+    ZS_REQUIRE(pairs >= 0 && cap_q > 0 && cap_t > 0, "bad sizes");
+    if (pairs == 0) return ZS_OK;
+    uint8_t *q8, *t8; int* ex;
+    zs_status st = l2_prepare(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, cap_t, dim,
+                              4 * ((size_t)cap_q + cap_t) * pairs, &q8, &t8, &ex);
+    if (st != ZS_OK) return st;
+    int* fi = ex; int* fd = fi + 2 * (size_t)cap_q * pairs;
+    int* bi = fd + 2 * (size_t)cap_q * pairs; int* bd = bi + 2 * (size_t)cap_t * pairs;
+    st = l2_top2(ctx, q8, d_nq, t8, d_nt, pairs, cap_q, cap_t, dim, fi, fd);
+    if (st != ZS_OK) return st;
+    st = l2_top2(ctx, t8, d_nt, q8, d_nq, pairs, cap_t, cap_q, dim, bi, bd);
+    if (st != ZS_OK) return st;
+    k_cross_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(fi, fd, bi, d_nq, cap_q, cap_t, 1, d_idx, d_dist);
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}

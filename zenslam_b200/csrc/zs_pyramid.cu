@@ -1,0 +1,147 @@
+// zs_pyramid.cu -- cv::buildOpticalFlowPyramid(img, pyr, win, maxLevel, withDerivatives=true) on the device
+// (reference: utils::pyramid, zenslam_core/source/utils/utils_opencv.cpp:525-530).
+//
+// Per level: (1) fill the REFLECT_101 padding of the image plane, (2) pyrDown into the next level's
+// interior, (3) Scharr (dx,dy) into the derivative plane interior (its padding stays zero).
+// All three are streaming u8 stencils: 4 pixels per thread, 32-bit loads from the padded plane so no
+// kernel needs border logic of its own.  HBM-bound; algorithmic bytes per image = sum over levels of
+// (read w*h) + (write w*h image + 4*w*h derivative).
+#include "zs_common.cuh"
+
+// ---- (1) reflect padding ---------------------------------------------------------------------------
+// grid: (1, padded rows, count); 128 threads stride over the columns that need filling.
+__global__ void __launch_bounds__(128) k_pad_reflect(zs_pyr_view v, int level, int first)
+{
+    const int w = v.w[level], h = v.h[level], pitch = v.pitch[level];
+    const int slot = zs_slot(first, blockIdx.z, v.slots);
+    uint8_t* plane = v.img[level] + (size_t)slot * v.slot_stride[level];
+    const int r = blockIdx.y;                         // padded row
+    const int sy = zs_reflect101(r - v.pad_y, h);
+    const uint8_t* src = plane + (size_t)(sy + v.pad_y) * pitch + v.pad_x;   // interior row sy
+    uint8_t* dst = plane + (size_t)r * pitch;
+    const bool interior_row = (r >= v.pad_y && r < v.pad_y + h);
+    const int PW = w + 2 * v.pad_x;
+    if (interior_row) {
+        // only the left and right pads
+        for (int c = threadIdx.x; c < 2 * v.pad_x; c += blockDim.x) {
+            const int px = c < v.pad_x ? c : (w + c);           // padded column
+            dst[px] = src[zs_reflect101(px - v.pad_x, w)];
+        }
+    } else {
+        for (int px = threadIdx.x; px < PW; px += blockDim.x)
+            dst[px] = src[zs_reflect101(px - v.pad_x, w)];
+    }
+}
+
+// ---- (2) pyrDown -------------------------------------------------------------------------------------
+// dst(x,y) = (sum_{i,j} k_i k_j src(2x+i-2, 2y+j-2) + 128) >> 8, k = [1 4 6 4 1]; src is the padded plane.
+__device__ __forceinline__ void pd_row(const uint8_t* __restrict__ row, int h4[4])
+{
+    // row points at source column 2*x0 (multiple of 8 => 4-byte aligned loads at -4, 0, 4, 8)
+    const uint32_t w0 = *(const uint32_t*)(row - 4), w1 = *(const uint32_t*)(row);
+    const uint32_t w2 = *(const uint32_t*)(row + 4), w3 = *(const uint32_t*)(row + 8);
+    int s[11];                                   // source columns 2*x0-2 .. 2*x0+8
+    s[0] = (w0 >> 16) & 255; s[1] = w0 >> 24;
+    s[2] = w1 & 255; s[3] = (w1 >> 8) & 255; s[4] = (w1 >> 16) & 255; s[5] = w1 >> 24;
+    s[6] = w2 & 255; s[7] = (w2 >> 8) & 255; s[8] = (w2 >> 16) & 255; s[9] = w2 >> 24;
+    s[10] = w3 & 255;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        h4[k] = s[2 * k] + s[2 * k + 4] + 4 * (s[2 * k + 1] + s[2 * k + 3]) + 6 * s[2 * k + 2];
+}
+
+__global__ void __launch_bounds__(256) k_pyr_down(zs_pyr_view v, int level, int first)
+{
+    const int dw = v.w[level + 1], dh = v.h[level + 1];
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x0 >= dw) return;
+    const int slot = zs_slot(first, blockIdx.z, v.slots);
+    const int sp = v.pitch[level];
+    const uint8_t* src = v.img[level] + (size_t)slot * v.slot_stride[level] + (size_t)v.pad_y * sp + v.pad_x;
+    const uint8_t* r = src + (ptrdiff_t)(2 * y - 2) * sp + 2 * x0;
+    int acc[4] = { 0, 0, 0, 0 }, t[4];
+    pd_row(r, t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = t[k];
+    pd_row(r + sp, t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] += 4 * t[k];
+    pd_row(r + 2 * sp, t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] += 6 * t[k];
+    pd_row(r + 3 * sp, t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] += 4 * t[k];
+    pd_row(r + 4 * sp, t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = (acc[k] + t[k] + 128) >> 8;
+    const int dp = v.pitch[level + 1];
+    uint8_t* dst = v.img[level + 1] + (size_t)slot * v.slot_stride[level + 1] + (size_t)(v.pad_y + y) * dp + v.pad_x + x0;
+    if (x0 + 4 <= dw) {
+        *(uint32_t*)dst = (uint32_t)acc[0] | ((uint32_t)acc[1] << 8) | ((uint32_t)acc[2] << 16) | ((uint32_t)acc[3] << 24);
+    } else {
+        for (int k = 0; x0 + k < dw; ++k) dst[k] = (uint8_t)acc[k];
+    }
+    (void)dh;
+}
+
+// ---- (3) Scharr ---------------------------------------------------------------------------------------
+// dx = 3*(r0[x+1]-r0[x-1]) + 10*(r1[x+1]-r1[x-1]) + 3*(r2[x+1]-r2[x-1])
+// dy = 3*(r2[x-1]-r0[x-1]) + 10*(r2[x]-r0[x]) + 3*(r2[x+1]-r0[x+1]);  REFLECT_101 comes from the padding.
+__device__ __forceinline__ void sc_row(const uint8_t* __restrict__ row, int s[6])
+{
+    // row points at column x0 (multiple of 4): columns x0-1 .. x0+4
+    const uint32_t w0 = *(const uint32_t*)(row - 4), w1 = *(const uint32_t*)(row), w2 = *(const uint32_t*)(row + 4);
+    s[0] = w0 >> 24;
+    s[1] = w1 & 255; s[2] = (w1 >> 8) & 255; s[3] = (w1 >> 16) & 255; s[4] = w1 >> 24;
+    s[5] = w2 & 255;
+}
+
+__global__ void __launch_bounds__(256) k_scharr(zs_pyr_view v, int level, int first)
+{
+    const int w = v.w[level];
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x0 >= w) return;
+    const int slot = zs_slot(first, blockIdx.z, v.slots);
+    const int pitch = v.pitch[level];
+    const size_t org = (size_t)slot * v.slot_stride[level] + (size_t)(v.pad_y + y) * pitch + v.pad_x + x0;
+    const uint8_t* r1 = v.img[level] + org;
+    int a[6], b[6], c[6];
+    sc_row(r1 - pitch, a); sc_row(r1, b); sc_row(r1 + pitch, c);
+    short2 out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int dx = 3 * (a[k + 2] - a[k]) + 10 * (b[k + 2] - b[k]) + 3 * (c[k + 2] - c[k]);
+        const int dy = 3 * (c[k] - a[k]) + 10 * (c[k + 1] - a[k + 1]) + 3 * (c[k + 2] - a[k + 2]);
+        out[k] = make_short2((short)dx, (short)dy);
+    }
+    short2* dst = v.der[level] + org;
+    if (x0 + 4 <= w) {
+        *(uint4*)dst = *(const uint4*)out;          // 16-byte aligned: pad_x, pitch and x0 are multiples of 4
+    } else {
+        for (int k = 0; x0 + k < w; ++k) dst[k] = out[k];
+    }
+}
+
+extern "C" zs_status zs_pyramid_build(zs_context* ctx, zs_pyramid* p, int first, int count)
+{
+    ZS_REQUIRE(ctx && p, "null argument");
+    ZS_REQUIRE(count >= 0 && count <= p->slots && first >= 0, "bad slot range");
+    if (count == 0) return ZS_OK;
+    const zs_pyr_view& v = p->v;
+    for (int l = 0; l < v.levels; ++l) {
+        const int w = v.w[l], h = v.h[l];
+        k_pad_reflect<<<dim3(1, h + 2 * v.pad_y, count), 128, 0, ctx->stream>>>(v, l, first);
+        ZS_LAUNCH_CHECK(ctx);
+        if (l + 1 < v.levels) {
+            const int dw = v.w[l + 1], dh = v.h[l + 1];
+            k_pyr_down<<<dim3(zs_div_up(zs_div_up(dw, 4), 256), dh, count), 256, 0, ctx->stream>>>(v, l, first);
+            ZS_LAUNCH_CHECK(ctx);
+        }
+        k_scharr<<<dim3(zs_div_up(zs_div_up(w, 4), 256), h, count), 256, 0, ctx->stream>>>(v, l, first);
+        ZS_LAUNCH_CHECK(ctx);
+    }
+    return ZS_OK;
+}

@@ -1,0 +1,66 @@
+"""zenslam::matcher mirror (zenslam_core/include/zenslam/matching/matcher.h:14-38,
+zenslam_core/source/matching/matcher.cpp:11-217, utils::create_matcher matching_utils.cpp:63-95).
+
+BRUTE = 1-NN with cross-check, KNN = 2-NN + Lowe ratio; Hamming for binary descriptors, L2 otherwise.
+The FLANN mode (approximate LSH / KD-tree) and the findFundamentalMat RANSAC gate (matcher.cpp:83-103)
+are CPU algorithms outside the hot path: FLANN raises, the gate is an optional callable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib
+from .options import slam_options
+from .runtime import Context
+from .types import DMatch
+
+
+class matcher:
+    def __init__(self, opts: slam_options, is_binary: bool, ctx: Context, epipolar_gate=None):
+        if opts.matcher == "FLANN":
+            raise NotImplementedError("matcher: FLANN (approximate) mode is not part of the CUDA backend")
+        self._options, self._is_binary, self._ctx, self._gate = opts, is_binary, ctx, epipolar_gate
+
+    # -- descriptor stage ------------------------------------------------------------------------
+    def _match_rows(self, d0: np.ndarray, d1: np.ndarray):
+        nq, nt = len(d0), len(d1)
+        if nq == 0 or nt == 0:
+            return []
+        if self._is_binary:
+            q = np.ascontiguousarray(d0, np.uint8); t = np.ascontiguousarray(d1, np.uint8)
+            dim, norm = 32, 0
+        else:
+            q = np.ascontiguousarray(d0, np.float32); t = np.ascontiguousarray(d1, np.float32)
+            dim, norm = q.shape[1], 1
+        mode = 0 if self._options.matcher == "KNN" else 1
+        qi = np.empty(nq, np.int32); ti = np.empty(nq, np.int32); dist = np.empty(nq, np.float32)
+        n = C.c_int(0)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(lib().zs_match_host(self._ctx._h, p(q), nq, p(t), nt, dim, norm, mode, float(self._options.matcher_ratio),
+                                  p(qi), p(ti), p(dist), C.byref(n)))
+        return [(int(qi[i]), int(ti[i]), float(dist[i])) for i in range(n.value)]
+
+    def _finish(self, rows, un_l, un_r):
+        if self._gate is not None and len(rows) >= 8:        # matcher.cpp:83-103 (caller-supplied, CPU)
+            rows = self._gate(rows, un_l, un_r)
+        # matcher.cpp:105-111: re-key to keypoint indices
+        return [DMatch(un_l[q].index, un_r[t].index, d) for q, t, d in rows]
+
+    # -- the two reference overloads -----------------------------------------------------------------
+    def match_keypoints(self, keypoints_0, keypoints_1) -> list:
+        if isinstance(keypoints_0, dict):
+            # map overload (matcher.cpp:13-114): ascending index order, skip indices present in the other set
+            un_l = [kp for idx, kp in sorted(keypoints_0.items()) if kp.index not in keypoints_1]
+            un_r = [kp for idx, kp in sorted(keypoints_1.items()) if kp.index not in keypoints_0]
+        else:
+            # vector overload (matcher.cpp:116-217): all keypoints with non-empty descriptors
+            if not keypoints_0 or not keypoints_1:
+                return []
+            un_l = [kp for kp in keypoints_0 if kp.descriptor is not None and len(kp.descriptor)]
+            un_r = [kp for kp in keypoints_1 if kp.descriptor is not None and len(kp.descriptor)]
+        if not un_l or not un_r:
+            return []
+        d0 = np.stack([kp.descriptor for kp in un_l]); d1 = np.stack([kp.descriptor for kp in un_r])
+        return self._finish(self._match_rows(d0, d1), un_l, un_r)

@@ -1,0 +1,91 @@
+"""pyr_lk plug-in mirror (zenslam_core/include/zenslam/tracking/pyr_lk.h:10-29) and the KLT glue of
+keypoint_tracker::track_keypoints (zenslam_core/source/tracking/keypoint_tracker.cpp:129-197, 343-434).
+
+`create_cuda_pyr_lk()` is the sibling of `metal::create_metal_pyr_lk()`
+(zenslam_metal/source/pyr_lk_factory.cpp:41-49): it returns None when the backend is unavailable so the
+caller can fall back to its own CPU implementation; the CUDA backend itself never falls back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+
+import numpy as np
+
+from ._lib import LK_GET_MIN_EIGENVALS, LK_USE_INITIAL_FLOW, LkParams, check, lib
+from .options import tracking_options
+from .runtime import Context, is_available
+
+
+class pyr_lk:
+    """Abstract KLT backend: same argument list as the reference's virtual (pyr_lk.h:15-26)."""
+
+    def calc_optical_flow_pyr_lk(self, prev_pyramid, next_pyramid, prev_points, next_points, win_size, max_level,
+                                 criteria, flags, min_eig_threshold=1e-4):
+        """-> (next_points (n,2) f32, status (n,) u8, err (n,) f32)"""
+        raise NotImplementedError
+
+
+def _level0(pyramid) -> np.ndarray:
+    # the reference passes cv::buildOpticalFlowPyramid output [img0, deriv0, img1, ...]; level 0 determines the rest
+    img = pyramid[0] if isinstance(pyramid, (list, tuple)) else pyramid
+    return np.ascontiguousarray(img, np.uint8)
+
+
+class cuda_pyr_lk(pyr_lk):
+    def __init__(self, ctx: Context):
+        self._ctx = ctx
+
+    def calc_optical_flow_pyr_lk(self, prev_pyramid, next_pyramid, prev_points, next_points, win_size, max_level,
+                                 criteria=(99, 0.001), flags=LK_GET_MIN_EIGENVALS, min_eig_threshold=1e-4):
+        prev, nxt = _level0(prev_pyramid), _level0(next_pyramid)
+        assert prev.shape == nxt.shape
+        h, w = prev.shape
+        pp = np.ascontiguousarray(prev_points, np.float32).reshape(-1, 2)
+        n = len(pp)
+        if flags & LK_USE_INITIAL_FLOW:
+            npts = np.ascontiguousarray(next_points, np.float32).reshape(-1, 2).copy()
+            assert len(npts) == n
+        else:
+            npts = np.zeros((n, 2), np.float32)
+        status = np.zeros(n, np.uint8); err = np.zeros(n, np.float32)
+        prm = LkParams(win_size[0], win_size[1], int(max_level), int(criteria[0]), float(criteria[1]), int(flags),
+                       float(min_eig_threshold))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(lib().zs_calc_optical_flow_pyr_lk_host(self._ctx._h, p(prev), p(nxt), w, h, w, p(pp), p(npts), n, p(status),
+                                                     p(err), C.byref(prm)))
+        return npts, status, err
+
+
+def create_cuda_pyr_lk(ctx: Context | None = None):
+    """Factory; None when no sm_100 device is usable (cf. pyr_lk_factory.cpp:43-46)."""
+    if not is_available():
+        return None
+    return cuda_pyr_lk(ctx if ctx is not None else Context())
+
+
+def track_keypoints(backend: pyr_lk, pyramid_0, pyramid_1, keypoints_0: list, tracking: tracking_options,
+                    predicted_points=None) -> list:
+    """keypoint_tracker::track_keypoints: forward LK (initial flow from `predicted_points` when given --
+    the temporal overload, keypoint_tracker.cpp:361-391), backward LK, keep i iff both statuses are set and
+    ||p0_back - p0|| < klt_threshold; survivors copy the keypoint with pt replaced (keypoint_tracker.cpp:188-196)."""
+    if not keypoints_0:
+        return []
+    p0 = np.array([kp.pt for kp in keypoints_0], np.float32)
+    crit = (99, 0.001)
+    if predicted_points is not None:
+        p1, st, _ = backend.calc_optical_flow_pyr_lk(pyramid_0, pyramid_1, p0, predicted_points, tracking.klt_window_size,
+                                                     tracking.klt_max_level, crit,
+                                                     LK_GET_MIN_EIGENVALS | LK_USE_INITIAL_FLOW)
+    else:
+        p1, st, _ = backend.calc_optical_flow_pyr_lk(pyramid_0, pyramid_1, p0, None, tracking.klt_window_size,
+                                                     tracking.klt_max_level, crit, LK_GET_MIN_EIGENVALS)
+    pb, sb, _ = backend.calc_optical_flow_pyr_lk(pyramid_1, pyramid_0, p1, None, tracking.klt_window_size,
+                                                 tracking.klt_max_level, crit, LK_GET_MIN_EIGENVALS)
+    out = []
+    for i, kp in enumerate(keypoints_0):
+        dx, dy = np.float32(pb[i, 0] - p0[i, 0]), np.float32(pb[i, 1] - p0[i, 1])
+        nrm = float(np.sqrt(np.float64(dx) * np.float64(dx) + np.float64(dy) * np.float64(dy)))
+        if st[i] and sb[i] and nrm < tracking.klt_threshold:
+            out.append(dataclasses.replace(kp, pt=(float(p1[i, 0]), float(p1[i, 1]))))
+    return out
