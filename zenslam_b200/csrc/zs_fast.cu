@@ -42,24 +42,26 @@ __device__ __forceinline__ bool fast_is_corner(const uint8_t* tile, int tp, int 
     return has_run9(dark) || has_run9(bright);
 }
 
-// s = max over 16 arcs of 9 of min(d) (dark) / min(-d) (bright); score = s - 1
+// s = max over 16 arcs of 9 of min(d) (dark) / min(-d) (bright); score = s - 1.
+// Sliding minimum / maximum over windows of 9 by doubling (2, 4, 8, +1).
+// NOTE: the arc minima and maxima are reduced separately and negated once at the end.  Folding the negation
+// into the loop (`best = max(best, max(mn9, -mx9))`) is miscompiled by ptxas 12.9 for sm_100a at -O1 and
+// above (3-input VIMNMX3 with a negated operand returns wrong values; verified on a B200, correct at -O0).
 __device__ __forceinline__ int fast_score(const int d[16])
 {
-    int best = -256;
-    // sliding minimum / maximum over windows of 9 by doubling: m2, m4, m8, then one more
     int mn2[16], mx2[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) { mn2[k] = min(d[k], d[(k + 1) & 15]); mx2[k] = max(d[k], d[(k + 1) & 15]); }
     int mn4[16], mx4[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) { mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); }
+    int bmn = -256, bmx = 256;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-        best = max(best, max(mn9, -mx9));
+        bmn = max(bmn, min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]));
+        bmx = min(bmx, max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]));
     }
-    return best - 1;
+    return max(bmn, -bmx) - 1;
 }
 
 struct fast_grid_args {
