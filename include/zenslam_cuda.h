@@ -230,6 +230,12 @@ ZS_API zs_status zs_frontend_upload(zs_frontend* fe, const uint8_t* left, const 
 ZS_API zs_status zs_frontend_run(zs_frontend* fe);
 /* copy results to host (synchronises) */
 ZS_API zs_status zs_frontend_download(zs_frontend* fe, const zs_frontend_results* res);
+/* per-stage device timing with CUDA events on the context's stream: stages are
+ * 0 pyramid, 1 FAST/grid, 2 ORB, 3 match, 4 KLT, 5 carry.  enable(1) resets; collect() synchronises and
+ * returns summed milliseconds per stage over the (at most 64 most recent) runs since enable. */
+#define ZS_FRONTEND_STAGES 6
+ZS_API zs_status zs_frontend_timing_enable(zs_frontend* fe, int on);
+ZS_API zs_status zs_frontend_timing_collect(zs_frontend* fe, float* stage_ms_sum, int* runs);
 /* upload + run + download with host buffers: the end-to-end call */
 ZS_API zs_status zs_frontend_process_host(zs_frontend* fe, const uint8_t* left, const uint8_t* right,
                                           size_t pitch, size_t stride, const zs_frontend_results* res);

@@ -88,6 +88,8 @@ SIGNATURES = {
     "zs_frontend_d2h_bytes": (Z, [P]),
     "zs_frontend_upload": (I, [P, P, P, Z, Z, I]),
     "zs_frontend_run": (I, [P]),
+    "zs_frontend_timing_enable": (I, [P, I]),
+    "zs_frontend_timing_collect": (I, [P, C.POINTER(C.c_float), C.POINTER(I)]),
     "zs_frontend_download": (I, [P, C.POINTER(FrontendResults)]),
     "zs_frontend_process_host": (I, [P, P, P, Z, Z, C.POINTER(FrontendResults)]),
 }

@@ -12,6 +12,9 @@
 
 #include "zs_common.cuh"
 
+#define ZS_FE_STAGES 6          // pyramid, fast, orb, match, klt, carry
+#define ZS_FE_TIMING_RING 64
+
 struct zs_frontend {
     zs_context* ctx;
     zs_frontend_options opt;
@@ -26,9 +29,14 @@ struct zs_frontend {
     float* t_pts; uint8_t* t_status; float* t_err; uint8_t* t_keep;   // [4B][cap]
     int* t_n;                                            // [4B] points tracked per job
     bool have_carry;
+    // optional per-stage device timing: a ring of event sets, one set per zs_frontend_run
+    int timing; int t_runs;
+    cudaEvent_t ev[ZS_FE_TIMING_RING][ZS_FE_STAGES + 1];
     // pinned host staging for process_host
     uint8_t* pin; size_t pin_bytes;
 };
+
+#define ZS_FE_MARK(i) do { if (fe->timing) ZS_CUDA(cudaEventRecord(fe->ev[fe->t_runs % ZS_FE_TIMING_RING][i], ctx->stream)); } while (0)
 
 static inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
@@ -102,6 +110,9 @@ extern "C" void zs_frontend_destroy(zs_frontend* fe)
     if (fe->pyr) zs_pyramid_destroy(fe->pyr);
     if (fe->dev) cudaFree(fe->dev);
     if (fe->pin) cudaFreeHost(fe->pin);
+    if (fe->ev[0][0])
+        for (int r = 0; r < ZS_FE_TIMING_RING; ++r)
+            for (int i = 0; i <= ZS_FE_STAGES; ++i) cudaEventDestroy(fe->ev[r][i]);
     free(fe);
 }
 
@@ -137,6 +148,7 @@ extern "C" zs_status zs_frontend_run(zs_frontend* fe)
     const int B = fe->B, cap = fe->cap;
     const zs_frontend_options& o = fe->opt;
     zs_status st;
+    ZS_FE_MARK(0);
     // 1. pyramids of the 2B new images (utils::pyramid, processor.cpp:37,53)
     if ((st = zs_pyramid_build(ctx, fe->pyr, 2, 2 * B)) != ZS_OK) return st;
     if (!fe->have_carry) {
@@ -144,16 +156,20 @@ extern "C" zs_status zs_frontend_run(zs_frontend* fe)
         // temporal jobs of frame 0 track zero points
         ZS_CUDA(cudaMemsetAsync(fe->n, 0, sizeof(int) * 2, ctx->stream));
     }
+    ZS_FE_MARK(1);
     // 2. detection (keypoint_tracker.cpp:53,69 -> keypoint_detector_grid.cpp:39-150), no occupancy: every cell is searched
     if ((st = zs_fast_grid_detect(ctx, fe->pyr, 2, 2 * B, o.cell_w, o.cell_h, o.fast_threshold, nullptr, fe->raw_xy, fe->raw_resp,
                                   fe->raw_n, cap)) != ZS_OK) return st;
+    ZS_FE_MARK(2);
     // 3. ORB::compute (keypoint_detector_grid.cpp:138)
     if ((st = zs_orb_compute(ctx, fe->pyr, 2, 2 * B, fe->raw_xy, fe->raw_resp, nullptr, fe->raw_n, cap, fe->xy + (size_t)2 * cap * 2,
                              fe->resp + (size_t)2 * cap, nullptr, fe->n + 2, fe->desc + (size_t)2 * cap * 32)) != ZS_OK) return st;
+    ZS_FE_MARK(3);
     // 4. stereo kNN + ratio (matcher.cpp:60-75), left = query, right = train
     if ((st = zs_match_hamming_knn2(ctx, fe->desc + (size_t)2 * cap * 32, fe->n + 2, (size_t)cap * 32,
                                     fe->desc + (size_t)(B + 2) * cap * 32, fe->n + B + 2, (size_t)cap * 32, B, cap, cap,
                                     o.matcher_ratio, fe->m_idx, fe->m_dist, fe->m_pass)) != ZS_OK) return st;
+    ZS_FE_MARK(4);
     // 5. four forward+backward KLT pairs per frame (keypoint_tracker.cpp:47,50,60-67,76-83)
     zs_lk_params prm;
     prm.win_w = o.klt_win_w; prm.win_h = o.klt_win_h; prm.max_level = o.klt_max_level; prm.max_iters = o.max_iters;
@@ -162,6 +178,7 @@ extern "C" zs_status zs_frontend_run(zs_frontend* fe)
                             fe->t_status, fe->t_err, 1, o.klt_threshold, fe->t_keep)) != ZS_OK) return st;
     k_gather_counts<<<zs_div_up(4 * B, 256), 256, 0, ctx->stream>>>(fe->n, fe->job_row, 4 * B, fe->t_n);
     ZS_LAUNCH_CHECK(ctx);
+    ZS_FE_MARK(5);
     // 6. carry the last stereo frame into slots 0/1 (pyramid planes and keypoints)
     const zs_pyr_view& v = fe->pyr->v;
     for (int cam = 0; cam < 2; ++cam) {
@@ -176,7 +193,38 @@ extern "C" zs_status zs_frontend_run(zs_frontend* fe)
                                 cudaMemcpyDeviceToDevice, ctx->stream));
         ZS_CUDA(cudaMemcpyAsync(fe->n + dst, fe->n + src, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     }
+    ZS_FE_MARK(6);
+    if (fe->timing) fe->t_runs++;
     fe->have_carry = true;
+    return ZS_OK;
+}
+
+// Per-stage device timing (CUDA events on the context's stream).  enable(1) resets the run counter;
+// collect() synchronises and returns the summed milliseconds per stage over the (at most 64 most recent) runs.
+extern "C" zs_status zs_frontend_timing_enable(zs_frontend* fe, int on)
+{
+    ZS_REQUIRE(fe, "null argument");
+    ZS_CUDA(cudaSetDevice(fe->ctx->device));
+    if (on && !fe->ev[0][0])
+        for (int r = 0; r < ZS_FE_TIMING_RING; ++r)
+            for (int i = 0; i <= ZS_FE_STAGES; ++i) ZS_CUDA(cudaEventCreate(&fe->ev[r][i]));
+    fe->timing = on; fe->t_runs = 0;
+    return ZS_OK;
+}
+
+extern "C" zs_status zs_frontend_timing_collect(zs_frontend* fe, float* stage_ms_sum, int* runs)
+{
+    ZS_REQUIRE(fe && stage_ms_sum && runs, "null argument");
+    ZS_CUDA(cudaStreamSynchronize(fe->ctx->stream));
+    const int n = fe->t_runs < ZS_FE_TIMING_RING ? fe->t_runs : ZS_FE_TIMING_RING;
+    for (int i = 0; i < ZS_FE_STAGES; ++i) stage_ms_sum[i] = 0.f;
+    for (int r = 0; r < n; ++r)
+        for (int i = 0; i < ZS_FE_STAGES; ++i) {
+            float ms = 0.f;
+            ZS_CUDA(cudaEventElapsedTime(&ms, fe->ev[r][i], fe->ev[r][i + 1]));
+            stage_ms_sum[i] += ms;
+        }
+    *runs = n;
     return ZS_OK;
 }
 

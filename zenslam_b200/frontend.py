@@ -79,6 +79,19 @@ class StereoFrontend:
     def run(self):
         check(lib().zs_frontend_run(self._h))
 
+    STAGES = ("pyramid", "fast_grid", "orb", "match", "klt", "carry")
+
+    def timing_enable(self, on=True):
+        check(lib().zs_frontend_timing_enable(self._h, 1 if on else 0))
+
+    def timing_collect(self):
+        """-> ({stage: mean ms per run}, runs) measured with CUDA events on the context's stream"""
+        ms = (C.c_float * 6)()
+        runs = C.c_int(0)
+        check(lib().zs_frontend_timing_collect(self._h, ms, C.byref(runs)))
+        n = max(1, runs.value)
+        return {k: ms[i] / n for i, k in enumerate(self.STAGES)}, runs.value
+
     def download(self) -> dict:
         host, res = self._results()
         check(lib().zs_frontend_download(self._h, C.byref(res)))
