@@ -23,6 +23,10 @@ struct zs_pyr_view {
     short2* der[ZS_MAX_LEVELS];
     // blurred level-0 image for ORB (un-padded, pitch blur_pitch)
     uint8_t* blur; int blur_pitch; size_t blur_slot;
+    // TMA descriptors in device memory (null when the window is wider than 31): [2*l] = image plane of level l
+    // as a (pitch, padded rows, slots) u8 tensor with a 48x32x1 box; [2*l+1] = derivative plane as u32 elements
+    // with a 36x32x1 box (TMA box origins must be 16-byte aligned).  Coordinates are padded-plane coordinates.
+    const void* tmaps;
 };
 
 struct zs_context {
@@ -45,6 +49,7 @@ struct zs_pyramid {
     zs_pyr_view v;
     void* block;        // one allocation backing every plane
     size_t block_bytes;
+    void* tmaps_dev;    // device copy of the CUtensorMap array
 };
 
 void zs_set_error(const char* fmt, ...);

@@ -2,7 +2,62 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <cuda.h>
+
 #include "zs_common.cuh"
+
+// cuTensorMapEncodeTiled is resolved through the runtime so that the library does not link libcuda
+typedef CUresult (*zs_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static zs_encode_tiled_fn get_encode_tiled()
+{
+    static zs_encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (zs_encode_tiled_fn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// TMA descriptors of a pyramid's planes (used by the KLT kernel to stage 32x32 patches)
+static zs_status make_tensor_maps(zs_pyramid* p)
+{
+    zs_pyr_view& v = p->v;
+    v.tmaps = nullptr; p->tmaps_dev = nullptr;
+    if (p->win_w > 31 || p->win_h > 31) return ZS_OK;      // patches would not fit the 32x32 box
+    zs_encode_tiled_fn enc = get_encode_tiled();
+    if (!enc) { zs_set_error("cuTensorMapEncodeTiled is not available from this driver"); return ZS_ERR_CUDA; }
+    CUtensorMap maps[2 * ZS_MAX_LEVELS];
+    for (int l = 0; l < v.levels; ++l) {
+        const cuuint64_t rows = (cuuint64_t)(v.h[l] + 2 * v.pad_y);
+        const cuuint64_t dims[3] = { (cuuint64_t)v.pitch[l], rows, (cuuint64_t)v.slots };
+        // TMA needs a 16-byte aligned box origin, so the boxes are wider than the 32 columns a window needs:
+        // 48 bytes cover any byte offset 0..15, 36 (dx,dy) words cover any word offset 0..3
+        const cuuint32_t box[3] = { 48, 32, 1 }, boxd[3] = { 36, 32, 1 }, es[3] = { 1, 1, 1 };
+        const cuuint64_t st8[2] = { (cuuint64_t)v.pitch[l], (cuuint64_t)v.slot_stride[l] };
+        CUresult r = enc(&maps[2 * l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, v.img[l], dims, st8, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { zs_set_error("cuTensorMapEncodeTiled(image level %d) failed: %d", l, (int)r); return ZS_ERR_CUDA; }
+        const cuuint64_t st32[2] = { (cuuint64_t)v.pitch[l] * 4, (cuuint64_t)v.slot_stride[l] * 4 };
+        r = enc(&maps[2 * l + 1], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, v.der[l], dims, st32, boxd, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { zs_set_error("cuTensorMapEncodeTiled(deriv level %d) failed: %d", l, (int)r); return ZS_ERR_CUDA; }
+    }
+    ZS_CUDA(cudaMalloc(&p->tmaps_dev, sizeof(CUtensorMap) * 2 * ZS_MAX_LEVELS));
+    ZS_CUDA(cudaMemcpyAsync(p->tmaps_dev, maps, sizeof(CUtensorMap) * 2 * v.levels, cudaMemcpyHostToDevice, p->ctx->stream));
+    ZS_CUDA(cudaStreamSynchronize(p->ctx->stream));        // `maps` is on this stack frame
+    v.tmaps = p->tmaps_dev;
+    return ZS_OK;
+}
 
 static thread_local char g_err[512] = "";
 
@@ -196,6 +251,8 @@ zs_status zs_pyramid_create(zs_context* ctx, int width, int height, int slots, i
         v.der[l] = (short2*)((uint8_t*)p->block + der_off[l]);
     }
     v.blur = (uint8_t*)p->block + blur_off;
+    zs_status st = make_tensor_maps(p);
+    if (st != ZS_OK) { cudaFree(p->block); free(p); return st; }
     *out = p;
     return ZS_OK;
 }
@@ -206,6 +263,7 @@ void zs_pyramid_destroy(zs_pyramid* p)
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     cudaFree(p->block);
+    if (p->tmaps_dev) cudaFree(p->tmaps_dev);
     free(p);
 }
 

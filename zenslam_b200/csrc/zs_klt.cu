@@ -8,6 +8,8 @@
 // One warp per feature; all pyramid levels and all Gauss-Newton iterations run inside the kernel (no
 // per-level launch).  The template patch lives in shared memory; the warp sweeps the window with its 32
 // lanes, control flow (early exits, iteration counts) is warp-uniform so divergence is across warps only.
+#include <stdlib.h>
+
 #include "zs_common.cuh"
 
 #define KLT_WARPS 8
@@ -196,7 +198,7 @@ __device__ __forceinline__ int pack_s16x2(int lo, int hi) { return (lo & 0xffff)
 
 template <int WW, int WH>
 __device__ __forceinline__ lk_result lk_track_point_v2(const klt_args& a, int slot_i, int slot_j, float2 prev, float2 init,
-                                                        bool use_init, int lane)
+                                                        bool use_init, int lane, int* sG)
 {
     const zs_pyr_view& v = a.v;
     const float hwx = (float)(WW - 1) * 0.5f, hwy = (float)(WH - 1) * 0.5f;
@@ -230,8 +232,8 @@ __device__ __forceinline__ lk_result lk_track_point_v2(const klt_args& a, int sl
         int w00, w01, w10, w11;
         lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
 
-        // ---- template (registers)
-        int Ix[WH], Iy[WH];
+        // ---- template: rolled row loop (small code), (Ix,Iy) handed over through shared memory as packed
+        // s16x2 words, then unpacked once into registers for the fully unrolled iteration loop
         int pA11 = 0, pA12 = 0, pA22 = 0, pc1 = 0, pc2 = 0;
         {
             const int wt = pack_s16x2(w00, w01), wb = pack_s16x2(w10, w11);
@@ -239,7 +241,7 @@ __device__ __forceinline__ lk_result lk_track_point_v2(const klt_args& a, int sl
             const short2* dp = dI + (ptrdiff_t)ipy * pitch + ipx + lane;
             unsigned pc = (unsigned)ip[0] | ((unsigned)ip[1] << 8);
             short2 c0 = dp[0], c1 = dp[1];
-#pragma unroll
+#pragma unroll 1
             for (int y = 0; y < WH; ++y) {
                 ip += pitch; dp += pitch;
                 const unsigned pn = (unsigned)ip[0] | ((unsigned)ip[1] << 8);
@@ -248,11 +250,17 @@ __device__ __forceinline__ lk_result lk_track_point_v2(const klt_args& a, int sl
                 int ixv = ((int)c0.x * w00 + (int)c1.x * w01 + (int)n0.x * w10 + (int)n1.x * w11 + (1 << 13)) >> 14;
                 int iyv = ((int)c0.y * w00 + (int)c1.y * w01 + (int)n0.y * w10 + (int)n1.y * w11 + (1 << 13)) >> 14;
                 if (!active) { ixv = 0; iyv = 0; }
-                Ix[y] = ixv; Iy[y] = iyv;
+                sG[y * 32 + lane] = pack_s16x2(ixv, iyv);
                 pA11 += ixv * ixv; pA12 += ixv * iyv; pA22 += iyv * iyv;
                 pc1 += ival * ixv; pc2 += ival * iyv;
                 pc = pn; c0 = n0; c1 = n1;
             }
+        }
+        int Ix[WH], Iy[WH];
+#pragma unroll
+        for (int y = 0; y < WH; ++y) {
+            const int g = sG[y * 32 + lane];       // written by this same lane: no synchronisation needed
+            Ix[y] = (int)(short)(g & 0xffff); Iy[y] = g >> 16;
         }
         const long long sA11 = warp_sum_exact(pA11), sA12 = warp_sum_exact(pA12), sA22 = warp_sum_exact(pA22);
         const long long sc1 = warp_sum_exact(pc1), sc2 = warp_sum_exact(pc2);
@@ -309,10 +317,11 @@ __device__ __forceinline__ lk_result lk_track_point_v2(const klt_args& a, int sl
 
 #define KLT2_WARPS 4
 
-// grid: (ceil(cap / KLT2_WARPS), jobs); no shared memory
+// grid: (ceil(cap / KLT2_WARPS), jobs); static smem: WH x 32 words per warp
 template <int WW, int WH>
 __global__ void __launch_bounds__(KLT2_WARPS * 32) k_klt_track_v2(klt_args a)
 {
+    __shared__ int s_g[KLT2_WARPS][WH * 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int job = blockIdx.y;
     const int i = blockIdx.x * KLT2_WARPS + warp;
@@ -320,22 +329,312 @@ __global__ void __launch_bounds__(KLT2_WARPS * 32) k_klt_track_v2(klt_args a)
     if (i >= min(a.count[in_row], a.cap)) return;
     const size_t o = (size_t)job * a.cap + i;
     const float2 p0 = a.prev_pts[(size_t)in_row * a.cap + i];
-    const bool use_init = (a.flags & ZS_LK_USE_INITIAL_FLOW) != 0;
+    bool use_init = (a.flags & ZS_LK_USE_INITIAL_FLOW) != 0;
     float2 init = make_float2(0.f, 0.f);
     if (use_init) init = a.next_pts[o];
-    const int si = a.prev_slot[job], sj = a.next_slot[job];
-    const lk_result f = lk_track_point_v2<WW, WH>(a, si, sj, p0, init, use_init, lane);
-    if (lane == 0) {
-        a.next_pts[o] = make_float2(f.x, f.y);
-        a.status[o] = (uint8_t)f.status;
-        a.err[o] = f.err;
-    }
-    if (a.fb) {
-        const lk_result b = lk_track_point_v2<WW, WH>(a, sj, si, make_float2(f.x, f.y), init, false, lane);
-        if (lane == 0) {
-            const float dx = __fsub_rn(b.x, p0.x), dy = __fsub_rn(b.y, p0.y);
+    int si = a.prev_slot[job], sj = a.next_slot[job];
+    float2 from = p0;
+    int fwd_status = 1;
+    // pass 0 = forward call; pass 1 (fb only) = backward call from the forward result without initial flow
+    // (keypoint_tracker.cpp:156-170).  One inlined instance of the tracker keeps the code inside the I-cache.
+#pragma unroll 1
+    for (int pass = 0; pass < (a.fb ? 2 : 1); ++pass) {
+        const lk_result f = lk_track_point_v2<WW, WH>(a, si, sj, from, init, use_init, lane, s_g[warp]);
+        if (pass == 0) {
+            if (lane == 0) {
+                a.next_pts[o] = make_float2(f.x, f.y);
+                a.status[o] = (uint8_t)f.status;
+                a.err[o] = f.err;
+            }
+            fwd_status = f.status;
+            from = make_float2(f.x, f.y);
+            const int t = si; si = sj; sj = t;
+            use_init = false;
+        } else if (lane == 0) {
+            // cv::norm(Point2f) -> sqrt((double)dx*dx + (double)dy*dy) < klt_threshold (keypoint_tracker.cpp:180)
+            const float dx = __fsub_rn(f.x, p0.x), dy = __fsub_rn(f.y, p0.y);
             const double nrm = sqrt((double)dx * (double)dx + (double)dy * (double)dy);
-            a.keep[o] = (uint8_t)(f.status && b.status && nrm < a.fb_thr);
+            a.keep[o] = (uint8_t)(fwd_status && f.status && nrm < a.fb_thr);
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// v3: TMA-staged patches.  Per warp, one elected lane asks the TMA unit for the patch of J (and, once per
+// level, the patch of I plus the (dx,dy) patch) around the window's integer origin; completion is signalled on
+// an mbarrier and no LSU instruction or register is spent on the gather.  TMA box origins must be 16-byte
+// aligned (an unaligned origin faults with "illegal instruction" on sm_100a), so the boxes are 48 bytes /
+// 36 words wide and start at the aligned column below the window; the residual offset is applied when the
+// lanes read shared memory (word offset folded into the address, byte offset folded into the funnel shifts
+// that form the (x, x+1) byte pairs anyway).  The J patch is fetched again only when the window leaves the
+// 16-byte block or changes row (most Gauss-Newton steps move < 1 px).
+//   lane = (k = lane & 3: columns 8k..8k+7, g = lane >> 2: rows g, g+8, g+16, g+24): 4 x 8 pixels per lane.
+// Arithmetic and results are identical to v2 / the generic kernel.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int x, int y, int z, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+__device__ __forceinline__ int dp2a_hi_su(int a_s16x2, unsigned b_u8, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s16x2), "r"(b_u8), "r"(c));
+    return d;
+}
+
+#define KLT3_WARPS 4
+#define KLT3_JP 12                   // J / I patch row pitch in words (48-byte TMA box)
+#define KLT3_DP 36                   // derivative patch row pitch in words
+#define KLT3_SJ_BYTES 1664           // 32 TMA rows x 48 B + one spill row read by masked pixels, 128-byte multiple
+#define KLT3_SD_BYTES 4864           // 32 TMA rows x 144 B + spill row (33 x 144 = 4752), 128-byte multiple
+#define KLT3_WARP_BYTES (KLT3_SJ_BYTES + KLT3_SD_BYTES + 128)
+
+// the eight (x, x+1) byte pairs of a lane's row: R0 = bytes 0..3, F0 = bytes 1..4, R1 = bytes 4..7, F1 = bytes 5..8
+struct row8 { unsigned R0, F0, R1, F1; };
+
+// w points at the word holding byte 0 (byte offset t = 0..3 inside it); sh = 8 t
+__device__ __forceinline__ row8 load_row8(const uint32_t* w, int sh)
+{
+    const unsigned w0 = w[0], w1 = w[1], w2 = w[2];
+    row8 r;
+    r.R0 = __funnelshift_r(w0, w1, sh); r.F0 = __funnelshift_rc(w0, w1, sh + 8);
+    r.R1 = __funnelshift_r(w1, w2, sh); r.F1 = __funnelshift_rc(w1, w2, sh + 8);
+    return r;
+}
+
+// bilinear sample of pixel P (0..7) from the row pair (top, bottom)
+template <int P>
+__device__ __forceinline__ int sample8(int wt, int wb, const row8& a, const row8& b)
+{
+    const unsigned ta = (P < 4) ? ((P & 1) ? a.F0 : a.R0) : ((P & 1) ? a.F1 : a.R1);
+    const unsigned tb = (P < 4) ? ((P & 1) ? b.F0 : b.R0) : ((P & 1) ? b.F1 : b.R1);
+    int acc;
+    if ((P & 3) < 2) acc = dp2a_lo_su(wt, ta, dp2a_lo_su(wb, tb, 1 << 8));
+    else acc = dp2a_hi_su(wt, ta, dp2a_hi_su(wb, tb, 1 << 8));
+    return acc >> 9;
+}
+
+template <int WW, int WH>
+__device__ __forceinline__ lk_result lk_track_point_v3(const klt_args& a, int slot_i, int slot_j, float2 prev, float2 init,
+                                                        bool use_init, int lane, uint8_t* sJ, uint8_t* sD, uint32_t bar,
+                                                        uint32_t& parity)
+{
+    const zs_pyr_view& v = a.v;
+    const float hwx = (float)(WW - 1) * 0.5f, hwy = (float)(WH - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (float)(1 << 20);
+    lk_result r; r.status = 1; r.err = 0.f; r.x = 0.f; r.y = 0.f;
+    float outx = 0.f, outy = 0.f;
+    const int top = min(a.max_level, v.levels - 1);
+    const int k = lane & 3, g = lane >> 2;
+    const uint32_t sJ_a = smem_u32(sJ), sD_a = smem_u32(sD);
+    const char* maps = (const char*)v.tmaps;
+    const uint32_t* jbase = (const uint32_t*)sJ + g * KLT3_JP + 2 * k;
+    const uint32_t* dbase = (const uint32_t*)sD + g * KLT3_DP + 8 * k;
+
+    for (int level = top; level >= 0; --level) {
+        const int cols = v.w[level], rows = v.h[level];
+        const float scale = 1.f / (float)(1 << level);
+        float px = __fmul_rn(prev.x, scale), py = __fmul_rn(prev.y, scale);
+        float nx, ny;
+        if (level == top) {
+            if (use_init) { nx = __fmul_rn(init.x, scale); ny = __fmul_rn(init.y, scale); }
+            else { nx = px; ny = py; }
+        } else { nx = __fmul_rn(outx, 2.f); ny = __fmul_rn(outy, 2.f); }
+        outx = nx; outy = ny;
+
+        px = __fsub_rn(px, hwx); py = __fsub_rn(py, hwy);
+        const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
+        if (ipx < -WW || ipx >= cols || ipy < -WH || ipy >= rows) {
+            if (level == 0) { r.status = 0; r.err = 0.f; }
+            continue;
+        }
+        int w00, w01, w10, w11;
+        lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
+
+        // ---- fetch the I patch (into the J buffer) and the derivative patch
+        const int gx = v.pad_x + ipx, gy = v.pad_y + ipy;          // padded-plane coordinates, gx >= 1
+        __syncwarp();
+        if (lane == 0) {
+            mbar_expect_tx(bar, 48 * 32 + 36 * 4 * 32);
+            tma_load_3d(sJ_a, maps + (size_t)(2 * level) * 128, gx & ~15, gy, slot_i, bar);
+            tma_load_3d(sD_a, maps + (size_t)(2 * level + 1) * 128, gx & ~3, gy, slot_i, bar);
+        }
+        mbar_wait(bar, parity); parity ^= 1;
+
+        // ---- template in registers: 4 row steps x 8 pixels per lane
+        int Ix[4][8], Iy[4][8];
+        int pA11 = 0, pA12 = 0, pA22 = 0, pc1 = 0, pc2 = 0;
+        {
+            const int wt = pack_s16x2(w00, w01), wb = pack_s16x2(w10, w11);
+            const uint32_t* jw = jbase + ((gx & 15) >> 2);
+            const int sh = (gx & 3) * 8;
+            const uint32_t* dw = dbase + (gx & 3);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const row8 ra = load_row8(jw + j * 8 * KLT3_JP, sh), rb = load_row8(jw + (j * 8 + 1) * KLT3_JP, sh);
+                int tx[9], ty[9], bx[9], by[9];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    const unsigned dt = dw[j * 8 * KLT3_DP + q], db = dw[(j * 8 + 1) * KLT3_DP + q];
+                    tx[q] = (int)(short)(dt & 0xffff); ty[q] = (int)dt >> 16;
+                    bx[q] = (int)(short)(db & 0xffff); by[q] = (int)db >> 16;
+                }
+                const bool row_masked = (8 * j + 7 >= WH) && (8 * j + g >= WH);
+                int iv[8];
+                iv[0] = sample8<0>(wt, wb, ra, rb); iv[1] = sample8<1>(wt, wb, ra, rb); iv[2] = sample8<2>(wt, wb, ra, rb);
+                iv[3] = sample8<3>(wt, wb, ra, rb); iv[4] = sample8<4>(wt, wb, ra, rb); iv[5] = sample8<5>(wt, wb, ra, rb);
+                iv[6] = sample8<6>(wt, wb, ra, rb); iv[7] = sample8<7>(wt, wb, ra, rb);
+#pragma unroll
+                for (int pp = 0; pp < 8; ++pp) {
+                    int ixv = (tx[pp] * w00 + tx[pp + 1] * w01 + bx[pp] * w10 + bx[pp + 1] * w11 + (1 << 13)) >> 14;
+                    int iyv = (ty[pp] * w00 + ty[pp + 1] * w01 + by[pp] * w10 + by[pp + 1] * w11 + (1 << 13)) >> 14;
+                    if ((8 * j + 7 >= WH) || (24 + pp >= WW)) {      // compile-time: only overhanging rows / columns
+                        bool masked = row_masked;
+                        if (24 + pp >= WW) masked = masked || (8 * k + pp >= WW);
+                        if (masked) { ixv = 0; iyv = 0; }
+                    }
+                    Ix[j][pp] = ixv; Iy[j][pp] = iyv;
+                    pA11 += ixv * ixv; pA12 += ixv * iyv; pA22 += iyv * iyv;
+                    pc1 += iv[pp] * ixv; pc2 += iv[pp] * iyv;
+                }
+            }
+        }
+        const long long sA11 = warp_sum_exact(pA11), sA12 = warp_sum_exact(pA12), sA22 = warp_sum_exact(pA22);
+        const long long sc1 = warp_sum_exact(pc1), sc2 = warp_sum_exact(pc2);
+        const float A11 = __fmul_rn(__ll2float_rn(sA11), FLT_SCALE), A12 = __fmul_rn(__ll2float_rn(sA12), FLT_SCALE),
+                    A22 = __fmul_rn(__ll2float_rn(sA22), FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dA = __fsub_rn(A11, A22);
+        const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * WW * WH));
+        if (a.flags & ZS_LK_GET_MIN_EIGENVALS) r.err = minEig;
+        if ((double)minEig < a.min_eig || D < 1.1920929e-07f) {
+            if (level == 0) r.status = 0;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+        nx = __fsub_rn(nx, hwx); ny = __fsub_rn(ny, hwy);
+        float pdx = 0.f, pdy = 0.f;
+        int cur_x0 = 0x7fffffff, cur_y = 0x7fffffff;       // origin of the J patch now in shared memory
+        for (int it = 0; it < a.max_iters; ++it) {
+            const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
+            if (inx < -WW || inx >= cols || iny < -WH || iny >= rows) {
+                if (level == 0) r.status = 0;
+                break;
+            }
+            const int jx = v.pad_x + inx, jy = v.pad_y + iny;
+            if ((jx & ~15) != cur_x0 || jy != cur_y) {
+                __syncwarp();                                  // every lane is done with the previous patch
+                cur_x0 = jx & ~15; cur_y = jy;
+                if (lane == 0) {
+                    mbar_expect_tx(bar, 48 * 32);
+                    tma_load_3d(sJ_a, maps + (size_t)(2 * level) * 128, cur_x0, cur_y, slot_j, bar);
+                }
+                mbar_wait(bar, parity); parity ^= 1;
+            }
+            lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
+            const int wt = pack_s16x2(w00, w01), wb = pack_s16x2(w10, w11);
+            const uint32_t* jw = jbase + ((jx & 15) >> 2);
+            const int sh = (jx & 3) * 8;
+            int pb1 = 0, pb2 = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const row8 ra = load_row8(jw + j * 8 * KLT3_JP, sh), rb = load_row8(jw + (j * 8 + 1) * KLT3_JP, sh);
+                int jv;
+                jv = sample8<0>(wt, wb, ra, rb); pb1 += jv * Ix[j][0]; pb2 += jv * Iy[j][0];
+                jv = sample8<1>(wt, wb, ra, rb); pb1 += jv * Ix[j][1]; pb2 += jv * Iy[j][1];
+                jv = sample8<2>(wt, wb, ra, rb); pb1 += jv * Ix[j][2]; pb2 += jv * Iy[j][2];
+                jv = sample8<3>(wt, wb, ra, rb); pb1 += jv * Ix[j][3]; pb2 += jv * Iy[j][3];
+                jv = sample8<4>(wt, wb, ra, rb); pb1 += jv * Ix[j][4]; pb2 += jv * Iy[j][4];
+                jv = sample8<5>(wt, wb, ra, rb); pb1 += jv * Ix[j][5]; pb2 += jv * Iy[j][5];
+                jv = sample8<6>(wt, wb, ra, rb); pb1 += jv * Ix[j][6]; pb2 += jv * Iy[j][6];
+                jv = sample8<7>(wt, wb, ra, rb); pb1 += jv * Ix[j][7]; pb2 += jv * Iy[j][7];
+            }
+            const long long sb1 = warp_sum_exact(pb1) - sc1, sb2 = warp_sum_exact(pb2) - sc2;
+            const float b1 = __fmul_rn(__ll2float_rn(sb1), FLT_SCALE), b2 = __fmul_rn(__ll2float_rn(sb2), FLT_SCALE);
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+            nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
+            outx = __fadd_rn(nx, hwx); outy = __fadd_rn(ny, hwy);
+            if ((double)dx * (double)dx + (double)dy * (double)dy <= a.eps2) break;
+            if (it > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
+                outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f)); outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+    }
+    r.x = outx; r.y = outy;
+    return r;
+}
+
+// grid: (ceil(cap / KLT3_WARPS), jobs); dynamic smem = KLT3_WARPS * KLT3_WARP_BYTES
+template <int WW, int WH>
+__global__ void __launch_bounds__(KLT3_WARPS * 32) k_klt_track_v3(klt_args a)
+{
+    extern __shared__ __align__(128) uint8_t smem3[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int job = blockIdx.y;
+    const int i = blockIdx.x * KLT3_WARPS + warp;
+    const int in_row = a.pts_row ? a.pts_row[job] : job;
+    if (i >= min(a.count[in_row], a.cap)) return;
+    uint8_t* sJ = smem3 + (size_t)warp * KLT3_WARP_BYTES;
+    uint8_t* sD = sJ + KLT3_SJ_BYTES;
+    const uint32_t bar = smem_u32(sD + KLT3_SD_BYTES);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // the spill rows are read (never used) by masked pixels; give them defined contents
+    ((uint32_t*)(sJ + 48 * 32))[lane] = 0;
+    ((uint32_t*)(sD + 144 * 32))[lane] = 0; ((uint32_t*)(sD + 144 * 32))[lane + 4] = 0;
+    __syncwarp();
+    uint32_t parity = 0;
+    const size_t o = (size_t)job * a.cap + i;
+    const float2 p0 = a.prev_pts[(size_t)in_row * a.cap + i];
+    bool use_init = (a.flags & ZS_LK_USE_INITIAL_FLOW) != 0;
+    float2 init = make_float2(0.f, 0.f);
+    if (use_init) init = a.next_pts[o];
+    int si = a.prev_slot[job], sj = a.next_slot[job];
+    float2 from = p0;
+    int fwd_status = 1;
+#pragma unroll 1
+    for (int pass = 0; pass < (a.fb ? 2 : 1); ++pass) {
+        const lk_result f = lk_track_point_v3<WW, WH>(a, si, sj, from, init, use_init, lane, sJ, sD, bar, parity);
+        if (pass == 0) {
+            if (lane == 0) {
+                a.next_pts[o] = make_float2(f.x, f.y);
+                a.status[o] = (uint8_t)f.status;
+                a.err[o] = f.err;
+            }
+            fwd_status = f.status;
+            from = make_float2(f.x, f.y);
+            const int t = si; si = sj; sj = t;
+            use_init = false;
+        } else if (lane == 0) {
+            const float dx = __fsub_rn(f.x, p0.x), dy = __fsub_rn(f.y, p0.y);
+            const double nrm = sqrt((double)dx * (double)dx + (double)dy * (double)dy);
+            a.keep[o] = (uint8_t)(fwd_status && f.status && nrm < a.fb_thr);
         }
     }
 }
@@ -398,7 +697,14 @@ zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_
     double eps = prm->epsilon; eps = eps < 0 ? 0 : eps > 10. ? 10. : eps;   // cv: clamp(epsilon, 0, 10)
     a.max_iters = mi; a.eps2 = eps * eps; a.flags = prm->flags; a.min_eig = prm->min_eig_threshold;
     a.status = d_status; a.err = d_err; a.fb = fb; a.fb_thr = fb_thr; a.keep = d_keep;
-    // specialised register-template kernels for the common window sizes (reference default 31x31)
+    // TMA-staged kernel for the reference's default window
+    if (a.win_w == 31 && a.win_h == 31 && a.v.tmaps && !getenv("ZS_KLT_NO_TMA")) {
+        const size_t smem3 = (size_t)KLT3_WARPS * KLT3_WARP_BYTES;
+        k_klt_track_v3<31, 31><<<dim3(zs_div_up(cap, KLT3_WARPS), jobs), KLT3_WARPS * 32, smem3, ctx->stream>>>(a);
+        ZS_LAUNCH_CHECK(ctx);
+        return ZS_OK;
+    }
+    // specialised register-template kernels for the common window sizes
     {
         const dim3 grid2(zs_div_up(cap, KLT2_WARPS), jobs);
         bool done = true;
