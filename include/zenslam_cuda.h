@@ -188,6 +188,13 @@ ZS_API zs_status zs_match_host(zs_context* ctx, const void* q, int nq, const voi
                                int norm, int mode, double ratio, int* query_idx, int* train_idx, float* distance,
                                int* n_out);
 
+/* cv::BFMatcher::knnMatch(query, train, k) / match() without the reference's gates: what a
+ * cv::DescriptorMatcher subclass needs (zenslam_cuda/source/bf_matcher.cpp) so zenslam::matcher's own code
+ * (matcher.cpp:60-80, 172-190) runs unchanged on top.  k = 1 or 2; cross_check requires k = 1.
+ * idx/dist are [nq][k]; idx = -1 where no neighbour exists (nt < k, or rejected by the cross check). */
+ZS_API zs_status zs_knn_match_host(zs_context* ctx, const void* q, int nq, const void* t, int nt, int dim,
+                                   int norm, int k, int cross_check, int* idx, float* dist);
+
 /* ---- batched stereo front-end ------------------------------------------------------------------
  * The per-frame call pattern of keypoint_tracker::track (keypoint_tracker.cpp:41-105) restated for
  * a batch of B consecutive stereo frames: per frame 2 pyramids, 2 grid detections + ORB, 1 stereo

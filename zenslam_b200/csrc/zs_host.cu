@@ -163,3 +163,54 @@ extern "C" zs_status zs_match_host(zs_context* ctx, const void* q, int nq, const
     *n_out = m;
     return ZS_OK;
 }
+
+extern "C" zs_status zs_knn_match_host(zs_context* ctx, const void* q, int nq, const void* t, int nt, int dim, int norm, int k,
+                                       int cross_check, int* idx, float* dist)
+{
+    ZS_REQUIRE(ctx, "null argument");
+    ZS_REQUIRE(k == 1 || k == 2, "k must be 1 or 2");
+    ZS_REQUIRE(!cross_check || k == 1, "cross check requires k = 1 (cv::BFMatcher asserts the same)");
+    ZS_REQUIRE(norm == 0 || norm == 1, "norm must be 0 (Hamming) or 1 (L2)");
+    if (nq <= 0) return ZS_OK;
+    ZS_REQUIRE(idx && dist, "null argument");
+    if (nt <= 0) {
+        for (int i = 0; i < nq * k; ++i) { idx[i] = -1; dist[i] = 0.f; }
+        return ZS_OK;
+    }
+    ZS_REQUIRE(q && t, "null argument");
+    if (norm == 0) ZS_REQUIRE(dim == 32 || dim == 256 || dim == 0, "Hamming descriptors are 32-byte rows");
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    const size_t row = norm == 0 ? 32 : sizeof(float) * (size_t)dim;
+    const size_t o_q = 256, o_t = o_q + al256(row * nq), o_idx = o_t + al256(row * nt), o_dist = o_idx + al256(sizeof(int) * 2 * nq),
+                 total = o_dist + al256(sizeof(float) * 2 * nq);
+    uint8_t* base;
+    ZS_CUDA(cudaMallocAsync((void**)&base, total, ctx->stream));
+    const int hdr[2] = { nq, nt };
+    ZS_CUDA(cudaMemcpyAsync(base, hdr, sizeof(hdr), cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(base + o_q, q, row * nq, cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(base + o_t, t, row * nt, cudaMemcpyHostToDevice, ctx->stream));
+    const int* d_nq = (const int*)base; const int* d_nt = d_nq + 1;
+    int* d_idx = (int*)(base + o_idx); float* d_dist = (float*)(base + o_dist);
+    zs_status st;
+    if (cross_check) {
+        st = norm == 0 ? zs_match_hamming_cross(ctx, base + o_q, d_nq, 0, base + o_t, d_nt, 0, 1, nq, nt, d_idx, d_dist)
+                       : zs_match_l2_cross(ctx, (const float*)(base + o_q), d_nq, 0, (const float*)(base + o_t), d_nt, 0, 1, nq, nt,
+                                           dim, d_idx, d_dist);
+    } else {
+        st = norm == 0 ? zs_match_hamming_knn2(ctx, base + o_q, d_nq, 0, base + o_t, d_nt, 0, 1, nq, nt, 1.0, d_idx, d_dist, nullptr)
+                       : zs_match_l2_knn2(ctx, (const float*)(base + o_q), d_nq, 0, (const float*)(base + o_t), d_nt, 0, 1, nq, nt,
+                                          dim, 1.0, d_idx, d_dist, nullptr);
+    }
+    if (st != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+    void* pin;
+    const int per = cross_check ? 1 : 2;
+    if ((st = zs_pinned(ctx, (sizeof(int) + sizeof(float)) * per * (size_t)nq, &pin)) != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+    int* h_idx = (int*)pin; float* h_dist = (float*)(h_idx + (size_t)per * nq);
+    ZS_CUDA(cudaMemcpyAsync(h_idx, d_idx, sizeof(int) * per * nq, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(h_dist, d_dist, sizeof(float) * per * nq, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ZS_CUDA(cudaFreeAsync(base, ctx->stream));
+    for (int i = 0; i < nq; ++i)
+        for (int j = 0; j < k; ++j) { idx[i * k + j] = h_idx[i * per + j]; dist[i * k + j] = h_dist[i * per + j]; }
+    return ZS_OK;
+}
