@@ -242,22 +242,43 @@ def run_ours(args, rank, world, local_rank):
     keep_frac = float(res["track_keep"].sum() / max(1, res["track_n"].sum()))
     value = world * B * K / (ms / 1000.0)
 
-    # ---- end to end: host buffers, H2D + D2H inside the timed region ------------------------------
-    for i in range(min(Wm, 3)):
-        fe.process(left_pin[i % nb], right_pin[i % nb])
+    # ---- end to end: host buffers, H2D + D2H of every step inside the timed region ---------------------
+    # (a) the pipelined public call: submit/wait keeps two batches in flight, so the PCIe copies of the neighbouring
+    #     batches overlap this batch's kernels; the pipeline starts empty and is drained inside the timed region
+    # (b) the blocking call process(): H2D -> kernels -> D2H strictly in sequence (what a per-frame caller sees)
+    def e2e_pipelined(steps, first):
+        fe.submit(left_pin[first % nb], right_pin[first % nb])
+        for i in range(1, steps):
+            j = (first + i) % nb
+            fe.submit(left_pin[j], right_pin[j])
+            fe.wait()
+        return fe.wait()
+
+    e2e_pipelined(max(2, min(Wm, 3)), 0)
     barrier()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
     g0.record(stream)
-    for i in range(K):
-        j = (Wm + i) % nb
-        out = fe.process(left_pin[j], right_pin[j])
+    out = e2e_pipelined(K, Wm)
     g1.record(stream)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1000.0
     e2e_ms = max_over_ranks(max(g0.elapsed_time(g1), wall_ms))
     e2e_value = world * B * K / (e2e_ms / 1000.0)
+    assert int(out["n_left"].min()) > 0
+
+    Ks = max(2, K // 2)
+    for i in range(2):
+        fe.process(left_pin[i % nb], right_pin[i % nb])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ks):
+        j = (Wm + i) % nb
+        out = fe.process(left_pin[j], right_pin[j])
+    barrier()
+    sync_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0)
+    e2e_sync_value = world * B * Ks / (sync_ms / 1000.0)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -275,7 +296,8 @@ def run_ours(args, rank, world, local_rank):
                              % (2 * B * 3.2, nb),
                        "parallelism": "independent sequences per GPU, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": fe.h2d_bytes, "d2h_bytes_per_step": fe.d2h_bytes,
-                    "ms_per_step": e2e_ms / K},
+                    "ms_per_step": e2e_ms / K, "call": "zs_frontend_submit_host/zs_frontend_wait (2 batches in flight)",
+                    "blocking_call_value": e2e_sync_value},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "stage_ms_per_step": stage_ms,

@@ -247,6 +247,14 @@ ZS_API zs_status zs_frontend_timing_collect(zs_frontend* fe, float* stage_ms_sum
 ZS_API zs_status zs_frontend_process_host(zs_frontend* fe, const uint8_t* left, const uint8_t* right,
                                           size_t pitch, size_t stride, const zs_frontend_results* res);
 
+/* pipelined end-to-end path: submit returns at once; up to two batches are in flight on three streams (H2D of
+ * batch k+1, kernels of batch k, D2H of batch k-1 overlap).  `res` buffers (ideally pinned) must stay valid until
+ * the matching zs_frontend_wait returns; waits complete in submission order. */
+ZS_API zs_status zs_frontend_submit_host(zs_frontend* fe, const uint8_t* left, const uint8_t* right,
+                                         size_t pitch, size_t stride, const zs_frontend_results* res);
+ZS_API zs_status zs_frontend_wait(zs_frontend* fe);
+ZS_API int zs_frontend_in_flight(const zs_frontend* fe);
+
 #ifdef __cplusplus
 }
 #endif

@@ -170,3 +170,42 @@ def test_frontend_batches_vs_oracle(ctx, w, h, B, cell):
                 assert np.array_equal(res["track_keep"][kind, k, :n].astype(bool), keep)
             prev = (PL, PR, xyl, xyr)
     fe.close()
+
+
+@pytest.mark.parametrize("w,h,B", [(752, 480, 2), (600, 360, 3)])     # 600: exercises the unaligned unpack path
+def test_frontend_pipelined_equals_blocking(ctx, w, h, B):
+    """submit/wait (two batches in flight on three streams) must return exactly what the blocking call returns,
+    batch for batch, including the state carried from batch to batch."""
+    from zenslam_b200 import slam_options
+    from zenslam_b200.frontend import StereoFrontend
+    nb = 4
+    seq, _ = syn.stereo_sequence(w, h, nb * B, 77 + w, subpixel=True)
+    lefts = [np.ascontiguousarray(seq[b * B:(b + 1) * B, 0]) for b in range(nb)]
+    rights = [np.ascontiguousarray(seq[b * B:(b + 1) * B, 1]) for b in range(nb)]
+    fe = StereoFrontend(ctx, w, h, B, slam_options())
+    want = [{k: v.copy() for k, v in fe.process(lefts[b], rights[b]).items()} for b in range(nb)]
+    fe.close()
+    fe = StereoFrontend(ctx, w, h, B, slam_options())
+    got = []
+    fe.submit(lefts[0], rights[0])
+    for b in range(1, nb):
+        fe.submit(lefts[b], rights[b])
+        assert fe.in_flight == 2
+        got.append({k: v.copy() for k, v in fe.wait().items()})
+    got.append({k: v.copy() for k, v in fe.wait().items()})
+    assert fe.in_flight == 0
+    with pytest.raises(Exception):
+        fe.wait()                                   # nothing in flight: error, not a hang
+    for b in range(nb):
+        nl = want[b]["n_left"]
+        assert np.array_equal(got[b]["n_left"], nl) and np.array_equal(got[b]["n_right"], want[b]["n_right"])
+        for k in range(B):
+            n = nl[k]
+            for key in ("kp_left", "desc_left", "match_idx", "match_pass"):
+                assert np.array_equal(got[b][key][k, :n], want[b][key][k, :n]), (b, k, key)
+            for kind in range(4):
+                m = want[b]["track_n"][kind, k]
+                assert got[b]["track_n"][kind, k] == m
+                assert np.array_equal(got[b]["track_pts"][kind, k, :m], want[b]["track_pts"][kind, k, :m])
+                assert np.array_equal(got[b]["track_keep"][kind, k, :m], want[b]["track_keep"][kind, k, :m])
+    fe.close()

@@ -93,6 +93,9 @@ SIGNATURES = {
     "zs_frontend_timing_collect": (I, [P, C.POINTER(C.c_float), C.POINTER(I)]),
     "zs_frontend_download": (I, [P, C.POINTER(FrontendResults)]),
     "zs_frontend_process_host": (I, [P, P, P, Z, Z, C.POINTER(FrontendResults)]),
+    "zs_frontend_submit_host": (I, [P, P, P, Z, Z, C.POINTER(FrontendResults)]),
+    "zs_frontend_wait": (I, [P]),
+    "zs_frontend_in_flight": (I, [P]),
 }
 
 _lib = None

@@ -34,6 +34,15 @@ struct zs_frontend {
     cudaEvent_t ev[ZS_FE_TIMING_RING][ZS_FE_STAGES + 1];
     // pinned host staging for process_host
     uint8_t* pin; size_t pin_bytes;
+    // pipelined host path (zs_frontend_submit_host / zs_frontend_wait): two in-flight batches.
+    //   copy-in stream:  H2D of batch k+1 into stage[(k+1)&1]      } all three overlap; the compute stream
+    //   compute stream:  unpack + hot path of batch k, snapshot    } is the context's stream
+    //   copy-out stream: D2H of batch k-1 from outbox[(k-1)&1]     }
+    cudaStream_t s_in, s_out;
+    uint8_t* stage[2]; size_t stage_bytes;     // raw host layout (pitch, stride) of 2B images
+    uint8_t* outbox[2]; size_t outbox_bytes;   // snapshot of every result array
+    cudaEvent_t ev_in[2], ev_unpacked[2], ev_run[2], ev_out[2];
+    bool busy[2]; uint64_t submitted, waited;
 };
 
 #define ZS_FE_MARK(i) do { if (fe->timing) ZS_CUDA(cudaEventRecord(fe->ev[fe->t_runs % ZS_FE_TIMING_RING][i], ctx->stream)); } while (0)
@@ -110,6 +119,16 @@ extern "C" void zs_frontend_destroy(zs_frontend* fe)
     if (fe->pyr) zs_pyramid_destroy(fe->pyr);
     if (fe->dev) cudaFree(fe->dev);
     if (fe->pin) cudaFreeHost(fe->pin);
+    if (fe->s_in) {
+        cudaStreamSynchronize(fe->s_in); cudaStreamSynchronize(fe->s_out);
+        for (int b = 0; b < 2; ++b) {
+            if (fe->stage[b]) cudaFree(fe->stage[b]);
+            if (fe->outbox[b]) cudaFree(fe->outbox[b]);
+            cudaEventDestroy(fe->ev_in[b]); cudaEventDestroy(fe->ev_unpacked[b]);
+            cudaEventDestroy(fe->ev_run[b]); cudaEventDestroy(fe->ev_out[b]);
+        }
+        cudaStreamDestroy(fe->s_in); cudaStreamDestroy(fe->s_out);
+    }
     if (fe->ev[0][0])
         for (int r = 0; r < ZS_FE_TIMING_RING; ++r)
             for (int i = 0; i <= ZS_FE_STAGES; ++i) cudaEventDestroy(fe->ev[r][i]);
@@ -249,11 +268,145 @@ extern "C" zs_status zs_frontend_download(zs_frontend* fe, const zs_frontend_res
     return ZS_OK;
 }
 
+extern "C" zs_status zs_frontend_submit_host(zs_frontend* fe, const uint8_t* left, const uint8_t* right, size_t pitch,
+                                             size_t stride, const zs_frontend_results* r);
+extern "C" zs_status zs_frontend_wait(zs_frontend* fe);
+
+// synchronous end-to-end call = one submission through the staged path, waited for at once
 extern "C" zs_status zs_frontend_process_host(zs_frontend* fe, const uint8_t* left, const uint8_t* right, size_t pitch,
                                               size_t stride, const zs_frontend_results* res)
 {
-    zs_status st = zs_frontend_upload(fe, left, right, pitch, stride, 1);
+    ZS_REQUIRE(fe, "null argument");
+    zs_status st;
+    while (fe->submitted > fe->waited)
+        if ((st = zs_frontend_wait(fe)) != ZS_OK) return st;
+    if ((st = zs_frontend_submit_host(fe, left, right, pitch, stride, res)) != ZS_OK) return st;
+    return zs_frontend_wait(fe);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Pipelined host path.  The synchronous zs_frontend_process_host serialises H2D -> compute -> D2H; at C2 the
+// copies cost as much as the kernels.  submit/wait keeps two batches in flight on three streams so that the
+// PCIe transfers of the neighbouring batches hide behind the kernels of the current one.
+// ------------------------------------------------------------------------------------------------------
+
+// staging (raw host layout) -> level-0 interiors of the padded planes; 16 bytes per thread when everything
+// is 16-byte aligned (C2: width 752, pitch 752), bytes otherwise.  grid: (ceil(w/16/128), height, images)
+__global__ void __launch_bounds__(128) k_unpack_level0(const uint8_t* __restrict__ src, size_t pitch, size_t stride,
+                                                       zs_pyr_view v, int first, int vec)
+{
+    const int w = v.w[0];
+    const int y = blockIdx.y, img = blockIdx.z;
+    const uint8_t* s = src + (size_t)img * stride + (size_t)y * pitch;
+    uint8_t* d = v.img[0] + (size_t)zs_slot(first, img, v.slots) * v.slot_stride[0] + (size_t)(v.pad_y + y) * v.pitch[0] + v.pad_x;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (x >= w) return;
+    if (vec && x + 16 <= w) {
+        *(uint4*)(d + x) = __ldcs((const uint4*)(s + x));
+    } else {
+        for (int k = 0; k < 16 && x + k < w; ++k) d[x + k] = s[x + k];
+    }
+}
+
+static zs_status pipeline_init(zs_frontend* fe, size_t stage_bytes)
+{
+    if (!fe->s_in) {
+        ZS_CUDA(cudaStreamCreateWithFlags(&fe->s_in, cudaStreamNonBlocking));
+        ZS_CUDA(cudaStreamCreateWithFlags(&fe->s_out, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            ZS_CUDA(cudaEventCreateWithFlags(&fe->ev_in[b], cudaEventDisableTiming));
+            ZS_CUDA(cudaEventCreateWithFlags(&fe->ev_unpacked[b], cudaEventDisableTiming));
+            ZS_CUDA(cudaEventCreateWithFlags(&fe->ev_run[b], cudaEventDisableTiming));
+            ZS_CUDA(cudaEventCreateWithFlags(&fe->ev_out[b], cudaEventDisableTiming));
+        }
+        fe->outbox_bytes = al256(zs_frontend_d2h_bytes(fe)) + 16 * 256;
+        for (int b = 0; b < 2; ++b) ZS_CUDA(cudaMalloc((void**)&fe->outbox[b], fe->outbox_bytes));
+    }
+    if (stage_bytes > fe->stage_bytes) {
+        ZS_CUDA(cudaStreamSynchronize(fe->s_in));
+        ZS_CUDA(cudaStreamSynchronize(fe->ctx->stream));
+        for (int b = 0; b < 2; ++b) {
+            if (fe->stage[b]) ZS_CUDA(cudaFree(fe->stage[b]));
+            fe->stage[b] = nullptr;
+            ZS_CUDA(cudaMalloc((void**)&fe->stage[b], stage_bytes));
+        }
+        fe->stage_bytes = stage_bytes;
+    }
+    return ZS_OK;
+}
+
+extern "C" zs_status zs_frontend_wait(zs_frontend* fe)
+{
+    ZS_REQUIRE(fe, "null argument");
+    ZS_REQUIRE(fe->waited < fe->submitted, "zs_frontend_wait: nothing in flight");
+    const int b = (int)(fe->waited & 1);
+    ZS_CUDA(cudaEventSynchronize(fe->ev_out[b]));
+    fe->busy[b] = false;
+    fe->waited++;
+    return ZS_OK;
+}
+
+extern "C" int zs_frontend_in_flight(const zs_frontend* fe) { return fe ? (int)(fe->submitted - fe->waited) : 0; }
+
+extern "C" zs_status zs_frontend_submit_host(zs_frontend* fe, const uint8_t* left, const uint8_t* right, size_t pitch,
+                                             size_t stride, const zs_frontend_results* r)
+{
+    ZS_REQUIRE(fe && left && right && r, "null argument");
+    ZS_REQUIRE(r->cap == fe->cap, "results.cap must equal zs_frontend_capacity()");
+    ZS_REQUIRE(pitch >= (size_t)fe->opt.width && stride >= pitch * (size_t)fe->opt.height, "bad pitch/stride");
+    ZS_REQUIRE(fe->submitted - fe->waited < 2, "two batches already in flight: call zs_frontend_wait first");
+    zs_context* ctx = fe->ctx;
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    const size_t B = fe->B, cap = fe->cap;
+    const size_t half = B * stride;
+    zs_status st = pipeline_init(fe, 2 * half);
     if (st != ZS_OK) return st;
+    const int b = (int)(fe->submitted & 1);
+
+    // copy-in stream: the staging buffer is free once the unpack of the batch that last used it has run
+    ZS_CUDA(cudaStreamWaitEvent(fe->s_in, fe->ev_unpacked[b], 0));
+    ZS_CUDA(cudaMemcpyAsync(fe->stage[b], left, half, cudaMemcpyHostToDevice, fe->s_in));
+    ZS_CUDA(cudaMemcpyAsync(fe->stage[b] + half, right, half, cudaMemcpyHostToDevice, fe->s_in));
+    ZS_CUDA(cudaEventRecord(fe->ev_in[b], fe->s_in));
+
+    // compute stream
+    ZS_CUDA(cudaStreamWaitEvent(ctx->stream, fe->ev_in[b], 0));
+    const zs_pyr_view& v = fe->pyr->v;
+    const int vec = (pitch % 16 == 0 && stride % 16 == 0 && ((uintptr_t)fe->stage[b] % 16) == 0 && fe->opt.width % 16 == 0) ? 1 : 0;
+    const dim3 grid(zs_div_up(zs_div_up(fe->opt.width, 16), 128), fe->opt.height, (unsigned)(2 * B));
+    k_unpack_level0<<<grid, 128, 0, ctx->stream>>>(fe->stage[b], pitch, stride, v, 2, vec);   // slots 2..2B+1 = L then R
+    ZS_LAUNCH_CHECK(ctx);
+    ZS_CUDA(cudaEventRecord(fe->ev_unpacked[b], ctx->stream));
     if ((st = zs_frontend_run(fe)) != ZS_OK) return st;
-    return zs_frontend_download(fe, res);
+    // the outbox is free once the D2H of the batch that last used it has finished
+    ZS_CUDA(cudaStreamWaitEvent(ctx->stream, fe->ev_out[b], 0));
+    struct part { const void* src; void* dst; size_t bytes; };
+    const part parts[14] = {
+        { fe->n + 2, r->n_left, sizeof(int) * B }, { fe->n + B + 2, r->n_right, sizeof(int) * B },
+        { fe->xy + 2 * cap * 2, r->kp_left, sizeof(float) * 2 * B * cap }, { fe->xy + (B + 2) * cap * 2, r->kp_right, sizeof(float) * 2 * B * cap },
+        { fe->resp + 2 * cap, r->resp_left, sizeof(float) * B * cap }, { fe->resp + (B + 2) * cap, r->resp_right, sizeof(float) * B * cap },
+        { fe->desc + 2 * cap * 32, r->desc_left, B * cap * 32 }, { fe->desc + (B + 2) * cap * 32, r->desc_right, B * cap * 32 },
+        { fe->m_idx, r->match_idx, sizeof(int) * 2 * B * cap }, { fe->m_dist, r->match_dist, sizeof(float) * 2 * B * cap },
+        { fe->m_pass, r->match_pass, B * cap },
+        { fe->t_pts, r->track_pts, sizeof(float) * 2 * 4 * B * cap }, { fe->t_keep, r->track_keep, 4 * B * cap },
+        { fe->t_n, r->track_n, sizeof(int) * 4 * B } };
+    size_t off[14], o = 0;
+    for (int i = 0; i < 14; ++i) {
+        off[i] = o;
+        if (parts[i].dst) {
+            ZS_CUDA(cudaMemcpyAsync(fe->outbox[b] + o, parts[i].src, parts[i].bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+            o += al256(parts[i].bytes);
+        }
+    }
+    ZS_CUDA(cudaEventRecord(fe->ev_run[b], ctx->stream));
+
+    // copy-out stream
+    ZS_CUDA(cudaStreamWaitEvent(fe->s_out, fe->ev_run[b], 0));
+    for (int i = 0; i < 14; ++i)
+        if (parts[i].dst)
+            ZS_CUDA(cudaMemcpyAsync(parts[i].dst, fe->outbox[b] + off[i], parts[i].bytes, cudaMemcpyDeviceToHost, fe->s_out));
+    ZS_CUDA(cudaEventRecord(fe->ev_out[b], fe->s_out));
+    fe->busy[b] = true;
+    fe->submitted++;
+    return ZS_OK;
 }

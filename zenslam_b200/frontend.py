@@ -35,6 +35,7 @@ class StereoFrontend:
         self.d2h_bytes = int(lib().zs_frontend_d2h_bytes(h))
         B, cap = batch, self.cap
         self._host = None
+        self._submitted = self._waited = 0
         self._shapes = dict(
             n_left=((B,), np.int32), n_right=((B,), np.int32),
             kp_left=((B, cap, 2), np.float32), kp_right=((B, cap, 2), np.float32),
@@ -54,18 +55,20 @@ class StereoFrontend:
         except Exception:
             pass
 
-    def _results(self):
-        """pinned host result buffers (allocated once) + the C struct that points at them"""
+    def _results(self, which: int = 0):
+        """pinned host result buffers (two sets, allocated once) + the C structs that point at them"""
         if self._host is None:
             import torch
-            self._host = {k: torch.empty(s, dtype=getattr(torch, np.dtype(d).name), pin_memory=True)
-                          for k, (s, d) in self._shapes.items()}
-            r = FrontendResults()
-            r.cap = self.cap
-            for k, t in self._host.items():
-                setattr(r, k, t.data_ptr())
-            self._res = r
-        return self._host, self._res
+            self._host, self._res = [], []
+            for _ in range(2):
+                host = {k: torch.empty(s, dtype=getattr(torch, np.dtype(d).name), pin_memory=True)
+                        for k, (s, d) in self._shapes.items()}
+                r = FrontendResults()
+                r.cap = self.cap
+                for k, t in host.items():
+                    setattr(r, k, t.data_ptr())
+                self._host.append(host); self._res.append(r)
+        return self._host[which], self._res[which]
 
     def upload(self, left, right):
         """left/right: (B, H, W) uint8 -- numpy / pinned torch CPU tensor (host) or torch cuda tensor."""
@@ -99,9 +102,33 @@ class StereoFrontend:
 
     def process(self, left, right) -> dict:
         """End-to-end: H2D of the batch, the whole hot path, D2H of every result (synchronous)."""
+        assert self._submitted == self._waited, "process() while submissions are outstanding: call wait() first"
         host, res = self._results()
         lp = left.ctypes.data if isinstance(left, np.ndarray) else left.data_ptr()
         rp = right.ctypes.data if isinstance(right, np.ndarray) else right.data_ptr()
         check(lib().zs_frontend_process_host(self._h, C.c_void_p(lp), C.c_void_p(rp), self.width,
                                              self.width * self.height, C.byref(res)))
         return {k: t.numpy() for k, t in host.items()}
+
+    # ---- pipelined end-to-end path: up to two batches in flight (H2D | kernels | D2H overlap) ----
+    def submit(self, left, right):
+        """enqueue one batch (host buffers, ideally pinned); returns at once.  Call wait() for the results,
+        in submission order; at most two submissions may be outstanding."""
+        host, res = self._results(self._submitted & 1)
+        lp = left.ctypes.data if isinstance(left, np.ndarray) else left.data_ptr()
+        rp = right.ctypes.data if isinstance(right, np.ndarray) else right.data_ptr()
+        check(lib().zs_frontend_submit_host(self._h, C.c_void_p(lp), C.c_void_p(rp), self.width,
+                                            self.width * self.height, C.byref(res)))
+        self._submitted += 1
+
+    def wait(self) -> dict:
+        """block until the oldest outstanding submission has landed in host memory; the returned arrays are
+        views of a pinned buffer that is reused two submissions later"""
+        host, _ = self._results(self._waited & 1)
+        check(lib().zs_frontend_wait(self._h))
+        self._waited += 1
+        return {k: t.numpy() for k, t in host.items()}
+
+    @property
+    def in_flight(self) -> int:
+        return int(lib().zs_frontend_in_flight(self._h))
