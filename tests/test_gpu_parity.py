@@ -372,3 +372,40 @@ def test_klt_multi_job_752(ctx):
         assert np.array_equal(st[j, :n], os_) and np.array_equal(p1[j, :n], o1) and np.array_equal(err[j, :n], oe)
         assert np.array_equal(keep[j, :n].astype(bool), okeep)
         assert okeep.mean() > 0.5 if n > 100 else True
+
+
+def test_l2_tensor_core_ragged_pairs_vs_oracle_and_cuda_core(ctx, monkeypatch):
+    """several pairs of different sizes in one launch (tile tails, pairs with an empty side, counts that are not
+    multiples of the 128-row tiles), checked against the oracle and against the CUDA-core dp4a kernel"""
+    from zenslam_b200.runtime import match_l2_cross, match_l2_knn2
+    rng = np.random.default_rng(99)
+    sizes = [(300, 129), (1, 1), (128, 128), (257, 511), (0, 40), (40, 0), (130, 2)]
+    cap_q, cap_t = 320, 512
+    q = np.zeros((len(sizes), cap_q, 128), np.float32); t = np.zeros((len(sizes), cap_t, 128), np.float32)
+    for k, (a, b) in enumerate(sizes):
+        q[k, :a] = rng.integers(0, 256, (a, 128)); t[k, :b] = rng.integers(0, 256, (b, 128))
+        # garbage beyond the counts must be ignored
+        q[k, a:] = rng.integers(0, 256, (cap_q - a, 128)); t[k, b:] = rng.integers(0, 256, (cap_t - b, 128))
+        if a > 5 and b > 100:
+            t[k, 100] = q[k, 5]; t[k, 20] = q[k, 5]                 # exact duplicates: tie on distance 0
+    nq = np.array([s[0] for s in sizes], np.int32); nt = np.array([s[1] for s in sizes], np.int32)
+    dq, dt, dnq, dnt = dev(ctx, q), dev(ctx, t), dev(ctx, nq), dev(ctx, nt)
+    idx, dist, ps = [x.cpu().numpy() for x in match_l2_knn2(ctx, dq, dnq, dt, dnt, 0.8)]
+    cidx, cdist = [x.cpu().numpy() for x in match_l2_cross(ctx, dq, dnq, dt, dnt)]
+    monkeypatch.setenv("ZS_L2_NO_TENSOR", "1")
+    idx2, dist2, ps2 = [x.cpu().numpy() for x in match_l2_knn2(ctx, dq, dnq, dt, dnt, 0.8)]
+    cidx2, cdist2 = [x.cpu().numpy() for x in match_l2_cross(ctx, dq, dnq, dt, dnt)]
+    monkeypatch.delenv("ZS_L2_NO_TENSOR")
+    for k, (a, b) in enumerate(sizes):
+        assert np.array_equal(idx[k, :a], idx2[k, :a]) and np.array_equal(dist[k, :a], dist2[k, :a]), k
+        assert np.array_equal(ps[k, :a], ps2[k, :a]) and np.array_equal(cidx[k, :a], cidx2[k, :a])
+        assert np.all(idx[k, a:] == -1) and np.all(cidx[k, a:] == -1)
+        if a == 0 or b == 0:
+            assert np.all(idx[k, :a] == -1)
+            continue
+        oi, od = oracle.match_l2_knn2(q[k, :a], t[k, :b])
+        assert np.array_equal(idx[k, :a], oi), k
+        assert np.array_equal(dist[k, :a][oi >= 0], od[oi >= 0])
+        oq, ot, odd = oracle.match_l2_cross(q[k, :a], t[k, :b])
+        keep = np.nonzero(cidx[k, :a] >= 0)[0]
+        assert np.array_equal(keep, oq) and np.array_equal(cidx[k, keep], ot) and np.array_equal(cdist[k, keep], odd)

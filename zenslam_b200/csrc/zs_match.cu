@@ -7,6 +7,10 @@
 // train descriptors in shared memory and every thread sweeps the tile with broadcast 128-bit reads,
 // XOR + POPC, keeping a running top-2.  Train indices are visited in ascending order with strict '<'
 // updates, which is exactly OpenCV's stable tie rule (smaller train index wins).  Integer-ALU bound.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "zs_common.cuh"
 
 #define MATCH_THREADS 128
@@ -213,7 +217,8 @@ extern "C" zs_status zs_match_hamming_cross(zs_context* ctx, const uint8_t* d_q,
 
 // ---- L2 (integer-valued float descriptors) -----------------------------------------------------------
 zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, const uint8_t* t8, const int* nt, int pairs,
-                            int cap_q, int cap_t, int dim, int* idx, int* dist);   // zs_match_l2.cu
+                            int cap_q, int cap_t, int dim, int* idx, int* dist, void* part);   // zs_match_l2.cu
+size_t zs_l2_tensor_part_ints(int pairs, int cap_q, int cap_t);                                  // ints of `part` scratch
 
 static zs_status l2_prepare(zs_context* ctx, const float* d_q, const int* d_nq, size_t q_stride, const float* d_t,
                             const int* d_nt, size_t t_stride, int pairs, int cap_q, int cap_t, int dim, size_t extra_ints,
@@ -243,9 +248,11 @@ static zs_status l2_prepare(zs_context* ctx, const float* d_q, const int* d_nq, 
 }
 
 static zs_status l2_top2(zs_context* ctx, const uint8_t* q8, const int* nq, const uint8_t* t8, const int* nt, int pairs,
-                         int cap_q, int cap_t, int dim, int* idx, int* dist)
+                         int cap_q, int cap_t, int dim, int* idx, int* dist, void* part)
 {
-    if (dim == 128) return zs_l2_tensor_top2(ctx, q8, nq, t8, nt, pairs, cap_q, cap_t, dim, idx, dist);
+    // 128-dim (SIFT) rows take the tcgen05 path; ZS_L2_NO_TENSOR=1 selects the CUDA-core dp4a kernel instead
+    // (used by tools/bench_l2.py and the tests to cross-check the two implementations)
+    if (dim == 128 && !getenv("ZS_L2_NO_TENSOR")) return zs_l2_tensor_top2(ctx, q8, nq, t8, nt, pairs, cap_q, cap_t, dim, idx, dist, part);
     const dim3 grid(zs_div_up(cap_q, MATCH_THREADS), pairs);
 #define L2_CASE(NW)                                                                                          \
     case NW:                                                                                                 \
@@ -283,10 +290,11 @@ extern "C" zs_status zs_match_l2_knn2(zs_context* ctx, const float* d_q, const i
     if (pairs == 0) return ZS_OK;
     uint8_t *q8, *t8; int* ex;
     zs_status st = l2_prepare(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, cap_t, dim,
-                              4 * (size_t)cap_q * pairs, &q8, &t8, &ex);
+                              4 * (size_t)cap_q * pairs + zs_l2_tensor_part_ints(pairs, cap_q, cap_t), &q8, &t8, &ex);
     if (st != ZS_OK) return st;
     int* ti = ex; int* td = ti + 2 * (size_t)cap_q * pairs;
-    st = l2_top2(ctx, q8, d_nq, t8, d_nt, pairs, cap_q, cap_t, dim, ti, td);
+    void* part = td + 2 * (size_t)cap_q * pairs;          // 16-byte aligned: every piece before it is a multiple of 16 bytes
+    st = l2_top2(ctx, q8, d_nq, t8, d_nt, pairs, cap_q, cap_t, dim, ti, td, part);
     if (st != ZS_OK) return st;
     k_knn2_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(ti, td, d_nq, cap_q, ratio, 1, d_idx, d_dist, d_pass);
     ZS_LAUNCH_CHECK(ctx);
@@ -302,13 +310,16 @@ extern "C" zs_status zs_match_l2_cross(zs_context* ctx, const float* d_q, const 
     if (pairs == 0) return ZS_OK;
     uint8_t *q8, *t8; int* ex;
     zs_status st = l2_prepare(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, cap_t, dim,
-                              4 * ((size_t)cap_q + cap_t) * pairs, &q8, &t8, &ex);
+                              4 * ((size_t)cap_q + cap_t) * pairs + std::max(zs_l2_tensor_part_ints(pairs, cap_q, cap_t),
+                                                                             zs_l2_tensor_part_ints(pairs, cap_t, cap_q)),
+                              &q8, &t8, &ex);
     if (st != ZS_OK) return st;
     int* fi = ex; int* fd = fi + 2 * (size_t)cap_q * pairs;
     int* bi = fd + 2 * (size_t)cap_q * pairs; int* bd = bi + 2 * (size_t)cap_t * pairs;
-    st = l2_top2(ctx, q8, d_nq, t8, d_nt, pairs, cap_q, cap_t, dim, fi, fd);
+    void* part = bd + 2 * (size_t)cap_t * pairs;
+    st = l2_top2(ctx, q8, d_nq, t8, d_nt, pairs, cap_q, cap_t, dim, fi, fd, part);
     if (st != ZS_OK) return st;
-    st = l2_top2(ctx, t8, d_nt, q8, d_nq, pairs, cap_t, cap_q, dim, bi, bd);
+    st = l2_top2(ctx, t8, d_nt, q8, d_nq, pairs, cap_t, cap_q, dim, bi, bd, part);
     if (st != ZS_OK) return st;
     k_cross_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(fi, fd, bi, d_nq, cap_q, cap_t, 1, d_idx, d_dist);
     ZS_LAUNCH_CHECK(ctx);

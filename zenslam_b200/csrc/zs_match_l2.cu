@@ -1,12 +1,275 @@
-// zs_match_l2.cu -- L2 top-2 for 128-dim integer-valued descriptors (cv::SIFT) -- placeholder that routes to
-// the exact CUDA-core dp4a kernel until the tcgen05 kernel lands.
+// zs_match_l2.cu -- L2 top-2 for 128-dim integer-valued descriptors (cv::SIFT) on the 5th-gen tensor cores.
+//
+// Reference: cv::BFMatcher(NORM_L2) behind zenslam::matcher for non-binary descriptors
+// (zenslam_core/source/matching/matcher.cpp:60-80, matching_utils.cpp:63-95, keypoint_tracker.cpp:22); SURVEY A.6.
+//
+// cv::SIFT descriptors are integers 0..255 stored as float, so ||a-b||^2 = |a|^2 + |b|^2 - 2 a.b is an exact
+// integer (< 2^24) and the dense contraction A.B^T is the one GEMM-shaped piece of the whole front-end:
+//   * operands are the u8-quantised rows (128 bytes = exactly one 128-byte swizzle row, K-major),
+//   * one CTA = one 128-query x 128-train tile: TMA (SWIZZLE_128B) stages both operand tiles in shared memory,
+//     a single elected thread issues 4 x tcgen05.mma.kind::i8 (M128 N128 K32, u8 x u8 -> s32 accumulators in TMEM),
+//     tcgen05.commit signals an mbarrier, four epilogue warps read their TMEM lane quarter with tcgen05.ld and
+//     keep a stable top-2 per query (ascending train index, strict '<': OpenCV's tie rule),
+//   * the train dimension is split across CTAs (grid = q-tiles x t-splits x pairs) so that even one 2000 x 2000
+//     problem fills the machine; a small merge kernel folds the per-split top-2 in ascending split order.
+// Integer MMA makes exactness a property of the instruction, not of rounding analysis.
+#include <cuda.h>
+
 #include "zs_common.cuh"
 
-zs_status zs_l2_cuda_core_top2(zs_context* ctx, const uint8_t* q8, const int* nq, const uint8_t* t8, const int* nt, int pairs,
-                               int cap_q, int cap_t, int dim, int* idx, int* dist);
+#define L2TC_M 128
+#define L2TC_N 128
+#define L2TC_K 128           // bytes per descriptor row
+#define L2TC_THREADS 192     // warp 0: TMEM alloc + TMA, warp 1: MMA issue, warps 2..5: epilogue
 
-zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, const uint8_t* t8, const int* nt, int pairs,
-                            int cap_q, int cap_t, int dim, int* idx, int* dist)
+typedef CUresult (*zs_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static zs_encode_tiled_fn l2_get_encode_tiled()
 {
-    return zs_l2_cuda_core_top2(ctx, q8, nq, t8, nt, pairs, cap_q, cap_t, dim, idx, dist);
+    static zs_encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (zs_encode_tiled_fn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+__device__ __forceinline__ uint32_t l2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void l2_mbar_init(uint32_t bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void l2_mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l2_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void l2_tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major; 1),
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024), [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t l2_smem_desc(uint32_t addr)
+{
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 (2) at [4,6), a/b format U8 (0) at [7,10)/[10,13),
+// a/b K-major (0) at 15/16, N >> 3 at [17,23), M >> 4 at [24,29)
+#define L2TC_IDESC ((2u << 4) | ((uint32_t)(L2TC_N >> 3) << 17) | ((uint32_t)(L2TC_M >> 4) << 24))
+
+struct l2tc_args {
+    const int* nq; const int* nt;
+    int cap_q, cap_t, splits;
+    int4* part;            // [pairs][cap_q][splits] = (i0, i1, d0, d1); only splits below ceil(nt/128) are written
+};
+
+struct l2_top2 { int d0, d1, i0, i1; };
+__device__ __forceinline__ void l2_top2_update(l2_top2& t, int d, int j)
+{
+    if (d < t.d0) { t.d1 = t.d0; t.i1 = t.i0; t.d0 = d; t.i0 = j; }
+    else if (d < t.d1) { t.d1 = d; t.i1 = j; }
+}
+
+// grid: (ceil(cap_q/128), splits, pairs); dynamic smem: 1024 (alignment slack) + 16 KB A + 16 KB B
+__global__ void __launch_bounds__(L2TC_THREADS) k_l2_tc_tile(const __grid_constant__ CUtensorMap map_q,
+                                                             const __grid_constant__ CUtensorMap map_t, l2tc_args a)
+{
+    extern __shared__ uint8_t l2_smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar[2];       // [0] operands landed, [1] accumulator ready
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_tnorm[L2TC_N];
+    const int pair = blockIdx.z, q0 = blockIdx.x * L2TC_M, t0 = blockIdx.y * L2TC_N;
+    const int n_q = min(a.nq[pair], a.cap_q), n_t = min(a.nt[pair], a.cap_t);
+    if (q0 >= n_q || t0 >= n_t) return;              // uniform per CTA: nothing allocated yet
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* sm = (uint8_t*)(((uintptr_t)l2_smem_raw + 1023) & ~(uintptr_t)1023);     // swizzle atoms are 1024-byte aligned
+    uint8_t* sA = sm; uint8_t* sB = sm + L2TC_M * L2TC_K;
+    const uint32_t bar_full = l2_smem_u32(&s_bar[0]), bar_acc = l2_smem_u32(&s_bar[1]);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(l2_smem_u32(&s_tmem)), "r"(L2TC_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else if (warp == 1 && lane == 0) {
+        l2_mbar_init(bar_full, 1);
+        l2_mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // rows past the pair's own count are other pairs' rows or zero fill: masked in the epilogue
+            l2_mbar_expect_tx(bar_full, (L2TC_M + L2TC_N) * L2TC_K);
+            l2_tma_load_2d(l2_smem_u32(sA), &map_q, 0, pair * a.cap_q + q0, bar_full);
+            l2_tma_load_2d(l2_smem_u32(sB), &map_t, 0, pair * a.cap_t + t0, bar_full);
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            l2_mbar_wait(bar_full, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t da = l2_smem_desc(l2_smem_u32(sA)), db = l2_smem_desc(l2_smem_u32(sB));
+#pragma unroll
+            for (int k = 0; k < L2TC_K / 32; ++k) {
+                // advancing K inside the 128-byte swizzle span = advancing the start address by 32 bytes (>> 4 = 2)
+                const uint64_t dak = da + (uint64_t)(2 * k), dbk = db + (uint64_t)(2 * k);
+                const uint32_t acc = k > 0 ? 1u : 0u;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                             ::"r"(tmem), "l"(dak), "l"(dbk), "r"(L2TC_IDESC), "r"(acc) : "memory");
+            }
+            // commit: arrives on bar_acc when the MMAs above have completed (implies fence::before_thread_sync)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_acc) : "memory");
+        }
+        __syncwarp();
+    } else {
+        // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4
+        const int e = threadIdx.x - 64;                       // 0..127
+        l2_mbar_wait(bar_full, 0);
+        // |b|^2 of train row e and |a|^2 of this thread's query row, straight from the swizzled tiles (a row's
+        // sixteen-byte chunks are permuted inside its own 128 bytes, which a norm does not care about)
+        {
+            const uint4* rb = (const uint4*)(sB + (size_t)e * L2TC_K);
+            int s = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 v = rb[c ^ (e & 7)];
+                s = (int)__dp4a(v.x, v.x, (unsigned)s); s = (int)__dp4a(v.y, v.y, (unsigned)s); s = (int)__dp4a(v.z, v.z, (unsigned)s); s = (int)__dp4a(v.w, v.w, (unsigned)s);
+            }
+            s_tnorm[e] = s;
+        }
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;                  // accumulator row == TMEM lane
+        int qn = 0;
+        {
+            const uint4* ra = (const uint4*)(sA + (size_t)row * L2TC_K);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 v = ra[c ^ (row & 7)];
+                qn = (int)__dp4a(v.x, v.x, (unsigned)qn); qn = (int)__dp4a(v.y, v.y, (unsigned)qn); qn = (int)__dp4a(v.z, v.z, (unsigned)qn); qn = (int)__dp4a(v.w, v.w, (unsigned)qn);
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");       // s_tnorm complete (epilogue warps only)
+        l2_mbar_wait(bar_acc, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        l2_top2 best = { 0x7fffffff, 0x7fffffff, -1, -1 };
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16);
+        const int ncol = min(L2TC_N, n_t - t0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < L2TC_N; c0 += 32) {
+            uint32_t v[32];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                         : "r"(taddr + (uint32_t)c0) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c0 < ncol) {                                  // warp-uniform
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < ncol) l2_top2_update(best, qn + s_tnorm[c0 + j] - 2 * (int)v[j], t0 + c0 + j);
+            }
+        }
+        if (q0 + row < n_q)
+            a.part[((size_t)pair * a.cap_q + q0 + row) * a.splits + blockIdx.y] = make_int4(best.i0, best.i1, best.d0, best.d1);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(L2TC_N) : "memory");
+    }
+}
+
+// fold the per-split top-2 in ascending split (= ascending train index) order; strict '<' keeps OpenCV's tie rule
+__global__ void __launch_bounds__(256) k_l2_tc_merge(l2tc_args a, int* __restrict__ o_idx, int* __restrict__ o_dist)
+{
+    const int pair = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_q = min(a.nq[pair], a.cap_q), n_t = min(a.nt[pair], a.cap_t);
+    if (q >= n_q) return;
+    const int4* p = a.part + ((size_t)pair * a.cap_q + q) * a.splits;
+    l2_top2 best = { 0x7fffffff, 0x7fffffff, -1, -1 };
+    const int valid = (n_t + L2TC_N - 1) / L2TC_N;
+    for (int s = 0; s < valid; ++s) {
+        const int4 v = p[s];
+        if (v.x >= 0) l2_top2_update(best, v.z, v.x);
+        if (v.y >= 0) l2_top2_update(best, v.w, v.y);
+    }
+    const size_t o = 2 * ((size_t)pair * a.cap_q + q);
+    o_idx[o] = best.i0; o_idx[o + 1] = best.i1; o_dist[o] = best.d0; o_dist[o + 1] = best.d1;
+}
+
+static zs_status l2_make_map(CUtensorMap* m, const uint8_t* base, size_t rows)
+{
+    zs_encode_tiled_fn enc = l2_get_encode_tiled();
+    if (!enc) { zs_set_error("cuTensorMapEncodeTiled is not available from this driver"); return ZS_ERR_CUDA; }
+    const cuuint64_t dims[2] = { L2TC_K, (cuuint64_t)rows };
+    const cuuint64_t strides[1] = { L2TC_K };
+    const cuuint32_t box[2] = { L2TC_K, L2TC_M }, es[2] = { 1, 1 };
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { zs_set_error("cuTensorMapEncodeTiled(L2 descriptors) failed: %d", (int)r); return ZS_ERR_CUDA; }
+    return ZS_OK;
+}
+
+// q8 / t8: [pairs][cap][128] u8 (16-byte aligned); idx / dist: [pairs][cap_q][2] (squared distances as int);
+// part: zs_l2_tensor_part_ints() ints of scratch for the per-split partial top-2
+zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, const uint8_t* t8, const int* nt, int pairs,
+                            int cap_q, int cap_t, int dim, int* idx, int* dist, void* part)
+{
+    ZS_REQUIRE(dim == L2TC_K, "tensor-core L2 path needs 128-dimensional descriptors");
+    ZS_REQUIRE(((uintptr_t)q8 % 16) == 0 && ((uintptr_t)t8 % 16) == 0, "descriptor arrays must be 16-byte aligned");
+    CUtensorMap mq, mt;
+    zs_status st = l2_make_map(&mq, q8, (size_t)pairs * cap_q);
+    if (st != ZS_OK) return st;
+    if ((st = l2_make_map(&mt, t8, (size_t)pairs * cap_t)) != ZS_OK) return st;
+    l2tc_args a;
+    a.nq = nq; a.nt = nt; a.cap_q = cap_q; a.cap_t = cap_t; a.splits = zs_div_up(cap_t, L2TC_N);
+    ZS_REQUIRE(part && ((uintptr_t)part % 16) == 0, "partial top-2 scratch must be 16-byte aligned");
+    a.part = (int4*)part;                                   // zs_l2_tensor_part_ints() ints of caller scratch
+    const size_t smem = 1024 + (size_t)(L2TC_M + L2TC_N) * L2TC_K;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZS_CUDA(cudaFuncSetAttribute(k_l2_tc_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_l2_tc_tile<<<dim3(zs_div_up(cap_q, L2TC_M), a.splits, pairs), L2TC_THREADS, smem, ctx->stream>>>(mq, mt, a);
+    ZS_LAUNCH_CHECK(ctx);
+    // unmatched rows keep (-1, INT_MAX) like the CUDA-core kernel; rows >= nq are not touched
+    k_l2_tc_merge<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(a, idx, dist);
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}
+
+size_t zs_l2_tensor_part_ints(int pairs, int cap_q, int cap_t)
+{
+    return 4 * (size_t)pairs * cap_q * zs_div_up(cap_t, L2TC_N);
 }
