@@ -26,9 +26,10 @@ struct zs_frontend {
     float* xy; float* resp; int* n; uint8_t* desc;       // [slots][cap]
     int* m_idx; float* m_dist; uint8_t* m_pass;          // [B][cap]
     int* job_prev; int* job_next; int* job_row;          // [4B]
+    int* job_next2; int* job_out2; int* job_prev_all;    // [4B] template sharing (see zs_frontend_create)
     float* t_pts; uint8_t* t_status; float* t_err; uint8_t* t_keep;   // [4B][cap]
     int* t_n;                                            // [4B] points tracked per job
-    bool have_carry;
+    bool have_carry; bool share;
     // optional per-stage device timing: a ring of event sets, one set per zs_frontend_run
     int timing; int t_runs;
     cudaEvent_t ev[ZS_FE_TIMING_RING][ZS_FE_STAGES + 1];
@@ -78,6 +79,7 @@ extern "C" zs_status zs_frontend_create(zs_context* ctx, const zs_frontend_optio
     CARVE(xy, float, 2 * S * cap) CARVE(resp, float, S * cap) CARVE(n, int, S) CARVE(desc, uint8_t, S * cap * 32)
     CARVE(m_idx, int, 2 * B * cap) CARVE(m_dist, float, 2 * B * cap) CARVE(m_pass, uint8_t, B * cap)
     CARVE(job_prev, int, J) CARVE(job_next, int, J) CARVE(job_row, int, J)
+    CARVE(job_next2, int, J) CARVE(job_out2, int, J) CARVE(job_prev_all, int, J)
     CARVE(t_pts, float, 2 * J * cap) CARVE(t_status, uint8_t, J * cap) CARVE(t_err, float, J * cap)
     CARVE(t_keep, uint8_t, J * cap) CARVE(t_n, int, J)
 #undef CARVE
@@ -88,11 +90,14 @@ extern "C" zs_status zs_frontend_create(zs_context* ctx, const zs_frontend_optio
 #define BIND(field, type) fe->field = (type*)(fe->dev + o_##field);
     BIND(raw_xy, float) BIND(raw_resp, float) BIND(raw_n, int) BIND(xy, float) BIND(resp, float) BIND(n, int)
     BIND(desc, uint8_t) BIND(m_idx, int) BIND(m_dist, float) BIND(m_pass, uint8_t) BIND(job_prev, int) BIND(job_next, int)
-    BIND(job_row, int) BIND(t_pts, float) BIND(t_status, uint8_t) BIND(t_err, float) BIND(t_keep, uint8_t) BIND(t_n, int)
+    BIND(job_row, int) BIND(job_next2, int) BIND(job_out2, int) BIND(job_prev_all, int) BIND(t_pts, float) BIND(t_status, uint8_t) BIND(t_err, float) BIND(t_keep, uint8_t) BIND(t_n, int)
 #undef BIND
-    // job tables: kind-major [4][B]
-    int* h = (int*)malloc(sizeof(int) * 3 * J);
-    int *hp = h, *hn = h + J, *hr = h + 2 * J;
+    // job tables: kind-major [4][B].  The stereo job of frame k (L_k -> R_k from the keypoints of L_k) and the temporal
+    // job of frame k+1 (L_k -> L_{k+1} from the same keypoints) share their forward template: the temporal job is
+    // folded into the stereo job as its second target (job_next2 / job_out2) and is itself skipped (prev slot -1).
+    // Only the temporal jobs of frame 0, whose source is the carried frame, run on their own.
+    int* h = (int*)malloc(sizeof(int) * 6 * J);
+    int *hp = h, *hn = h + J, *hr = h + 2 * J, *hn2 = h + 3 * J, *ho2 = h + 4 * J, *hpa = h + 5 * J;
     for (size_t k = 0; k < B; ++k) {
         const int L = 2 + (int)k, R = (int)B + 2 + (int)k;
         const int Lp = k == 0 ? 0 : L - 1, Rp = k == 0 ? 1 : R - 1;
@@ -100,13 +105,22 @@ extern "C" zs_status zs_frontend_create(zs_context* ctx, const zs_frontend_optio
         hp[1 * B + k] = Rp; hn[1 * B + k] = R; hr[1 * B + k] = Rp;      // temporal right
         hp[2 * B + k] = L;  hn[2 * B + k] = R; hr[2 * B + k] = L;       // stereo L -> R
         hp[3 * B + k] = R;  hn[3 * B + k] = L; hr[3 * B + k] = R;       // stereo R -> L
+        for (int kind = 0; kind < 4; ++kind) { hn2[kind * B + k] = -1; ho2[kind * B + k] = -1; hpa[kind * B + k] = hp[kind * B + k]; }
     }
-    e = cudaMemcpyAsync(fe->job_prev, hp, sizeof(int) * J, cudaMemcpyHostToDevice, ctx->stream);
+    for (size_t k = 0; k + 1 < B; ++k) {
+        hn2[2 * B + k] = 2 + (int)k + 1;          ho2[2 * B + k] = (int)(0 * B + k + 1);   hp[0 * B + k + 1] = -1;
+        hn2[3 * B + k] = (int)B + 2 + (int)k + 1; ho2[3 * B + k] = (int)(1 * B + k + 1);   hp[1 * B + k + 1] = -1;
+    }
+    const bool share = !getenv("ZS_KLT_NO_SHARE") && opt->klt_win_w == 31 && opt->klt_win_h == 31 && fe->pyr->v.tmaps;
+    e = cudaMemcpyAsync(fe->job_prev, share ? hp : hpa, sizeof(int) * J, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(fe->job_next, hn, sizeof(int) * J, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(fe->job_row, hr, sizeof(int) * J, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(fe->job_next2, hn2, sizeof(int) * J, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(fe->job_out2, ho2, sizeof(int) * J, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     free(h);
     if (e != cudaSuccess) { zs_frontend_destroy(fe); return zs_cuda_fail(e, "frontend job tables", __FILE__, __LINE__); }
+    fe->share = share;
     *out = fe;
     return ZS_OK;
 }
@@ -194,7 +208,8 @@ extern "C" zs_status zs_frontend_run(zs_frontend* fe)
     prm.win_w = o.klt_win_w; prm.win_h = o.klt_win_h; prm.max_level = o.klt_max_level; prm.max_iters = o.max_iters;
     prm.epsilon = o.epsilon; prm.flags = ZS_LK_GET_MIN_EIGENVALS; prm.min_eig_threshold = o.min_eig_threshold;
     if ((st = zs_klt_launch(ctx, fe->pyr, fe->job_prev, fe->job_next, fe->xy, fe->t_pts, fe->n, fe->job_row, 4 * B, cap, &prm,
-                            fe->t_status, fe->t_err, 1, o.klt_threshold, fe->t_keep)) != ZS_OK) return st;
+                            fe->t_status, fe->t_err, 1, o.klt_threshold, fe->t_keep, fe->share ? fe->job_next2 : nullptr,
+                            fe->share ? fe->job_out2 : nullptr)) != ZS_OK) return st;
     k_gather_counts<<<zs_div_up(4 * B, 256), 256, 0, ctx->stream>>>(fe->n, fe->job_row, 4 * B, fe->t_n);
     ZS_LAUNCH_CHECK(ctx);
     ZS_FE_MARK(5);

@@ -8,6 +8,7 @@
 // One warp per feature; all pyramid levels and all Gauss-Newton iterations run inside the kernel (no
 // per-level launch).  The template patch lives in shared memory; the warp sweeps the window with its 32
 // lanes, control flow (early exits, iteration counts) is warp-uniform so divergence is across warps only.
+#include <math.h>
 #include <stdlib.h>
 
 #include "zs_common.cuh"
@@ -19,8 +20,12 @@ struct klt_args {
     const int* prev_slot; const int* next_slot;
     const float2* prev_pts; float2* next_pts; const int* count;
     const int* pts_row;      // optional: row of prev_pts / count each job reads (null: row = job)
+    // optional second target per job (template sharing): job j also tracks its points into slot next_slot2[j] and
+    // writes those results to the rows of job out_job2[j] (< 0: none).  A job whose prev_slot is < 0 is skipped.
+    const int* next_slot2; const int* out_job2;
     int cap, win_w, win_h, max_level, max_iters, flags;
     double eps2, min_eig;
+    float eps2_lo, eps2_hi;  // float band around eps2 inside which the double comparison is evaluated
     uint8_t* status; float* err;
     int fb; double fb_thr; uint8_t* keep;
 };
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(KLT2_WARPS * 32) k_klt_track_v2(klt_args a)
 
 
 // ------------------------------------------------------------------------------------------------------
-// v3: TMA-staged patches.  Per warp, one elected lane asks the TMA unit for the patch of J (and, once per
+// v3/v4: TMA-staged patches.  Per warp, one elected lane asks the TMA unit for the patch of J (and, once per
 // level, the patch of I plus the (dx,dy) patch) around the window's integer origin; completion is signalled on
 // an mbarrier and no LSU instruction or register is spent on the gather.  TMA box origins must be 16-byte
 // aligned (an unaligned origin faults with "illegal instruction" on sm_100a), so the boxes are 48 bytes /
@@ -434,16 +439,20 @@ __device__ __forceinline__ int sample8(int wt, int wb, const row8& a, const row8
     return acc >> 9;
 }
 
+// Up to two targets per source point: the per-level template (I patch, gradients, A matrix) depends only on the
+// source image and point, so jobs that track the SAME keypoints of the SAME image into two different images
+// (stereo L->R of frame k and temporal L_k -> L_{k+1}) share it and only the Gauss-Newton loops run twice.
+struct lk_state { float outx, outy; int status; };
+
 template <int WW, int WH>
-__device__ __forceinline__ lk_result lk_track_point_v3(const klt_args& a, int slot_i, int slot_j, float2 prev, float2 init,
-                                                        bool use_init, int lane, uint8_t* sJ, uint8_t* sD, uint32_t bar,
-                                                        uint32_t& parity)
+__device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i, int slot_j0, int slot_j1, int ntgt,
+                                                  float2 prev, float2 init, bool use_init, int lane, uint8_t* sJ, uint8_t* sD,
+                                                  uint32_t bar, uint32_t& parity, lk_state& t0, lk_state& t1, float& err)
 {
     const zs_pyr_view& v = a.v;
     const float hwx = (float)(WW - 1) * 0.5f, hwy = (float)(WH - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (float)(1 << 20);
-    lk_result r; r.status = 1; r.err = 0.f; r.x = 0.f; r.y = 0.f;
-    float outx = 0.f, outy = 0.f;
+    t0.status = 1; t1.status = 1; t0.outx = t0.outy = t1.outx = t1.outy = 0.f; err = 0.f;
     const int top = min(a.max_level, v.levels - 1);
     const int k = lane & 3, g = lane >> 2;
     const uint32_t sJ_a = smem_u32(sJ), sD_a = smem_u32(sD);
@@ -455,17 +464,19 @@ __device__ __forceinline__ lk_result lk_track_point_v3(const klt_args& a, int sl
         const int cols = v.w[level], rows = v.h[level];
         const float scale = 1.f / (float)(1 << level);
         float px = __fmul_rn(prev.x, scale), py = __fmul_rn(prev.y, scale);
-        float nx, ny;
         if (level == top) {
-            if (use_init) { nx = __fmul_rn(init.x, scale); ny = __fmul_rn(init.y, scale); }
-            else { nx = px; ny = py; }
-        } else { nx = __fmul_rn(outx, 2.f); ny = __fmul_rn(outy, 2.f); }
-        outx = nx; outy = ny;
+            if (use_init) { t0.outx = __fmul_rn(init.x, scale); t0.outy = __fmul_rn(init.y, scale); }
+            else { t0.outx = px; t0.outy = py; }
+            t1.outx = px; t1.outy = py;                       // second targets never carry an initial flow
+        } else {
+            t0.outx = __fmul_rn(t0.outx, 2.f); t0.outy = __fmul_rn(t0.outy, 2.f);
+            t1.outx = __fmul_rn(t1.outx, 2.f); t1.outy = __fmul_rn(t1.outy, 2.f);
+        }
 
         px = __fsub_rn(px, hwx); py = __fsub_rn(py, hwy);
         const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
         if (ipx < -WW || ipx >= cols || ipy < -WH || ipy >= rows) {
-            if (level == 0) { r.status = 0; r.err = 0.f; }
+            if (level == 0) { t0.status = 0; t1.status = 0; err = 0.f; }
             continue;
         }
         int w00, w01, w10, w11;
@@ -527,74 +538,93 @@ __device__ __forceinline__ lk_result lk_track_point_v3(const klt_args& a, int sl
         const float dA = __fsub_rn(A11, A22);
         const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
         const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * WW * WH));
-        if (a.flags & ZS_LK_GET_MIN_EIGENVALS) r.err = minEig;
+        if (a.flags & ZS_LK_GET_MIN_EIGENVALS) err = minEig;
         if ((double)minEig < a.min_eig || D < 1.1920929e-07f) {
-            if (level == 0) r.status = 0;
+            if (level == 0) { t0.status = 0; t1.status = 0; }
             continue;
         }
         D = __fdiv_rn(1.f, D);
-        nx = __fsub_rn(nx, hwx); ny = __fsub_rn(ny, hwy);
-        float pdx = 0.f, pdy = 0.f;
-        int cur_x0 = 0x7fffffff, cur_y = 0x7fffffff;       // origin of the J patch now in shared memory
-        for (int it = 0; it < a.max_iters; ++it) {
-            const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
-            if (inx < -WW || inx >= cols || iny < -WH || iny >= rows) {
-                if (level == 0) r.status = 0;
-                break;
-            }
-            const int jx = v.pad_x + inx, jy = v.pad_y + iny;
-            if ((jx & ~15) != cur_x0 || jy != cur_y) {
-                __syncwarp();                                  // every lane is done with the previous patch
-                cur_x0 = jx & ~15; cur_y = jy;
-                if (lane == 0) {
-                    mbar_expect_tx(bar, 48 * 32);
-                    tma_load_3d(sJ_a, maps + (size_t)(2 * level) * 128, cur_x0, cur_y, slot_j, bar);
+
+        // ---- Gauss-Newton loops, one per target (a single copy of the loop body: the state is swapped in and out)
+#pragma unroll 1
+        for (int t = 0; t < ntgt; ++t) {
+            const int slot_j = t ? slot_j1 : slot_j0;
+            float outx = t ? t1.outx : t0.outx, outy = t ? t1.outy : t0.outy;
+            int status = 1;
+            float nx = __fsub_rn(outx, hwx), ny = __fsub_rn(outy, hwy);
+            float pdx = 0.f, pdy = 0.f;
+            int cur_x0 = 0x7fffffff, cur_y = 0x7fffffff;       // origin of the J patch now in shared memory
+            for (int it = 0; it < a.max_iters; ++it) {
+                const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
+                if (inx < -WW || inx >= cols || iny < -WH || iny >= rows) {
+                    status = 0;
+                    break;
                 }
-                mbar_wait(bar, parity); parity ^= 1;
-            }
-            lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
-            const int wt = pack_s16x2(w00, w01), wb = pack_s16x2(w10, w11);
-            const uint32_t* jw = jbase + ((jx & 15) >> 2);
-            const int sh = (jx & 3) * 8;
-            int pb1 = 0, pb2 = 0;
+                const int jx = v.pad_x + inx, jy = v.pad_y + iny;
+                if ((jx & ~15) != cur_x0 || jy != cur_y) {
+                    __syncwarp();                                  // every lane is done with the previous patch
+                    cur_x0 = jx & ~15; cur_y = jy;
+                    if (lane == 0) {
+                        mbar_expect_tx(bar, 48 * 32);
+                        tma_load_3d(sJ_a, maps + (size_t)(2 * level) * 128, cur_x0, cur_y, slot_j, bar);
+                    }
+                    mbar_wait(bar, parity); parity ^= 1;
+                }
+                lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
+                const int wt = pack_s16x2(w00, w01), wb = pack_s16x2(w10, w11);
+                const uint32_t* jw = jbase + ((jx & 15) >> 2);
+                const int sh = (jx & 3) * 8;
+                int pb1 = 0, pb2 = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const row8 ra = load_row8(jw + j * 8 * KLT3_JP, sh), rb = load_row8(jw + (j * 8 + 1) * KLT3_JP, sh);
-                int jv;
-                jv = sample8<0>(wt, wb, ra, rb); pb1 += jv * Ix[j][0]; pb2 += jv * Iy[j][0];
-                jv = sample8<1>(wt, wb, ra, rb); pb1 += jv * Ix[j][1]; pb2 += jv * Iy[j][1];
-                jv = sample8<2>(wt, wb, ra, rb); pb1 += jv * Ix[j][2]; pb2 += jv * Iy[j][2];
-                jv = sample8<3>(wt, wb, ra, rb); pb1 += jv * Ix[j][3]; pb2 += jv * Iy[j][3];
-                jv = sample8<4>(wt, wb, ra, rb); pb1 += jv * Ix[j][4]; pb2 += jv * Iy[j][4];
-                jv = sample8<5>(wt, wb, ra, rb); pb1 += jv * Ix[j][5]; pb2 += jv * Iy[j][5];
-                jv = sample8<6>(wt, wb, ra, rb); pb1 += jv * Ix[j][6]; pb2 += jv * Iy[j][6];
-                jv = sample8<7>(wt, wb, ra, rb); pb1 += jv * Ix[j][7]; pb2 += jv * Iy[j][7];
+                for (int j = 0; j < 4; ++j) {
+                    const row8 ra = load_row8(jw + j * 8 * KLT3_JP, sh), rb = load_row8(jw + (j * 8 + 1) * KLT3_JP, sh);
+                    int jv;
+                    jv = sample8<0>(wt, wb, ra, rb); pb1 += jv * Ix[j][0]; pb2 += jv * Iy[j][0];
+                    jv = sample8<1>(wt, wb, ra, rb); pb1 += jv * Ix[j][1]; pb2 += jv * Iy[j][1];
+                    jv = sample8<2>(wt, wb, ra, rb); pb1 += jv * Ix[j][2]; pb2 += jv * Iy[j][2];
+                    jv = sample8<3>(wt, wb, ra, rb); pb1 += jv * Ix[j][3]; pb2 += jv * Iy[j][3];
+                    jv = sample8<4>(wt, wb, ra, rb); pb1 += jv * Ix[j][4]; pb2 += jv * Iy[j][4];
+                    jv = sample8<5>(wt, wb, ra, rb); pb1 += jv * Ix[j][5]; pb2 += jv * Iy[j][5];
+                    jv = sample8<6>(wt, wb, ra, rb); pb1 += jv * Ix[j][6]; pb2 += jv * Iy[j][6];
+                    jv = sample8<7>(wt, wb, ra, rb); pb1 += jv * Ix[j][7]; pb2 += jv * Iy[j][7];
+                }
+                const long long sb1 = warp_sum_exact(pb1) - sc1, sb2 = warp_sum_exact(pb2) - sc2;
+                const float b1 = __fmul_rn(__ll2float_rn(sb1), FLT_SCALE), b2 = __fmul_rn(__ll2float_rn(sb2), FLT_SCALE);
+                const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+                const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+                nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
+                outx = __fadd_rn(nx, hwx); outy = __fadd_rn(ny, hwy);
+                // OpenCV: (double)dx*dx + (double)dy*dy <= eps^2.  A float estimate decides unless it falls inside a
+                // +-1e-6 relative band around eps^2 (its own error is < 2e-7), where the exact double form is evaluated.
+                const float ss = fmaf(dx, dx, __fmul_rn(dy, dy));
+                bool conv = ss <= a.eps2_lo;
+                if (!conv && ss < a.eps2_hi) conv = (double)dx * (double)dx + (double)dy * (double)dy <= a.eps2;
+                if (conv) break;
+                // OpenCV: fabs(dx + pdx) < 0.01 && fabs(dy + pdy) < 0.01 in double; for a float v, v < 0.01 <=> v <= 0.01f
+                // (0.01f = 0.00999999978 is the largest float below 0.01)
+                if (it > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f) {
+                    outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f)); outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
+                    break;
+                }
+                pdx = dx; pdy = dy;
             }
-            const long long sb1 = warp_sum_exact(pb1) - sc1, sb2 = warp_sum_exact(pb2) - sc2;
-            const float b1 = __fmul_rn(__ll2float_rn(sb1), FLT_SCALE), b2 = __fmul_rn(__ll2float_rn(sb2), FLT_SCALE);
-            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
-            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
-            nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
-            outx = __fadd_rn(nx, hwx); outy = __fadd_rn(ny, hwy);
-            if ((double)dx * (double)dx + (double)dy * (double)dy <= a.eps2) break;
-            if (it > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
-                outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f)); outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
-                break;
-            }
-            pdx = dx; pdy = dy;
+            if (t) { t1.outx = outx; t1.outy = outy; if (level == 0 && !status) t1.status = 0; }
+            else { t0.outx = outx; t0.outy = outy; if (level == 0 && !status) t0.status = 0; }
         }
     }
-    r.x = outx; r.y = outy;
-    return r;
 }
 
 // grid: (ceil(cap / KLT3_WARPS), jobs); dynamic smem = KLT3_WARPS * KLT3_WARP_BYTES
+// passes: 0 = forward (one or two targets), 1 = backward of target 0, 2 = backward of target 1 (fb only); one
+// inlined instance of the tracker serves all passes (keeps the code inside the instruction cache).
 template <int WW, int WH>
-__global__ void __launch_bounds__(KLT3_WARPS * 32) k_klt_track_v3(klt_args a)
+__global__ void __launch_bounds__(KLT3_WARPS * 32) k_klt_track_v4(klt_args a)
 {
     extern __shared__ __align__(128) uint8_t smem3[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int job = blockIdx.y;
+    const int slot_src = a.prev_slot[job];
+    if (slot_src < 0) return;                                  // job folded into another job's second target
     const int i = blockIdx.x * KLT3_WARPS + warp;
     const int in_row = a.pts_row ? a.pts_row[job] : job;
     if (i >= min(a.count[in_row], a.cap)) return;
@@ -610,31 +640,48 @@ __global__ void __launch_bounds__(KLT3_WARPS * 32) k_klt_track_v3(klt_args a)
     ((uint32_t*)(sD + 144 * 32))[lane] = 0; ((uint32_t*)(sD + 144 * 32))[lane + 4] = 0;
     __syncwarp();
     uint32_t parity = 0;
-    const size_t o = (size_t)job * a.cap + i;
-    const float2 p0 = a.prev_pts[(size_t)in_row * a.cap + i];
-    bool use_init = (a.flags & ZS_LK_USE_INITIAL_FLOW) != 0;
-    float2 init = make_float2(0.f, 0.f);
-    if (use_init) init = a.next_pts[o];
-    int si = a.prev_slot[job], sj = a.next_slot[job];
-    float2 from = p0;
-    int fwd_status = 1;
+    // Per-warp bookkeeping lives in the 128-byte scratch line behind the barrier (warp-uniform values, written by
+    // every lane with the same data, read back as broadcasts): it would otherwise sit in registers across the
+    // whole inlined tracker and push the kernel past 128 registers (4 CTAs per SM).
+    //   w[4] slot_src  w[5] slot_t0  w[6] slot_t1  w[7] ntgt  w[8..9] p0  w[10..12] f0  w[13..15] f1  w[16] job1
+    volatile int* w = (volatile int*)(sD + KLT3_SD_BYTES);
+    volatile float* wf = (volatile float*)w;
+    {
+        const int job1 = a.out_job2 ? a.out_job2[job] : -1;
+        w[4] = slot_src; w[5] = a.next_slot[job]; w[6] = job1 >= 0 ? a.next_slot2[job] : -1; w[7] = job1 >= 0 ? 2 : 1; w[16] = job1;
+        const float2 p0 = a.prev_pts[(size_t)in_row * a.cap + i];
+        wf[8] = p0.x; wf[9] = p0.y;
+    }
+    __syncwarp();
+    const bool use_init = (a.flags & ZS_LK_USE_INITIAL_FLOW) != 0;
+    const int passes = a.fb ? 1 + w[7] : 1;
 #pragma unroll 1
-    for (int pass = 0; pass < (a.fb ? 2 : 1); ++pass) {
-        const lk_result f = lk_track_point_v3<WW, WH>(a, si, sj, from, init, use_init, lane, sJ, sD, bar, parity);
+    for (int pass = 0; pass < passes; ++pass) {
+        // pass 0: forward from p0 (one or two targets); pass 1 / 2: backward of target 0 / 1 from its forward result,
+        // images swapped, no initial flow (keypoint_tracker.cpp:156-170)
+        const int si = pass == 0 ? w[4] : w[4 + pass], sj0 = pass == 0 ? w[5] : w[4], sj1 = w[6];
+        const float2 from = make_float2(wf[pass == 0 ? 8 : 7 + 3 * pass], wf[pass == 0 ? 9 : 8 + 3 * pass]);
+        float2 init = make_float2(0.f, 0.f);
+        const bool ui = use_init && pass == 0;
+        if (ui) init = a.next_pts[(size_t)job * a.cap + i];
+        lk_state r0, r1; float err;
+        lk_track_point_v4<WW, WH>(a, si, sj0, sj1, pass == 0 ? w[7] : 1, from, init, ui, lane, sJ, sD, bar, parity, r0, r1, err);
+        const int job1 = w[16];
+        const size_t o0 = (size_t)job * a.cap + i, o1 = (size_t)(job1 >= 0 ? job1 : job) * a.cap + i;
         if (pass == 0) {
+            __syncwarp();
+            wf[10] = r0.outx; wf[11] = r0.outy; w[12] = r0.status; wf[13] = r1.outx; wf[14] = r1.outy; w[15] = r1.status;
+            __syncwarp();
             if (lane == 0) {
-                a.next_pts[o] = make_float2(f.x, f.y);
-                a.status[o] = (uint8_t)f.status;
-                a.err[o] = f.err;
+                a.next_pts[o0] = make_float2(r0.outx, r0.outy); a.status[o0] = (uint8_t)r0.status; a.err[o0] = err;
+                if (job1 >= 0) { a.next_pts[o1] = make_float2(r1.outx, r1.outy); a.status[o1] = (uint8_t)r1.status; a.err[o1] = err; }
             }
-            fwd_status = f.status;
-            from = make_float2(f.x, f.y);
-            const int t = si; si = sj; sj = t;
-            use_init = false;
         } else if (lane == 0) {
-            const float dx = __fsub_rn(f.x, p0.x), dy = __fsub_rn(f.y, p0.y);
+            // cv::norm(Point2f) -> sqrt((double)dx*dx + (double)dy*dy) < klt_threshold (keypoint_tracker.cpp:180)
+            const float dx = __fsub_rn(r0.outx, wf[8]), dy = __fsub_rn(r0.outy, wf[9]);
             const double nrm = sqrt((double)dx * (double)dx + (double)dy * (double)dy);
-            a.keep[o] = (uint8_t)(fwd_status && f.status && nrm < a.fb_thr);
+            const int fs = w[9 + 3 * pass];
+            a.keep[pass == 1 ? o0 : o1] = (uint8_t)(fs && r0.status && nrm < a.fb_thr);
         }
     }
 }
@@ -679,7 +726,8 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) k_klt_track(klt_args a)
 
 zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_slot, const int* d_next_slot,
                         const float* d_prev_pts, float* d_next_pts, const int* d_count, const int* d_pts_row, int jobs, int cap,
-                        const zs_lk_params* prm, uint8_t* d_status, float* d_err, int fb, double fb_thr, uint8_t* d_keep)
+                        const zs_lk_params* prm, uint8_t* d_status, float* d_err, int fb, double fb_thr, uint8_t* d_keep,
+                        const int* d_next_slot2, const int* d_out_job2)
 {
     ZS_REQUIRE(ctx && p && d_prev_slot && d_next_slot && d_prev_pts && d_next_pts && d_count && prm && d_status && d_err,
                "null argument");
@@ -697,13 +745,20 @@ zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_
     double eps = prm->epsilon; eps = eps < 0 ? 0 : eps > 10. ? 10. : eps;   // cv: clamp(epsilon, 0, 10)
     a.max_iters = mi; a.eps2 = eps * eps; a.flags = prm->flags; a.min_eig = prm->min_eig_threshold;
     a.status = d_status; a.err = d_err; a.fb = fb; a.fb_thr = fb_thr; a.keep = d_keep;
+    a.next_slot2 = d_next_slot2; a.out_job2 = d_out_job2;
+    if (a.eps2 < 1e-30) { a.eps2_lo = -1.f; a.eps2_hi = 3.0e38f; }         // always take the exact comparison
+    else {
+        a.eps2_lo = nextafterf((float)(a.eps2 * (1.0 - 1e-6)), 0.f);
+        a.eps2_hi = nextafterf((float)(a.eps2 * (1.0 + 1e-6)), 3.0e38f);
+    }
     // TMA-staged kernel for the reference's default window
     if (a.win_w == 31 && a.win_h == 31 && a.v.tmaps && !getenv("ZS_KLT_NO_TMA")) {
         const size_t smem3 = (size_t)KLT3_WARPS * KLT3_WARP_BYTES;
-        k_klt_track_v3<31, 31><<<dim3(zs_div_up(cap, KLT3_WARPS), jobs), KLT3_WARPS * 32, smem3, ctx->stream>>>(a);
+        k_klt_track_v4<31, 31><<<dim3(zs_div_up(cap, KLT3_WARPS), jobs), KLT3_WARPS * 32, smem3, ctx->stream>>>(a);
         ZS_LAUNCH_CHECK(ctx);
         return ZS_OK;
     }
+    ZS_REQUIRE(!d_out_job2, "second targets need the TMA-staged 31x31 kernel");
     // specialised register-template kernels for the common window sizes
     {
         const dim3 grid2(zs_div_up(cap, KLT2_WARPS), jobs);
@@ -736,7 +791,7 @@ extern "C" zs_status zs_klt_track(zs_context* ctx, const zs_pyramid* p, const in
                                   const zs_lk_params* params, uint8_t* d_status, float* d_err)
 {
     return zs_klt_launch(ctx, p, d_prev_slot, d_next_slot, d_prev_pts, d_next_pts, d_count, nullptr, jobs, cap, params,
-                         d_status, d_err, 0, 0.0, nullptr);
+                         d_status, d_err, 0, 0.0, nullptr, nullptr, nullptr);
 }
 
 extern "C" zs_status zs_klt_track_fb(zs_context* ctx, const zs_pyramid* p, const int* d_prev_slot, const int* d_next_slot,
@@ -746,5 +801,5 @@ extern "C" zs_status zs_klt_track_fb(zs_context* ctx, const zs_pyramid* p, const
 {
     ZS_REQUIRE(d_keep, "d_keep is null");
     return zs_klt_launch(ctx, p, d_prev_slot, d_next_slot, d_prev_pts, d_next_pts, d_count, nullptr, jobs, cap, params,
-                         d_status, d_err, 1, klt_threshold, d_keep);
+                         d_status, d_err, 1, klt_threshold, d_keep, nullptr, nullptr);
 }
