@@ -8,6 +8,8 @@
 // 16-bit ring-mask test finds the (few) corners, those are compacted with a ballot and scored densely
 // (one lane per corner), NMS and the first-maximum selection run on the shared score tile.  Integer only.
 // HBM traffic: each image byte is read once (cells never overlap) + 16 B per cell written.
+#include <stdlib.h>
+
 #include "zs_common.cuh"
 
 #define FAST_WARPS 8
@@ -172,6 +174,158 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_grid(fast_grid_args a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// v2 grid kernel (even cell sizes, e.g. the reference's default 16x16 and the 32x32 of the large-frame config).
+// A block owns FG2_CELLS consecutive cells of one cell row.  The strip is staged once with 16-byte loads and
+// expanded into two u16x2 "pair planes" in shared memory (E holds pixel pairs (0,1),(2,3).., O holds (1,2),(3,4)..),
+// so that the two horizontally adjacent interior pixels a thread owns see every ring position as ONE aligned
+// 32-bit shared load.  The FAST decision and score then need no per-pixel branching at all:
+//     dark arc  : all 9 ring pixels < c - t   <=>   min over arcs of (max over the arc) < c - t
+//     bright arc: all 9 ring pixels > c + t   <=>   max over arcs of (min over the arc) > c + t
+//     s' = max(c - A, B - c), corner <=> s' > t, response = s' - 1                 (same integers as v1)
+// and the sliding 9-window min / max over the 16-ring is 2 x 32 three-input VIMNMX3.U16x2 (two pixels per
+// instruction) plus two 16 -> 1 reductions.  NMS and the per-cell first maximum run on a u8 score tile.
+// ------------------------------------------------------------------------------------------------------
+#define FG2_CELLS 16
+#define FG2_THREADS 160
+
+template <bool MAX>
+__device__ __forceinline__ unsigned mm3(unsigned a, unsigned b, unsigned c) { return MAX ? __vimax3_u16x2(a, b, c) : __vimin3_u16x2(a, b, c); }
+
+// reduce over all 16 circular 9-windows: MAX9 = false: max_k min(window_k)  (bright side, B);  true: min_k max(window_k)  (dark side, A)
+template <bool MAX9>
+__device__ __forceinline__ unsigned ring_window9(const unsigned p[16])
+{
+    unsigned a[16], b[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = mm3<MAX9>(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) b[k] = mm3<MAX9>(a[k], a[(k + 3) & 15], a[(k + 6) & 15]);
+    unsigned r[6];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) r[k] = mm3<!MAX9>(b[3 * k], b[3 * k + 1], b[3 * k + 2]);
+    r[5] = b[15];
+    const unsigned u = mm3<!MAX9>(r[0], r[1], r[2]), w = mm3<!MAX9>(r[3], r[4], r[5]);
+    return MAX9 ? __vminu2(u, w) : __vmaxu2(u, w);
+}
+
+template <int CW, int CH>
+__global__ void __launch_bounds__(FG2_THREADS) k_fast_grid_v2(fast_grid_args a)
+{
+    constexpr int TW = FG2_CELLS * CW;            // strip width in pixels
+    constexpr int PW = TW / 2 + 4;                // words per pair-plane row (+ slack for the x+4 reads at the right edge)
+    constexpr int IW = CW - 6, IH = CH - 6;       // interior (tested) pixels per cell
+    constexpr int PPR = IW / 2;                   // pixel pairs per cell row (IW is even)
+    constexpr int ROWP = FG2_CELLS * PPR;         // pairs per strip row
+    constexpr int TOTAL = ROWP * IH;
+    static_assert(CW % 4 == 0 && CW >= 8 && CH >= 7, "cell shape");
+    extern __shared__ __align__(16) uint8_t fsm[];
+    uint32_t* sE = (uint32_t*)fsm;                                  // [CH][PW]
+    uint32_t* sO = sE + CH * PW;                                    // [CH][PW]
+    uint8_t* sS = (uint8_t*)(sO + CH * PW);                         // score tile [CH][TW]
+    int* sBest = (int*)(sS + CH * TW);                              // [FG2_CELLS]
+    uint8_t* sRaw = (uint8_t*)(sBest + FG2_CELLS);                  // raw strip [CH][TW + 16]
+    constexpr int RP = TW + 16;
+
+    const int img = blockIdx.z, gy = blockIdx.y, cell0 = blockIdx.x * FG2_CELLS;
+    const int ncell = min(FG2_CELLS, a.gw - cell0);
+    const int tid = threadIdx.x;
+    const int slot = zs_slot(a.first, img, a.v.slots);
+    const int pitch = a.v.pitch[0];
+    const uint8_t* src = a.v.img[0] + (size_t)slot * a.v.slot_stride[0] + (size_t)(a.v.pad_y + gy * CH) * pitch + a.v.pad_x + cell0 * CW;
+    const int valid_w = ncell * CW;               // pixels of this strip that belong to cells
+
+    // ---- stage the raw strip: 16-byte loads (interiors are 16-byte aligned: pad_x, pitch and CW*FG2_CELLS are multiples of 16)
+    for (int i = tid; i < CH * (RP / 16); i += FG2_THREADS) {
+        const int r = i / (RP / 16), c = (i - r * (RP / 16)) * 16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (c < valid_w) v = *(const uint4*)(src + (size_t)r * pitch + c);
+        *(uint4*)(sRaw + r * RP + c) = v;
+    }
+    for (int i = tid; i < CH * TW / 4; i += FG2_THREADS) ((uint32_t*)sS)[i] = 0;
+    if (tid < FG2_CELLS) sBest[tid] = 0;
+    __syncthreads();
+    // ---- expand into the pair planes: word j of E = (p[2j], p[2j+1]), of O = (p[2j+1], p[2j+2]) as u16x2
+    for (int i = tid; i < CH * (TW / 4 + 1); i += FG2_THREADS) {
+        const int r = i / (TW / 4 + 1), q = i - r * (TW / 4 + 1);
+        const uint32_t w = *(const uint32_t*)(sRaw + r * RP + 4 * q);
+        const uint32_t nb = sRaw[r * RP + 4 * q + 4];
+        uint32_t* e = sE + r * PW + 2 * q; uint32_t* o = sO + r * PW + 2 * q;
+        e[0] = __byte_perm(w, 0, 0x4140); e[1] = __byte_perm(w, 0, 0x4342);
+        o[0] = __byte_perm(w, 0, 0x4241); o[1] = (w >> 24) | (nb << 16);
+    }
+    __syncthreads();
+
+    // ---- scores: one thread per pair of horizontally adjacent interior pixels
+    const unsigned tt = (unsigned)a.threshold * 0x10001u;
+    for (int idx = tid; idx < TOTAL; idx += FG2_THREADS) {
+        const int ry = idx / ROWP, rem = idx - ry * ROWP;
+        const int cell = rem / PPR, pr = rem - cell * PPR;
+        if (cell >= ncell) continue;
+        const int y = ry + 3, x = cell * CW + 3 + 2 * pr;          // x is odd: (x+dx) odd -> plane O, even -> plane E
+        const uint32_t* eb = sE + y * PW + (x >> 1);               // word holding pair (x-1, x)
+        const uint32_t* ob = sO + y * PW + (x >> 1);               // word holding pair (x, x+1)
+        unsigned p[16];
+        // ring order of SURVEY A.1: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+        p[0] = ob[3 * PW];      p[1] = eb[3 * PW + 1];  p[2] = ob[2 * PW + 1];  p[3] = eb[1 * PW + 2];
+        p[4] = eb[2];           p[5] = eb[-1 * PW + 2]; p[6] = ob[-2 * PW + 1]; p[7] = eb[-3 * PW + 1];
+        p[8] = ob[-3 * PW];     p[9] = eb[-3 * PW];     p[10] = ob[-2 * PW - 1]; p[11] = eb[-1 * PW - 1];
+        p[12] = eb[-1];         p[13] = eb[1 * PW - 1]; p[14] = ob[2 * PW - 1];  p[15] = eb[3 * PW];
+        const unsigned c = ob[0];
+        const unsigned A = ring_window9<true>(p);                  // min over arcs of the arc maximum
+        const unsigned B = ring_window9<false>(p);                 // max over arcs of the arc minimum
+        // s' = max(c - A, B - c) per half, saturating at 0 (a negative side can never win against the threshold)
+        const unsigned sd = __vsubus2(c, A), sb = __vsubus2(B, c);
+        const unsigned sp = __vmaxu2(sd, sb);
+        const unsigned corner = __vcmpgtu2(sp, tt);                // 0xffff per half where s' > t
+        const unsigned sc = __vadd2(sp, 0xffffffffu) & corner;      // response s' - 1 per half (s' >= 1 wherever corner is set)
+        sS[y * TW + x] = (uint8_t)(sc & 0xff);
+        sS[y * TW + x + 1] = (uint8_t)(sc >> 16);
+    }
+    __syncthreads();
+
+    // ---- NMS (strictly greater than all 8 neighbours; untested border pixels score 0) + first maximum per cell
+    for (int idx = tid; idx < TOTAL; idx += FG2_THREADS) {
+        const int ry = idx / ROWP, rem = idx - ry * ROWP;
+        const int cell = rem / PPR, pr = rem - cell * PPR;
+        if (cell >= ncell) continue;
+        const int y = ry + 3, xc = 3 + 2 * pr, x = cell * CW + xc;
+        const uint8_t* r1 = sS + y * TW + x;
+        const unsigned m0 = *(const uint16_t*)(r1 - 1), m1 = *(const uint16_t*)(r1 + 1);        // (x-1,x) (x+1,x+2)
+        const int s0 = m0 >> 8, s1 = m1 & 0xff;
+        if ((s0 | s1) == 0) continue;
+        const unsigned t0 = *(const uint16_t*)(r1 - TW - 1), t1 = *(const uint16_t*)(r1 - TW + 1);
+        const unsigned b0 = *(const uint16_t*)(r1 + TW - 1), b1 = *(const uint16_t*)(r1 + TW + 1);
+        // neighbours of pixel x: columns x-1, x, x+1 of the rows above/below, x-1 and x+1 of its own row
+        const int n0 = max(max(max((int)(t0 & 0xff), (int)(t0 >> 8)), max((int)(t1 & 0xff), (int)(b0 & 0xff))),
+                           max(max((int)(b0 >> 8), (int)(b1 & 0xff)), max((int)(m0 & 0xff), s1)));
+        const int n1 = max(max(max((int)(t0 >> 8), (int)(t1 & 0xff)), max((int)(t1 >> 8), (int)(b0 >> 8))),
+                           max(max((int)(b1 & 0xff), (int)(b1 >> 8)), max(s0, (int)(m1 >> 8))));
+        // the pair's second pixel is later in raster order, so on equal scores the first one must win: keys carry 0xfffff - raster
+        if (s0 > n0) atomicMax(&sBest[cell], ((s0 + 1) << 20) | (0xfffff - (y * CW + xc)));
+        if (s1 > n1) atomicMax(&sBest[cell], ((s1 + 1) << 20) | (0xfffff - (y * CW + xc + 1)));
+    }
+    __syncthreads();
+    if (tid < ncell) {
+        const int cellg = gy * a.gw + cell0 + tid;
+        int out = -1;
+        const int best = sBest[tid];
+        if (best != 0 && !(a.occupied && a.occupied[(size_t)img * a.gw * a.gh + cellg])) {
+            const int s = (best >> 20) - 1, pz = 0xfffff - (best & 0xfffff);
+            const int yy = pz / CW, xx = pz - yy * CW;
+            out = (s << 20) | (yy << 10) | xx;
+        }
+        a.cand[(size_t)img * a.gw * a.gh + cellg] = out;
+    }
+}
+
+template <int CW, int CH>
+static size_t fast_grid_v2_smem()
+{
+    constexpr int TW = FG2_CELLS * CW, PW = TW / 2 + 4;
+    return (size_t)2 * CH * PW * 4 + (size_t)CH * TW + FG2_CELLS * 4 + (size_t)CH * (TW + 16);
+}
+
 // Compaction in cell row-major order: one block per image, block-wide exclusive scan over the cells.
 __global__ void __launch_bounds__(1024) k_grid_compact(const int* __restrict__ cand, int cells, int gw, int cw, int ch,
                                                        float2* __restrict__ oxy,
@@ -226,6 +380,22 @@ extern "C" zs_status zs_fast_grid_detect(zs_context* ctx, const zs_pyramid* p, i
     fast_grid_args a;
     a.v = p->v; a.first = first; a.count = count; a.cw = cell_w; a.ch = cell_h; a.gw = gw; a.gh = gh;
     a.threshold = threshold; a.occupied = d_occupied; a.cand = (int*)scratch;
+    if (!getenv("ZS_FAST_V1") && ((cell_w == 16 && cell_h == 16) || (cell_w == 32 && cell_h == 32))) {
+        const dim3 grid(zs_div_up(gw, FG2_CELLS), gh, count);
+        if (cell_w == 16) {
+            const size_t smem = fast_grid_v2_smem<16, 16>();
+            k_fast_grid_v2<16, 16><<<grid, FG2_THREADS, smem, ctx->stream>>>(a);
+        } else {
+            const size_t smem = fast_grid_v2_smem<32, 32>();
+            static bool attr = false;
+            if (!attr) { ZS_CUDA(cudaFuncSetAttribute(k_fast_grid_v2<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+            k_fast_grid_v2<32, 32><<<grid, FG2_THREADS, smem, ctx->stream>>>(a);
+        }
+        ZS_LAUNCH_CHECK(ctx);
+        k_grid_compact<<<count, 1024, 0, ctx->stream>>>(a.cand, cells, gw, cell_w, cell_h, (float2*)d_xy, d_response, d_count, cap);
+        ZS_LAUNCH_CHECK(ctx);
+        return ZS_OK;
+    }
     const int tp = (cell_w + 3) & ~3;
     const int list_cap = (cell_w - 6) * (cell_h - 6);
     const size_t smem = (size_t)FAST_WARPS * (2 * tp * cell_h + 2 * ((list_cap + 1) & ~1));
