@@ -7,6 +7,8 @@
 //   k_orb_filter    order-preserving compaction of the keypoints that survive the 31-px border filter.
 //   k_orb_describe  warp per keypoint, lane = descriptor byte: 8 tests x 2 gathers from the (L2-resident)
 //                   blurred plane; pattern rows fetched as int4 from a 1 KB table.
+#include <math.h>
+
 #include "zs_common.cuh"
 #include "../../include/zs_orb_pattern.h"
 
@@ -19,11 +21,19 @@
 #define G2 0x1.869472p-3f
 #define G3 0x1.ba95c0p-3f
 
-// grid: (ceil(w/64), ceil(h/32), count), 256 threads
+// u8 -> float without a conversion instruction: drop the byte into the mantissa of 2^23 and subtract 2^23 (exact)
+__device__ __forceinline__ float u8f(uint32_t w, int k)
+{
+    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 + k)), 8388608.f);     // 0x4B0000bb = 2^23 + bb
+}
+
+// grid: (ceil(w/64), ceil(h/32), count), 256 threads.  Four horizontally adjacent outputs per thread in both
+// passes: the row pass reads 3 words of the staged u8 tile and writes one float4, the column pass reads seven
+// float4 and writes one u8x4 word.  The per-output arithmetic (and its order) is OpenCV's, see SURVEY A.3.
 __global__ void __launch_bounds__(256) k_orb_blur(zs_pyr_view v, int first)
 {
-    __shared__ uint8_t s_in[BLUR_TH + 6][BLUR_TW + 8];     // 38 x 72
-    __shared__ float s_row[BLUR_TH + 6][BLUR_TW];          // row-pass results
+    __shared__ __align__(16) uint8_t s_in[BLUR_TH + 6][BLUR_TW + 8];     // 38 x 72
+    __shared__ __align__(16) float s_row[BLUR_TH + 6][BLUR_TW];          // row-pass results
     const int w = v.w[0], h = v.h[0], pitch = v.pitch[0];
     const int slot = zs_slot(first, blockIdx.z, v.slots);
     const int x0 = blockIdx.x * BLUR_TW, y0 = blockIdx.y * BLUR_TH;
@@ -38,33 +48,56 @@ __global__ void __launch_bounds__(256) k_orb_blur(zs_pyr_view v, int first)
         *(uint32_t*)&s_in[r][4 * c] = val;
     }
     __syncthreads();
-    // row pass: s = g0*x0; s = fma(x_i, g_i, s), i = 1..6
-    for (int i = threadIdx.x; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
-        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
-        const uint8_t* p = &s_in[r][c + 1];                // column x0 + c - 3
-        float s = __fmul_rn(G0, (float)p[0]);
-        s = fmaf((float)p[1], G1, s);
-        s = fmaf((float)p[2], G2, s);
-        s = fmaf((float)p[3], G3, s);
-        s = fmaf((float)p[4], G2, s);
-        s = fmaf((float)p[5], G1, s);
-        s = fmaf((float)p[6], G0, s);
-        s_row[r][c] = s;
+    // row pass: s = g0*x0; s = fma(x_i, g_i, s), i = 1..6.  Output column c needs staged bytes c+1 .. c+7.
+    for (int i = threadIdx.x; i < (BLUR_TH + 6) * (BLUR_TW / 4); i += 256) {
+        const int r = i / (BLUR_TW / 4), c = (i - r * (BLUR_TW / 4)) * 4;
+        const uint32_t* wp = (const uint32_t*)&s_in[r][c];
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        float f[10];                                        // staged bytes c+1 .. c+10
+        f[0] = u8f(w0, 1); f[1] = u8f(w0, 2); f[2] = u8f(w0, 3);
+        f[3] = u8f(w1, 0); f[4] = u8f(w1, 1); f[5] = u8f(w1, 2); f[6] = u8f(w1, 3);
+        f[7] = u8f(w2, 0); f[8] = u8f(w2, 1); f[9] = u8f(w2, 2);
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float t = __fmul_rn(G0, f[k]);
+            t = fmaf(f[k + 1], G1, t);
+            t = fmaf(f[k + 2], G2, t);
+            t = fmaf(f[k + 3], G3, t);
+            t = fmaf(f[k + 4], G2, t);
+            t = fmaf(f[k + 5], G1, t);
+            t = fmaf(f[k + 6], G0, t);
+            o[k] = t;
+        }
+        *(float4*)&s_row[r][c] = make_float4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();
     // column pass: s = g3*r0; s = fma(r_{+k} + r_{-k}, g_{3+k}, s), k = 1..3; round half even, saturate
     uint8_t* dst = v.blur + (size_t)slot * v.blur_slot;
-    for (int i = threadIdx.x; i < BLUR_TH * BLUR_TW; i += 256) {
-        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
+    for (int i = threadIdx.x; i < BLUR_TH * (BLUR_TW / 4); i += 256) {
+        const int r = i / (BLUR_TW / 4), c = (i - r * (BLUR_TW / 4)) * 4;
         const int x = x0 + c, y = y0 + r;
         if (x >= w || y >= h) continue;
-        float s = __fmul_rn(G3, s_row[r + 3][c]);
-        s = fmaf(__fadd_rn(s_row[r + 4][c], s_row[r + 2][c]), G2, s);
-        s = fmaf(__fadd_rn(s_row[r + 5][c], s_row[r + 1][c]), G1, s);
-        s = fmaf(__fadd_rn(s_row[r + 6][c], s_row[r + 0][c]), G0, s);
-        int q = __float2int_rn(s);
-        q = q < 0 ? 0 : q > 255 ? 255 : q;
-        dst[(size_t)y * v.blur_pitch + x] = (uint8_t)q;
+        float4 rr[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) rr[k] = *(const float4*)&s_row[r + k][c];
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a0 = ((const float*)&rr[0])[k], a1 = ((const float*)&rr[1])[k], a2 = ((const float*)&rr[2])[k],
+                        a3 = ((const float*)&rr[3])[k], a4 = ((const float*)&rr[4])[k], a5 = ((const float*)&rr[5])[k],
+                        a6 = ((const float*)&rr[6])[k];
+            float t = __fmul_rn(G3, a3);
+            t = fmaf(__fadd_rn(a4, a2), G2, t);
+            t = fmaf(__fadd_rn(a5, a1), G1, t);
+            t = fmaf(__fadd_rn(a6, a0), G0, t);
+            int q = __float2int_rn(t);
+            q = q < 0 ? 0 : q > 255 ? 255 : q;
+            packed |= (uint32_t)q << (8 * k);
+        }
+        uint8_t* o = dst + (size_t)y * v.blur_pitch + x;
+        if (x + 4 <= w) *(uint32_t*)o = packed;            // blur_pitch is a multiple of 128 and x of 4
+        else for (int k = 0; x + k < w; ++k) o[k] = (uint8_t)(packed >> (8 * k));
     }
 }
 
@@ -124,35 +157,70 @@ __global__ void __launch_bounds__(1024) k_orb_filter(const float2* __restrict__ 
 
 __device__ int4 g_orb_pattern[256] = ZS_ORB_PATTERN_INIT;   // global copy: lane-divergent reads go through L1
 
-// grid: (ceil(cap/8), count), 256 threads = 8 warps = 8 keypoints
+// grid: (ceil(cap/8), count), 256 threads = 8 warps = 8 keypoints.
+// The 512 sample points of a keypoint lie within 19 px of its centre (pattern radius 18.4 + rounding), and the border
+// filter keeps every centre >= 31 px inside the image, so the warp first stages the 39 x 44-byte neighbourhood with
+// coalesced 32-bit loads (39 rows x 11 words = ~14 loads per lane, each row one or two 32-byte sectors) and then
+// gathers from shared memory -- instead of 512 single-byte gathers that each touch their own sector in L2.
+#define ORB_R 19
+#define ORB_PW 11                                      // words per staged row (39 + up to 3 alignment bytes <= 44)
+#define ORB_ROWS (2 * ORB_R + 1)
+// cos / sin of the keypoint angles, once per keypoint (double math like OpenCV; FP64 is scarce on B200, so this
+// is kept out of the describe kernel, where every lane of a warp would repeat it)
+__global__ void k_orb_trig(const float* __restrict__ angles, const int* __restrict__ counts, int cap, float2* __restrict__ ab)
+{
+    const int img = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(counts[img], cap)) return;
+    const size_t off = (size_t)img * cap + i;
+    // OpenCV: angle *= (float)(CV_PI/180.f); a = (float)cos(angle), b = (float)sin(angle)  (double math)
+    const float angle = __fmul_rn(angles[off], (float)(3.14159265358979323846 / 180.0));
+    ab[off] = make_float2((float)cos((double)angle), (float)sin((double)angle));
+}
+
+// ab: per-keypoint (cos, sin) or null, in which case every keypoint uses (a0, b0) -- the constants for the angle
+// -1 degree that FAST keypoints carry, computed once on the host
 __global__ void __launch_bounds__(256) k_orb_describe(zs_pyr_view v, int first, const float2* __restrict__ xys,
-                                                      const float* __restrict__ angles,
+                                                      const float2* __restrict__ ab, float a0, float b0,
                                                       const int* __restrict__ counts, int cap, uint8_t* __restrict__ desc)
 {
+    __shared__ uint32_t s_patch[8][ORB_ROWS * ORB_PW];
+    __shared__ int4 s_pattern[256];                    // transposed: [bit][lane], so a warp reads 512 contiguous bytes per bit
     const int img = blockIdx.y;
-    const int kp = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int warp = threadIdx.x >> 5;
+    const int kp = blockIdx.x * 8 + warp;
     const int lane = threadIdx.x & 31;
+    if (blockIdx.x * 8 >= counts[img]) return;         // whole block idle
+    // (the table row a lane needs for bit b is 8*lane + b: read straight from global memory that is one 16-byte
+    // piece out of 32 different cache lines per load -- the kernel used to spend most of its time there)
+    s_pattern[(threadIdx.x & 7) * 32 + (threadIdx.x >> 3)] = g_orb_pattern[threadIdx.x];
+    __syncthreads();
     if (kp >= counts[img]) return;
     const size_t off = (size_t)img * cap + kp;
     const int slot = zs_slot(first, img, v.slots);
     const int pitch = v.blur_pitch;
     const float2 xy = xys[off];
     const int cx = __float2int_rn(xy.x), cy = __float2int_rn(xy.y);
-    const uint8_t* c = v.blur + (size_t)slot * v.blur_slot + (size_t)cy * pitch + cx;
-    float angle = angles ? angles[off] : -1.f;
-    // OpenCV: angle *= (float)(CV_PI/180.f); a = (float)cos(angle), b = (float)sin(angle)  (double math)
-    angle = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.0));
-    const float a = (float)cos((double)angle), b = (float)sin((double)angle);
+    const int x0 = (cx - ORB_R) & ~3;                  // first staged column (4-byte aligned; the plane pitch is a multiple of 128)
+    const uint8_t* src = v.blur + (size_t)slot * v.blur_slot + (size_t)(cy - ORB_R) * pitch + x0;
+    uint32_t* sp = s_patch[warp];
+    for (int i = lane; i < ORB_ROWS * ORB_PW; i += 32) {
+        const int r = i / ORB_PW, c = i - r * ORB_PW;
+        sp[i] = *(const uint32_t*)(src + (size_t)r * pitch + 4 * c);
+    }
+    __syncwarp();
+    const uint8_t* c = (const uint8_t*)sp + ORB_R * (ORB_PW * 4) + (cx - x0);     // the centre pixel inside the staged patch
+    float a = a0, b = b0;
+    if (ab) { const float2 t = ab[off]; a = t.x; b = t.y; }
     int val = 0;
 #pragma unroll
     for (int bit = 0; bit < 8; ++bit) {
-        const int4 pt = g_orb_pattern[lane * 8 + bit];
-        const float x0 = __fsub_rn(__fmul_rn((float)pt.x, a), __fmul_rn((float)pt.y, b));
-        const float y0 = __fadd_rn(__fmul_rn((float)pt.x, b), __fmul_rn((float)pt.y, a));
-        const float x1 = __fsub_rn(__fmul_rn((float)pt.z, a), __fmul_rn((float)pt.w, b));
-        const float y1 = __fadd_rn(__fmul_rn((float)pt.z, b), __fmul_rn((float)pt.w, a));
-        const int t0 = c[__float2int_rn(y0) * pitch + __float2int_rn(x0)];
-        const int t1 = c[__float2int_rn(y1) * pitch + __float2int_rn(x1)];
+        const int4 pt = s_pattern[bit * 32 + lane];
+        const float x0f = __fsub_rn(__fmul_rn((float)pt.x, a), __fmul_rn((float)pt.y, b));
+        const float y0f = __fadd_rn(__fmul_rn((float)pt.x, b), __fmul_rn((float)pt.y, a));
+        const float x1f = __fsub_rn(__fmul_rn((float)pt.z, a), __fmul_rn((float)pt.w, b));
+        const float y1f = __fadd_rn(__fmul_rn((float)pt.z, b), __fmul_rn((float)pt.w, a));
+        const int t0 = c[__float2int_rn(y0f) * (ORB_PW * 4) + __float2int_rn(x0f)];
+        const int t1 = c[__float2int_rn(y1f) * (ORB_PW * 4) + __float2int_rn(x1f)];
         val |= (t0 < t1) << bit;
     }
     desc[off * 32 + lane] = (uint8_t)val;
@@ -172,14 +240,24 @@ extern "C" zs_status zs_orb_compute(zs_context* ctx, const zs_pyramid* p, int fi
     float* d_angle = nullptr;
     if (d_angle_in) {
         void* s;
-        st = zs_scratch(ctx, sizeof(float) * (size_t)cap * count, &s);
+        st = zs_scratch(ctx, sizeof(float) * 3 * (size_t)cap * count + 64, &s);
         if (st != ZS_OK) return st;
         d_angle = (float*)s;
     }
     k_orb_filter<<<count, 1024, 0, ctx->stream>>>((const float2*)d_xy_in, d_resp_in, d_angle_in, d_count_in, cap, p->width,
                                                   p->height, (float2*)d_xy, d_resp, d_angle, d_src_index, d_count);
     ZS_LAUNCH_CHECK(ctx);
-    k_orb_describe<<<dim3(zs_div_up(cap, 8), count), 256, 0, ctx->stream>>>(p->v, first, (const float2*)d_xy, d_angle, d_count, cap, d_desc);
+    float2* d_ab = nullptr;
+    // angle -1 degree: (float)cos / (float)sin of the double value of the float product, as OpenCV computes them
+    const float ang = -1.f * (float)(3.14159265358979323846 / 180.0);
+    const float a0 = (float)cos((double)ang), b0 = (float)sin((double)ang);
+    if (d_angle) {
+        // the compacted angles sit in the first half of the scratch block; (cos, sin) pairs go behind them
+        d_ab = (float2*)(d_angle + (((size_t)cap * count + 3) & ~(size_t)3));
+        k_orb_trig<<<dim3(zs_div_up(cap, 256), count), 256, 0, ctx->stream>>>(d_angle, d_count, cap, d_ab);
+        ZS_LAUNCH_CHECK(ctx);
+    }
+    k_orb_describe<<<dim3(zs_div_up(cap, 8), count), 256, 0, ctx->stream>>>(p->v, first, (const float2*)d_xy, d_ab, a0, b0, d_count, cap, d_desc);
     ZS_LAUNCH_CHECK(ctx);
     return ZS_OK;
 }

@@ -9,28 +9,52 @@
 #include "zs_common.cuh"
 
 // ---- (1) reflect padding ---------------------------------------------------------------------------
-// grid: (1, padded rows, count); 128 threads stride over the columns that need filling.
-__global__ void __launch_bounds__(128) k_pad_reflect(zs_pyr_view v, int level, int first)
+// grid: (1, ceil(padded rows / 32), count); 256 threads = 8 warps, each warp fills rows r, r+8, r+16, r+24 of its
+// 32-row group (one block per row was block-launch bound: 139 k tiny blocks per level 0).  Interior rows get their left / right pads; rows above / below the
+// image are whole copies of the reflected interior row (pads included).  Everything is produced as 32-bit words
+// (pad_x and the pitch are multiples of 16): a word whose four source pixels are consecutive and ascending is
+// one load when the source offset is aligned, otherwise four byte reads from the just-staged interior row.
+__global__ void __launch_bounds__(256) k_pad_reflect(zs_pyr_view v, int level, int first)
 {
     const int w = v.w[level], h = v.h[level], pitch = v.pitch[level];
     const int slot = zs_slot(first, blockIdx.z, v.slots);
     uint8_t* plane = v.img[level] + (size_t)slot * v.slot_stride[level];
-    const int r = blockIdx.y;                         // padded row
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int rr = (threadIdx.x >> 5); rr < 32; rr += 8) {
+    const int r = blockIdx.y * 32 + rr;               // padded row
+    if (r >= h + 2 * v.pad_y) break;
     const int sy = zs_reflect101(r - v.pad_y, h);
     const uint8_t* src = plane + (size_t)(sy + v.pad_y) * pitch + v.pad_x;   // interior row sy
     uint8_t* dst = plane + (size_t)r * pitch;
     const bool interior_row = (r >= v.pad_y && r < v.pad_y + h);
-    const int PW = w + 2 * v.pad_x;
-    if (interior_row) {
-        // only the left and right pads
-        for (int c = threadIdx.x; c < 2 * v.pad_x; c += blockDim.x) {
-            const int px = c < v.pad_x ? c : (w + c);           // padded column
-            dst[px] = src[zs_reflect101(px - v.pad_x, w)];
+    const int wpad = v.pad_x >> 2;                    // words per side pad
+    const int wint = (w + 3) >> 2;                    // words covering the interior (the last may run into the right pad)
+    const int wright0 = w >> 2;                       // first word that contains right-pad pixels
+    const int wtotal = (w + 2 * v.pad_x + 3) >> 2;    // words per padded row (the pitch is rounded up beyond this)
+    // word index q covers padded columns 4q .. 4q+3
+    // interior rows only touch the words outside the fully-interior ones (the image itself lives there)
+    const int n = interior_row ? wtotal - wright0 : wtotal;
+    for (int j = lane; j < n; j += 32) {
+        const int q = (interior_row && j >= wpad) ? j + wright0 : j;
+        const int px0 = 4 * q - v.pad_x;              // image column of the word's first pixel
+        const bool left = q < wpad, inside = !left && (q - wpad) < wright0;
+        uint32_t val;
+        if (inside && ((px0 & 3) == 0)) {
+            val = *(const uint32_t*)(src + px0);      // straight copy of four interior pixels of the reflected row
+        } else {
+            val = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int px = px0 + k;
+                // a partial last interior word keeps its interior bytes (they are re-read and re-written unchanged)
+                val |= (uint32_t)src[zs_reflect101(px, w)] << (8 * k);
+            }
         }
-    } else {
-        for (int px = threadIdx.x; px < PW; px += blockDim.x)
-            dst[px] = src[zs_reflect101(px - v.pad_x, w)];
+        *(uint32_t*)(dst + 4 * q) = val;
     }
+    (void)wint;
+  }
 }
 
 // ---- (2) pyrDown -------------------------------------------------------------------------------------
@@ -133,7 +157,7 @@ extern "C" zs_status zs_pyramid_build(zs_context* ctx, zs_pyramid* p, int first,
     const zs_pyr_view& v = p->v;
     for (int l = 0; l < v.levels; ++l) {
         const int w = v.w[l], h = v.h[l];
-        k_pad_reflect<<<dim3(1, h + 2 * v.pad_y, count), 128, 0, ctx->stream>>>(v, l, first);
+        k_pad_reflect<<<dim3(1, zs_div_up(h + 2 * v.pad_y, 32), count), 256, 0, ctx->stream>>>(v, l, first);
         ZS_LAUNCH_CHECK(ctx);
         if (l + 1 < v.levels) {
             const int dw = v.w[l + 1], dh = v.h[l + 1];
