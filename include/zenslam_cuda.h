@@ -101,6 +101,14 @@ ZS_API zs_status zs_fast_detect(zs_context* ctx, const zs_pyramid* p, int first,
                                 const uint8_t* d_mask, float* d_xy, float* d_response,
                                 int* d_count, int cap);
 
+/* ---- sub-pixel refinement: cv::cornerSubPix(image, pts, win, Size(-1,-1), {EPS+COUNT, max_iters, epsilon}) ----
+ * keypoint_detector_parallel::detect_keypoints refines the grid corners with win (5,5), 30 iterations, eps 0.01
+ * (zenslam_core/source/detection/keypoint_detector_parallel.cpp:160-170).  d_xy is [count][cap][2], refined in place
+ * on level 0 of slots first..first+count-1; win_w / win_h are HALF sizes (1..7), like cv::Size(5,5).  Bit-identical to
+ * OpenCV built without IPP. */
+ZS_API zs_status zs_corner_subpix(zs_context* ctx, const zs_pyramid* p, int first, int count, float* d_xy,
+                                  const int* d_count, int cap, int win_w, int win_h, int max_iters, double epsilon);
+
 /* ---- description: cv::ORB::create()->compute(image, keypoints, descriptors) ----------------
  * (keypoint_detector_grid.cpp:138).  Drops keypoints outside the 31-px border keeping order,
  * blurs (7x7 sigma 2, float32), 256 rBRIEF tests rotated by the keypoint angle (degrees; NULL = -1,
@@ -182,6 +190,14 @@ ZS_API zs_status zs_detect_keypoints_grid_host(zs_context* ctx, const uint8_t* i
                                                size_t pitch, int cell_w, int cell_h, int threshold,
                                                const uint8_t* occupied, float* x, float* y, float* response,
                                                uint8_t* desc, int* n_out);
+/* keypoint_detector_parallel::detect_keypoints (keypoint_detector_parallel.cpp:40-193): the same cells and first
+ * strongest corner per cell as the grid detector, then cv::cornerSubPix (5x5 half window, 30 iterations, eps 0.01),
+ * then ORB::compute at cvRound(pt).  Same arguments and outputs as zs_detect_keypoints_grid_host; x / y come back
+ * sub-pixel. */
+ZS_API zs_status zs_detect_keypoints_parallel_host(zs_context* ctx, const uint8_t* img, int width, int height,
+                                                   size_t pitch, int cell_w, int cell_h, int threshold,
+                                                   const uint8_t* occupied, float* x, float* y, float* response,
+                                                   uint8_t* desc, int* n_out);
 /* matcher::match_keypoints descriptor stage: mode 0 = KNN (ratio), 1 = BRUTE (cross-check);
  * norm 0 = Hamming (32-byte rows), 1 = L2 (dim floats).  Outputs sized nq; *n_out matches. */
 ZS_API zs_status zs_match_host(zs_context* ctx, const void* q, int nq, const void* t, int nt, int dim,

@@ -291,3 +291,19 @@ class FrontendOptions:
     klt_max_level: int = 3
     klt_threshold: float = 1.0
     matcher_ratio: float = 0.8
+
+
+# ---------------------------------------------------------------------------------------------
+# cornerSubPix (PARALLEL_GRID detector)
+# ---------------------------------------------------------------------------------------------
+def corner_subpix(img, xy, win=(5, 5), max_iters=30, eps=0.01):
+    """cv::cornerSubPix(img, pts, win, (-1,-1), (EPS+COUNT, max_iters, eps)) as keypoint_detector_parallel calls it
+    (keypoint_detector_parallel.cpp:160-170).  xy: (n, 2) float32 -> refined copy."""
+    img = _u8img(img)
+    h, w = img.shape
+    out = np.ascontiguousarray(xy, np.float32).copy()
+    L = lib()
+    L.zso_corner_subpix.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_double]
+    L.zso_corner_subpix(_p(img), w, h, w, _p(out), len(out), win[0], win[1], max_iters, float(eps))
+    return out

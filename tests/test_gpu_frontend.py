@@ -209,3 +209,26 @@ def test_frontend_pipelined_equals_blocking(ctx, w, h, B):
                 assert np.array_equal(got[b]["track_pts"][kind, k, :m], want[b]["track_pts"][kind, k, :m])
                 assert np.array_equal(got[b]["track_keep"][kind, k, :m], want[b]["track_keep"][kind, k, :m])
     fe.close()
+
+
+def test_keypoint_detector_parallel_mirror(ctx, golden):
+    """PARALLEL_GRID: grid corners -> cornerSubPix -> ORB::compute at cvRound(pt) (keypoint_detector_parallel.cpp:40-193),
+    against the cv2 fixture (IPP off) and against the oracle on a full-size frame"""
+    from zenslam_b200 import detection_options, keypoint
+    from zenslam_b200.detection import keypoint_detector_parallel
+    g = golden("subpix")
+    det = keypoint_detector_parallel(detection_options(), ctx)
+    kps = det.detect_keypoints(g["L"], {})
+    assert np.array_equal(np.array([k.pt for k in kps], np.float32), np.stack([g["cv_par_kx"], g["cv_par_ky"]], 1))
+    assert np.array_equal(np.stack([k.descriptor for k in kps]), g["cv_par_desc"])
+    L, _ = syn.stereo_pair(752, 480, 1003)
+    keypoint.index_next = 7
+    kps = det.detect_keypoints(L, {})
+    x, y, s = oracle.grid_detect(L, (16, 16), 10)
+    ref = oracle.corner_subpix(L, np.stack([x, y], 1).astype(np.float32))
+    kept, desc = oracle.orb_compute(L, ref[:, 0].copy(), ref[:, 1].copy())
+    assert [k.index for k in kps] == list(range(7, 7 + len(kept)))
+    assert np.array_equal(np.array([k.pt for k in kps], np.float32), ref[kept])
+    assert np.array_equal(np.array([k.response for k in kps], np.float32), s[kept].astype(np.float32))
+    assert np.array_equal(np.stack([k.descriptor for k in kps]), desc)
+    assert any(k.pt[0] != int(k.pt[0]) for k in kps)                  # points really are sub-pixel

@@ -409,3 +409,47 @@ def test_l2_tensor_core_ragged_pairs_vs_oracle_and_cuda_core(ctx, monkeypatch):
         oq, ot, odd = oracle.match_l2_cross(q[k, :a], t[k, :b])
         keep = np.nonzero(cidx[k, :a] >= 0)[0]
         assert np.array_equal(keep, oq) and np.array_equal(cidx[k, keep], ot) and np.array_equal(cdist[k, keep], odd)
+
+
+# ---------------------------------------------------------------------------------------------
+# cornerSubPix (PARALLEL_GRID detector)
+# ---------------------------------------------------------------------------------------------
+def test_corner_subpix_golden(ctx, golden):
+    """bit-exact against cv2.cornerSubPix (IPP off) on the fixture, image-border points included"""
+    from zenslam_b200.runtime import Pyramid, corner_subpix
+    g = golden("subpix")
+    L, pts = g["L"], g["pts"]
+    h, w = L.shape
+    pyr = Pyramid(ctx, w, h, 2, (31, 31), 0)
+    pyr.upload(L[None], 1)
+    pyr.build(1, 1)
+    cap = len(pts) + 7
+    xy = np.zeros((1, cap, 2), np.float32); xy[0, :len(pts)] = pts; xy[0, len(pts):] = 9.5     # beyond count: untouched
+    d = dev(ctx, xy)
+    corner_subpix(pyr, 1, 1, d, dev(ctx, np.array([len(pts)], np.int32)))
+    got = d.cpu().numpy()[0]
+    assert np.array_equal(got[:len(pts)], g["cv_subpix"])
+    assert np.all(got[len(pts):] == 9.5)
+    assert np.abs(got[:len(pts)] - g["cv_subpix_ipp"]).max() < 5e-3
+
+
+@pytest.mark.parametrize("w,h,cell,thr,win,its,eps", [(752, 480, (16, 16), 10, (5, 5), 30, 0.01), (640, 400, (32, 32), 5, (3, 7), 5, 0.0),
+                                                      (320, 200, (16, 16), 1, (7, 2), 100, 0.1)])
+def test_corner_subpix_batch_vs_oracle(ctx, w, h, cell, thr, win, its, eps):
+    from zenslam_b200.runtime import Pyramid, corner_subpix, fast_grid_detect
+    B = 3
+    seq, _ = syn.stereo_sequence(w, h, B, 31 + w, subpixel=True)
+    imgs = np.ascontiguousarray(seq[:, 0])
+    pyr = Pyramid(ctx, w, h, B, (31, 31), 0)
+    pyr.upload(imgs, 0)
+    pyr.build(0, B)
+    xy, resp, n = fast_grid_detect(pyr, 0, B, cell, thr)
+    before = xy.cpu().numpy().copy()
+    corner_subpix(pyr, 0, B, xy, n, win, its, eps)
+    after, cnt = xy.cpu().numpy(), n.cpu().numpy()
+    moved = 0
+    for k in range(B):
+        want = oracle.corner_subpix(imgs[k], before[k, :cnt[k]], win, its, eps)
+        assert np.array_equal(after[k, :cnt[k]], want), k
+        moved += int((np.abs(want - before[k, :cnt[k]]).max(1) > 0).sum())
+    assert moved > 0

@@ -133,3 +133,17 @@ def test_empty_inputs():
     P = oracle.Pyramid(np.zeros((64, 64), np.uint8), (15, 15), 3)
     p1, st, err = oracle.lk_track(P, P, np.zeros((0, 2), np.float32))
     assert p1.shape == (0, 2)
+
+
+def test_corner_subpix_golden(golden):
+    """cv::cornerSubPix (PARALLEL_GRID detector): the C restatement is bit-exact against cv2 with IPP off on every
+    fixture point, image-border points included, and within 5e-3 px of cv2's IPP path."""
+    g = golden("subpix")
+    got = oracle.corner_subpix(g["L"], g["pts"])
+    assert np.array_equal(got, g["cv_subpix"])
+    assert np.abs(got - g["cv_subpix_ipp"]).max() < 5e-3
+    # degenerate inputs
+    assert oracle.corner_subpix(g["L"], np.zeros((0, 2), np.float32)).shape == (0, 2)
+    flat = np.full((64, 64), 77, np.uint8)
+    p = np.array([[20.5, 30.25]], np.float32)
+    assert np.array_equal(oracle.corner_subpix(flat, p), p)            # singular normal matrix: point unchanged

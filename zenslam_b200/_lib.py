@@ -70,6 +70,7 @@ SIGNATURES = {
     "zs_pyramid_download_deriv": (I, [P, P, I, I, P]),
     "zs_fast_grid_detect": (I, [P, P, I, I, I, I, I, P, P, P, P, I]),
     "zs_fast_detect": (I, [P, P, I, I, I, P, P, P, P, I]),
+    "zs_corner_subpix": (I, [P, P, I, I, P, P, I, I, I, I, D]),
     "zs_orb_compute": (I, [P, P, I, I, P, P, P, P, I, P, P, P, P, P]),
     "zs_orb_download_blur": (I, [P, P, I, P]),
     "zs_match_hamming_knn2": (I, [P, P, P, Z, P, P, Z, I, I, I, D, P, P, P]),
@@ -80,6 +81,7 @@ SIGNATURES = {
     "zs_klt_track_fb": (I, [P, P, P, P, P, P, P, I, I, C.POINTER(LkParams), D, P, P, P]),
     "zs_calc_optical_flow_pyr_lk_host": (I, [P, P, P, I, I, Z, P, P, I, P, P, C.POINTER(LkParams)]),
     "zs_detect_keypoints_grid_host": (I, [P, P, I, I, Z, I, I, I, P, P, P, P, P, C.POINTER(I)]),
+    "zs_detect_keypoints_parallel_host": (I, [P, P, I, I, Z, I, I, I, P, P, P, P, P, C.POINTER(I)]),
     "zs_match_host": (I, [P, P, I, P, I, I, I, I, D, P, P, P, C.POINTER(I)]),
     "zs_knn_match_host": (I, [P, P, I, P, I, I, I, I, I, P, P]),
     "zs_frontend_create": (I, [P, C.POINTER(FrontendOptions), C.POINTER(P)]),

@@ -61,9 +61,9 @@ extern "C" zs_status zs_calc_optical_flow_pyr_lk_host(zs_context* ctx, const uin
     return ZS_OK;
 }
 
-extern "C" zs_status zs_detect_keypoints_grid_host(zs_context* ctx, const uint8_t* img, int width, int height, size_t pitch,
-                                                   int cell_w, int cell_h, int threshold, const uint8_t* occupied, float* x,
-                                                   float* y, float* response, uint8_t* desc, int* n_out)
+static zs_status detect_grid_host(zs_context* ctx, const uint8_t* img, int width, int height, size_t pitch, int cell_w, int cell_h,
+                                  int threshold, const uint8_t* occupied, float* x, float* y, float* response, uint8_t* desc,
+                                  int* n_out, int subpix)
 {
     ZS_REQUIRE(ctx && img && x && y && response && desc && n_out, "null argument");
     ZS_REQUIRE(cell_w > 0 && cell_h > 0, "bad cell size");
@@ -86,6 +86,10 @@ extern "C" zs_status zs_detect_keypoints_grid_host(zs_context* ctx, const uint8_
     if (occupied) ZS_CUDA(cudaMemcpyAsync(base + o_occ, occupied, cells, cudaMemcpyHostToDevice, ctx->stream));
     st = zs_fast_grid_detect(ctx, p, 0, 1, cell_w, cell_h, threshold, occupied ? base + o_occ : nullptr, (float*)(base + o_xy0),
                              (float*)(base + o_r0), (int*)(base + o_n0), cells);
+    // PARALLEL_GRID: cv::cornerSubPix(win 5x5, 30 iterations, eps 0.01) on every selected corner before ORB::compute
+    // (keypoint_detector_parallel.cpp:160-170)
+    if (st == ZS_OK && subpix)
+        st = zs_corner_subpix(ctx, p, 0, 1, (float*)(base + o_xy0), (const int*)(base + o_n0), cells, 5, 5, 30, 0.01);
     if (st == ZS_OK)
         st = zs_orb_compute(ctx, p, 0, 1, (const float*)(base + o_xy0), (const float*)(base + o_r0), nullptr,
                             (const int*)(base + o_n0), cells, (float*)(base + o_xy), (float*)(base + o_r), nullptr,
@@ -107,6 +111,20 @@ extern "C" zs_status zs_detect_keypoints_grid_host(zs_context* ctx, const uint8_
     ZS_CUDA(cudaFreeAsync(base, ctx->stream));
     *n_out = n;
     return ZS_OK;
+}
+
+extern "C" zs_status zs_detect_keypoints_grid_host(zs_context* ctx, const uint8_t* img, int width, int height, size_t pitch,
+                                                   int cell_w, int cell_h, int threshold, const uint8_t* occupied, float* x,
+                                                   float* y, float* response, uint8_t* desc, int* n_out)
+{
+    return detect_grid_host(ctx, img, width, height, pitch, cell_w, cell_h, threshold, occupied, x, y, response, desc, n_out, 0);
+}
+
+extern "C" zs_status zs_detect_keypoints_parallel_host(zs_context* ctx, const uint8_t* img, int width, int height, size_t pitch,
+                                                       int cell_w, int cell_h, int threshold, const uint8_t* occupied, float* x,
+                                                       float* y, float* response, uint8_t* desc, int* n_out)
+{
+    return detect_grid_host(ctx, img, width, height, pitch, cell_w, cell_h, threshold, occupied, x, y, response, desc, n_out, 1);
 }
 
 extern "C" zs_status zs_match_host(zs_context* ctx, const void* q, int nq, const void* t, int nt, int dim, int norm, int mode,

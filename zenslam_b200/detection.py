@@ -40,6 +40,8 @@ def _emit(xs, ys, resp, desc) -> list:
 class keypoint_detector_grid(keypoint_detector):
     """keypoint_detector_grid (zenslam_core/source/detection/keypoint_detector_grid.cpp:9-150)."""
 
+    _entry = "zs_detect_keypoints_grid_host"
+
     def __init__(self, options: detection_options, ctx: Context):
         _require_fast_orb(options)
         self._options, self._ctx = options, ctx
@@ -65,11 +67,19 @@ class keypoint_detector_grid(keypoint_detector):
         desc = np.empty((cells, 32), np.uint8)
         n = C.c_int(0)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
-        check(lib().zs_detect_keypoints_grid_host(self._ctx._h, p(image), w, h, w, cw, ch, int(self._options.fast_threshold),
+        check(getattr(lib(), self._entry)(self._ctx._h, p(image), w, h, w, cw, ch, int(self._options.fast_threshold),
                                                   p(occ) if occ is not None else None, p(xs), p(ys), p(resp), p(desc),
                                                   C.byref(n)))
         k = n.value
         return _emit(xs[:k], ys[:k], resp[:k], desc[:k].copy())
+
+
+class keypoint_detector_parallel(keypoint_detector_grid):
+    """keypoint_detector_parallel (zenslam_core/source/detection/keypoint_detector_parallel.cpp:40-193): the grid
+    detector's cells, then cv::cornerSubPix (win 5x5, 30 its, eps 0.01) on every selected corner, then ORB::compute
+    at cvRound(pt).  The reference's per-cell std::async threads are an execution detail, not a result."""
+
+    _entry = "zs_detect_keypoints_parallel_host"
 
 
 class keypoint_detector_simple(keypoint_detector):

@@ -201,6 +201,14 @@ def fast_detect(pyr: Pyramid, first, count, threshold=10, mask=None, cap=65536):
     return xy, resp, n
 
 
+def corner_subpix(pyr: Pyramid, first, count, xy, n, win=(5, 5), max_iters=30, epsilon=0.01):
+    """cv::cornerSubPix on level 0 of slots first..; xy (count, cap, 2) f32 cuda, refined IN PLACE; n (count,) i32"""
+    cap = xy.shape[1]
+    check(lib().zs_corner_subpix(pyr.ctx._h, pyr._h, first, count, _ptr(xy), _ptr(n), cap, win[0], win[1], max_iters,
+                                 float(epsilon)))
+    return xy
+
+
 def orb_compute(pyr: Pyramid, first, count, xy, resp, n, angle=None):
     """-> xy', resp', src_index, n', desc (count, cap, 32) u8"""
     torch = _torch()
