@@ -64,6 +64,26 @@ ZS_API void* zs_context_stream(zs_context* ctx);
 /* number of kernels this library has launched on the context since creation */
 ZS_API uint64_t zs_context_launch_count(const zs_context* ctx);
 
+/* ---- pre-processing: processor::process (zenslam_core/source/processor.cpp:25-55), SURVEY 8(f1) -----------
+ * utils::convert_color(BGR2GRAY) -> optional CLAHE(4.0, 8x8) (processor.h:38) -> utils::rectify = cv::remap(INTER_LINEAR)
+ * with the CV_32FC1 maps of cv::initUndistortRectifyMap (utils.cpp:119-124, calibration.cpp:60-70).  Device pointers;
+ * `count` images `stride` bytes apart (stride 0 = the same image / the same maps for every item); bit-exact vs cv2. */
+ZS_API zs_status zs_cvt_bgr2gray(zs_context* ctx, const uint8_t* d_bgr, size_t pitch, size_t stride, int width, int height,
+                                 int count, uint8_t* d_gray, size_t gray_pitch, size_t gray_stride);
+ZS_API zs_status zs_clahe(zs_context* ctx, const uint8_t* d_src, size_t pitch, size_t stride, int width, int height,
+                          int count, double clip_limit, int tiles_x, int tiles_y, uint8_t* d_dst, size_t dst_pitch,
+                          size_t dst_stride);
+/* map_pitch / map_stride are in floats; taps outside the source read 0 (BORDER_CONSTANT) */
+ZS_API zs_status zs_remap_linear(zs_context* ctx, const uint8_t* d_src, size_t pitch, size_t stride, int src_width,
+                                 int src_height, int count, const float* d_map_x, const float* d_map_y, size_t map_pitch,
+                                 size_t map_stride, int dst_width, int dst_height, uint8_t* d_dst, size_t dst_pitch,
+                                 size_t dst_stride);
+/* the image path of processor::process for one HOST image: channels 3 (BGR) or 1; map_x / map_y may be NULL (no
+ * rectification); `undistorted` receives width*height bytes (frame::processed::undistorted) */
+ZS_API zs_status zs_process_image_host(zs_context* ctx, const uint8_t* image, int channels, int width, int height,
+                                       size_t pitch, int clahe_enabled, double clahe_clip_limit, const float* map_x,
+                                       const float* map_y, uint8_t* undistorted);
+
 /* ---- pyramids: cv::buildOpticalFlowPyramid(img, pyr, win, maxLevel, withDerivatives=true) ----
  * utils::pyramid (zenslam_core/source/utils/utils_opencv.cpp:525-530; called processor.cpp:37,53).
  * One zs_pyramid holds `slots` images of identical size.  Level l of slot s is an image plane
@@ -79,6 +99,9 @@ ZS_API zs_status zs_pyramid_upload(zs_context* ctx, zs_pyramid* p, const uint8_t
                                    size_t stride, int first, int count, int src_is_host);
 /* build levels 1.. and all derivative planes for slots first..first+count-1 (modulo slots) */
 ZS_API zs_status zs_pyramid_build(zs_context* ctx, zs_pyramid* p, int first, int count);
+/* device address of the level-0 interior of a slot (pitch / slot stride in bytes): lets the pre-processing kernels
+ * above produce a frame directly where the pyramid kernels read it */
+ZS_API zs_status zs_pyramid_level0(const zs_pyramid* p, int slot, uint8_t** d_ptr, size_t* pitch, size_t* slot_stride);
 /* test access: copy one un-padded level image (u8, w*h) / derivative plane (int16, w*h*2) to host */
 ZS_API zs_status zs_pyramid_download_image(zs_context* ctx, const zs_pyramid* p, int slot, int level, uint8_t* dst);
 ZS_API zs_status zs_pyramid_download_deriv(zs_context* ctx, const zs_pyramid* p, int slot, int level, int16_t* dst);

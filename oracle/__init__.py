@@ -307,3 +307,40 @@ def corner_subpix(img, xy, win=(5, 5), max_iters=30, eps=0.01):
                                     C.c_int, C.c_double]
     L.zso_corner_subpix(_p(img), w, h, w, _p(out), len(out), win[0], win[1], max_iters, float(eps))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# pre-processing (processor::process): BGR->gray, CLAHE, remap
+# ---------------------------------------------------------------------------------------------
+def bgr2gray(bgr):
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    h, w, c = bgr.shape
+    assert c == 3
+    out = np.empty((h, w), np.uint8)
+    L = lib()
+    L.zso_bgr2gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.zso_bgr2gray(_p(bgr), w, h, 3 * w, _p(out), w)
+    return out
+
+
+def clahe(img, clip_limit=4.0, tiles=(8, 8)):
+    img = _u8img(img)
+    h, w = img.shape
+    out = np.empty_like(img)
+    L = lib()
+    L.zso_clahe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.zso_clahe(_p(img), w, h, w, float(clip_limit), tiles[0], tiles[1], _p(out), w)
+    return out
+
+
+def remap_linear(img, map_x, map_y):
+    img = _u8img(img)
+    h, w = img.shape
+    map_x = np.ascontiguousarray(map_x, np.float32); map_y = np.ascontiguousarray(map_y, np.float32)
+    dh, dw = map_x.shape
+    out = np.empty((dh, dw), np.uint8)
+    L = lib()
+    L.zso_remap_linear.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_int]
+    L.zso_remap_linear(_p(img), w, h, w, _p(map_x), _p(map_y), dw, dw, dh, _p(out), dw)
+    return out

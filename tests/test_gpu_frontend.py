@@ -232,3 +232,26 @@ def test_keypoint_detector_parallel_mirror(ctx, golden):
     assert np.array_equal(np.array([k.response for k in kps], np.float32), s[kept].astype(np.float32))
     assert np.array_equal(np.stack([k.descriptor for k in kps]), desc)
     assert any(k.pt[0] != int(k.pt[0]) for k in kps)                  # points really are sub-pixel
+
+
+def test_processor_mirror_golden_and_oracle(ctx, golden):
+    """pre-processing on the device (processor.cpp:25-55): against the cv2 fixture and, at full frame size, the oracle"""
+    from zenslam_b200.processing import processor
+    g = golden("preproc")
+    maps = [(g["map_x"], g["map_y"])]
+    assert np.array_equal(processor(ctx).process_image(g["bgr"]), g["cv_gray"])
+    assert np.array_equal(processor(ctx, clahe_enabled=True).process_image(g["bgr"]), g["cv_clahe"])
+    assert np.array_equal(processor(ctx, maps=maps).process_image(g["bgr"]), g["cv_remap_gray"])
+    assert np.array_equal(processor(ctx, clahe_enabled=True, maps=maps).process_image(g["bgr"]), g["cv_remap_clahe"])
+    assert np.array_equal(processor(ctx, clahe_enabled=True, maps=maps).process_image(g["cv_gray"]), g["cv_remap_clahe"])   # gray input
+    # full-size frame, width not a multiple of 4 in the BGR rows, against the oracle
+    w, h = 750, 478
+    rng = np.random.default_rng(5)
+    tex = syn.crop(syn.base_texture(752, 480, 77), 752, 480, 0, 0)[:h, :w]
+    bgr = np.stack([tex, np.roll(tex, 3, 1), 255 - tex], -1).astype(np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    r2 = ((xx - w / 2) ** 2 + (yy - h / 2) ** 2) / (w * w / 4)
+    mx = (w / 2 + (xx - w / 2) * (1 + 0.11 * r2)).astype(np.float32); my = (h / 2 + (yy - h / 2) * (1 + 0.11 * r2)).astype(np.float32)
+    want = oracle.remap_linear(oracle.clahe(oracle.bgr2gray(bgr), 4.0), mx, my)
+    got = processor(ctx, clahe_enabled=True, maps=[(mx, my)]).process_image(bgr)
+    assert np.array_equal(got, want)

@@ -147,3 +147,15 @@ def test_corner_subpix_golden(golden):
     flat = np.full((64, 64), 77, np.uint8)
     p = np.array([[20.5, 30.25]], np.float32)
     assert np.array_equal(oracle.corner_subpix(flat, p), p)            # singular normal matrix: point unchanged
+
+
+def test_preprocessing_golden(golden):
+    """processor::process image path: BGR->gray, CLAHE(4.0), remap(INTER_LINEAR) -- bit-exact against cv2"""
+    g = golden("preproc")
+    gray = oracle.bgr2gray(g["bgr"])
+    assert np.array_equal(gray, g["cv_gray"])
+    cl = oracle.clahe(gray, 4.0)
+    assert np.array_equal(cl, g["cv_clahe"])
+    assert np.array_equal(oracle.clahe(gray, 2.0, (4, 6)), g["cv_clahe_2_4x6"])
+    assert np.array_equal(oracle.remap_linear(gray, g["map_x"], g["map_y"]), g["cv_remap_gray"])
+    assert np.array_equal(oracle.remap_linear(cl, g["map_x"], g["map_y"]), g["cv_remap_clahe"])

@@ -60,6 +60,11 @@ SIGNATURES = {
     "zs_context_synchronize": (I, [P]),
     "zs_context_stream": (P, [P]),
     "zs_context_launch_count": (C.c_uint64, [P]),
+    "zs_cvt_bgr2gray": (I, [P, P, Z, Z, I, I, I, P, Z, Z]),
+    "zs_clahe": (I, [P, P, Z, Z, I, I, I, D, I, I, P, Z, Z]),
+    "zs_remap_linear": (I, [P, P, Z, Z, I, I, I, P, P, Z, Z, I, I, P, Z, Z]),
+    "zs_process_image_host": (I, [P, P, I, I, I, Z, I, D, P, P, P]),
+    "zs_pyramid_level0": (I, [P, I, C.POINTER(P), C.POINTER(Z), C.POINTER(Z)]),
     "zs_pyramid_create": (I, [P, I, I, I, I, I, I, C.POINTER(P)]),
     "zs_pyramid_destroy": (None, [P]),
     "zs_pyramid_levels": (I, [P]),
