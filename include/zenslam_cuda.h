@@ -234,6 +234,14 @@ ZS_API zs_status zs_match_host(zs_context* ctx, const void* q, int nq, const voi
 ZS_API zs_status zs_knn_match_host(zs_context* ctx, const void* q, int nq, const void* t, int nt, int dim,
                                    int norm, int k, int cross_check, int* idx, float* dist);
 
+/* keypoint_tracker::assign_landmark_indices, descriptor stage (zenslam_core/source/tracking/keypoint_tracker.cpp:262-287;
+ * SURVEY 8 f2): cv::BFMatcher(NORM_HAMMING, crossCheck=true).match(new keypoints, landmarks) gated by
+ * distance <= max_descriptor_distance.  n keypoint rows against m landmark rows (m can be 10^4..10^5: the train side is
+ * split across blocks).  landmark_row[i] = matched landmark row or -1; the radius search that selects the landmarks
+ * and the index bookkeeping stay on the host. */
+ZS_API zs_status zs_assign_landmarks_host(zs_context* ctx, const uint8_t* keypoint_desc, int n, const uint8_t* landmark_desc,
+                                          int m, double max_descriptor_distance, int* landmark_row, float* distance);
+
 /* ---- batched stereo front-end ------------------------------------------------------------------
  * The per-frame call pattern of keypoint_tracker::track (keypoint_tracker.cpp:41-105) restated for
  * a batch of B consecutive stereo frames: per frame 2 pyramids, 2 grid detections + ORB, 1 stereo

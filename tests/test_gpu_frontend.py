@@ -255,3 +255,29 @@ def test_processor_mirror_golden_and_oracle(ctx, golden):
     want = oracle.remap_linear(oracle.clahe(oracle.bgr2gray(bgr), 4.0), mx, my)
     got = processor(ctx, clahe_enabled=True, maps=[(mx, my)]).process_image(bgr)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n,m", [(1100, 30000), (37, 5000), (300, 2049)])
+def test_assign_landmark_indices_large_map(ctx, n, m):
+    """new keypoints against a large landmark map (rectangular Hamming, train side split across blocks),
+    cross-check + distance gate of keypoint_tracker.cpp:262-287, against the oracle"""
+    from zenslam_b200 import keypoint
+    from zenslam_b200.matching import assign_landmark_indices
+    rng = np.random.default_rng(n + m)
+    lm = rng.integers(0, 256, (m, 32), dtype=np.uint8)
+    q = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    src = rng.choice(m, n // 2, replace=False)
+    q[:n // 2] = lm[src]                                              # true landmarks, some with a few flipped bits
+    flip = rng.integers(0, 32, n // 2)
+    q[np.arange(n // 2), flip] ^= rng.integers(0, 4, n // 2).astype(np.uint8)
+    lm[(src[:5] + 1) % m] = lm[src[:5]]                               # duplicated landmarks: ties resolved by index
+    kps = [keypoint(pt=(0.0, 0.0), index=10_000_000 + i, descriptor=q[i]) for i in range(n)]
+    kps[3].descriptor = None                                          # keypoints without descriptors are skipped
+    landmark_indices = np.arange(m) * 7 + 3
+    got_n = assign_landmark_indices(ctx, kps, lm, landmark_indices, 32.0)
+    rows = [i for i in range(n) if i != 3]
+    oq, ot, od = oracle.match_hamming_cross(q[rows], lm)
+    want = {rows[a]: int(landmark_indices[b]) for a, b, d in zip(oq, ot, od) if d <= 32.0}
+    assert got_n == len(want) and got_n >= n // 4
+    for i, kp in enumerate(kps):
+        assert kp.index == want.get(i, 10_000_000 + i), i

@@ -89,6 +89,7 @@ SIGNATURES = {
     "zs_detect_keypoints_parallel_host": (I, [P, P, I, I, Z, I, I, I, P, P, P, P, P, C.POINTER(I)]),
     "zs_match_host": (I, [P, P, I, P, I, I, I, I, D, P, P, P, C.POINTER(I)]),
     "zs_knn_match_host": (I, [P, P, I, P, I, I, I, I, I, P, P]),
+    "zs_assign_landmarks_host": (I, [P, P, I, P, I, D, P, P]),
     "zs_frontend_create": (I, [P, C.POINTER(FrontendOptions), C.POINTER(P)]),
     "zs_frontend_destroy": (None, [P]),
     "zs_frontend_capacity": (I, [P]),

@@ -232,3 +232,18 @@ extern "C" zs_status zs_knn_match_host(zs_context* ctx, const void* q, int nq, c
         for (int j = 0; j < k; ++j) { idx[i * k + j] = h_idx[i * per + j]; dist[i * k + j] = h_dist[i * per + j]; }
     return ZS_OK;
 }
+
+// keypoint_tracker::assign_landmark_indices, descriptor stage (keypoint_tracker.cpp:262-287): cross-checked 1-NN of the
+// new keypoints' descriptors against the landmark descriptors, kept when distance <= max_descriptor_distance.
+extern "C" zs_status zs_assign_landmarks_host(zs_context* ctx, const uint8_t* keypoint_desc, int n, const uint8_t* landmark_desc,
+                                              int m, double max_descriptor_distance, int* landmark_row, float* distance)
+{
+    ZS_REQUIRE(ctx, "null argument");
+    if (n <= 0) return ZS_OK;
+    ZS_REQUIRE(landmark_row && distance, "null argument");
+    zs_status st = zs_knn_match_host(ctx, keypoint_desc, n, landmark_desc, m, 32, 0, 1, 1, landmark_row, distance);
+    if (st != ZS_OK) return st;
+    for (int i = 0; i < n; ++i)
+        if (landmark_row[i] >= 0 && !((double)distance[i] <= max_descriptor_distance)) { landmark_row[i] = -1; distance[i] = 0.f; }
+    return ZS_OK;
+}

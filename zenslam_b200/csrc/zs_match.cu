@@ -24,24 +24,29 @@ __device__ __forceinline__ void top2_update(top2& t, int d, int j)
     else if (d < t.d1) { t.d1 = d; t.i1 = j; }
 }
 
-// grid: (ceil(cap_q / 128), pairs)
+// grid: (ceil(cap_q / 128), splits, pairs).  With splits > 1 (large rectangular problems: new keypoints against the
+// landmark map, keypoint_tracker.cpp:199-291) block y sweeps train rows [y*chunk, (y+1)*chunk) and writes a partial
+// top-2 (int4 i0,i1,d0,d1) per (query, split); k_top2_merge folds the partials in ascending split order.
 __global__ void __launch_bounds__(MATCH_THREADS) k_hamming_top2(
     const uint8_t* __restrict__ q, const int* __restrict__ nq, size_t q_stride,
     const uint8_t* __restrict__ t, const int* __restrict__ nt, size_t t_stride,
-    int* __restrict__ o_idx, int* __restrict__ o_dist, int out_stride /* ints per pair */)
+    int* __restrict__ o_idx, int* __restrict__ o_dist, int out_stride /* ints per pair */,
+    int chunk, int splits, int cap_q, int4* __restrict__ part)
 {
     __shared__ uint4 tile[MATCH_TILE * 2];
-    const int pair = blockIdx.y;
+    const int pair = blockIdx.z;
     const int n_q = nq[pair], n_t = nt[pair];
     const int qi = blockIdx.x * MATCH_THREADS + threadIdx.x;
     if (blockIdx.x * MATCH_THREADS >= n_q) return;
+    const int t_begin = blockIdx.y * chunk, t_end = min(n_t, t_begin + chunk);
+    if (splits > 1 && t_begin >= n_t) return;             // the merge only reads splits that exist
     const uint4* qp = (const uint4*)(q + (size_t)pair * q_stride);
     const uint4* tp = (const uint4*)(t + (size_t)pair * t_stride);
     uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
     if (qi < n_q) { qa = qp[2 * qi]; qb = qp[2 * qi + 1]; }
     top2 best = { 0x7fffffff, 0x7fffffff, -1, -1 };
-    for (int base = 0; base < n_t; base += MATCH_TILE) {
-        const int m = min(MATCH_TILE, n_t - base);
+    for (int base = t_begin; base < t_end; base += MATCH_TILE) {
+        const int m = min(MATCH_TILE, t_end - base);
         __syncthreads();
         for (int i = threadIdx.x; i < 2 * m; i += MATCH_THREADS) tile[i] = tp[2 * base + i];
         __syncthreads();
@@ -54,10 +59,32 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_hamming_top2(
         }
     }
     if (qi < n_q) {
-        int* oi = o_idx + (size_t)pair * out_stride + 2 * qi;
-        int* od = o_dist + (size_t)pair * out_stride + 2 * qi;
-        oi[0] = best.i0; oi[1] = best.i1; od[0] = best.d0; od[1] = best.d1;
+        if (splits > 1) {
+            part[((size_t)pair * cap_q + qi) * splits + blockIdx.y] = make_int4(best.i0, best.i1, best.d0, best.d1);
+        } else {
+            int* oi = o_idx + (size_t)pair * out_stride + 2 * qi;
+            int* od = o_dist + (size_t)pair * out_stride + 2 * qi;
+            oi[0] = best.i0; oi[1] = best.i1; od[0] = best.d0; od[1] = best.d1;
+        }
     }
+}
+
+// fold per-split partial top-2 in ascending split (= ascending train index) order; strict '<' keeps the tie rule
+__global__ void __launch_bounds__(256) k_top2_merge(const int4* __restrict__ part, const int* __restrict__ nq, const int* __restrict__ nt,
+                                                    int cap_q, int chunk, int splits, int* __restrict__ o_idx, int* __restrict__ o_dist)
+{
+    const int pair = blockIdx.y, qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= min(nq[pair], cap_q)) return;
+    const int valid = min(splits, (nt[pair] + chunk - 1) / chunk);
+    const int4* p = part + ((size_t)pair * cap_q + qi) * splits;
+    top2 best = { 0x7fffffff, 0x7fffffff, -1, -1 };
+    for (int s = 0; s < valid; ++s) {
+        const int4 v = p[s];
+        if (v.x >= 0) top2_update(best, v.z, v.x);
+        if (v.y >= 0) top2_update(best, v.w, v.y);
+    }
+    const size_t o = 2 * ((size_t)pair * cap_q + qi);
+    o_idx[o] = best.i0; o_idx[o + 1] = best.i1; o_dist[o] = best.d0; o_dist[o + 1] = best.d1;
 }
 
 // knn2 epilogue: int distances -> float, ratio gate of matcher.cpp:70
@@ -163,12 +190,28 @@ __global__ void k_f32_to_u8(const float* __restrict__ src, const int* __restrict
     dst[(size_t)pair * cap * dim + i] = (uint8_t)r;
 }
 
-static zs_status hamming_top2(zs_context* ctx, const uint8_t* q, const int* nq, size_t qs, const uint8_t* t, const int* nt,
-                              size_t ts, int pairs, int cap_q, int* idx, int* dist)
+#define HAMMING_SPLIT_CHUNK 2048          // train rows per split once a problem has more than 2 chunks
+
+static int hamming_splits(int cap_t) { return cap_t > 2 * HAMMING_SPLIT_CHUNK ? zs_div_up(cap_t, HAMMING_SPLIT_CHUNK) : 1; }
+// ints of scratch the partial top-2 of one direction need (0 when the train side is not split)
+static size_t hamming_part_ints(int pairs, int cap_q, int cap_t)
 {
-    k_hamming_top2<<<dim3(zs_div_up(cap_q, MATCH_THREADS), pairs), MATCH_THREADS, 0, ctx->stream>>>(
-        q, nq, qs, t, nt, ts, idx, dist, 2 * cap_q);
+    const int sp = hamming_splits(cap_t);
+    return sp > 1 ? 4 * (size_t)pairs * cap_q * sp : 0;
+}
+
+static zs_status hamming_top2(zs_context* ctx, const uint8_t* q, const int* nq, size_t qs, const uint8_t* t, const int* nt,
+                              size_t ts, int pairs, int cap_q, int cap_t, int* idx, int* dist, void* part)
+{
+    const int splits = hamming_splits(cap_t);
+    const int chunk = splits > 1 ? HAMMING_SPLIT_CHUNK : 0x7fffffff;
+    k_hamming_top2<<<dim3(zs_div_up(cap_q, MATCH_THREADS), splits, pairs), MATCH_THREADS, 0, ctx->stream>>>(
+        q, nq, qs, t, nt, ts, idx, dist, 2 * cap_q, chunk, splits, cap_q, (int4*)part);
     ZS_LAUNCH_CHECK(ctx);
+    if (splits > 1) {
+        k_top2_merge<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>((const int4*)part, nq, nt, cap_q, chunk, splits, idx, dist);
+        ZS_LAUNCH_CHECK(ctx);
+    }
     return ZS_OK;
 }
 
@@ -182,10 +225,10 @@ extern "C" zs_status zs_match_hamming_knn2(zs_context* ctx, const uint8_t* d_q, 
                "descriptor arrays must be 16-byte aligned");
     if (pairs == 0) return ZS_OK;
     void* s;
-    zs_status st = zs_scratch(ctx, sizeof(int) * 4 * (size_t)cap_q * pairs, &s);
+    zs_status st = zs_scratch(ctx, sizeof(int) * (4 * (size_t)cap_q * pairs + hamming_part_ints(pairs, cap_q, cap_t)), &s);
     if (st != ZS_OK) return st;
     int* ti = (int*)s; int* td = ti + 2 * (size_t)cap_q * pairs;
-    st = hamming_top2(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, ti, td);
+    st = hamming_top2(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, cap_t, ti, td, td + 2 * (size_t)cap_q * pairs);
     if (st != ZS_OK) return st;
     k_knn2_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(ti, td, d_nq, cap_q, ratio, 0, d_idx, d_dist, d_pass);
     ZS_LAUNCH_CHECK(ctx);
@@ -202,13 +245,15 @@ extern "C" zs_status zs_match_hamming_cross(zs_context* ctx, const uint8_t* d_q,
                "descriptor arrays must be 16-byte aligned");
     if (pairs == 0) return ZS_OK;
     void* s;
-    zs_status st = zs_scratch(ctx, sizeof(int) * 4 * ((size_t)cap_q + cap_t) * pairs, &s);
+    zs_status st = zs_scratch(ctx, sizeof(int) * (4 * ((size_t)cap_q + cap_t) * pairs +
+                                                  std::max(hamming_part_ints(pairs, cap_q, cap_t), hamming_part_ints(pairs, cap_t, cap_q))), &s);
     if (st != ZS_OK) return st;
     int* fi = (int*)s; int* fd = fi + 2 * (size_t)cap_q * pairs;
     int* bi = fd + 2 * (size_t)cap_q * pairs; int* bd = bi + 2 * (size_t)cap_t * pairs;
-    st = hamming_top2(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, fi, fd);
+    void* part = bd + 2 * (size_t)cap_t * pairs;          // 16-byte aligned: every piece before it is a multiple of 16 bytes
+    st = hamming_top2(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, cap_t, fi, fd, part);
     if (st != ZS_OK) return st;
-    st = hamming_top2(ctx, d_t, d_nt, t_stride, d_q, d_nq, q_stride, pairs, cap_t, bi, bd);
+    st = hamming_top2(ctx, d_t, d_nt, t_stride, d_q, d_nq, q_stride, pairs, cap_t, cap_q, bi, bd, part);
     if (st != ZS_OK) return st;
     k_cross_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(fi, fd, bi, d_nq, cap_q, cap_t, 0, d_idx, d_dist);
     ZS_LAUNCH_CHECK(ctx);

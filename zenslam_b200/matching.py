@@ -64,3 +64,27 @@ class matcher:
             return []
         d0 = np.stack([kp.descriptor for kp in un_l]); d1 = np.stack([kp.descriptor for kp in un_r])
         return self._finish(self._match_rows(d0, d1), un_l, un_r)
+
+
+def assign_landmark_indices(ctx: Context, keypoints: list, landmark_descriptors: np.ndarray, landmark_indices,
+                            max_descriptor_distance: float) -> int:
+    """keypoint_tracker::assign_landmark_indices, after the radius search has picked the candidate landmarks
+    (zenslam_core/source/tracking/keypoint_tracker.cpp:199-291): cross-checked Hamming 1-NN of the keypoints that carry
+    a descriptor against the landmark descriptors; a keypoint whose match has distance <= max_descriptor_distance takes
+    the landmark's index.  Mutates `keypoints` like the reference; returns the number of re-indexed keypoints."""
+    if not keypoints or landmark_descriptors is None or len(landmark_descriptors) == 0:
+        return 0
+    rows = [i for i, kp in enumerate(keypoints) if kp.descriptor is not None and len(kp.descriptor)]
+    if not rows:
+        return 0
+    q = np.ascontiguousarray(np.stack([keypoints[i].descriptor for i in rows]), np.uint8)
+    t = np.ascontiguousarray(landmark_descriptors, np.uint8)
+    lm = np.empty(len(rows), np.int32); dist = np.empty(len(rows), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(lib().zs_assign_landmarks_host(ctx._h, p(q), len(rows), p(t), len(t), float(max_descriptor_distance), p(lm), p(dist)))
+    n = 0
+    for j, i in enumerate(rows):
+        if lm[j] >= 0:
+            keypoints[i].index = int(landmark_indices[int(lm[j])])
+            n += 1
+    return n
