@@ -27,7 +27,29 @@ __device__ __forceinline__ void top2_update(top2& t, int d, int j)
 // grid: (ceil(cap_q / 128), splits, pairs).  With splits > 1 (large rectangular problems: new keypoints against the
 // landmark map, keypoint_tracker.cpp:199-291) block y sweeps train rows [y*chunk, (y+1)*chunk) and writes a partial
 // top-2 (int4 i0,i1,d0,d1) per (query, split); k_top2_merge folds the partials in ascending split order.
-__global__ void __launch_bounds__(MATCH_THREADS) k_hamming_top2(
+// popcount of a 256-bit XOR with 4 POPC instead of 8: POPC issues at a quarter of the LOP3 rate on sm_100 (the kernel
+// was POPC-bound: 1.28 G POPC per 128-pair batch at ~16 per clock per SM), so the eight words are first reduced with
+// carry-save adders (LOP3 0x96 = a^b^c, 0xe8 = majority) to one word each of weight 1, 2, 4 and 8.
+__device__ __forceinline__ int hamming256(const uint4& qa, const uint4& qb, const uint4& a, const uint4& b)
+{
+    const unsigned w0 = qa.x ^ a.x, w1 = qa.y ^ a.y, w2 = qa.z ^ a.z, w3 = qa.w ^ a.w;
+    const unsigned w4 = qb.x ^ b.x, w5 = qb.y ^ b.y, w6 = qb.z ^ b.z, w7 = qb.w ^ b.w;
+    const unsigned s1 = w0 ^ w1 ^ w2, c1 = (w0 & w1) | (w2 & (w0 | w1));
+    const unsigned s2 = w3 ^ w4 ^ w5, c2 = (w3 & w4) | (w5 & (w3 | w4));
+    const unsigned s3 = s1 ^ s2 ^ w6, c3 = (s1 & s2) | (w6 & (s1 | s2));
+    const unsigned ones = s3 ^ w7, c4 = s3 & w7;
+    const unsigned s5 = c1 ^ c2 ^ c3, c5 = (c1 & c2) | (c3 & (c1 | c2));
+    const unsigned twos = s5 ^ c4, c6 = s5 & c4;
+    const unsigned fours = c5 ^ c6, eights = c5 & c6;
+    return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
+}
+
+// Each thread owns HQ query descriptors in registers (8 x u32 each): one pair of broadcast 128-bit shared loads of a train
+// row then feeds HQ distances, so the shared-memory pipe (the limiter of the one-query-per-thread form: ncu showed
+// mio_throttle as the top stall) carries a quarter of the traffic per distance.
+#define HAMMING_THREADS 128
+template <int HQ, bool CSA>
+__global__ void __launch_bounds__(HAMMING_THREADS) k_hamming_top2(
     const uint8_t* __restrict__ q, const int* __restrict__ nq, size_t q_stride,
     const uint8_t* __restrict__ t, const int* __restrict__ nt, size_t t_stride,
     int* __restrict__ o_idx, int* __restrict__ o_dist, int out_stride /* ints per pair */,
@@ -36,35 +58,50 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_hamming_top2(
     __shared__ uint4 tile[MATCH_TILE * 2];
     const int pair = blockIdx.z;
     const int n_q = nq[pair], n_t = nt[pair];
-    const int qi = blockIdx.x * MATCH_THREADS + threadIdx.x;
-    if (blockIdx.x * MATCH_THREADS >= n_q) return;
+    const int q0 = blockIdx.x * (HAMMING_THREADS * HQ);
+    if (q0 >= n_q) return;
     const int t_begin = blockIdx.y * chunk, t_end = min(n_t, t_begin + chunk);
     if (splits > 1 && t_begin >= n_t) return;             // the merge only reads splits that exist
     const uint4* qp = (const uint4*)(q + (size_t)pair * q_stride);
     const uint4* tp = (const uint4*)(t + (size_t)pair * t_stride);
-    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
-    if (qi < n_q) { qa = qp[2 * qi]; qb = qp[2 * qi + 1]; }
-    top2 best = { 0x7fffffff, 0x7fffffff, -1, -1 };
+    // query k of this thread is row q0 + k*HAMMING_THREADS + threadIdx.x (consecutive threads read consecutive rows)
+    uint4 qa[HQ], qb[HQ];
+    top2 best[HQ];
+#pragma unroll
+    for (int k = 0; k < HQ; ++k) {
+        const int qi = q0 + k * HAMMING_THREADS + threadIdx.x;
+        qa[k] = make_uint4(0, 0, 0, 0); qb[k] = qa[k];
+        if (qi < n_q) { qa[k] = qp[2 * qi]; qb[k] = qp[2 * qi + 1]; }
+        best[k].d0 = best[k].d1 = 0x7fffffff; best[k].i0 = best[k].i1 = -1;
+    }
     for (int base = t_begin; base < t_end; base += MATCH_TILE) {
         const int m = min(MATCH_TILE, t_end - base);
         __syncthreads();
-        for (int i = threadIdx.x; i < 2 * m; i += MATCH_THREADS) tile[i] = tp[2 * base + i];
+        for (int i = threadIdx.x; i < 2 * m; i += HAMMING_THREADS) tile[i] = tp[2 * base + i];
         __syncthreads();
 #pragma unroll 4
         for (int j = 0; j < m; ++j) {
             const uint4 a = tile[2 * j], b = tile[2 * j + 1];
-            const int d = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) +
-                          __popc(qb.x ^ b.x) + __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
-            top2_update(best, d, base + j);
+#pragma unroll
+            for (int k = 0; k < HQ; ++k) {
+                int d;
+                if (CSA) d = hamming256(qa[k], qb[k], a, b);
+                else d = __popc(qa[k].x ^ a.x) + __popc(qa[k].y ^ a.y) + __popc(qa[k].z ^ a.z) + __popc(qa[k].w ^ a.w) +
+                         __popc(qb[k].x ^ b.x) + __popc(qb[k].y ^ b.y) + __popc(qb[k].z ^ b.z) + __popc(qb[k].w ^ b.w);
+                top2_update(best[k], d, base + j);
+            }
         }
     }
-    if (qi < n_q) {
+#pragma unroll
+    for (int k = 0; k < HQ; ++k) {
+        const int qi = q0 + k * HAMMING_THREADS + threadIdx.x;
+        if (qi >= n_q) continue;
         if (splits > 1) {
-            part[((size_t)pair * cap_q + qi) * splits + blockIdx.y] = make_int4(best.i0, best.i1, best.d0, best.d1);
+            part[((size_t)pair * cap_q + qi) * splits + blockIdx.y] = make_int4(best[k].i0, best[k].i1, best[k].d0, best[k].d1);
         } else {
             int* oi = o_idx + (size_t)pair * out_stride + 2 * qi;
             int* od = o_dist + (size_t)pair * out_stride + 2 * qi;
-            oi[0] = best.i0; oi[1] = best.i1; od[0] = best.d0; od[1] = best.d1;
+            oi[0] = best[k].i0; oi[1] = best[k].i1; od[0] = best[k].d0; od[1] = best[k].d1;
         }
     }
 }
@@ -190,23 +227,48 @@ __global__ void k_f32_to_u8(const float* __restrict__ src, const int* __restrict
     dst[(size_t)pair * cap * dim + i] = (uint8_t)r;
 }
 
-#define HAMMING_SPLIT_CHUNK 2048          // train rows per split once a problem has more than 2 chunks
+// Train-side splitting: a block sweeps `chunk` train rows.  Large maps are cut into 2048-row chunks; small problems are
+// cut too when the grid would otherwise leave the machine short of warps (the kernel is latency-bound per warp).
+#define HAMMING_SPLIT_CHUNK 2048
+static int g_hamming_split_override = -1;
 
-static int hamming_splits(int cap_t) { return cap_t > 2 * HAMMING_SPLIT_CHUNK ? zs_div_up(cap_t, HAMMING_SPLIT_CHUNK) : 1; }
+static int hamming_splits(int pairs, int cap_q, int cap_t)
+{
+    if (g_hamming_split_override < 0) { const char* e = getenv("ZS_HAMMING_SPLITS"); g_hamming_split_override = e ? atoi(e) : 0; }
+    if (cap_t > 2 * HAMMING_SPLIT_CHUNK) return zs_div_up(cap_t, HAMMING_SPLIT_CHUNK);
+    if (g_hamming_split_override > 0) return g_hamming_split_override;
+    const long long blocks = (long long)zs_div_up(cap_q, 128) * pairs;
+    int sp = (int)((148LL * 32 + blocks - 1) / blocks);
+    const int max_sp = cap_t / 256 > 0 ? cap_t / 256 : 1;
+    sp = sp < 1 ? 1 : sp > 8 ? 8 : sp;
+    return sp > max_sp ? max_sp : sp;
+}
+static int hamming_chunk(int cap_t, int splits) { return splits > 1 ? (zs_div_up(cap_t, splits) + 127) / 128 * 128 : 0x7fffffff; }
 // ints of scratch the partial top-2 of one direction need (0 when the train side is not split)
 static size_t hamming_part_ints(int pairs, int cap_q, int cap_t)
 {
-    const int sp = hamming_splits(cap_t);
+    const int sp = hamming_splits(pairs, cap_q, cap_t);
     return sp > 1 ? 4 * (size_t)pairs * cap_q * sp : 0;
 }
 
 static zs_status hamming_top2(zs_context* ctx, const uint8_t* q, const int* nq, size_t qs, const uint8_t* t, const int* nt,
                               size_t ts, int pairs, int cap_q, int cap_t, int* idx, int* dist, void* part)
 {
-    const int splits = hamming_splits(cap_t);
-    const int chunk = splits > 1 ? HAMMING_SPLIT_CHUNK : 0x7fffffff;
-    k_hamming_top2<<<dim3(zs_div_up(cap_q, MATCH_THREADS), splits, pairs), MATCH_THREADS, 0, ctx->stream>>>(
-        q, nq, qs, t, nt, ts, idx, dist, 2 * cap_q, chunk, splits, cap_q, (int4*)part);
+    const int splits = hamming_splits(pairs, cap_q, cap_t);
+    const int chunk = cap_t > 2 * HAMMING_SPLIT_CHUNK ? HAMMING_SPLIT_CHUNK : hamming_chunk(cap_t, splits);
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("ZS_HAMMING_VARIANT"); variant = e ? atoi(e) : 0; }
+#define HAM_LAUNCH(HQ_, CSA_)                                                                                                   \
+    k_hamming_top2<HQ_, CSA_><<<dim3(zs_div_up(cap_q, HAMMING_THREADS * HQ_), splits, pairs), HAMMING_THREADS, 0, ctx->stream>>>( \
+        q, nq, qs, t, nt, ts, idx, dist, 2 * cap_q, chunk, splits, cap_q, (int4*)part)
+    switch (variant) {
+    case 2: HAM_LAUNCH(2, false); break;
+    case 3: HAM_LAUNCH(2, true); break;
+    case 4: HAM_LAUNCH(4, true); break;
+    case 5: HAM_LAUNCH(1, false); break;
+    default: HAM_LAUNCH(1, true); break;
+    }
+#undef HAM_LAUNCH
     ZS_LAUNCH_CHECK(ctx);
     if (splits > 1) {
         k_top2_merge<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>((const int4*)part, nq, nt, cap_q, chunk, splits, idx, dist);

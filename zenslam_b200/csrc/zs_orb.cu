@@ -192,7 +192,19 @@ __global__ void __launch_bounds__(256) k_orb_describe(zs_pyr_view v, int first, 
     if (blockIdx.x * 8 >= counts[img]) return;         // whole block idle
     // (the table row a lane needs for bit b is 8*lane + b: read straight from global memory that is one 16-byte
     // piece out of 32 different cache lines per load -- the kernel used to spend most of its time there)
-    s_pattern[(threadIdx.x & 7) * 32 + (threadIdx.x >> 3)] = g_orb_pattern[threadIdx.x];
+    {
+        int4 pt = g_orb_pattern[threadIdx.x];
+        if (!ab) {
+            // constant angle: store the two byte offsets (relative to the patch centre) instead of the coordinates
+            const float x0f = __fsub_rn(__fmul_rn((float)pt.x, a0), __fmul_rn((float)pt.y, b0));
+            const float y0f = __fadd_rn(__fmul_rn((float)pt.x, b0), __fmul_rn((float)pt.y, a0));
+            const float x1f = __fsub_rn(__fmul_rn((float)pt.z, a0), __fmul_rn((float)pt.w, b0));
+            const float y1f = __fadd_rn(__fmul_rn((float)pt.z, b0), __fmul_rn((float)pt.w, a0));
+            pt.x = __float2int_rn(y0f) * (ORB_PW * 4) + __float2int_rn(x0f);
+            pt.y = __float2int_rn(y1f) * (ORB_PW * 4) + __float2int_rn(x1f);
+        }
+        s_pattern[(threadIdx.x & 7) * 32 + (threadIdx.x >> 3)] = pt;
+    }
     __syncthreads();
     if (kp >= counts[img]) return;
     const size_t off = (size_t)img * cap + kp;
@@ -203,25 +215,45 @@ __global__ void __launch_bounds__(256) k_orb_describe(zs_pyr_view v, int first, 
     const int x0 = (cx - ORB_R) & ~3;                  // first staged column (4-byte aligned; the plane pitch is a multiple of 128)
     const uint8_t* src = v.blur + (size_t)slot * v.blur_slot + (size_t)(cy - ORB_R) * pitch + x0;
     uint32_t* sp = s_patch[warp];
-    for (int i = lane; i < ORB_ROWS * ORB_PW; i += 32) {
-        const int r = i / ORB_PW, c = i - r * ORB_PW;
-        sp[i] = *(const uint32_t*)(src + (size_t)r * pitch + 4 * c);
+    // 429 words = 13 full rounds of 32 lanes + 13 words: all loads are issued before the first store
+    uint32_t stage[14];
+#pragma unroll
+    for (int k = 0; k < 14; ++k) {
+        const int i = lane + 32 * k;
+        const int r = i / ORB_PW, cc = i - r * ORB_PW;
+        stage[k] = (i < ORB_ROWS * ORB_PW) ? *(const uint32_t*)(src + (size_t)r * pitch + 4 * cc) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 14; ++k) {
+        const int i = lane + 32 * k;
+        if (i < ORB_ROWS * ORB_PW) sp[i] = stage[k];
     }
     __syncwarp();
     const uint8_t* c = (const uint8_t*)sp + ORB_R * (ORB_PW * 4) + (cx - x0);     // the centre pixel inside the staged patch
-    float a = a0, b = b0;
-    if (ab) { const float2 t = ab[off]; a = t.x; b = t.y; }
     int val = 0;
+    if (ab) {
+        const float2 t = ab[off];
+        const float a = t.x, b = t.y;
 #pragma unroll
-    for (int bit = 0; bit < 8; ++bit) {
-        const int4 pt = s_pattern[bit * 32 + lane];
-        const float x0f = __fsub_rn(__fmul_rn((float)pt.x, a), __fmul_rn((float)pt.y, b));
-        const float y0f = __fadd_rn(__fmul_rn((float)pt.x, b), __fmul_rn((float)pt.y, a));
-        const float x1f = __fsub_rn(__fmul_rn((float)pt.z, a), __fmul_rn((float)pt.w, b));
-        const float y1f = __fadd_rn(__fmul_rn((float)pt.z, b), __fmul_rn((float)pt.w, a));
-        const int t0 = c[__float2int_rn(y0f) * (ORB_PW * 4) + __float2int_rn(x0f)];
-        const int t1 = c[__float2int_rn(y1f) * (ORB_PW * 4) + __float2int_rn(x1f)];
-        val |= (t0 < t1) << bit;
+        for (int bit = 0; bit < 8; ++bit) {
+            const int4 pt = s_pattern[bit * 32 + lane];
+            const float x0f = __fsub_rn(__fmul_rn((float)pt.x, a), __fmul_rn((float)pt.y, b));
+            const float y0f = __fadd_rn(__fmul_rn((float)pt.x, b), __fmul_rn((float)pt.y, a));
+            const float x1f = __fsub_rn(__fmul_rn((float)pt.z, a), __fmul_rn((float)pt.w, b));
+            const float y1f = __fadd_rn(__fmul_rn((float)pt.z, b), __fmul_rn((float)pt.w, a));
+            const int t0 = c[__float2int_rn(y0f) * (ORB_PW * 4) + __float2int_rn(x0f)];
+            const int t1 = c[__float2int_rn(y1f) * (ORB_PW * 4) + __float2int_rn(x1f)];
+            val |= (t0 < t1) << bit;
+        }
+    } else {
+        // every keypoint carries the same angle (FAST keypoints: -1 degree): the rotated, rounded sample offsets were
+        // computed once per block into s_pattern (see above), so a bit costs two shared loads and a compare
+#pragma unroll
+        for (int bit = 0; bit < 8; ++bit) {
+            const int4 pt = s_pattern[bit * 32 + lane];
+            const int t0 = c[pt.x], t1 = c[pt.y];
+            val |= (t0 < t1) << bit;
+        }
     }
     desc[off * 32 + lane] = (uint8_t)val;
 }
