@@ -407,7 +407,13 @@ __device__ __forceinline__ int dp2a_hi_su(int a_s16x2, unsigned b_u8, int c)
     return d;
 }
 
-#define KLT3_WARPS 4
+// One warp per CTA and 24 CTAs per SM: with 32-thread CTAs ptxas fits the tracker in 80 registers (28 bytes of spill)
+// instead of 125, so 24 warps instead of 16 hide the serial tail of every Gauss-Newton step (REDUX, 2x2 solve, TMA
+// waits); measured 13.25 -> 12.07 ms per 128-frame batch.  20 CTAs: 12.14 ms; 28: 13.3 ms; 32: 14.2 ms (spills).
+#define KLT3_WARPS 1
+#ifndef KLT4_MIN_BLOCKS
+#define KLT4_MIN_BLOCKS 24
+#endif
 #define KLT3_JP 12                   // J / I patch row pitch in words (48-byte TMA box)
 #define KLT3_DP 36                   // derivative patch row pitch in words
 #define KLT3_SJ_BYTES 1664           // 32 TMA rows x 48 B + one spill row read by masked pixels, 128-byte multiple
@@ -618,7 +624,7 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
 // passes: 0 = forward (one or two targets), 1 = backward of target 0, 2 = backward of target 1 (fb only); one
 // inlined instance of the tracker serves all passes (keeps the code inside the instruction cache).
 template <int WW, int WH>
-__global__ void __launch_bounds__(KLT3_WARPS * 32) k_klt_track_v4(klt_args a)
+__global__ void __launch_bounds__(KLT3_WARPS * 32, KLT4_MIN_BLOCKS) k_klt_track_v4(klt_args a)
 {
     extern __shared__ __align__(128) uint8_t smem3[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
