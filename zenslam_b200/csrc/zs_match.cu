@@ -214,17 +214,28 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_l2u8_top2(
     }
 }
 
-// float (integer-valued, 0..255) -> u8, flagging anything else
-__global__ void k_f32_to_u8(const float* __restrict__ src, const int* __restrict__ n, size_t src_stride, int cap, int dim,
-                            uint8_t* __restrict__ dst, int* __restrict__ bad)
+// float (integer-valued, 0..255) -> u8, flagging anything else; four values per thread (dim is a multiple of 4 and rows
+// are 16-byte aligned whenever the caller's stride is a multiple of 4 floats, which the launcher checks)
+__global__ void __launch_bounds__(256) k_f32_to_u8(const float* __restrict__ src, const int* __restrict__ n, size_t src_stride, int cap,
+                                                   int dim, uint8_t* __restrict__ dst, int* __restrict__ bad, int vec)
 {
     const int pair = blockIdx.y;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)min(n[pair], cap) * dim) return;
-    const float v = src[(size_t)pair * src_stride + i];
-    const int r = __float2int_rn(v);
-    if ((float)r != v || r < 0 || r > 255) atomicExch(bad, 1);
-    dst[(size_t)pair * cap * dim + i] = (uint8_t)r;
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const size_t total = (size_t)min(n[pair], cap) * dim;
+    if (i >= total) return;
+    const float* s = src + (size_t)pair * src_stride + i;
+    float v[4];
+    if (vec) { const float4 f = *(const float4*)s; v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w; }
+    else { v[0] = s[0]; v[1] = s[1]; v[2] = s[2]; v[3] = s[3]; }
+    uint32_t out = 0; bool wrong = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = __float2int_rn(v[k]);
+        wrong |= ((float)r != v[k] || r < 0 || r > 255);
+        out |= (uint32_t)(r & 255) << (8 * k);
+    }
+    if (wrong) atomicExch(bad, 1);
+    *(uint32_t*)(dst + (size_t)pair * cap * dim + i) = out;
 }
 
 // Train-side splitting: a block sweeps `chunk` train rows.  Large maps are cut into 2048-row chunks; small problems are
@@ -340,9 +351,10 @@ static zs_status l2_prepare(zs_context* ctx, const float* d_q, const int* d_nq, 
     int* bad = (int*)(*t8 + tb);
     *extra = bad + 64;
     ZS_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
-    k_f32_to_u8<<<dim3(zs_div_up(cap_q * dim, 256), pairs), 256, 0, ctx->stream>>>(d_q, d_nq, q_stride, cap_q, dim, *q8, bad);
+    const int vq = ((uintptr_t)d_q % 16 == 0 && q_stride % 4 == 0) ? 1 : 0, vt = ((uintptr_t)d_t % 16 == 0 && t_stride % 4 == 0) ? 1 : 0;
+    k_f32_to_u8<<<dim3(zs_div_up(zs_div_up(cap_q * dim, 4), 256), pairs), 256, 0, ctx->stream>>>(d_q, d_nq, q_stride, cap_q, dim, *q8, bad, vq);
     ZS_LAUNCH_CHECK(ctx);
-    k_f32_to_u8<<<dim3(zs_div_up(cap_t * dim, 256), pairs), 256, 0, ctx->stream>>>(d_t, d_nt, t_stride, cap_t, dim, *t8, bad);
+    k_f32_to_u8<<<dim3(zs_div_up(zs_div_up(cap_t * dim, 4), 256), pairs), 256, 0, ctx->stream>>>(d_t, d_nt, t_stride, cap_t, dim, *t8, bad, vt);
     ZS_LAUNCH_CHECK(ctx);
     int h_bad = 0;
     ZS_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -176,9 +176,15 @@ __global__ void __launch_bounds__(L2TC_THREADS) k_l2_tc_tile(const __grid_consta
         asm volatile("bar.sync 1, 128;" ::: "memory");       // s_tnorm complete (epilogue warps only)
         l2_mbar_wait(bar_acc, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        l2_top2 best = { 0x7fffffff, 0x7fffffff, -1, -1 };
+        // running top-2 over packed keys (d2 << 7 | column): d2 < 2^23 and a tile has 128 columns, so a key fits 30 bits and
+        // orders by distance first, column second -- exactly the stable rule (smaller train index wins a tie).  Per element:
+        // one IMAD for d2, one for the key, min / max / min for the two best.
+        unsigned k0 = 0x7fffffffu, k1 = 0x7fffffffu;
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16);
         const int ncol = min(L2TC_N, n_t - t0);
+        // masked columns get an infinite norm once, instead of a per-element bounds test in the loop
+        if (e >= ncol) s_tnorm[e] = 0x3fffffff;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
         for (int c0 = 0; c0 < L2TC_N; c0 += 32) {
             uint32_t v[32];
@@ -193,12 +199,19 @@ __global__ void __launch_bounds__(L2TC_THREADS) k_l2_tc_tile(const __grid_consta
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (c0 < ncol) {                                  // warp-uniform
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c0 + j < ncol) l2_top2_update(best, qn + s_tnorm[c0 + j] - 2 * (int)v[j], t0 + c0 + j);
+                for (int j = 0; j < 32; ++j) {
+                    const unsigned d2 = (unsigned)(qn + s_tnorm[c0 + j] - 2 * (int)v[j]);
+                    const unsigned key = d2 < 0x800000u ? (d2 << 7) | (unsigned)(c0 + j) : 0x7fffffffu;
+                    k1 = min(k1, max(k0, key));
+                    k0 = min(k0, key);
+                }
             }
         }
-        if (q0 + row < n_q)
-            a.part[((size_t)pair * a.cap_q + q0 + row) * a.splits + blockIdx.y] = make_int4(best.i0, best.i1, best.d0, best.d1);
+        if (q0 + row < n_q) {
+            const int i0 = k0 != 0x7fffffffu ? t0 + (int)(k0 & 127u) : -1, i1 = k1 != 0x7fffffffu ? t0 + (int)(k1 & 127u) : -1;
+            a.part[((size_t)pair * a.cap_q + q0 + row) * a.splits + blockIdx.y] =
+                make_int4(i0, i1, i0 >= 0 ? (int)(k0 >> 7) : 0x7fffffff, i1 >= 0 ? (int)(k1 >> 7) : 0x7fffffff);
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
