@@ -293,7 +293,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD, "batch_stereo_frames": B, "keypoints_per_image": kp_mean,
                        "fb_keep_fraction": keep_frac, "distinct_batches": nb,
                        "l2": "inputs larger than L2: one batch's pyramids are %.0f MB, %d distinct batches cycled"
-                             % (2 * B * 3.2, nb),
+                             % (2 * B * 3.2 * (W * H) / (752.0 * 480.0), nb),
                        "parallelism": "independent sequences per GPU, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": fe.h2d_bytes, "d2h_bytes_per_step": fe.d2h_bytes,
                     "ms_per_step": e2e_ms / K, "call": "zs_frontend_submit_host/zs_frontend_wait (2 batches in flight)",
@@ -361,7 +361,16 @@ def main():
     ap.add_argument("--batch", type=int, default=128, help="stereo frames per step per GPU")
     ap.add_argument("--batches", type=int, default=2, help="distinct synthetic batches cycled through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="C2", choices=["C2", "C4", "C5"],
+                    help="C2 (default, the headline): 752x480 cells 16; C4: 1280x1024 cells 32; C5: 3840x2160 cells 32")
     args = ap.parse_args()
+    global W, H, CELL, WORKLOAD
+    if args.config != "C2":
+        W, H = (1280, 1024) if args.config == "C4" else (3840, 2160)
+        CELL = (32, 32)
+        WORKLOAD = WORKLOAD.replace("C2: 752x480", "%s: %dx%d" % (args.config, W, H)).replace("16x16 cells", "32x32 cells")
+        if args.batch == 128:
+            args.batch = 64 if args.config == "C4" else 16
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     rank = int(os.environ.get("RANK", "0"))

@@ -281,3 +281,55 @@ def test_assign_landmark_indices_large_map(ctx, n, m):
     assert got_n == len(want) and got_n >= n // 4
     for i, kp in enumerate(kps):
         assert kp.index == want.get(i, 10_000_000 + i), i
+
+
+@pytest.mark.parametrize("w,h,cell,name", [(1280, 1024, (32, 32), "C4"), (3840, 2160, (32, 32), "C5")])
+def test_frontend_full_size_configs(ctx, w, h, cell, name):
+    """BASELINE configs 4 and 5 at their full frame sizes.  Detection, description and the stereo match are checked
+    against the oracle outright (they are cheap on the CPU); the 8 KLT calls are checked (a) against the oracle on a
+    sample of the points and (b) through size-independent properties: with integer ground-truth motion the forward
+    track of every kept point lands within 0.05 px of the true displacement, forward-backward returns to the start,
+    and a second run of the same batch reproduces every output bit for bit."""
+    from zenslam_b200 import detection_options, slam_options, tracking_options
+    from zenslam_b200.frontend import StereoFrontend
+    B = 2
+    opts = slam_options(matcher="KNN", matcher_ratio=0.8, detection=detection_options(cell_size=cell), tracking=tracking_options())
+    seq, offs = syn.stereo_sequence(w, h, B, 4000 + w, subpixel=False)        # integer motion: exact ground truth
+    fe = StereoFrontend(ctx, w, h, B, opts)
+    L, R = np.ascontiguousarray(seq[:, 0]), np.ascontiguousarray(seq[:, 1])
+    res = {k: v.copy() for k, v in fe.process(L, R).items()}
+    fe.close()
+    fe = StereoFrontend(ctx, w, h, B, opts)
+    res2 = fe.process(L, R)
+    for k in res:
+        assert np.array_equal(res[k], res2[k]), k                                # determinism at full size
+    fe.close()
+    win, ml = (31, 31), 3
+    for k in range(B):
+        xyl, rl, dl = oracle_detect(L[k], cell, 10)
+        xyr, rr, dr = oracle_detect(R[k], cell, 10)
+        nl, nr = res["n_left"][k], res["n_right"][k]
+        assert nl == len(xyl) and nr == len(xyr) and nl > 0.7 * (w // cell[0]) * (h // cell[1]) * 0.8
+        assert np.array_equal(res["kp_left"][k, :nl], xyl) and np.array_equal(res["kp_right"][k, :nr], xyr)
+        assert np.array_equal(res["desc_left"][k, :nl], dl) and np.array_equal(res["desc_right"][k, :nr], dr)
+        oi, od = oracle.match_hamming_knn2(dl, dr)
+        assert np.array_equal(res["match_idx"][k, :nl], oi) and np.array_equal(res["match_dist"][k, :nl], od.astype(np.float32))
+        # stereo L->R: the right view is the left view shifted by the disparity (6 px): true flow = (-6, 0)
+        keep = res["track_keep"][2, k, :nl].astype(bool)
+        assert keep.mean() > 0.9
+        flow = res["track_pts"][2, k, :nl][keep] - xyl[keep]
+        assert np.abs(flow - np.array([-6.0, 0.0], np.float32)).max() < 0.05
+        # oracle on a sample of the points (every 16th), forward + backward + gate
+        PL, PR = oracle.Pyramid(L[k], win, ml), oracle.Pyramid(R[k], win, ml)
+        sel = np.arange(0, nl, 16)
+        o1, os_, _ = oracle.lk_track(PL, PR, xyl[sel], None, win, ml)
+        ob, osb, _ = oracle.lk_track(PR, PL, o1, None, win, ml)
+        assert np.array_equal(res["track_pts"][2, k, sel], o1)
+        assert np.array_equal(res["track_keep"][2, k, sel].astype(bool), oracle.fb_check(xyl[sel], ob, os_, osb, 1.0))
+    # temporal L: frame 0 -> 1 moves by the known integer offset
+    d = offs[1] - offs[0]
+    n0 = res["n_left"][0]
+    keep = res["track_keep"][0, 1, :n0].astype(bool)
+    assert res["track_n"][0, 1] == n0 and keep.mean() > 0.9
+    flow = res["track_pts"][0, 1, :n0][keep] - res["kp_left"][0, :n0][keep]
+    assert np.abs(flow + d.astype(np.float32)).max() < 0.05
