@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_grid(fast_grid_args a)
 
 // ------------------------------------------------------------------------------------------------------
 // v2 grid kernel (even cell sizes, e.g. the reference's default 16x16 and the 32x32 of the large-frame config).
-// A block owns FG2_CELLS consecutive cells of one cell row.  The strip is staged once with 16-byte loads and
+// A block owns NC consecutive cells of one cell row (16 cells of 16 px, 4 cells of 32 px: 256 / 128 px strips).  The strip is staged once with 16-byte loads and
 // expanded into two u16x2 "pair planes" in shared memory (E holds pixel pairs (0,1),(2,3).., O holds (1,2),(3,4)..),
 // so that the two horizontally adjacent interior pixels a thread owns see every ring position as ONE aligned
 // 32-bit shared load.  The FAST decision and score then need no per-pixel branching at all:
@@ -186,7 +186,6 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) k_fast_grid(fast_grid_args a)
 // and the sliding 9-window min / max over the 16-ring is 2 x 32 three-input VIMNMX3.U16x2 (two pixels per
 // instruction) plus two 16 -> 1 reductions.  NMS and the per-cell first maximum run on a u8 score tile.
 // ------------------------------------------------------------------------------------------------------
-#define FG2_CELLS 16
 #define FG2_THREADS 160
 
 template <bool MAX>
@@ -209,33 +208,33 @@ __device__ __forceinline__ unsigned ring_window9(const unsigned p[16])
     return MAX9 ? __vminu2(u, w) : __vmaxu2(u, w);
 }
 
-template <int CW, int CH>
+template <int CW, int CH, int NC>
 __global__ void __launch_bounds__(FG2_THREADS) k_fast_grid_v2(fast_grid_args a)
 {
-    constexpr int TW = FG2_CELLS * CW;            // strip width in pixels
+    constexpr int TW = NC * CW;            // strip width in pixels
     constexpr int PW = TW / 2 + 4;                // words per pair-plane row (+ slack for the x+4 reads at the right edge)
     constexpr int IW = CW - 6, IH = CH - 6;       // interior (tested) pixels per cell
     constexpr int PPR = IW / 2;                   // pixel pairs per cell row (IW is even)
-    constexpr int ROWP = FG2_CELLS * PPR;         // pairs per strip row
+    constexpr int ROWP = NC * PPR;         // pairs per strip row
     constexpr int TOTAL = ROWP * IH;
     static_assert(CW % 4 == 0 && CW >= 8 && CH >= 7, "cell shape");
     extern __shared__ __align__(16) uint8_t fsm[];
     uint32_t* sE = (uint32_t*)fsm;                                  // [CH][PW]
     uint32_t* sO = sE + CH * PW;                                    // [CH][PW]
     uint8_t* sS = (uint8_t*)(sO + CH * PW);                         // score tile [CH][TW]
-    int* sBest = (int*)(sS + CH * TW);                              // [FG2_CELLS]
-    uint8_t* sRaw = (uint8_t*)(sBest + FG2_CELLS);                  // raw strip [CH][TW + 16]
+    int* sBest = (int*)(sS + CH * TW);                              // [NC]
+    uint8_t* sRaw = (uint8_t*)(sBest + NC);                  // raw strip [CH][TW + 16]
     constexpr int RP = TW + 16;
 
-    const int img = blockIdx.z, gy = blockIdx.y, cell0 = blockIdx.x * FG2_CELLS;
-    const int ncell = min(FG2_CELLS, a.gw - cell0);
+    const int img = blockIdx.z, gy = blockIdx.y, cell0 = blockIdx.x * NC;
+    const int ncell = min(NC, a.gw - cell0);
     const int tid = threadIdx.x;
     const int slot = zs_slot(a.first, img, a.v.slots);
     const int pitch = a.v.pitch[0];
     const uint8_t* src = a.v.img[0] + (size_t)slot * a.v.slot_stride[0] + (size_t)(a.v.pad_y + gy * CH) * pitch + a.v.pad_x + cell0 * CW;
     const int valid_w = ncell * CW;               // pixels of this strip that belong to cells
 
-    // ---- stage the raw strip: 16-byte loads (interiors are 16-byte aligned: pad_x, pitch and CW*FG2_CELLS are multiples of 16)
+    // ---- stage the raw strip: 16-byte loads (interiors are 16-byte aligned: pad_x, pitch and CW*NC are multiples of 16)
     for (int i = tid; i < CH * (RP / 16); i += FG2_THREADS) {
         const int r = i / (RP / 16), c = (i - r * (RP / 16)) * 16;
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -243,7 +242,7 @@ __global__ void __launch_bounds__(FG2_THREADS) k_fast_grid_v2(fast_grid_args a)
         *(uint4*)(sRaw + r * RP + c) = v;
     }
     for (int i = tid; i < CH * TW / 4; i += FG2_THREADS) ((uint32_t*)sS)[i] = 0;
-    if (tid < FG2_CELLS) sBest[tid] = 0;
+    if (tid < NC) sBest[tid] = 0;
     __syncthreads();
     // ---- expand into the pair planes: word j of E = (p[2j], p[2j+1]), of O = (p[2j+1], p[2j+2]) as u16x2
     for (int i = tid; i < CH * (TW / 4 + 1); i += FG2_THREADS) {
@@ -319,11 +318,11 @@ __global__ void __launch_bounds__(FG2_THREADS) k_fast_grid_v2(fast_grid_args a)
     }
 }
 
-template <int CW, int CH>
+template <int CW, int CH, int NC>
 static size_t fast_grid_v2_smem()
 {
-    constexpr int TW = FG2_CELLS * CW, PW = TW / 2 + 4;
-    return (size_t)2 * CH * PW * 4 + (size_t)CH * TW + FG2_CELLS * 4 + (size_t)CH * (TW + 16);
+    constexpr int TW = NC * CW, PW = TW / 2 + 4;
+    return (size_t)2 * CH * PW * 4 + (size_t)CH * TW + NC * 4 + (size_t)CH * (TW + 16);
 }
 
 // Compaction in cell row-major order: one block per image, block-wide exclusive scan over the cells.
@@ -381,15 +380,13 @@ extern "C" zs_status zs_fast_grid_detect(zs_context* ctx, const zs_pyramid* p, i
     a.v = p->v; a.first = first; a.count = count; a.cw = cell_w; a.ch = cell_h; a.gw = gw; a.gh = gh;
     a.threshold = threshold; a.occupied = d_occupied; a.cand = (int*)scratch;
     if (!getenv("ZS_FAST_V1") && ((cell_w == 16 && cell_h == 16) || (cell_w == 32 && cell_h == 32))) {
-        const dim3 grid(zs_div_up(gw, FG2_CELLS), gh, count);
         if (cell_w == 16) {
-            const size_t smem = fast_grid_v2_smem<16, 16>();
-            k_fast_grid_v2<16, 16><<<grid, FG2_THREADS, smem, ctx->stream>>>(a);
+            const size_t smem = fast_grid_v2_smem<16, 16, 16>();
+            k_fast_grid_v2<16, 16, 16><<<dim3(zs_div_up(gw, 16), gh, count), FG2_THREADS, smem, ctx->stream>>>(a);
         } else {
-            const size_t smem = fast_grid_v2_smem<32, 32>();
-            static bool attr = false;
-            if (!attr) { ZS_CUDA(cudaFuncSetAttribute(k_fast_grid_v2<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-            k_fast_grid_v2<32, 32><<<grid, FG2_THREADS, smem, ctx->stream>>>(a);
+            // 4 cells (128 px) per block keep the pair planes at 26 KB, so 8 blocks fit an SM instead of 2
+            const size_t smem = fast_grid_v2_smem<32, 32, 4>();
+            k_fast_grid_v2<32, 32, 4><<<dim3(zs_div_up(gw, 4), gh, count), FG2_THREADS, smem, ctx->stream>>>(a);
         }
         ZS_LAUNCH_CHECK(ctx);
         k_grid_compact<<<count, 1024, 0, ctx->stream>>>(a.cand, cells, gw, cell_w, cell_h, (float2*)d_xy, d_response, d_count, cap);
