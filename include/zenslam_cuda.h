@@ -242,6 +242,26 @@ ZS_API zs_status zs_knn_match_host(zs_context* ctx, const void* q, int nq, const
 ZS_API zs_status zs_assign_landmarks_host(zs_context* ctx, const uint8_t* keypoint_desc, int n, const uint8_t* landmark_desc,
                                           int m, double max_descriptor_distance, int* landmark_row, float* distance);
 
+/* ---- stereo triangulation with its gates: triangulator::triangulate_keypoints ----------------------------------
+ * (zenslam_core/source/mapping/triangulator.cpp:39-132, filter_epipolar :152-188; cv::triangulatePoints behind
+ * utils::triangulate_points, mapping/triangulation_utils.cpp:135-160).  SURVEY 8(f3).  n matched pairs (same keypoint
+ * index in both cameras; the matching by index is host bookkeeping).  P0 / P1: 3x4 projection matrices, F: 3x3
+ * fundamental matrix (calibration.fundamental_matrix[0]; NULL = no epipolar filter), t: translation of camera 1 in
+ * camera 0 -- all HOST pointers, row-major doubles.  Outputs: xyz [n][3] doubles (every pair, like points3d_all),
+ * keep [n] (the pairs that survive every gate), optional diag [n][4] = epipolar error, reprojection errors, angle. */
+typedef struct {
+    int filter_epipolar;             /* triangulation.filter_epipolar */
+    double epipolar_threshold;       /* triangulation.epipolar_threshold (0.01) */
+    double reprojection_threshold;   /* triangulation.reprojection_threshold (1.0) */
+    double min_depth, max_depth;     /* triangulation.min_depth / max_depth (1.0 / 50.0) */
+} zs_triangulation_params;
+ZS_API zs_status zs_triangulate_keypoints(zs_context* ctx, const double* P0, const double* P1, const double* F, const double* t,
+                                          const float* d_pts0, const float* d_pts1, int n, const zs_triangulation_params* params,
+                                          double* d_xyz, uint8_t* d_keep, double* d_diag);
+ZS_API zs_status zs_triangulate_keypoints_host(zs_context* ctx, const double* P0, const double* P1, const double* F,
+                                               const double* t, const float* pts0, const float* pts1, int n,
+                                               const zs_triangulation_params* params, double* xyz, uint8_t* keep, double* diag);
+
 /* ---- batched stereo front-end ------------------------------------------------------------------
  * The per-frame call pattern of keypoint_tracker::track (keypoint_tracker.cpp:41-105) restated for
  * a batch of B consecutive stereo frames: per frame 2 pyramids, 2 grid detections + ORB, 1 stereo

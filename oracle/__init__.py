@@ -344,3 +344,24 @@ def remap_linear(img, map_x, map_y):
                                    C.c_void_p, C.c_int]
     L.zso_remap_linear(_p(img), w, h, w, _p(map_x), _p(map_y), dw, dw, dh, _p(out), dw)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# stereo triangulation with gates (triangulator::triangulate_keypoints)
+# ---------------------------------------------------------------------------------------------
+def triangulate_keypoints(P0, P1, F, t, pts0, pts1, epipolar_threshold=0.01, reprojection_threshold=1.0, min_depth=1.0,
+                          max_depth=50.0):
+    """-> xyz (n,3) f64, keep (n,) bool, diag (n,4) f64 [epipolar error, reprojection error cam0, cam1, angle deg]"""
+    P0 = np.ascontiguousarray(P0, np.float64); P1 = np.ascontiguousarray(P1, np.float64)
+    t = np.ascontiguousarray(t, np.float64)
+    pts0 = np.ascontiguousarray(pts0, np.float32); pts1 = np.ascontiguousarray(pts1, np.float32)
+    n = len(pts0)
+    xyz = np.zeros((n, 3), np.float64); keep = np.zeros(n, np.uint8); diag = np.zeros((n, 4), np.float64)
+    Fp = None
+    if F is not None:
+        F = np.ascontiguousarray(F, np.float64); Fp = _p(F)
+    L = lib()
+    L.zso_triangulate_keypoints.argtypes = [C.c_void_p] * 6 + [C.c_int] + [C.c_double] * 4 + [C.c_void_p] * 3
+    L.zso_triangulate_keypoints(_p(P0), _p(P1), Fp, _p(t), _p(pts0), _p(pts1), n, float(epipolar_threshold),
+                                float(reprojection_threshold), float(min_depth), float(max_depth), _p(xyz), _p(keep), _p(diag))
+    return xyz, keep.astype(bool), diag

@@ -333,3 +333,38 @@ def test_frontend_full_size_configs(ctx, w, h, cell, name):
     assert res["track_n"][0, 1] == n0 and keep.mean() > 0.9
     flow = res["track_pts"][0, 1, :n0][keep] - res["kp_left"][0, :n0][keep]
     assert np.abs(flow + d.astype(np.float32)).max() < 0.05
+
+
+def test_triangulator_mirror(ctx, golden):
+    """SURVEY 8(f3): epipolar gate + cv::triangulatePoints + reprojection/depth/parallax gates on the device, against the
+    cv2 fixture and the oracle.  Floating point: the 3-D points must agree to float rounding (they are ratios of
+    float-rounded SVD outputs), the keep decisions everywhere except within 1e-6 of a threshold."""
+    from zenslam_b200 import keypoint
+    from zenslam_b200.triangulation import triangulation_options, triangulator
+    g = golden("triangulate")
+    tri = triangulator(ctx, g["P0"], g["P1"], g["F"], g["t"])
+    xyz, keep, diag = tri.triangulate_points(g["pts0"], g["pts1"], with_diag=True)
+    X4 = g["cv_points4d"].astype(np.float64)
+    ok = np.abs(X4[3]) > 1e-9
+    want = np.where(ok, X4[:3] / np.where(ok, X4[3], 1.0), 0.0).T
+    scale = np.maximum(np.abs(want).max(1, keepdims=True), 1e-6)
+    assert (np.abs(xyz - want) / scale).max() < 1e-5
+    assert np.mean(np.all(xyz == want, axis=1)) > 0.98                 # almost always the very same floats
+    oxyz, okeep, odiag = oracle.triangulate_keypoints(g["P0"], g["P1"], g["F"], g["t"], g["pts0"], g["pts1"])
+    n0 = np.linalg.norm(oxyz, axis=1)
+    margin = np.min(np.stack([np.abs(np.abs(odiag[:, 0]) - 0.01), np.abs(n0 - 1.0), np.abs(n0 - 50.0), np.abs(odiag[:, 1] - 1.0),
+                              np.abs(odiag[:, 2] - 1.0), np.abs(odiag[:, 3] - 0.25), np.abs(oxyz[:, 2])]), 0)
+    safe = margin > 1e-6
+    assert safe.mean() > 0.99 and np.array_equal(keep[safe], okeep[safe])
+    assert np.allclose(diag[safe], odiag[safe], rtol=1e-5, atol=1e-7)
+    # map overload: pairs by common index, ascending (triangulator.cpp:39-132)
+    k0 = {i * 3: keypoint(pt=tuple(g["pts0"][i]), index=i * 3) for i in range(200)}
+    k1 = {i * 3: keypoint(pt=tuple(g["pts1"][i]), index=i * 3) for i in range(0, 200, 2)}
+    pts = tri.triangulate_keypoints(k0, k1)
+    want_idx = [i * 3 for i in range(0, 200, 2) if keep[i]]
+    assert [p.index for p in pts] == want_idx
+    # no epipolar filter keeps a superset
+    tri2 = triangulator(ctx, g["P0"], g["P1"], None, g["t"], triangulation_options(filter_epipolar=False))
+    _, keep2 = tri2.triangulate_points(g["pts0"], g["pts1"])
+    assert keep2.sum() >= keep.sum()
+    assert tri.triangulate_points(np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32))[0].shape == (0, 3)

@@ -159,3 +159,26 @@ def test_preprocessing_golden(golden):
     assert np.array_equal(oracle.clahe(gray, 2.0, (4, 6)), g["cv_clahe_2_4x6"])
     assert np.array_equal(oracle.remap_linear(gray, g["map_x"], g["map_y"]), g["cv_remap_gray"])
     assert np.array_equal(oracle.remap_linear(cl, g["map_x"], g["map_y"]), g["cv_remap_clahe"])
+
+
+def _points3d_from_cv(X4):
+    """utils::triangulate_points' conversion (triangulation_utils.cpp:150-157)"""
+    X4 = X4.astype(np.float64)
+    ok = np.abs(X4[3]) > 1e-9
+    return np.where(ok, X4[:3] / np.where(ok, X4[3], 1.0), 0.0).T
+
+
+def test_triangulate_golden(golden):
+    """cv::triangulatePoints restated (DLT + OpenCV's one-sided Jacobi SVD, float output): identical to cv2 on the fixture;
+    the gates behave as triangulator.cpp:118-127 says"""
+    g = golden("triangulate")
+    xyz, keep, diag = oracle.triangulate_keypoints(g["P0"], g["P1"], g["F"], g["t"], g["pts0"], g["pts1"])
+    want = _points3d_from_cv(g["cv_points4d"])
+    assert np.array_equal(xyz, want)
+    n0 = np.linalg.norm(xyz, axis=1)
+    ref_keep = ((np.abs(diag[:, 0]) < 0.01) & (xyz[:, 2] > 0) & (n0 > 1.0) & (n0 < 50.0) & (diag[:, 1] < 1.0) & (diag[:, 2] < 1.0) &
+                (diag[:, 3] > 0.25) & (diag[:, 3] < 179.75))
+    assert np.array_equal(keep, ref_keep) and 50 < keep.sum() < len(keep)
+    # without the epipolar filter more pairs survive, and none is lost
+    _, keep2, _ = oracle.triangulate_keypoints(g["P0"], g["P1"], None, g["t"], g["pts0"], g["pts1"])
+    assert keep2.sum() >= keep.sum() and np.all(keep2[keep])

@@ -26,6 +26,11 @@ class LkParams(C.Structure):
                 ("epsilon", C.c_double), ("flags", C.c_int), ("min_eig_threshold", C.c_double)]
 
 
+class TriangulationParams(C.Structure):
+    _fields_ = [("filter_epipolar", C.c_int), ("epipolar_threshold", C.c_double), ("reprojection_threshold", C.c_double),
+                ("min_depth", C.c_double), ("max_depth", C.c_double)]
+
+
 class FrontendOptions(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("batch", C.c_int),
                 ("cell_w", C.c_int), ("cell_h", C.c_int), ("fast_threshold", C.c_int),
@@ -90,6 +95,8 @@ SIGNATURES = {
     "zs_match_host": (I, [P, P, I, P, I, I, I, I, D, P, P, P, C.POINTER(I)]),
     "zs_knn_match_host": (I, [P, P, I, P, I, I, I, I, I, P, P]),
     "zs_assign_landmarks_host": (I, [P, P, I, P, I, D, P, P]),
+    "zs_triangulate_keypoints": (I, [P, P, P, P, P, P, P, I, C.POINTER(TriangulationParams), P, P, P]),
+    "zs_triangulate_keypoints_host": (I, [P, P, P, P, P, P, P, I, C.POINTER(TriangulationParams), P, P, P]),
     "zs_frontend_create": (I, [P, C.POINTER(FrontendOptions), C.POINTER(P)]),
     "zs_frontend_destroy": (None, [P]),
     "zs_frontend_capacity": (I, [P]),
