@@ -280,6 +280,35 @@ def run_ours(args, rank, world, local_rank):
     sync_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0)
     e2e_sync_value = world * B * Ks / (sync_ms / 1000.0)
 
+    raw_line = None
+    if args.raw:
+        # optional: raw BGR camera frames + CLAHE + rectification maps in front of the same path (processor::process,
+        # SURVEY 8 f1); 3x the H2D bytes, three more streaming kernels per step
+        yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+        r2 = ((xx - W / 2) ** 2 + (yy - H / 2) ** 2) / (W * W / 4)
+        maps = [((W / 2 + (xx - W / 2) * (1 + kk * r2)).astype(np.float32), (H / 2 + (yy - H / 2) * (1 + kk * r2)).astype(np.float32))
+                for kk in (0.05, -0.04)]
+        lb = torch.stack([left, left.roll(2, -1), left // 2 + 40], -1).contiguous().pin_memory()
+        rb = torch.stack([right, right.roll(2, -1), right // 2 + 40], -1).contiguous().pin_memory()
+        fe.set_preprocess(3, True, 4.0, maps)
+
+        def raw_pipelined(steps, first):
+            fe.submit(lb[first % nb], rb[first % nb])
+            for i in range(1, steps):
+                j = (first + i) % nb
+                fe.submit(lb[j], rb[j])
+                fe.wait()
+            return fe.wait()
+        raw_pipelined(3, 0)
+        barrier()
+        t0 = time.perf_counter()
+        raw_pipelined(K, Wm)
+        barrier()
+        raw_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0)
+        raw_line = {"value": world * B * K / (raw_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": fe.h2d_bytes,
+                    "input": "BGR frames; BGR2GRAY + CLAHE(4.0) + remap(INTER_LINEAR) on the device before the pyramids"}
+        fe.set_preprocess(1, False, 4.0, None)
+
     if rank == 0:
         peak, peak_src = peaks()
         P = sum(((W + (1 << l) - 1) >> l) * ((H + (1 << l) - 1) >> l) for l in range(fe_levels(W, H)))
@@ -309,6 +338,8 @@ def run_ours(args, rank, world, local_rank):
                          "note": "KLT is instruction-issue bound (ncu: 85 % issue-active, DRAM 1.3 % of peak), not HBM bound "
                                  "(SURVEY 8d); the compulsory-bytes figure is reported as the contract asks, see DESIGN.md"},
         }
+        if raw_line:
+            line["e2e_raw_bgr"] = raw_line
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
@@ -361,6 +392,7 @@ def main():
     ap.add_argument("--batch", type=int, default=128, help="stereo frames per step per GPU")
     ap.add_argument("--batches", type=int, default=2, help="distinct synthetic batches cycled through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--raw", action="store_true", help="also time the end-to-end path fed with raw BGR frames (device pre-processing)")
     ap.add_argument("--config", default="C2", choices=["C2", "C4", "C5"],
                     help="C2 (default, the headline): 752x480 cells 16; C4: 1280x1024 cells 32; C5: 3840x2160 cells 32")
     args = ap.parse_args()

@@ -320,6 +320,13 @@ ZS_API zs_status zs_frontend_process_host(zs_frontend* fe, const uint8_t* left, 
 ZS_API zs_status zs_frontend_submit_host(zs_frontend* fe, const uint8_t* left, const uint8_t* right,
                                          size_t pitch, size_t stride, const zs_frontend_results* res);
 ZS_API zs_status zs_frontend_wait(zs_frontend* fe);
+/* raw camera frames in: run processor::process's image path (processor.cpp:25-55) on the device in front of the pyramid
+ * build -- channels 3 = BGR (COLOR_BGR2GRAY), optional CLAHE(clip), optional rectification with the calibration's
+ * CV_32FC1 maps (HOST pointers, width*height floats each; all four or none).  Affects zs_frontend_submit_host and
+ * zs_frontend_process_host, whose left / right buffers then hold `channels` bytes per pixel. */
+ZS_API zs_status zs_frontend_set_preprocess(zs_frontend* fe, int channels, int clahe_enabled, double clahe_clip_limit,
+                                            const float* map_x_left, const float* map_y_left, const float* map_x_right,
+                                            const float* map_y_right);
 ZS_API int zs_frontend_in_flight(const zs_frontend* fe);
 
 #ifdef __cplusplus

@@ -368,3 +368,57 @@ def test_triangulator_mirror(ctx, golden):
     _, keep2 = tri2.triangulate_points(g["pts0"], g["pts1"])
     assert keep2.sum() >= keep.sum()
     assert tri.triangulate_points(np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32))[0].shape == (0, 3)
+
+
+@pytest.mark.parametrize("clahe,use_maps,channels", [(True, True, 3), (False, True, 1), (True, False, 3), (False, False, 3)])
+def test_frontend_with_preprocessing(ctx, clahe, use_maps, channels):
+    """raw camera frames in (SURVEY 8 f1 hooked into the batched front-end): BGR -> gray -> CLAHE -> rectification on the
+    device must give exactly the results of the plain front-end fed with frames pre-processed by the oracle"""
+    from zenslam_b200 import slam_options
+    from zenslam_b200.frontend import StereoFrontend
+    w, h, B = 752, 480, 2
+    seq, _ = syn.stereo_sequence(w, h, 2 * B, 611, subpixel=True)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    maps = []
+    for cam, kk in enumerate((0.06, -0.04)):
+        r2 = ((xx - w / 2) ** 2 + (yy - h / 2) ** 2) / (w * w / 4)
+        maps.append(((w / 2 + (xx - w / 2) * (1 + kk * r2) + 0.3 * cam).astype(np.float32), (h / 2 + (yy - h / 2) * (1 + kk * r2)).astype(np.float32)))
+
+    def raw(img):                                   # a colour frame whose gray value is not simply one channel
+        if channels == 1:
+            return img
+        return np.stack([img, np.roll(img, 2, 1), (img.astype(np.int32) * 3 // 4 + 20).astype(np.uint8)], -1)
+
+    def pre(img, cam):
+        g = oracle.bgr2gray(raw(img)) if channels == 3 else img
+        if clahe:
+            g = oracle.clahe(g, 4.0)
+        if use_maps:
+            g = oracle.remap_linear(g, maps[cam][0], maps[cam][1])
+        return g
+
+    fe_ref = StereoFrontend(ctx, w, h, B, slam_options())
+    fe = StereoFrontend(ctx, w, h, B, slam_options())
+    fe.set_preprocess(channels, clahe, 4.0, maps if use_maps else None)
+    for b in range(2):
+        chunk = seq[b * B:(b + 1) * B]
+        Lr = np.ascontiguousarray(np.stack([raw(f) for f in chunk[:, 0]])); Rr = np.ascontiguousarray(np.stack([raw(f) for f in chunk[:, 1]]))
+        Lp = np.ascontiguousarray(np.stack([pre(f, 0) for f in chunk[:, 0]])); Rp = np.ascontiguousarray(np.stack([pre(f, 1) for f in chunk[:, 1]]))
+        want = {k: v.copy() for k, v in fe_ref.process(Lp, Rp).items()}
+        if b == 0:
+            got = fe.process(Lr, Rr)
+        else:
+            fe.submit(Lr, Rr); got = fe.wait()
+        assert want["n_left"].min() > 300
+        for k in range(B):
+            nl, nr = want["n_left"][k], want["n_right"][k]
+            assert got["n_left"][k] == nl and got["n_right"][k] == nr
+            for key in ("kp_left", "desc_left", "match_idx", "match_pass"):
+                assert np.array_equal(got[key][k, :nl], want[key][k, :nl]), (b, k, key)
+            assert np.array_equal(got["desc_right"][k, :nr], want["desc_right"][k, :nr])
+            for kind in range(4):
+                m = want["track_n"][kind, k]
+                assert got["track_n"][kind, k] == m
+                assert np.array_equal(got["track_pts"][kind, k, :m], want["track_pts"][kind, k, :m])
+                assert np.array_equal(got["track_keep"][kind, k, :m], want["track_keep"][kind, k, :m])
+    fe.close(); fe_ref.close()

@@ -110,6 +110,7 @@ SIGNATURES = {
     "zs_frontend_process_host": (I, [P, P, P, Z, Z, C.POINTER(FrontendResults)]),
     "zs_frontend_submit_host": (I, [P, P, P, Z, Z, C.POINTER(FrontendResults)]),
     "zs_frontend_wait": (I, [P]),
+    "zs_frontend_set_preprocess": (I, [P, I, I, D, P, P, P, P]),
     "zs_frontend_in_flight": (I, [P]),
 }
 

@@ -44,6 +44,11 @@ struct zs_frontend {
     uint8_t* outbox[2]; size_t outbox_bytes;   // snapshot of every result array
     cudaEvent_t ev_in[2], ev_unpacked[2], ev_run[2], ev_out[2];
     bool busy[2]; uint64_t submitted, waited;
+    // optional pre-processing of the raw camera frames (processor::process, processor.cpp:25-55): BGR -> gray,
+    // CLAHE, remap with per-camera maps, written straight into level 0 of the pyramid slots
+    int pp_enabled, pp_channels, pp_clahe; double pp_clip;
+    float* pp_maps;                 // device: [4][H][W] = map_x_left, map_y_left, map_x_right, map_y_right (null: no remap)
+    uint8_t* pp_tmp[2]; size_t pp_pitch;   // two gray planes [2B][H][pp_pitch]
 };
 
 #define ZS_FE_MARK(i) do { if (fe->timing) ZS_CUDA(cudaEventRecord(fe->ev[fe->t_runs % ZS_FE_TIMING_RING][i], ctx->stream)); } while (0)
@@ -133,6 +138,9 @@ extern "C" void zs_frontend_destroy(zs_frontend* fe)
     if (fe->pyr) zs_pyramid_destroy(fe->pyr);
     if (fe->dev) cudaFree(fe->dev);
     if (fe->pin) cudaFreeHost(fe->pin);
+    if (fe->pp_maps) cudaFree(fe->pp_maps);
+    if (fe->pp_tmp[0]) cudaFree(fe->pp_tmp[0]);
+    if (fe->pp_tmp[1]) cudaFree(fe->pp_tmp[1]);
     if (fe->s_in) {
         cudaStreamSynchronize(fe->s_in); cudaStreamSynchronize(fe->s_out);
         for (int b = 0; b < 2; ++b) {
@@ -153,7 +161,7 @@ extern "C" int zs_frontend_capacity(const zs_frontend* fe) { return fe ? fe->cap
 
 extern "C" size_t zs_frontend_h2d_bytes(const zs_frontend* fe)
 {
-    return fe ? (size_t)2 * fe->B * fe->opt.width * fe->opt.height : 0;
+    return fe ? (size_t)2 * fe->B * fe->opt.width * fe->opt.height * (fe->pp_enabled ? fe->pp_channels : 1) : 0;
 }
 
 extern "C" size_t zs_frontend_d2h_bytes(const zs_frontend* fe)
@@ -368,7 +376,8 @@ extern "C" zs_status zs_frontend_submit_host(zs_frontend* fe, const uint8_t* lef
 {
     ZS_REQUIRE(fe && left && right && r, "null argument");
     ZS_REQUIRE(r->cap == fe->cap, "results.cap must equal zs_frontend_capacity()");
-    ZS_REQUIRE(pitch >= (size_t)fe->opt.width && stride >= pitch * (size_t)fe->opt.height, "bad pitch/stride");
+    const size_t ch = fe->pp_enabled ? (size_t)fe->pp_channels : 1;
+    ZS_REQUIRE(pitch >= ch * (size_t)fe->opt.width && stride >= pitch * (size_t)fe->opt.height, "bad pitch/stride");
     ZS_REQUIRE(fe->submitted - fe->waited < 2, "two batches already in flight: call zs_frontend_wait first");
     zs_context* ctx = fe->ctx;
     ZS_CUDA(cudaSetDevice(ctx->device));
@@ -387,10 +396,46 @@ extern "C" zs_status zs_frontend_submit_host(zs_frontend* fe, const uint8_t* lef
     // compute stream
     ZS_CUDA(cudaStreamWaitEvent(ctx->stream, fe->ev_in[b], 0));
     const zs_pyr_view& v = fe->pyr->v;
-    const int vec = (pitch % 16 == 0 && stride % 16 == 0 && ((uintptr_t)fe->stage[b] % 16) == 0 && fe->opt.width % 16 == 0) ? 1 : 0;
-    const dim3 grid(zs_div_up(zs_div_up(fe->opt.width, 16), 128), fe->opt.height, (unsigned)(2 * B));
-    k_unpack_level0<<<grid, 128, 0, ctx->stream>>>(fe->stage[b], pitch, stride, v, 2, vec);   // slots 2..2B+1 = L then R
-    ZS_LAUNCH_CHECK(ctx);
+    const int W = fe->opt.width, H = fe->opt.height;
+    if (!fe->pp_enabled) {
+        const int vec = (pitch % 16 == 0 && stride % 16 == 0 && ((uintptr_t)fe->stage[b] % 16) == 0 && W % 16 == 0) ? 1 : 0;
+        const dim3 grid(zs_div_up(zs_div_up(W, 16), 128), H, (unsigned)(2 * B));
+        k_unpack_level0<<<grid, 128, 0, ctx->stream>>>(fe->stage[b], pitch, stride, v, 2, vec);   // slots 2..2B+1 = L then R
+        ZS_LAUNCH_CHECK(ctx);
+    } else {
+        // raw frames -> gray -> (CLAHE) -> (remap) -> level 0 of slots 2..2B+1; every stage handles all 2B images at once
+        const uint8_t* cur = fe->stage[b]; size_t cp = pitch, cs = stride;
+        const size_t gp = fe->pp_pitch, gs = gp * (size_t)H;
+        uint8_t* l0; size_t l0p, l0s;
+        if ((st = zs_pyramid_level0(fe->pyr, 2, &l0, &l0p, &l0s)) != ZS_OK) return st;
+        int next_tmp = 0;
+        const bool remap = fe->pp_maps != nullptr;
+        if (fe->pp_channels == 3) {
+            const bool last = !fe->pp_clahe && !remap;
+            uint8_t* d = last ? l0 : fe->pp_tmp[next_tmp]; const size_t dp = last ? l0p : gp, ds = last ? l0s : gs;
+            if ((st = zs_cvt_bgr2gray(ctx, cur, cp, cs, W, H, (int)(2 * B), d, dp, ds)) != ZS_OK) return st;
+            cur = d; cp = dp; cs = ds; next_tmp ^= 1;
+        }
+        if (fe->pp_clahe) {
+            const bool last = !remap;
+            uint8_t* d = last ? l0 : fe->pp_tmp[next_tmp]; const size_t dp = last ? l0p : gp, ds = last ? l0s : gs;
+            if ((st = zs_clahe(ctx, cur, cp, cs, W, H, (int)(2 * B), fe->pp_clip, 8, 8, d, dp, ds)) != ZS_OK) return st;
+            cur = d; cp = dp; cs = ds; next_tmp ^= 1;
+        }
+        if (remap) {
+            const size_t px = (size_t)W * H;
+            for (int cam = 0; cam < 2; ++cam)
+                if ((st = zs_remap_linear(ctx, cur + (size_t)cam * B * cs, cp, cs, W, H, (int)B, fe->pp_maps + (size_t)(2 * cam) * px,
+                                          fe->pp_maps + (size_t)(2 * cam + 1) * px, (size_t)W, 0, W, H, l0 + (size_t)cam * B * l0s, l0p, l0s)) != ZS_OK)
+                    return st;
+        } else if (cur == fe->stage[b]) {
+            // gray input, no CLAHE, no remap: plain unpack
+            const int vec = (pitch % 16 == 0 && stride % 16 == 0 && ((uintptr_t)fe->stage[b] % 16) == 0 && W % 16 == 0) ? 1 : 0;
+            const dim3 grid(zs_div_up(zs_div_up(W, 16), 128), H, (unsigned)(2 * B));
+            k_unpack_level0<<<grid, 128, 0, ctx->stream>>>(fe->stage[b], pitch, stride, v, 2, vec);
+            ZS_LAUNCH_CHECK(ctx);
+        }
+    }
     ZS_CUDA(cudaEventRecord(fe->ev_unpacked[b], ctx->stream));
     if ((st = zs_frontend_run(fe)) != ZS_OK) return st;
     // the outbox is free once the D2H of the batch that last used it has finished
@@ -423,5 +468,36 @@ extern "C" zs_status zs_frontend_submit_host(zs_frontend* fe, const uint8_t* lef
     ZS_CUDA(cudaEventRecord(fe->ev_out[b], fe->s_out));
     fe->busy[b] = true;
     fe->submitted++;
+    return ZS_OK;
+}
+
+// Raw camera frames in: the image path of processor::process (zenslam_core/source/processor.cpp:25-55) runs on the device
+// in front of the pyramid build.  channels 3 = BGR (utils::convert_color), clahe_enabled = detection.clahe_enabled with
+// cv::createCLAHE(clahe_clip_limit) (processor.h:38), maps = calibration.map_x / map_y per camera (CV_32FC1, W*H floats
+// each, HOST pointers, all four or none).  Applies to zs_frontend_submit_host / zs_frontend_process_host.
+extern "C" zs_status zs_frontend_set_preprocess(zs_frontend* fe, int channels, int clahe_enabled, double clahe_clip_limit,
+                                                const float* map_x_left, const float* map_y_left, const float* map_x_right,
+                                                const float* map_y_right)
+{
+    ZS_REQUIRE(fe, "null argument");
+    ZS_REQUIRE(channels == 1 || channels == 3, "channels must be 1 (gray) or 3 (BGR)");
+    const int nmaps = (map_x_left != nullptr) + (map_y_left != nullptr) + (map_x_right != nullptr) + (map_y_right != nullptr);
+    ZS_REQUIRE(nmaps == 0 || nmaps == 4, "give all four rectification maps or none");
+    ZS_REQUIRE(fe->submitted == fe->waited, "batches in flight: call zs_frontend_wait first");
+    zs_context* ctx = fe->ctx;
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    const size_t px = (size_t)fe->opt.width * fe->opt.height;
+    if (fe->pp_maps) { ZS_CUDA(cudaFree(fe->pp_maps)); fe->pp_maps = nullptr; }
+    if (nmaps == 4) {
+        ZS_CUDA(cudaMalloc((void**)&fe->pp_maps, sizeof(float) * 4 * px));
+        const float* m[4] = { map_x_left, map_y_left, map_x_right, map_y_right };
+        for (int i = 0; i < 4; ++i) ZS_CUDA(cudaMemcpy(fe->pp_maps + (size_t)i * px, m[i], sizeof(float) * px, cudaMemcpyHostToDevice));
+    }
+    fe->pp_pitch = ((size_t)fe->opt.width + 15) / 16 * 16;
+    for (int i = 0; i < 2; ++i)
+        if (!fe->pp_tmp[i]) ZS_CUDA(cudaMalloc((void**)&fe->pp_tmp[i], fe->pp_pitch * fe->opt.height * 2 * (size_t)fe->B));
+    fe->pp_channels = channels; fe->pp_clahe = clahe_enabled ? 1 : 0; fe->pp_clip = clahe_clip_limit;
+    fe->pp_enabled = (channels == 3 || clahe_enabled || nmaps == 4) ? 1 : 0;
     return ZS_OK;
 }

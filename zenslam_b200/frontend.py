@@ -36,6 +36,7 @@ class StereoFrontend:
         B, cap = batch, self.cap
         self._host = None
         self._submitted = self._waited = 0
+        self._channels = 1
         self._shapes = dict(
             n_left=((B,), np.int32), n_right=((B,), np.int32),
             kp_left=((B, cap, 2), np.float32), kp_right=((B, cap, 2), np.float32),
@@ -69,6 +70,20 @@ class StereoFrontend:
                     setattr(r, k, t.data_ptr())
                 self._host.append(host); self._res.append(r)
         return self._host[which], self._res[which]
+
+    def set_preprocess(self, channels: int = 1, clahe_enabled: bool = False, clahe_clip_limit: float = 4.0, maps=None):
+        """raw camera frames in (processor::process, processor.cpp:25-55): channels 3 = BGR; maps = ((map_x_l, map_y_l),
+        (map_x_r, map_y_r)) float32 (H, W) arrays or None.  submit()/process() then take (B, H, W[, 3]) raw frames."""
+        ptrs = [None] * 4
+        keep = []
+        if maps is not None:
+            for i, m in enumerate((maps[0][0], maps[0][1], maps[1][0], maps[1][1])):
+                a = np.ascontiguousarray(m, np.float32)
+                assert a.shape == (self.height, self.width)
+                keep.append(a); ptrs[i] = a.ctypes.data_as(C.c_void_p)
+        check(lib().zs_frontend_set_preprocess(self._h, channels, 1 if clahe_enabled else 0, float(clahe_clip_limit), *ptrs))
+        self._channels = channels
+        self.h2d_bytes = int(lib().zs_frontend_h2d_bytes(self._h))
 
     def upload(self, left, right):
         """left/right: (B, H, W) uint8 -- numpy / pinned torch CPU tensor (host) or torch cuda tensor."""
@@ -106,8 +121,8 @@ class StereoFrontend:
         host, res = self._results()
         lp = left.ctypes.data if isinstance(left, np.ndarray) else left.data_ptr()
         rp = right.ctypes.data if isinstance(right, np.ndarray) else right.data_ptr()
-        check(lib().zs_frontend_process_host(self._h, C.c_void_p(lp), C.c_void_p(rp), self.width,
-                                             self.width * self.height, C.byref(res)))
+        check(lib().zs_frontend_process_host(self._h, C.c_void_p(lp), C.c_void_p(rp), self.width * self._channels,
+                                             self.width * self.height * self._channels, C.byref(res)))
         return {k: t.numpy() for k, t in host.items()}
 
     # ---- pipelined end-to-end path: up to two batches in flight (H2D | kernels | D2H overlap) ----
@@ -117,8 +132,8 @@ class StereoFrontend:
         host, res = self._results(self._submitted & 1)
         lp = left.ctypes.data if isinstance(left, np.ndarray) else left.data_ptr()
         rp = right.ctypes.data if isinstance(right, np.ndarray) else right.data_ptr()
-        check(lib().zs_frontend_submit_host(self._h, C.c_void_p(lp), C.c_void_p(rp), self.width,
-                                            self.width * self.height, C.byref(res)))
+        check(lib().zs_frontend_submit_host(self._h, C.c_void_p(lp), C.c_void_p(rp), self.width * self._channels,
+                                            self.width * self.height * self._channels, C.byref(res)))
         self._submitted += 1
 
     def wait(self) -> dict:
