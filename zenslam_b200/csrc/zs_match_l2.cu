@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(L2TC_THREADS) k_l2_tc_tile(const __grid_consta
     extern __shared__ uint8_t l2_smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[2];       // [0] operands landed, [1] accumulator ready
     __shared__ uint32_t s_tmem;
-    __shared__ int s_tnorm[L2TC_N];
+    __shared__ __align__(16) int s_tnorm[L2TC_N];
     const int pair = blockIdx.z, q0 = blockIdx.x * L2TC_M, t0 = blockIdx.y * L2TC_N;
     const int n_q = min(a.nq[pair], a.cap_q), n_t = min(a.nt[pair], a.cap_t);
     if (q0 >= n_q || t0 >= n_t) return;              // uniform per CTA: nothing allocated yet
@@ -176,14 +176,15 @@ __global__ void __launch_bounds__(L2TC_THREADS) k_l2_tc_tile(const __grid_consta
         asm volatile("bar.sync 1, 128;" ::: "memory");       // s_tnorm complete (epilogue warps only)
         l2_mbar_wait(bar_acc, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // running top-2 over packed keys (d2 << 7 | column): d2 < 2^23 and a tile has 128 columns, so a key fits 30 bits and
-        // orders by distance first, column second -- exactly the stable rule (smaller train index wins a tie).  Per element:
-        // one IMAD for d2, one for the key, min / max / min for the two best.
-        unsigned k0 = 0x7fffffffu, k1 = 0x7fffffffu;
+        // running top-2 over packed keys.  key = d2 * 128 + column orders by distance first, column second -- the stable rule
+        // (smaller train index wins a tie) -- and d2 = |a|^2 + |b|^2 - 2 a.b < 2^23.  |a|^2 is the same for every column of
+        // a row, so it is left out of the loop: key' = (|b|^2 * 128 + column) - 256 * dot is ONE IMAD per element (the
+        // bracket is a per-column table in shared memory), followed by min / min / max for the two best.  Signed compare:
+        // key' lies in (-2^31, 2^30).
+        int k0 = 0x7fffffff, k1 = 0x7fffffff;
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16);
         const int ncol = min(L2TC_N, n_t - t0);
-        // masked columns get an infinite norm once, instead of a per-element bounds test in the loop
-        if (e >= ncol) s_tnorm[e] = 0x3fffffff;
+        s_tnorm[e] = s_tnorm[e] * 128 + e;                   // own entry only; published by the barrier below
         asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
         for (int c0 = 0; c0 < L2TC_N; c0 += 32) {
@@ -197,20 +198,30 @@ __global__ void __launch_bounds__(L2TC_THREADS) k_l2_tc_tile(const __grid_consta
                            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                          : "r"(taddr + (uint32_t)c0) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (c0 < ncol) {                                  // warp-uniform
+            const int4* tn4 = (const int4*)&s_tnorm[c0];
+            if (c0 + 32 <= ncol) {                            // warp-uniform: a full chunk needs no per-column test
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const unsigned d2 = (unsigned)(qn + s_tnorm[c0 + j] - 2 * (int)v[j]);
-                    const unsigned key = d2 < 0x800000u ? (d2 << 7) | (unsigned)(c0 + j) : 0x7fffffffu;
-                    k1 = min(k1, max(k0, key));
-                    k0 = min(k0, key);
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const int4 tn = tn4[j4];
+                    const int kk[4] = { tn.x - 256 * (int)v[4 * j4], tn.y - 256 * (int)v[4 * j4 + 1], tn.z - 256 * (int)v[4 * j4 + 2],
+                                        tn.w - 256 * (int)v[4 * j4 + 3] };
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { k1 = max(k0, min(k1, kk[q])); k0 = min(k0, kk[q]); }
                 }
+            } else if (c0 < ncol) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < ncol) {
+                        const int key = s_tnorm[c0 + j] - 256 * (int)v[j];
+                        k1 = max(k0, min(k1, key)); k0 = min(k0, key);
+                    }
             }
         }
         if (q0 + row < n_q) {
-            const int i0 = k0 != 0x7fffffffu ? t0 + (int)(k0 & 127u) : -1, i1 = k1 != 0x7fffffffu ? t0 + (int)(k1 & 127u) : -1;
+            const int f0 = k0 + qn * 128, f1 = k1 + qn * 128;          // put |a|^2 back: (d2 << 7) | column
+            const int i0 = k0 != 0x7fffffff ? t0 + (f0 & 127) : -1, i1 = k1 != 0x7fffffff ? t0 + (f1 & 127) : -1;
             a.part[((size_t)pair * a.cap_q + q0 + row) * a.splits + blockIdx.y] =
-                make_int4(i0, i1, i0 >= 0 ? (int)(k0 >> 7) : 0x7fffffff, i1 >= 0 ? (int)(k1 >> 7) : 0x7fffffff);
+                make_int4(i0, i1, i0 >= 0 ? (f0 >> 7) : 0x7fffffff, i1 >= 0 ? (f1 >> 7) : 0x7fffffff);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
