@@ -14,6 +14,7 @@
 //     problem fills the machine; a small merge kernel folds the per-split top-2 in ascending split order.
 // Integer MMA makes exactness a property of the instruction, not of rounding analysis.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "zs_common.cuh"
 
@@ -58,6 +59,18 @@ __device__ __forceinline__ void l2_mbar_wait(uint32_t bar, uint32_t parity)
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
+}
+// polling with back-off for the single-lane producer / MMA roles: they share their scheduler with an epilogue warp, and a
+// tight try_wait loop steals its issue slots (ncu: ~20 % of the kernel's samples sat in those loops)
+__device__ __forceinline__ void l2_mbar_wait_backoff(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
 }
 __device__ __forceinline__ void l2_tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar)
 {
@@ -251,6 +264,213 @@ __global__ void __launch_bounds__(256) k_l2_tc_merge(l2tc_args a, int* __restric
     o_idx[o] = best.i0; o_idx[o + 1] = best.i1; o_dist[o] = best.d0; o_dist[o + 1] = best.d1;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Persistent, pipelined variant: a CTA keeps its 128-query tile in shared memory and walks `tpc` consecutive train
+// tiles.  Three roles run concurrently and hand tiles to one another through mbarriers:
+//   warp 0 (one lane)   TMA producer: train tile i+1 streams into the other half of a 2-stage ring while
+//   warp 1 (one lane)   the MMA issuer runs the 4 x tcgen05.mma of tile i into TMEM accumulator (i & 1), and
+//   warps 2..5          the epilogue drains accumulator (i-1 & 1) with tcgen05.ld and updates the running top-2.
+// tcgen05.commit releases both the smem stage (back to the producer) and the accumulator (on to the epilogue);
+// the epilogue releases the accumulator back to the MMA issuer as soon as its tcgen05.ld have landed.
+// Row norms come from a small pre-pass (k_l2_row_norms) so the epilogue never touches the operand tiles.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_l2_row_norms(const uint8_t* __restrict__ rows, size_t nrows, int* __restrict__ norms)
+{
+    const size_t r = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= nrows) return;
+    const uint32_t v = ((const uint32_t*)(rows + r * L2TC_K))[threadIdx.x & 31];
+    int s = (int)__dp4a(v, v, 0u);
+    s = __reduce_add_sync(0xffffffffu, s);
+    if ((threadIdx.x & 31) == 0) norms[r] = s;
+}
+
+struct l2p_args {
+    const int* nq; const int* nt;
+    int cap_q, cap_t, splits, tpc;
+    const int* qnorm; const int* tnorm;        // [pairs*cap_q], [pairs*cap_t]
+    int4* part;
+};
+
+__device__ __forceinline__ void l2_mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+#define L2P_BSTAGES 4
+// grid: (ceil(cap_q/128), splits, pairs); dynamic smem: 1024 slack + 16 KB A + L2P_BSTAGES x 16 KB B
+__global__ void __launch_bounds__(L2TC_THREADS) k_l2_tc_persist(const __grid_constant__ CUtensorMap map_q,
+                                                                const __grid_constant__ CUtensorMap map_t, l2p_args a)
+{
+    extern __shared__ uint8_t l2_smem_raw[];
+    // barriers: 0 full_a | 1..NB full_b | 1+NB..2NB empty_b | 1+2NB, 2+2NB acc_full | 3+2NB, 4+2NB acc_empty
+    constexpr int NB = L2P_BSTAGES;
+    __shared__ __align__(8) uint64_t s_bar[5 + 2 * NB];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) int s_tn[2][L2TC_N];
+    const int pair = blockIdx.z, q0 = blockIdx.x * L2TC_M;
+    const int n_q = min(a.nq[pair], a.cap_q), n_t = min(a.nt[pair], a.cap_t);
+    const int tiles_total = (n_t + L2TC_N - 1) / L2TC_N, tile_begin = blockIdx.y * a.tpc;
+    if (q0 >= n_q || tile_begin >= tiles_total) return;          // uniform per CTA
+    const int ntile = min(a.tpc, tiles_total - tile_begin);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* sm = (uint8_t*)(((uintptr_t)l2_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = sm; uint8_t* sB0 = sm + L2TC_M * L2TC_K;
+    const uint32_t bar0 = l2_smem_u32(&s_bar[0]);
+#define BAR(i) (bar0 + 8u * (uint32_t)(i))
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(l2_smem_u32(&s_tmem)), "r"(2 * L2TC_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 3 + 2 * NB; ++i) l2_mbar_init(BAR(i), 1);
+        l2_mbar_init(BAR(3 + 2 * NB), 4); l2_mbar_init(BAR(4 + 2 * NB), 4);         // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            l2_mbar_expect_tx(BAR(0), L2TC_M * L2TC_K);
+            l2_tma_load_2d(l2_smem_u32(sA), &map_q, 0, pair * a.cap_q + q0, BAR(0));
+            for (int i = 0; i < ntile; ++i) {
+                const int sb = i % NB, pb = (i / NB) & 1;
+                l2_mbar_wait_backoff(BAR(1 + NB + sb), pb ^ 1);   // stage free (passes at once the first time round)
+                l2_mbar_expect_tx(BAR(1 + sb), L2TC_N * L2TC_K);
+                l2_tma_load_2d(l2_smem_u32(sB0 + sb * (L2TC_N * L2TC_K)), &map_t, 0, pair * a.cap_t + (tile_begin + i) * L2TC_N, BAR(1 + sb));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            l2_mbar_wait(BAR(0), 0);
+            const uint64_t da = l2_smem_desc(l2_smem_u32(sA));
+            for (int i = 0; i < ntile; ++i) {
+                const int st = i & 1, ph = (i >> 1) & 1;          // accumulator ring (2 deep)
+                const int sb = i % NB, pb = (i / NB) & 1;         // operand ring (NB deep: covers the TMA round trip)
+                l2_mbar_wait_backoff(BAR(1 + sb), pb);            // train tile landed
+                l2_mbar_wait_backoff(BAR(3 + 2 * NB + st), ph ^ 1);   // accumulator drained
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t db = l2_smem_desc(l2_smem_u32(sB0 + sb * (L2TC_N * L2TC_K)));
+                const uint32_t d = tmem + (uint32_t)(st * L2TC_N);
+#pragma unroll
+                for (int k = 0; k < L2TC_K / 32; ++k) {
+                    const uint64_t dak = da + (uint64_t)(2 * k), dbk = db + (uint64_t)(2 * k);
+                    const uint32_t acc = k > 0 ? 1u : 0u;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(d), "l"(dak), "l"(dbk), "r"(L2TC_IDESC), "r"(acc) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(1 + NB + sb)) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(1 + 2 * NB + st)) : "memory");
+            }
+        }
+        __syncwarp();
+    } else {
+        const int e = threadIdx.x - 64;
+        const int quarter = warp & 3, row = quarter * 32 + lane;
+        const int qn = (q0 + row < n_q) ? a.qnorm[(size_t)pair * a.cap_q + q0 + row] : 0;
+        l2_top2 best = { 0x7fffffff, 0x7fffffff, -1, -1 };
+        // the train norms of tile i+1 are fetched while tile i is being reduced (a load issued right before the barrier
+        // exposed a full global-memory round trip per tile)
+        const int* tnp = a.tnorm + (size_t)pair * a.cap_t;
+        int tn_next = (tile_begin * L2TC_N + e < n_t) ? tnp[tile_begin * L2TC_N + e] : 0;
+        for (int i = 0; i < ntile; ++i) {
+            const int st = i & 1, ph = (i >> 1) & 1;
+            const int t0 = (tile_begin + i) * L2TC_N, ncol = min(L2TC_N, n_t - t0);
+            // per-column key table of this tile: |b|^2 * 128 + column (see k_l2_tc_tile)
+            s_tn[st][e] = tn_next * 128 + e;
+            if (i + 1 < ntile) tn_next = (t0 + L2TC_N + e < n_t) ? tnp[t0 + L2TC_N + e] : 0;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            l2_mbar_wait(BAR(1 + 2 * NB + st), ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // four independent (best, second) chains -- element j feeds chain j % 4 -- so the min / max updates of
+            // consecutive elements do not wait on one another (a single serial chain left the epilogue latency-bound);
+            // keys are unique per column, so the order in which candidates are folded does not matter
+            int c0k[4] = { 0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff }, c1k[4] = { 0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff };
+            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(st * L2TC_N);
+#pragma unroll 1
+            for (int c0 = 0; c0 < L2TC_N; c0 += 32) {
+                uint32_t v[32];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                               "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                             : "r"(taddr + (uint32_t)c0) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 + 32 >= L2TC_N) {
+                    // the last chunk is in registers: hand the accumulator back to the MMA issuer before the arithmetic
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) l2_mbar_arrive(BAR(3 + 2 * NB + st));
+                }
+                const int4* tn4 = (const int4*)&s_tn[st][c0];
+                if (c0 + 32 <= ncol) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const int4 tn = tn4[j4];
+                        const int kk[4] = { tn.x - 256 * (int)v[4 * j4], tn.y - 256 * (int)v[4 * j4 + 1], tn.z - 256 * (int)v[4 * j4 + 2],
+                                            tn.w - 256 * (int)v[4 * j4 + 3] };
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { c1k[q] = max(c0k[q], min(c1k[q], kk[q])); c0k[q] = min(c0k[q], kk[q]); }
+                    }
+                } else if (c0 < ncol) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < ncol) {
+                            const int key = s_tn[st][c0 + j] - 256 * (int)v[j];
+                            c1k[j & 3] = max(c0k[j & 3], min(c1k[j & 3], key)); c0k[j & 3] = min(c0k[j & 3], key);
+                        }
+                }
+            }
+            // the two smallest of the eight chain values
+            int k0 = c0k[0], k1 = c1k[0];
+#pragma unroll
+            for (int q = 1; q < 4; ++q) {
+                k1 = max(k0, min(k1, c0k[q])); k0 = min(k0, c0k[q]);
+                k1 = min(k1, c1k[q]);                        // c1k[q] >= c0k[q] >= new k0: it can only replace the second best
+            }
+            // fold the tile's two best into the running top-2 (tiles come in ascending train order; strict '<')
+            if (k0 != 0x7fffffff) { const int f = k0 + qn * 128; l2_top2_update(best, f >> 7, t0 + (f & 127)); }
+            if (k1 != 0x7fffffff) { const int f = k1 + qn * 128; l2_top2_update(best, f >> 7, t0 + (f & 127)); }
+        }
+        if (q0 + row < n_q)
+            a.part[((size_t)pair * a.cap_q + q0 + row) * a.splits + blockIdx.y] = make_int4(best.i0, best.i1, best.d0, best.d1);
+    }
+#undef BAR
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * L2TC_N) : "memory");
+    }
+}
+
+// merge for the persistent kernel: split s covers train tiles [s*tpc, (s+1)*tpc)
+__global__ void __launch_bounds__(256) k_l2p_merge(l2p_args a, int* __restrict__ o_idx, int* __restrict__ o_dist)
+{
+    const int pair = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_q = min(a.nq[pair], a.cap_q), n_t = min(a.nt[pair], a.cap_t);
+    if (q >= n_q) return;
+    const int4* p = a.part + ((size_t)pair * a.cap_q + q) * a.splits;
+    l2_top2 best = { 0x7fffffff, 0x7fffffff, -1, -1 };
+    const int tiles_total = (n_t + L2TC_N - 1) / L2TC_N;
+    const int valid = (tiles_total + a.tpc - 1) / a.tpc;
+    for (int s = 0; s < valid; ++s) {
+        const int4 v = p[s];
+        if (v.x >= 0) l2_top2_update(best, v.z, v.x);
+        if (v.y >= 0) l2_top2_update(best, v.w, v.y);
+    }
+    const size_t o = 2 * ((size_t)pair * a.cap_q + q);
+    o_idx[o] = best.i0; o_idx[o + 1] = best.i1; o_dist[o] = best.d0; o_dist[o + 1] = best.d1;
+}
+
 static zs_status l2_make_map(CUtensorMap* m, const uint8_t* base, size_t rows)
 {
     zs_encode_tiled_fn enc = l2_get_encode_tiled();
@@ -275,6 +495,33 @@ zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, c
     zs_status st = l2_make_map(&mq, q8, (size_t)pairs * cap_q);
     if (st != ZS_OK) return st;
     if ((st = l2_make_map(&mt, t8, (size_t)pairs * cap_t)) != ZS_OK) return st;
+    const int q_tiles = zs_div_up(cap_q, L2TC_M), t_tiles = zs_div_up(cap_t, L2TC_N);
+    if (!getenv("ZS_L2_ONE_TILE")) {
+        // persistent kernel: enough CTAs for two waves of 2 CTAs per SM, otherwise as many train tiles per CTA as possible
+        int splits = (int)((4LL * ctx->sm_count + (long long)q_tiles * pairs - 1) / ((long long)q_tiles * pairs));
+        splits = splits < 1 ? 1 : splits > t_tiles ? t_tiles : splits;
+        l2p_args b;
+        b.nq = nq; b.nt = nt; b.cap_q = cap_q; b.cap_t = cap_t;
+        b.tpc = zs_div_up(t_tiles, splits); b.splits = zs_div_up(t_tiles, b.tpc);
+        b.part = (int4*)part;
+        int* norms = (int*)part + 4 * (size_t)pairs * cap_q * t_tiles;           // behind the (worst-case) partial area
+        b.qnorm = norms; b.tnorm = norms + (size_t)pairs * cap_q;
+        k_l2_row_norms<<<zs_div_up(pairs * cap_q, 8), 256, 0, ctx->stream>>>(q8, (size_t)pairs * cap_q, norms);
+        ZS_LAUNCH_CHECK(ctx);
+        k_l2_row_norms<<<zs_div_up(pairs * cap_t, 8), 256, 0, ctx->stream>>>(t8, (size_t)pairs * cap_t, norms + (size_t)pairs * cap_q);
+        ZS_LAUNCH_CHECK(ctx);
+        const size_t smem = 1024 + (size_t)(L2TC_M + L2P_BSTAGES * L2TC_N) * L2TC_K;
+        static bool attr_p = false;
+        if (!attr_p) {
+            ZS_CUDA(cudaFuncSetAttribute(k_l2_tc_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_p = true;
+        }
+        k_l2_tc_persist<<<dim3(q_tiles, b.splits, pairs), L2TC_THREADS, smem, ctx->stream>>>(mq, mt, b);
+        ZS_LAUNCH_CHECK(ctx);
+        k_l2p_merge<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(b, idx, dist);
+        ZS_LAUNCH_CHECK(ctx);
+        return ZS_OK;
+    }
     l2tc_args a;
     a.nq = nq; a.nt = nt; a.cap_q = cap_q; a.cap_t = cap_t; a.splits = zs_div_up(cap_t, L2TC_N);
     ZS_REQUIRE(part && ((uintptr_t)part % 16) == 0, "partial top-2 scratch must be 16-byte aligned");
@@ -295,5 +542,6 @@ zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, c
 
 size_t zs_l2_tensor_part_ints(int pairs, int cap_q, int cap_t)
 {
-    return 4 * (size_t)pairs * cap_q * zs_div_up(cap_t, L2TC_N);
+    // per-split partial top-2 (worst case: one split per train tile) + the row norms of both sides
+    return 4 * (size_t)pairs * cap_q * zs_div_up(cap_t, L2TC_N) + (size_t)pairs * ((size_t)cap_q + cap_t) + 64;
 }
