@@ -1,6 +1,7 @@
 // zs_common.cuh -- shared declarations of libzenslam_cuda.so (sm_100a only).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -86,6 +87,12 @@ __device__ __forceinline__ int zs_reflect101(int p, int n)
 }
 
 __device__ __forceinline__ int zs_slot(int first, int i, int slots) { return (first + i) % slots; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (zs_context.cu); null when the driver lacks it
+typedef CUresult (*zs_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+zs_encode_tiled_fn zs_get_encode_tiled();
 
 // internal launchers (defined in the per-stage .cu files)
 zs_status zs_launch_orb_blur(zs_context* ctx, const zs_pyramid* p, int first, int count);

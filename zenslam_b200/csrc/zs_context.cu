@@ -7,11 +7,7 @@
 #include "zs_common.cuh"
 
 // cuTensorMapEncodeTiled is resolved through the runtime so that the library does not link libcuda
-typedef CUresult (*zs_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static zs_encode_tiled_fn get_encode_tiled()
+zs_encode_tiled_fn zs_get_encode_tiled()
 {
     static zs_encode_tiled_fn fn = nullptr;
     if (!fn) {
@@ -32,7 +28,7 @@ static zs_status make_tensor_maps(zs_pyramid* p)
     zs_pyr_view& v = p->v;
     v.tmaps = nullptr; p->tmaps_dev = nullptr;
     if (p->win_w > 31 || p->win_h > 31) return ZS_OK;      // patches would not fit the 32x32 box
-    zs_encode_tiled_fn enc = get_encode_tiled();
+    zs_encode_tiled_fn enc = zs_get_encode_tiled();
     if (!enc) { zs_set_error("cuTensorMapEncodeTiled is not available from this driver"); return ZS_ERR_CUDA; }
     CUtensorMap maps[2 * ZS_MAX_LEVELS];
     for (int l = 0; l < v.levels; ++l) {

@@ -23,25 +23,6 @@
 #define L2TC_K 128           // bytes per descriptor row
 #define L2TC_THREADS 192     // warp 0: TMEM alloc + TMA, warp 1: MMA issue, warps 2..5: epilogue
 
-typedef CUresult (*zs_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static zs_encode_tiled_fn l2_get_encode_tiled()
-{
-    static zs_encode_tiled_fn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (zs_encode_tiled_fn)p;
-        else
-            cudaGetLastError();
-    }
-    return fn;
-}
-
 __device__ __forceinline__ uint32_t l2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void l2_mbar_init(uint32_t bar, int count)
@@ -473,7 +454,7 @@ __global__ void __launch_bounds__(256) k_l2p_merge(l2p_args a, int* __restrict__
 
 static zs_status l2_make_map(CUtensorMap* m, const uint8_t* base, size_t rows)
 {
-    zs_encode_tiled_fn enc = l2_get_encode_tiled();
+    zs_encode_tiled_fn enc = zs_get_encode_tiled();
     if (!enc) { zs_set_error("cuTensorMapEncodeTiled is not available from this driver"); return ZS_ERR_CUDA; }
     const cuuint64_t dims[2] = { L2TC_K, (cuuint64_t)rows };
     const cuuint64_t strides[1] = { L2TC_K };
