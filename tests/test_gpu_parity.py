@@ -374,16 +374,24 @@ def test_klt_multi_job_752(ctx):
         assert okeep.mean() > 0.5 if n > 100 else True
 
 
-def test_l2_tensor_core_ragged_pairs_vs_oracle_and_cuda_core(ctx, monkeypatch):
+@pytest.mark.parametrize("groups", [1, 2, 4])
+def test_l2_tensor_core_ragged_pairs_vs_oracle_and_cuda_core(ctx, monkeypatch, groups):
     """several pairs of different sizes in one launch (tile tails, pairs with an empty side, counts that are not
-    multiples of the 128-row tiles), checked against the oracle and against the CUDA-core dp4a kernel"""
+    multiples of the 128-row tiles, low-entropy rows full of distance ties), checked against the oracle and against
+    the CUDA-core dp4a kernel, for 1 / 2 / 4 epilogue warps per TMEM lane quarter (the column groups of a tile are
+    folded with an explicit index tie-break)"""
     from zenslam_b200.runtime import match_l2_cross, match_l2_knn2
+    monkeypatch.setenv("ZS_L2_EPI_GROUPS", str(groups))
     rng = np.random.default_rng(99)
-    sizes = [(300, 129), (1, 1), (128, 128), (257, 511), (0, 40), (40, 0), (130, 2)]
+    sizes = [(300, 129), (1, 1), (128, 128), (257, 511), (0, 40), (40, 0), (130, 2), (320, 500)]
     cap_q, cap_t = 320, 512
     q = np.zeros((len(sizes), cap_q, 128), np.float32); t = np.zeros((len(sizes), cap_t, 128), np.float32)
     for k, (a, b) in enumerate(sizes):
-        q[k, :a] = rng.integers(0, 256, (a, 128)); t[k, :b] = rng.integers(0, 256, (b, 128))
+        hi = 2 if k == len(sizes) - 1 else 256                      # last pair: 0/1 rows -> many equal distances
+        q[k, :a] = rng.integers(0, hi, (a, 128)); t[k, :b] = rng.integers(0, hi, (b, 128))
+        if hi == 2:
+            q[k, :a, 8:] = 0; t[k, :b, 8:] = 0                      # 8 informative bits: every row has dozens of ties
+            t[k, 300] = t[k, 40] = t[k, 170] = q[k, 7]
         # garbage beyond the counts must be ignored
         q[k, a:] = rng.integers(0, 256, (cap_q - a, 128)); t[k, b:] = rng.integers(0, 256, (cap_t - b, 128))
         if a > 5 and b > 100:

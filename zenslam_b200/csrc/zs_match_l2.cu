@@ -278,16 +278,30 @@ __device__ __forceinline__ void l2_mbar_arrive(uint32_t bar)
 }
 
 #define L2P_BSTAGES 4
+__device__ __forceinline__ int l2_min3(int a, int b, int c)
+{
+    int d;
+    asm("min.s32 %0, %1, %2;\n\tmin.s32 %0, %0, %3;" : "=&r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// CG = epilogue warps per TMEM lane quarter (the 128 accumulator columns of a tile are split into CG groups of
+// 128/CG); threads = 64 + 128 CG.  One epilogue warp per scheduler (CG = 1) leaves the drain latency-bound -- a
+// warp cannot issue its dependent min/max chain back to back -- so the MMA issuer idles on acc_empty; with CG = 2 or
+// 4 every scheduler interleaves 4 to 8 epilogue warps (2 CTAs per SM) and the drain approaches the issue rate.
 // grid: (ceil(cap_q/128), splits, pairs); dynamic smem: 1024 slack + 16 KB A + L2P_BSTAGES x 16 KB B
-__global__ void __launch_bounds__(L2TC_THREADS) k_l2_tc_persist(const __grid_constant__ CUtensorMap map_q,
-                                                                const __grid_constant__ CUtensorMap map_t, l2p_args a)
+template <int CG>
+__global__ void __launch_bounds__(64 + 128 * CG, 2) k_l2_tc_persist(const __grid_constant__ CUtensorMap map_q,
+                                                                     const __grid_constant__ CUtensorMap map_t, l2p_args a)
 {
     extern __shared__ uint8_t l2_smem_raw[];
     // barriers: 0 full_a | 1..NB full_b | 1+NB..2NB empty_b | 1+2NB, 2+2NB acc_full | 3+2NB, 4+2NB acc_empty
     constexpr int NB = L2P_BSTAGES;
+    constexpr int NCOL = L2TC_N / CG;                // accumulator columns per epilogue warp
+    constexpr int CW = CG >= 4 ? 16 : 32;            // columns per tcgen05.ld (register budget: 56 at 576 threads x 2 CTAs)
     __shared__ __align__(8) uint64_t s_bar[5 + 2 * NB];
     __shared__ uint32_t s_tmem;
-    __shared__ __align__(16) int s_tn[2][L2TC_N];
+    __shared__ __align__(16) int s_tn[4 * CG][NCOL];             // per-warp column key table (private: no CTA barrier)
+    __shared__ __align__(16) int4 s_best[CG > 1 ? CG - 1 : 1][L2TC_M];
     const int pair = blockIdx.z, q0 = blockIdx.x * L2TC_M;
     const int n_q = min(a.nq[pair], a.cap_q), n_t = min(a.nt[pair], a.cap_t);
     const int tiles_total = (n_t + L2TC_N - 1) / L2TC_N, tile_begin = blockIdx.y * a.tpc;
@@ -304,7 +318,7 @@ __global__ void __launch_bounds__(L2TC_THREADS) k_l2_tc_persist(const __grid_con
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     } else if (warp == 1 && lane == 0) {
         for (int i = 0; i < 3 + 2 * NB; ++i) l2_mbar_init(BAR(i), 1);
-        l2_mbar_init(BAR(3 + 2 * NB), 4); l2_mbar_init(BAR(4 + 2 * NB), 4);         // one arrival per epilogue warp
+        l2_mbar_init(BAR(3 + 2 * NB), 4 * CG); l2_mbar_init(BAR(4 + 2 * NB), 4 * CG);   // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -350,61 +364,87 @@ __global__ void __launch_bounds__(L2TC_THREADS) k_l2_tc_persist(const __grid_con
         }
         __syncwarp();
     } else {
-        const int e = threadIdx.x - 64;
-        const int quarter = warp & 3, row = quarter * 32 + lane;
+        // epilogue warp w = warp - 2: TMEM lane quarter = warp % 4 (hardware rule), column group cg = w / 4
+        const int ew = warp - 2, quarter = warp & 3, cg = ew >> 2, row = quarter * 32 + lane;
         const int qn = (q0 + row < n_q) ? a.qnorm[(size_t)pair * a.cap_q + q0 + row] : 0;
         l2_top2 best = { 0x7fffffff, 0x7fffffff, -1, -1 };
-        // the train norms of tile i+1 are fetched while tile i is being reduced (a load issued right before the barrier
-        // exposed a full global-memory round trip per tile)
+        int* tn = s_tn[ew];
+        // the train norms of tile i+1 are fetched while tile i is being reduced; lane l owns columns l, l+32, .. of
+        // the warp's column group
         const int* tnp = a.tnorm + (size_t)pair * a.cap_t;
-        int tn_next = (tile_begin * L2TC_N + e < n_t) ? tnp[tile_begin * L2TC_N + e] : 0;
+        int tn_next[NCOL / 32 > 0 ? NCOL / 32 : 1];
+#pragma unroll
+        for (int u = 0; u < NCOL / 32; ++u) {
+            const int col = tile_begin * L2TC_N + cg * NCOL + u * 32 + lane;
+            tn_next[u] = col < n_t ? tnp[col] : 0;
+        }
         for (int i = 0; i < ntile; ++i) {
             const int st = i & 1, ph = (i >> 1) & 1;
-            const int t0 = (tile_begin + i) * L2TC_N, ncol = min(L2TC_N, n_t - t0);
-            // per-column key table of this tile: |b|^2 * 128 + column (see k_l2_tc_tile)
-            s_tn[st][e] = tn_next * 128 + e;
-            if (i + 1 < ntile) tn_next = (t0 + L2TC_N + e < n_t) ? tnp[t0 + L2TC_N + e] : 0;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int t0 = (tile_begin + i) * L2TC_N, ncol = min(NCOL, n_t - t0 - cg * NCOL);   // may be <= 0
+            // per-column key table of this warp's columns: |b|^2 * 128 + column (see k_l2_tc_tile)
+            __syncwarp();                                        // every lane is done with the previous tile's table
+#pragma unroll
+            for (int u = 0; u < NCOL / 32; ++u) {
+                tn[u * 32 + lane] = tn_next[u] * 128 + cg * NCOL + u * 32 + lane;
+                const int col = t0 + L2TC_N + cg * NCOL + u * 32 + lane;
+                if (i + 1 < ntile) tn_next[u] = col < n_t ? tnp[col] : 0;
+            }
+            __syncwarp();
             l2_mbar_wait(BAR(1 + 2 * NB + st), ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // four independent (best, second) chains -- element j feeds chain j % 4 -- so the min / max updates of
-            // consecutive elements do not wait on one another (a single serial chain left the epilogue latency-bound);
-            // keys are unique per column, so the order in which candidates are folded does not matter
+            // consecutive elements do not wait on one another; keys are unique per column, so the order in which
+            // candidates are folded does not matter
             int c0k[4] = { 0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff }, c1k[4] = { 0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff };
-            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(st * L2TC_N);
+            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(st * L2TC_N + cg * NCOL);
 #pragma unroll 1
-            for (int c0 = 0; c0 < L2TC_N; c0 += 32) {
-                uint32_t v[32];
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                               "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                             : "r"(taddr + (uint32_t)c0) : "memory");
+            for (int c0 = 0; c0 < NCOL; c0 += CW) {
+                uint32_t v[CW];
+                if (CW == 32)
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                                   "=r"(v[16 % CW]), "=r"(v[17 % CW]), "=r"(v[18 % CW]), "=r"(v[19 % CW]), "=r"(v[20 % CW]), "=r"(v[21 % CW]),
+                                   "=r"(v[22 % CW]), "=r"(v[23 % CW]), "=r"(v[24 % CW]), "=r"(v[25 % CW]), "=r"(v[26 % CW]), "=r"(v[27 % CW]),
+                                   "=r"(v[28 % CW]), "=r"(v[29 % CW]), "=r"(v[30 % CW]), "=r"(v[31 % CW])
+                                 : "r"(taddr + (uint32_t)c0) : "memory");
+                else
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                                 : "r"(taddr + (uint32_t)c0) : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 + 32 >= L2TC_N) {
+                if (c0 + CW >= NCOL) {
                     // the last chunk is in registers: hand the accumulator back to the MMA issuer before the arithmetic
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) l2_mbar_arrive(BAR(3 + 2 * NB + st));
                 }
-                const int4* tn4 = (const int4*)&s_tn[st][c0];
-                if (c0 + 32 <= ncol) {
+                const int4* tn4 = (const int4*)&tn[c0];
+                if (c0 + CW <= ncol) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const int4 tn = tn4[j4];
-                        const int kk[4] = { tn.x - 256 * (int)v[4 * j4], tn.y - 256 * (int)v[4 * j4 + 1], tn.z - 256 * (int)v[4 * j4 + 2],
-                                            tn.w - 256 * (int)v[4 * j4 + 3] };
+                    for (int j4 = 0; j4 < CW / 4; ++j4) {
+                        const int4 t4 = tn4[j4];
+                        const int kk[4] = { t4.x - 256 * (int)v[4 * j4], t4.y - 256 * (int)v[4 * j4 + 1], t4.z - 256 * (int)v[4 * j4 + 2],
+                                            t4.w - 256 * (int)v[4 * j4 + 3] };
+                        // two candidates per chain update: lo/hi of the pair, then second' = min3(second, hi, max(best, lo)),
+                        // best' = min(best, lo) -- 5 ALU-pipe instructions per 2 elements instead of 6 (the epilogue is bound
+                        // by the half-rate ALU pipe that executes VIMNMX, not by issue slots or the tensor pipe)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) { c1k[q] = max(c0k[q], min(c1k[q], kk[q])); c0k[q] = min(c0k[q], kk[q]); }
+                        for (int q = 0; q < 2; ++q) {
+                            const int lo = min(kk[2 * q], kk[2 * q + 1]), hi = max(kk[2 * q], kk[2 * q + 1]);
+                            const int ch = (2 * j4 + q) & 3;
+                            c1k[ch] = l2_min3(c1k[ch], hi, max(c0k[ch], lo)); c0k[ch] = min(c0k[ch], lo);
+                        }
                     }
                 } else if (c0 < ncol) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
+                    for (int j = 0; j < CW; ++j)
                         if (c0 + j < ncol) {
-                            const int key = s_tn[st][c0 + j] - 256 * (int)v[j];
+                            const int key = tn[c0 + j] - 256 * (int)v[j];
                             c1k[j & 3] = max(c0k[j & 3], min(c1k[j & 3], key)); c0k[j & 3] = min(c0k[j & 3], key);
                         }
                 }
@@ -416,11 +456,33 @@ __global__ void __launch_bounds__(L2TC_THREADS) k_l2_tc_persist(const __grid_con
                 k1 = max(k0, min(k1, c0k[q])); k0 = min(k0, c0k[q]);
                 k1 = min(k1, c1k[q]);                        // c1k[q] >= c0k[q] >= new k0: it can only replace the second best
             }
-            // fold the tile's two best into the running top-2 (tiles come in ascending train order; strict '<')
+            // fold the tile's two best into the running top-2 (a warp sees its columns in ascending train order; strict '<')
             if (k0 != 0x7fffffff) { const int f = k0 + qn * 128; l2_top2_update(best, f >> 7, t0 + (f & 127)); }
             if (k1 != 0x7fffffff) { const int f = k1 + qn * 128; l2_top2_update(best, f >> 7, t0 + (f & 127)); }
         }
-        if (q0 + row < n_q)
+        // fold the CG column groups of a row: train indices interleave between groups, so ties are broken explicitly
+        // (smaller index wins -- the order cv::BFMatcher's ascending scan with strict '<' produces)
+        if (CG > 1) {
+            if (cg > 0) s_best[cg - 1][row] = make_int4(best.i0, best.i1, best.d0, best.d1);
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * CG) : "memory");
+            if (cg == 0) {
+#pragma unroll
+                for (int g = 0; g < CG - 1; ++g) {
+                    const int4 o = s_best[g][row];
+                    const int od[2] = { o.z, o.w }, oi[2] = { o.x, o.y };
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (oi[u] < 0) continue;
+                        if (od[u] < best.d0 || (od[u] == best.d0 && oi[u] < best.i0)) {
+                            best.d1 = best.d0; best.i1 = best.i0; best.d0 = od[u]; best.i0 = oi[u];
+                        } else if (od[u] < best.d1 || (od[u] == best.d1 && oi[u] < best.i1)) {
+                            best.d1 = od[u]; best.i1 = oi[u];
+                        }
+                    }
+                }
+            }
+        }
+        if (cg == 0 && q0 + row < n_q)
             a.part[((size_t)pair * a.cap_q + q0 + row) * a.splits + blockIdx.y] = make_int4(best.i0, best.i1, best.d0, best.d1);
     }
 #undef BAR
@@ -494,10 +556,17 @@ zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, c
         const size_t smem = 1024 + (size_t)(L2TC_M + L2P_BSTAGES * L2TC_N) * L2TC_K;
         static bool attr_p = false;
         if (!attr_p) {
-            ZS_CUDA(cudaFuncSetAttribute(k_l2_tc_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ZS_CUDA(cudaFuncSetAttribute(k_l2_tc_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ZS_CUDA(cudaFuncSetAttribute(k_l2_tc_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ZS_CUDA(cudaFuncSetAttribute(k_l2_tc_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_p = true;
         }
-        k_l2_tc_persist<<<dim3(q_tiles, b.splits, pairs), L2TC_THREADS, smem, ctx->stream>>>(mq, mt, b);
+        const char* eg = getenv("ZS_L2_EPI_GROUPS");             // 1, 2 or 4 epilogue warps per TMEM lane quarter
+        const int cgsel = eg ? atoi(eg) : 2;
+        const dim3 grid(q_tiles, b.splits, pairs);
+        if (cgsel == 1) k_l2_tc_persist<1><<<grid, 64 + 128, smem, ctx->stream>>>(mq, mt, b);
+        else if (cgsel == 2) k_l2_tc_persist<2><<<grid, 64 + 256, smem, ctx->stream>>>(mq, mt, b);
+        else k_l2_tc_persist<4><<<grid, 64 + 512, smem, ctx->stream>>>(mq, mt, b);
         ZS_LAUNCH_CHECK(ctx);
         k_l2p_merge<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(b, idx, dist);
         ZS_LAUNCH_CHECK(ctx);
