@@ -202,6 +202,63 @@ def orb_compute(img, xs, ys, angles=None):
     return kept, desc
 
 
+def resize_linear_exact(img, dw, dh):
+    """cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT) for u8 single channel."""
+    img = _u8img(img)
+    h, w = img.shape
+    out = np.empty((dh, dw), np.uint8)
+    lib().zso_resize_linear_exact(_p(img), w, h, w, _p(out), dw, dh, dw)
+    return out
+
+
+def fast_atan2(y, x):
+    f = lib().zso_fast_atan2_deg
+    f.restype = C.c_float; f.argtypes = [C.c_float, C.c_float]
+    return float(f(float(y), float(x)))
+
+
+def orb_level_sizes(w, h, scale_factor=1.2, nlevels=8):
+    out = []
+    s = C.c_float(); lw = C.c_int(); lh = C.c_int()
+    f = lib().zso_orb_level_size
+    f.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    for l in range(nlevels):
+        f(w, h, scale_factor, l, C.byref(s), C.byref(lw), C.byref(lh))
+        out.append((float(s.value), int(lw.value), int(lh.value)))
+    return out
+
+
+def orb_detect(img, mask=None, nfeatures=500, scale_factor=1.2, nlevels=8, edge=31, patch=31, fast_threshold=20,
+               describe=True):
+    """cv::ORB::create(nfeatures, scale_factor, nlevels, edge, 0, 2, HARRIS_SCORE, patch, fast_threshold)->detect(img,
+    mask) [+ cv::ORB::create()->compute] in canonical order (octave, y, x).
+    Returns dict(x, y, size, angle, response, octave[, desc])."""
+    img = _u8img(img)
+    h, w = img.shape
+    m = None
+    if mask is not None:
+        m = np.ascontiguousarray(mask, np.uint8)
+        assert m.shape == img.shape
+    cap = 4 * nfeatures + 64
+    f = lib().zso_orb_detect
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
+                  C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_int]
+    while True:
+        x = np.empty(cap, np.float32); y = np.empty(cap, np.float32); size = np.empty(cap, np.float32)
+        ang = np.empty(cap, np.float32); resp = np.empty(cap, np.float32); octv = np.empty(cap, np.int32)
+        desc = np.zeros((cap, 32), np.uint8) if describe else None
+        n = f(_p(img), w, h, w, _p(m) if m is not None else None, w, nfeatures, scale_factor, nlevels, edge, patch,
+              fast_threshold, _p(x), _p(y), _p(size), _p(ang), _p(resp), _p(octv), _p(desc) if describe else None, cap)
+        if n <= cap:
+            break
+        cap = n
+    out = dict(x=x[:n].copy(), y=y[:n].copy(), size=size[:n].copy(), angle=ang[:n].copy(), response=resp[:n].copy(),
+               octave=octv[:n].copy())
+    if describe:
+        out["desc"] = desc[:n].copy()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # matching
 # ---------------------------------------------------------------------------------------------

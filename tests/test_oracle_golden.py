@@ -182,3 +182,25 @@ def test_triangulate_golden(golden):
     # without the epipolar filter more pairs survive, and none is lost
     _, keep2, _ = oracle.triangulate_keypoints(g["P0"], g["P1"], None, g["t"], g["pts0"], g["pts1"])
     assert keep2.sum() >= keep.sum() and np.all(keep2[keep])
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_orb_multiscale_detector_golden(golden, case):
+    """`feature: ORB` (keypoint_detector_simple.cpp:17,49,54): the C restatement of cv::ORB::detect (8-level
+    INTER_LINEAR_EXACT pyramid, FAST + mask + border, retainBest by FAST score, Harris, retainBest, IC angle) and of
+    cv::ORB::compute on those multi-scale keypoints reproduces cv2 bit for bit -- positions, sizes, angles, Harris
+    responses, octaves, descriptors -- as a set in canonical (octave, y, x) order"""
+    g = golden("orb_detect")
+    mask = g[case + "_mask"] if (case + "_mask") in g.files else None
+    o = oracle.orb_detect(g[case + "_img"], mask, fast_threshold=int(g[case + "_thr"]))
+    for k in ("x", "y", "size", "angle", "response", "octave", "desc"):
+        assert np.array_equal(o[k], g[case + "_" + k]), k
+
+
+def test_resize_linear_exact_and_fast_atan2_golden(golden):
+    g = golden("orb_detect")
+    l1 = oracle.resize_linear_exact(g["a_img"], 313, 200)
+    assert np.array_equal(l1, g["resize_313x200"])
+    assert np.array_equal(oracle.resize_linear_exact(l1, 261, 167), g["resize_261x167"])
+    got = np.array([oracle.fast_atan2(y, x) for y, x in g["atan_yx"]], np.float32)
+    assert np.array_equal(got, g["atan_deg"])
