@@ -145,6 +145,39 @@ ZS_API zs_status zs_orb_compute(zs_context* ctx, const zs_pyramid* p, int first,
 /* test access: the blurred level-0 image ORB samples from (u8, w*h) */
 ZS_API zs_status zs_orb_download_blur(zs_context* ctx, const zs_pyramid* p, int slot, uint8_t* dst);
 
+/* ---- multi-scale ORB detector: `feature: ORB` ----------------------------------------------
+ * cv::ORB::create(nfeatures, scale_factor, nlevels, edge_threshold, 0, 2, HARRIS_SCORE, patch_size, fast_threshold)
+ *   ->detect(image, keypoints, mask), then (optional) cv::ORB::create()->compute(image, keypoints, descriptors)
+ * (zenslam_core/source/detection/keypoint_detector_simple.cpp:17,27,49,54; the reference passes 500, 1.2f, 8, 31, 31 and
+ * detection.fast_threshold).  Images [count][height][pitch] u8 on the device, optional masks of the same shape (0 =
+ * rejected).  Outputs are [count][cap] device arrays, cap = zs_orb_detector_capacity(); d_xy is (x, y) interleaved;
+ * d_count receives the true number per image (ZS_ERR_CAPACITY is never raised: at most cap are stored).
+ * The keypoint set, sizes, angles, Harris responses, octaves and descriptors equal OpenCV's; the order is canonical
+ * (octave ascending, then y, then x) because OpenCV's own order comes out of std::nth_element.  d_desc may be NULL
+ * (detect only); describing needs edge_threshold >= 31 and patch_size 31 (cv::ORB::create() defaults on the compute side). */
+typedef struct zs_orb_detector zs_orb_detector;
+ZS_API zs_status zs_orb_detector_create(zs_context* ctx, int width, int height, int max_images, int nfeatures,
+                                        float scale_factor, int nlevels, int edge_threshold, int patch_size,
+                                        int fast_threshold, zs_orb_detector** out);
+ZS_API void zs_orb_detector_destroy(zs_orb_detector* det);
+ZS_API int zs_orb_detector_capacity(const zs_orb_detector* det);
+ZS_API zs_status zs_orb_detector_level(const zs_orb_detector* det, int level, int* width, int* height, float* scale,
+                                       int* nfeatures);
+ZS_API zs_status zs_orb_detect_and_compute(zs_context* ctx, zs_orb_detector* det, const uint8_t* d_img, size_t pitch,
+                                           size_t stride, const uint8_t* d_mask, size_t mask_pitch, size_t mask_stride,
+                                           int count, float* d_xy, float* d_size, float* d_angle, float* d_response,
+                                           int* d_octave, int* d_count, uint8_t* d_desc /* [count][cap][32] or NULL */);
+/* test access: which = 0 pyramid image, 1 mask, 2 blurred image of `level` of image `image` (u8, level w*h) */
+ZS_API zs_status zs_orb_detector_download_level(zs_context* ctx, const zs_orb_detector* det, int image, int level,
+                                                int which, uint8_t* dst);
+/* host mirror of keypoint_detector_simple::detect_keypoints with `feature: ORB` (mask may be NULL; outputs sized cap;
+ * *n_out = keypoints found, ZS_ERR_CAPACITY if that exceeds cap) */
+ZS_API zs_status zs_detect_keypoints_orb_host(zs_context* ctx, const uint8_t* img, int width, int height, size_t pitch,
+                                              const uint8_t* mask, size_t mask_pitch, int nfeatures, float scale_factor,
+                                              int nlevels, int edge_threshold, int patch_size, int fast_threshold,
+                                              float* x, float* y, float* size, float* angle, float* response,
+                                              int* octave, uint8_t* desc /* or NULL */, int cap, int* n_out);
+
 /* ---- matching: cv::BFMatcher as used by zenslam::matcher --------------------------------------
  * (zenslam_core/source/matching/matcher.cpp:60-80; utils::create_matcher matching_utils.cpp:63-95)
  * `pairs` independent problems; problem k matches queries d_q + k*q_stride (nq[k] rows) against

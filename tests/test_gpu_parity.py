@@ -461,3 +461,95 @@ def test_corner_subpix_batch_vs_oracle(ctx, w, h, cell, thr, win, its, eps):
         assert np.array_equal(after[k, :cnt[k]], want), k
         moved += int((np.abs(want - before[k, :cnt[k]]).max(1) > 0).sum())
     assert moved > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-scale ORB detector (`feature: ORB`)
+# ---------------------------------------------------------------------------------------------
+ORB_KEYS = ("x", "y", "size", "angle", "response", "octave", "desc")
+
+
+def _orb_gpu(det, images, masks=None):
+    r = det.detect_and_compute(images, masks)
+    out = []
+    for k in range(len(images)):
+        n = int(r["n"][k])
+        assert n <= det.cap
+        xy = r["xy"][k, :n].cpu().numpy()
+        out.append(dict(x=xy[:, 0].copy(), y=xy[:, 1].copy(), size=r["size"][k, :n].cpu().numpy(),
+                        angle=r["angle"][k, :n].cpu().numpy(), response=r["response"][k, :n].cpu().numpy(),
+                        octave=r["octave"][k, :n].cpu().numpy(), desc=r["desc"][k, :n].cpu().numpy()))
+    return out
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_orb_multiscale_detector_golden(ctx, golden, case):
+    """bit-exact against cv2's ORB detect + compute on the committed fixture (set in canonical order), with and without
+    a mask; the pyramid levels equal cv2.resize(INTER_LINEAR_EXACT)"""
+    from zenslam_b200.runtime import OrbDetector
+    g = golden("orb_detect")
+    img = g[case + "_img"]
+    mask = g[case + "_mask"] if (case + "_mask") in g.files else None
+    h, w = img.shape
+    det = OrbDetector(ctx, w, h, 1, fast_threshold=int(g[case + "_thr"]))
+    o = _orb_gpu(det, img[None], None if mask is None else mask[None])[0]
+    for k in ORB_KEYS:
+        assert np.array_equal(o[k], g[case + "_" + k]), k
+    if case == "a":
+        assert np.array_equal(det.download_level(0, 1), g["resize_313x200"])
+        assert np.array_equal(det.download_level(0, 2), g["resize_261x167"])
+    det.close()
+
+
+@pytest.mark.parametrize("w,h,thr,batch", [(752, 480, 10, 3), (1280, 720, 20, 2), (200, 150, 5, 2)])
+def test_orb_multiscale_detector_vs_oracle(ctx, w, h, thr, batch):
+    """batches of frames (one masked) against the oracle at the reference's ORB parameters; small frames lose their
+    top levels to the 31-px edge filter"""
+    from zenslam_b200.runtime import OrbDetector
+    imgs = np.stack([syn.stereo_pair(w, h, 8100 + i)[0] for i in range(batch)])
+    rng = np.random.default_rng(5)
+    masks = np.full_like(imgs, 255)
+    yy, xx = np.mgrid[0:h, 0:w]
+    for _ in range(150):
+        cx, cy = rng.integers(0, w), rng.integers(0, h)
+        masks[0][(xx - cx) ** 2 + (yy - cy) ** 2 <= 64] = 0
+    det = OrbDetector(ctx, w, h, batch, fast_threshold=thr)
+    got = _orb_gpu(det, imgs, masks)
+    for k in range(batch):
+        o = oracle.orb_detect(imgs[k], masks[k], fast_threshold=thr)
+        assert len(o["x"]) > 0
+        for key in ORB_KEYS:
+            assert np.array_equal(got[k][key], o[key]), (k, key)
+    # detect only, no mask: same keypoints as the unmasked oracle
+    r = det.detect_and_compute(imgs[:1], None, describe=False)
+    o = oracle.orb_detect(imgs[0], None, fast_threshold=thr, describe=False)
+    n = int(r["n"][0])
+    assert n == len(o["x"]) and np.array_equal(r["xy"][0, :n, 0].cpu().numpy(), o["x"])
+    assert np.array_equal(r["angle"][0, :n].cpu().numpy(), o["angle"])
+    det.close()
+
+
+def test_simple_detector_feature_orb_mirror(ctx):
+    """keypoint_detector_simple with `feature: ORB` through the host-pointer entry (zs_detect_keypoints_orb_host):
+    existing keypoints mask discs of radius min(cell)/2 (keypoint_detector_simple.cpp:41-48)"""
+    from zenslam_b200 import detection_options
+    from zenslam_b200.detection import keypoint_detector_simple
+    from zenslam_b200.types import keypoint
+    w, h = 640, 400
+    img = syn.stereo_pair(w, h, 8200)[0]
+    opt = detection_options(feature_detector="ORB", fast_threshold=12, algorithm="SIMPLE")
+    det = keypoint_detector_simple(opt, ctx)
+    first = det.detect_keypoints(img, None)
+    o = oracle.orb_detect(img, None, fast_threshold=12)
+    assert len(first) == len(o["x"]) > 100
+    assert np.array_equal(np.array([k.pt for k in first], np.float32), np.stack([o["x"], o["y"]], 1))
+    assert np.array_equal(np.stack([k.descriptor for k in first]), o["desc"])
+    assert [k.octave for k in first] == o["octave"].tolist()
+    existing = {k.index: k for k in first[::3]}
+    second = det.detect_keypoints(img, existing)
+    mask = det._mask(h, w, existing)
+    o2 = oracle.orb_detect(img, mask, fast_threshold=12)
+    assert np.array_equal(np.array([k.pt for k in second], np.float32), np.stack([o2["x"], o2["y"]], 1))
+    assert np.array_equal(np.array([k.angle for k in second], np.float32), o2["angle"])
+    assert np.array_equal(np.array([k.response for k in second], np.float32), o2["response"])
+    assert second[0].index == first[-1].index + 1                      # sequential global indices

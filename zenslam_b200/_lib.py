@@ -83,6 +83,14 @@ SIGNATURES = {
     "zs_corner_subpix": (I, [P, P, I, I, P, P, I, I, I, I, D]),
     "zs_orb_compute": (I, [P, P, I, I, P, P, P, P, I, P, P, P, P, P]),
     "zs_orb_download_blur": (I, [P, P, I, P]),
+    "zs_orb_detector_create": (I, [P, I, I, I, I, C.c_float, I, I, I, I, C.POINTER(P)]),
+    "zs_orb_detector_destroy": (None, [P]),
+    "zs_orb_detector_capacity": (I, [P]),
+    "zs_orb_detector_level": (I, [P, I, C.POINTER(I), C.POINTER(I), C.POINTER(C.c_float), C.POINTER(I)]),
+    "zs_orb_detect_and_compute": (I, [P, P, P, Z, Z, P, Z, Z, I, P, P, P, P, P, P, P]),
+    "zs_orb_detector_download_level": (I, [P, P, I, I, I, P]),
+    "zs_detect_keypoints_orb_host": (I, [P, P, I, I, Z, P, Z, I, C.c_float, I, I, I, I, P, P, P, P, P, P, P, I,
+                                         C.POINTER(I)]),
     "zs_match_hamming_knn2": (I, [P, P, P, Z, P, P, Z, I, I, I, D, P, P, P]),
     "zs_match_hamming_cross": (I, [P, P, P, Z, P, P, Z, I, I, I, P, P]),
     "zs_match_l2_knn2": (I, [P, P, P, Z, P, P, Z, I, I, I, I, D, P, P, P]),

@@ -42,6 +42,8 @@ struct zs_context {
     void* pinned; size_t pinned_bytes;
     // cached pyramids for the single-image host mirrors: [0] LK (2 slots), [1] detection (1 slot)
     zs_pyramid* host_pyr[2];
+    // cached multi-scale ORB detector of zs_detect_keypoints_orb_host and the parameters it was built for
+    zs_orb_detector* host_orb; int host_orb_key[8]; float host_orb_sf;
 };
 
 struct zs_pyramid {

@@ -140,6 +140,7 @@ void zs_context_destroy(zs_context* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 2; ++i) if (c->host_pyr[i]) zs_pyramid_destroy(c->host_pyr[i]);
+    if (c->host_orb) zs_orb_detector_destroy(c->host_orb);
     if (c->scratch) cudaFree(c->scratch);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->own_stream) cudaStreamDestroy(c->stream);

@@ -87,9 +87,31 @@ class keypoint_detector_simple(keypoint_detector):
     FAST with a mask that is 0 inside discs of radius min(cell)/2 around existing keypoints."""
 
     def __init__(self, options: detection_options, ctx: Context, cap: int = 1 << 17):
-        _require_fast_orb(options)
+        # `feature: ORB` = cv::ORB::create(500, 1.2f, 8, 31, 0, 2, HARRIS_SCORE, 31, fast_threshold) as the detector
+        # (keypoint_detector_simple.cpp:17); the descriptor stays cv::ORB::create() (:27)
+        if options.feature_detector not in ("FAST", "ORB") or options.descriptor != "ORB":
+            raise NotImplementedError("the CUDA detector implements feature FAST or ORB with descriptor ORB")
         self._options, self._ctx, self._cap = options, ctx, cap
         self._pyr = None
+
+    def _detect_orb(self, image, mask) -> list:
+        h, w = image.shape
+        cap = 500 + 32 * 8 + 64
+        x = np.empty(cap, np.float32); y = np.empty(cap, np.float32); size = np.empty(cap, np.float32)
+        ang = np.empty(cap, np.float32); resp = np.empty(cap, np.float32); octv = np.empty(cap, np.int32)
+        desc = np.empty((cap, 32), np.uint8)
+        n = C.c_int(0)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(lib().zs_detect_keypoints_orb_host(self._ctx._h, p(image), w, h, w, p(mask) if mask is not None else None, w,
+                                                 500, 1.2, 8, 31, 31, int(self._options.fast_threshold), p(x), p(y), p(size),
+                                                 p(ang), p(resp), p(octv), p(desc), cap, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            out.append(keypoint(pt=(float(x[i]), float(y[i])), size=float(size[i]), angle=float(ang[i]),
+                                response=float(resp[i]), octave=int(octv[i]), class_id=-1, index=keypoint.index_next,
+                                descriptor=desc[i].copy()))
+            keypoint.index_next += 1
+        return out
 
     def _mask(self, h, w, keypoints_existing):
         if not keypoints_existing:
@@ -111,6 +133,8 @@ class keypoint_detector_simple(keypoint_detector):
     def detect_keypoints(self, image: np.ndarray, keypoints_existing=None) -> list:
         image = np.ascontiguousarray(image, np.uint8)
         h, w = image.shape
+        if self._options.feature_detector == "ORB":
+            return self._detect_orb(image, self._mask(h, w, keypoints_existing))
         if self._pyr is None or (self._pyr.width, self._pyr.height) != (w, h):
             self._pyr = Pyramid(self._ctx, w, h, 1, (16, 16), 0)
         pyr = self._pyr

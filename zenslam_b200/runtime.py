@@ -224,6 +224,67 @@ def orb_compute(pyr: Pyramid, first, count, xy, resp, n, angle=None):
     return oxy, oresp, src, on, desc
 
 
+class OrbDetector:
+    """zs_orb_detector: cv::ORB::create(nfeatures, scale_factor, nlevels, edge, 0, 2, HARRIS_SCORE, patch, fast_threshold)
+    ->detect(image, mask) [+ cv::ORB::create()->compute] for batches of up to max_images frames of one size
+    (keypoint_detector_simple.cpp:17,27,49,54).  Keypoints come back in canonical order (octave, y, x)."""
+
+    def __init__(self, ctx: Context, width: int, height: int, max_images: int = 1, nfeatures: int = 500,
+                 scale_factor: float = 1.2, nlevels: int = 8, edge_threshold: int = 31, patch_size: int = 31,
+                 fast_threshold: int = 20):
+        self.ctx, self.width, self.height, self.max_images, self.nlevels = ctx, width, height, max_images, nlevels
+        h = C.c_void_p()
+        check(lib().zs_orb_detector_create(ctx._h, width, height, max_images, nfeatures, float(scale_factor), nlevels,
+                                           edge_threshold, patch_size, fast_threshold, C.byref(h)))
+        self._h = h
+        self.cap = lib().zs_orb_detector_capacity(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().zs_orb_detector_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def level(self, level):
+        w, h, s, n = C.c_int(), C.c_int(), C.c_float(), C.c_int()
+        check(lib().zs_orb_detector_level(self._h, level, C.byref(w), C.byref(h), C.byref(s), C.byref(n)))
+        return w.value, h.value, s.value, n.value
+
+    def download_level(self, image, level, which=0):
+        import numpy as np
+        w, h, _, _ = self.level(level)
+        out = np.empty((h, w), np.uint8)
+        check(lib().zs_orb_detector_download_level(self.ctx._h, self._h, image, level, which, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def detect_and_compute(self, images, masks=None, describe=True):
+        """images / masks: (count, H, W) u8 (numpy or cuda tensors).  -> dict of cuda tensors: xy (count, cap, 2),
+        size, angle, response (count, cap) f32, octave (count, cap) i32, n (count,) i32[, desc (count, cap, 32) u8]"""
+        torch = _torch()
+        ctx = self.ctx
+        img = ctx.to_device(images, torch.uint8).reshape(-1, self.height, self.width).contiguous()
+        count = img.shape[0]
+        m = None
+        if masks is not None:
+            m = ctx.to_device(masks, torch.uint8).reshape(count, self.height, self.width).contiguous()
+        cap = self.cap
+        out = dict(xy=ctx.empty((count, cap, 2), torch.float32), size=ctx.empty((count, cap), torch.float32),
+                   angle=ctx.empty((count, cap), torch.float32), response=ctx.empty((count, cap), torch.float32),
+                   octave=ctx.empty((count, cap), torch.int32), n=ctx.empty((count,), torch.int32))
+        if describe:
+            out["desc"] = ctx.empty((count, cap, 32), torch.uint8)
+        plane = self.width * self.height
+        check(lib().zs_orb_detect_and_compute(ctx._h, self._h, _ptr(img), self.width, plane, _ptr(m), self.width, plane, count,
+                                              _ptr(out["xy"]), _ptr(out["size"]), _ptr(out["angle"]), _ptr(out["response"]),
+                                              _ptr(out["octave"]), _ptr(out["n"]), _ptr(out.get("desc"))))
+        return out
+
+
 def match_hamming_knn2(ctx: Context, q, nq, t, nt, ratio=0.8):
     """q (pairs, cap_q, 32) u8, t (pairs, cap_t, 32) u8 -> idx (pairs, cap_q, 2), dist, pass"""
     torch = _torch()
