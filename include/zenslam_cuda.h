@@ -254,6 +254,13 @@ ZS_API zs_status zs_detect_keypoints_parallel_host(zs_context* ctx, const uint8_
                                                    size_t pitch, int cell_w, int cell_h, int threshold,
                                                    const uint8_t* occupied, float* x, float* y, float* response,
                                                    uint8_t* desc, int* n_out);
+/* keypoint_detector_simple::detect_keypoints with `feature: FAST` (keypoint_detector_simple.cpp:38-63): full-frame
+ * cv::FAST(threshold, NMS) + mask (host, [height][mask_pitch], 0 = rejected, may be NULL), then ORB::compute.  Outputs
+ * sized cap; ZS_ERR_CAPACITY (with *n_out = corners found) when the frame holds more corners than cap. */
+ZS_API zs_status zs_detect_keypoints_simple_host(zs_context* ctx, const uint8_t* img, int width, int height,
+                                                 size_t pitch, const uint8_t* mask, size_t mask_pitch, int threshold,
+                                                 float* x, float* y, float* response, uint8_t* desc, int cap,
+                                                 int* n_out);
 /* matcher::match_keypoints descriptor stage: mode 0 = KNN (ratio), 1 = BRUTE (cross-check);
  * norm 0 = Hamming (32-byte rows), 1 = L2 (dim floats).  Outputs sized nq; *n_out matches. */
 ZS_API zs_status zs_match_host(zs_context* ctx, const void* q, int nq, const void* t, int nt, int dim,

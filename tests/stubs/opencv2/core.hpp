@@ -42,6 +42,8 @@ namespace cv
         double epsilon { };
     };
 
+    struct Scalar { double v[4] { }; Scalar() = default; Scalar(double v0) { v[0] = v0; } };
+
     struct MatStep { size_t v { }; operator size_t() const { return v; } };
 
     class Mat
@@ -49,6 +51,7 @@ namespace cv
     public:
         Mat() = default;
         Mat(int rows_, int cols_, int type_) : rows(rows_), cols(cols_), _type(type_) { }
+        Mat(Size size_, int type_, const Scalar&) : rows(size_.height), cols(size_.width), _type(type_) { }
         int     rows { }, cols { };
         uchar*  data { };
         MatStep step { };

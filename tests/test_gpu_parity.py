@@ -553,3 +553,28 @@ def test_simple_detector_feature_orb_mirror(ctx):
     assert np.array_equal(np.array([k.angle for k in second], np.float32), o2["angle"])
     assert np.array_equal(np.array([k.response for k in second], np.float32), o2["response"])
     assert second[0].index == first[-1].index + 1                      # sequential global indices
+
+
+def test_simple_detector_host_entry(ctx):
+    """zs_detect_keypoints_simple_host (what the C++ adapter binds for algorithm SIMPLE + feature FAST): full-frame FAST +
+    mask + ORB::compute in raster order, and ZS_ERR_CAPACITY instead of a silent truncation"""
+    import ctypes as C
+    from zenslam_b200._lib import ZenslamCudaError, check, lib
+    w, h, thr = 320, 240, 10
+    img = syn.stereo_pair(w, h, 8300)[0]
+    mask = np.full((h, w), 255, np.uint8); mask[40:90, 100:220] = 0
+    cap = ((w + 1) // 2) * ((h + 1) // 2)
+    x = np.empty(cap, np.float32); y = np.empty(cap, np.float32); r = np.empty(cap, np.float32)
+    d = np.empty((cap, 32), np.uint8); n = C.c_int(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(lib().zs_detect_keypoints_simple_host(ctx._h, p(img), w, h, w, p(mask), w, thr, p(x), p(y), p(r), p(d), cap, C.byref(n)))
+    fx, fy, fs = oracle.fast_detect(img, thr)
+    keep = mask[fy, fx] != 0
+    fx, fy, fs = fx[keep], fy[keep], fs[keep]
+    kept, desc = oracle.orb_compute(img, fx, fy)
+    assert n.value == len(kept) > 200
+    assert np.array_equal(x[:n.value], fx[kept].astype(np.float32)) and np.array_equal(y[:n.value], fy[kept].astype(np.float32))
+    assert np.array_equal(r[:n.value], fs[kept].astype(np.float32)) and np.array_equal(d[:n.value], desc)
+    with pytest.raises(ZenslamCudaError, match="capacity"):
+        check(lib().zs_detect_keypoints_simple_host(ctx._h, p(img), w, h, w, None, w, thr, p(x), p(y), p(r), p(d), 50, C.byref(n)))
+    assert n.value > 50

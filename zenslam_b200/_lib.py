@@ -100,6 +100,7 @@ SIGNATURES = {
     "zs_calc_optical_flow_pyr_lk_host": (I, [P, P, P, I, I, Z, P, P, I, P, P, C.POINTER(LkParams)]),
     "zs_detect_keypoints_grid_host": (I, [P, P, I, I, Z, I, I, I, P, P, P, P, P, C.POINTER(I)]),
     "zs_detect_keypoints_parallel_host": (I, [P, P, I, I, Z, I, I, I, P, P, P, P, P, C.POINTER(I)]),
+    "zs_detect_keypoints_simple_host": (I, [P, P, I, I, Z, P, Z, I, P, P, P, P, I, C.POINTER(I)]),
     "zs_match_host": (I, [P, P, I, P, I, I, I, I, D, P, P, P, C.POINTER(I)]),
     "zs_knn_match_host": (I, [P, P, I, P, I, I, I, I, I, P, P]),
     "zs_assign_landmarks_host": (I, [P, P, I, P, I, D, P, P]),

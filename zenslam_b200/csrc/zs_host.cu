@@ -127,6 +127,64 @@ extern "C" zs_status zs_detect_keypoints_parallel_host(zs_context* ctx, const ui
     return detect_grid_host(ctx, img, width, height, pitch, cell_w, cell_h, threshold, occupied, x, y, response, desc, n_out, 1);
 }
 
+// keypoint_detector_simple::detect_keypoints with `feature: FAST` (keypoint_detector_simple.cpp:38-63): full-frame
+// cv::FAST + mask, ORB::compute; no cap on the count in the reference, so the caller sizes the outputs (cap)
+extern "C" zs_status zs_detect_keypoints_simple_host(zs_context* ctx, const uint8_t* img, int width, int height, size_t pitch,
+                                                     const uint8_t* mask, size_t mask_pitch, int threshold, float* x, float* y,
+                                                     float* response, uint8_t* desc, int cap, int* n_out)
+{
+    ZS_REQUIRE(ctx && img && x && y && response && desc && n_out, "null argument");
+    ZS_REQUIRE(width > 0 && height > 0 && cap > 0, "bad sizes");
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    *n_out = 0;
+    zs_pyramid* p;
+    zs_status st = host_pyramid(ctx, 1, width, height, 1, 16, 16, 0, &p);
+    if (st != ZS_OK) return st;
+    if ((st = zs_pyramid_upload(ctx, p, img, pitch, pitch * height, 0, 1, 1)) != ZS_OK) return st;
+    if ((st = zs_pyramid_build(ctx, p, 0, 1)) != ZS_OK) return st;
+    const size_t plane = al256((size_t)width * height);
+    const size_t o_mask = 0, o_xy0 = plane, o_r0 = o_xy0 + al256(sizeof(float) * 2 * cap), o_n0 = o_r0 + al256(sizeof(float) * cap),
+                 o_xy = o_n0 + 256, o_r = o_xy + al256(sizeof(float) * 2 * cap), o_n = o_r + al256(sizeof(float) * cap),
+                 o_desc = o_n + 256, total = o_desc + al256((size_t)cap * 32);
+    uint8_t* base;
+    ZS_CUDA(cudaMallocAsync((void**)&base, total, ctx->stream));
+    if (mask)
+        ZS_CUDA(cudaMemcpy2DAsync(base + o_mask, width, mask, mask_pitch, width, height, cudaMemcpyHostToDevice, ctx->stream));
+    st = zs_fast_detect(ctx, p, 0, 1, threshold, mask ? base + o_mask : nullptr, (float*)(base + o_xy0), (float*)(base + o_r0),
+                        (int*)(base + o_n0), cap);
+    int found = 0;
+    if (st == ZS_OK) {
+        ZS_CUDA(cudaMemcpyAsync(&found, base + o_n0, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (found > cap) {
+            cudaFreeAsync(base, ctx->stream);
+            *n_out = found;
+            zs_set_error("full-frame FAST found %d corners, capacity is %d", found, cap);
+            return ZS_ERR_CAPACITY;
+        }
+        st = zs_orb_compute(ctx, p, 0, 1, (const float*)(base + o_xy0), (const float*)(base + o_r0), nullptr,
+                            (const int*)(base + o_n0), cap, (float*)(base + o_xy), (float*)(base + o_r), nullptr,
+                            (int*)(base + o_n), base + o_desc);
+    }
+    if (st != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+    int n = 0;
+    ZS_CUDA(cudaMemcpyAsync(&n, base + o_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n > 0) {
+        void* pin;
+        if ((st = zs_pinned(ctx, sizeof(float) * 2 * n, &pin)) != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+        ZS_CUDA(cudaMemcpyAsync(pin, base + o_xy, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        ZS_CUDA(cudaMemcpyAsync(response, base + o_r, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        ZS_CUDA(cudaMemcpyAsync(desc, base + o_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+        const float* xy = (const float*)pin;
+        for (int i = 0; i < n; ++i) { x[i] = xy[2 * i]; y[i] = xy[2 * i + 1]; }
+    }
+    ZS_CUDA(cudaFreeAsync(base, ctx->stream));
+    *n_out = n;
+    return ZS_OK;
+}
+
 extern "C" zs_status zs_match_host(zs_context* ctx, const void* q, int nq, const void* t, int nt, int dim, int norm, int mode,
                                    double ratio, int* query_idx, int* train_idx, float* distance, int* n_out)
 {
