@@ -167,7 +167,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -338,11 +338,14 @@ def run_ours(args, rank, world, local_rank):
                          "note": "KLT is instruction-issue bound (ncu: 85 % issue-active, DRAM 1.3 % of peak), not HBM bound "
                                  "(SURVEY 8d); the compulsory-bytes figure is reported as the contract asks, see DESIGN.md"},
         }
+        issue = klt_issue(B, stage_ms["klt"], clocks)
+        if issue:
+            line["roofline"]["issue"] = issue
         if raw_line:
             line["e2e_raw_bgr"] = raw_line
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line), flush=True)
+        emit(line)
     fe.close()
     if world > 1:
         dist.destroy_process_group()
@@ -354,6 +357,24 @@ def klt_traffic(batch):
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "r1_klt_traffic.json")))
         return (t["dram_bytes_read"] + t["dram_bytes_write"]) * batch / t["batch_stereo_frames"]
+    except Exception:
+        return None
+
+
+def klt_issue(batch, klt_ms, clocks):
+    """The roofline that actually bounds the KLT kernel: warp instructions issued per second against the chip's issue rate
+    (SMs x 4 schedulers x SM clock).  The instruction count of one launch comes from the committed ncu capture of this very
+    workload (smsp__inst_executed.sum at batch 128, linear in the batch); the time is this run's."""
+    try:
+        import torch
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_klt_traffic.json")))
+        inst = t["warp_instructions"] * batch / t["batch_stereo_frames"]
+        sms = torch.cuda.get_device_properties(0).multi_processor_count
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        peak = sms * 4 * mhz * 1e6
+        ach = inst / (klt_ms * 1e-3)
+        return {"bound": "issue", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s", "frac": ach / peak,
+                "warp_instructions_per_launch": inst}
     except Exception:
         return None
 
@@ -383,7 +404,31 @@ def cpu_baseline():
                       "oracle/cv2_ref.py, 1 OpenCV thread per process)" % (cores, fpw, cv2.__version__)}
 
 
+_JSON_FD = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout when
+    NCCL_DEBUG is set in the environment), so everything except that line is sent to stderr: fd 1 is pointed at fd 2 for the
+    whole run and the line goes to a duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
