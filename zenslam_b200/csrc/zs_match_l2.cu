@@ -43,6 +43,7 @@ __device__ __forceinline__ void l2_mbar_wait(uint32_t bar, uint32_t parity)
 }
 // polling with back-off for the single-lane producer / MMA roles: they share their scheduler with an epilogue warp, and a
 // tight try_wait loop steals its issue slots (ncu: ~20 % of the kernel's samples sat in those loops)
+template <int NS = 64>
 __device__ __forceinline__ void l2_mbar_wait_backoff(uint32_t bar, uint32_t parity)
 {
     uint32_t done;
@@ -50,7 +51,7 @@ __device__ __forceinline__ void l2_mbar_wait_backoff(uint32_t bar, uint32_t pari
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) break;
-        __nanosleep(64);
+        __nanosleep(NS);
     }
 }
 __device__ __forceinline__ void l2_tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar)
@@ -278,6 +279,15 @@ __device__ __forceinline__ void l2_mbar_arrive(uint32_t bar)
 }
 
 #define L2P_BSTAGES 4
+// back-off of the two single-lane roles while they wait (ns): both have slack -- the operand ring is 4 tiles deep and the
+// MMA of tile i+2 only has to land before the epilogue finishes tile i+1 -- and every poll they issue competes with the
+// epilogue warps of lane quarters 0 and 1 for the same schedulers and the same ALU pipe
+#ifndef L2P_SLEEP_TMA
+#define L2P_SLEEP_TMA 512
+#endif
+#ifndef L2P_SLEEP_MMA
+#define L2P_SLEEP_MMA 256
+#endif
 __device__ __forceinline__ int l2_min3(int a, int b, int c)
 {
     int d;
@@ -332,7 +342,7 @@ __global__ void __launch_bounds__(64 + 128 * CG, 2) k_l2_tc_persist(const __grid
             l2_tma_load_2d(l2_smem_u32(sA), &map_q, 0, pair * a.cap_q + q0, BAR(0));
             for (int i = 0; i < ntile; ++i) {
                 const int sb = i % NB, pb = (i / NB) & 1;
-                l2_mbar_wait_backoff(BAR(1 + NB + sb), pb ^ 1);   // stage free (passes at once the first time round)
+                l2_mbar_wait_backoff<L2P_SLEEP_TMA>(BAR(1 + NB + sb), pb ^ 1);   // stage free (passes at once the first time round)
                 l2_mbar_expect_tx(BAR(1 + sb), L2TC_N * L2TC_K);
                 l2_tma_load_2d(l2_smem_u32(sB0 + sb * (L2TC_N * L2TC_K)), &map_t, 0, pair * a.cap_t + (tile_begin + i) * L2TC_N, BAR(1 + sb));
             }
@@ -345,8 +355,8 @@ __global__ void __launch_bounds__(64 + 128 * CG, 2) k_l2_tc_persist(const __grid
             for (int i = 0; i < ntile; ++i) {
                 const int st = i & 1, ph = (i >> 1) & 1;          // accumulator ring (2 deep)
                 const int sb = i % NB, pb = (i / NB) & 1;         // operand ring (NB deep: covers the TMA round trip)
-                l2_mbar_wait_backoff(BAR(1 + sb), pb);            // train tile landed
-                l2_mbar_wait_backoff(BAR(3 + 2 * NB + st), ph ^ 1);   // accumulator drained
+                l2_mbar_wait_backoff<L2P_SLEEP_MMA>(BAR(1 + sb), pb);            // train tile landed
+                l2_mbar_wait_backoff<L2P_SLEEP_MMA>(BAR(3 + 2 * NB + st), ph ^ 1);   // accumulator drained
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t db = l2_smem_desc(l2_smem_u32(sB0 + sb * (L2TC_N * L2TC_K)));
                 const uint32_t d = tmem + (uint32_t)(st * L2TC_N);
@@ -542,6 +552,7 @@ zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, c
     if (!getenv("ZS_L2_ONE_TILE")) {
         // persistent kernel: enough CTAs for two waves of 2 CTAs per SM, otherwise as many train tiles per CTA as possible
         int splits = (int)((4LL * ctx->sm_count + (long long)q_tiles * pairs - 1) / ((long long)q_tiles * pairs));
+        if (const char* es = getenv("ZS_L2_SPLITS")) splits = atoi(es);
         splits = splits < 1 ? 1 : splits > t_tiles ? t_tiles : splits;
         l2p_args b;
         b.nq = nq; b.nt = nt; b.cap_q = cap_q; b.cap_t = cap_t;
