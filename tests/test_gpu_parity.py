@@ -578,3 +578,29 @@ def test_simple_detector_host_entry(ctx):
     with pytest.raises(ZenslamCudaError, match="capacity"):
         check(lib().zs_detect_keypoints_simple_host(ctx._h, p(img), w, h, w, None, w, thr, p(x), p(y), p(r), p(d), 50, C.byref(n)))
     assert n.value > 50
+
+
+def test_orb_multiscale_detector_large_frame_and_degenerate_options(ctx):
+    """BASELINE config 5 frame size (3840 x 2160): hundreds of thousands of FAST corners per level funnel through the
+    histogram / rank-count selection; plus the degenerate settings OpenCV accepts (nfeatures 0, one level)"""
+    from zenslam_b200._lib import ZenslamCudaError
+    from zenslam_b200.runtime import OrbDetector
+    w, h = 3840, 2160
+    img = syn.stereo_pair(w, h, 8400)[0]
+    det = OrbDetector(ctx, w, h, 1, fast_threshold=10)
+    got = _orb_gpu(det, img[None])[0]
+    o = oracle.orb_detect(img, None, fast_threshold=10)
+    assert len(o["x"]) >= 500
+    for key in ORB_KEYS:
+        assert np.array_equal(got[key], o[key]), key
+    det.close()
+    small = img[:300, :400].copy()
+    for kw in (dict(nfeatures=0), dict(nlevels=1, nfeatures=50), dict(nlevels=3, nfeatures=7, scale_factor=1.5)):
+        det = OrbDetector(ctx, 400, 300, 1, fast_threshold=10, **kw)
+        got = _orb_gpu(det, small[None])[0]
+        o = oracle.orb_detect(small, None, fast_threshold=10, **kw)
+        for key in ORB_KEYS:
+            assert np.array_equal(got[key], o[key]), (kw, key)
+        det.close()
+    with pytest.raises(ZenslamCudaError):
+        OrbDetector(ctx, 20, 20, 1, nlevels=16, scale_factor=2.0)          # top levels would be empty
