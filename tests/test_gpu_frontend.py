@@ -125,6 +125,35 @@ def test_pyr_lk_mirror_and_fb(ctx):
     assert e1.shape == (0, 2)
 
 
+def test_track_keylines_mirror(ctx):
+    """utils::track_keylines (tracking_utils.cpp:14-143): both endpoints through the pyr_lk seam, forward + backward,
+    all four statuses and both FB errors gate the keyline; survivors get new endpoints, midpoint, length, angle"""
+    from zenslam_b200 import tracking_options
+    from zenslam_b200.tracking import create_cuda_pyr_lk, track_keylines
+    from zenslam_b200.types import keyline
+    lk = create_cuda_pyr_lk(ctx)
+    seq, _ = syn.stereo_sequence(752, 480, 2, 1010, subpixel=True)
+    A, B = seq[0, 0], seq[1, 0]
+    rng = np.random.default_rng(4)
+    s = np.stack([rng.uniform(-10, 760, 300), rng.uniform(-10, 490, 300)], 1).astype(np.float32)
+    e = (s + rng.uniform(-60, 60, (300, 2))).astype(np.float32)
+    lines = {i: keyline(startPointX=float(s[i, 0]), startPointY=float(s[i, 1]), endPointX=float(e[i, 0]),
+                        endPointY=float(e[i, 1]), index=i) for i in range(300)}
+    got = track_keylines(lk, A, B, lines, tracking_options())
+    PA, PB = oracle.Pyramid(A, (31, 31), 3), oracle.Pyramid(B, (31, 31), 3)
+    s1, ss, _ = oracle.lk_track(PA, PB, s, None); e1, se, _ = oracle.lk_track(PA, PB, e, None)
+    sb, ssb, _ = oracle.lk_track(PB, PA, s1, None); eb, seb, _ = oracle.lk_track(PB, PA, e1, None)
+    keep = oracle.fb_check(s, sb, ss, ssb, 1.0) & oracle.fb_check(e, eb, se, seb, 1.0)
+    assert 50 < keep.sum() < 300
+    assert [k.index for k in got] == list(np.nonzero(keep)[0])
+    assert np.array_equal(np.array([(k.startPointX, k.startPointY) for k in got], np.float32), s1[keep])
+    assert np.array_equal(np.array([(k.endPointX, k.endPointY) for k in got], np.float32), e1[keep])
+    k0 = got[0]
+    assert abs(k0.lineLength - np.hypot(k0.endPointX - k0.startPointX, k0.endPointY - k0.startPointY)) < 1e-3
+    assert abs(k0.pt[0] - 0.5 * (k0.startPointX + k0.endPointX)) < 1e-4
+    assert track_keylines(lk, A, B, {}, tracking_options()) == []
+
+
 @pytest.mark.parametrize("w,h,B,cell", [(752, 480, 3, (16, 16)), (640, 400, 2, (32, 32))])
 def test_frontend_batches_vs_oracle(ctx, w, h, B, cell):
     from zenslam_b200 import detection_options, slam_options, tracking_options

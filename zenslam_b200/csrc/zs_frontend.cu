@@ -30,6 +30,9 @@ struct zs_frontend {
     float* t_pts; uint8_t* t_status; float* t_err; uint8_t* t_keep;   // [4B][cap]
     int* t_n;                                            // [4B] points tracked per job
     bool have_carry; bool share;
+    // CUDA graph of one zs_frontend_run (the launch sequence is static once a previous frame is carried): captured on the
+    // second run, replayed afterwards -- at small batches the ~25 launches per run are launch-bound
+    bool graph_ok; cudaGraphExec_t gexec; void* g_scratch; uint64_t g_launches;
     // optional per-stage device timing: a ring of event sets, one set per zs_frontend_run
     int timing; int t_runs;
     cudaEvent_t ev[ZS_FE_TIMING_RING][ZS_FE_STAGES + 1];
@@ -126,6 +129,7 @@ extern "C" zs_status zs_frontend_create(zs_context* ctx, const zs_frontend_optio
     free(h);
     if (e != cudaSuccess) { zs_frontend_destroy(fe); return zs_cuda_fail(e, "frontend job tables", __FILE__, __LINE__); }
     fe->share = share;
+    fe->graph_ok = !getenv("ZS_FE_NO_GRAPH");
     *out = fe;
     return ZS_OK;
 }
@@ -135,6 +139,7 @@ extern "C" void zs_frontend_destroy(zs_frontend* fe)
     if (!fe) return;
     cudaSetDevice(fe->ctx->device);
     cudaStreamSynchronize(fe->ctx->stream);
+    if (fe->gexec) cudaGraphExecDestroy(fe->gexec);
     if (fe->pyr) zs_pyramid_destroy(fe->pyr);
     if (fe->dev) cudaFree(fe->dev);
     if (fe->pin) cudaFreeHost(fe->pin);
@@ -181,11 +186,52 @@ extern "C" zs_status zs_frontend_upload(zs_frontend* fe, const uint8_t* left, co
     return zs_pyramid_upload(fe->ctx, fe->pyr, right, pitch, stride, fe->B + 2, fe->B, src_is_host);
 }
 
+static zs_status frontend_run_body(zs_frontend* fe);
+
 extern "C" zs_status zs_frontend_run(zs_frontend* fe)
 {
     ZS_REQUIRE(fe, "null argument");
     zs_context* ctx = fe->ctx;
     ZS_CUDA(cudaSetDevice(ctx->device));
+    // eager: first run of a sequence (no carried frame yet; it also sizes the context scratch), per-stage timing on,
+    // or capture found unusable (e.g. the legacy default stream)
+    if (!fe->graph_ok || fe->timing || !fe->have_carry) return frontend_run_body(fe);
+    if (fe->gexec && fe->g_scratch != ctx->scratch) {           // another call re-grew the scratch the kernels point into
+        cudaGraphExecDestroy(fe->gexec);
+        fe->gexec = nullptr;
+    }
+    if (!fe->gexec) {
+        void* scratch_before = ctx->scratch;
+        const uint64_t l0 = ctx->launches;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            fe->graph_ok = false;
+            return frontend_run_body(fe);
+        }
+        const zs_status st = frontend_run_body(fe);
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        const bool good = st == ZS_OK && e == cudaSuccess && g && ctx->scratch == scratch_before &&
+                          cudaGraphInstantiate(&fe->gexec, g, 0) == cudaSuccess;
+        if (g) cudaGraphDestroy(g);
+        if (!good) {
+            cudaGetLastError();
+            fe->gexec = nullptr; fe->graph_ok = false;
+            ctx->launches = l0;
+            return st != ZS_OK ? st : frontend_run_body(fe);   // nothing ran during the capture
+        }
+        fe->g_launches = ctx->launches - l0;                    // kernels per replay (counted at launch below)
+        ctx->launches = l0;
+        fe->g_scratch = ctx->scratch;
+    }
+    ZS_CUDA(cudaGraphLaunch(fe->gexec, ctx->stream));
+    ctx->launches += fe->g_launches;
+    return ZS_OK;
+}
+
+static zs_status frontend_run_body(zs_frontend* fe)
+{
+    zs_context* ctx = fe->ctx;
     const int B = fe->B, cap = fe->cap;
     const zs_frontend_options& o = fe->opt;
     zs_status st;

@@ -89,3 +89,40 @@ def track_keypoints(backend: pyr_lk, pyramid_0, pyramid_1, keypoints_0: list, tr
         if st[i] and sb[i] and nrm < tracking.klt_threshold:
             out.append(dataclasses.replace(kp, pt=(float(p1[i, 0]), float(p1[i, 1]))))
     return out
+
+
+def track_keylines(backend: pyr_lk, pyramid_0, pyramid_1, keylines_0, tracking: tracking_options) -> list:
+    """utils::track_keylines (zenslam_core/source/tracking/tracking_utils.cpp:14-143): both endpoints of every keyline
+    go through the same pyr_lk seam -- forward 0 -> 1, backward 1 -> 0 from the forward results, (99, 0.001),
+    OPTFLOW_LK_GET_MIN_EIGENVALS; a keyline survives iff all four statuses are set and both forward-backward errors
+    (cv::norm narrowed to float) are below klt_threshold; its endpoints, midpoint, length and angle are rewritten."""
+    values = list(keylines_0.values()) if hasattr(keylines_0, "values") else list(keylines_0)
+    if not values:
+        return []
+    f32 = np.float32
+    s0 = np.array([(k.startPointX, k.startPointY) for k in values], f32)
+    e0 = np.array([(k.endPointX, k.endPointY) for k in values], f32)
+    crit = (99, 0.001)
+    args = (tracking.klt_window_size, tracking.klt_max_level, crit, LK_GET_MIN_EIGENVALS)
+    s1, st_sf, _ = backend.calc_optical_flow_pyr_lk(pyramid_0, pyramid_1, s0, None, *args)
+    e1, st_ef, _ = backend.calc_optical_flow_pyr_lk(pyramid_0, pyramid_1, e0, None, *args)
+    sb, st_sb, _ = backend.calc_optical_flow_pyr_lk(pyramid_1, pyramid_0, s1, None, *args)
+    eb, st_eb, _ = backend.calc_optical_flow_pyr_lk(pyramid_1, pyramid_0, e1, None, *args)
+
+    def fb_error(back, orig):
+        dx, dy = f32(back[0] - orig[0]), f32(back[1] - orig[1])
+        return f32(np.sqrt(np.float64(dx) * np.float64(dx) + np.float64(dy) * np.float64(dy)))
+
+    out = []
+    for i, kl in enumerate(values):
+        if not (st_sf[i] and st_ef[i] and st_sb[i] and st_eb[i]):
+            continue
+        if not (float(fb_error(sb[i], s0[i])) < tracking.klt_threshold and float(fb_error(eb[i], e0[i])) < tracking.klt_threshold):
+            continue
+        dx, dy = f32(e1[i, 0] - s1[i, 0]), f32(e1[i, 1] - s1[i, 1])
+        out.append(dataclasses.replace(
+            kl, startPointX=float(s1[i, 0]), startPointY=float(s1[i, 1]), endPointX=float(e1[i, 0]), endPointY=float(e1[i, 1]),
+            pt=(float(f32(f32(s1[i, 0] + e1[i, 0]) * f32(0.5))), float(f32(f32(s1[i, 1] + e1[i, 1]) * f32(0.5)))),
+            lineLength=float(np.sqrt(f32(f32(dx * dx) + f32(dy * dy)))),
+            angle=float(f32(f32(np.arctan2(dy, dx)) * f32(180.0)) / f32(np.pi))))
+    return out
