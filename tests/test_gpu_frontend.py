@@ -125,6 +125,71 @@ def test_pyr_lk_mirror_and_fb(ctx):
     assert e1.shape == (0, 2)
 
 
+def test_keypoint_tracker_track_flow_vs_oracle(ctx):
+    """keypoint_tracker::track (keypoint_tracker.cpp:41-105) over several frames, state carried from frame to frame:
+    temporal tracks, occupancy-aware detection, stereo tracks of the keypoints the other camera lacks, index-keyed maps.
+    The CUDA-backed mirror and the same host glue over the oracle (C restatement of OpenCV) must produce identical maps."""
+    import dataclasses
+    from zenslam_b200 import detection_options, keypoint, slam_options, tracking_options
+    from zenslam_b200.keypoint_tracker import keypoint_tracker, stereo_frame
+    from zenslam_b200.tracking import create_cuda_pyr_lk, pyr_lk
+
+    class oracle_pyr_lk(pyr_lk):
+        def calc_optical_flow_pyr_lk(self, prev_pyramid, next_pyramid, prev_points, next_points, win_size, max_level,
+                                     criteria=(99, 0.001), flags=8, min_eig_threshold=1e-4):
+            P0, P1 = oracle.Pyramid(prev_pyramid, win_size, max_level), oracle.Pyramid(next_pyramid, win_size, max_level)
+            return oracle.lk_track(P0, P1, np.asarray(prev_points, np.float32), next_points, win_size, max_level)
+
+    class oracle_detector:
+        def __init__(self, opt):
+            self.opt = opt
+
+        def detect_keypoints(self, image, existing):
+            cw, ch = self.opt.cell_size
+            h, w = image.shape
+            occ = np.zeros((h // ch, w // cw), np.uint8)
+            for kp in (existing.values() if existing else []):
+                gx, gy = int(kp.pt[0]) // cw, int(kp.pt[1]) // ch
+                if 0 <= gx < occ.shape[1] and 0 <= gy < occ.shape[0]:
+                    occ[gy, gx] = 1
+            x, y, s = oracle.grid_detect(image, (cw, ch), self.opt.fast_threshold, occ)
+            kept, desc = oracle.orb_compute(image, x, y)
+            out = []
+            for i, k in enumerate(kept):
+                out.append(keypoint(pt=(float(x[k]), float(y[k])), response=float(s[k]), index=keypoint.index_next, descriptor=desc[i]))
+                keypoint.index_next += 1
+            return out
+
+    w, h, frames = 376, 240, 4
+    seq, _ = syn.stereo_sequence(w, h, frames, 1020, subpixel=True)
+    opts = slam_options(matcher="KNN", detection=detection_options(), tracking=tracking_options(filter_epipolar=False))
+
+    def run(tracker):
+        keypoint.index_next = 0
+        prev = stereo_frame((seq[0, 0], seq[0, 1]))
+        out = []
+        for t in range(frames):
+            cur = stereo_frame((seq[t, 0], seq[t, 1]))
+            k0, k1 = tracker.track(prev, cur)
+            out.append((k0, k1))
+            prev = dataclasses.replace(cur, keypoints=(k0, k1))
+        return out
+
+    got = run(keypoint_tracker(opts, ctx, create_cuda_pyr_lk(ctx)))
+    ref = run(keypoint_tracker(opts, ctx, oracle_pyr_lk(), detector=oracle_detector(opts.detection)))
+    for t in range(frames):
+        for cam in range(2):
+            g, r = got[t][cam], ref[t][cam]
+            assert sorted(g) == sorted(r), (t, cam)
+            assert all(g[i].pt == r[i].pt and np.array_equal(g[i].descriptor, r[i].descriptor) for i in g), (t, cam)
+    n_last = len(got[-1][0])
+    shared = len(set(got[-1][0]) & set(got[-1][1]))
+    carried = len(set(got[-1][0]) & set(got[0][0]))
+    assert n_last > 200 and shared > 100 and carried > 50, (n_last, shared, carried)     # tracks survive, stereo pairs exist
+    with pytest.raises(NotImplementedError):
+        keypoint_tracker(slam_options(), ctx, create_cuda_pyr_lk(ctx))                  # filter_epipolar on, no RANSAC callable
+
+
 def test_track_keylines_mirror(ctx):
     """utils::track_keylines (tracking_utils.cpp:14-143): both endpoints through the pyr_lk seam, forward + backward,
     all four statuses and both FB errors gate the keyline; survivors get new endpoints, midpoint, length, angle"""

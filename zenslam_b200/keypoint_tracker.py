@@ -1,0 +1,104 @@
+"""keypoint_tracker::track mirror (zenslam_core/source/tracking/keypoint_tracker.cpp:41-105): the per-frame caller of
+the hot path, with the reference's own bookkeeping -- index-keyed keypoint maps, occupancy-aware detection, stereo
+tracking of the keypoints the other camera does not have yet.
+
+Every computation goes through the same seams the C++ adapter binds (keypoint_detector, pyr_lk); this file is host
+glue only.  What the reference does around it and this backend leaves on the CPU is injected, not re-implemented:
+  * landmark projection for the initial flow (keypoint_tracker.cpp:361-373) -> `predicted_points` callable,
+  * assign_landmark_indices (:55,71) -> `assign_landmarks` callable (zenslam_b200.matching.assign_landmark_indices fits),
+  * filter_epipolar's cv::findFundamentalMat RANSAC (:293-341) -> `epipolar_filter` callable; without one the
+    option tracking.filter_epipolar must be off (the RANSAC gate is out of scope).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+from .detection import keypoint_detector_grid, keypoint_detector_parallel, keypoint_detector_simple
+from .options import slam_options
+from .tracking import pyr_lk, track_keypoints
+
+
+class keypoint_map(dict):
+    """zenslam::map<keypoint> : std::map<size_t, keypoint> (types/map.h:24-100): ordered by index, add() keeps an
+    existing entry unless overwrite is set."""
+
+    def add(self, items, overwrite: bool = False):
+        for kp in (items if isinstance(items, (list, tuple)) else [items]):
+            if overwrite or kp.index not in self:
+                self[kp.index] = kp
+
+    def values_sorted(self) -> list:
+        return [self[k] for k in sorted(self)]
+
+    def values_unmatched(self, other) -> list:
+        return [self[k] for k in sorted(self) if k not in other]
+
+    def values_matched(self, other) -> list:
+        return [self[k] for k in sorted(self) if k in other]
+
+
+@dataclass
+class stereo_frame:
+    """the pieces of frame::processed / frame::estimated that track() reads: level-0 images of the two pyramids
+    (the device rebuilds cv::buildOpticalFlowPyramid from them), the undistorted images and the keypoint maps"""
+    undistorted: tuple
+    keypoints: tuple = field(default_factory=lambda: (keypoint_map(), keypoint_map()))
+
+    @property
+    def pyramids(self):
+        return self.undistorted
+
+
+class keypoint_tracker:
+    def __init__(self, options: slam_options, ctx, backend: pyr_lk, detector=None, predicted_points=None,
+                 assign_landmarks=None, epipolar_filter=None):
+        self._options, self._pyr_lk = options, backend
+        det = options.detection
+        if detector is not None:
+            self._detector = detector
+        elif det.algorithm == "SIMPLE":           # keypoint_tracker.cpp:27-38
+            self._detector = keypoint_detector_simple(det, ctx)
+        elif det.algorithm == "GRID":
+            self._detector = keypoint_detector_grid(det, ctx)
+        else:
+            self._detector = keypoint_detector_parallel(det, ctx)
+        self._predicted_points, self._assign, self._epipolar = predicted_points, assign_landmarks, epipolar_filter
+        if options.tracking.filter_epipolar and epipolar_filter is None:
+            raise NotImplementedError("tracking.filter_epipolar needs an epipolar_filter callable: the reference's gate is "
+                                      "cv::findFundamentalMat RANSAC on the CPU (keypoint_tracker.cpp:301-308)")
+
+    def _track(self, img_0, img_1, keypoints: list, camera_index=None) -> list:
+        predicted = None
+        if camera_index is not None and self._predicted_points is not None:
+            predicted = self._predicted_points(keypoints, camera_index)
+        return track_keypoints(self._pyr_lk, img_0, img_1, keypoints, self._options.tracking, predicted)
+
+    def track(self, frame_0: stereo_frame, frame_1: stereo_frame):
+        """-> (keypoints_0, keypoints_1) of frame_1 (keypoint_tracker.cpp:41-105)"""
+        kp0, kp1 = keypoint_map(), keypoint_map()
+        # temporal tracks of both cameras (:47-51); the overload with a pose passes OPTFLOW_USE_INITIAL_FLOW with the
+        # keypoint's own position where no landmark is known, which is what the plain call starts from too
+        kp0.add(self._track(frame_0.pyramids[0], frame_1.pyramids[0], frame_0.keypoints[0].values_sorted(), 0))
+        kp1.add(self._track(frame_0.pyramids[1], frame_1.pyramids[1], frame_0.keypoints[1].values_sorted(), 1))
+        # new keypoints in the cells the tracked ones leave free (:53-57)
+        detected_0 = self._detector.detect_keypoints(frame_1.undistorted[0], kp0)
+        if self._assign is not None:
+            self._assign(detected_0)
+        kp0.add(detected_0)
+        # left keypoints the right camera does not have yet: stereo track L -> R (:59-67)
+        kp1.add(self._track(frame_1.pyramids[0], frame_1.pyramids[1], kp0.values_unmatched(kp1)))
+        detected_1 = self._detector.detect_keypoints(frame_1.undistorted[1], kp1)
+        if self._assign is not None:
+            self._assign(detected_1)
+        kp1.add(detected_1)
+        # and the other way round (:73-83)
+        kp0.add(self._track(frame_1.pyramids[1], frame_1.pyramids[0], kp1.values_unmatched(kp0)))
+        if self._options.tracking.filter_epipolar:
+            m0, m1 = kp0.values_matched(kp1), kp1.values_matched(kp0)
+            keep = self._epipolar(m0, m1)
+            f0, f1 = keypoint_map(), keypoint_map()
+            for a, b, k in zip(m0, m1, keep):
+                if k:
+                    f0.add(a); f1.add(b)
+            return f0, f1
+        return kp0, kp1
