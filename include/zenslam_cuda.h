@@ -240,6 +240,16 @@ ZS_API zs_status zs_calc_optical_flow_pyr_lk_host(zs_context* ctx,
                                                   int width, int height, size_t pitch,
                                                   const float* prev_pts, float* next_pts, int n,
                                                   uint8_t* status, float* err, const zs_lk_params* params);
+/* keypoint_tracker::track_keypoints as ONE call (keypoint_tracker.cpp:129-197, :343-434): forward LK from points_0
+ * (initial flow predicted_1, or NULL for none), backward LK from the forward results, keep[i] = both statuses set and
+ * ||p0_back - p0|| < klt_threshold.  Same results as two zs_calc_optical_flow_pyr_lk_host calls + the reference's gate,
+ * with one upload / pyramid build per frame instead of two and both passes in one kernel.  points_1 receives the
+ * forward results for every point; status / err (forward pass) may be NULL. */
+ZS_API zs_status zs_track_keypoints_host(zs_context* ctx, const uint8_t* img_0, const uint8_t* img_1,
+                                         int width, int height, size_t pitch, const float* points_0,
+                                         const float* predicted_1, int n, const zs_lk_params* params,
+                                         double klt_threshold, float* points_1, uint8_t* status, float* err,
+                                         uint8_t* keep);
 /* keypoint_detector_grid::detect_keypoints: occupied [grid_h*grid_w] or NULL; outputs sized
  * grid_w*grid_h (x, y, response) and *32 (desc); *n_out = keypoints that survive ORB's border filter. */
 ZS_API zs_status zs_detect_keypoints_grid_host(zs_context* ctx, const uint8_t* img, int width, int height,

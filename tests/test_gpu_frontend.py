@@ -119,6 +119,14 @@ def test_pyr_lk_mirror_and_fb(ctx):
     keep = oracle.fb_check(pts, ob, os_, osb, 1.0)
     assert [k.index for k in tracked] == list(np.nonzero(keep)[0])
     assert np.array_equal(np.array([k.pt for k in tracked], np.float32), o1[keep])
+    # the fused host entry (forward + backward + gate in one device call) gives the same survivors and positions,
+    # with and without an initial flow
+    fused = track_keypoints(lk, A, B, kps, tracking_options(), fused=True)
+    assert [k.index for k in fused] == [k.index for k in tracked] and [k.pt for k in fused] == [k.pt for k in tracked]
+    pred = (pts + rng.uniform(-4, 4, pts.shape)).astype(np.float32)
+    t2 = track_keypoints(lk, A, B, kps, tracking_options(), predicted_points=pred)
+    f2 = track_keypoints(lk, A, B, kps, tracking_options(), predicted_points=pred, fused=True)
+    assert len(t2) > 100 and [k.index for k in f2] == [k.index for k in t2] and [k.pt for k in f2] == [k.pt for k in t2]
     # empty input (keypoint_tracker.cpp:122)
     assert track_keypoints(lk, A, B, [], tracking_options()) == []
     e1, es, ee = lk.calc_optical_flow_pyr_lk(A, B, np.zeros((0, 2), np.float32), None, (31, 31), 3)

@@ -61,6 +61,52 @@ extern "C" zs_status zs_calc_optical_flow_pyr_lk_host(zs_context* ctx, const uin
     return ZS_OK;
 }
 
+// keypoint_tracker::track_keypoints in one call (keypoint_tracker.cpp:129-197 stereo, :343-434 temporal): forward LK
+// (initial flow optional), backward LK from the forward results, forward-backward gate.  The reference makes two pyr_lk
+// calls for this; through the pyr_lk seam each of them uploads both frames and rebuilds both pyramids, here that happens
+// once and both passes + the gate run in one kernel (zs_klt_track_fb).
+extern "C" zs_status zs_track_keypoints_host(zs_context* ctx, const uint8_t* img_0, const uint8_t* img_1, int width, int height,
+                                             size_t pitch, const float* points_0, const float* predicted_1, int n,
+                                             const zs_lk_params* prm, double klt_threshold, float* points_1, uint8_t* status,
+                                             float* err, uint8_t* keep)
+{
+    ZS_REQUIRE(ctx && img_0 && img_1 && prm, "null argument");
+    ZS_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return ZS_OK;
+    ZS_REQUIRE(points_0 && points_1 && keep, "null argument");
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    zs_pyramid* p;
+    zs_status st = host_pyramid(ctx, 0, width, height, 2, prm->win_w, prm->win_h, prm->max_level, &p);
+    if (st != ZS_OK) return st;
+    if ((st = zs_pyramid_upload(ctx, p, img_0, pitch, pitch * height, 0, 1, 1)) != ZS_OK) return st;
+    if ((st = zs_pyramid_upload(ctx, p, img_1, pitch, pitch * height, 1, 1, 1)) != ZS_OK) return st;
+    if ((st = zs_pyramid_build(ctx, p, 0, 2)) != ZS_OK) return st;
+    const size_t o_prev = 256, o_next = o_prev + al256(sizeof(float) * 2 * n), o_err = o_next + al256(sizeof(float) * 2 * n),
+                 o_st = o_err + al256(sizeof(float) * n), o_keep = o_st + al256(n), total = o_keep + al256(n);
+    void* s;
+    if ((st = zs_scratch(ctx, total, &s)) != ZS_OK) return st;
+    uint8_t* base = (uint8_t*)s;
+    const int hdr[3] = { 0, 1, n };
+    ZS_CUDA(cudaMemcpyAsync(base, hdr, sizeof(hdr), cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(base + o_prev, points_0, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    zs_lk_params q = *prm;
+    if (predicted_1) {
+        q.flags |= ZS_LK_USE_INITIAL_FLOW;
+        ZS_CUDA(cudaMemcpyAsync(base + o_next, predicted_1, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        q.flags &= ~ZS_LK_USE_INITIAL_FLOW;
+    }
+    st = zs_klt_track_fb(ctx, p, (const int*)base, (const int*)base + 1, (const float*)(base + o_prev), (float*)(base + o_next),
+                         (const int*)base + 2, 1, n, &q, klt_threshold, base + o_st, (float*)(base + o_err), base + o_keep);
+    if (st != ZS_OK) return st;
+    ZS_CUDA(cudaMemcpyAsync(points_1, base + o_next, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) ZS_CUDA(cudaMemcpyAsync(status, base + o_st, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (err) ZS_CUDA(cudaMemcpyAsync(err, base + o_err, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(keep, base + o_keep, n, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZS_OK;
+}
+
 static zs_status detect_grid_host(zs_context* ctx, const uint8_t* img, int width, int height, size_t pitch, int cell_w, int cell_h,
                                   int threshold, const uint8_t* occupied, float* x, float* y, float* response, uint8_t* desc,
                                   int* n_out, int subpix)

@@ -57,6 +57,23 @@ class cuda_pyr_lk(pyr_lk):
         return npts, status, err
 
 
+    def track_keypoints_fused(self, pyramid_0, pyramid_1, points_0, predicted_1, win_size, max_level, klt_threshold,
+                              criteria=(99, 0.001), min_eig_threshold=1e-4):
+        """zs_track_keypoints_host: forward + backward LK + FB gate in one device call -> (points_1, status, keep)"""
+        a, b = _level0(pyramid_0), _level0(pyramid_1)
+        h, w = a.shape
+        p0 = np.ascontiguousarray(points_0, np.float32).reshape(-1, 2)
+        n = len(p0)
+        pred = None if predicted_1 is None else np.ascontiguousarray(predicted_1, np.float32).reshape(-1, 2)
+        p1 = np.zeros((n, 2), np.float32); status = np.zeros(n, np.uint8); keep = np.zeros(n, np.uint8)
+        prm = LkParams(win_size[0], win_size[1], int(max_level), int(criteria[0]), float(criteria[1]), LK_GET_MIN_EIGENVALS,
+                       float(min_eig_threshold))
+        p = lambda x: x.ctypes.data_as(C.c_void_p)
+        check(lib().zs_track_keypoints_host(self._ctx._h, p(a), p(b), w, h, w, p(p0), p(pred) if pred is not None else None, n,
+                                            C.byref(prm), float(klt_threshold), p(p1), p(status), None, p(keep)))
+        return p1, status, keep
+
+
 def create_cuda_pyr_lk(ctx: Context | None = None):
     """Factory; None when no sm_100 device is usable (cf. pyr_lk_factory.cpp:43-46)."""
     if not is_available():
@@ -65,13 +82,18 @@ def create_cuda_pyr_lk(ctx: Context | None = None):
 
 
 def track_keypoints(backend: pyr_lk, pyramid_0, pyramid_1, keypoints_0: list, tracking: tracking_options,
-                    predicted_points=None) -> list:
+                    predicted_points=None, fused: bool = False) -> list:
     """keypoint_tracker::track_keypoints: forward LK (initial flow from `predicted_points` when given --
     the temporal overload, keypoint_tracker.cpp:361-391), backward LK, keep i iff both statuses are set and
     ||p0_back - p0|| < klt_threshold; survivors copy the keypoint with pt replaced (keypoint_tracker.cpp:188-196)."""
     if not keypoints_0:
         return []
     p0 = np.array([kp.pt for kp in keypoints_0], np.float32)
+    if fused and isinstance(backend, cuda_pyr_lk):
+        # one device call instead of the two pyr_lk calls + host gate below: same results (tests compare both routes)
+        p1, _, keep = backend.track_keypoints_fused(pyramid_0, pyramid_1, p0, predicted_points, tracking.klt_window_size,
+                                                    tracking.klt_max_level, tracking.klt_threshold)
+        return [dataclasses.replace(kp, pt=(float(p1[i, 0]), float(p1[i, 1]))) for i, kp in enumerate(keypoints_0) if keep[i]]
     crit = (99, 0.001)
     if predicted_points is not None:
         p1, st, _ = backend.calc_optical_flow_pyr_lk(pyramid_0, pyramid_1, p0, predicted_points, tracking.klt_window_size,

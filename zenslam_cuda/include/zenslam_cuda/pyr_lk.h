@@ -26,4 +26,22 @@ namespace zenslam::cuda
         cv::TermCriteria criteria,
         int flags,
         double min_eig_threshold = 1e-4);
+
+    /** keypoint_tracker::track_keypoints' two pyr_lk calls and its forward-backward gate (keypoint_tracker.cpp:129-197,
+     *  :343-434) as one device call: forward LK from `points_0` (with `predicted_1` as initial flow when it is not empty),
+     *  backward LK from the results, keep[i] = both statuses set and ||p0_back - p0|| < klt_threshold.  Identical results;
+     *  each frame is uploaded and its pyramid built once instead of twice.  Optional: the pyr_lk seam alone is enough for a
+     *  drop-in, this is the shortcut a maintainer can take inside track_keypoints. */
+    void track_keypoints_fb(
+        const std::vector<cv::Mat>& pyramid_0,
+        const std::vector<cv::Mat>& pyramid_1,
+        const std::vector<cv::Point2f>& points_0,
+        const std::vector<cv::Point2f>& predicted_1,
+        std::vector<cv::Point2f>& points_1,
+        std::vector<uchar>& keep,
+        cv::Size win_size,
+        int max_level,
+        double klt_threshold,
+        cv::TermCriteria criteria = { cv::TermCriteria::COUNT | cv::TermCriteria::EPS, 99, 0.001 },
+        double min_eig_threshold = 1e-4);
 }
