@@ -240,6 +240,11 @@ ZS_API zs_status zs_calc_optical_flow_pyr_lk_host(zs_context* ctx,
                                                   int width, int height, size_t pitch,
                                                   const float* prev_pts, float* next_pts, int n,
                                                   uint8_t* status, float* err, const zs_lk_params* params);
+/* The two LK host entries keep the device pyramids of the last few frames (keyed by a 64-bit hash of the frame's bytes,
+ * least-recently-used replacement), because the reference's eight LK calls per stereo frame see only four distinct images
+ * and two of those were already seen by the previous frame's calls.  A hit skips the upload and the pyramid build; results
+ * are unaffected.  ZS_LK_NO_CACHE=1 in the environment disables it.  This returns the hit / miss counts (test access). */
+ZS_API zs_status zs_lk_cache_stats(const zs_context* ctx, uint64_t* hits, uint64_t* misses);
 /* keypoint_tracker::track_keypoints as ONE call (keypoint_tracker.cpp:129-197, :343-434): forward LK from points_0
  * (initial flow predicted_1, or NULL for none), backward LK from the forward results, keep[i] = both statuses set and
  * ||p0_back - p0|| < klt_threshold.  Same results as two zs_calc_optical_flow_pyr_lk_host calls + the reference's gate,

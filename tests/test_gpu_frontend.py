@@ -198,6 +198,44 @@ def test_keypoint_tracker_track_flow_vs_oracle(ctx):
         keypoint_tracker(slam_options(), ctx, create_cuda_pyr_lk(ctx))                  # filter_epipolar on, no RANSAC callable
 
 
+def test_lk_host_pyramid_cache(ctx):
+    """the LK host entries keep the pyramids of the frames they saw (content-keyed): repeated frames hit, a frame whose
+    bytes changed in place misses, and results never depend on the cache state"""
+    import ctypes as C
+    from zenslam_b200._lib import lib
+    from zenslam_b200.tracking import create_cuda_pyr_lk
+    lk = create_cuda_pyr_lk(ctx)
+    seq, _ = syn.stereo_sequence(376, 240, 5, 1030, subpixel=True)
+    rng = np.random.default_rng(9)
+    pts = np.stack([rng.uniform(5, 370, 200), rng.uniform(5, 235, 200)], 1).astype(np.float32)
+
+    def stats():
+        h, m = C.c_uint64(), C.c_uint64()
+        lib().zs_lk_cache_stats(ctx._h, C.byref(h), C.byref(m))
+        return h.value, m.value
+
+    def check(a, b):
+        p1, st, err = lk.calc_optical_flow_pyr_lk([a], [b], pts, None, (21, 21), 2, (99, 0.001), 8, 1e-4)
+        o1, os_, oe = oracle.lk_track(oracle.Pyramid(a, (21, 21), 2), oracle.Pyramid(b, (21, 21), 2), pts, None, (21, 21), 2)
+        assert np.array_equal(p1, o1) and np.array_equal(st, os_) and np.array_equal(err, oe)
+
+    frames = [np.ascontiguousarray(seq[t, 0]) for t in range(5)]
+    check(frames[0], frames[1])                       # new window geometry: both miss
+    h0, m0 = stats()
+    check(frames[1], frames[0])                       # both hit
+    check(frames[1], frames[2])                       # one hit, one miss
+    h1, m1 = stats()
+    assert (h1 - h0, m1 - m0) == (3, 1)
+    buf = frames[2]                                   # same buffer, new content: must not be served from the cache
+    buf[:] = frames[4]
+    check(frames[1], buf)
+    h2, m2 = stats()
+    assert (h2 - h1, m2 - m1) == (1, 1)
+    for t in range(5):                                # more distinct frames than slots: eviction keeps results right
+        check(frames[t % 5], frames[(t + 3) % 5])
+    check(frames[0], frames[0])                       # the same frame twice occupies two slots
+
+
 def test_track_keylines_mirror(ctx):
     """utils::track_keylines (tracking_utils.cpp:14-143): both endpoints through the pyr_lk seam, forward + backward,
     all four statuses and both FB errors gate the keyline; survivors get new endpoints, midpoint, length, angle"""

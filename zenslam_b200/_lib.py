@@ -98,6 +98,7 @@ SIGNATURES = {
     "zs_klt_track": (I, [P, P, P, P, P, P, P, I, I, C.POINTER(LkParams), P, P]),
     "zs_klt_track_fb": (I, [P, P, P, P, P, P, P, I, I, C.POINTER(LkParams), D, P, P, P]),
     "zs_calc_optical_flow_pyr_lk_host": (I, [P, P, P, I, I, Z, P, P, I, P, P, C.POINTER(LkParams)]),
+    "zs_lk_cache_stats": (I, [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "zs_track_keypoints_host": (I, [P, P, P, I, I, Z, P, P, I, C.POINTER(LkParams), D, P, P, P, P]),
     "zs_detect_keypoints_grid_host": (I, [P, P, I, I, Z, I, I, I, P, P, P, P, P, C.POINTER(I)]),
     "zs_detect_keypoints_parallel_host": (I, [P, P, I, I, Z, I, I, I, P, P, P, P, P, C.POINTER(I)]),

@@ -10,6 +10,7 @@
 #include "../../include/zenslam_cuda.h"
 
 #define ZS_MAX_LEVELS 8
+#define ZS_LK_CACHE_SLOTS 6
 
 // Device-side view of a zs_pyramid: S slots, `levels` levels.  Level l image plane of slot s starts at
 // img[l] + s*img_slot[l]; interior pixel (x,y) at + (y + pad_y)*pitch[l] + pad_x + x.  The derivative
@@ -44,6 +45,10 @@ struct zs_context {
     zs_pyramid* host_pyr[2];
     // cached multi-scale ORB detector of zs_detect_keypoints_orb_host and the parameters it was built for
     zs_orb_detector* host_orb; int host_orb_key[8]; float host_orb_sf;
+    // which frames the slots of host_pyr[0] hold (zs_host.cu: the reference's eight LK calls per stereo frame see only
+    // four distinct images, two of them already seen by the previous frame's calls)
+    uint64_t lk_hash[ZS_LK_CACHE_SLOTS], lk_stamp[ZS_LK_CACHE_SLOTS], lk_clock;
+    uint64_t lk_hits, lk_misses;
 };
 
 struct zs_pyramid {

@@ -1,6 +1,8 @@
 // zs_host.cu -- host-pointer mirrors of the reference's calls (single image, synchronous): what the C++
 // adapter in zenslam_cuda/ binds for drop-in use.  They stage through the context's device scratch, run the
 // same kernels as the batched path with batch 1, and copy the results back.
+#include <stdlib.h>
+
 #include "zs_common.cuh"
 
 static zs_status host_pyramid(zs_context* ctx, int which, int w, int h, int slots, int win_w, int win_h, int max_level,
@@ -23,6 +25,69 @@ static zs_status host_pyramid(zs_context* ctx, int which, int w, int h, int slot
 
 static inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
+// 64-bit content hash of a frame (four interleaved multiply-xorshift lanes over 8-byte words; ~20 us for 752 x 480).
+// It keys the device-side pyramid cache below: a frame whose bytes were seen before keeps its slot, so its upload and
+// pyramid build are skipped.  The key is the content, not the pointer -- buffers are recycled between frames.
+static uint64_t frame_hash(const uint8_t* img, int w, int h, size_t pitch)
+{
+    const uint64_t K = 0x9E3779B97F4A7C15ull;
+    uint64_t a = K ^ (uint64_t)w, b = K * 3 ^ (uint64_t)h, c = K * 5, d = K * 7;
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* r = img + (size_t)y * pitch;
+        int x = 0;
+        for (; x + 32 <= w; x += 32) {
+            uint64_t v[4];
+            memcpy(v, r + x, 32);
+            a = (a ^ v[0]) * K; a ^= a >> 29;
+            b = (b ^ v[1]) * K; b ^= b >> 29;
+            c = (c ^ v[2]) * K; c ^= c >> 29;
+            d = (d ^ v[3]) * K; d ^= d >> 29;
+        }
+        uint64_t t = 0;
+        for (; x < w; ++x) t = t * 257 + r[x];
+        a = (a ^ t ^ (uint64_t)y) * K; a ^= a >> 29;
+    }
+    uint64_t hsh = a ^ (b * K) ^ ((c * K) >> 7) ^ (d << 3);
+    hsh ^= hsh >> 31; hsh *= K; hsh ^= hsh >> 29;
+    return hsh ? hsh : 1;                      // 0 marks an empty slot
+}
+
+// the LK pyramid of the host mirrors: ZS_LK_CACHE_SLOTS slots, least-recently-used replacement
+static zs_status lk_pyramid(zs_context* ctx, int w, int h, const zs_lk_params* prm, zs_pyramid** out)
+{
+    zs_pyramid* before = ctx->host_pyr[0];
+    zs_status st = host_pyramid(ctx, 0, w, h, ZS_LK_CACHE_SLOTS, prm->win_w, prm->win_h, prm->max_level, out);
+    if (st == ZS_OK && *out != before) {       // new geometry: nothing cached yet
+        memset(ctx->lk_hash, 0, sizeof(ctx->lk_hash));
+        memset(ctx->lk_stamp, 0, sizeof(ctx->lk_stamp));
+    }
+    return st;
+}
+
+static zs_status lk_slot(zs_context* ctx, zs_pyramid* p, const uint8_t* img, int w, int h, size_t pitch, int avoid, int* slot)
+{
+    static const bool no_cache = getenv("ZS_LK_NO_CACHE") != nullptr;
+    const uint64_t hsh = frame_hash(img, w, h, pitch);
+    int lru = -1;
+    for (int s = 0; s < ZS_LK_CACHE_SLOTS; ++s) {
+        if (s == avoid) continue;
+        if (!no_cache && ctx->lk_hash[s] == hsh) {
+            ctx->lk_stamp[s] = ++ctx->lk_clock; ctx->lk_hits++;
+            *slot = s;
+            return ZS_OK;
+        }
+        if (lru < 0 || ctx->lk_stamp[s] < ctx->lk_stamp[lru]) lru = s;
+    }
+    ctx->lk_misses++;
+    ctx->lk_hash[lru] = 0;                      // not valid until both calls below have been queued
+    zs_status st = zs_pyramid_upload(ctx, p, img, pitch, pitch * h, lru, 1, 1);
+    if (st != ZS_OK) return st;
+    if ((st = zs_pyramid_build(ctx, p, lru, 1)) != ZS_OK) return st;
+    ctx->lk_hash[lru] = hsh; ctx->lk_stamp[lru] = ++ctx->lk_clock;
+    *slot = lru;
+    return ZS_OK;
+}
+
 extern "C" zs_status zs_calc_optical_flow_pyr_lk_host(zs_context* ctx, const uint8_t* prev_img, const uint8_t* next_img,
                                                       int width, int height, size_t pitch, const float* prev_pts,
                                                       float* next_pts, int n, uint8_t* status, float* err,
@@ -34,11 +99,11 @@ extern "C" zs_status zs_calc_optical_flow_pyr_lk_host(zs_context* ctx, const uin
     ZS_REQUIRE(prev_pts && next_pts && status && err, "null argument");
     ZS_CUDA(cudaSetDevice(ctx->device));
     zs_pyramid* p;
-    zs_status st = host_pyramid(ctx, 0, width, height, 2, prm->win_w, prm->win_h, prm->max_level, &p);
+    zs_status st = lk_pyramid(ctx, width, height, prm, &p);
     if (st != ZS_OK) return st;
-    if ((st = zs_pyramid_upload(ctx, p, prev_img, pitch, pitch * height, 0, 1, 1)) != ZS_OK) return st;
-    if ((st = zs_pyramid_upload(ctx, p, next_img, pitch, pitch * height, 1, 1, 1)) != ZS_OK) return st;
-    if ((st = zs_pyramid_build(ctx, p, 0, 2)) != ZS_OK) return st;
+    int slot_prev = 0, slot_next = 1;
+    if ((st = lk_slot(ctx, p, prev_img, width, height, pitch, -1, &slot_prev)) != ZS_OK) return st;
+    if ((st = lk_slot(ctx, p, next_img, width, height, pitch, slot_prev, &slot_next)) != ZS_OK) return st;
     // scratch: [slots(2) count(1)] | prev n*2 f | next n*2 f | err n f | status n
     const size_t o_prev = 256, o_next = o_prev + al256(sizeof(float) * 2 * n), o_err = o_next + al256(sizeof(float) * 2 * n),
                  o_st = o_err + al256(sizeof(float) * n), total = o_st + al256(n);
@@ -46,7 +111,7 @@ extern "C" zs_status zs_calc_optical_flow_pyr_lk_host(zs_context* ctx, const uin
     void* s;
     if ((st = zs_scratch(ctx, total, &s)) != ZS_OK) return st;
     uint8_t* base = (uint8_t*)s;
-    const int hdr[3] = { 0, 1, n };
+    const int hdr[3] = { slot_prev, slot_next, n };
     ZS_CUDA(cudaMemcpyAsync(base, hdr, sizeof(hdr), cudaMemcpyHostToDevice, ctx->stream));
     ZS_CUDA(cudaMemcpyAsync(base + o_prev, prev_pts, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
     if (prm->flags & ZS_LK_USE_INITIAL_FLOW)
@@ -58,6 +123,14 @@ extern "C" zs_status zs_calc_optical_flow_pyr_lk_host(zs_context* ctx, const uin
     ZS_CUDA(cudaMemcpyAsync(status, base + o_st, n, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaMemcpyAsync(err, base + o_err, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZS_OK;
+}
+
+extern "C" zs_status zs_lk_cache_stats(const zs_context* ctx, uint64_t* hits, uint64_t* misses)
+{
+    ZS_REQUIRE(ctx, "null argument");
+    if (hits) *hits = ctx->lk_hits;
+    if (misses) *misses = ctx->lk_misses;
     return ZS_OK;
 }
 
@@ -76,17 +149,17 @@ extern "C" zs_status zs_track_keypoints_host(zs_context* ctx, const uint8_t* img
     ZS_REQUIRE(points_0 && points_1 && keep, "null argument");
     ZS_CUDA(cudaSetDevice(ctx->device));
     zs_pyramid* p;
-    zs_status st = host_pyramid(ctx, 0, width, height, 2, prm->win_w, prm->win_h, prm->max_level, &p);
+    zs_status st = lk_pyramid(ctx, width, height, prm, &p);
     if (st != ZS_OK) return st;
-    if ((st = zs_pyramid_upload(ctx, p, img_0, pitch, pitch * height, 0, 1, 1)) != ZS_OK) return st;
-    if ((st = zs_pyramid_upload(ctx, p, img_1, pitch, pitch * height, 1, 1, 1)) != ZS_OK) return st;
-    if ((st = zs_pyramid_build(ctx, p, 0, 2)) != ZS_OK) return st;
+    int slot_0 = 0, slot_1 = 1;
+    if ((st = lk_slot(ctx, p, img_0, width, height, pitch, -1, &slot_0)) != ZS_OK) return st;
+    if ((st = lk_slot(ctx, p, img_1, width, height, pitch, slot_0, &slot_1)) != ZS_OK) return st;
     const size_t o_prev = 256, o_next = o_prev + al256(sizeof(float) * 2 * n), o_err = o_next + al256(sizeof(float) * 2 * n),
                  o_st = o_err + al256(sizeof(float) * n), o_keep = o_st + al256(n), total = o_keep + al256(n);
     void* s;
     if ((st = zs_scratch(ctx, total, &s)) != ZS_OK) return st;
     uint8_t* base = (uint8_t*)s;
-    const int hdr[3] = { 0, 1, n };
+    const int hdr[3] = { slot_0, slot_1, n };
     ZS_CUDA(cudaMemcpyAsync(base, hdr, sizeof(hdr), cudaMemcpyHostToDevice, ctx->stream));
     ZS_CUDA(cudaMemcpyAsync(base + o_prev, points_0, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
     zs_lk_params q = *prm;
