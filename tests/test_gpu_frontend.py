@@ -265,16 +265,19 @@ def test_track_keylines_mirror(ctx):
     assert track_keylines(lk, A, B, {}, tracking_options()) == []
 
 
-@pytest.mark.parametrize("w,h,B,cell", [(752, 480, 3, (16, 16)), (640, 400, 2, (32, 32))])
-def test_frontend_batches_vs_oracle(ctx, w, h, B, cell):
+# three batches each: the first runs eagerly, the second is captured into a CUDA graph, the third replays it.  21 x 21
+# takes the register-template kernel, 45 x 45 the generic kernel (> 48 KB of dynamic shared memory: its attribute change
+# is not capturable, so that front-end must fall back to eager launches without an error)
+@pytest.mark.parametrize("w,h,B,cell,win,ml", [(752, 480, 3, (16, 16), (31, 31), 3), (640, 400, 2, (32, 32), (31, 31), 3),
+                                               (400, 300, 2, (16, 16), (21, 21), 2), (400, 300, 1, (16, 16), (45, 45), 2)])
+def test_frontend_batches_vs_oracle(ctx, w, h, B, cell, win, ml):
     from zenslam_b200 import detection_options, slam_options, tracking_options
     from zenslam_b200.frontend import StereoFrontend
     opts = slam_options(matcher="KNN", matcher_ratio=0.8, detection=detection_options(cell_size=cell),
-                        tracking=tracking_options())
+                        tracking=tracking_options(klt_window_size=win, klt_max_level=ml))
     fe = StereoFrontend(ctx, w, h, B, opts)
-    nb = 2
+    nb = 3
     seq, _ = syn.stereo_sequence(w, h, nb * B, 5000 + w, subpixel=True)
-    win, ml = (31, 31), 3
     prev = None     # (imgL, imgR, kpL, kpR)
     for b in range(nb):
         chunk = seq[b * B:(b + 1) * B]

@@ -218,7 +218,9 @@ extern "C" zs_status zs_frontend_run(zs_frontend* fe)
             cudaGetLastError();
             fe->gexec = nullptr; fe->graph_ok = false;
             ctx->launches = l0;
-            return st != ZS_OK ? st : frontend_run_body(fe);   // nothing ran during the capture
+            // nothing ran during the capture: run it eagerly (a call that is merely illegal while capturing, e.g. an
+            // attribute change for a large-window kernel, succeeds now; a genuine error shows up again)
+            return frontend_run_body(fe);
         }
         fe->g_launches = ctx->launches - l0;                    // kernels per replay (counted at launch below)
         ctx->launches = l0;
