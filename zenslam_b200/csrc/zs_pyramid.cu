@@ -76,10 +76,13 @@ __device__ __forceinline__ void pd_row(const uint8_t* __restrict__ row, int h4[4
 
 __global__ void __launch_bounds__(256) k_pyr_down(zs_pyr_view v, int level, int first)
 {
+    // work items = 4-pixel groups, flattened over (row, group) so that every thread of a block has one even when a row
+    // holds fewer than 256 groups (a block per row left 63 % of the threads idle at level 0 -> 1 and more above)
     const int dw = v.w[level + 1], dh = v.h[level + 1];
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y;
-    if (x0 >= dw) return;
+    const int wq = (dw + 3) >> 2;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = item / wq, x0 = (item - y * wq) * 4;
+    if (y >= dh) return;
     const int slot = zs_slot(first, blockIdx.z, v.slots);
     const int sp = v.pitch[level];
     const uint8_t* src = v.img[level] + (size_t)slot * v.slot_stride[level] + (size_t)v.pad_y * sp + v.pad_x;
@@ -107,7 +110,6 @@ __global__ void __launch_bounds__(256) k_pyr_down(zs_pyr_view v, int level, int 
     } else {
         for (int k = 0; x0 + k < dw; ++k) dst[k] = (uint8_t)acc[k];
     }
-    (void)dh;
 }
 
 // ---- (3) Scharr ---------------------------------------------------------------------------------------
@@ -125,9 +127,10 @@ __device__ __forceinline__ void sc_row(const uint8_t* __restrict__ row, int s[6]
 __global__ void __launch_bounds__(256) k_scharr(zs_pyr_view v, int level, int first)
 {
     const int w = v.w[level];
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y;
-    if (x0 >= w) return;
+    const int wq = (w + 3) >> 2;                         // flattened (row, 4-pixel group) items, see k_pyr_down
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = item / wq, x0 = (item - y * wq) * 4;
+    if (y >= v.h[level]) return;
     const int slot = zs_slot(first, blockIdx.z, v.slots);
     const int pitch = v.pitch[level];
     const size_t org = (size_t)slot * v.slot_stride[level] + (size_t)(v.pad_y + y) * pitch + v.pad_x + x0;
@@ -161,10 +164,10 @@ extern "C" zs_status zs_pyramid_build(zs_context* ctx, zs_pyramid* p, int first,
         ZS_LAUNCH_CHECK(ctx);
         if (l + 1 < v.levels) {
             const int dw = v.w[l + 1], dh = v.h[l + 1];
-            k_pyr_down<<<dim3(zs_div_up(zs_div_up(dw, 4), 256), dh, count), 256, 0, ctx->stream>>>(v, l, first);
+            k_pyr_down<<<dim3(zs_div_up(zs_div_up(dw, 4) * dh, 256), 1, count), 256, 0, ctx->stream>>>(v, l, first);
             ZS_LAUNCH_CHECK(ctx);
         }
-        k_scharr<<<dim3(zs_div_up(zs_div_up(w, 4), 256), h, count), 256, 0, ctx->stream>>>(v, l, first);
+        k_scharr<<<dim3(zs_div_up(zs_div_up(w, 4) * h, 256), 1, count), 256, 0, ctx->stream>>>(v, l, first);
         ZS_LAUNCH_CHECK(ctx);
     }
     return ZS_OK;
