@@ -106,4 +106,5 @@ zs_status zs_launch_orb_blur(zs_context* ctx, const zs_pyramid* p, int first, in
 zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_slot, const int* d_next_slot,
                         const float* d_prev_pts, float* d_next_pts, const int* d_count, const int* d_pts_row, int jobs, int cap,
                         const zs_lk_params* prm, uint8_t* d_status, float* d_err, int fb, double fb_thr, uint8_t* d_keep,
-                        const int* d_next_slot2 = nullptr, const int* d_out_job2 = nullptr);
+                        const int* d_next_slot2 = nullptr, const int* d_out_job2 = nullptr, const int* d_job_list = nullptr,
+                        int n_list = 0);

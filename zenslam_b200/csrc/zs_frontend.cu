@@ -27,6 +27,7 @@ struct zs_frontend {
     int* m_idx; float* m_dist; uint8_t* m_pass;          // [B][cap]
     int* job_prev; int* job_next; int* job_row;          // [4B]
     int* job_next2; int* job_out2; int* job_prev_all;    // [4B] template sharing (see zs_frontend_create)
+    int* job_list; int n_job_list;                       // jobs that still own work once temporal jobs are folded
     float* t_pts; uint8_t* t_status; float* t_err; uint8_t* t_keep;   // [4B][cap]
     int* t_n;                                            // [4B] points tracked per job
     bool have_carry; bool share;
@@ -87,7 +88,7 @@ extern "C" zs_status zs_frontend_create(zs_context* ctx, const zs_frontend_optio
     CARVE(xy, float, 2 * S * cap) CARVE(resp, float, S * cap) CARVE(n, int, S) CARVE(desc, uint8_t, S * cap * 32)
     CARVE(m_idx, int, 2 * B * cap) CARVE(m_dist, float, 2 * B * cap) CARVE(m_pass, uint8_t, B * cap)
     CARVE(job_prev, int, J) CARVE(job_next, int, J) CARVE(job_row, int, J)
-    CARVE(job_next2, int, J) CARVE(job_out2, int, J) CARVE(job_prev_all, int, J)
+    CARVE(job_next2, int, J) CARVE(job_out2, int, J) CARVE(job_prev_all, int, J) CARVE(job_list, int, J)
     CARVE(t_pts, float, 2 * J * cap) CARVE(t_status, uint8_t, J * cap) CARVE(t_err, float, J * cap)
     CARVE(t_keep, uint8_t, J * cap) CARVE(t_n, int, J)
 #undef CARVE
@@ -98,7 +99,7 @@ extern "C" zs_status zs_frontend_create(zs_context* ctx, const zs_frontend_optio
 #define BIND(field, type) fe->field = (type*)(fe->dev + o_##field);
     BIND(raw_xy, float) BIND(raw_resp, float) BIND(raw_n, int) BIND(xy, float) BIND(resp, float) BIND(n, int)
     BIND(desc, uint8_t) BIND(m_idx, int) BIND(m_dist, float) BIND(m_pass, uint8_t) BIND(job_prev, int) BIND(job_next, int)
-    BIND(job_row, int) BIND(job_next2, int) BIND(job_out2, int) BIND(job_prev_all, int) BIND(t_pts, float) BIND(t_status, uint8_t) BIND(t_err, float) BIND(t_keep, uint8_t) BIND(t_n, int)
+    BIND(job_row, int) BIND(job_next2, int) BIND(job_out2, int) BIND(job_prev_all, int) BIND(job_list, int) BIND(t_pts, float) BIND(t_status, uint8_t) BIND(t_err, float) BIND(t_keep, uint8_t) BIND(t_n, int)
 #undef BIND
     // job tables: kind-major [4][B].  The stereo job of frame k (L_k -> R_k from the keypoints of L_k) and the temporal
     // job of frame k+1 (L_k -> L_{k+1} from the same keypoints) share their forward template: the temporal job is
@@ -125,6 +126,13 @@ extern "C" zs_status zs_frontend_create(zs_context* ctx, const zs_frontend_optio
     if (e == cudaSuccess) e = cudaMemcpyAsync(fe->job_row, hr, sizeof(int) * J, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(fe->job_next2, hn2, sizeof(int) * J, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(fe->job_out2, ho2, sizeof(int) * J, cudaMemcpyHostToDevice, ctx->stream);
+    // the jobs that still launch blocks once the temporal jobs are folded: 2B + 2 of the 4B
+    fe->n_job_list = 0;
+    if (share) {
+        int* hl = hpa;                                     // hpa is no longer needed when sharing
+        for (size_t j = 0; j < J; ++j) if (hp[j] >= 0) hl[fe->n_job_list++] = (int)j;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(fe->job_list, hl, sizeof(int) * fe->n_job_list, cudaMemcpyHostToDevice, ctx->stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     free(h);
     if (e != cudaSuccess) { zs_frontend_destroy(fe); return zs_cuda_fail(e, "frontend job tables", __FILE__, __LINE__); }
@@ -265,7 +273,7 @@ static zs_status frontend_run_body(zs_frontend* fe)
     prm.epsilon = o.epsilon; prm.flags = ZS_LK_GET_MIN_EIGENVALS; prm.min_eig_threshold = o.min_eig_threshold;
     if ((st = zs_klt_launch(ctx, fe->pyr, fe->job_prev, fe->job_next, fe->xy, fe->t_pts, fe->n, fe->job_row, 4 * B, cap, &prm,
                             fe->t_status, fe->t_err, 1, o.klt_threshold, fe->t_keep, fe->share ? fe->job_next2 : nullptr,
-                            fe->share ? fe->job_out2 : nullptr)) != ZS_OK) return st;
+                            fe->share ? fe->job_out2 : nullptr, fe->share ? fe->job_list : nullptr, fe->n_job_list)) != ZS_OK) return st;
     k_gather_counts<<<zs_div_up(4 * B, 256), 256, 0, ctx->stream>>>(fe->n, fe->job_row, 4 * B, fe->t_n);
     ZS_LAUNCH_CHECK(ctx);
     ZS_FE_MARK(5);

@@ -23,6 +23,7 @@ struct klt_args {
     // optional second target per job (template sharing): job j also tracks its points into slot next_slot2[j] and
     // writes those results to the rows of job out_job2[j] (< 0: none).  A job whose prev_slot is < 0 is skipped.
     const int* next_slot2; const int* out_job2;
+    const int* job_list;     // optional: blockIdx.y indexes this list of jobs to run (the rest were folded into second targets)
     int cap, win_w, win_h, max_level, max_iters, flags;
     double eps2, min_eig;
     float eps2_lo, eps2_hi;  // float band around eps2 inside which the double comparison is evaluated
@@ -628,7 +629,7 @@ __global__ void __launch_bounds__(KLT3_WARPS * 32, KLT4_MIN_BLOCKS) k_klt_track_
 {
     extern __shared__ __align__(128) uint8_t smem3[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int job = blockIdx.y;
+    const int job = a.job_list ? a.job_list[blockIdx.y] : blockIdx.y;
     const int slot_src = a.prev_slot[job];
     if (slot_src < 0) return;                                  // job folded into another job's second target
     const int i = blockIdx.x * KLT3_WARPS + warp;
@@ -733,7 +734,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) k_klt_track(klt_args a)
 zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_slot, const int* d_next_slot,
                         const float* d_prev_pts, float* d_next_pts, const int* d_count, const int* d_pts_row, int jobs, int cap,
                         const zs_lk_params* prm, uint8_t* d_status, float* d_err, int fb, double fb_thr, uint8_t* d_keep,
-                        const int* d_next_slot2, const int* d_out_job2)
+                        const int* d_next_slot2, const int* d_out_job2, const int* d_job_list, int n_list)
 {
     ZS_REQUIRE(ctx && p && d_prev_slot && d_next_slot && d_prev_pts && d_next_pts && d_count && prm && d_status && d_err,
                "null argument");
@@ -751,7 +752,7 @@ zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_
     double eps = prm->epsilon; eps = eps < 0 ? 0 : eps > 10. ? 10. : eps;   // cv: clamp(epsilon, 0, 10)
     a.max_iters = mi; a.eps2 = eps * eps; a.flags = prm->flags; a.min_eig = prm->min_eig_threshold;
     a.status = d_status; a.err = d_err; a.fb = fb; a.fb_thr = fb_thr; a.keep = d_keep;
-    a.next_slot2 = d_next_slot2; a.out_job2 = d_out_job2;
+    a.next_slot2 = d_next_slot2; a.out_job2 = d_out_job2; a.job_list = nullptr;
     if (a.eps2 < 1e-30) { a.eps2_lo = -1.f; a.eps2_hi = 3.0e38f; }         // always take the exact comparison
     else {
         a.eps2_lo = nextafterf((float)(a.eps2 * (1.0 - 1e-6)), 0.f);
@@ -760,7 +761,9 @@ zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_
     // TMA-staged kernel for the reference's default window
     if (a.win_w == 31 && a.win_h == 31 && a.v.tmaps && !getenv("ZS_KLT_NO_TMA")) {
         const size_t smem3 = (size_t)KLT3_WARPS * KLT3_WARP_BYTES;
-        k_klt_track_v4<31, 31><<<dim3(zs_div_up(cap, KLT3_WARPS), jobs), KLT3_WARPS * 32, smem3, ctx->stream>>>(a);
+        // with a job list only the jobs that still own work get blocks (folded jobs would launch cap empty CTAs each)
+        if (d_job_list && n_list > 0) a.job_list = d_job_list;
+        k_klt_track_v4<31, 31><<<dim3(zs_div_up(cap, KLT3_WARPS), a.job_list ? n_list : jobs), KLT3_WARPS * 32, smem3, ctx->stream>>>(a);
         ZS_LAUNCH_CHECK(ctx);
         return ZS_OK;
     }
@@ -797,7 +800,7 @@ extern "C" zs_status zs_klt_track(zs_context* ctx, const zs_pyramid* p, const in
                                   const zs_lk_params* params, uint8_t* d_status, float* d_err)
 {
     return zs_klt_launch(ctx, p, d_prev_slot, d_next_slot, d_prev_pts, d_next_pts, d_count, nullptr, jobs, cap, params,
-                         d_status, d_err, 0, 0.0, nullptr, nullptr, nullptr);
+                         d_status, d_err, 0, 0.0, nullptr, nullptr, nullptr, nullptr, 0);
 }
 
 extern "C" zs_status zs_klt_track_fb(zs_context* ctx, const zs_pyramid* p, const int* d_prev_slot, const int* d_next_slot,
@@ -807,5 +810,5 @@ extern "C" zs_status zs_klt_track_fb(zs_context* ctx, const zs_pyramid* p, const
 {
     ZS_REQUIRE(d_keep, "d_keep is null");
     return zs_klt_launch(ctx, p, d_prev_slot, d_next_slot, d_prev_pts, d_next_pts, d_count, nullptr, jobs, cap, params,
-                         d_status, d_err, 1, klt_threshold, d_keep, nullptr, nullptr);
+                         d_status, d_err, 1, klt_threshold, d_keep, nullptr, nullptr, nullptr, 0);
 }
