@@ -110,3 +110,100 @@ def test_klt_random(ctx, seed):
     assert np.array_equal(st[:n], os_) and np.array_equal(p1[:n], o1) and np.array_equal(err[:n], oe), (win, ml, w, h)
     assert np.array_equal(keep[:n].astype(bool), oracle.fb_check(pts, ob, os_, osb, 1.0))
     p.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_preprocessing_random(ctx, seed):
+    """BGR->gray, CLAHE(clip), remap with maps that leave the frame (constant-0 border), odd sizes, against the oracle"""
+    from zenslam_b200.processing import processor
+    rng = np.random.default_rng(300 + seed)
+    w, h = int(rng.integers(64, 500)), int(rng.integers(64, 360))
+    tex = _image(rng, w, h, seed % 4)
+    bgr = np.stack([tex, np.roll(tex, int(rng.integers(1, 9)), 1), (255 - tex // 2)], -1).astype(np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    k1 = float(rng.uniform(-0.3, 0.3)); sx, sy = rng.uniform(-6, 6, 2)
+    r2 = ((xx - w / 2) ** 2 + (yy - h / 2) ** 2) / (w * w / 4)
+    mx = (w / 2 + (xx - w / 2) * (1 + k1 * r2) + sx).astype(np.float32)
+    my = (h / 2 + (yy - h / 2) * (1 + k1 * r2) + sy).astype(np.float32)
+    clip = float(rng.choice([2.0, 4.0, 40.0]))
+    gray = oracle.bgr2gray(bgr)
+    assert np.array_equal(processor(ctx).process_image(bgr), gray)
+    assert np.array_equal(processor(ctx, clahe_enabled=True, clahe_clip_limit=clip).process_image(bgr), oracle.clahe(gray, clip))
+    want = oracle.remap_linear(oracle.clahe(gray, clip), mx, my)
+    assert np.array_equal(processor(ctx, clahe_enabled=True, clahe_clip_limit=clip, maps=[(mx, my)]).process_image(bgr), want)
+    assert np.array_equal(processor(ctx, maps=[(mx, my)]).process_image(gray), oracle.remap_linear(gray, mx, my))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_corner_subpix_random(ctx, seed):
+    from zenslam_b200.runtime import Pyramid, corner_subpix
+    rng = np.random.default_rng(400 + seed)
+    w, h = int(rng.integers(60, 400)), int(rng.integers(60, 300))
+    img = _image(rng, w, h, seed % 4)
+    n = int(rng.integers(1, 300))
+    pts = np.stack([rng.uniform(0, w - 1, n), rng.uniform(0, h - 1, n)], 1).astype(np.float32)
+    pts[: n // 5] = np.rint(pts[: n // 5])
+    win = [(5, 5), (3, 3), (7, 7), (2, 6), (5, 5), (1, 1)][seed]
+    its, eps = int(rng.choice([1, 5, 30])), float(rng.choice([0.001, 0.01, 0.1]))
+    pyr = Pyramid(ctx, w, h, 1, (31, 31), 0)
+    pyr.upload(img[None], 0); pyr.build(0, 1)
+    cap = max(n, 1)
+    xy = dev(ctx, pts[None].copy())
+    corner_subpix(pyr, 0, 1, xy, dev(ctx, np.array([n], np.int32)), win, its, eps)
+    assert cap >= n
+    assert np.array_equal(xy[0, :n].cpu().numpy(), oracle.corner_subpix(img, pts, win, its, eps))
+    pyr.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_l2_random(ctx, seed):
+    """ragged SIFT-like and low-entropy pairs: tensor-core kNN-2 + ratio and cross-check against the oracle"""
+    from zenslam_b200.runtime import match_l2_cross, match_l2_knn2
+    rng = np.random.default_rng(500 + seed)
+    pairs = int(rng.integers(1, 5))
+    cap_q, cap_t = int(rng.integers(1, 700)), int(rng.integers(1, 900))
+    hi = [256, 256, 4, 256, 2, 64][seed]
+    q = rng.integers(0, hi, (pairs, cap_q, 128)).astype(np.float32); t = rng.integers(0, hi, (pairs, cap_t, 128)).astype(np.float32)
+    nq = rng.integers(0, cap_q + 1, pairs).astype(np.int32); nt = rng.integers(0, cap_t + 1, pairs).astype(np.int32)
+    nq[0], nt[0] = cap_q, cap_t
+    for k in range(pairs):                                 # plant exact duplicates: distance-0 ties across tiles
+        if nq[k] > 2 and nt[k] > 140:
+            t[k, 3] = t[k, 139] = q[k, 1]
+    idx, dist, ps = [x.cpu().numpy() for x in match_l2_knn2(ctx, dev(ctx, q), dev(ctx, nq), dev(ctx, t), dev(ctx, nt), 0.8)]
+    cidx, cdist = [x.cpu().numpy() for x in match_l2_cross(ctx, dev(ctx, q), dev(ctx, nq), dev(ctx, t), dev(ctx, nt))]
+    for k in range(pairs):
+        a, b = int(nq[k]), int(nt[k])
+        if a == 0 or b == 0:
+            assert np.all(idx[k, :a] == -1) and np.all(cidx[k, :a] == -1)
+            continue
+        oi, od = oracle.match_l2_knn2(q[k, :a], t[k, :b])
+        assert np.array_equal(idx[k, :a], oi), (k, a, b)
+        assert np.array_equal(dist[k, :a][oi >= 0], od[oi >= 0])
+        if b >= 2:
+            assert np.array_equal(np.nonzero(ps[k, :a])[0], oracle.ratio_test(oi, od, 0.8)[0])
+        oq, ot, odd = oracle.match_l2_cross(q[k, :a], t[k, :b])
+        keep = np.nonzero(cidx[k, :a] >= 0)[0]
+        assert np.array_equal(keep, oq) and np.array_equal(cidx[k, keep], ot) and np.array_equal(cdist[k, keep], odd)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_orb_detector_random(ctx, seed):
+    from zenslam_b200.runtime import OrbDetector
+    rng = np.random.default_rng(600 + seed)
+    w, h = int(rng.integers(150, 700)), int(rng.integers(120, 500))
+    kw = [dict(), dict(nfeatures=120, nlevels=4), dict(scale_factor=1.44, nlevels=5, nfeatures=900), dict(nfeatures=40)][seed]
+    thr = int(rng.choice([5, 10, 20]))
+    imgs = np.stack([_image(rng, w, h, (seed + k) % 4) for k in range(2)])
+    mask = np.full((2, h, w), 255, np.uint8)
+    mask[0, : h // 3] = 0
+    mask[1][rng.random((h, w)) < 0.3] = 0
+    det = OrbDetector(ctx, w, h, 2, fast_threshold=thr, **kw)
+    r = det.detect_and_compute(imgs, mask)
+    for k in range(2):
+        o = oracle.orb_detect(imgs[k], mask[k], fast_threshold=thr, **kw)
+        n = int(r["n"][k])
+        assert n == len(o["x"]), (k, n, len(o["x"]))
+        assert np.array_equal(r["xy"][k, :n].cpu().numpy(), np.stack([o["x"], o["y"]], 1))
+        for key in ("size", "angle", "response", "octave", "desc"):
+            assert np.array_equal(r[key][k, :n].cpu().numpy(), o[key]), (k, key)
+    det.close()
