@@ -317,6 +317,34 @@ ZS_API zs_status zs_triangulate_keypoints_host(zs_context* ctx, const double* P0
                                                const double* t, const float* pts0, const float* pts1, int n,
                                                const zs_triangulation_params* params, double* xyz, uint8_t* keep, double* diag);
 
+/* ---- per-frame stereo tracker: keypoint_tracker::track -------------------------------------------------------
+ * (zenslam_core/source/tracking/keypoint_tracker.cpp:41-105) for ONE stereo sequence, one call per stereo frame, state
+ * (previous pyramids and the two index-keyed keypoint maps) kept on the device: temporal forward-backward KLT of both
+ * cameras, grid detection behind the occupancy of the tracked keypoints, stereo tracks L -> R / R -> L of the keypoints
+ * the other camera lacks, sequential keypoint indices (keypoint::index_next).  Algorithm GRID, feature FAST, descriptor
+ * ORB.  Left to the host, as injected callables are in the Python mirror: landmark projection for the initial flow,
+ * assign_landmark_indices, filter_epipolar (cv::findFundamentalMat RANSAC).  Results: both maps in key (index) order. */
+typedef struct zs_tracker zs_tracker;
+typedef struct {
+    int width, height;
+    int cell_w, cell_h, fast_threshold;            /* detection.cell_size, detection.fast_threshold */
+    int klt_win_w, klt_win_h, klt_max_level;       /* tracking.klt_window_size, tracking.klt_max_level */
+    double klt_threshold;                          /* tracking.klt_threshold */
+    int capacity;                                  /* keypoints per camera; 0 = 2 x cells + 64 */
+    int first_index;                               /* keypoint::index_next when the sequence starts */
+} zs_tracker_options;
+typedef struct {                                   /* HOST pointers; arrays sized cap >= zs_tracker_capacity(); any may be NULL */
+    int cap;
+    int* n;                                        /* [2] keypoints per camera */
+    int* index[2]; float* xy[2]; float* response[2]; uint8_t* desc[2];
+    int* next_index;                               /* keypoint::index_next after this frame */
+} zs_tracker_results;
+ZS_API zs_status zs_tracker_create(zs_context* ctx, const zs_tracker_options* opt, zs_tracker** out);
+ZS_API void zs_tracker_destroy(zs_tracker* t);
+ZS_API int zs_tracker_capacity(const zs_tracker* t);
+ZS_API zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, const uint8_t* right, size_t pitch,
+                                       const zs_tracker_results* res);
+
 /* ---- batched stereo front-end ------------------------------------------------------------------
  * The per-frame call pattern of keypoint_tracker::track (keypoint_tracker.cpp:41-105) restated for
  * a batch of B consecutive stereo frames: per frame 2 pyramids, 2 grid detections + ORB, 1 stereo

@@ -198,6 +198,40 @@ def test_keypoint_tracker_track_flow_vs_oracle(ctx):
         keypoint_tracker(slam_options(), ctx, create_cuda_pyr_lk(ctx))                  # filter_epipolar on, no RANSAC callable
 
 
+@pytest.mark.parametrize("w,h,cell", [(376, 240, (16, 16)), (640, 400, (32, 32))])
+def test_device_tracker_equals_track_mirror(ctx, w, h, cell):
+    """zs_tracker (maps, previous pyramids and index counter on the device, one call per stereo frame) against the
+    keypoint_tracker.track mirror, which is itself checked against the oracle: same index sets, positions, responses and
+    descriptors in both cameras on every frame, same keypoint::index_next"""
+    import dataclasses
+    from zenslam_b200 import detection_options, keypoint, slam_options, tracking_options
+    from zenslam_b200.keypoint_tracker import device_keypoint_tracker, keypoint_tracker, stereo_frame
+    from zenslam_b200.tracking import create_cuda_pyr_lk
+    frames = 6
+    seq, _ = syn.stereo_sequence(w, h, frames, 1040 + w, subpixel=True)
+    opts = slam_options(matcher="KNN", detection=detection_options(cell_size=cell), tracking=tracking_options(filter_epipolar=False))
+    keypoint.index_next = 0
+    host = keypoint_tracker(opts, ctx, create_cuda_pyr_lk(ctx))
+    prev = stereo_frame((seq[0, 0], seq[0, 1]))
+    want = []
+    for t in range(frames):
+        cur = stereo_frame((seq[t, 0], seq[t, 1]))
+        k0, k1 = host.track(prev, cur)
+        want.append((k0, k1, keypoint.index_next))
+        prev = dataclasses.replace(cur, keypoints=(k0, k1))
+    keypoint.index_next = 0
+    dev_trk = device_keypoint_tracker(opts, ctx, w, h)
+    for t in range(frames):
+        g0, g1 = dev_trk.track(seq[t, 0], seq[t, 1])
+        for cam, (g, r) in enumerate(((g0, want[t][0]), (g1, want[t][1]))):
+            assert list(g) == sorted(r), (t, cam, len(g), len(r))
+            for i in g:
+                assert g[i].pt == r[i].pt and g[i].response == r[i].response and np.array_equal(g[i].descriptor, r[i].descriptor), (t, cam, i)
+        assert keypoint.index_next == want[t][2]
+    assert len(set(g0) & set(want[0][0])) > 30 and len(set(g0) & set(g1)) > 100           # tracks survive, stereo pairs exist
+    dev_trk.close()
+
+
 def test_lk_host_pyramid_cache(ctx):
     """the LK host entries keep the pyramids of the frames they saw (content-keyed): repeated frames hit, a frame whose
     bytes changed in place misses, and results never depend on the cache state"""

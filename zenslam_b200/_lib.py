@@ -31,6 +31,17 @@ class TriangulationParams(C.Structure):
                 ("min_depth", C.c_double), ("max_depth", C.c_double)]
 
 
+class TrackerOptions(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("cell_w", C.c_int), ("cell_h", C.c_int), ("fast_threshold", C.c_int),
+                ("klt_win_w", C.c_int), ("klt_win_h", C.c_int), ("klt_max_level", C.c_int), ("klt_threshold", C.c_double),
+                ("capacity", C.c_int), ("first_index", C.c_int)]
+
+
+class TrackerResults(C.Structure):
+    _fields_ = [("cap", C.c_int), ("n", C.c_void_p), ("index", C.c_void_p * 2), ("xy", C.c_void_p * 2),
+                ("response", C.c_void_p * 2), ("desc", C.c_void_p * 2), ("next_index", C.c_void_p)]
+
+
 class FrontendOptions(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("batch", C.c_int),
                 ("cell_w", C.c_int), ("cell_h", C.c_int), ("fast_threshold", C.c_int),
@@ -108,6 +119,10 @@ SIGNATURES = {
     "zs_assign_landmarks_host": (I, [P, P, I, P, I, D, P, P]),
     "zs_triangulate_keypoints": (I, [P, P, P, P, P, P, P, I, C.POINTER(TriangulationParams), P, P, P]),
     "zs_triangulate_keypoints_host": (I, [P, P, P, P, P, P, P, I, C.POINTER(TriangulationParams), P, P, P]),
+    "zs_tracker_create": (I, [P, C.POINTER(TrackerOptions), C.POINTER(P)]),
+    "zs_tracker_destroy": (None, [P]),
+    "zs_tracker_capacity": (I, [P]),
+    "zs_tracker_track_host": (I, [P, P, P, Z, C.POINTER(TrackerResults)]),
     "zs_frontend_create": (I, [P, C.POINTER(FrontendOptions), C.POINTER(P)]),
     "zs_frontend_destroy": (None, [P]),
     "zs_frontend_capacity": (I, [P]),

@@ -1,0 +1,367 @@
+// zs_tracker.cu -- keypoint_tracker::track (zenslam_core/source/tracking/keypoint_tracker.cpp:41-105) for one stereo
+// sequence, one call per stereo frame, all bookkeeping on the device:
+//
+//   temporal forward-backward KLT of both cameras' keypoints (:47-51)            zs_klt_launch, 2 jobs
+//   detection in the cells the tracked left keypoints leave free (:53-57)        occupancy -> zs_fast_grid_detect -> zs_orb_compute
+//   stereo track L -> R of the left keypoints the right camera lacks (:59-67)    index-set difference -> zs_klt_launch
+//   detection in the right image behind the occupancy of ALL right keypoints     (:69-73)
+//   stereo track R -> L of the right keypoints the left camera lacks (:75-83)
+//
+// zenslam::map<keypoint> is a std::map keyed by keypoint::index (types/map.h:24-100): here each camera's map is a
+// structure of arrays kept SORTED by index (index, xy, response, descriptor), so "values in key order" is array order,
+// `contains` is a binary search and `add` without overwrite is an append of indices known to be absent, followed by one
+// sort per frame.  New keypoints take sequential indices from a device-side counter in detection order (left image
+// first), exactly like keypoint::index_next.  Not done here (injected on the host in the reference too): landmark
+// projection for the initial flow, assign_landmark_indices, filter_epipolar's RANSAC.
+#include "zs_common.cuh"
+
+#define TRK_THREADS 1024
+
+struct trk_map {                 // one camera's keypoint map
+    int* idx; float* xy; float* resp; uint8_t* desc; int* n;     // [cap], [cap][2], [cap], [cap][32], [1]
+};
+
+struct zs_tracker {
+    zs_context* ctx;
+    zs_tracker_options opt;
+    int cap, cells, gw, gh;
+    uint64_t frame;
+    zs_pyramid* pyr;             // 4 slots: (frame & 1) * 2 + camera
+    uint8_t* dev; size_t dev_bytes;
+    trk_map prev[2], cur[2], tmp;                 // tmp: sort destination
+    int* slots;                  // [8] job slot table, rewritten per frame
+    float* t_pts; uint8_t* t_status; float* t_err; uint8_t* t_keep;   // [2][cap] KLT outputs
+    uint8_t* occ;                // [cells]
+    float* raw_xy; float* raw_resp; int* raw_n;   // grid candidates before ORB's border filter [cells]
+    float* det_xy; float* det_resp; int* det_n; uint8_t* det_desc;   // after ORB::compute
+    int* sel; int* sel_n; float* sel_pts;         // positions of the entries to stereo-track, their count, their points
+    int* next_index;             // device copy of keypoint::index_next
+    int* overflow;               // set when a map would exceed cap
+};
+
+// ordered compaction of the temporally tracked keypoints of camera blockIdx.x: cur = {prev[i] : keep[i]} with the new positions
+__global__ void __launch_bounds__(TRK_THREADS) k_trk_compact(trk_map p0, trk_map p1, trk_map c0, trk_map c1, const float* __restrict__ t_pts,
+                                                             const uint8_t* __restrict__ keep, int cap)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const trk_map p = blockIdx.x ? p1 : p0, c = blockIdx.x ? c1 : c0;
+    const float* pts = t_pts + (size_t)blockIdx.x * cap * 2;
+    const uint8_t* kp = keep + (size_t)blockIdx.x * cap;
+    const int n = min(*p.n, cap), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += TRK_THREADS) {
+        const int i = base + threadIdx.x;
+        const bool f = i < n && kp[i];
+        const uint32_t m = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) warp_sums[warp] = __popc(m);
+        __syncthreads();
+        int woff = 0, total = 0;
+        for (int k = 0; k < TRK_THREADS / 32; ++k) { const int s = warp_sums[k]; if (k < warp) woff += s; total += s; }
+        if (f) {
+            const int o = carry + woff + __popc(m & ((1u << lane) - 1));
+            c.idx[o] = p.idx[i]; c.xy[2 * o] = pts[2 * i]; c.xy[2 * o + 1] = pts[2 * i + 1]; c.resp[o] = p.resp[i];
+            const uint4* s = (const uint4*)(p.desc + (size_t)i * 32);
+            uint4* d = (uint4*)(c.desc + (size_t)o * 32);
+            d[0] = s[0]; d[1] = s[1];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *c.n = carry;
+}
+
+// occupied[int(pt.x) / cw][int(pt.y) / ch] (keypoint_detector_grid.cpp:47-64: truncating cast, then integer division)
+__global__ void __launch_bounds__(TRK_THREADS) k_trk_occupancy(trk_map m, int cap, int gw, int gh, int cw, int ch, uint8_t* __restrict__ occ)
+{
+    for (int i = threadIdx.x; i < gw * gh; i += TRK_THREADS) occ[i] = 0;
+    __syncthreads();
+    const int n = min(*m.n, cap);
+    for (int i = threadIdx.x; i < n; i += TRK_THREADS) {
+        const int gx = (int)m.xy[2 * i] / cw, gy = (int)m.xy[2 * i + 1] / ch;
+        if (gx >= 0 && gx < gw && gy >= 0 && gy < gh) occ[gy * gw + gx] = 1;
+    }
+}
+
+// map.add(detected): new keypoints get index_next, index_next + 1, .. in detection order (keypoint_detector_grid.cpp:142-147)
+__global__ void __launch_bounds__(TRK_THREADS) k_trk_append_detected(trk_map m, int cap, const float* __restrict__ dxy, const float* __restrict__ dresp,
+                                                                     const uint8_t* __restrict__ ddesc, const int* __restrict__ dn,
+                                                                     int* __restrict__ next_index, int* __restrict__ overflow)
+{
+    const int n = *m.n, k = *dn, first = *next_index;
+    for (int i = threadIdx.x; i < k; i += TRK_THREADS) {
+        const int o = n + i;
+        if (o >= cap) continue;
+        m.idx[o] = first + i; m.xy[2 * o] = dxy[2 * i]; m.xy[2 * o + 1] = dxy[2 * i + 1]; m.resp[o] = dresp[i];
+        const uint4* s = (const uint4*)(ddesc + (size_t)i * 32);
+        uint4* d = (uint4*)(m.desc + (size_t)o * 32);
+        d[0] = s[0]; d[1] = s[1];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (n + k > cap) *overflow = 1;
+        *m.n = min(n + k, cap);
+        *next_index = first + k;
+    }
+}
+
+// the values of `a` whose index `b` does not contain, in key order (map::values_unmatched): positions + points for KLT.
+// `b` is searched in its first nb_sorted entries, which are sorted by index.
+__global__ void __launch_bounds__(TRK_THREADS) k_trk_unmatched(trk_map a, trk_map b, int nb_sorted_is_all, const int* __restrict__ nb_sorted, int cap,
+                                                               int* __restrict__ sel, int* __restrict__ sel_n, float* __restrict__ sel_pts)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int na = min(*a.n, cap), nb = nb_sorted_is_all ? min(*b.n, cap) : *nb_sorted;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < na; base += TRK_THREADS) {
+        const int i = base + threadIdx.x;
+        bool f = false;
+        if (i < na) {
+            const int key = a.idx[i];
+            int lo = 0, hi = nb;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (b.idx[mid] < key) lo = mid + 1; else hi = mid; }
+            f = !(lo < nb && b.idx[lo] == key);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) warp_sums[warp] = __popc(m);
+        __syncthreads();
+        int woff = 0, total = 0;
+        for (int k = 0; k < TRK_THREADS / 32; ++k) { const int s = warp_sums[k]; if (k < warp) woff += s; total += s; }
+        if (f) {
+            const int o = carry + woff + __popc(m & ((1u << lane) - 1));
+            sel[o] = i; sel_pts[2 * o] = a.xy[2 * i]; sel_pts[2 * o + 1] = a.xy[2 * i + 1];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *sel_n = carry;
+}
+
+// dst.add(stereo-tracked): the kept ones of the selected entries of src, with their tracked positions, in order
+__global__ void __launch_bounds__(TRK_THREADS) k_trk_append_tracked(trk_map src, trk_map dst, int cap, const int* __restrict__ sel,
+                                                                    const int* __restrict__ sel_n, const float* __restrict__ t_pts,
+                                                                    const uint8_t* __restrict__ keep, int* __restrict__ overflow)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int ns = *sel_n, n0 = *dst.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ns; base += TRK_THREADS) {
+        const int i = base + threadIdx.x;
+        const bool f = i < ns && keep[i];
+        const uint32_t m = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) warp_sums[warp] = __popc(m);
+        __syncthreads();
+        int woff = 0, total = 0;
+        for (int k = 0; k < TRK_THREADS / 32; ++k) { const int s = warp_sums[k]; if (k < warp) woff += s; total += s; }
+        if (f) {
+            const int o = n0 + carry + woff + __popc(m & ((1u << lane) - 1));
+            if (o < cap) {
+                const int j = sel[i];
+                dst.idx[o] = src.idx[j]; dst.xy[2 * o] = t_pts[2 * i]; dst.xy[2 * o + 1] = t_pts[2 * i + 1]; dst.resp[o] = src.resp[j];
+                const uint4* s = (const uint4*)(src.desc + (size_t)j * 32);
+                uint4* d = (uint4*)(dst.desc + (size_t)o * 32);
+                d[0] = s[0]; d[1] = s[1];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (n0 + carry > cap) *overflow = 1;
+        *dst.n = min(n0 + carry, cap);
+    }
+}
+
+// sort a map by index into `out` (rank by counting: indices are unique, n is a few thousand at most)
+__global__ void __launch_bounds__(TRK_THREADS) k_trk_sort(trk_map m, trk_map out, int cap)
+{
+    const int n = min(*m.n, cap);
+    for (int i = threadIdx.x; i < n; i += TRK_THREADS) {
+        const int key = m.idx[i];
+        int r = 0;
+        for (int j = 0; j < n; ++j) r += m.idx[j] < key;
+        out.idx[r] = key; out.xy[2 * r] = m.xy[2 * i]; out.xy[2 * r + 1] = m.xy[2 * i + 1]; out.resp[r] = m.resp[i];
+        const uint4* s = (const uint4*)(m.desc + (size_t)i * 32);
+        uint4* d = (uint4*)(out.desc + (size_t)r * 32);
+        d[0] = s[0]; d[1] = s[1];
+    }
+    if (threadIdx.x == 0) *out.n = n;
+}
+
+static inline size_t trk_al(size_t v) { return (v + 255) / 256 * 256; }
+
+extern "C" zs_status zs_tracker_create(zs_context* ctx, const zs_tracker_options* opt, zs_tracker** out)
+{
+    ZS_REQUIRE(ctx && opt && out, "null argument");
+    ZS_REQUIRE(opt->width > 0 && opt->height > 0 && opt->cell_w > 0 && opt->cell_h > 0, "bad geometry");
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    ZS_REQUIRE((opt->width / opt->cell_w) * (opt->height / opt->cell_h) > 0, "cells larger than the image");
+    zs_tracker* t = (zs_tracker*)calloc(1, sizeof(zs_tracker));
+    t->ctx = ctx; t->opt = *opt;
+    t->gw = opt->width / opt->cell_w; t->gh = opt->height / opt->cell_h; t->cells = t->gw * t->gh;
+    // a camera's map holds at most one keypoint per cell from its own detections plus the ones tracked over from the
+    // other camera; twice the cell count is a generous bound, overflow is reported
+    t->cap = opt->capacity > 0 ? opt->capacity : 2 * t->cells + 64;
+    zs_status st = zs_pyramid_create(ctx, opt->width, opt->height, 4, opt->klt_win_w, opt->klt_win_h, opt->klt_max_level, &t->pyr);
+    if (st != ZS_OK) { free(t); return st; }
+    const size_t cap = t->cap, cells = t->cells;
+    size_t off = 0;
+    size_t o_map[5][5];
+    for (int m = 0; m < 5; ++m) {
+        o_map[m][0] = off; off += trk_al(sizeof(int) * cap);
+        o_map[m][1] = off; off += trk_al(sizeof(float) * 2 * cap);
+        o_map[m][2] = off; off += trk_al(sizeof(float) * cap);
+        o_map[m][3] = off; off += trk_al(32 * cap);
+        o_map[m][4] = off; off += 256;
+    }
+#define TCARVE(name, bytes) const size_t o_##name = off; off += trk_al(bytes);
+    TCARVE(slots, sizeof(int) * 16) TCARVE(t_pts, sizeof(float) * 4 * cap) TCARVE(t_status, 2 * cap) TCARVE(t_err, sizeof(float) * 2 * cap)
+    TCARVE(t_keep, 2 * cap) TCARVE(occ, cells) TCARVE(raw_xy, sizeof(float) * 2 * cells) TCARVE(raw_resp, sizeof(float) * cells)
+    TCARVE(raw_n, 256) TCARVE(det_xy, sizeof(float) * 2 * cells) TCARVE(det_resp, sizeof(float) * cells) TCARVE(det_n, 256)
+    TCARVE(det_desc, 32 * cells) TCARVE(sel, sizeof(int) * cap) TCARVE(sel_n, 256) TCARVE(sel_pts, sizeof(float) * 2 * cap)
+    TCARVE(next_index, 256) TCARVE(overflow, 256)
+#undef TCARVE
+    cudaError_t e = cudaMalloc((void**)&t->dev, off);
+    if (e != cudaSuccess) { zs_pyramid_destroy(t->pyr); free(t); return zs_cuda_fail(e, "cudaMalloc(tracker)", __FILE__, __LINE__); }
+    t->dev_bytes = off;
+    e = cudaMemsetAsync(t->dev, 0, off, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(t->dev); zs_pyramid_destroy(t->pyr); free(t); return zs_cuda_fail(e, "cudaMemset(tracker)", __FILE__, __LINE__); }
+    trk_map* maps[5] = { &t->prev[0], &t->prev[1], &t->cur[0], &t->cur[1], &t->tmp };
+    for (int m = 0; m < 5; ++m) {
+        maps[m]->idx = (int*)(t->dev + o_map[m][0]); maps[m]->xy = (float*)(t->dev + o_map[m][1]);
+        maps[m]->resp = (float*)(t->dev + o_map[m][2]); maps[m]->desc = t->dev + o_map[m][3]; maps[m]->n = (int*)(t->dev + o_map[m][4]);
+    }
+#define TBIND(name, type) t->name = (type*)(t->dev + o_##name);
+    TBIND(slots, int) TBIND(t_pts, float) TBIND(t_status, uint8_t) TBIND(t_err, float) TBIND(t_keep, uint8_t) TBIND(occ, uint8_t)
+    TBIND(raw_xy, float) TBIND(raw_resp, float) TBIND(raw_n, int) TBIND(det_xy, float) TBIND(det_resp, float) TBIND(det_n, int)
+    TBIND(det_desc, uint8_t) TBIND(sel, int) TBIND(sel_n, int) TBIND(sel_pts, float) TBIND(next_index, int) TBIND(overflow, int)
+#undef TBIND
+    if (opt->first_index > 0) {
+        const int fi = opt->first_index;
+        e = cudaMemcpyAsync(t->next_index, &fi, sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { cudaFree(t->dev); zs_pyramid_destroy(t->pyr); free(t); return zs_cuda_fail(e, "tracker init", __FILE__, __LINE__); }
+    }
+    *out = t;
+    return ZS_OK;
+}
+
+extern "C" void zs_tracker_destroy(zs_tracker* t)
+{
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    if (t->pyr) zs_pyramid_destroy(t->pyr);
+    if (t->dev) cudaFree(t->dev);
+    free(t);
+}
+
+extern "C" int zs_tracker_capacity(const zs_tracker* t) { return t ? t->cap : 0; }
+
+// detection of one camera behind the occupancy of its current map (keypoint_tracker.cpp:53-57 / 69-73)
+static zs_status trk_detect(zs_tracker* t, int cam, int slot)
+{
+    zs_context* ctx = t->ctx;
+    const zs_tracker_options& o = t->opt;
+    k_trk_occupancy<<<1, TRK_THREADS, 0, ctx->stream>>>(t->cur[cam], t->cap, t->gw, t->gh, o.cell_w, o.cell_h, t->occ);
+    ZS_LAUNCH_CHECK(ctx);
+    zs_status st = zs_fast_grid_detect(ctx, t->pyr, slot, 1, o.cell_w, o.cell_h, o.fast_threshold, t->occ, t->raw_xy, t->raw_resp, t->raw_n,
+                                       t->cells);
+    if (st != ZS_OK) return st;
+    if ((st = zs_orb_compute(ctx, t->pyr, slot, 1, t->raw_xy, t->raw_resp, nullptr, t->raw_n, t->cells, t->det_xy, t->det_resp, nullptr,
+                             t->det_n, t->det_desc)) != ZS_OK) return st;
+    k_trk_append_detected<<<1, TRK_THREADS, 0, ctx->stream>>>(t->cur[cam], t->cap, t->det_xy, t->det_resp, t->det_desc, t->det_n, t->next_index,
+                                                              t->overflow);
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}
+
+// stereo track of the keypoints of camera `from` that camera `to` lacks (keypoint_tracker.cpp:59-67 / 75-83)
+static zs_status trk_stereo(zs_tracker* t, int from, int to, int slot_from, int slot_to, const zs_lk_params* prm, int to_sorted_all,
+                            const int* d_to_sorted)
+{
+    zs_context* ctx = t->ctx;
+    k_trk_unmatched<<<1, TRK_THREADS, 0, ctx->stream>>>(t->cur[from], t->cur[to], to_sorted_all, d_to_sorted, t->cap, t->sel, t->sel_n, t->sel_pts);
+    ZS_LAUNCH_CHECK(ctx);
+    const int hs[2] = { slot_from, slot_to };
+    ZS_CUDA(cudaMemcpyAsync(t->slots + 8, hs, sizeof(hs), cudaMemcpyHostToDevice, ctx->stream));
+    zs_status st = zs_klt_launch(ctx, t->pyr, t->slots + 8, t->slots + 9, t->sel_pts, t->t_pts, t->sel_n, nullptr, 1, t->cap, prm, t->t_status,
+                                 t->t_err, 1, t->opt.klt_threshold, t->t_keep);
+    if (st != ZS_OK) return st;
+    k_trk_append_tracked<<<1, TRK_THREADS, 0, ctx->stream>>>(t->cur[from], t->cur[to], t->cap, t->sel, t->sel_n, t->t_pts, t->t_keep, t->overflow);
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}
+
+extern "C" zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, const uint8_t* right, size_t pitch,
+                                           const zs_tracker_results* res)
+{
+    ZS_REQUIRE(t && left && right && res, "null argument");
+    ZS_REQUIRE(res->cap >= t->cap, "results.cap must be at least zs_tracker_capacity()");
+    zs_context* ctx = t->ctx;
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    const zs_tracker_options& o = t->opt;
+    const int cap = t->cap;
+    const int cs = (int)(t->frame & 1) * 2, ps = 2 - cs;          // pyramid slots of the current / previous stereo frame
+    zs_status st;
+    if ((st = zs_pyramid_upload(ctx, t->pyr, left, pitch, pitch * o.height, cs, 1, 1)) != ZS_OK) return st;
+    if ((st = zs_pyramid_upload(ctx, t->pyr, right, pitch, pitch * o.height, cs + 1, 1, 1)) != ZS_OK) return st;
+    if ((st = zs_pyramid_build(ctx, t->pyr, cs, 2)) != ZS_OK) return st;
+    zs_lk_params prm;
+    prm.win_w = o.klt_win_w; prm.win_h = o.klt_win_h; prm.max_level = o.klt_max_level; prm.max_iters = 99; prm.epsilon = 0.001;
+    prm.flags = ZS_LK_GET_MIN_EIGENVALS; prm.min_eig_threshold = 1e-4;
+    // 1. temporal tracks of both cameras (:47-51); frame 0 has no previous keypoints (n = 0)
+    {
+        const int hs[4] = { ps, ps + 1, cs, cs + 1 };
+        ZS_CUDA(cudaMemcpyAsync(t->slots, hs, sizeof(hs), cudaMemcpyHostToDevice, ctx->stream));
+        // the two maps' xy / n arrays are separate allocations: one job per launch keeps the kernel interface simple
+        for (int cam = 0; cam < 2; ++cam) {
+            if ((st = zs_klt_launch(ctx, t->pyr, t->slots + cam, t->slots + 2 + cam, t->prev[cam].xy, t->t_pts + (size_t)cam * cap * 2,
+                                    t->prev[cam].n, nullptr, 1, cap, &prm, t->t_status + (size_t)cam * cap, t->t_err + (size_t)cam * cap, 1,
+                                    o.klt_threshold, t->t_keep + (size_t)cam * cap)) != ZS_OK) return st;
+        }
+        k_trk_compact<<<2, TRK_THREADS, 0, ctx->stream>>>(t->prev[0], t->prev[1], t->cur[0], t->cur[1], t->t_pts, t->t_keep, cap);
+        ZS_LAUNCH_CHECK(ctx);
+    }
+    // 2. new left keypoints in the free cells (:53-57)
+    if ((st = trk_detect(t, 0, cs)) != ZS_OK) return st;
+    // 3. left keypoints the right camera lacks: L -> R (:59-67); the right map holds only its temporal tracks, sorted
+    if ((st = trk_stereo(t, 0, 1, cs, cs + 1, &prm, 1, nullptr)) != ZS_OK) return st;
+    // 4. new right keypoints behind the occupancy of everything the right map now holds (:69-73)
+    if ((st = trk_detect(t, 1, cs + 1)) != ZS_OK) return st;
+    // 5. right keypoints the left camera lacks: R -> L (:75-83); the left map (tracks + detections) is still sorted
+    if ((st = trk_stereo(t, 1, 0, cs + 1, cs, &prm, 1, nullptr)) != ZS_OK) return st;
+    // 6. key order for the output and for the next frame's searches; the sorted maps become `prev`
+    for (int cam = 0; cam < 2; ++cam) {
+        k_trk_sort<<<1, TRK_THREADS, 0, ctx->stream>>>(t->cur[cam], t->prev[cam], cap);
+        ZS_LAUNCH_CHECK(ctx);
+    }
+    // results
+    int h_n[2] = { 0, 0 }, h_over = 0, h_next = 0;
+    ZS_CUDA(cudaMemcpyAsync(&h_n[0], t->prev[0].n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(&h_n[1], t->prev[1].n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(&h_over, t->overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(&h_next, t->next_index, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    for (int cam = 0; cam < 2; ++cam) {
+        const size_t c = (size_t)cap;
+        if (res->index[cam]) ZS_CUDA(cudaMemcpyAsync(res->index[cam], t->prev[cam].idx, sizeof(int) * c, cudaMemcpyDeviceToHost, ctx->stream));
+        if (res->xy[cam]) ZS_CUDA(cudaMemcpyAsync(res->xy[cam], t->prev[cam].xy, sizeof(float) * 2 * c, cudaMemcpyDeviceToHost, ctx->stream));
+        if (res->response[cam]) ZS_CUDA(cudaMemcpyAsync(res->response[cam], t->prev[cam].resp, sizeof(float) * c, cudaMemcpyDeviceToHost, ctx->stream));
+        if (res->desc[cam]) ZS_CUDA(cudaMemcpyAsync(res->desc[cam], t->prev[cam].desc, 32 * c, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (res->n) { res->n[0] = h_n[0]; res->n[1] = h_n[1]; }
+    if (res->next_index) *res->next_index = h_next;
+    t->frame++;
+    if (h_over) { zs_set_error("tracker capacity %d exceeded", cap); return ZS_ERR_CAPACITY; }
+    return ZS_OK;
+}

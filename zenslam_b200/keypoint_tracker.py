@@ -102,3 +102,68 @@ class keypoint_tracker:
                     f0.add(a); f1.add(b)
             return f0, f1
         return kp0, kp1
+
+
+class device_keypoint_tracker:
+    """zs_tracker: the same track() flow with the keypoint maps, the previous pyramids and keypoint::index_next kept on the
+    device -- one C-ABI call per stereo frame instead of seven.  GRID / FAST / ORB, filter_epipolar off (see the module
+    docstring for what stays on the host)."""
+
+    def __init__(self, options: slam_options, ctx, width: int, height: int, first_index: int = 0, capacity: int = 0):
+        import ctypes as C
+
+        from ._lib import TrackerOptions, check, lib
+        det, trk = options.detection, options.tracking
+        if det.algorithm != "GRID" or det.feature_detector != "FAST" or det.descriptor != "ORB":
+            raise NotImplementedError("the device tracker implements algorithm GRID with feature FAST and descriptor ORB")
+        if trk.filter_epipolar:
+            raise NotImplementedError("tracking.filter_epipolar is a CPU RANSAC in the reference; switch it off or filter the result")
+        self._ctx, self.width, self.height = ctx, width, height
+        o = TrackerOptions(width, height, det.cell_size[0], det.cell_size[1], det.fast_threshold, trk.klt_window_size[0],
+                           trk.klt_window_size[1], trk.klt_max_level, trk.klt_threshold, capacity, first_index)
+        h = C.c_void_p()
+        check(lib().zs_tracker_create(ctx._h, C.byref(o), C.byref(h)))
+        self._h = h
+        self.cap = lib().zs_tracker_capacity(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            from ._lib import lib
+            lib().zs_tracker_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def track(self, left, right):
+        """-> (keypoints_0, keypoints_1): keypoint_map per camera, like keypoint_tracker.track; advances keypoint.index_next"""
+        import ctypes as C
+
+        import numpy as np
+
+        from ._lib import TrackerResults, check, lib
+        from .types import keypoint
+        left = np.ascontiguousarray(left, np.uint8); right = np.ascontiguousarray(right, np.uint8)
+        assert left.shape == right.shape == (self.height, self.width)
+        cap = self.cap
+        n = np.zeros(2, np.int32); nxt = np.zeros(1, np.int32)
+        idx = [np.empty(cap, np.int32) for _ in range(2)]; xy = [np.empty((cap, 2), np.float32) for _ in range(2)]
+        resp = [np.empty(cap, np.float32) for _ in range(2)]; desc = [np.empty((cap, 32), np.uint8) for _ in range(2)]
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        r = TrackerResults()
+        r.cap = cap; r.n = p(n).value; r.next_index = p(nxt).value
+        for c in range(2):
+            r.index[c] = p(idx[c]).value; r.xy[c] = p(xy[c]).value; r.response[c] = p(resp[c]).value; r.desc[c] = p(desc[c]).value
+        check(lib().zs_tracker_track_host(self._h, p(left), p(right), self.width, C.byref(r)))
+        keypoint.index_next = int(nxt[0])
+        out = []
+        for c in range(2):
+            m = keypoint_map()
+            for i in range(int(n[c])):
+                m[int(idx[c][i])] = keypoint(pt=(float(xy[c][i, 0]), float(xy[c][i, 1])), response=float(resp[c][i]),
+                                             index=int(idx[c][i]), descriptor=desc[c][i].copy())
+            out.append(m)
+        return out[0], out[1]
