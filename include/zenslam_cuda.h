@@ -330,7 +330,7 @@ typedef struct {
     int cell_w, cell_h, fast_threshold;            /* detection.cell_size, detection.fast_threshold */
     int klt_win_w, klt_win_h, klt_max_level;       /* tracking.klt_window_size, tracking.klt_max_level */
     double klt_threshold;                          /* tracking.klt_threshold */
-    int capacity;                                  /* keypoints per camera; 0 = 2 x cells + 64 */
+    int capacity;                                  /* keypoints per camera; 0 = 4 x cells + 64 */
     int first_index;                               /* keypoint::index_next when the sequence starts */
 } zs_tracker_options;
 typedef struct {                                   /* HOST pointers; arrays sized cap >= zs_tracker_capacity(); any may be NULL */

@@ -208,9 +208,10 @@ extern "C" zs_status zs_tracker_create(zs_context* ctx, const zs_tracker_options
     zs_tracker* t = (zs_tracker*)calloc(1, sizeof(zs_tracker));
     t->ctx = ctx; t->opt = *opt;
     t->gw = opt->width / opt->cell_w; t->gh = opt->height / opt->cell_h; t->cells = t->gw * t->gh;
-    // a camera's map holds at most one keypoint per cell from its own detections plus the ones tracked over from the
-    // other camera; twice the cell count is a generous bound, overflow is reported
-    t->cap = opt->capacity > 0 ? opt->capacity : 2 * t->cells + 64;
+    // a camera's map holds its own detections (at most one per cell and frame) plus the keypoints tracked over from the
+    // other camera, and tracked keypoints may share a cell: in steady state it settles near twice the cell count; the
+    // default leaves a factor of two above that, and overflow is reported, not hidden
+    t->cap = opt->capacity > 0 ? opt->capacity : 4 * t->cells + 64;
     zs_status st = zs_pyramid_create(ctx, opt->width, opt->height, 4, opt->klt_win_w, opt->klt_win_h, opt->klt_max_level, &t->pyr);
     if (st != ZS_OK) { free(t); return st; }
     const size_t cap = t->cap, cells = t->cells;
