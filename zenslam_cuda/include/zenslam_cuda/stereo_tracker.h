@@ -1,0 +1,40 @@
+#pragma once
+
+#include <array>
+#include <memory>
+
+#include <opencv2/core.hpp>
+
+#include "zenslam/detection/detection_options.h"
+#include "zenslam/tracking_options.h"
+#include "zenslam/types/keypoint.h"
+#include "zenslam/types/map.h"
+
+struct zs_tracker;
+
+namespace zenslam::cuda
+{
+    /** keypoint_tracker::track (zenslam_core/source/tracking/keypoint_tracker.cpp:41-105) with its frame-to-frame state
+     *  -- the previous pyramids, both keypoint maps, keypoint::index_next -- kept on the GPU: one device call per stereo
+     *  frame.  Algorithm GRID, feature FAST, descriptor ORB (anything else throws at construction).  What the reference
+     *  does around the KLT / detection calls with CPU-only inputs stays with the caller: the pose-predicted initial flow,
+     *  assign_landmark_indices and filter_epipolar (cv::findFundamentalMat) are applied to the returned maps.
+     *  keypoint_tracker::track is not a virtual seam, so this class is an opt-in replacement of its body. */
+    class stereo_tracker final
+    {
+    public:
+        /** `detection` / `tracking` = slam_options::detection / ::tracking (all_options.h:111-137) */
+        stereo_tracker(const detection_options& detection, const tracking_options& tracking, cv::Size image_size);
+        ~stereo_tracker();
+
+        stereo_tracker(const stereo_tracker&)            = delete;
+        stereo_tracker& operator=(const stereo_tracker&) = delete;
+
+        /** undistorted grayscale images of the new stereo frame -> the two keypoint maps of that frame */
+        [[nodiscard]] auto track(const cv::Mat& undistorted_0, const cv::Mat& undistorted_1) -> std::array<map<keypoint>, 2>;
+
+    private:
+        zs_tracker* _tracker  = nullptr;
+        int         _capacity = 0;
+    };
+}

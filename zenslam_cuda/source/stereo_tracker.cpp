@@ -1,0 +1,101 @@
+#include "zenslam_cuda/stereo_tracker.h"
+
+#include <stdexcept>
+#include <vector>
+
+#include "context.h"
+
+zenslam::cuda::stereo_tracker::stereo_tracker(const detection_options& detection, const tracking_options& tracking, const cv::Size image_size)
+{
+    if (detection.algorithm != detection_algorithm::GRID || detection.feature_detector != feature_type::FAST || detection.descriptor != descriptor_type::ORB)
+        throw std::invalid_argument("stereo_tracker: algorithm GRID with feature FAST and descriptor ORB runs on the GPU");
+
+    if (detail::context() == nullptr)
+        throw std::runtime_error("stereo_tracker: no sm_100 device (there is no CPU fallback in this backend)");
+
+    zs_tracker_options tracker_options { };
+    tracker_options.width          = image_size.width;
+    tracker_options.height         = image_size.height;
+    tracker_options.cell_w         = detection.cell_size.width;
+    tracker_options.cell_h         = detection.cell_size.height;
+    tracker_options.fast_threshold = detection.fast_threshold;
+    tracker_options.klt_win_w      = tracking.klt_window_size.width;
+    tracker_options.klt_win_h      = tracking.klt_window_size.height;
+    tracker_options.klt_max_level  = tracking.klt_max_level;
+    tracker_options.klt_threshold  = tracking.klt_threshold;
+    tracker_options.capacity       = 0;
+    tracker_options.first_index    = static_cast<int>(keypoint::index_next);
+
+    std::scoped_lock lock { detail::context_mutex() };
+
+    detail::check(zs_tracker_create(detail::context(), &tracker_options, &_tracker), "zs_tracker_create");
+
+    _capacity = zs_tracker_capacity(_tracker);
+}
+
+zenslam::cuda::stereo_tracker::~stereo_tracker()
+{
+    std::scoped_lock lock { detail::context_mutex() };
+
+    zs_tracker_destroy(_tracker);
+}
+
+auto zenslam::cuda::stereo_tracker::track(const cv::Mat& undistorted_0, const cv::Mat& undistorted_1) -> std::array<map<keypoint>, 2>
+{
+    CV_Assert(undistorted_0.type() == CV_8UC1 && undistorted_1.type() == CV_8UC1 && undistorted_0.size() == undistorted_1.size());
+
+    cv::Mat image_0 = undistorted_0;
+    cv::Mat image_1 = undistorted_1;
+
+    if (image_0.step != image_1.step)
+    {
+        image_0 = image_0.clone();
+        image_1 = image_1.clone();
+    }
+
+    const auto capacity = static_cast<size_t>(_capacity);
+
+    int                count[2]   = { 0, 0 };
+    int                index_next = 0;
+    std::vector<int>   index[2]   = { std::vector<int>(capacity), std::vector<int>(capacity) };
+    std::vector<float> xy[2]      = { std::vector<float>(2 * capacity), std::vector<float>(2 * capacity) };
+    std::vector<float> response[2] = { std::vector<float>(capacity), std::vector<float>(capacity) };
+    cv::Mat            descriptors[2] = { cv::Mat(_capacity, 32, CV_8UC1), cv::Mat(_capacity, 32, CV_8UC1) };
+
+    zs_tracker_results results { };
+    results.cap        = _capacity;
+    results.n          = count;
+    results.next_index = &index_next;
+
+    for (auto camera = 0; camera < 2; ++camera)
+    {
+        results.index[camera]    = index[camera].data();
+        results.xy[camera]       = xy[camera].data();
+        results.response[camera] = response[camera].data();
+        results.desc[camera]     = descriptors[camera].data;
+    }
+
+    {
+        std::scoped_lock lock { detail::context_mutex() };
+
+        detail::check(zs_tracker_track_host(_tracker, image_0.data, image_1.data, image_0.step, &results), "zs_tracker_track_host");
+    }
+
+    // new keypoints took sequential indices on the device, exactly as keypoint::index_next++ would have handed them out
+    keypoint::index_next = static_cast<size_t>(index_next);
+
+    std::array<map<keypoint>, 2> keypoints { };
+
+    for (auto camera = 0; camera < 2; ++camera)
+    {
+        for (auto i = 0; i < count[camera]; ++i)
+        {
+            // FAST keypoints: size 7, angle -1, octave 0, class_id -1 (tracked copies keep everything but pt)
+            const cv::KeyPoint keypoint_cv { xy[camera][2 * i], xy[camera][2 * i + 1], 7.0f, -1.0f, response[camera][i], 0, -1 };
+
+            keypoints[camera].add(keypoint { keypoint_cv, static_cast<size_t>(index[camera][i]), descriptors[camera].row(i).clone() });
+        }
+    }
+
+    return keypoints;
+}
