@@ -432,14 +432,16 @@ extern "C" zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, c
     if ((st = zs_pyramid_upload(ctx, t->pyr, left, pitch, pitch * o.height, cs, 1, 1)) != ZS_OK) return st;
     if ((st = zs_pyramid_upload(ctx, t->pyr, right, pitch, pitch * o.height, cs + 1, 1, 1)) != ZS_OK) return st;
     if ((st = trk_frame(t, par)) != ZS_OK) return st;
-    // results
+    // results: the four counters first, then only the live part of every array
     int h_n[2] = { 0, 0 }, h_over = 0, h_next = 0;
     ZS_CUDA(cudaMemcpyAsync(&h_n[0], t->prev[0].n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaMemcpyAsync(&h_n[1], t->prev[1].n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaMemcpyAsync(&h_over, t->overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaMemcpyAsync(&h_next, t->next_index, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int cam = 0; cam < 2; ++cam) {
-        const size_t c = (size_t)cap;
+        const size_t c = (size_t)(h_n[cam] < cap ? h_n[cam] : cap);
+        if (c == 0) continue;
         if (res->index[cam]) ZS_CUDA(cudaMemcpyAsync(res->index[cam], t->prev[cam].idx, sizeof(int) * c, cudaMemcpyDeviceToHost, ctx->stream));
         if (res->xy[cam]) ZS_CUDA(cudaMemcpyAsync(res->xy[cam], t->prev[cam].xy, sizeof(float) * 2 * c, cudaMemcpyDeviceToHost, ctx->stream));
         if (res->response[cam]) ZS_CUDA(cudaMemcpyAsync(res->response[cam], t->prev[cam].resp, sizeof(float) * c, cudaMemcpyDeviceToHost, ctx->stream));
