@@ -342,6 +342,10 @@ typedef struct {                                   /* HOST pointers; arrays size
 ZS_API zs_status zs_tracker_create(zs_context* ctx, const zs_tracker_options* opt, zs_tracker** out);
 ZS_API void zs_tracker_destroy(zs_tracker* t);
 ZS_API int zs_tracker_capacity(const zs_tracker* t);
+/* optional, before a track call: predicted positions in the NEXT frame for some of camera's current keypoints, by
+ * keypoint index (strictly ascending) -- the landmark projections keypoint_tracker.cpp:361-373 feeds to
+ * OPTFLOW_USE_INITIAL_FLOW.  Keypoints without a prediction start from their own position.  Consumed by the next call. */
+ZS_API zs_status zs_tracker_set_predictions(zs_tracker* t, int camera, const int* index, const float* xy, int n);
 ZS_API zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, const uint8_t* right, size_t pitch,
                                        const zs_tracker_results* res);
 

@@ -232,6 +232,51 @@ def test_device_tracker_equals_track_mirror(ctx, w, h, cell):
     dev_trk.close()
 
 
+def test_device_tracker_with_predicted_initial_flow(ctx):
+    """temporal tracks that start from host-supplied predictions (landmark projections, keypoint_tracker.cpp:361-373):
+    zs_tracker_set_predictions against the mirror's predicted_points callable, frame by frame"""
+    import dataclasses
+    from zenslam_b200 import detection_options, keypoint, slam_options, tracking_options
+    from zenslam_b200.keypoint_tracker import device_keypoint_tracker, keypoint_tracker, stereo_frame
+    from zenslam_b200.tracking import create_cuda_pyr_lk
+    w, h, frames = 376, 240, 5
+    seq, _ = syn.stereo_sequence(w, h, frames, 1055, subpixel=True)
+    opts = slam_options(matcher="KNN", detection=detection_options(), tracking=tracking_options(filter_epipolar=False))
+
+    def predict(kp, cam):                        # a third of the keypoints carry a prediction, offset from their position
+        return (kp.pt[0] + 1.5 * (cam + 1), kp.pt[1] - 1.0) if kp.index % 3 == 0 else None
+
+    def predicted_points(keypoints, cam):
+        return np.array([predict(k, cam) or k.pt for k in keypoints], np.float32)
+
+    keypoint.index_next = 0
+    host = keypoint_tracker(opts, ctx, create_cuda_pyr_lk(ctx), predicted_points=predicted_points)
+    prev = stereo_frame((seq[0, 0], seq[0, 1]))
+    want = []
+    for t in range(frames):
+        cur = stereo_frame((seq[t, 0], seq[t, 1]))
+        k0, k1 = host.track(prev, cur)
+        want.append((k0, k1))
+        prev = dataclasses.replace(cur, keypoints=(k0, k1))
+    keypoint.index_next = 0
+    dev_trk = device_keypoint_tracker(opts, ctx, w, h)
+    last = ({}, {})
+    for t in range(frames):
+        for cam in range(2):
+            dev_trk.set_predictions(cam, {i: predict(k, cam) for i, k in last[cam].items() if predict(k, cam)})
+        g = dev_trk.track(seq[t, 0], seq[t, 1])
+        for cam in range(2):
+            assert list(g[cam]) == sorted(want[t][cam]), (t, cam)
+            assert all(g[cam][i].pt == want[t][cam][i].pt for i in g[cam]), (t, cam)
+        last = g
+    # the predictions changed something: without them the second frame differs
+    keypoint.index_next = 0
+    plain = device_keypoint_tracker(opts, ctx, w, h)
+    p = [plain.track(seq[t, 0], seq[t, 1]) for t in range(2)][1]
+    assert any(p[0][i].pt != want[1][0][i].pt for i in set(p[0]) & set(want[1][0])) or set(p[0]) != set(want[1][0])
+    dev_trk.close(); plain.close()
+
+
 def test_lk_host_pyramid_cache(ctx):
     """the LK host entries keep the pyramids of the frames they saw (content-keyed): repeated frames hit, a frame whose
     bytes changed in place misses, and results never depend on the cache state"""

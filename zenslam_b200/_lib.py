@@ -122,6 +122,7 @@ SIGNATURES = {
     "zs_tracker_create": (I, [P, C.POINTER(TrackerOptions), C.POINTER(P)]),
     "zs_tracker_destroy": (None, [P]),
     "zs_tracker_capacity": (I, [P]),
+    "zs_tracker_set_predictions": (I, [P, I, P, P, I]),
     "zs_tracker_track_host": (I, [P, P, P, Z, C.POINTER(TrackerResults)]),
     "zs_frontend_create": (I, [P, C.POINTER(FrontendOptions), C.POINTER(P)]),
     "zs_frontend_destroy": (None, [P]),

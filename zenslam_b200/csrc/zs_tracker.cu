@@ -41,6 +41,7 @@ struct zs_tracker {
     float* raw_xy; float* raw_resp; int* raw_n;   // grid candidates before ORB's border filter [cells]
     float* det_xy; float* det_resp; int* det_n; uint8_t* det_desc;   // after ORB::compute
     int* sel; int* sel_n; float* sel_pts;         // positions of the entries to stereo-track, their count, their points
+    int* pred_idx; float* pred_xy; int* pred_n;   // [2][cap], [2][cap][2], [2]: initial-flow predictions for the next frame, by index
     int* marks;                  // [2][2] per camera: map sizes before the appends that start a new sorted run (see k_trk_sort)
     int* next_index;             // device copy of keypoint::index_next
     int* overflow;               // set when a map would exceed cap
@@ -78,6 +79,29 @@ __global__ void __launch_bounds__(TRK_THREADS) k_trk_compact(trk_map p0, trk_map
         __syncthreads();
     }
     if (threadIdx.x == 0) *c.n = carry;
+}
+
+// initial flow of the temporal tracks (keypoint_tracker.cpp:361-373): the predicted position where the host supplied one
+// for the keypoint's index (landmark projection), the keypoint's own position otherwise; the predictions are consumed
+__global__ void __launch_bounds__(TRK_THREADS) k_trk_init_flow(trk_map p0, trk_map p1, int cap, const int* __restrict__ pred_idx,
+                                                               const float* __restrict__ pred_xy, int* __restrict__ pred_n,
+                                                               float* __restrict__ t_pts)
+{
+    const trk_map p = blockIdx.x ? p1 : p0;
+    const int* pi = pred_idx + (size_t)blockIdx.x * cap;
+    const float* px = pred_xy + (size_t)blockIdx.x * cap * 2;
+    float* out = t_pts + (size_t)blockIdx.x * cap * 2;
+    const int n = min(*p.n, cap), np = min(pred_n[blockIdx.x], cap);
+    for (int i = threadIdx.x; i < n; i += TRK_THREADS) {
+        const int key = p.idx[i];
+        int lo = 0, hi = np;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (pi[mid] < key) lo = mid + 1; else hi = mid; }
+        const bool hit = lo < np && pi[lo] == key;
+        out[2 * i] = hit ? px[2 * lo] : p.xy[2 * i];
+        out[2 * i + 1] = hit ? px[2 * lo + 1] : p.xy[2 * i + 1];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) pred_n[blockIdx.x] = 0;
 }
 
 // occupied[int(pt.x) / cw][int(pt.y) / ch] (keypoint_detector_grid.cpp:47-64: truncating cast, then integer division)
@@ -260,6 +284,7 @@ extern "C" zs_status zs_tracker_create(zs_context* ctx, const zs_tracker_options
     TCARVE(raw_n, 256) TCARVE(det_xy, sizeof(float) * 2 * cells) TCARVE(det_resp, sizeof(float) * cells) TCARVE(det_n, 256)
     TCARVE(det_desc, 32 * cells) TCARVE(sel, sizeof(int) * cap) TCARVE(sel_n, 256) TCARVE(sel_pts, sizeof(float) * 2 * cap)
     TCARVE(next_index, 256) TCARVE(overflow, 256) TCARVE(marks, 256)
+    TCARVE(pred_idx, sizeof(int) * 2 * cap) TCARVE(pred_xy, sizeof(float) * 4 * cap) TCARVE(pred_n, 256)
 #undef TCARVE
     cudaError_t e = cudaMalloc((void**)&t->dev, off);
     if (e != cudaSuccess) { zs_pyramid_destroy(t->pyr); free(t); return zs_cuda_fail(e, "cudaMalloc(tracker)", __FILE__, __LINE__); }
@@ -276,7 +301,7 @@ extern "C" zs_status zs_tracker_create(zs_context* ctx, const zs_tracker_options
 #define TBIND(name, type) t->name = (type*)(t->dev + o_##name);
     TBIND(slots, int) TBIND(t_pts, float) TBIND(t_status, uint8_t) TBIND(t_err, float) TBIND(t_keep, uint8_t) TBIND(occ, uint8_t)
     TBIND(raw_xy, float) TBIND(raw_resp, float) TBIND(raw_n, int) TBIND(det_xy, float) TBIND(det_resp, float) TBIND(det_n, int)
-    TBIND(det_desc, uint8_t) TBIND(sel, int) TBIND(sel_n, int) TBIND(sel_pts, float) TBIND(next_index, int) TBIND(overflow, int) TBIND(marks, int)
+    TBIND(det_desc, uint8_t) TBIND(sel, int) TBIND(sel_n, int) TBIND(sel_pts, float) TBIND(next_index, int) TBIND(overflow, int) TBIND(marks, int) TBIND(pred_idx, int) TBIND(pred_xy, float) TBIND(pred_n, int)
 #undef TBIND
     {
         int hs[16];
@@ -312,6 +337,22 @@ extern "C" void zs_tracker_destroy(zs_tracker* t)
 }
 
 extern "C" int zs_tracker_capacity(const zs_tracker* t) { return t ? t->cap : 0; }
+
+extern "C" zs_status zs_tracker_set_predictions(zs_tracker* t, int camera, const int* index, const float* xy, int n)
+{
+    ZS_REQUIRE(t && (camera == 0 || camera == 1), "bad argument");
+    ZS_REQUIRE(n >= 0 && n <= t->cap && (n == 0 || (index && xy)), "bad prediction list");
+    zs_context* ctx = t->ctx;
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    for (int i = 1; i < n; ++i) ZS_REQUIRE(index[i - 1] < index[i], "prediction indices must be strictly ascending");
+    if (n > 0) {
+        ZS_CUDA(cudaMemcpyAsync(t->pred_idx + (size_t)camera * t->cap, index, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+        ZS_CUDA(cudaMemcpyAsync(t->pred_xy + (size_t)camera * t->cap * 2, xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ZS_CUDA(cudaMemcpyAsync(t->pred_n + camera, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA(cudaStreamSynchronize(ctx->stream));     // the host arrays may go away after the call
+    return ZS_OK;
+}
 
 // detection of one camera behind the occupancy of its current map (keypoint_tracker.cpp:53-57 / 69-73)
 static zs_status trk_detect(zs_tracker* t, int cam, int slot, int* d_mark)
@@ -359,8 +400,14 @@ static zs_status trk_frame_body(zs_tracker* t, int par)
     zs_lk_params prm;
     prm.win_w = o.klt_win_w; prm.win_h = o.klt_win_h; prm.max_level = o.klt_max_level; prm.max_iters = 99; prm.epsilon = 0.001;
     prm.flags = ZS_LK_GET_MIN_EIGENVALS; prm.min_eig_threshold = 1e-4;
-    // 1. temporal tracks of both cameras (:47-51), one launch with two jobs; frame 0 has no previous keypoints (n = 0)
-    if ((st = zs_klt_launch(ctx, t->pyr, sl, sl + 2, t->prev[0].xy, t->t_pts, t->prev[0].n, nullptr, 2, cap, &prm, t->t_status, t->t_err, 1,
+    // 1. temporal tracks of both cameras (:47-51, the overload with initial flow :343-434), one launch with two jobs;
+    //    frame 0 has no previous keypoints (n = 0).  OPTFLOW_USE_INITIAL_FLOW with the keypoint's own position is what the
+    //    plain call starts from, so the flag is always on and the graph is the same with and without predictions.
+    k_trk_init_flow<<<2, TRK_THREADS, 0, ctx->stream>>>(t->prev[0], t->prev[1], cap, t->pred_idx, t->pred_xy, t->pred_n, t->t_pts);
+    ZS_LAUNCH_CHECK(ctx);
+    zs_lk_params prm_init = prm;
+    prm_init.flags |= ZS_LK_USE_INITIAL_FLOW;
+    if ((st = zs_klt_launch(ctx, t->pyr, sl, sl + 2, t->prev[0].xy, t->t_pts, t->prev[0].n, nullptr, 2, cap, &prm_init, t->t_status, t->t_err, 1,
                             o.klt_threshold, t->t_keep)) != ZS_OK) return st;
     k_trk_compact<<<2, TRK_THREADS, 0, ctx->stream>>>(t->prev[0], t->prev[1], t->cur[0], t->cur[1], t->t_pts, t->t_keep, cap);
     ZS_LAUNCH_CHECK(ctx);

@@ -138,6 +138,19 @@ class device_keypoint_tracker:
         except Exception:
             pass
 
+    def set_predictions(self, camera: int, predictions: dict):
+        """{keypoint index: (x, y)} -- initial flow of the next temporal track for those keypoints (landmark projections,
+        keypoint_tracker.cpp:361-373); consumed by the next track()"""
+        import ctypes as C
+
+        import numpy as np
+
+        from ._lib import check, lib
+        keys = sorted(predictions)
+        idx = np.array(keys, np.int32); xy = np.array([predictions[k] for k in keys], np.float32).reshape(-1, 2)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(lib().zs_tracker_set_predictions(self._h, camera, p(idx), p(xy), len(keys)))
+
     def track(self, left, right):
         """-> (keypoints_0, keypoints_1): keypoint_map per camera, like keypoint_tracker.track; advances keypoint.index_next"""
         import ctypes as C

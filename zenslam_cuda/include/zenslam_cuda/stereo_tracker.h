@@ -1,6 +1,7 @@
 #pragma once
 
 #include <array>
+#include <map>
 #include <memory>
 
 #include <opencv2/core.hpp>
@@ -29,6 +30,10 @@ namespace zenslam::cuda
 
         stereo_tracker(const stereo_tracker&)            = delete;
         stereo_tracker& operator=(const stereo_tracker&) = delete;
+
+        /** optional, before track(): predicted positions in the next frame for some keypoints of `camera`, keyed by
+         *  keypoint index -- the landmark projections keypoint_tracker.cpp:361-373 uses as initial flow */
+        void set_predictions(int camera, const std::map<size_t, cv::Point2f>& predictions);
 
         /** undistorted grayscale images of the new stereo frame -> the two keypoint maps of that frame */
         [[nodiscard]] auto track(const cv::Mat& undistorted_0, const cv::Mat& undistorted_1) -> std::array<map<keypoint>, 2>;

@@ -40,6 +40,26 @@ zenslam::cuda::stereo_tracker::~stereo_tracker()
     zs_tracker_destroy(_tracker);
 }
 
+void zenslam::cuda::stereo_tracker::set_predictions(const int camera, const std::map<size_t, cv::Point2f>& predictions)
+{
+    std::vector<int>   index { };
+    std::vector<float> xy { };
+
+    index.reserve(predictions.size());
+    xy.reserve(2 * predictions.size());
+
+    for (const auto& [key, point] : predictions)       // std::map iterates in ascending key order, as the C entry requires
+    {
+        index.push_back(static_cast<int>(key));
+        xy.push_back(point.x);
+        xy.push_back(point.y);
+    }
+
+    std::scoped_lock lock { detail::context_mutex() };
+
+    detail::check(zs_tracker_set_predictions(_tracker, camera, index.data(), xy.data(), static_cast<int>(index.size())), "zs_tracker_set_predictions");
+}
+
 auto zenslam::cuda::stereo_tracker::track(const cv::Mat& undistorted_0, const cv::Mat& undistorted_1) -> std::array<map<keypoint>, 2>
 {
     CV_Assert(undistorted_0.type() == CV_8UC1 && undistorted_1.type() == CV_8UC1 && undistorted_0.size() == undistorted_1.size());
