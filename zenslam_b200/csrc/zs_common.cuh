@@ -81,6 +81,16 @@ zs_status zs_cuda_fail(cudaError_t e, const char* what, const char* file, int li
         if (!(cond)) { zs_set_error("%s:%d: %s", __FILE__, __LINE__, msg); return ZS_ERR_INVALID; } \
     } while (0)
 
+// stream-ordered temporary of one host-mirror call: freed on every exit path (the error returns of ZS_CUDA included)
+struct zs_async_buffer {
+    uint8_t* p = nullptr;
+    cudaStream_t stream;
+    explicit zs_async_buffer(cudaStream_t s) : stream(s) {}
+    ~zs_async_buffer() { if (p) cudaFreeAsync(p, stream); }
+    zs_async_buffer(const zs_async_buffer&) = delete;
+    zs_async_buffer& operator=(const zs_async_buffer&) = delete;
+};
+
 zs_status zs_scratch(zs_context* ctx, size_t bytes, void** out);
 zs_status zs_pinned(zs_context* ctx, size_t bytes, void** out);
 

@@ -200,8 +200,9 @@ static zs_status detect_grid_host(zs_context* ctx, const uint8_t* img, int width
     const size_t o_occ = 0, o_xy0 = al256(cells), o_r0 = o_xy0 + al256(sizeof(float) * 2 * cells),
                  o_n0 = o_r0 + al256(sizeof(float) * cells), o_xy = o_n0 + 256, o_r = o_xy + al256(sizeof(float) * 2 * cells),
                  o_n = o_r + al256(sizeof(float) * cells), o_desc = o_n + 256, total = o_desc + al256((size_t)cells * 32);
-    uint8_t* base;
-    ZS_CUDA(cudaMallocAsync((void**)&base, total, ctx->stream));
+    zs_async_buffer buf(ctx->stream);
+    ZS_CUDA(cudaMallocAsync((void**)&buf.p, total, ctx->stream));
+    uint8_t* base = buf.p;
     if (occupied) ZS_CUDA(cudaMemcpyAsync(base + o_occ, occupied, cells, cudaMemcpyHostToDevice, ctx->stream));
     st = zs_fast_grid_detect(ctx, p, 0, 1, cell_w, cell_h, threshold, occupied ? base + o_occ : nullptr, (float*)(base + o_xy0),
                              (float*)(base + o_r0), (int*)(base + o_n0), cells);
@@ -213,13 +214,13 @@ static zs_status detect_grid_host(zs_context* ctx, const uint8_t* img, int width
         st = zs_orb_compute(ctx, p, 0, 1, (const float*)(base + o_xy0), (const float*)(base + o_r0), nullptr,
                             (const int*)(base + o_n0), cells, (float*)(base + o_xy), (float*)(base + o_r), nullptr,
                             (int*)(base + o_n), base + o_desc);
-    if (st != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+    if (st != ZS_OK) return st;
     int n = 0;
     ZS_CUDA(cudaMemcpyAsync(&n, base + o_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaStreamSynchronize(ctx->stream));
     if (n > 0) {
         void* pin;
-        if ((st = zs_pinned(ctx, sizeof(float) * 2 * n, &pin)) != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+        if ((st = zs_pinned(ctx, sizeof(float) * 2 * n, &pin)) != ZS_OK) return st;
         ZS_CUDA(cudaMemcpyAsync(pin, base + o_xy, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
         ZS_CUDA(cudaMemcpyAsync(response, base + o_r, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
         ZS_CUDA(cudaMemcpyAsync(desc, base + o_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -227,7 +228,6 @@ static zs_status detect_grid_host(zs_context* ctx, const uint8_t* img, int width
         const float* xy = (const float*)pin;
         for (int i = 0; i < n; ++i) { x[i] = xy[2 * i]; y[i] = xy[2 * i + 1]; }
     }
-    ZS_CUDA(cudaFreeAsync(base, ctx->stream));
     *n_out = n;
     return ZS_OK;
 }
@@ -265,8 +265,9 @@ extern "C" zs_status zs_detect_keypoints_simple_host(zs_context* ctx, const uint
     const size_t o_mask = 0, o_xy0 = plane, o_r0 = o_xy0 + al256(sizeof(float) * 2 * cap), o_n0 = o_r0 + al256(sizeof(float) * cap),
                  o_xy = o_n0 + 256, o_r = o_xy + al256(sizeof(float) * 2 * cap), o_n = o_r + al256(sizeof(float) * cap),
                  o_desc = o_n + 256, total = o_desc + al256((size_t)cap * 32);
-    uint8_t* base;
-    ZS_CUDA(cudaMallocAsync((void**)&base, total, ctx->stream));
+    zs_async_buffer buf(ctx->stream);
+    ZS_CUDA(cudaMallocAsync((void**)&buf.p, total, ctx->stream));
+    uint8_t* base = buf.p;
     if (mask)
         ZS_CUDA(cudaMemcpy2DAsync(base + o_mask, width, mask, mask_pitch, width, height, cudaMemcpyHostToDevice, ctx->stream));
     st = zs_fast_detect(ctx, p, 0, 1, threshold, mask ? base + o_mask : nullptr, (float*)(base + o_xy0), (float*)(base + o_r0),
@@ -276,7 +277,6 @@ extern "C" zs_status zs_detect_keypoints_simple_host(zs_context* ctx, const uint
         ZS_CUDA(cudaMemcpyAsync(&found, base + o_n0, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         ZS_CUDA(cudaStreamSynchronize(ctx->stream));
         if (found > cap) {
-            cudaFreeAsync(base, ctx->stream);
             *n_out = found;
             zs_set_error("full-frame FAST found %d corners, capacity is %d", found, cap);
             return ZS_ERR_CAPACITY;
@@ -285,13 +285,13 @@ extern "C" zs_status zs_detect_keypoints_simple_host(zs_context* ctx, const uint
                             (const int*)(base + o_n0), cap, (float*)(base + o_xy), (float*)(base + o_r), nullptr,
                             (int*)(base + o_n), base + o_desc);
     }
-    if (st != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+    if (st != ZS_OK) return st;
     int n = 0;
     ZS_CUDA(cudaMemcpyAsync(&n, base + o_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaStreamSynchronize(ctx->stream));
     if (n > 0) {
         void* pin;
-        if ((st = zs_pinned(ctx, sizeof(float) * 2 * n, &pin)) != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+        if ((st = zs_pinned(ctx, sizeof(float) * 2 * n, &pin)) != ZS_OK) return st;
         ZS_CUDA(cudaMemcpyAsync(pin, base + o_xy, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
         ZS_CUDA(cudaMemcpyAsync(response, base + o_r, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
         ZS_CUDA(cudaMemcpyAsync(desc, base + o_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -299,7 +299,6 @@ extern "C" zs_status zs_detect_keypoints_simple_host(zs_context* ctx, const uint
         const float* xy = (const float*)pin;
         for (int i = 0; i < n; ++i) { x[i] = xy[2 * i]; y[i] = xy[2 * i + 1]; }
     }
-    ZS_CUDA(cudaFreeAsync(base, ctx->stream));
     *n_out = n;
     return ZS_OK;
 }
@@ -318,8 +317,9 @@ extern "C" zs_status zs_match_host(zs_context* ctx, const void* q, int nq, const
     if (norm == 0) ZS_REQUIRE(dim == 32 || dim == 256 || dim == 0, "Hamming descriptors are 32-byte rows");
     const size_t o_q = 256, o_t = o_q + al256(row * nq), o_idx = o_t + al256(row * nt), o_dist = o_idx + al256(sizeof(int) * 2 * nq),
                  o_pass = o_dist + al256(sizeof(float) * 2 * nq), total = o_pass + al256(nq);
-    uint8_t* base;
-    ZS_CUDA(cudaMallocAsync((void**)&base, total, ctx->stream));
+    zs_async_buffer buf(ctx->stream);
+    ZS_CUDA(cudaMallocAsync((void**)&buf.p, total, ctx->stream));
+    uint8_t* base = buf.p;
     const int hdr[2] = { nq, nt };
     ZS_CUDA(cudaMemcpyAsync(base, hdr, sizeof(hdr), cudaMemcpyHostToDevice, ctx->stream));
     ZS_CUDA(cudaMemcpyAsync(base + o_q, q, row * nq, cudaMemcpyHostToDevice, ctx->stream));
@@ -334,17 +334,16 @@ extern "C" zs_status zs_match_host(zs_context* ctx, const void* q, int nq, const
         if (mode == 0) st = zs_match_l2_knn2(ctx, (const float*)(base + o_q), d_nq, 0, (const float*)(base + o_t), d_nt, 0, 1, nq, nt, dim, ratio, d_idx, d_dist, d_pass);
         else st = zs_match_l2_cross(ctx, (const float*)(base + o_q), d_nq, 0, (const float*)(base + o_t), d_nt, 0, 1, nq, nt, dim, d_idx, d_dist);
     }
-    if (st != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+    if (st != ZS_OK) return st;
     void* pin;
     const size_t hb = sizeof(int) * 2 * nq + sizeof(float) * 2 * nq + nq;
-    if ((st = zs_pinned(ctx, hb, &pin)) != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+    if ((st = zs_pinned(ctx, hb, &pin)) != ZS_OK) return st;
     int* h_idx = (int*)pin; float* h_dist = (float*)(h_idx + 2 * nq); uint8_t* h_pass = (uint8_t*)(h_dist + 2 * nq);
     const int per = mode == 0 ? 2 : 1;
     ZS_CUDA(cudaMemcpyAsync(h_idx, d_idx, sizeof(int) * per * nq, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaMemcpyAsync(h_dist, d_dist, sizeof(float) * per * nq, cudaMemcpyDeviceToHost, ctx->stream));
     if (mode == 0) ZS_CUDA(cudaMemcpyAsync(h_pass, d_pass, nq, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaStreamSynchronize(ctx->stream));
-    ZS_CUDA(cudaFreeAsync(base, ctx->stream));
     int m = 0;
     for (int i = 0; i < nq; ++i) {
         if (mode == 0) {
@@ -378,8 +377,9 @@ extern "C" zs_status zs_knn_match_host(zs_context* ctx, const void* q, int nq, c
     const size_t row = norm == 0 ? 32 : sizeof(float) * (size_t)dim;
     const size_t o_q = 256, o_t = o_q + al256(row * nq), o_idx = o_t + al256(row * nt), o_dist = o_idx + al256(sizeof(int) * 2 * nq),
                  total = o_dist + al256(sizeof(float) * 2 * nq);
-    uint8_t* base;
-    ZS_CUDA(cudaMallocAsync((void**)&base, total, ctx->stream));
+    zs_async_buffer buf(ctx->stream);
+    ZS_CUDA(cudaMallocAsync((void**)&buf.p, total, ctx->stream));
+    uint8_t* base = buf.p;
     const int hdr[2] = { nq, nt };
     ZS_CUDA(cudaMemcpyAsync(base, hdr, sizeof(hdr), cudaMemcpyHostToDevice, ctx->stream));
     ZS_CUDA(cudaMemcpyAsync(base + o_q, q, row * nq, cudaMemcpyHostToDevice, ctx->stream));
@@ -396,15 +396,14 @@ extern "C" zs_status zs_knn_match_host(zs_context* ctx, const void* q, int nq, c
                        : zs_match_l2_knn2(ctx, (const float*)(base + o_q), d_nq, 0, (const float*)(base + o_t), d_nt, 0, 1, nq, nt,
                                           dim, 1.0, d_idx, d_dist, nullptr);
     }
-    if (st != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+    if (st != ZS_OK) return st;
     void* pin;
     const int per = cross_check ? 1 : 2;
-    if ((st = zs_pinned(ctx, (sizeof(int) + sizeof(float)) * per * (size_t)nq, &pin)) != ZS_OK) { cudaFreeAsync(base, ctx->stream); return st; }
+    if ((st = zs_pinned(ctx, (sizeof(int) + sizeof(float)) * per * (size_t)nq, &pin)) != ZS_OK) return st;
     int* h_idx = (int*)pin; float* h_dist = (float*)(h_idx + (size_t)per * nq);
     ZS_CUDA(cudaMemcpyAsync(h_idx, d_idx, sizeof(int) * per * nq, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaMemcpyAsync(h_dist, d_dist, sizeof(float) * per * nq, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaStreamSynchronize(ctx->stream));
-    ZS_CUDA(cudaFreeAsync(base, ctx->stream));
     for (int i = 0; i < nq; ++i)
         for (int j = 0; j < k; ++j) { idx[i * k + j] = h_idx[i * per + j]; dist[i * k + j] = h_dist[i * per + j]; }
     return ZS_OK;

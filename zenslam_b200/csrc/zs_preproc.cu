@@ -243,8 +243,9 @@ extern "C" zs_status zs_process_image_host(zs_context* ctx, const uint8_t* image
     const size_t gpitch = ((size_t)width + 15) / 16 * 16;
     const size_t o_in = 0, o_g0 = o_in + (pitch * height + 255) / 256 * 256, o_g1 = o_g0 + (gpitch * height + 255) / 256 * 256,
                  o_mx = o_g1 + (gpitch * height + 255) / 256 * 256, o_my = o_mx + (px * 4 + 255) / 256 * 256, total = o_my + (px * 4 + 255) / 256 * 256;
-    uint8_t* base;
-    ZS_CUDA(cudaMallocAsync((void**)&base, total, ctx->stream));
+    zs_async_buffer buf(ctx->stream);
+    ZS_CUDA(cudaMallocAsync((void**)&buf.p, total, ctx->stream));
+    uint8_t* base = buf.p;
     zs_status st = ZS_OK;
     cudaError_t e = cudaMemcpyAsync(base + o_in, image, pitch * height, cudaMemcpyHostToDevice, ctx->stream);
     uint8_t* cur = base + o_g0; uint8_t* other = base + o_g1;
@@ -267,7 +268,6 @@ extern "C" zs_status zs_process_image_host(zs_context* ctx, const uint8_t* image
     if (e == cudaSuccess && st == ZS_OK)
         e = cudaMemcpy2DAsync(undistorted, width, cur, gpitch, width, height, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFreeAsync(base, ctx->stream);
     if (e != cudaSuccess) return zs_cuda_fail(e, "zs_process_image_host", __FILE__, __LINE__);
     return st;
 }

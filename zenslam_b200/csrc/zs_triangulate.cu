@@ -193,8 +193,9 @@ extern "C" zs_status zs_triangulate_keypoints_host(zs_context* ctx, const double
     ZS_CUDA(cudaSetDevice(ctx->device));
     const size_t o_p0 = 0, o_p1 = o_p0 + ((size_t)n * 8 + 255) / 256 * 256, o_xyz = o_p1 + ((size_t)n * 8 + 255) / 256 * 256,
                  o_diag = o_xyz + ((size_t)n * 24 + 255) / 256 * 256, o_keep = o_diag + ((size_t)n * 32 + 255) / 256 * 256, total = o_keep + n;
-    uint8_t* base;
-    ZS_CUDA(cudaMallocAsync((void**)&base, total, ctx->stream));
+    zs_async_buffer buf(ctx->stream);
+    ZS_CUDA(cudaMallocAsync((void**)&buf.p, total, ctx->stream));
+    uint8_t* base = buf.p;
     cudaError_t e = cudaMemcpyAsync(base + o_p0, pts0, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(base + o_p1, pts1, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
     zs_status st = ZS_OK;
@@ -205,7 +206,6 @@ extern "C" zs_status zs_triangulate_keypoints_host(zs_context* ctx, const double
     if (e == cudaSuccess && st == ZS_OK) e = cudaMemcpyAsync(keep, base + o_keep, n, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && st == ZS_OK && diag) e = cudaMemcpyAsync(diag, base + o_diag, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFreeAsync(base, ctx->stream);
     if (e != cudaSuccess) return zs_cuda_fail(e, "zs_triangulate_keypoints_host", __FILE__, __LINE__);
     return st;
 }
