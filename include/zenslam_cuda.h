@@ -318,7 +318,8 @@ ZS_API zs_status zs_triangulate_keypoints_host(zs_context* ctx, const double* P0
                                                const zs_triangulation_params* params, double* xyz, uint8_t* keep, double* diag);
 
 /* ---- per-frame stereo tracker: keypoint_tracker::track -------------------------------------------------------
- * (zenslam_core/source/tracking/keypoint_tracker.cpp:41-105) for ONE stereo sequence, one call per stereo frame, state
+ * (zenslam_core/source/tracking/keypoint_tracker.cpp:41-105) for S independent stereo sequences in lock-step (S = 1: the
+ * reference's own use), one call per stereo frame, state
  * (previous pyramids and the two index-keyed keypoint maps) kept on the device: temporal forward-backward KLT of both
  * cameras, grid detection behind the occupancy of the tracked keypoints, stereo tracks L -> R / R -> L of the keypoints
  * the other camera lacks, sequential keypoint indices (keypoint::index_next).  Algorithm GRID, feature FAST, descriptor
@@ -332,22 +333,26 @@ typedef struct {
     double klt_threshold;                          /* tracking.klt_threshold */
     int capacity;                                  /* keypoints per camera; 0 = 4 x cells + 64 */
     int first_index;                               /* keypoint::index_next when the sequence starts */
+    int sequences;                                 /* independent stereo sequences tracked in lock-step; 0 = 1 */
 } zs_tracker_options;
-typedef struct {                                   /* HOST pointers; arrays sized cap >= zs_tracker_capacity(); any may be NULL */
-    int cap;
-    int* n;                                        /* [2] keypoints per camera */
-    int* index[2]; float* xy[2]; float* response[2]; uint8_t* desc[2];
-    int* next_index;                               /* keypoint::index_next after this frame */
+typedef struct {                                   /* HOST pointers, S = sequences; any may be NULL */
+    int cap;                                       /* row length of the arrays below, >= zs_tracker_capacity() */
+    int* n;                                        /* [S][2] keypoints per sequence and camera */
+    int* index[2]; float* xy[2]; float* response[2]; uint8_t* desc[2];   /* per camera: [S][cap], [S][cap][2], [S][cap], [S][cap][32] */
+    int* next_index;                               /* [S] keypoint::index_next of every sequence after this frame */
 } zs_tracker_results;
 ZS_API zs_status zs_tracker_create(zs_context* ctx, const zs_tracker_options* opt, zs_tracker** out);
 ZS_API void zs_tracker_destroy(zs_tracker* t);
 ZS_API int zs_tracker_capacity(const zs_tracker* t);
+ZS_API int zs_tracker_sequences(const zs_tracker* t);
 /* optional, before a track call: predicted positions in the NEXT frame for some of camera's current keypoints, by
  * keypoint index (strictly ascending) -- the landmark projections keypoint_tracker.cpp:361-373 feeds to
  * OPTFLOW_USE_INITIAL_FLOW.  Keypoints without a prediction start from their own position.  Consumed by the next call. */
-ZS_API zs_status zs_tracker_set_predictions(zs_tracker* t, int camera, const int* index, const float* xy, int n);
+ZS_API zs_status zs_tracker_set_predictions(zs_tracker* t, int sequence, int camera, const int* index, const float* xy,
+                                            int n);
+/* left / right: the new frame of every sequence, [S][height][pitch] with `stride` bytes between sequences (0 = pitch * height) */
 ZS_API zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, const uint8_t* right, size_t pitch,
-                                       const zs_tracker_results* res);
+                                       size_t stride, const zs_tracker_results* res);
 
 /* ---- batched stereo front-end ------------------------------------------------------------------
  * The per-frame call pattern of keypoint_tracker::track (keypoint_tracker.cpp:41-105) restated for

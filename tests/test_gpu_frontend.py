@@ -232,6 +232,45 @@ def test_device_tracker_equals_track_mirror(ctx, w, h, cell):
     dev_trk.close()
 
 
+def test_device_tracker_batched_sequences(ctx):
+    """three independent stereo sequences tracked in lock-step by one zs_tracker: every sequence must equal its own
+    single-sequence run (maps, positions, descriptors, index counters), including per-sequence predictions"""
+    from zenslam_b200 import detection_options, keypoint, slam_options, tracking_options
+    from zenslam_b200.keypoint_tracker import device_keypoint_tracker
+    w, h, frames, S = 376, 240, 5, 3
+    seqs = [syn.stereo_sequence(w, h, frames, 1070 + s, subpixel=True)[0] for s in range(S)]
+    opts = slam_options(matcher="KNN", detection=detection_options(), tracking=tracking_options(filter_epipolar=False))
+
+    def pred_for(maps, s):
+        return {i: (k.pt[0] + 0.75 * (s + 1), k.pt[1] + 0.5) for i, k in maps.items() if i % 4 == s}
+
+    want = []
+    for s in range(S):
+        keypoint.index_next = 0
+        one = device_keypoint_tracker(opts, ctx, w, h)
+        per_frame, last = [], ({}, {})
+        for t in range(frames):
+            one.set_predictions(0, pred_for(last[0], s))
+            last = one.track(seqs[s][t, 0], seqs[s][t, 1])
+            per_frame.append((last, one.next_index[0]))
+        want.append(per_frame)
+        one.close()
+    multi = device_keypoint_tracker(opts, ctx, w, h, sequences=S)
+    last = [({}, {})] * S
+    for t in range(frames):
+        for s in range(S):
+            multi.set_predictions(0, pred_for(last[s][0], s), sequence=s)
+        got = multi.track_all(np.stack([seqs[s][t, 0] for s in range(S)]), np.stack([seqs[s][t, 1] for s in range(S)]))
+        for s in range(S):
+            (w0, w1), nxt = want[s][t]
+            for g, r in ((got[s][0], w0), (got[s][1], w1)):
+                assert list(g) == list(r), (t, s)
+                assert all(g[i].pt == r[i].pt and np.array_equal(g[i].descriptor, r[i].descriptor) for i in g), (t, s)
+            assert multi.next_index[s] == nxt
+        last = got
+    multi.close()
+
+
 def test_device_tracker_with_predicted_initial_flow(ctx):
     """temporal tracks that start from host-supplied predictions (landmark projections, keypoint_tracker.cpp:361-373):
     zs_tracker_set_predictions against the mirror's predicted_points callable, frame by frame"""

@@ -34,7 +34,7 @@ class TriangulationParams(C.Structure):
 class TrackerOptions(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("cell_w", C.c_int), ("cell_h", C.c_int), ("fast_threshold", C.c_int),
                 ("klt_win_w", C.c_int), ("klt_win_h", C.c_int), ("klt_max_level", C.c_int), ("klt_threshold", C.c_double),
-                ("capacity", C.c_int), ("first_index", C.c_int)]
+                ("capacity", C.c_int), ("first_index", C.c_int), ("sequences", C.c_int)]
 
 
 class TrackerResults(C.Structure):
@@ -122,8 +122,9 @@ SIGNATURES = {
     "zs_tracker_create": (I, [P, C.POINTER(TrackerOptions), C.POINTER(P)]),
     "zs_tracker_destroy": (None, [P]),
     "zs_tracker_capacity": (I, [P]),
-    "zs_tracker_set_predictions": (I, [P, I, P, P, I]),
-    "zs_tracker_track_host": (I, [P, P, P, Z, C.POINTER(TrackerResults)]),
+    "zs_tracker_sequences": (I, [P]),
+    "zs_tracker_set_predictions": (I, [P, I, I, P, P, I]),
+    "zs_tracker_track_host": (I, [P, P, P, Z, Z, C.POINTER(TrackerResults)]),
     "zs_frontend_create": (I, [P, C.POINTER(FrontendOptions), C.POINTER(P)]),
     "zs_frontend_destroy": (None, [P]),
     "zs_frontend_capacity": (I, [P]),

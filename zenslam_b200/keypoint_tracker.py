@@ -106,10 +106,12 @@ class keypoint_tracker:
 
 class device_keypoint_tracker:
     """zs_tracker: the same track() flow with the keypoint maps, the previous pyramids and keypoint::index_next kept on the
-    device -- one C-ABI call per stereo frame instead of seven.  GRID / FAST / ORB, filter_epipolar off (see the module
-    docstring for what stays on the host)."""
+    device -- one C-ABI call per stereo frame instead of seven -- for `sequences` independent stereo sequences in lock-step
+    (1 = the reference's own use).  GRID / FAST / ORB, filter_epipolar off (see the module docstring for what stays on
+    the host)."""
 
-    def __init__(self, options: slam_options, ctx, width: int, height: int, first_index: int = 0, capacity: int = 0):
+    def __init__(self, options: slam_options, ctx, width: int, height: int, first_index: int = 0, capacity: int = 0,
+                 sequences: int = 1):
         import ctypes as C
 
         from ._lib import TrackerOptions, check, lib
@@ -118,13 +120,14 @@ class device_keypoint_tracker:
             raise NotImplementedError("the device tracker implements algorithm GRID with feature FAST and descriptor ORB")
         if trk.filter_epipolar:
             raise NotImplementedError("tracking.filter_epipolar is a CPU RANSAC in the reference; switch it off or filter the result")
-        self._ctx, self.width, self.height = ctx, width, height
+        self._ctx, self.width, self.height, self.sequences = ctx, width, height, sequences
         o = TrackerOptions(width, height, det.cell_size[0], det.cell_size[1], det.fast_threshold, trk.klt_window_size[0],
-                           trk.klt_window_size[1], trk.klt_max_level, trk.klt_threshold, capacity, first_index)
+                           trk.klt_window_size[1], trk.klt_max_level, trk.klt_threshold, capacity, first_index, sequences)
         h = C.c_void_p()
         check(lib().zs_tracker_create(ctx._h, C.byref(o), C.byref(h)))
         self._h = h
         self.cap = lib().zs_tracker_capacity(h)
+        self.next_index = [first_index] * sequences
 
     def close(self):
         if getattr(self, "_h", None):
@@ -138,7 +141,7 @@ class device_keypoint_tracker:
         except Exception:
             pass
 
-    def set_predictions(self, camera: int, predictions: dict):
+    def set_predictions(self, camera: int, predictions: dict, sequence: int = 0):
         """{keypoint index: (x, y)} -- initial flow of the next temporal track for those keypoints (landmark projections,
         keypoint_tracker.cpp:361-373); consumed by the next track()"""
         import ctypes as C
@@ -149,34 +152,47 @@ class device_keypoint_tracker:
         keys = sorted(predictions)
         idx = np.array(keys, np.int32); xy = np.array([predictions[k] for k in keys], np.float32).reshape(-1, 2)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
-        check(lib().zs_tracker_set_predictions(self._h, camera, p(idx), p(xy), len(keys)))
+        check(lib().zs_tracker_set_predictions(self._h, sequence, camera, p(idx), p(xy), len(keys)))
 
-    def track(self, left, right):
-        """-> (keypoints_0, keypoints_1): keypoint_map per camera, like keypoint_tracker.track; advances keypoint.index_next"""
+    def track_all(self, left, right):
+        """left / right: (sequences, H, W) u8 -> [(keypoints_0, keypoints_1)] per sequence (keypoint_map each); the
+        per-sequence index counters are in self.next_index afterwards"""
         import ctypes as C
 
         import numpy as np
 
         from ._lib import TrackerResults, check, lib
         from .types import keypoint
-        left = np.ascontiguousarray(left, np.uint8); right = np.ascontiguousarray(right, np.uint8)
-        assert left.shape == right.shape == (self.height, self.width)
+        S = self.sequences
+        left = np.ascontiguousarray(left, np.uint8).reshape(S, self.height, self.width)
+        right = np.ascontiguousarray(right, np.uint8).reshape(S, self.height, self.width)
         cap = self.cap
-        n = np.zeros(2, np.int32); nxt = np.zeros(1, np.int32)
-        idx = [np.empty(cap, np.int32) for _ in range(2)]; xy = [np.empty((cap, 2), np.float32) for _ in range(2)]
-        resp = [np.empty(cap, np.float32) for _ in range(2)]; desc = [np.empty((cap, 32), np.uint8) for _ in range(2)]
+        n = np.zeros((S, 2), np.int32); nxt = np.zeros(S, np.int32)
+        idx = [np.empty((S, cap), np.int32) for _ in range(2)]; xy = [np.empty((S, cap, 2), np.float32) for _ in range(2)]
+        resp = [np.empty((S, cap), np.float32) for _ in range(2)]; desc = [np.empty((S, cap, 32), np.uint8) for _ in range(2)]
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         r = TrackerResults()
         r.cap = cap; r.n = p(n).value; r.next_index = p(nxt).value
         for c in range(2):
             r.index[c] = p(idx[c]).value; r.xy[c] = p(xy[c]).value; r.response[c] = p(resp[c]).value; r.desc[c] = p(desc[c]).value
-        check(lib().zs_tracker_track_host(self._h, p(left), p(right), self.width, C.byref(r)))
-        keypoint.index_next = int(nxt[0])
+        check(lib().zs_tracker_track_host(self._h, p(left), p(right), self.width, self.width * self.height, C.byref(r)))
+        self.next_index = [int(v) for v in nxt]
         out = []
-        for c in range(2):
-            m = keypoint_map()
-            for i in range(int(n[c])):
-                m[int(idx[c][i])] = keypoint(pt=(float(xy[c][i, 0]), float(xy[c][i, 1])), response=float(resp[c][i]),
-                                             index=int(idx[c][i]), descriptor=desc[c][i].copy())
-            out.append(m)
-        return out[0], out[1]
+        for s in range(S):
+            maps = []
+            for c in range(2):
+                m = keypoint_map()
+                for i in range(int(n[s, c])):
+                    m[int(idx[c][s, i])] = keypoint(pt=(float(xy[c][s, i, 0]), float(xy[c][s, i, 1])), response=float(resp[c][s, i]),
+                                                    index=int(idx[c][s, i]), descriptor=desc[c][s, i].copy())
+                maps.append(m)
+            out.append((maps[0], maps[1]))
+        return out
+
+    def track(self, left, right):
+        """one sequence: -> (keypoints_0, keypoints_1) like keypoint_tracker.track; advances keypoint.index_next"""
+        from .types import keypoint
+        assert self.sequences == 1
+        k0, k1 = self.track_all(left, right)[0]
+        keypoint.index_next = self.next_index[0]
+        return k0, k1

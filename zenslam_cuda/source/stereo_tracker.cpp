@@ -25,6 +25,7 @@ zenslam::cuda::stereo_tracker::stereo_tracker(const detection_options& detection
     tracker_options.klt_threshold  = tracking.klt_threshold;
     tracker_options.capacity       = 0;
     tracker_options.first_index    = static_cast<int>(keypoint::index_next);
+    tracker_options.sequences      = 1;
 
     std::scoped_lock lock { detail::context_mutex() };
 
@@ -57,7 +58,7 @@ void zenslam::cuda::stereo_tracker::set_predictions(const int camera, const std:
 
     std::scoped_lock lock { detail::context_mutex() };
 
-    detail::check(zs_tracker_set_predictions(_tracker, camera, index.data(), xy.data(), static_cast<int>(index.size())), "zs_tracker_set_predictions");
+    detail::check(zs_tracker_set_predictions(_tracker, 0, camera, index.data(), xy.data(), static_cast<int>(index.size())), "zs_tracker_set_predictions");
 }
 
 auto zenslam::cuda::stereo_tracker::track(const cv::Mat& undistorted_0, const cv::Mat& undistorted_1) -> std::array<map<keypoint>, 2>
@@ -98,7 +99,7 @@ auto zenslam::cuda::stereo_tracker::track(const cv::Mat& undistorted_0, const cv
     {
         std::scoped_lock lock { detail::context_mutex() };
 
-        detail::check(zs_tracker_track_host(_tracker, image_0.data, image_1.data, image_0.step, &results), "zs_tracker_track_host");
+        detail::check(zs_tracker_track_host(_tracker, image_0.data, image_1.data, image_0.step, 0, &results), "zs_tracker_track_host");
     }
 
     // new keypoints took sequential indices on the device, exactly as keypoint::index_next++ would have handed them out
