@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Throughput of the stateful keypoint_tracker::track flow on the device (zs_tracker): S independent 752x480 stereo
+sequences tracked in lock-step, one zs_tracker_track_host call per time step, host images in / both keypoint maps out.
+
+    python tools/bench_tracker.py [--sequences 1 8 32] [--frames 24]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sequences", type=int, nargs="+", default=[1, 8, 32])
+    ap.add_argument("--frames", type=int, default=24)
+    ap.add_argument("--width", type=int, default=752)
+    ap.add_argument("--height", type=int, default=480)
+    a = ap.parse_args()
+    from zenslam_b200 import detection_options, slam_options, synthetic as syn, tracking_options
+    from zenslam_b200._lib import TrackerResults, check, lib
+    from zenslam_b200.keypoint_tracker import device_keypoint_tracker
+    from zenslam_b200.runtime import Context
+    ctx = Context(0)
+    w, h, F = a.width, a.height, a.frames
+    opts = slam_options(detection=detection_options(), tracking=tracking_options(filter_epipolar=False))
+    base = [syn.stereo_sequence(w, h, F, 4100 + s, subpixel=True)[0] for s in range(4)]      # four distinct sequences, reused
+    out = {}
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    for S in a.sequences:
+        trk = device_keypoint_tracker(opts, ctx, w, h, sequences=S)
+        cap = trk.cap
+        n = np.zeros((S, 2), np.int32); nxt = np.zeros(S, np.int32)
+        idx = [np.empty((S, cap), np.int32) for _ in range(2)]; xy = [np.empty((S, cap, 2), np.float32) for _ in range(2)]
+        resp = [np.empty((S, cap), np.float32) for _ in range(2)]; desc = [np.empty((S, cap, 32), np.uint8) for _ in range(2)]
+        r = TrackerResults(); r.cap = cap; r.n = p(n).value; r.next_index = p(nxt).value
+        for c in range(2):
+            r.index[c] = p(idx[c]).value; r.xy[c] = p(xy[c]).value; r.response[c] = p(resp[c]).value; r.desc[c] = p(desc[c]).value
+        L = [np.ascontiguousarray(np.stack([base[s % 4][t, 0] for s in range(S)])) for t in range(F)]
+        R = [np.ascontiguousarray(np.stack([base[s % 4][t, 1] for s in range(S)])) for t in range(F)]
+        warm = F // 3
+        for t in range(warm):
+            check(lib().zs_tracker_track_host(trk._h, p(L[t]), p(R[t]), w, w * h, C.byref(r)))
+        t0 = time.perf_counter()
+        for t in range(warm, F):
+            check(lib().zs_tracker_track_host(trk._h, p(L[t]), p(R[t]), w, w * h, C.byref(r)))
+        dt = (time.perf_counter() - t0) / (F - warm)
+        out["sequences_%d" % S] = {"ms_per_step": dt * 1e3, "stereo_frames_per_s": S / dt, "keypoints_per_camera": float(n.mean())}
+        trk.close()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

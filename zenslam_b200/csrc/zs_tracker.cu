@@ -504,17 +504,19 @@ extern "C" zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, c
     ZS_CUDA(cudaMemcpyAsync(h_next, t->next_index, sizeof(int) * S, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaMemcpyAsync(h_over, t->overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    // one strided copy per field and camera: rows = sequences, row length = the longest live map of that camera
     const size_t rc = (size_t)res->cap;
-    for (int sq = 0; sq < S; ++sq)
-        for (int cam = 0; cam < 2; ++cam) {
-            const trk_map m = t->prev.at(sq, cam);
-            const size_t c = (size_t)(h_n[2 * sq + cam] < cap ? h_n[2 * sq + cam] : cap);
-            if (c == 0) continue;
-            if (res->index[cam]) ZS_CUDA(cudaMemcpyAsync(res->index[cam] + sq * rc, m.idx, sizeof(int) * c, cudaMemcpyDeviceToHost, ctx->stream));
-            if (res->xy[cam]) ZS_CUDA(cudaMemcpyAsync(res->xy[cam] + sq * rc * 2, m.xy, sizeof(float) * 2 * c, cudaMemcpyDeviceToHost, ctx->stream));
-            if (res->response[cam]) ZS_CUDA(cudaMemcpyAsync(res->response[cam] + sq * rc, m.resp, sizeof(float) * c, cudaMemcpyDeviceToHost, ctx->stream));
-            if (res->desc[cam]) ZS_CUDA(cudaMemcpyAsync(res->desc[cam] + sq * rc * 32, m.desc, 32 * c, cudaMemcpyDeviceToHost, ctx->stream));
-        }
+    for (int cam = 0; cam < 2; ++cam) {
+        size_t c = 0;
+        for (int sq = 0; sq < S; ++sq) { const size_t v = (size_t)(h_n[2 * sq + cam] < cap ? h_n[2 * sq + cam] : cap); c = v > c ? v : c; }
+        if (c == 0) continue;
+        const trk_map m = t->prev.at(0, cam);
+        const size_t dr = 2 * (size_t)cap;                 // device rows of one camera are two maps apart
+        if (res->index[cam]) ZS_CUDA(cudaMemcpy2DAsync(res->index[cam], rc * sizeof(int), m.idx, dr * sizeof(int), c * sizeof(int), S, cudaMemcpyDeviceToHost, ctx->stream));
+        if (res->xy[cam]) ZS_CUDA(cudaMemcpy2DAsync(res->xy[cam], rc * 2 * sizeof(float), m.xy, dr * 2 * sizeof(float), c * 2 * sizeof(float), S, cudaMemcpyDeviceToHost, ctx->stream));
+        if (res->response[cam]) ZS_CUDA(cudaMemcpy2DAsync(res->response[cam], rc * sizeof(float), m.resp, dr * sizeof(float), c * sizeof(float), S, cudaMemcpyDeviceToHost, ctx->stream));
+        if (res->desc[cam]) ZS_CUDA(cudaMemcpy2DAsync(res->desc[cam], rc * 32, m.desc, dr * 32, c * 32, S, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     ZS_CUDA(cudaStreamSynchronize(ctx->stream));
     if (res->n) memcpy(res->n, h_n, sizeof(int) * 2 * S);
     if (res->next_index) memcpy(res->next_index, h_next, sizeof(int) * S);
