@@ -353,6 +353,10 @@ ZS_API zs_status zs_tracker_set_predictions(zs_tracker* t, int sequence, int cam
 /* left / right: the new frame of every sequence, [S][height][pitch] with `stride` bytes between sequences (0 = pitch * height) */
 ZS_API zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, const uint8_t* right, size_t pitch,
                                        size_t stride, const zs_tracker_results* res);
+/* the same step with the frames already on the device (enqueued on the context's stream, no host synchronisation), and the
+ * copy of the current maps to the host as a separate call -- for callers that keep frames resident or pipeline transfers */
+ZS_API zs_status zs_tracker_track(zs_tracker* t, const uint8_t* d_left, const uint8_t* d_right, size_t pitch, size_t stride);
+ZS_API zs_status zs_tracker_download(zs_tracker* t, const zs_tracker_results* res);
 
 /* ---- batched stereo front-end ------------------------------------------------------------------
  * The per-frame call pattern of keypoint_tracker::track (keypoint_tracker.cpp:41-105) restated for

@@ -51,8 +51,26 @@ def main():
         for t in range(warm, F):
             check(lib().zs_tracker_track_host(trk._h, p(L[t]), p(R[t]), w, w * h, C.byref(r)))
         dt = (time.perf_counter() - t0) / (F - warm)
-        out["sequences_%d" % S] = {"ms_per_step": dt * 1e3, "stereo_frames_per_s": S / dt, "keypoints_per_camera": float(n.mean())}
-        trk.close()
+        # frames resident on the device, maps left there (one download at the end): the device-side rate of the same flow
+        import torch
+        Ld = [torch.from_numpy(x).cuda() for x in L]; Rd = [torch.from_numpy(x).cuda() for x in R]
+        trk2 = device_keypoint_tracker(opts, ctx, w, h, sequences=S)
+        for t in range(warm):
+            check(lib().zs_tracker_track(trk2._h, C.c_void_p(Ld[t].data_ptr()), C.c_void_p(Rd[t].data_ptr()), w, w * h))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(warm, F):
+            check(lib().zs_tracker_track(trk2._h, C.c_void_p(Ld[t].data_ptr()), C.c_void_p(Rd[t].data_ptr()), w, w * h))
+        e1.record()
+        torch.cuda.synchronize()
+        ddt = e0.elapsed_time(e1) / (F - warm) / 1e3
+        n2 = np.zeros((S, 2), np.int32)
+        r2 = TrackerResults(); r2.cap = cap; r2.n = p(n2).value
+        check(lib().zs_tracker_download(trk2._h, C.byref(r2)))
+        assert np.array_equal(n2, n)
+        out["sequences_%d" % S] = {"ms_per_step": dt * 1e3, "stereo_frames_per_s": S / dt, "keypoints_per_camera": float(n.mean()),
+                                   "device_resident_ms_per_step": ddt * 1e3, "device_resident_stereo_frames_per_s": S / ddt}
+        trk.close(); trk2.close()
     print(json.dumps(out))
 
 

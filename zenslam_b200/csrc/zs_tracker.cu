@@ -480,22 +480,37 @@ static zs_status trk_frame(zs_tracker* t, int par)
     return ZS_OK;
 }
 
-extern "C" zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, const uint8_t* right, size_t pitch, size_t stride,
-                                           const zs_tracker_results* res)
+// one time step with the new frames already on the device (or on the host: src_is_host); results stay on the device
+static zs_status trk_step(zs_tracker* t, const uint8_t* left, const uint8_t* right, size_t pitch, size_t stride, int src_is_host)
 {
-    ZS_REQUIRE(t && left && right && res, "null argument");
+    zs_context* ctx = t->ctx;
+    const int S = t->S;
+    if (stride == 0) stride = pitch * t->opt.height;
+    const int par = (int)(t->frame & 1);
+    zs_status st;
+    if ((st = zs_pyramid_upload(ctx, t->pyr, left, pitch, stride, (par * 2) * S, S, src_is_host)) != ZS_OK) return st;
+    if ((st = zs_pyramid_upload(ctx, t->pyr, right, pitch, stride, (par * 2 + 1) * S, S, src_is_host)) != ZS_OK) return st;
+    if ((st = trk_frame(t, par)) != ZS_OK) return st;
+    t->frame++;
+    return ZS_OK;
+}
+
+extern "C" zs_status zs_tracker_track(zs_tracker* t, const uint8_t* d_left, const uint8_t* d_right, size_t pitch, size_t stride)
+{
+    ZS_REQUIRE(t && d_left && d_right, "null argument");
+    ZS_CUDA(cudaSetDevice(t->ctx->device));
+    return trk_step(t, d_left, d_right, pitch, stride, 0);
+}
+
+extern "C" zs_status zs_tracker_download(zs_tracker* t, const zs_tracker_results* res)
+{
+    ZS_REQUIRE(t && res, "null argument");
     ZS_REQUIRE(res->cap >= t->cap, "results.cap must be at least zs_tracker_capacity()");
     zs_context* ctx = t->ctx;
     ZS_CUDA(cudaSetDevice(ctx->device));
-    const zs_tracker_options& o = t->opt;
     const int S = t->S, cap = t->cap;
-    if (stride == 0) stride = pitch * o.height;
-    const int par = (int)(t->frame & 1);
     zs_status st;
-    if ((st = zs_pyramid_upload(ctx, t->pyr, left, pitch, stride, (par * 2) * S, S, 1)) != ZS_OK) return st;
-    if ((st = zs_pyramid_upload(ctx, t->pyr, right, pitch, stride, (par * 2 + 1) * S, S, 1)) != ZS_OK) return st;
-    if ((st = trk_frame(t, par)) != ZS_OK) return st;
-    // results: the counters first, then only the live part of every array.  Host arrays: n [S][2], next_index [S],
+    // the counters first, then only the live part of every array.  Host arrays: n [S][2], next_index [S],
     // per camera index [S][res->cap], xy [S][res->cap][2], response [S][res->cap], desc [S][res->cap][32]
     void* pin;
     if ((st = zs_pinned(ctx, sizeof(int) * (3 * (size_t)S + 1), &pin)) != ZS_OK) return st;
@@ -520,7 +535,17 @@ extern "C" zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, c
     ZS_CUDA(cudaStreamSynchronize(ctx->stream));
     if (res->n) memcpy(res->n, h_n, sizeof(int) * 2 * S);
     if (res->next_index) memcpy(res->next_index, h_next, sizeof(int) * S);
-    t->frame++;
     if (*h_over) { zs_set_error("tracker capacity %d exceeded", cap); return ZS_ERR_CAPACITY; }
     return ZS_OK;
+}
+
+extern "C" zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, const uint8_t* right, size_t pitch, size_t stride,
+                                           const zs_tracker_results* res)
+{
+    ZS_REQUIRE(t && left && right && res, "null argument");
+    ZS_REQUIRE(res->cap >= t->cap, "results.cap must be at least zs_tracker_capacity()");
+    ZS_CUDA(cudaSetDevice(t->ctx->device));
+    zs_status st = trk_step(t, left, right, pitch, stride, 1);
+    if (st != ZS_OK) return st;
+    return zs_tracker_download(t, res);
 }
