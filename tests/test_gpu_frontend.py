@@ -269,6 +269,20 @@ def test_device_tracker_batched_sequences(ctx):
             assert multi.next_index[s] == nxt
         last = got
     multi.close()
+    # frames resident on the device, maps downloaded once at the end: the same final maps (no predictions this time)
+    import torch
+    a = device_keypoint_tracker(opts, ctx, w, h, sequences=S)
+    b = device_keypoint_tracker(opts, ctx, w, h, sequences=S)
+    for t in range(frames):
+        L = np.stack([seqs[s][t, 0] for s in range(S)]); R = np.stack([seqs[s][t, 1] for s in range(S)])
+        ha = a.track_all(L, R)
+        b.track_device(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda())
+    hb = b.download()
+    for s in range(S):
+        for cam in range(2):
+            assert list(ha[s][cam]) == list(hb[s][cam]) and all(ha[s][cam][i].pt == hb[s][cam][i].pt for i in ha[s][cam])
+    assert a.next_index == b.next_index
+    a.close(); b.close()
 
 
 def test_device_tracker_with_predicted_initial_flow(ctx):

@@ -157,6 +157,27 @@ class device_keypoint_tracker:
     def track_all(self, left, right):
         """left / right: (sequences, H, W) u8 -> [(keypoints_0, keypoints_1)] per sequence (keypoint_map each); the
         per-sequence index counters are in self.next_index afterwards"""
+        import numpy as np
+        S = self.sequences
+        left = np.ascontiguousarray(left, np.uint8).reshape(S, self.height, self.width)
+        right = np.ascontiguousarray(right, np.uint8).reshape(S, self.height, self.width)
+        return self._run(left, right, host=True)
+
+    def track_device(self, left, right):
+        """the same step with (sequences, H, W) u8 CUDA tensors: enqueued on the context's stream, no host copy;
+        call download() when the maps are wanted"""
+        import ctypes as C
+
+        from ._lib import check, lib
+        assert left.is_cuda and right.is_cuda and left.is_contiguous() and right.is_contiguous()
+        check(lib().zs_tracker_track(self._h, C.c_void_p(left.data_ptr()), C.c_void_p(right.data_ptr()), self.width,
+                                     self.width * self.height))
+
+    def download(self):
+        """-> [(keypoints_0, keypoints_1)] per sequence: the maps after the last step"""
+        return self._run(None, None, host=False)
+
+    def _run(self, left, right, host):
         import ctypes as C
 
         import numpy as np
@@ -164,8 +185,6 @@ class device_keypoint_tracker:
         from ._lib import TrackerResults, check, lib
         from .types import keypoint
         S = self.sequences
-        left = np.ascontiguousarray(left, np.uint8).reshape(S, self.height, self.width)
-        right = np.ascontiguousarray(right, np.uint8).reshape(S, self.height, self.width)
         cap = self.cap
         n = np.zeros((S, 2), np.int32); nxt = np.zeros(S, np.int32)
         idx = [np.empty((S, cap), np.int32) for _ in range(2)]; xy = [np.empty((S, cap, 2), np.float32) for _ in range(2)]
@@ -175,7 +194,10 @@ class device_keypoint_tracker:
         r.cap = cap; r.n = p(n).value; r.next_index = p(nxt).value
         for c in range(2):
             r.index[c] = p(idx[c]).value; r.xy[c] = p(xy[c]).value; r.response[c] = p(resp[c]).value; r.desc[c] = p(desc[c]).value
-        check(lib().zs_tracker_track_host(self._h, p(left), p(right), self.width, self.width * self.height, C.byref(r)))
+        if host:
+            check(lib().zs_tracker_track_host(self._h, p(left), p(right), self.width, self.width * self.height, C.byref(r)))
+        else:
+            check(lib().zs_tracker_download(self._h, C.byref(r)))
         self.next_index = [int(v) for v in nxt]
         out = []
         for s in range(S):
