@@ -119,9 +119,12 @@ class Pyramid:
         self.levels = lib().zso_pyramid_levels(self._h)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().zso_pyramid_free(self._h)
-            self._h = None
+        try:                                   # module globals may already be gone at interpreter shutdown
+            if getattr(self, "_h", None):
+                lib().zso_pyramid_free(self._h)
+                self._h = None
+        except Exception:
+            pass
 
     def level_size(self, l):
         w, h = C.c_int(), C.c_int()

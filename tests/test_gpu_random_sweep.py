@@ -207,3 +207,35 @@ def test_orb_detector_random(ctx, seed):
         for key in ("size", "angle", "response", "octave", "desc"):
             assert np.array_equal(r[key][k, :n].cpu().numpy(), o[key]), (k, key)
     det.close()
+
+
+@pytest.mark.parametrize("w,h,win,ml", [(32, 32, (31, 31), 3), (16, 16, (15, 15), 2), (8, 200, (5, 5), 3), (200, 8, (7, 7), 4),
+                                        (63, 63, (31, 31), 3), (64, 64, (31, 31), 3), (4096, 16, (9, 9), 2)])
+def test_extreme_frame_shapes(ctx, w, h, win, ml):
+    """frames barely larger than the LK window, one-cell-high strips, very wide rows: level counts, pyramids, Scharr planes,
+    grid detection, the ORB border filter and KLT on white noise against the oracle"""
+    from zenslam_b200 import LK_GET_MIN_EIGENVALS
+    from zenslam_b200.runtime import LK, Pyramid, fast_grid_detect, klt_track, orb_compute
+    rng = np.random.default_rng(w * 7 + h)
+    img = rng.integers(0, 256, (h, w)).astype(np.uint8)
+    img2 = np.roll(img, 1, 1)
+    p = Pyramid(ctx, w, h, 2, win, ml)
+    p.upload(np.stack([img, img2]), 0); p.build(0, 2)
+    P, P2 = oracle.Pyramid(img, win, ml), oracle.Pyramid(img2, win, ml)
+    assert p.levels == P.levels
+    for l in range(P.levels):
+        assert np.array_equal(p.image(0, l), P.image(l)) and np.array_equal(p.deriv(0, l), P.deriv(l)), l
+    cell = (16, 16) if min(w, h) >= 16 else (8, 8)
+    xy, resp, n = fast_grid_detect(p, 0, 2, cell, 10)
+    x, y, s = oracle.grid_detect(img, cell, 10)
+    assert int(n[0]) == len(x) and np.array_equal(xy[0, :len(x)].cpu().numpy(), np.stack([x, y], 1).astype(np.float32).reshape(-1, 2))
+    _, _, _, on, _ = orb_compute(p, 0, 2, xy, resp, n)
+    assert int(on[0]) == len(oracle.orb_compute(img, x, y)[0])
+    pts = np.stack([rng.uniform(-3, w + 3, 40), rng.uniform(-3, h + 3, 40)], 1).astype(np.float32)
+    lk = LK(win, ml, 99, 0.001, LK_GET_MIN_EIGENVALS, 1e-4)
+    out = klt_track(p, dev(ctx, np.array([0], np.int32)), dev(ctx, np.array([1], np.int32)), dev(ctx, pts[None]),
+                    dev(ctx, np.array([40], np.int32)), lk, None, 1.0)
+    p1, st, err, keep = [o[0].cpu().numpy() for o in out]
+    o1, os_, oe = oracle.lk_track(P, P2, pts, None, win, ml)
+    assert np.array_equal(st, os_) and np.array_equal(p1, o1) and np.array_equal(err, oe)
+    p.close()
