@@ -322,8 +322,8 @@ ZS_API zs_status zs_triangulate_keypoints_host(zs_context* ctx, const double* P0
  * reference's own use), one call per stereo frame, state
  * (previous pyramids and the two index-keyed keypoint maps) kept on the device: temporal forward-backward KLT of both
  * cameras, grid detection behind the occupancy of the tracked keypoints, stereo tracks L -> R / R -> L of the keypoints
- * the other camera lacks, sequential keypoint indices (keypoint::index_next).  Algorithm GRID, feature FAST, descriptor
- * ORB.  Left to the host, as injected callables are in the Python mirror: landmark projection for the initial flow,
+ * the other camera lacks, sequential keypoint indices (keypoint::index_next).  Algorithm GRID or PARALLEL_GRID, feature
+ * FAST, descriptor ORB.  Left to the host, as injected callables are in the Python mirror: landmark projection for the initial flow,
  * assign_landmark_indices, filter_epipolar (cv::findFundamentalMat RANSAC).  Results: both maps in key (index) order. */
 typedef struct zs_tracker zs_tracker;
 typedef struct {
@@ -334,6 +334,7 @@ typedef struct {
     int capacity;                                  /* keypoints per camera; 0 = 4 x cells + 64 */
     int first_index;                               /* keypoint::index_next when the sequence starts */
     int sequences;                                 /* independent stereo sequences tracked in lock-step; 0 = 1 */
+    int parallel_grid;                             /* detection.algorithm PARALLEL_GRID: cornerSubPix on the new corners */
 } zs_tracker_options;
 typedef struct {                                   /* HOST pointers, S = sequences; any may be NULL */
     int cap;                                       /* row length of the arrays below, >= zs_tracker_capacity() */

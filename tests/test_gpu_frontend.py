@@ -198,8 +198,9 @@ def test_keypoint_tracker_track_flow_vs_oracle(ctx):
         keypoint_tracker(slam_options(), ctx, create_cuda_pyr_lk(ctx))                  # filter_epipolar on, no RANSAC callable
 
 
-@pytest.mark.parametrize("w,h,cell", [(376, 240, (16, 16)), (640, 400, (32, 32))])
-def test_device_tracker_equals_track_mirror(ctx, w, h, cell):
+@pytest.mark.parametrize("w,h,cell,algorithm", [(376, 240, (16, 16), "GRID"), (640, 400, (32, 32), "GRID"),
+                                                 (376, 240, (16, 16), "PARALLEL_GRID")])
+def test_device_tracker_equals_track_mirror(ctx, w, h, cell, algorithm):
     """zs_tracker (maps, previous pyramids and index counter on the device, one call per stereo frame) against the
     keypoint_tracker.track mirror, which is itself checked against the oracle: same index sets, positions, responses and
     descriptors in both cameras on every frame, same keypoint::index_next"""
@@ -209,7 +210,8 @@ def test_device_tracker_equals_track_mirror(ctx, w, h, cell):
     from zenslam_b200.tracking import create_cuda_pyr_lk
     frames = 6
     seq, _ = syn.stereo_sequence(w, h, frames, 1040 + w, subpixel=True)
-    opts = slam_options(matcher="KNN", detection=detection_options(cell_size=cell), tracking=tracking_options(filter_epipolar=False))
+    opts = slam_options(matcher="KNN", detection=detection_options(cell_size=cell, algorithm=algorithm),
+                        tracking=tracking_options(filter_epipolar=False))
     keypoint.index_next = 0
     host = keypoint_tracker(opts, ctx, create_cuda_pyr_lk(ctx))
     prev = stereo_frame((seq[0, 0], seq[0, 1]))

@@ -34,7 +34,7 @@ class TriangulationParams(C.Structure):
 class TrackerOptions(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("cell_w", C.c_int), ("cell_h", C.c_int), ("fast_threshold", C.c_int),
                 ("klt_win_w", C.c_int), ("klt_win_h", C.c_int), ("klt_max_level", C.c_int), ("klt_threshold", C.c_double),
-                ("capacity", C.c_int), ("first_index", C.c_int), ("sequences", C.c_int)]
+                ("capacity", C.c_int), ("first_index", C.c_int), ("sequences", C.c_int), ("parallel_grid", C.c_int)]
 
 
 class TrackerResults(C.Structure):

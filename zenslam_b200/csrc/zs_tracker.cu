@@ -383,6 +383,10 @@ static zs_status trk_detect(zs_tracker* t, int cam, int first_slot, int* d_mark)
     zs_status st = zs_fast_grid_detect(ctx, t->pyr, first_slot, t->S, o.cell_w, o.cell_h, o.fast_threshold, t->occ, t->raw_xy, t->raw_resp,
                                        t->raw_n, t->cells);
     if (st != ZS_OK) return st;
+    // PARALLEL_GRID: cv::cornerSubPix(win 5x5, 30 iterations, eps 0.01) on the selected corners before ORB::compute
+    // (keypoint_detector_parallel.cpp:160-170)
+    if (o.parallel_grid && (st = zs_corner_subpix(ctx, t->pyr, first_slot, t->S, t->raw_xy, t->raw_n, t->cells, 5, 5, 30, 0.01)) != ZS_OK)
+        return st;
     if ((st = zs_orb_compute(ctx, t->pyr, first_slot, t->S, t->raw_xy, t->raw_resp, nullptr, t->raw_n, t->cells, t->det_xy, t->det_resp,
                              nullptr, t->det_n, t->det_desc)) != ZS_OK) return st;
     k_trk_append_detected<<<t->S, TRK_THREADS, 0, ctx->stream>>>(t->cur, cam, t->cells, t->det_xy, t->det_resp, t->det_desc, t->det_n,

@@ -116,13 +116,14 @@ class device_keypoint_tracker:
 
         from ._lib import TrackerOptions, check, lib
         det, trk = options.detection, options.tracking
-        if det.algorithm != "GRID" or det.feature_detector != "FAST" or det.descriptor != "ORB":
-            raise NotImplementedError("the device tracker implements algorithm GRID with feature FAST and descriptor ORB")
+        if det.algorithm not in ("GRID", "PARALLEL_GRID") or det.feature_detector != "FAST" or det.descriptor != "ORB":
+            raise NotImplementedError("the device tracker implements algorithm GRID / PARALLEL_GRID with feature FAST and descriptor ORB")
         if trk.filter_epipolar:
             raise NotImplementedError("tracking.filter_epipolar is a CPU RANSAC in the reference; switch it off or filter the result")
         self._ctx, self.width, self.height, self.sequences = ctx, width, height, sequences
         o = TrackerOptions(width, height, det.cell_size[0], det.cell_size[1], det.fast_threshold, trk.klt_window_size[0],
-                           trk.klt_window_size[1], trk.klt_max_level, trk.klt_threshold, capacity, first_index, sequences)
+                           trk.klt_window_size[1], trk.klt_max_level, trk.klt_threshold, capacity, first_index, sequences,
+                           1 if det.algorithm == "PARALLEL_GRID" else 0)
         h = C.c_void_p()
         check(lib().zs_tracker_create(ctx._h, C.byref(o), C.byref(h)))
         self._h = h

@@ -7,8 +7,8 @@
 
 zenslam::cuda::stereo_tracker::stereo_tracker(const detection_options& detection, const tracking_options& tracking, const cv::Size image_size)
 {
-    if (detection.algorithm != detection_algorithm::GRID || detection.feature_detector != feature_type::FAST || detection.descriptor != descriptor_type::ORB)
-        throw std::invalid_argument("stereo_tracker: algorithm GRID with feature FAST and descriptor ORB runs on the GPU");
+    if (detection.algorithm == detection_algorithm::SIMPLE || detection.feature_detector != feature_type::FAST || detection.descriptor != descriptor_type::ORB)
+        throw std::invalid_argument("stereo_tracker: algorithm GRID or PARALLEL_GRID with feature FAST and descriptor ORB runs on the GPU");
 
     if (detail::context() == nullptr)
         throw std::runtime_error("stereo_tracker: no sm_100 device (there is no CPU fallback in this backend)");
@@ -26,6 +26,7 @@ zenslam::cuda::stereo_tracker::stereo_tracker(const detection_options& detection
     tracker_options.capacity       = 0;
     tracker_options.first_index    = static_cast<int>(keypoint::index_next);
     tracker_options.sequences      = 1;
+    tracker_options.parallel_grid  = detection.algorithm == detection_algorithm::PARALLEL_GRID ? 1 : 0;
 
     std::scoped_lock lock { detail::context_mutex() };
 
