@@ -358,6 +358,14 @@ ZS_API zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, const
  * copy of the current maps to the host as a separate call -- for callers that keep frames resident or pipeline transfers */
 ZS_API zs_status zs_tracker_track(zs_tracker* t, const uint8_t* d_left, const uint8_t* d_right, size_t pitch, size_t stride);
 ZS_API zs_status zs_tracker_download(zs_tracker* t, const zs_tracker_results* res);
+/* pipelined host path: up to two steps in flight (copy-in of step k+1 | step k | copy-out of step k-1 on three streams).
+ * `res` names where the maps of THIS step go (whole rows are copied; entries past n are unspecified); the arrays and the
+ * frames must stay valid until the zs_tracker_wait that returns this step, and should be pinned for the copies to overlap.
+ * zs_tracker_wait returns the oldest step in flight (filling its n / next_index). */
+ZS_API zs_status zs_tracker_submit_host(zs_tracker* t, const uint8_t* left, const uint8_t* right, size_t pitch,
+                                        size_t stride, const zs_tracker_results* res);
+ZS_API zs_status zs_tracker_wait(zs_tracker* t);
+ZS_API int zs_tracker_in_flight(const zs_tracker* t);
 
 /* ---- batched stereo front-end ------------------------------------------------------------------
  * The per-frame call pattern of keypoint_tracker::track (keypoint_tracker.cpp:41-105) restated for

@@ -287,6 +287,58 @@ def test_device_tracker_batched_sequences(ctx):
     a.close(); b.close()
 
 
+def test_device_tracker_pipelined_equals_blocking(ctx):
+    """zs_tracker_submit_host / zs_tracker_wait (two steps in flight on three streams, frames staged, maps snapshotted)
+    must return, step for step, what the blocking call returns"""
+    import ctypes as C
+    import torch
+    from zenslam_b200 import detection_options, slam_options, tracking_options
+    from zenslam_b200._lib import TrackerResults, check, lib
+    from zenslam_b200.keypoint_tracker import device_keypoint_tracker
+    w, h, frames, S = 376, 240, 7, 2
+    seqs = [syn.stereo_sequence(w, h, frames, 1090 + s, subpixel=True)[0] for s in range(S)]
+    L = [np.ascontiguousarray(np.stack([seqs[s][t, 0] for s in range(S)])) for t in range(frames)]
+    R = [np.ascontiguousarray(np.stack([seqs[s][t, 1] for s in range(S)])) for t in range(frames)]
+    opts = slam_options(matcher="KNN", detection=detection_options(), tracking=tracking_options(filter_epipolar=False))
+    ref = device_keypoint_tracker(opts, ctx, w, h, sequences=S)
+    want = [ref.track_all(L[t], R[t]) for t in range(frames)]
+    ref.close()
+    trk = device_keypoint_tracker(opts, ctx, w, h, sequences=S)
+    cap = trk.cap
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    Lp = [torch.from_numpy(x).pin_memory() for x in L]; Rp = [torch.from_numpy(x).pin_memory() for x in R]
+    bufs = []
+    for t in range(frames):
+        b = dict(n=np.zeros((S, 2), np.int32), nxt=np.zeros(S, np.int32), idx=[np.zeros((S, cap), np.int32) for _ in range(2)],
+                 xy=[np.zeros((S, cap, 2), np.float32) for _ in range(2)], desc=[np.zeros((S, cap, 32), np.uint8) for _ in range(2)])
+        r = TrackerResults(); r.cap = cap; r.n = p(b["n"]).value; r.next_index = p(b["nxt"]).value
+        for c in range(2):
+            r.index[c] = p(b["idx"][c]).value; r.xy[c] = p(b["xy"][c]).value; r.desc[c] = p(b["desc"][c]).value
+        b["r"] = r
+        bufs.append(b)
+    done = 0
+
+    def check_step(t):
+        b = bufs[t]
+        for s in range(S):
+            for c in range(2):
+                m = want[t][s][c]
+                n = int(b["n"][s, c])
+                assert n == len(m) and b["idx"][c][s, :n].tolist() == list(m), (t, s, c)
+                assert np.array_equal(b["xy"][c][s, :n], np.array([m[i].pt for i in m], np.float32).reshape(-1, 2))
+                assert np.array_equal(b["desc"][c][s, :n], np.stack([m[i].descriptor for i in m]))
+
+    for t in range(frames):
+        check(lib().zs_tracker_submit_host(trk._h, C.c_void_p(Lp[t].data_ptr()), C.c_void_p(Rp[t].data_ptr()), w, w * h, C.byref(bufs[t]["r"])))
+        assert 1 <= lib().zs_tracker_in_flight(trk._h) <= 2
+        if t >= 1:
+            check(lib().zs_tracker_wait(trk._h)); check_step(done); done += 1
+    while lib().zs_tracker_in_flight(trk._h):
+        check(lib().zs_tracker_wait(trk._h)); check_step(done); done += 1
+    assert done == frames
+    trk.close()
+
+
 def test_device_tracker_with_predicted_initial_flow(ctx):
     """temporal tracks that start from host-supplied predictions (landmark projections, keypoint_tracker.cpp:361-373):
     zs_tracker_set_predictions against the mirror's predicted_points callable, frame by frame"""

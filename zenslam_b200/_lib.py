@@ -127,6 +127,9 @@ SIGNATURES = {
     "zs_tracker_track_host": (I, [P, P, P, Z, Z, C.POINTER(TrackerResults)]),
     "zs_tracker_track": (I, [P, P, P, Z, Z]),
     "zs_tracker_download": (I, [P, C.POINTER(TrackerResults)]),
+    "zs_tracker_submit_host": (I, [P, P, P, Z, Z, C.POINTER(TrackerResults)]),
+    "zs_tracker_wait": (I, [P]),
+    "zs_tracker_in_flight": (I, [P]),
     "zs_frontend_create": (I, [P, C.POINTER(FrontendOptions), C.POINTER(P)]),
     "zs_frontend_destroy": (None, [P]),
     "zs_frontend_capacity": (I, [P]),

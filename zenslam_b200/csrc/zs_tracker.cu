@@ -59,6 +59,16 @@ struct zs_tracker {
     // CUDA graph of the per-frame launch sequence (pyramids ... sort), one per frame parity; uploads and result copies
     // stay outside.  Captured the second time a parity comes round (the first run sizes the context scratch).
     bool graph_ok; cudaGraphExec_t gexec[2]; void* g_scratch[2]; uint64_t g_launches[2]; int runs[2];
+    // pipelined host path (zs_tracker_submit_host / zs_tracker_wait): two steps in flight on three streams --
+    // copy-in: frames of step k+1 -> stage[(k+1)&1]; compute (the context's stream): unpack, step k, snapshot of the maps
+    // into outbox[k&1]; copy-out: outbox[(k-1)&1] -> the caller's arrays.  Frames must be staged: step k reads the pyramid
+    // slots of step k-1's parity, which is where step k+1's frames will live.
+    cudaStream_t s_in, s_out;
+    uint8_t* stage[2]; uint8_t* outbox[2]; size_t outbox_bytes;
+    cudaEvent_t ev_in[2], ev_unpacked[2], ev_run[2], ev_out[2];
+    bool busy[2]; uint64_t submitted, waited;
+    int* h_tail[2];              // pinned: n [2S] | next_index [S] | overflow, per in-flight step
+    zs_tracker_results pending[2];
 };
 
 __device__ __forceinline__ int trk_lower_bound(const int* __restrict__ a, int lo, int hi, int key)
@@ -348,6 +358,16 @@ extern "C" void zs_tracker_destroy(zs_tracker* t)
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     for (int par = 0; par < 2; ++par) if (t->gexec[par]) cudaGraphExecDestroy(t->gexec[par]);
+    if (t->s_in) {
+        cudaStreamSynchronize(t->s_in); cudaStreamSynchronize(t->s_out);
+        for (int b = 0; b < 2; ++b) {
+            if (t->stage[b]) cudaFree(t->stage[b]);
+            if (t->outbox[b]) cudaFree(t->outbox[b]);
+            if (t->h_tail[b]) cudaFreeHost(t->h_tail[b]);
+            cudaEventDestroy(t->ev_in[b]); cudaEventDestroy(t->ev_unpacked[b]); cudaEventDestroy(t->ev_run[b]); cudaEventDestroy(t->ev_out[b]);
+        }
+        cudaStreamDestroy(t->s_in); cudaStreamDestroy(t->s_out);
+    }
     if (t->pyr) zs_pyramid_destroy(t->pyr);
     if (t->dev) cudaFree(t->dev);
     free(t);
@@ -552,4 +572,119 @@ extern "C" zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, c
     zs_status st = trk_step(t, left, right, pitch, stride, 1);
     if (st != ZS_OK) return st;
     return zs_tracker_download(t, res);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Pipelined host path: see the comment in zs_tracker.  Host buffers should be pinned (cudaHostAlloc /
+// cudaHostRegister) for the copies to overlap; pageable buffers work but serialise inside the driver.
+// ------------------------------------------------------------------------------------------------------
+static zs_status trk_pipeline_init(zs_tracker* t)
+{
+    if (t->s_in) return ZS_OK;
+    const size_t S = t->S, cap = t->cap, R = 2 * S;
+    ZS_CUDA(cudaStreamCreateWithFlags(&t->s_in, cudaStreamNonBlocking));
+    ZS_CUDA(cudaStreamCreateWithFlags(&t->s_out, cudaStreamNonBlocking));
+    // outbox: idx [R][cap] | xy [R][cap][2] | resp [R][cap] | desc [R][cap][32] | n [R] | next_index [S] | overflow
+    t->outbox_bytes = trk_al(sizeof(int) * R * cap) + trk_al(sizeof(float) * 2 * R * cap) + trk_al(sizeof(float) * R * cap) +
+                      trk_al(32 * R * cap) + trk_al(sizeof(int) * (R + S + 1));
+    for (int b = 0; b < 2; ++b) {
+        ZS_CUDA(cudaEventCreateWithFlags(&t->ev_in[b], cudaEventDisableTiming));
+        ZS_CUDA(cudaEventCreateWithFlags(&t->ev_unpacked[b], cudaEventDisableTiming));
+        ZS_CUDA(cudaEventCreateWithFlags(&t->ev_run[b], cudaEventDisableTiming));
+        ZS_CUDA(cudaEventCreateWithFlags(&t->ev_out[b], cudaEventDisableTiming));
+        ZS_CUDA(cudaMalloc((void**)&t->stage[b], 2 * S * (size_t)t->opt.width * t->opt.height));
+        ZS_CUDA(cudaMalloc((void**)&t->outbox[b], t->outbox_bytes));
+        ZS_CUDA(cudaMallocHost((void**)&t->h_tail[b], sizeof(int) * (R + S + 1)));
+    }
+    return ZS_OK;
+}
+
+extern "C" zs_status zs_tracker_wait(zs_tracker* t)
+{
+    ZS_REQUIRE(t, "null argument");
+    ZS_REQUIRE(t->waited < t->submitted, "zs_tracker_wait: nothing in flight");
+    const int b = (int)(t->waited & 1), S = t->S;
+    ZS_CUDA(cudaEventSynchronize(t->ev_out[b]));
+    const zs_tracker_results& res = t->pending[b];
+    const int* tail = t->h_tail[b];
+    if (res.n) memcpy(res.n, tail, sizeof(int) * 2 * S);
+    if (res.next_index) memcpy(res.next_index, tail + 2 * S, sizeof(int) * S);
+    t->busy[b] = false;
+    t->waited++;
+    if (tail[3 * S]) { zs_set_error("tracker capacity %d exceeded", t->cap); return ZS_ERR_CAPACITY; }
+    return ZS_OK;
+}
+
+extern "C" int zs_tracker_in_flight(const zs_tracker* t) { return t ? (int)(t->submitted - t->waited) : 0; }
+
+// res: where the maps of THIS step go; the arrays must stay valid until the zs_tracker_wait that returns this step
+extern "C" zs_status zs_tracker_submit_host(zs_tracker* t, const uint8_t* left, const uint8_t* right, size_t pitch, size_t stride,
+                                            const zs_tracker_results* res)
+{
+    ZS_REQUIRE(t && left && right && res, "null argument");
+    ZS_REQUIRE(res->cap >= t->cap, "results.cap must be at least zs_tracker_capacity()");
+    zs_context* ctx = t->ctx;
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    zs_status st = trk_pipeline_init(t);
+    if (st != ZS_OK) return st;
+    const int b = (int)(t->submitted & 1);
+    if (t->busy[b] && (st = zs_tracker_wait(t)) != ZS_OK) return st;      // at most two steps in flight
+    const size_t S = t->S, cap = t->cap, R = 2 * S, w = t->opt.width, h = t->opt.height;
+    if (stride == 0) stride = pitch * h;
+    // copy-in: the staging buffer is free once the step that last used it has been unpacked
+    ZS_CUDA(cudaStreamWaitEvent(t->s_in, t->ev_unpacked[b], 0));
+    cudaMemcpy3DParms c;
+    for (int cam = 0; cam < 2; ++cam) {
+        memset(&c, 0, sizeof(c));
+        c.srcPtr = make_cudaPitchedPtr((void*)(cam ? right : left), pitch, pitch, stride / pitch);
+        c.dstPtr = make_cudaPitchedPtr((void*)(t->stage[b] + (size_t)cam * S * w * h), w, w, h);
+        c.extent = make_cudaExtent(w, h, S);
+        c.kind = cudaMemcpyHostToDevice;
+        if (stride % pitch != 0) {
+            for (size_t sq = 0; sq < S; ++sq)
+                ZS_CUDA(cudaMemcpy2DAsync(t->stage[b] + ((size_t)cam * S + sq) * w * h, w, (cam ? right : left) + sq * stride, pitch, w, h,
+                                          cudaMemcpyHostToDevice, t->s_in));
+        } else {
+            ZS_CUDA(cudaMemcpy3DAsync(&c, t->s_in));
+        }
+    }
+    ZS_CUDA(cudaEventRecord(t->ev_in[b], t->s_in));
+    // compute: unpack into this step's pyramid slots, run the step, snapshot the maps
+    ZS_CUDA(cudaStreamWaitEvent(ctx->stream, t->ev_in[b], 0));
+    ZS_CUDA(cudaStreamWaitEvent(ctx->stream, t->ev_out[b], 0));          // the outbox of two steps ago has been read
+    const int par = (int)(t->frame & 1);
+    if ((st = zs_pyramid_upload(ctx, t->pyr, t->stage[b], w, w * h, (par * 2) * (int)S, (int)S, 0)) != ZS_OK) return st;
+    if ((st = zs_pyramid_upload(ctx, t->pyr, t->stage[b] + S * w * h, w, w * h, (par * 2 + 1) * (int)S, (int)S, 0)) != ZS_OK) return st;
+    ZS_CUDA(cudaEventRecord(t->ev_unpacked[b], ctx->stream));
+    if ((st = trk_frame(t, par)) != ZS_OK) return st;
+    t->frame++;
+    uint8_t* ob = t->outbox[b];
+    const size_t o_idx = 0, o_xy = o_idx + trk_al(sizeof(int) * R * cap), o_resp = o_xy + trk_al(sizeof(float) * 2 * R * cap),
+                 o_desc = o_resp + trk_al(sizeof(float) * R * cap), o_tail = o_desc + trk_al(32 * R * cap);
+    const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
+    ZS_CUDA(cudaMemcpyAsync(ob + o_idx, t->prev.idx, sizeof(int) * R * cap, dd, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(ob + o_xy, t->prev.xy, sizeof(float) * 2 * R * cap, dd, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(ob + o_resp, t->prev.resp, sizeof(float) * R * cap, dd, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(ob + o_desc, t->prev.desc, 32 * R * cap, dd, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(ob + o_tail, t->prev.n, sizeof(int) * R, dd, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(ob + o_tail + sizeof(int) * R, t->next_index, sizeof(int) * S, dd, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(ob + o_tail + sizeof(int) * (R + S), t->overflow, sizeof(int), dd, ctx->stream));
+    ZS_CUDA(cudaEventRecord(t->ev_run[b], ctx->stream));
+    // copy-out: whole rows (the counts are not known on the host yet); rows of one camera are two maps apart
+    ZS_CUDA(cudaStreamWaitEvent(t->s_out, t->ev_run[b], 0));
+    const size_t rc = (size_t)res->cap;
+    const cudaMemcpyKind dh = cudaMemcpyDeviceToHost;
+    for (int cam = 0; cam < 2; ++cam) {
+        const size_t r0 = (size_t)cam * cap;               // first element of this camera's first row
+        if (res->index[cam]) ZS_CUDA(cudaMemcpy2DAsync(res->index[cam], rc * sizeof(int), ob + o_idx + r0 * sizeof(int), 2 * cap * sizeof(int), cap * sizeof(int), S, dh, t->s_out));
+        if (res->xy[cam]) ZS_CUDA(cudaMemcpy2DAsync(res->xy[cam], rc * 2 * sizeof(float), ob + o_xy + r0 * 2 * sizeof(float), 4 * cap * sizeof(float), 2 * cap * sizeof(float), S, dh, t->s_out));
+        if (res->response[cam]) ZS_CUDA(cudaMemcpy2DAsync(res->response[cam], rc * sizeof(float), ob + o_resp + r0 * sizeof(float), 2 * cap * sizeof(float), cap * sizeof(float), S, dh, t->s_out));
+        if (res->desc[cam]) ZS_CUDA(cudaMemcpy2DAsync(res->desc[cam], rc * 32, ob + o_desc + r0 * 32, 64 * cap, 32 * cap, S, dh, t->s_out));
+    }
+    ZS_CUDA(cudaMemcpyAsync(t->h_tail[b], ob + o_tail, sizeof(int) * (R + S + 1), dh, t->s_out));
+    ZS_CUDA(cudaEventRecord(t->ev_out[b], t->s_out));
+    t->pending[b] = *res;
+    t->busy[b] = true;
+    t->submitted++;
+    return ZS_OK;
 }
