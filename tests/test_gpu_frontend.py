@@ -337,6 +337,19 @@ def test_device_tracker_pipelined_equals_blocking(ctx):
         check(lib().zs_tracker_wait(trk._h)); check_step(done); done += 1
     assert done == frames
     trk.close()
+    # the same through the Python mirror's submit / wait
+    py = device_keypoint_tracker(opts, ctx, w, h, sequences=S)
+    got = []
+    for t in range(frames):
+        py.submit(Lp[t], Rp[t])
+        if t >= 1:
+            got.append(py.wait())
+    got.append(py.wait())
+    for t in range(frames):
+        for s in range(S):
+            for c in range(2):
+                assert list(got[t][s][c]) == list(want[t][s][c]) and all(got[t][s][c][i].pt == want[t][s][c][i].pt for i in got[t][s][c])
+    py.close()
 
 
 def test_device_tracker_with_predicted_initial_flow(ctx):

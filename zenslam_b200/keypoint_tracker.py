@@ -178,6 +178,60 @@ class device_keypoint_tracker:
         """-> [(keypoints_0, keypoints_1)] per sequence: the maps after the last step"""
         return self._run(None, None, host=False)
 
+    def submit(self, left, right):
+        """pipelined host path (zs_tracker_submit_host): enqueue one step from (sequences, H, W) u8 pinned tensors / arrays;
+        up to two steps may be in flight, wait() returns them oldest first.  The frames must stay alive until then."""
+        import ctypes as C
+
+        import numpy as np
+
+        from ._lib import TrackerResults, check, lib
+        torch = __import__("torch")
+        if not hasattr(self, "_slots"):
+            S, cap = self.sequences, self.cap
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+            self._slots, self._queue, self._step = [], [], 0
+            for _ in range(2):
+                d = dict(n=pin((S, 2), torch.int32), nxt=pin((S,), torch.int32), idx=[pin((S, cap), torch.int32) for _ in range(2)],
+                         xy=[pin((S, cap, 2), torch.float32) for _ in range(2)], resp=[pin((S, cap), torch.float32) for _ in range(2)],
+                         desc=[pin((S, cap, 32), torch.uint8) for _ in range(2)])
+                r = TrackerResults(); r.cap = cap; r.n = d["n"].data_ptr(); r.next_index = d["nxt"].data_ptr()
+                for c in range(2):
+                    r.index[c] = d["idx"][c].data_ptr(); r.xy[c] = d["xy"][c].data_ptr(); r.response[c] = d["resp"][c].data_ptr()
+                    r.desc[c] = d["desc"][c].data_ptr()
+                d["r"] = r
+                self._slots.append(d)
+        if len(self._queue) == 2:
+            raise RuntimeError("two steps are already in flight: call wait() first")
+        as_t = lambda a: a if hasattr(a, "data_ptr") else torch.from_numpy(np.ascontiguousarray(a, np.uint8))
+        lt, rt = as_t(left).contiguous(), as_t(right).contiguous()
+        d = self._slots[self._step & 1]
+        check(lib().zs_tracker_submit_host(self._h, C.c_void_p(lt.data_ptr()), C.c_void_p(rt.data_ptr()), self.width,
+                                           self.width * self.height, C.byref(d["r"])))
+        self._queue.append((d, lt, rt))
+        self._step += 1
+
+    def wait(self):
+        """-> [(keypoints_0, keypoints_1)] per sequence of the oldest step in flight"""
+        from ._lib import check, lib
+        from .types import keypoint
+        d, _, _ = self._queue.pop(0)
+        check(lib().zs_tracker_wait(self._h))
+        n, nxt = d["n"].numpy(), d["nxt"].numpy()
+        self.next_index = [int(v) for v in nxt]
+        out = []
+        for s in range(self.sequences):
+            maps = []
+            for c in range(2):
+                idx, xy, resp, desc = d["idx"][c].numpy(), d["xy"][c].numpy(), d["resp"][c].numpy(), d["desc"][c].numpy()
+                m = keypoint_map()
+                for i in range(int(n[s, c])):
+                    m[int(idx[s, i])] = keypoint(pt=(float(xy[s, i, 0]), float(xy[s, i, 1])), response=float(resp[s, i]),
+                                                 index=int(idx[s, i]), descriptor=desc[s, i].copy())
+                maps.append(m)
+            out.append((maps[0], maps[1]))
+        return out
+
     def _run(self, left, right, host):
         import ctypes as C
 
