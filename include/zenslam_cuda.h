@@ -358,6 +358,11 @@ ZS_API zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, const
  * copy of the current maps to the host as a separate call -- for callers that keep frames resident or pipeline transfers */
 ZS_API zs_status zs_tracker_track(zs_tracker* t, const uint8_t* d_left, const uint8_t* d_right, size_t pitch, size_t stride);
 ZS_API zs_status zs_tracker_download(zs_tracker* t, const zs_tracker_results* res);
+/* filter_epipolar (keypoint_tracker.cpp:293-341) on the maps of the last step of `sequence`, F (row-major 3x3) from the
+ * caller -- the reference estimates it with cv::findFundamentalMat RANSAC on the matched points, which stays on the CPU:
+ * both maps keep only the keypoints present in both whose |pt0^T F pt1| < threshold.  The filtered maps are what the next
+ * step tracks from; read them back with zs_tracker_download. */
+ZS_API zs_status zs_tracker_filter_epipolar(zs_tracker* t, int sequence, const double* F, double threshold);
 /* pipelined host path: up to two steps in flight (copy-in of step k+1 | step k | copy-out of step k-1 on three streams).
  * `res` names where the maps of THIS step go (whole rows are copied; entries past n are unspecified); the arrays and the
  * frames must stay valid until the zs_tracker_wait that returns this step, and should be pinned for the copies to overlap.

@@ -35,6 +35,9 @@ namespace cv
     };
     using Size = Size_<int>;
 
+    template <typename T, int M, int N> struct Matx { T val[M * N] { }; };
+    using Matx33d = Matx<double, 3, 3>;
+
     struct TermCriteria
     {
         enum Type { COUNT = 1, MAX_ITER = COUNT, EPS = 2 };

@@ -287,6 +287,56 @@ def test_device_tracker_batched_sequences(ctx):
     a.close(); b.close()
 
 
+def test_device_tracker_filter_epipolar(ctx):
+    """filter_epipolar (keypoint_tracker.cpp:293-341) with a caller-supplied F: the device filter after every step against
+    the mirror's epipolar_filter callable evaluating |pt0^T F pt1| in the same double arithmetic; the filtered maps are
+    what the next frame tracks from in both implementations"""
+    import dataclasses
+    from zenslam_b200 import detection_options, keypoint, slam_options, tracking_options
+    from zenslam_b200.keypoint_tracker import device_keypoint_tracker, keypoint_tracker, stereo_frame
+    from zenslam_b200.tracking import create_cuda_pyr_lk
+    w, h, frames = 376, 240, 5
+    seq, _ = syn.stereo_sequence(w, h, frames, 1110, subpixel=True)
+    # rectified stereo: F = [t]_x with t along x, so that pt0^T F pt1 = y1 - y0 (plus a little skew to make every term matter)
+    F = np.array([[0.0, 1e-6, 0.0], [-1e-6, 0.0, -1.0], [0.0, 1.0, 0.002]], np.float64)
+    thr = 0.0027                                      # err = 0.002 + 6e-6 y on this pair (disparity 6 px): the upper half passes
+
+    def epipolar_filter(m0, m1):
+        keep = []
+        for a, b in zip(m0, m1):
+            x0, y0 = np.float64(np.float32(a.pt[0])), np.float64(np.float32(a.pt[1]))
+            x1, y1 = np.float64(np.float32(b.pt[0])), np.float64(np.float32(b.pt[1]))
+            r = [(x0 * F[0, j] + y0 * F[1, j]) + F[2, j] for j in range(3)]
+            keep.append(abs((r[0] * x1 + r[1] * y1) + r[2]) < thr)
+        return keep
+
+    opts_h = slam_options(matcher="KNN", detection=detection_options(), tracking=tracking_options(filter_epipolar=True))
+    keypoint.index_next = 0
+    host = keypoint_tracker(opts_h, ctx, create_cuda_pyr_lk(ctx), epipolar_filter=epipolar_filter)
+    prev = stereo_frame((seq[0, 0], seq[0, 1]))
+    want = []
+    for t in range(frames):
+        cur = stereo_frame((seq[t, 0], seq[t, 1]))
+        k0, k1 = host.track(prev, cur)
+        want.append((k0, k1))
+        prev = dataclasses.replace(cur, keypoints=(k0, k1))
+    opts_d = slam_options(matcher="KNN", detection=detection_options(), tracking=tracking_options(filter_epipolar=False))
+    keypoint.index_next = 0
+    dev_trk = device_keypoint_tracker(opts_d, ctx, w, h)
+    dropped = 0
+    for t in range(frames):
+        before = dev_trk.track(seq[t, 0], seq[t, 1])
+        dev_trk.filter_epipolar(F, thr)
+        g = dev_trk.download()[0]
+        dropped += len(before[0]) - len(g[0])
+        for cam in range(2):
+            assert list(g[cam]) == sorted(want[t][cam]), (t, cam, len(g[cam]), len(want[t][cam]))
+            assert all(g[cam][i].pt == want[t][cam][i].pt for i in g[cam])
+        assert list(g[0]) == list(g[1])                       # only keypoints present in both cameras survive
+    assert dropped > 0 and len(g[0]) > 20
+    dev_trk.close()
+
+
 def test_device_tracker_pipelined_equals_blocking(ctx):
     """zs_tracker_submit_host / zs_tracker_wait (two steps in flight on three streams, frames staged, maps snapshotted)
     must return, step for step, what the blocking call returns"""

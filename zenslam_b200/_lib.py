@@ -127,6 +127,7 @@ SIGNATURES = {
     "zs_tracker_track_host": (I, [P, P, P, Z, Z, C.POINTER(TrackerResults)]),
     "zs_tracker_track": (I, [P, P, P, Z, Z]),
     "zs_tracker_download": (I, [P, C.POINTER(TrackerResults)]),
+    "zs_tracker_filter_epipolar": (I, [P, I, P, D]),
     "zs_tracker_submit_host": (I, [P, P, P, Z, Z, C.POINTER(TrackerResults)]),
     "zs_tracker_wait": (I, [P]),
     "zs_tracker_in_flight": (I, [P]),

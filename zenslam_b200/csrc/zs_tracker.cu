@@ -574,6 +574,69 @@ extern "C" zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, c
     return zs_tracker_download(t, res);
 }
 
+// filter_epipolar (keypoint_tracker.cpp:293-341) with the fundamental matrix supplied by the caller (the reference estimates
+// it with cv::findFundamentalMat RANSAC on the matched points -- a CPU step -- right before this test): both maps keep only
+// the keypoints whose index is in BOTH maps and whose epipolar error |pt0^T F pt1| is below the threshold.  Matx product
+// order: (pt0^T F) first, each sum left to right in double.  One block per sequence; `prev` holds the maps of the last step.
+__global__ void __launch_bounds__(TRK_THREADS) k_trk_filter_epipolar(trk_maps maps, trk_maps tmp, int seq, double f00, double f01, double f02,
+                                                                     double f10, double f11, double f12, double f20, double f21, double f22,
+                                                                     double threshold)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int cap = maps.cap;
+    const trk_map a = maps.at(seq, 0), b = maps.at(seq, 1), oa = tmp.at(seq, 0), ob = tmp.at(seq, 1);
+    const int na = min(*a.n, cap), nb = min(*b.n, cap);
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < na; base += TRK_THREADS) {
+        const int i = base + threadIdx.x;
+        bool f = false;
+        int j = 0;
+        if (i < na) {
+            const int key = a.idx[i];
+            j = trk_lower_bound(b.idx, 0, nb, key);
+            if (j < nb && b.idx[j] == key) {
+                const double x0 = (double)a.xy[2 * i], y0 = (double)a.xy[2 * i + 1], x1 = (double)b.xy[2 * j], y1 = (double)b.xy[2 * j + 1];
+                const double r0 = __dadd_rn(__dadd_rn(__dmul_rn(x0, f00), __dmul_rn(y0, f10)), f20);      // pt0 = (x0, y0, 1)
+                const double r1 = __dadd_rn(__dadd_rn(__dmul_rn(x0, f01), __dmul_rn(y0, f11)), f21);
+                const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(x0, f02), __dmul_rn(y0, f12)), f22);
+                const double err = __dadd_rn(__dadd_rn(__dmul_rn(r0, x1), __dmul_rn(r1, y1)), r2);
+                f = fabs(err) < threshold;
+            }
+        }
+        const int o = trk_scan_step(f, warp_sums, &carry);
+        if (f) {
+            oa.idx[o] = a.idx[i]; oa.xy[2 * o] = a.xy[2 * i]; oa.xy[2 * o + 1] = a.xy[2 * i + 1]; oa.resp[o] = a.resp[i];
+            trk_copy_desc(oa.desc + (size_t)o * 32, a.desc + (size_t)i * 32);
+            ob.idx[o] = b.idx[j]; ob.xy[2 * o] = b.xy[2 * j]; ob.xy[2 * o + 1] = b.xy[2 * j + 1]; ob.resp[o] = b.resp[j];
+            trk_copy_desc(ob.desc + (size_t)o * 32, b.desc + (size_t)j * 32);
+        }
+    }
+    __syncthreads();
+    const int kept = carry;
+    // copy the compacted maps back (tmp = the other generation, free between steps)
+    for (int i = threadIdx.x; i < kept; i += TRK_THREADS) {
+        a.idx[i] = oa.idx[i]; a.xy[2 * i] = oa.xy[2 * i]; a.xy[2 * i + 1] = oa.xy[2 * i + 1]; a.resp[i] = oa.resp[i];
+        trk_copy_desc(a.desc + (size_t)i * 32, oa.desc + (size_t)i * 32);
+        b.idx[i] = ob.idx[i]; b.xy[2 * i] = ob.xy[2 * i]; b.xy[2 * i + 1] = ob.xy[2 * i + 1]; b.resp[i] = ob.resp[i];
+        trk_copy_desc(b.desc + (size_t)i * 32, ob.desc + (size_t)i * 32);
+    }
+    if (threadIdx.x == 0) { *a.n = kept; *b.n = kept; }
+}
+
+extern "C" zs_status zs_tracker_filter_epipolar(zs_tracker* t, int sequence, const double* F, double threshold)
+{
+    ZS_REQUIRE(t && F && sequence >= 0 && sequence < t->S, "bad argument");
+    ZS_REQUIRE(t->submitted == t->waited, "steps are still in flight: wait for them first");
+    zs_context* ctx = t->ctx;
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    // with pt0 = (x0, y0, 1): the 1 * F(2, j) terms are added last, like Matx's k = 2 term
+    k_trk_filter_epipolar<<<1, TRK_THREADS, 0, ctx->stream>>>(t->prev, t->cur, sequence, F[0], F[1], F[2], F[3], F[4], F[5], F[6], F[7], F[8], threshold);
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Pipelined host path: see the comment in zs_tracker.  Host buffers should be pinned (cudaHostAlloc /
 // cudaHostRegister) for the copies to overlap; pageable buffers work but serialise inside the driver.

@@ -178,6 +178,17 @@ class device_keypoint_tracker:
         """-> [(keypoints_0, keypoints_1)] per sequence: the maps after the last step"""
         return self._run(None, None, host=False)
 
+    def filter_epipolar(self, fundamental, threshold: float, sequence: int = 0):
+        """keypoint_tracker::filter_epipolar with a caller-supplied F (3x3): the maps of the last step keep only the
+        keypoints present in both cameras with |pt0^T F pt1| < threshold; the next step tracks from the filtered maps"""
+        import ctypes as C
+
+        import numpy as np
+
+        from ._lib import check, lib
+        F = np.ascontiguousarray(fundamental, np.float64).reshape(3, 3)
+        check(lib().zs_tracker_filter_epipolar(self._h, sequence, F.ctypes.data_as(C.c_void_p), float(threshold)))
+
     def submit(self, left, right):
         """pipelined host path (zs_tracker_submit_host): enqueue one step from (sequences, H, W) u8 pinned tensors / arrays;
         up to two steps may be in flight, wait() returns them oldest first.  The frames must stay alive until then."""

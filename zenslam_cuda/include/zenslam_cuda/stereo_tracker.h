@@ -35,10 +35,17 @@ namespace zenslam::cuda
          *  keypoint index -- the landmark projections keypoint_tracker.cpp:361-373 uses as initial flow */
         void set_predictions(int camera, const std::map<size_t, cv::Point2f>& predictions);
 
+        /** keypoint_tracker::filter_epipolar's gate with F from the caller (cv::findFundamentalMat on the matched points of
+         *  the maps track() returned): the device-side maps keep only keypoints present in both cameras with
+         *  |pt0^T F pt1| < threshold; returns the filtered maps, which are also what the next track() starts from */
+        [[nodiscard]] auto filter_epipolar(const cv::Matx33d& fundamental, double threshold) -> std::array<map<keypoint>, 2>;
+
         /** undistorted grayscale images of the new stereo frame -> the two keypoint maps of that frame */
         [[nodiscard]] auto track(const cv::Mat& undistorted_0, const cv::Mat& undistorted_1) -> std::array<map<keypoint>, 2>;
 
     private:
+        [[nodiscard]] auto download() -> std::array<map<keypoint>, 2>;
+
         zs_tracker* _tracker  = nullptr;
         int         _capacity = 0;
     };

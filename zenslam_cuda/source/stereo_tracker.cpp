@@ -62,6 +62,61 @@ void zenslam::cuda::stereo_tracker::set_predictions(const int camera, const std:
     detail::check(zs_tracker_set_predictions(_tracker, 0, camera, index.data(), xy.data(), static_cast<int>(index.size())), "zs_tracker_set_predictions");
 }
 
+namespace
+{
+    // host side of zs_tracker_results for one sequence, and its conversion to the reference's maps
+    struct host_maps
+    {
+        explicit host_maps(const int capacity) :
+            capacity { capacity }
+        {
+            for (auto camera = 0; camera < 2; ++camera)
+            {
+                index[camera].resize(capacity);
+                xy[camera].resize(2 * static_cast<size_t>(capacity));
+                response[camera].resize(capacity);
+                descriptors[camera] = cv::Mat(capacity, 32, CV_8UC1);
+
+                results.index[camera]    = index[camera].data();
+                results.xy[camera]       = xy[camera].data();
+                results.response[camera] = response[camera].data();
+                results.desc[camera]     = descriptors[camera].data;
+            }
+
+            results.cap        = capacity;
+            results.n          = count;
+            results.next_index = &index_next;
+        }
+
+        [[nodiscard]] auto to_maps() const -> std::array<zenslam::map<zenslam::keypoint>, 2>
+        {
+            std::array<zenslam::map<zenslam::keypoint>, 2> keypoints { };
+
+            for (auto camera = 0; camera < 2; ++camera)
+            {
+                for (auto i = 0; i < count[camera]; ++i)
+                {
+                    // FAST keypoints: size 7, angle -1, octave 0, class_id -1 (tracked copies keep everything but pt)
+                    const cv::KeyPoint keypoint_cv { xy[camera][2 * i], xy[camera][2 * i + 1], 7.0f, -1.0f, response[camera][i], 0, -1 };
+
+                    keypoints[camera].add(zenslam::keypoint { keypoint_cv, static_cast<size_t>(index[camera][i]), descriptors[camera].row(i).clone() });
+                }
+            }
+
+            return keypoints;
+        }
+
+        int                capacity   = 0;
+        int                count[2]   = { 0, 0 };
+        int                index_next = 0;
+        std::vector<int>   index[2]   = { };
+        std::vector<float> xy[2]      = { };
+        std::vector<float> response[2] = { };
+        cv::Mat            descriptors[2] = { };
+        zs_tracker_results results { };
+    };
+}
+
 auto zenslam::cuda::stereo_tracker::track(const cv::Mat& undistorted_0, const cv::Mat& undistorted_1) -> std::array<map<keypoint>, 2>
 {
     CV_Assert(undistorted_0.type() == CV_8UC1 && undistorted_1.type() == CV_8UC1 && undistorted_0.size() == undistorted_1.size());
@@ -75,49 +130,41 @@ auto zenslam::cuda::stereo_tracker::track(const cv::Mat& undistorted_0, const cv
         image_1 = image_1.clone();
     }
 
-    const auto capacity = static_cast<size_t>(_capacity);
-
-    int                count[2]   = { 0, 0 };
-    int                index_next = 0;
-    std::vector<int>   index[2]   = { std::vector<int>(capacity), std::vector<int>(capacity) };
-    std::vector<float> xy[2]      = { std::vector<float>(2 * capacity), std::vector<float>(2 * capacity) };
-    std::vector<float> response[2] = { std::vector<float>(capacity), std::vector<float>(capacity) };
-    cv::Mat            descriptors[2] = { cv::Mat(_capacity, 32, CV_8UC1), cv::Mat(_capacity, 32, CV_8UC1) };
-
-    zs_tracker_results results { };
-    results.cap        = _capacity;
-    results.n          = count;
-    results.next_index = &index_next;
-
-    for (auto camera = 0; camera < 2; ++camera)
-    {
-        results.index[camera]    = index[camera].data();
-        results.xy[camera]       = xy[camera].data();
-        results.response[camera] = response[camera].data();
-        results.desc[camera]     = descriptors[camera].data;
-    }
+    host_maps host { _capacity };
 
     {
         std::scoped_lock lock { detail::context_mutex() };
 
-        detail::check(zs_tracker_track_host(_tracker, image_0.data, image_1.data, image_0.step, 0, &results), "zs_tracker_track_host");
+        detail::check(zs_tracker_track_host(_tracker, image_0.data, image_1.data, image_0.step, 0, &host.results), "zs_tracker_track_host");
     }
 
     // new keypoints took sequential indices on the device, exactly as keypoint::index_next++ would have handed them out
-    keypoint::index_next = static_cast<size_t>(index_next);
+    keypoint::index_next = static_cast<size_t>(host.index_next);
 
-    std::array<map<keypoint>, 2> keypoints { };
+    return host.to_maps();
+}
 
-    for (auto camera = 0; camera < 2; ++camera)
+auto zenslam::cuda::stereo_tracker::download() -> std::array<map<keypoint>, 2>
+{
+    host_maps host { _capacity };
+
     {
-        for (auto i = 0; i < count[camera]; ++i)
-        {
-            // FAST keypoints: size 7, angle -1, octave 0, class_id -1 (tracked copies keep everything but pt)
-            const cv::KeyPoint keypoint_cv { xy[camera][2 * i], xy[camera][2 * i + 1], 7.0f, -1.0f, response[camera][i], 0, -1 };
+        std::scoped_lock lock { detail::context_mutex() };
 
-            keypoints[camera].add(keypoint { keypoint_cv, static_cast<size_t>(index[camera][i]), descriptors[camera].row(i).clone() });
-        }
+        detail::check(zs_tracker_download(_tracker, &host.results), "zs_tracker_download");
     }
 
-    return keypoints;
+    return host.to_maps();
+}
+
+auto zenslam::cuda::stereo_tracker::filter_epipolar(const cv::Matx33d& fundamental, const double threshold) -> std::array<map<keypoint>, 2>
+{
+    {
+        std::scoped_lock lock { detail::context_mutex() };
+
+        // cv::Matx stores row-major, which is what the C entry takes
+        detail::check(zs_tracker_filter_epipolar(_tracker, 0, fundamental.val, threshold), "zs_tracker_filter_epipolar");
+    }
+
+    return download();
 }
