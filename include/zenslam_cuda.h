@@ -323,8 +323,10 @@ ZS_API zs_status zs_triangulate_keypoints_host(zs_context* ctx, const double* P0
  * (previous pyramids and the two index-keyed keypoint maps) kept on the device: temporal forward-backward KLT of both
  * cameras, grid detection behind the occupancy of the tracked keypoints, stereo tracks L -> R / R -> L of the keypoints
  * the other camera lacks, sequential keypoint indices (keypoint::index_next).  Algorithm GRID or PARALLEL_GRID, feature
- * FAST, descriptor ORB.  Left to the host, as injected callables are in the Python mirror: landmark projection for the initial flow,
- * assign_landmark_indices, filter_epipolar (cv::findFundamentalMat RANSAC).  Results: both maps in key (index) order. */
+ * FAST, descriptor ORB.  Host-side pieces of the reference's flow: the landmark projection behind the initial flow (its
+ * result comes in through zs_tracker_set_predictions) and the RANSAC that estimates F for filter_epipolar (the gate itself
+ * is zs_tracker_filter_epipolar).  assign_landmark_indices (keypoint_tracker.cpp:55,71) is not applied: the tracker behaves
+ * like track() with an empty landmark map.  Results: both maps in key (index) order. */
 typedef struct zs_tracker zs_tracker;
 typedef struct {
     int width, height;
