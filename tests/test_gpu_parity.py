@@ -29,8 +29,11 @@ def dev(ctx, a, dtype=None):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("w,h,win,ml", [(256, 192, (15, 15), 3), (752, 480, (31, 31), 3), (752, 480, (63, 63), 4),
                                         (321, 243, (21, 21), 5), (1280, 720, (31, 21), 3)])
-def test_pyramid_vs_oracle(ctx, w, h, win, ml):
+@pytest.mark.parametrize("path", ["ZS_PYR_FUSED", "ZS_PYR_SPLIT"])
+def test_pyramid_vs_oracle(ctx, w, h, win, ml, path, monkeypatch):
+    """both builders -- one fused launch per level (few images) and pad / pyrDown / Scharr as separate passes (many)"""
     from zenslam_b200.runtime import Pyramid
+    monkeypatch.setenv(path, "1")
     imgs = np.stack([syn.stereo_pair(w, h, 10 + w)[0], syn.stereo_pair(w, h, 11 + w)[1],
                      np.random.default_rng(w).integers(0, 256, (h, w), dtype=np.uint8)])
     p = Pyramid(ctx, w, h, 3, win, ml)
@@ -43,6 +46,26 @@ def test_pyramid_vs_oracle(ctx, w, h, win, ml):
             assert p.level_size(l) == P.level_size(l)
             assert np.array_equal(p.image(s, l), P.image(l)), (s, l)
             assert np.array_equal(p.deriv(s, l), P.deriv(l)), (s, l)
+
+
+@pytest.mark.parametrize("path", ["ZS_PYR_FUSED", "ZS_PYR_SPLIT"])
+def test_pyramid_every_width_residue(ctx, path, monkeypatch):
+    """the fused builder patches the out-of-image columns of a row's first / last 4-pixel item in registers: every
+    residue of the width mod 8 (and both parities of the height) at every level, on white noise"""
+    from zenslam_b200.runtime import Pyramid
+    monkeypatch.setenv(path, "1")
+    for w in range(64, 81):
+        h = 40 + (w & 1) + (w >> 2 & 1) * 2
+        img = np.random.default_rng(w).integers(0, 256, (2, h, w), dtype=np.uint8)
+        p = Pyramid(ctx, w, h, 2, (9, 9), 2)
+        p.upload(img, 0)
+        p.build(0, 2)
+        for s in range(2):
+            P = oracle.Pyramid(img[s], (9, 9), 2)
+            assert p.levels == P.levels
+            for l in range(P.levels):
+                assert np.array_equal(p.image(s, l), P.image(l)), (w, h, s, l)
+                assert np.array_equal(p.deriv(s, l), P.deriv(l)), (w, h, s, l)
 
 
 def test_pyramid_golden(ctx, golden):
