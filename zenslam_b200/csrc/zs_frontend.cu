@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include "zs_common.cuh"
+#include <algorithm>
 
 #define ZS_FE_STAGES 6          // pyramid, fast, orb, match, klt, carry
 #define ZS_FE_TIMING_RING 64
@@ -60,6 +61,26 @@ struct zs_frontend {
 static inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
 // t_n[j] = n[row[j]]
+// the carried frame: up to 2 x (2 planes per level + keypoints + count) device-to-device segments in one launch; every
+// segment is 4-byte granular and 16-byte aligned unless it is shorter than that (the keypoint count)
+#define FE_CARRY_BLOCKS 16
+struct fe_carry_seg { const void* src; void* dst; size_t bytes; };
+struct fe_carry_args { fe_carry_seg seg[2 * (2 * ZS_MAX_LEVELS + 2)]; int n; };
+
+__global__ void __launch_bounds__(256) k_fe_carry(const fe_carry_args a)
+{
+    const fe_carry_seg s = a.seg[blockIdx.y];
+    const bool wide = (((uintptr_t)s.src | (uintptr_t)s.dst) & 15) == 0;
+    const size_t n16 = wide ? s.bytes >> 4 : 0;
+    const size_t step = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint4* s16 = (const uint4*)s.src;
+    uint4* d16 = (uint4*)s.dst;
+    for (size_t i = t0; i < n16; i += step) d16[i] = s16[i];
+    const uint32_t* s4 = (const uint32_t*)s.src;
+    uint32_t* d4 = (uint32_t*)s.dst;
+    for (size_t i = n16 * 4 + t0; i < (s.bytes >> 2); i += step) d4[i] = s4[i];
+}
+
 __global__ void k_gather_counts(const int* __restrict__ n, const int* __restrict__ row, int jobs, int* __restrict__ out)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -277,20 +298,25 @@ static zs_status frontend_run_body(zs_frontend* fe)
     k_gather_counts<<<zs_div_up(4 * B, 256), 256, 0, ctx->stream>>>(fe->n, fe->job_row, 4 * B, fe->t_n);
     ZS_LAUNCH_CHECK(ctx);
     ZS_FE_MARK(5);
-    // 6. carry the last stereo frame into slots 0/1 (pyramid planes and keypoints)
+    // 6. carry the last stereo frame into slots 0/1 (pyramid planes and keypoints): one kernel over all the segments (twenty
+    //    separate copy nodes cost 65 us per run -- a quarter of a batch-1 step)
     const zs_pyr_view& v = fe->pyr->v;
+    fe_carry_args ca;
+    ca.n = 0;
     for (int cam = 0; cam < 2; ++cam) {
         const int src = cam == 0 ? B + 1 : 2 * B + 1, dst = cam;
         for (int l = 0; l < v.levels; ++l) {
-            ZS_CUDA(cudaMemcpyAsync(v.img[l] + (size_t)dst * v.slot_stride[l], v.img[l] + (size_t)src * v.slot_stride[l],
-                                    v.slot_stride[l], cudaMemcpyDeviceToDevice, ctx->stream));
-            ZS_CUDA(cudaMemcpyAsync(v.der[l] + (size_t)dst * v.slot_stride[l], v.der[l] + (size_t)src * v.slot_stride[l],
-                                    v.slot_stride[l] * sizeof(short2), cudaMemcpyDeviceToDevice, ctx->stream));
+            ca.seg[ca.n++] = { v.img[l] + (size_t)src * v.slot_stride[l], v.img[l] + (size_t)dst * v.slot_stride[l], v.slot_stride[l] };
+            ca.seg[ca.n++] = { v.der[l] + (size_t)src * v.slot_stride[l], v.der[l] + (size_t)dst * v.slot_stride[l],
+                               v.slot_stride[l] * sizeof(short2) };
         }
-        ZS_CUDA(cudaMemcpyAsync(fe->xy + (size_t)dst * cap * 2, fe->xy + (size_t)src * cap * 2, sizeof(float) * 2 * cap,
-                                cudaMemcpyDeviceToDevice, ctx->stream));
-        ZS_CUDA(cudaMemcpyAsync(fe->n + dst, fe->n + src, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        ca.seg[ca.n++] = { fe->xy + (size_t)src * cap * 2, fe->xy + (size_t)dst * cap * 2, sizeof(float) * 2 * (size_t)cap };
+        ca.seg[ca.n++] = { fe->n + src, fe->n + dst, sizeof(int) };
     }
+    // blocks per segment: 64 KB per block of the largest plane, between 16 (752x480: 20 x 16 blocks) and two per SM
+    const int cb = (int)std::min<size_t>(std::max<size_t>(FE_CARRY_BLOCKS, v.slot_stride[0] * sizeof(short2) / 65536), 296);
+    k_fe_carry<<<dim3(cb, ca.n), 256, 0, ctx->stream>>>(ca);
+    ZS_LAUNCH_CHECK(ctx);
     ZS_FE_MARK(6);
     if (fe->timing) fe->t_runs++;
     fe->have_carry = true;
