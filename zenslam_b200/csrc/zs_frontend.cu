@@ -396,16 +396,19 @@ extern "C" zs_status zs_frontend_process_host(zs_frontend* fe, const uint8_t* le
 // ------------------------------------------------------------------------------------------------------
 
 // staging (raw host layout) -> level-0 interiors of the padded planes; 16 bytes per thread when everything
-// is 16-byte aligned (C2: width 752, pitch 752), bytes otherwise.  grid: (ceil(w/16/128), height, images)
-__global__ void __launch_bounds__(128) k_unpack_level0(const uint8_t* __restrict__ src, size_t pitch, size_t stride,
+// is 16-byte aligned (C2: width 752, pitch 752), bytes otherwise.  Items = (row, 16-byte group) flattened, so that a
+// block is full whatever the row length (a block per row: 47 of 128 threads busy at 752 pixels, 123 k blocks per batch).
+// grid: (ceil(h * ceil(w/16) / 256), 1, images)
+__global__ void __launch_bounds__(256) k_unpack_level0(const uint8_t* __restrict__ src, size_t pitch, size_t stride,
                                                        zs_pyr_view v, int first, int vec)
 {
-    const int w = v.w[0];
-    const int y = blockIdx.y, img = blockIdx.z;
+    const int w = v.w[0], h = v.h[0];
+    const int wg = (w + 15) >> 4;
+    const int item = blockIdx.x * 256 + threadIdx.x;
+    const int y = item / wg, x = (item - y * wg) * 16, img = blockIdx.z;
+    if (y >= h) return;
     const uint8_t* s = src + (size_t)img * stride + (size_t)y * pitch;
     uint8_t* d = v.img[0] + (size_t)zs_slot(first, img, v.slots) * v.slot_stride[0] + (size_t)(v.pad_y + y) * v.pitch[0] + v.pad_x;
-    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (x >= w) return;
     if (vec && x + 16 <= w) {
         *(uint4*)(d + x) = __ldcs((const uint4*)(s + x));
     } else {
@@ -481,8 +484,8 @@ extern "C" zs_status zs_frontend_submit_host(zs_frontend* fe, const uint8_t* lef
     const int W = fe->opt.width, H = fe->opt.height;
     if (!fe->pp_enabled) {
         const int vec = (pitch % 16 == 0 && stride % 16 == 0 && ((uintptr_t)fe->stage[b] % 16) == 0 && W % 16 == 0) ? 1 : 0;
-        const dim3 grid(zs_div_up(zs_div_up(W, 16), 128), H, (unsigned)(2 * B));
-        k_unpack_level0<<<grid, 128, 0, ctx->stream>>>(fe->stage[b], pitch, stride, v, 2, vec);   // slots 2..2B+1 = L then R
+        const dim3 grid(zs_div_up(zs_div_up(W, 16) * H, 256), 1, (unsigned)(2 * B));
+        k_unpack_level0<<<grid, 256, 0, ctx->stream>>>(fe->stage[b], pitch, stride, v, 2, vec);   // slots 2..2B+1 = L then R
         ZS_LAUNCH_CHECK(ctx);
     } else {
         // raw frames -> gray -> (CLAHE) -> (remap) -> level 0 of slots 2..2B+1; every stage handles all 2B images at once
@@ -513,8 +516,8 @@ extern "C" zs_status zs_frontend_submit_host(zs_frontend* fe, const uint8_t* lef
         } else if (cur == fe->stage[b]) {
             // gray input, no CLAHE, no remap: plain unpack
             const int vec = (pitch % 16 == 0 && stride % 16 == 0 && ((uintptr_t)fe->stage[b] % 16) == 0 && W % 16 == 0) ? 1 : 0;
-            const dim3 grid(zs_div_up(zs_div_up(W, 16), 128), H, (unsigned)(2 * B));
-            k_unpack_level0<<<grid, 128, 0, ctx->stream>>>(fe->stage[b], pitch, stride, v, 2, vec);
+            const dim3 grid(zs_div_up(zs_div_up(W, 16) * H, 256), 1, (unsigned)(2 * B));
+            k_unpack_level0<<<grid, 256, 0, ctx->stream>>>(fe->stage[b], pitch, stride, v, 2, vec);
             ZS_LAUNCH_CHECK(ctx);
         }
     }

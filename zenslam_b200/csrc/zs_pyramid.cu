@@ -9,52 +9,56 @@
 #include "zs_common.cuh"
 
 // ---- (1) reflect padding ---------------------------------------------------------------------------
-// grid: (1, ceil(padded rows / 32), count); 256 threads = 8 warps, each warp fills rows r, r+8, r+16, r+24 of its
-// 32-row group (one block per row was block-launch bound: 139 k tiny blocks per level 0).  Interior rows get their left / right pads; rows above / below the
-// image are whole copies of the reflected interior row (pads included).  Everything is produced as 32-bit words
-// (pad_x and the pitch are multiples of 16): a word whose four source pixels are consecutive and ascending is
-// one load when the source offset is aligned, otherwise four byte reads from the just-staged interior row.
-__global__ void __launch_bounds__(256) k_pad_reflect(zs_pyr_view v, int level, int first)
+// The padding of a plane as flat 32-bit word items, one per thread (pad_x and the pitch are multiples of 16):
+//   region A: the 2 pad_y rows above / below the image, whole padded rows (copies of the reflected interior row);
+//   region B: the left and right pads of the h interior rows.
+// A word whose four source pixels are consecutive and ascending is one aligned load from the interior row, otherwise
+// four byte reads through REFLECT_101 -- the interior is all a pad item ever reads.  (One warp per four rows with a
+// lane loop per row, the first version, was latency-bound: 39 us for the 21 MB of level-0 padding of 256 images.)
+static int pad_items_host(const zs_pyr_view& v, int level)
+{
+    const int w = v.w[level], h = v.h[level];
+    const int wtotal = (w + 2 * v.pad_x + 3) >> 2;
+    return 2 * v.pad_y * wtotal + h * (wtotal - (w >> 2));
+}
+
+__device__ __forceinline__ void pad_item(const zs_pyr_view& v, int level, uint8_t* __restrict__ plane, int item)
 {
     const int w = v.w[level], h = v.h[level], pitch = v.pitch[level];
-    const int slot = zs_slot(first, blockIdx.z, v.slots);
-    uint8_t* plane = v.img[level] + (size_t)slot * v.slot_stride[level];
-    const int lane = threadIdx.x & 31;
-#pragma unroll 1
-  for (int rr = (threadIdx.x >> 5); rr < 32; rr += 8) {
-    const int r = blockIdx.y * 32 + rr;               // padded row
-    if (r >= h + 2 * v.pad_y) break;
+    const int wpad = v.pad_x >> 2;                    // words per side pad
+    const int wright0 = w >> 2;                       // first interior-relative word that contains right-pad pixels
+    const int wtotal = (w + 2 * v.pad_x + 3) >> 2;
+    const int na = 2 * v.pad_y * wtotal, nside = wtotal - wright0;
+    int r, q;                                         // padded row, word of the padded row (columns 4q .. 4q+3)
+    if (item < na) {
+        const int ra = item / wtotal;
+        q = item - ra * wtotal;
+        r = ra < v.pad_y ? ra : h + ra;
+    } else {
+        const int it = item - na, y = it / nside, j = it - y * nside;
+        if (y >= h) return;
+        r = v.pad_y + y;
+        q = j >= wpad ? j + wright0 : j;              // a partial last interior word keeps its interior bytes
+    }
     const int sy = zs_reflect101(r - v.pad_y, h);
     const uint8_t* src = plane + (size_t)(sy + v.pad_y) * pitch + v.pad_x;   // interior row sy
-    uint8_t* dst = plane + (size_t)r * pitch;
-    const bool interior_row = (r >= v.pad_y && r < v.pad_y + h);
-    const int wpad = v.pad_x >> 2;                    // words per side pad
-    const int wint = (w + 3) >> 2;                    // words covering the interior (the last may run into the right pad)
-    const int wright0 = w >> 2;                       // first word that contains right-pad pixels
-    const int wtotal = (w + 2 * v.pad_x + 3) >> 2;    // words per padded row (the pitch is rounded up beyond this)
-    // word index q covers padded columns 4q .. 4q+3
-    // interior rows only touch the words outside the fully-interior ones (the image itself lives there)
-    const int n = interior_row ? wtotal - wright0 : wtotal;
-    for (int j = lane; j < n; j += 32) {
-        const int q = (interior_row && j >= wpad) ? j + wright0 : j;
-        const int px0 = 4 * q - v.pad_x;              // image column of the word's first pixel
-        const bool left = q < wpad, inside = !left && (q - wpad) < wright0;
-        uint32_t val;
-        if (inside && ((px0 & 3) == 0)) {
-            val = *(const uint32_t*)(src + px0);      // straight copy of four interior pixels of the reflected row
-        } else {
-            val = 0;
+    const int px0 = 4 * q - v.pad_x;                  // image column of the word's first pixel
+    uint32_t val;
+    if (px0 >= 0 && px0 + 4 <= w) {
+        val = *(const uint32_t*)(src + px0);          // straight copy of four interior pixels of the reflected row
+    } else {
+        val = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int px = px0 + k;
-                // a partial last interior word keeps its interior bytes (they are re-read and re-written unchanged)
-                val |= (uint32_t)src[zs_reflect101(px, w)] << (8 * k);
-            }
-        }
-        *(uint32_t*)(dst + 4 * q) = val;
+        for (int k = 0; k < 4; ++k) val |= (uint32_t)src[zs_reflect101(px0 + k, w)] << (8 * k);
     }
-    (void)wint;
-  }
+    *(uint32_t*)(plane + (size_t)r * pitch + 4 * q) = val;
+}
+
+// grid: (ceil(items / 256), 1, count)
+__global__ void __launch_bounds__(256) k_pad_reflect(zs_pyr_view v, int level, int first)
+{
+    const int slot = zs_slot(first, blockIdx.z, v.slots);
+    pad_item(v, level, v.img[level] + (size_t)slot * v.slot_stride[level], blockIdx.x * 256 + threadIdx.x);
 }
 
 // ---- (2) pyrDown -------------------------------------------------------------------------------------
@@ -279,32 +283,8 @@ __global__ void __launch_bounds__(256, 8) k_pyr_level(zs_pyr_view v, int level, 
         return;
     }
     b -= nb_down;
-    // pad role: same work split as k_pad_reflect (which reads the interior only)
-    const int lane = threadIdx.x & 31;
-#pragma unroll 1
-    for (int rr = (threadIdx.x >> 5); rr < 32; rr += 8) {
-        const int r = b * 32 + rr;
-        if (r >= h + 2 * v.pad_y) break;
-        const int sy = zs_reflect101(r - v.pad_y, h);
-        const uint8_t* srow = src + (size_t)sy * pitch;
-        uint8_t* dst = plane + (size_t)r * pitch;
-        const bool interior_row = (r >= v.pad_y && r < v.pad_y + h);
-        const int wpad = v.pad_x >> 2, wright0 = w >> 2, wtotal = (w + 2 * v.pad_x + 3) >> 2;
-        const int n = interior_row ? wtotal - wright0 : wtotal;
-        for (int j = lane; j < n; j += 32) {
-            const int q = (interior_row && j >= wpad) ? j + wright0 : j;
-            const int px0 = 4 * q - v.pad_x;
-            const bool inside = q >= wpad && (q - wpad) < wright0;
-            uint32_t val;
-            if (inside && ((px0 & 3) == 0)) val = *(const uint32_t*)(srow + px0);
-            else {
-                val = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) val |= (uint32_t)srow[zs_reflect101(px0 + k, w)] << (8 * k);
-            }
-            *(uint32_t*)(dst + 4 * q) = val;
-        }
-    }
+    // pad role
+    pad_item(v, level, plane, b * 256 + threadIdx.x);
 }
 
 extern "C" zs_status zs_pyramid_build(zs_context* ctx, zs_pyramid* p, int first, int count)
@@ -313,23 +293,24 @@ extern "C" zs_status zs_pyramid_build(zs_context* ctx, zs_pyramid* p, int first,
     ZS_REQUIRE(count >= 0 && count <= p->slots && first >= 0, "bad slot range");
     if (count == 0) return ZS_OK;
     const zs_pyr_view& v = p->v;
-    // Measured at 752x480 (bench stage events): fused 37 vs 65 us for 2 images, 45 vs 70 us for 8, 87 vs 96 us for 32, but
-    // 472 vs 369 us for 256 -- with hundreds of images in flight the three separate streaming passes win, with few the
-    // launch count does.  ZS_PYR_SPLIT / ZS_PYR_FUSED force one or the other.
+    // Measured at 752x480 (bench stage events, fused vs three passes): 2 images 37 vs 65 us and 8 images 45 vs 70 us (28 us
+    // for 2 with the flat pad items), 32 images 79 vs 82 us (whole step equal), 64: 135 vs 121, 128: 247 vs 199, 256: 468 vs
+    // 357 -- with many images in flight the three separate streaming passes win, with few the launch count does.
+    // ZS_PYR_SPLIT / ZS_PYR_FUSED force one or the other.
     const int force = getenv("ZS_PYR_SPLIT") ? 1 : getenv("ZS_PYR_FUSED") ? 2 : 0;
-    const bool split = force == 1 || (force == 0 && count > 32);
+    const bool split = force == 1 || (force == 0 && count > 16);
     for (int l = 0; l < v.levels; ++l) {
         const int w = v.w[l], h = v.h[l];
         const bool down = l + 1 < v.levels;
         const int nb_scharr = zs_div_up(zs_div_up(w, 4) * h, 256);
         const int nb_down = down ? zs_div_up(zs_div_up(v.w[l + 1], 4) * v.h[l + 1], 256) : 0;
-        const int nb_pad = zs_div_up(h + 2 * v.pad_y, 32);
+        const int nb_pad = zs_div_up(pad_items_host(v, l), 256);
         if (!split) {
             k_pyr_level<<<dim3(nb_scharr + nb_down + nb_pad, 1, count), 256, 0, ctx->stream>>>(v, l, first, nb_scharr, nb_down);
             ZS_LAUNCH_CHECK(ctx);
             continue;
         }
-        k_pad_reflect<<<dim3(1, nb_pad, count), 256, 0, ctx->stream>>>(v, l, first);
+        k_pad_reflect<<<dim3(nb_pad, 1, count), 256, 0, ctx->stream>>>(v, l, first);
         ZS_LAUNCH_CHECK(ctx);
         if (down) {
             k_pyr_down<<<dim3(nb_down, 1, count), 256, 0, ctx->stream>>>(v, l, first);
