@@ -35,12 +35,34 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H = 752, 480
-CELL, FAST_T = (16, 16), 10
-WIN, MAX_LEVEL, KLT_THR, RATIO = (31, 31), 3, 1.0, 0.8
 METRIC, UNIT = "stereo_frames_per_s", "stereo frames/s"
-WORKLOAD = ("C2: 752x480 synthetic stereo sequence; per frame 2 pyramids + 2 grid FAST (16x16 cells, thr 10) + ORB "
-            "+ 1 stereo Hamming kNN-ratio + 4 fwd/bwd KLT pairs (31x31, 4 levels, 99 its, eps 1e-3)")
+RATIO = 0.8
+# name -> frame size, detector cells / FAST threshold / algorithm, KLT window / max_level / FB threshold, default batch
+CONFIGS = {
+    "C2":       dict(w=752,  h=480,  cell=(16, 16), thr=10, alg="GRID",          win=(31, 31), ml=3, klt_thr=1.0, batch=128),
+    "C4":       dict(w=1280, h=1024, cell=(32, 32), thr=10, alg="GRID",          win=(31, 31), ml=3, klt_thr=1.0, batch=64),
+    "C5":       dict(w=3840, h=2160, cell=(32, 32), thr=10, alg="GRID",          win=(31, 31), ml=3, klt_thr=1.0, batch=16),
+    # the only configuration the reference ships (zenslam_options/options/tumvi.yaml:38-47) at the TUM-VI frame size
+    "TUMVI":    dict(w=1024, h=1024, cell=(64, 64), thr=1,  alg="PARALLEL_GRID", win=(63, 63), ml=4, klt_thr=2.0, batch=128),
+    "TUMVI752": dict(w=752,  h=480,  cell=(64, 64), thr=1,  alg="PARALLEL_GRID", win=(63, 63), ml=4, klt_thr=2.0, batch=128),
+}
+
+
+def set_config(name):
+    global CFG, W, H, CELL, FAST_T, WIN, MAX_LEVEL, KLT_THR, WORKLOAD
+    CFG = dict(CONFIGS[name], name=name)
+    W, H, CELL, FAST_T = CFG["w"], CFG["h"], CFG["cell"], CFG["thr"]
+    WIN, MAX_LEVEL, KLT_THR = CFG["win"], CFG["ml"], CFG["klt_thr"]
+    WORKLOAD = ("%s: %dx%d synthetic stereo sequence; per frame 2 pyramids + 2 grid FAST (%dx%d cells, thr %d)%s + ORB "
+                "+ 1 stereo Hamming kNN-ratio + 4 fwd/bwd KLT pairs (%dx%d, %d levels, 99 its, eps 1e-3)"
+                % (name, W, H, CELL[0], CELL[1], FAST_T, " + cornerSubPix" if CFG["alg"] == "PARALLEL_GRID" else "",
+                   WIN[0], WIN[1], fe_levels(W, H)))
+    return CFG
+
+
+def cpu_options():
+    from oracle import FrontendOptions
+    return FrontendOptions(CELL, FAST_T, WIN, MAX_LEVEL, KLT_THR, RATIO, CFG["alg"] == "PARALLEL_GRID")
 
 
 def peaks():
@@ -109,11 +131,12 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
     """one process: `frames` stereo frames of the reference call pattern through cv2, 1 OpenCV thread"""
-    seed, frames = args
+    seed, frames, cfg_name = args
     import cv2
     cv2.setNumThreads(1)
-    from oracle import FrontendOptions, cv2_ref
-    opts = FrontendOptions(CELL, FAST_T, WIN, MAX_LEVEL, KLT_THR, RATIO)
+    from oracle import cv2_ref
+    set_config(cfg_name)          # spawned workers import this module afresh: the configuration travels with the task
+    opts = cpu_options()
     seq = make_sequence(frames + 1, seed)
     # frame 0 primes the "previous frame" state (not timed)
     prev = cv2_ref.stereo_frame(seq[0, 0], seq[0, 1], seq[0, 0], seq[0, 1], np.zeros((0, 2), np.float32),
@@ -132,7 +155,7 @@ def cpu_pool(cores):
 def cpu_step(pool, cores, frames_per_worker, seed0):
     """all workers run concurrently; returns (stereo frames, wall seconds) for the step"""
     t0 = time.perf_counter()
-    out = pool.map(_cpu_worker, [(seed0 + i, frames_per_worker) for i in range(cores)])
+    out = pool.map(_cpu_worker, [(seed0 + i, frames_per_worker, CFG["name"]) for i in range(cores)])
     wall = time.perf_counter() - t0
     # the per-worker timers exclude process spawn, imports and synthetic-data generation
     busy = max(o[0] for o in out)
@@ -167,6 +190,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    line["cpu_baseline"].update(cpu_overhead(value, cores))
     emit(line)
 
 
@@ -176,8 +200,6 @@ def run_reference(args, rank, world):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from zenslam_b200 import detection_options, slam_options, tracking_options
-    from zenslam_b200.frontend import StereoFrontend
     from zenslam_b200.runtime import Context
 
     if not torch.cuda.is_available():
@@ -185,10 +207,41 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pin_rank_to_cores(local_rank, world)
     ctx = Context(local_rank)
+    line = measure_frontend(args, rank, world, local_rank, ctx, light=False)
+    if rank == 0:
+        if world == 1 and not args.no_extra:
+            line["extra"] = extras(args, ctx)
+        emit(line)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def pin_rank_to_cores(local_rank, world):
+    """one rank per GPU and an equal, disjoint share of the host cores per rank: the per-step host work (graph launch,
+    staging copies) of N ranks otherwise lands on whatever cores the scheduler picks and jitters the max-over-ranks time"""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cores) >= world:
+            per = len(cores) // world
+            os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]))
+    except Exception:
+        pass
+
+
+def measure_frontend(args, rank, world, local_rank, ctx, light=False):
+    """one configuration (the globals set by set_config) through the batched front-end -> the JSON line (rank 0) or None.
+    light: value + e2e + stage times only (the `extra` one-liners): no blocking-call / raw-BGR / sustained / CPU legs."""
+    import torch
+    import torch.distributed as dist
+    from zenslam_b200 import detection_options, slam_options, tracking_options
+    from zenslam_b200.frontend import StereoFrontend
+
     B, K, Wm = args.batch, args.steps, args.warmup
     opts = slam_options(matcher="KNN", matcher_ratio=RATIO,
-                        detection=detection_options(cell_size=CELL, fast_threshold=FAST_T),
+                        detection=detection_options(cell_size=CELL, fast_threshold=FAST_T, algorithm=CFG["alg"]),
                         tracking=tracking_options(klt_window_size=WIN, klt_max_level=MAX_LEVEL, klt_threshold=KLT_THR))
     fe = StereoFrontend(ctx, W, H, B, opts)
 
@@ -212,6 +265,14 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def all_ranks(v):
+        if world == 1:
+            return [v]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = v
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
 
     stream = torch.cuda.current_stream()
 
@@ -245,13 +306,36 @@ def run_ours(args, rank, world, local_rank):
         fe.upload(left_dev[j], right_dev[j]); fe.run()
     e1.record(stream)
     barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_own = e0.elapsed_time(e1)
+    ms = max_over_ranks(ms_own)
+    rank_ms = all_ranks(ms_own / K)
     launches = ctx.launches - launches0
     res = fe.download()
     clocks = sampler.stop() if rank == 0 else None
     kp_mean = float(np.mean(np.concatenate([res["n_left"], res["n_right"]])))
     keep_frac = float(res["track_keep"].sum() / max(1, res["track_n"].sum()))
     value = world * B * K / (ms / 1000.0)
+
+    # ---- sustained: the same loop for at least --min-seconds (same step count on every rank), clocks sampled throughout
+    sustained = None
+    if not light and args.min_seconds > 0:
+        n_sus = int(np.ceil(args.min_seconds * 1000.0 / (ms / K)))
+        samp2 = ClockSampler(local_rank)
+        if rank == 0:
+            samp2.start()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        u0.record(stream)
+        for i in range(n_sus):
+            j = i % nb
+            fe.upload(left_dev[j], right_dev[j]); fe.run()
+            if (i & 15) == 15:
+                torch.cuda.synchronize()          # bound the launch queue; 16 steps of work stay queued behind it
+        u1.record(stream)
+        barrier()
+        sus_ms = max_over_ranks(u0.elapsed_time(u1))
+        sustained = {"value": world * B * n_sus / (sus_ms / 1000.0), "unit": UNIT, "seconds": sus_ms / 1000.0, "steps": n_sus,
+                     "ms_per_step": sus_ms / n_sus, "clocks": samp2.stop() if rank == 0 else None}
 
     # ---- end to end: host buffers, H2D + D2H of every step inside the timed region ---------------------
     # (a) the pipelined public call: submit/wait keeps two batches in flight, so the PCIe copies of the neighbouring
@@ -279,20 +363,22 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = world * B * K / (e2e_ms / 1000.0)
     assert int(out["n_left"].min()) > 0
 
-    Ks = max(2, K // 2)
-    for i in range(2):
-        fe.process(left_pin[i % nb], right_pin[i % nb])
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(Ks):
-        j = (Wm + i) % nb
-        out = fe.process(left_pin[j], right_pin[j])
-    barrier()
-    sync_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0)
-    e2e_sync_value = world * B * Ks / (sync_ms / 1000.0)
+    e2e_sync_value = None
+    if not light:
+        Ks = max(2, K // 2)
+        for i in range(2):
+            fe.process(left_pin[i % nb], right_pin[i % nb])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Ks):
+            j = (Wm + i) % nb
+            out = fe.process(left_pin[j], right_pin[j])
+        barrier()
+        sync_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0)
+        e2e_sync_value = world * B * Ks / (sync_ms / 1000.0)
 
     raw_line = None
-    if args.raw:
+    if args.raw and not light:
         # optional: raw BGR camera frames + CLAHE + rectification maps in front of the same path (processor::process,
         # SURVEY 8 f1); 3x the H2D bytes, three more streaming kernels per step
         yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
@@ -320,12 +406,21 @@ def run_ours(args, rank, world, local_rank):
                     "input": "BGR frames; BGR2GRAY + CLAHE(4.0) + remap(INTER_LINEAR) on the device before the pyramids"}
         fe.set_preprocess(1, False, 4.0, None)
 
+    line = None
     if rank == 0:
         peak, peak_src = peaks()
         P = sum(((W + (1 << l) - 1) >> l) * ((H + (1 << l) - 1) >> l) for l in range(fe_levels(W, H)))
         klt_bytes = B * 8 * (2 * P + 21 * kp_mean)          # 8 KLT calls x (two pyramids + points in/out)
         klt_s = stage_ms["klt"] / 1000.0
         achieved = klt_bytes / klt_s / 1e9 if klt_s > 0 else 0.0
+        # per-stage algorithmic bytes of SURVEY 8(d) (per stereo frame: both images) against the stage's device time
+        cells = (W // CELL[0]) * (H // CELL[1])
+        stage_bytes = {"pyramid": 2 * P, "fast_grid": 2 * (W * H + 16 * cells), "orb": 4 * W * H + 2 * kp_mean * (512 + 32),
+                       "match": 80 * kp_mean, "klt": 8 * (2 * P + 21 * kp_mean)}
+        stage_roofline = {k: {"algorithmic_bytes_per_step": B * b, "ms": stage_ms[k],
+                              "achieved_gbs": (B * b / (stage_ms[k] * 1e-3) / 1e9) if stage_ms[k] > 0 else None,
+                              "frac_of_hbm_peak": (B * b / (stage_ms[k] * 1e-3) / 1e9 / peak) if stage_ms[k] > 0 else None}
+                          for k, b in stage_bytes.items()}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -341,28 +436,86 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "stage_ms_per_step": stage_ms,
+            "stage_roofline": stage_roofline,
+            "rank_ms_per_step": {"min": min(rank_ms), "median": float(np.median(rank_ms)), "max": max(rank_ms)},
             "stage_timing": {"ms_per_step": staged_pass_ms, "steps": K,
                              "note": "same K batches run eagerly with CUDA events between the stages, immediately before the "
                                      "timed region; the timed region replays one CUDA graph per batch"},
             "roofline": {"kernel": "k_klt_track (fused forward+backward LK, 4 pairs x B frames per launch)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": klt_traffic(B),
+                         "frac": achieved / peak if peak else None, "traffic": klt_traffic(B) if CFG["name"] == "C2" else None,
                          "algorithmic_bytes_per_launch": klt_bytes, "avg_launch_ms": stage_ms["klt"],
                          "peak_source": peak_src,
                          "note": "KLT is instruction-issue bound (ncu: 85 % issue-active, DRAM 1.3 % of peak), not HBM bound "
                                  "(SURVEY 8d); the compulsory-bytes figure is reported as the contract asks, see DESIGN.md"},
         }
-        issue = klt_issue(B, stage_ms["klt"], clocks)
+        issue = klt_issue(B, stage_ms["klt"], clocks) if CFG["name"] == "C2" else None
         if issue:
             line["roofline"]["issue"] = issue
+        if sustained:
+            line["sustained"] = sustained
         if raw_line:
             line["e2e_raw_bgr"] = raw_line
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not light:
             line["cpu_baseline"] = cpu_baseline()
-        emit(line)
     fe.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return line
+
+
+def extras(args, ctx):
+    """Cheap measurements of the other paths, carried in the default line (`extra`): the per-frame seam calls, the stateful
+    device tracker, and one-liners of BASELINE configs 3-5 and the shipped tumvi.yaml configuration.  Rank 0, one GPU."""
+    import copy
+    out = {}
+    keep = CFG["name"]
+
+    def guarded(name, fn):
+        t0 = time.perf_counter()
+        try:
+            out[name] = fn()
+        except Exception as e:                      # an extra must never take the headline line down with it
+            out[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        if isinstance(out[name], dict):
+            out[name]["bench_seconds"] = round(time.perf_counter() - t0, 2)
+
+    def seams():
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_seams
+        return bench_seams.measure(ctx, frames=30, warm=6)
+
+    def tracker():
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_tracker
+        r = bench_tracker.measure(ctx, [1, 32], frames=18)
+        r["call"] = "zs_tracker_track_host / zs_tracker_track / zs_tracker_submit_host: keypoint_tracker::track with its state on the device"
+        return r
+
+    def config(name, steps):
+        def run():
+            a = copy.copy(args)
+            set_config(name)
+            a.batch, a.steps, a.warmup, a.batches = CFG["batch"], steps, 3, 2
+            ln = measure_frontend(a, 0, 1, ctx.device, ctx, light=True)
+            return {k: ln[k] for k in ("value", "unit", "ms_per_step", "steps", "e2e", "stage_ms_per_step", "stage_roofline",
+                                       "gpu_launches")} | {"workload": ln["config"]["workload"], "batch_stereo_frames": a.batch,
+                                                           "keypoints_per_image": ln["config"]["keypoints_per_image"],
+                                                           "roofline_klt_frac": ln["roofline"]["frac"]}
+        return run
+
+    def c3():
+        a = copy.copy(args)
+        a.batch, a.steps, a.warmup = 64, 5, 3
+        ln = measure_c3(a, 0, 1, ctx, light=True)
+        return {k: ln[k] for k in ("value", "unit", "ms_per_step", "steps", "e2e", "roofline", "gpu_launches")}
+
+    guarded("seams_e2e", seams)
+    guarded("tracker", tracker)
+    guarded("C3", c3)
+    guarded("C4", config("C4", 3))
+    guarded("C5", config("C5", 3))
+    guarded("TUMVI", config("TUMVI", 3))
+    set_config(keep)
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -405,7 +558,7 @@ def c3_cpu(cores, pairs_per_worker, seed):
 def run_c3(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from zenslam_b200.runtime import Context, match_l2_cross, match_l2_knn2
+    from zenslam_b200.runtime import Context
     if args.impl == "reference":
         if rank != 0:
             return
@@ -427,8 +580,21 @@ def run_c3(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pin_rank_to_cores(local_rank, world)
     ctx = Context(local_rank)
-    B = 64 if args.batch == 128 else args.batch
+    line = measure_c3(args, rank, world, ctx, light=False)
+    if rank == 0:
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_c3(args, rank, world, ctx, light=False):
+    import torch
+    import torch.distributed as dist
+    from zenslam_b200.runtime import match_l2_cross, match_l2_knn2
+    local_rank = ctx.device
+    B = 64 if args.batch in (0, 128) else args.batch
     K, Wm = args.steps, max(3, args.warmup)
     nb = 3                                                           # 3 x 131 MB of float descriptors > the 126 MB L2
     host = [torch.from_numpy(c3_descriptors(B, 31000 + 97 * rank + i)).pin_memory() for i in range(nb)]
@@ -518,16 +684,15 @@ def run_c3(args, rank, world, local_rank):
                              "note": "integer ops counted as flops against the dense bf16 peak; avg_launch_ms is the WHOLE kNN call "
                                      "(the tensor kernel alone is 84.5 us of it, profiles/r1_l2_tc_persist_epi2_ncu.md); the drain of "
                                      "the accumulators (exact top-2 per query), not the tensor pipe, bounds the kernel -- DESIGN.md"}}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not light:
             cores = os.cpu_count() or 1
             c3_cpu(cores, 1, 50)
             import cv2
             line["cpu_baseline"] = {"value": c3_cpu(cores, 1, 950), "unit": UNIT, "cores": cores, "kind": "reference",
                                     "sample": "%d processes x 1 stereo frame, cv2 %s BFMatcher(NORM_L2) knnMatch + cross-check"
                                               % (cores, cv2.__version__)}
-        emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 def klt_traffic(batch):
@@ -581,11 +746,12 @@ def cpu_baseline():
     out = {"value": frames / busy, "unit": UNIT, "cores": cores, "kind": "port",
            "sample": "%d processes x %d frames of the same workload (reference glue over real cv2 %s calls, "
                      "oracle/cv2_ref.py, 1 OpenCV thread per process)" % (cores, fpw, cv2.__version__)}
+    out.update(cpu_overhead(out["value"], cores))
     # the reference's own deployment shape -- ONE process, OpenCV's default thread pool
     try:
-        from oracle import FrontendOptions, cv2_ref
+        from oracle import cv2_ref
         cv2.setNumThreads(-1)
-        opts = FrontendOptions(CELL, FAST_T, WIN, MAX_LEVEL, KLT_THR, RATIO)
+        opts = cpu_options()
         seq = make_sequence(4, 7100)
         prev = cv2_ref.stereo_frame(seq[0, 0], seq[0, 1], seq[0, 0], seq[0, 1], np.zeros((0, 2), np.float32),
                                     np.zeros((0, 2), np.float32), opts)
@@ -597,6 +763,25 @@ def cpu_baseline():
     except Exception as e:            # the (ii) figure above is the contract's; this one is informational
         out["single_process"] = {"error": str(e)[:200]}
     return out
+
+
+def cpu_overhead(value, cores):
+    """What the Python restatement spends on work the C++ reference does not do (pyramid rebuilds inside the 8 Python LK
+    calls, interpreter time of the per-cell loop), measured on this host, and the baseline with it taken out: the GPU/CPU
+    ratio against `value_without_overhead` is the conservative one."""
+    try:
+        import cv2
+        from oracle import cv2_ref
+        cv2.setNumThreads(1)
+        ov = cv2_ref.overhead_estimate(make_sequence(1, 7200)[0, 0], cpu_options())
+        per_frame = cores / value                       # seconds one worker spends per stereo frame
+        frac = min(0.9, (ov["pyramid_rebuild"] + ov["python_cell_loop"]) / per_frame)
+        return {"overhead_not_in_reference": {"pyramid_rebuild_ms_per_frame": 1e3 * ov["pyramid_rebuild"],
+                                              "python_cell_loop_ms_per_frame": 1e3 * ov["python_cell_loop"],
+                                              "fraction_of_frame": frac},
+                "value_without_overhead": value / (1.0 - frac)}
+    except Exception as e:
+        return {"overhead_not_in_reference": {"error": str(e)[:200]}}
 
 
 _JSON_FD = None
@@ -629,20 +814,22 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="stereo frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="stereo frames per step per GPU (default: the configuration's, 128 at C2)")
     ap.add_argument("--batches", type=int, default=2, help="distinct synthetic batches cycled through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--raw", action="store_true", help="also time the end-to-end path fed with raw BGR frames (device pre-processing)")
-    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"],
-                    help="C2 (default, the headline): 752x480 cells 16; C3: 2000 x 2000 SIFT-shaped L2 matching per stereo frame (match stage only); C4: 1280x1024 cells 32; C5: 3840x2160 cells 32")
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5", "TUMVI", "TUMVI752"],
+                    help="C2 (default, the headline): 752x480 cells 16; C3: 2000 x 2000 SIFT-shaped L2 matching per stereo frame "
+                         "(match stage only); C4: 1280x1024 cells 32; C5: 3840x2160 cells 32; TUMVI: the reference's shipped "
+                         "tumvi.yaml (cells 64, thr 1, PARALLEL_GRID, KLT 63x63 / max_level 4) at 1024x1024; TUMVI752: same at 752x480")
+    ap.add_argument("--min-seconds", type=float, default=5.0,
+                    help="after the K timed steps, keep stepping for at least this long and report the sustained figure "
+                         "(value, clocks) next to the burst one; 0 disables")
+    ap.add_argument("--no-extra", action="store_true", help="skip the `extra` block (per-frame seams, stateful tracker, C3/C4/C5 one-liners)")
     args = ap.parse_args()
-    global W, H, CELL, WORKLOAD
-    if args.config not in ("C2", "C3"):
-        W, H = (1280, 1024) if args.config == "C4" else (3840, 2160)
-        CELL = (32, 32)
-        WORKLOAD = WORKLOAD.replace("C2: 752x480", "%s: %dx%d" % (args.config, W, H)).replace("16x16 cells", "32x32 cells")
-        if args.batch == 128:
-            args.batch = 64 if args.config == "C4" else 16
+    set_config("C2" if args.config == "C3" else args.config)
+    if args.batch <= 0:
+        args.batch = CFG["batch"]
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     rank = int(os.environ.get("RANK", "0"))

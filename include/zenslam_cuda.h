@@ -63,6 +63,9 @@ ZS_API zs_status zs_context_synchronize(zs_context* ctx);
 ZS_API void* zs_context_stream(zs_context* ctx);
 /* number of kernels this library has launched on the context since creation */
 ZS_API uint64_t zs_context_launch_count(const zs_context* ctx);
+/* The ZS_* A/B switches are environment variables read once, when the context is created, never on a
+ * launch path; this re-reads them (measurement / test hook; every variant computes the same results). */
+ZS_API zs_status zs_context_reload_switches(zs_context* ctx);
 
 /* ---- pre-processing: processor::process (zenslam_core/source/processor.cpp:25-55), SURVEY 8(f1) -----------
  * utils::convert_color(BGR2GRAY) -> optional CLAHE(4.0, 8x8) (processor.h:38) -> utils::rectify = cv::remap(INTER_LINEAR)
@@ -256,7 +259,11 @@ ZS_API zs_status zs_track_keypoints_host(zs_context* ctx, const uint8_t* img_0, 
                                          double klt_threshold, float* points_1, uint8_t* status, float* err,
                                          uint8_t* keep);
 /* keypoint_detector_grid::detect_keypoints: occupied [grid_h*grid_w] or NULL; outputs sized
- * grid_w*grid_h (x, y, response) and *32 (desc); *n_out = keypoints that survive ORB's border filter. */
+ * grid_w*grid_h (x, y, response) and *32 (desc); *n_out = keypoints that survive ORB's border filter.
+ * Limit: the reference sends a free cell where FAST finds nothing through _describer->detect (the 8-level ORB detector,
+ * keypoint_detector_grid.cpp:92-95).  That can never yield a keypoint for cells up to 62 px (31-px edge threshold) -- every
+ * configuration of BASELINE.json -- and is not implemented: with cells >= 63 px this call returns ZS_ERR_UNSUPPORTED when
+ * such a cell occurs instead of diverging silently.  PARALLEL_GRID (tumvi.yaml) has no such step in the reference. */
 ZS_API zs_status zs_detect_keypoints_grid_host(zs_context* ctx, const uint8_t* img, int width, int height,
                                                size_t pitch, int cell_w, int cell_h, int threshold,
                                                const uint8_t* occupied, float* x, float* y, float* response,
@@ -389,6 +396,8 @@ typedef struct {
     double klt_threshold;          /* slam.tracking.klt_threshold */
     double matcher_ratio;          /* slam.matcher_ratio */
     int max_iters; double epsilon; double min_eig_threshold;
+    int parallel_grid;             /* slam.detection.algorithm == PARALLEL_GRID: cv::cornerSubPix on the grid corners
+                                      (keypoint_detector_parallel.cpp:160-170); 0 = GRID */
 } zs_frontend_options;
 
 typedef struct {               /* per-frame result views, all HOST pointers, [batch][cap] rows */

@@ -351,6 +351,7 @@ class FrontendOptions:
     klt_max_level: int = 3
     klt_threshold: float = 1.0
     matcher_ratio: float = 0.8
+    parallel_grid: bool = False          # detection.algorithm == PARALLEL_GRID (tumvi.yaml:43)
 
 
 # ---------------------------------------------------------------------------------------------

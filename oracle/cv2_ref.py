@@ -60,12 +60,27 @@ def orb_compute(img, xs, ys, angles=None):
     return kx, ky, desc
 
 
-def detect_keypoints(img, cell=(16, 16), threshold=10, occupied=None):
-    """Full keypoint_detector_grid::detect_keypoints -> (x, y, response, desc)."""
+def corner_subpix(img, xs, ys):
+    """cv::cornerSubPix(image, pts, Size(5,5), Size(-1,-1), {EPS+COUNT, 30, 0.01}) of the PARALLEL_GRID detector
+    (keypoint_detector_parallel.cpp:160-170)."""
+    cv2 = _cv2()
+    if len(xs) == 0:
+        return xs, ys
+    c = np.stack([xs, ys], 1).astype(np.float32).reshape(-1, 1, 2).copy()
+    cv2.cornerSubPix(img, c, (5, 5), (-1, -1), (cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 30, 0.01))
+    return np.ascontiguousarray(c[:, 0, 0]), np.ascontiguousarray(c[:, 0, 1])
+
+
+def detect_keypoints(img, cell=(16, 16), threshold=10, occupied=None, parallel_grid=False):
+    """Full keypoint_detector_grid::detect_keypoints (or, with parallel_grid, keypoint_detector_parallel::detect_keypoints,
+    keypoint_detector_parallel.cpp:40-193) -> (x, y, response, desc)."""
     xs, ys, sc = grid_detect(img, cell, threshold, occupied)
+    if parallel_grid:
+        xs, ys = corner_subpix(img, xs, ys)
     kx, ky, desc = orb_compute(img, xs, ys)
     # responses of the survivors: ORB::compute keeps order, so match by position
-    keep = (xs >= 31) & (xs < img.shape[1] - 31) & (ys >= 31) & (ys < img.shape[0] - 31)
+    rx, ry = np.rint(xs), np.rint(ys)          # ORB's border filter tests cvRound(pt) (round half to even, like np.rint)
+    keep = (rx >= 31) & (rx < img.shape[1] - 31) & (ry >= 31) & (ry < img.shape[0] - 31)
     return kx, ky, sc[keep], desc
 
 
@@ -128,8 +143,9 @@ def stereo_frame(prev_l, prev_r, cur_l, cur_r, prev_kp_l, prev_kp_r, opts):
     win, ml = tuple(opts.klt_window_size), int(opts.klt_max_level)
     cv2.buildOpticalFlowPyramid(cur_l, win, ml)          # utils::pyramid (utils_opencv.cpp:525-530)
     cv2.buildOpticalFlowPyramid(cur_r, win, ml)
-    xl, yl, rl, dl = detect_keypoints(cur_l, opts.cell_size, opts.fast_threshold)
-    xr, yr, rr, dr = detect_keypoints(cur_r, opts.cell_size, opts.fast_threshold)
+    pg = bool(getattr(opts, "parallel_grid", False))
+    xl, yl, rl, dl = detect_keypoints(cur_l, opts.cell_size, opts.fast_threshold, None, pg)
+    xr, yr, rr, dr = detect_keypoints(cur_r, opts.cell_size, opts.fast_threshold, None, pg)
     matches = match_knn_ratio(dl, dr, opts.matcher_ratio)
     kl = np.stack([xl, yl], 1) if len(xl) else np.zeros((0, 2), np.float32)
     kr = np.stack([xr, yr], 1) if len(xr) else np.zeros((0, 2), np.float32)
@@ -139,3 +155,35 @@ def stereo_frame(prev_l, prev_r, cur_l, cur_r, prev_kp_l, prev_kp_r, opts):
     s_rl = track_fb(cur_r, cur_l, kr, None, win, ml, opts.klt_threshold)
     return dict(kp_l=kl, kp_r=kr, resp_l=rl, resp_r=rr, desc_l=dl, desc_r=dr, matches=matches,
                 temporal_l=t_l, temporal_r=t_r, stereo_lr=s_lr, stereo_rl=s_rl)
+
+
+def overhead_estimate(img, opts, reps=3):
+    """What `stereo_frame` spends per stereo frame on work the C++ reference does not do (bench.py reports it next to the CPU
+    baseline so that the GPU/CPU ratio can be bounded):
+      * pyramid rebuilds -- Python's calcOpticalFlowPyrLK takes raw images only, so each of the 8 LK calls rebuilds both image
+        pyramids and the Scharr planes of its source image, while the reference hands over the two pyramids processor.cpp built;
+      * interpreter time of the per-cell loop of `grid_detect` (the reference's loop is C++).
+    Returns seconds per stereo frame: dict(pyramid_rebuild=..., python_cell_loop=...)."""
+    import time
+    cv2 = _cv2()
+    win, ml = tuple(opts.klt_window_size), int(opts.klt_max_level)
+    ta = tb = 1e9
+    for _ in range(reps):
+        t0 = time.perf_counter(); cv2.buildOpticalFlowPyramid(img, win, ml, None, True); ta = min(ta, time.perf_counter() - t0)
+        t0 = time.perf_counter(); cv2.buildOpticalFlowPyramid(img, win, ml, None, False); tb = min(tb, time.perf_counter() - t0)
+    pyr = 8 * 2 * tb + 8 * max(0.0, ta - tb)
+    fast = cv2.FastFeatureDetector_create(int(opts.fast_threshold))
+    h, w = img.shape
+    cw, ch = opts.cell_size
+    loop = 1e9
+    for _ in range(reps):
+        inner = 0.0
+        t0 = time.perf_counter()
+        for gy in range(h // ch):
+            for gx in range(w // cw):
+                roi = img[gy * ch:(gy + 1) * ch, gx * cw:(gx + 1) * cw]
+                t1 = time.perf_counter()
+                fast.detect(roi, None)
+                inner += time.perf_counter() - t1
+        loop = min(loop, time.perf_counter() - t0 - inner)
+    return dict(pyramid_rebuild=pyr, python_cell_loop=2 * loop)

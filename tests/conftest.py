@@ -22,6 +22,25 @@ def golden():
     return load
 
 
+@pytest.fixture
+def switches(monkeypatch):
+    """Set / clear the library's ZS_* A/B switches for one test.  They are read once when a context is created (never on a
+    launch path), so a live context is told to re-read them; everything is restored at teardown."""
+    touched = []
+
+    class Switches:
+        def set(self, ctx, name, value="1"):
+            monkeypatch.setenv(name, str(value)); ctx.reload_switches(); touched.append(ctx)
+
+        def clear(self, ctx, name):
+            monkeypatch.delenv(name, raising=False); ctx.reload_switches(); touched.append(ctx)
+
+    yield Switches()
+    monkeypatch.undo()
+    for c in touched:
+        c.reload_switches()
+
+
 def has_cv2():
     try:
         import cv2  # noqa: F401

@@ -30,10 +30,10 @@ def dev(ctx, a, dtype=None):
 @pytest.mark.parametrize("w,h,win,ml", [(256, 192, (15, 15), 3), (752, 480, (31, 31), 3), (752, 480, (63, 63), 4),
                                         (321, 243, (21, 21), 5), (1280, 720, (31, 21), 3)])
 @pytest.mark.parametrize("path", ["ZS_PYR_FUSED", "ZS_PYR_SPLIT"])
-def test_pyramid_vs_oracle(ctx, w, h, win, ml, path, monkeypatch):
+def test_pyramid_vs_oracle(ctx, w, h, win, ml, path, switches):
     """both builders -- one fused launch per level (few images) and pad / pyrDown / Scharr as separate passes (many)"""
     from zenslam_b200.runtime import Pyramid
-    monkeypatch.setenv(path, "1")
+    switches.set(ctx, path)
     imgs = np.stack([syn.stereo_pair(w, h, 10 + w)[0], syn.stereo_pair(w, h, 11 + w)[1],
                      np.random.default_rng(w).integers(0, 256, (h, w), dtype=np.uint8)])
     p = Pyramid(ctx, w, h, 3, win, ml)
@@ -49,11 +49,11 @@ def test_pyramid_vs_oracle(ctx, w, h, win, ml, path, monkeypatch):
 
 
 @pytest.mark.parametrize("path", ["ZS_PYR_FUSED", "ZS_PYR_SPLIT"])
-def test_pyramid_every_width_residue(ctx, path, monkeypatch):
+def test_pyramid_every_width_residue(ctx, path, switches):
     """the fused builder patches the out-of-image columns of a row's first / last 4-pixel item in registers: every
     residue of the width mod 8 (and both parities of the height) at every level, on white noise"""
     from zenslam_b200.runtime import Pyramid
-    monkeypatch.setenv(path, "1")
+    switches.set(ctx, path)
     for w in range(64, 81):
         h = 40 + (w & 1) + (w >> 2 & 1) * 2
         img = np.random.default_rng(w).integers(0, 256, (2, h, w), dtype=np.uint8)
@@ -398,13 +398,13 @@ def test_klt_multi_job_752(ctx):
 
 
 @pytest.mark.parametrize("groups", [1, 2, 4])
-def test_l2_tensor_core_ragged_pairs_vs_oracle_and_cuda_core(ctx, monkeypatch, groups):
+def test_l2_tensor_core_ragged_pairs_vs_oracle_and_cuda_core(ctx, switches, groups):
     """several pairs of different sizes in one launch (tile tails, pairs with an empty side, counts that are not
     multiples of the 128-row tiles, low-entropy rows full of distance ties), checked against the oracle and against
     the CUDA-core dp4a kernel, for 1 / 2 / 4 epilogue warps per TMEM lane quarter (the column groups of a tile are
     folded with an explicit index tie-break)"""
     from zenslam_b200.runtime import match_l2_cross, match_l2_knn2
-    monkeypatch.setenv("ZS_L2_EPI_GROUPS", str(groups))
+    switches.set(ctx, "ZS_L2_EPI_GROUPS", groups)
     rng = np.random.default_rng(99)
     sizes = [(300, 129), (1, 1), (128, 128), (257, 511), (0, 40), (40, 0), (130, 2), (320, 500)]
     cap_q, cap_t = 320, 512
@@ -423,10 +423,10 @@ def test_l2_tensor_core_ragged_pairs_vs_oracle_and_cuda_core(ctx, monkeypatch, g
     dq, dt, dnq, dnt = dev(ctx, q), dev(ctx, t), dev(ctx, nq), dev(ctx, nt)
     idx, dist, ps = [x.cpu().numpy() for x in match_l2_knn2(ctx, dq, dnq, dt, dnt, 0.8)]
     cidx, cdist = [x.cpu().numpy() for x in match_l2_cross(ctx, dq, dnq, dt, dnt)]
-    monkeypatch.setenv("ZS_L2_NO_TENSOR", "1")
+    switches.set(ctx, "ZS_L2_NO_TENSOR")
     idx2, dist2, ps2 = [x.cpu().numpy() for x in match_l2_knn2(ctx, dq, dnq, dt, dnt, 0.8)]
     cidx2, cdist2 = [x.cpu().numpy() for x in match_l2_cross(ctx, dq, dnq, dt, dnt)]
-    monkeypatch.delenv("ZS_L2_NO_TENSOR")
+    switches.clear(ctx, "ZS_L2_NO_TENSOR")
     for k, (a, b) in enumerate(sizes):
         assert np.array_equal(idx[k, :a], idx2[k, :a]) and np.array_equal(dist[k, :a], dist2[k, :a]), k
         assert np.array_equal(ps[k, :a], ps2[k, :a]) and np.array_equal(cidx[k, :a], cidx2[k, :a])

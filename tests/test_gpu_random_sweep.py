@@ -212,12 +212,12 @@ def test_orb_detector_random(ctx, seed):
 @pytest.mark.parametrize("w,h,win,ml", [(32, 32, (31, 31), 3), (16, 16, (15, 15), 2), (8, 200, (5, 5), 3), (200, 8, (7, 7), 4),
                                         (63, 63, (31, 31), 3), (64, 64, (31, 31), 3), (4096, 16, (9, 9), 2)])
 @pytest.mark.parametrize("path", ["ZS_PYR_FUSED", "ZS_PYR_SPLIT"])
-def test_extreme_frame_shapes(ctx, w, h, win, ml, path, monkeypatch):
+def test_extreme_frame_shapes(ctx, w, h, win, ml, path, switches):
     """frames barely larger than the LK window, one-cell-high strips, very wide rows: level counts, pyramids, Scharr planes,
     grid detection, the ORB border filter and KLT on white noise against the oracle"""
     from zenslam_b200 import LK_GET_MIN_EIGENVALS
     from zenslam_b200.runtime import LK, Pyramid, fast_grid_detect, klt_track, orb_compute
-    monkeypatch.setenv(path, "1")
+    switches.set(ctx, path)
     rng = np.random.default_rng(w * 7 + h)
     img = rng.integers(0, 256, (h, w)).astype(np.uint8)
     img2 = np.roll(img, 1, 1)

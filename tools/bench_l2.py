@@ -38,9 +38,9 @@ def main():
     out = {}
     for name, env in (("tcgen05_i8", None), ("cuda_core_dp4a", "1")):
         if env:
-            os.environ["ZS_L2_NO_TENSOR"] = env
+            os.environ["ZS_L2_NO_TENSOR"] = env; ctx.reload_switches()
         else:
-            os.environ.pop("ZS_L2_NO_TENSOR", None)
+            os.environ.pop("ZS_L2_NO_TENSOR", None); ctx.reload_switches()
         for _ in range(3):
             r = match_l2_knn2(ctx, q, n, t, n, 0.8)
         torch.cuda.synchronize()

@@ -16,24 +16,17 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--sequences", type=int, nargs="+", default=[1, 8, 32])
-    ap.add_argument("--frames", type=int, default=24)
-    ap.add_argument("--width", type=int, default=752)
-    ap.add_argument("--height", type=int, default=480)
-    a = ap.parse_args()
+def measure(ctx, sequences, frames=24, w=752, h=480):
+    """-> {"sequences_S": {...}}: blocking host call, device-resident and pipelined host rates of zs_tracker for every S"""
     from zenslam_b200 import detection_options, slam_options, synthetic as syn, tracking_options
     from zenslam_b200._lib import TrackerResults, check, lib
     from zenslam_b200.keypoint_tracker import device_keypoint_tracker
-    from zenslam_b200.runtime import Context
-    ctx = Context(0)
-    w, h, F = a.width, a.height, a.frames
+    F = frames
     opts = slam_options(detection=detection_options(), tracking=tracking_options(filter_epipolar=False))
     base = [syn.stereo_sequence(w, h, F, 4100 + s, subpixel=True)[0] for s in range(4)]      # four distinct sequences, reused
     out = {}
     p = lambda x: x.ctypes.data_as(C.c_void_p)
-    for S in a.sequences:
+    for S in sequences:
         trk = device_keypoint_tracker(opts, ctx, w, h, sequences=S)
         cap = trk.cap
         n = np.zeros((S, 2), np.int32); nxt = np.zeros(S, np.int32)
@@ -103,7 +96,18 @@ def main():
                                    "device_resident_ms_per_step": ddt * 1e3, "device_resident_stereo_frames_per_s": S / ddt,
                                    "pipelined_ms_per_step": pdt * 1e3, "pipelined_stereo_frames_per_s": S / pdt}
         trk.close(); trk2.close()
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sequences", type=int, nargs="+", default=[1, 8, 32])
+    ap.add_argument("--frames", type=int, default=24)
+    ap.add_argument("--width", type=int, default=752)
+    ap.add_argument("--height", type=int, default=480)
+    a = ap.parse_args()
+    from zenslam_b200.runtime import Context
+    print(json.dumps(measure(Context(0), a.sequences, a.frames, a.width, a.height)))
 
 
 if __name__ == "__main__":

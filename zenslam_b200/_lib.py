@@ -47,7 +47,8 @@ class FrontendOptions(C.Structure):
                 ("cell_w", C.c_int), ("cell_h", C.c_int), ("fast_threshold", C.c_int),
                 ("klt_win_w", C.c_int), ("klt_win_h", C.c_int), ("klt_max_level", C.c_int),
                 ("klt_threshold", C.c_double), ("matcher_ratio", C.c_double),
-                ("max_iters", C.c_int), ("epsilon", C.c_double), ("min_eig_threshold", C.c_double)]
+                ("max_iters", C.c_int), ("epsilon", C.c_double), ("min_eig_threshold", C.c_double),
+                ("parallel_grid", C.c_int)]
 
 
 class FrontendResults(C.Structure):
@@ -76,6 +77,7 @@ SIGNATURES = {
     "zs_context_synchronize": (I, [P]),
     "zs_context_stream": (P, [P]),
     "zs_context_launch_count": (C.c_uint64, [P]),
+    "zs_context_reload_switches": (I, [P]),
     "zs_cvt_bgr2gray": (I, [P, P, Z, Z, I, I, I, P, Z, Z]),
     "zs_clahe": (I, [P, P, Z, Z, I, I, I, D, I, I, P, Z, Z]),
     "zs_remap_linear": (I, [P, P, Z, Z, I, I, I, P, P, Z, Z, I, I, P, Z, Z]),

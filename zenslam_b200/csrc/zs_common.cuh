@@ -25,14 +25,24 @@ struct zs_pyr_view {
     short2* der[ZS_MAX_LEVELS];
     // blurred level-0 image for ORB (un-padded, pitch blur_pitch)
     uint8_t* blur; int blur_pitch; size_t blur_slot;
-    // TMA descriptors in device memory (null when the window is wider than 31): [2*l] = image plane of level l
-    // as a (pitch, padded rows, slots) u8 tensor with a 48x32x1 box; [2*l+1] = derivative plane as u32 elements
-    // with a 36x32x1 box (TMA box origins must be 16-byte aligned).  Coordinates are padded-plane coordinates.
+    // TMA descriptors in device memory: [2*l] = image plane of level l as a (pitch, padded rows, slots) u8 tensor with a
+    // 48x33x1 box; [2*l+1] = derivative plane as u32 elements with a 36x33x1 box (TMA box origins must be 16-byte
+    // aligned): one box = the patch of one 32x32 window tile.  Coordinates are padded-plane coordinates.
     const void* tmaps;
 };
 
+// A/B switches: environment variables read ONCE when a context is created -- never on a launch
+// path -- and again only when zs_context_reload_switches is called (the tests / benches flip them between runs).
+struct zs_switches {
+    bool fe_no_graph, klt_no_tma, klt_no_share, lk_no_cache, fast_v1, l2_no_tensor, l2_one_tile, fast_pretest;
+    int pyr_force;               // 0 = by batch size, 1 = ZS_PYR_SPLIT, 2 = ZS_PYR_FUSED
+    int hamming_splits, hamming_variant, l2_splits, l2_epi_groups, klt_blocks63;   // 0 = default
+};
+void zs_read_switches(zs_switches* s);
+
 struct zs_context {
     int device;
+    zs_switches sw;
     cudaStream_t stream;
     bool own_stream;
     int sm_count;
@@ -112,6 +122,7 @@ typedef CUresult (*zs_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint
 zs_encode_tiled_fn zs_get_encode_tiled();
 
 // internal launchers (defined in the per-stage .cu files)
+bool zs_klt_tiled_window(const zs_context* ctx, const zs_pyramid* p, int win_w, int win_h);
 zs_status zs_launch_orb_blur(zs_context* ctx, const zs_pyramid* p, int first, int count);
 zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_slot, const int* d_next_slot,
                         const float* d_prev_pts, float* d_next_pts, const int* d_count, const int* d_pts_row, int jobs, int cap,

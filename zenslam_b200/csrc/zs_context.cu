@@ -27,16 +27,15 @@ static zs_status make_tensor_maps(zs_pyramid* p)
 {
     zs_pyr_view& v = p->v;
     v.tmaps = nullptr; p->tmaps_dev = nullptr;
-    if (p->win_w > 31 || p->win_h > 31) return ZS_OK;      // patches would not fit the 32x32 box
     zs_encode_tiled_fn enc = zs_get_encode_tiled();
     if (!enc) { zs_set_error("cuTensorMapEncodeTiled is not available from this driver"); return ZS_ERR_CUDA; }
     CUtensorMap maps[2 * ZS_MAX_LEVELS];
     for (int l = 0; l < v.levels; ++l) {
         const cuuint64_t rows = (cuuint64_t)(v.h[l] + 2 * v.pad_y);
         const cuuint64_t dims[3] = { (cuuint64_t)v.pitch[l], rows, (cuuint64_t)v.slots };
-        // TMA needs a 16-byte aligned box origin, so the boxes are wider than the 32 columns a window needs:
-        // 48 bytes cover any byte offset 0..15, 36 (dx,dy) words cover any word offset 0..3
-        const cuuint32_t box[3] = { 48, 32, 1 }, boxd[3] = { 36, 32, 1 }, es[3] = { 1, 1, 1 };
+        // TMA needs a 16-byte aligned box origin, so the boxes are wider than the 33 columns a 32-wide window tile needs:
+        // 48 bytes cover any byte offset 0..15, 36 (dx,dy) words cover any word offset 0..3; 33 rows = 32 + the bilinear row
+        const cuuint32_t box[3] = { 48, 33, 1 }, boxd[3] = { 36, 33, 1 }, es[3] = { 1, 1, 1 };
         const cuuint64_t st8[2] = { (cuuint64_t)v.pitch[l], (cuuint64_t)v.slot_stride[l] };
         CUresult r = enc(&maps[2 * l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, v.img[l], dims, st8, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -53,6 +52,19 @@ static zs_status make_tensor_maps(zs_pyramid* p)
     ZS_CUDA(cudaStreamSynchronize(p->ctx->stream));        // `maps` is on this stack frame
     v.tmaps = p->tmaps_dev;
     return ZS_OK;
+}
+
+void zs_read_switches(zs_switches* s)
+{
+    auto on = [](const char* n) { return getenv(n) != nullptr; };
+    auto num = [](const char* n) { const char* e = getenv(n); return e ? atoi(e) : 0; };
+    s->fe_no_graph = on("ZS_FE_NO_GRAPH"); s->klt_no_tma = on("ZS_KLT_NO_TMA"); s->klt_no_share = on("ZS_KLT_NO_SHARE");
+    s->lk_no_cache = on("ZS_LK_NO_CACHE"); s->fast_v1 = on("ZS_FAST_V1"); s->l2_no_tensor = on("ZS_L2_NO_TENSOR");
+    s->l2_one_tile = on("ZS_L2_ONE_TILE"); s->fast_pretest = on("ZS_FAST_PRETEST");
+    s->pyr_force = on("ZS_PYR_SPLIT") ? 1 : on("ZS_PYR_FUSED") ? 2 : 0;
+    s->hamming_splits = num("ZS_HAMMING_SPLITS"); s->hamming_variant = num("ZS_HAMMING_VARIANT");
+    s->l2_splits = num("ZS_L2_SPLITS"); s->l2_epi_groups = num("ZS_L2_EPI_GROUPS");
+    s->klt_blocks63 = num("ZS_KLT_BLOCKS63");
 }
 
 static thread_local char g_err[512] = "";
@@ -123,6 +135,7 @@ zs_status zs_context_create(int device, void* stream, zs_context** out)
     ZS_CUDA(cudaSetDevice(device));
     zs_context* c = (zs_context*)calloc(1, sizeof(zs_context));
     c->device = device;
+    zs_read_switches(&c->sw);
     c->sm_count = prop.multiProcessorCount;
     if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
     else {
@@ -151,6 +164,13 @@ zs_status zs_context_synchronize(zs_context* c)
 {
     ZS_REQUIRE(c, "ctx is null");
     ZS_CUDA(cudaStreamSynchronize(c->stream));
+    return ZS_OK;
+}
+
+zs_status zs_context_reload_switches(zs_context* c)
+{
+    ZS_REQUIRE(c, "ctx is null");
+    zs_read_switches(&c->sw);
     return ZS_OK;
 }
 

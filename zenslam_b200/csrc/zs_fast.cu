@@ -328,10 +328,14 @@ extern "C" zs_status zs_fast_grid_detect(zs_context* ctx, const zs_pyramid* p, i
     fast_grid_args a;
     a.v = p->v; a.first = first; a.count = count; a.cw = cell_w; a.ch = cell_h; a.gw = gw; a.gh = gh;
     a.threshold = threshold; a.occupied = d_occupied; a.cand = (int*)scratch;
-    if (!getenv("ZS_FAST_V1") && ((cell_w == 16 && cell_h == 16) || (cell_w == 32 && cell_h == 32))) {
+    if (!ctx->sw.fast_v1 && ((cell_w == 16 && cell_h == 16) || (cell_w == 32 && cell_h == 32) || (cell_w == 64 && cell_h == 64))) {
         if (cell_w == 16) {
             const size_t smem = fast_grid_v2_smem<16, 16, 16>();
             k_fast_grid_v2<16, 16, 16><<<dim3(zs_div_up(gw, 16), gh, count), FG2_THREADS, smem, ctx->stream>>>(a);
+        } else if (cell_w == 64) {
+            // the shipped configuration (tumvi.yaml:38: cell_size [64, 64]): one 64x64 cell per block, 28 KB of planes
+            const size_t smem = fast_grid_v2_smem<64, 64, 1>();
+            k_fast_grid_v2<64, 64, 1><<<dim3(gw, gh, count), FG2_THREADS, smem, ctx->stream>>>(a);
         } else {
             // 4 cells (128 px) per block keep the pair planes at 26 KB, so 8 blocks fit an SM instead of 2
             const size_t smem = fast_grid_v2_smem<32, 32, 4>();

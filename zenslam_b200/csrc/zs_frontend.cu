@@ -141,7 +141,7 @@ extern "C" zs_status zs_frontend_create(zs_context* ctx, const zs_frontend_optio
         hn2[2 * B + k] = 2 + (int)k + 1;          ho2[2 * B + k] = (int)(0 * B + k + 1);   hp[0 * B + k + 1] = -1;
         hn2[3 * B + k] = (int)B + 2 + (int)k + 1; ho2[3 * B + k] = (int)(1 * B + k + 1);   hp[1 * B + k + 1] = -1;
     }
-    const bool share = !getenv("ZS_KLT_NO_SHARE") && opt->klt_win_w == 31 && opt->klt_win_h == 31 && fe->pyr->v.tmaps;
+    const bool share = !ctx->sw.klt_no_share && zs_klt_tiled_window(ctx, fe->pyr, opt->klt_win_w, opt->klt_win_h);
     e = cudaMemcpyAsync(fe->job_prev, share ? hp : hpa, sizeof(int) * J, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(fe->job_next, hn, sizeof(int) * J, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(fe->job_row, hr, sizeof(int) * J, cudaMemcpyHostToDevice, ctx->stream);
@@ -158,7 +158,7 @@ extern "C" zs_status zs_frontend_create(zs_context* ctx, const zs_frontend_optio
     free(h);
     if (e != cudaSuccess) { zs_frontend_destroy(fe); return zs_cuda_fail(e, "frontend job tables", __FILE__, __LINE__); }
     fe->share = share;
-    fe->graph_ok = !getenv("ZS_FE_NO_GRAPH");
+    fe->graph_ok = !ctx->sw.fe_no_graph;
     *out = fe;
     return ZS_OK;
 }
@@ -278,6 +278,8 @@ static zs_status frontend_run_body(zs_frontend* fe)
     // 2. detection (keypoint_tracker.cpp:53,69 -> keypoint_detector_grid.cpp:39-150), no occupancy: every cell is searched
     if ((st = zs_fast_grid_detect(ctx, fe->pyr, 2, 2 * B, o.cell_w, o.cell_h, o.fast_threshold, nullptr, fe->raw_xy, fe->raw_resp,
                                   fe->raw_n, cap)) != ZS_OK) return st;
+    // PARALLEL_GRID (what tumvi.yaml:43 ships): cv::cornerSubPix on every selected corner (keypoint_detector_parallel.cpp:160-170)
+    if (o.parallel_grid && (st = zs_corner_subpix(ctx, fe->pyr, 2, 2 * B, fe->raw_xy, fe->raw_n, cap, 5, 5, 30, 0.01)) != ZS_OK) return st;
     ZS_FE_MARK(2);
     // 3. ORB::compute (keypoint_detector_grid.cpp:138)
     if ((st = zs_orb_compute(ctx, fe->pyr, 2, 2 * B, fe->raw_xy, fe->raw_resp, nullptr, fe->raw_n, cap, fe->xy + (size_t)2 * cap * 2,

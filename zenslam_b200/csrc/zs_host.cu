@@ -66,7 +66,7 @@ static zs_status lk_pyramid(zs_context* ctx, int w, int h, const zs_lk_params* p
 
 static zs_status lk_slot(zs_context* ctx, zs_pyramid* p, const uint8_t* img, int w, int h, size_t pitch, int avoid, int* slot)
 {
-    static const bool no_cache = getenv("ZS_LK_NO_CACHE") != nullptr;
+    const bool no_cache = ctx->sw.lk_no_cache;
     const uint64_t hsh = frame_hash(img, w, h, pitch);
     int lru = -1;
     for (int s = 0; s < ZS_LK_CACHE_SLOTS; ++s) {
@@ -215,9 +215,23 @@ static zs_status detect_grid_host(zs_context* ctx, const uint8_t* img, int width
                             (const int*)(base + o_n0), cells, (float*)(base + o_xy), (float*)(base + o_r), nullptr,
                             (int*)(base + o_n), base + o_desc);
     if (st != ZS_OK) return st;
-    int n = 0;
+    int n = 0, n_raw = 0;
     ZS_CUDA(cudaMemcpyAsync(&n, base + o_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(&n_raw, base + o_n0, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!subpix && cell_w >= 63 && cell_h >= 63) {
+        // GRID only (PARALLEL_GRID has no such step): a free cell where FAST finds nothing goes through _describer->detect
+        // (keypoint_detector_grid.cpp:92-95) -- the 8-level ORB detector, which CAN return a keypoint once the cell is wider
+        // than twice its 31-px edge threshold.  That fallback is not implemented: fail loudly instead of diverging silently.
+        int free_cells = cells;
+        if (occupied) for (int i = 0; i < cells; ++i) free_cells -= occupied[i] ? 1 : 0;
+        if (n_raw < free_cells) {
+            zs_set_error("GRID detector with cells >= 63 px: %d free cell(s) without a FAST corner would take the reference's "
+                         "ORB::detect fallback (keypoint_detector_grid.cpp:92-95), which this backend does not implement; use "
+                         "PARALLEL_GRID (no fallback in the reference) or cells <= 62 px", free_cells - n_raw);
+            return ZS_ERR_UNSUPPORTED;
+        }
+    }
     if (n > 0) {
         void* pin;
         if ((st = zs_pinned(ctx, sizeof(float) * 2 * n, &pin)) != ZS_OK) return st;

@@ -408,18 +408,25 @@ __device__ __forceinline__ int dp2a_hi_su(int a_s16x2, unsigned b_u8, int c)
     return d;
 }
 
-// One warp per CTA and 24 CTAs per SM: with 32-thread CTAs ptxas fits the tracker in 80 registers (28 bytes of spill)
-// instead of 125, so 24 warps instead of 16 hide the serial tail of every Gauss-Newton step (REDUX, 2x2 solve, TMA
-// waits); measured 13.25 -> 12.07 ms per 128-frame batch.  20 CTAs: 12.14 ms; 28: 13.3 ms; 32: 14.2 ms (spills).
-#define KLT3_WARPS 1
-#ifndef KLT4_MIN_BLOCKS
-#define KLT4_MIN_BLOCKS 24
-#endif
-#define KLT3_JP 12                   // J / I patch row pitch in words (48-byte TMA box)
-#define KLT3_DP 36                   // derivative patch row pitch in words
-#define KLT3_SJ_BYTES 1664           // 32 TMA rows x 48 B + one spill row read by masked pixels, 128-byte multiple
-#define KLT3_SD_BYTES 4864           // 32 TMA rows x 144 B + spill row (33 x 144 = 4752), 128-byte multiple
-#define KLT3_WARP_BYTES (KLT3_SJ_BYTES + KLT3_SD_BYTES + 128)
+// One warp per 32x32 window tile, one feature per CTA: a 31x31 window is one tile (one-warp CTAs, 24 per SM: with 32-thread
+// CTAs ptxas fits the tracker in 80 registers instead of 125, so 24 warps instead of 16 hide the serial tail of every
+// Gauss-Newton step -- REDUX, 2x2 solve, TMA waits; measured 13.25 -> 12.07 ms per 128-frame batch; 20 CTAs: 12.14 ms; 28:
+// 13.3 ms; 32: 14.2 ms (spills)).  A 63x63 window (tumvi.yaml:45) is 2x2 tiles = four warps that each run the same code on
+// their own TMA-staged patch and add their exact integer partial sums through shared memory (one CTA barrier per sum set,
+// double-buffered); every warp then repeats the scalar tail on identical numbers, so control flow stays CTA-uniform.
+#define KLT4_JP 12                   // J / I patch row pitch in words (48-byte TMA box)
+#define KLT4_DP 36                   // derivative patch row pitch in words
+#define KLT4_ROWS 33                 // TMA box rows: 32 window rows + the bilinear row below
+#define KLT4_SJ_BYTES 1664           // 33 rows x 48 B = 1584, rounded to a 128-byte multiple
+#define KLT4_SD_BYTES 4864           // 33 rows x 144 B = 4752, rounded to a 128-byte multiple
+#define KLT4_WARP_BYTES (KLT4_SJ_BYTES + KLT4_SD_BYTES + 128)
+
+template <int WW, int WH>
+struct klt4_cfg {
+    static constexpr int TX = (WW + 31) / 32, TY = (WH + 31) / 32, NT = TX * TY;       // tiles = warps per CTA
+    static constexpr int LW = WW - 32 * (TX - 1), LH = WH - 32 * (TY - 1);             // size of the last tile column / row
+    static constexpr int JB = TY > 1 ? 4 : (WH + 7) / 8;                               // 8-row bands a tile sweeps
+};
 
 // the eight (x, x+1) byte pairs of a lane's row: R0 = bytes 0..3, F0 = bytes 1..4, R1 = bytes 4..7, F1 = bytes 5..8
 struct row8 { unsigned R0, F0, R1, F1; };
@@ -446,6 +453,29 @@ __device__ __forceinline__ int sample8(int wt, int wb, const row8& a, const row8
     return acc >> 9;
 }
 
+// exact sum of N per-warp totals over the NT warps of the CTA (identity for one-warp CTAs).  red = [2][NT][N] in shared
+// memory; the buffer alternates so that one barrier per call suffices (a warp can only overwrite a buffer after every
+// warp has passed the barrier of the call in between, i.e. after every warp has read it).
+template <int NT, int N>
+__device__ __forceinline__ void cta_sum(long long (&v)[N], long long* red, int& phase, int warp, int lane)
+{
+    if (NT == 1) return;
+    long long* buf = red + phase * (NT * 5);
+    if (lane == 0) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) buf[warp * 5 + n] = v[n];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        long long t = 0;
+#pragma unroll
+        for (int w = 0; w < NT; ++w) t += buf[w * 5 + n];
+        v[n] = t;
+    }
+    phase ^= 1;
+}
+
 // Up to two targets per source point: the per-level template (I patch, gradients, A matrix) depends only on the
 // source image and point, so jobs that track the SAME keypoints of the SAME image into two different images
 // (stereo L->R of frame k and temporal L_k -> L_{k+1}) share it and only the Gauss-Newton loops run twice.
@@ -453,19 +483,24 @@ struct lk_state { float outx, outy; int status; };
 
 template <int WW, int WH>
 __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i, int slot_j0, int slot_j1, int ntgt,
-                                                  float2 prev, float2 init, bool use_init, int lane, uint8_t* sJ, uint8_t* sD,
-                                                  uint32_t bar, uint32_t& parity, lk_state& t0, lk_state& t1, float& err)
+                                                  float2 prev, float2 init, bool use_init, int warp, int lane, uint8_t* sJ,
+                                                  uint8_t* sD, uint32_t bar, uint32_t& parity, long long* red, int& phase,
+                                                  lk_state& t0, lk_state& t1, float& err)
 {
+    typedef klt4_cfg<WW, WH> cfg;
     const zs_pyr_view& v = a.v;
     const float hwx = (float)(WW - 1) * 0.5f, hwy = (float)(WH - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (float)(1 << 20);
     t0.status = 1; t1.status = 1; t0.outx = t0.outy = t1.outx = t1.outy = 0.f; err = 0.f;
     const int top = min(a.max_level, v.levels - 1);
     const int k = lane & 3, g = lane >> 2;
+    // this warp's tile: origin offset inside the window and valid size (compile-time for single-tile windows)
+    const int tx = cfg::TX == 1 ? 0 : warp % cfg::TX, ty = cfg::TY == 1 ? 0 : warp / cfg::TX;
+    const int tw = (cfg::TX == 1 || tx == cfg::TX - 1) ? cfg::LW : 32, th = (cfg::TY == 1 || ty == cfg::TY - 1) ? cfg::LH : 32;
     const uint32_t sJ_a = smem_u32(sJ), sD_a = smem_u32(sD);
     const char* maps = (const char*)v.tmaps;
-    const uint32_t* jbase = (const uint32_t*)sJ + g * KLT3_JP + 2 * k;
-    const uint32_t* dbase = (const uint32_t*)sD + g * KLT3_DP + 8 * k;
+    const uint32_t* jbase = (const uint32_t*)sJ + g * KLT4_JP + 2 * k;
+    const uint32_t* dbase = (const uint32_t*)sD + g * KLT4_DP + 8 * k;
 
     for (int level = top; level >= 0; --level) {
         const int cols = v.w[level], rows = v.h[level];
@@ -489,18 +524,18 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
         int w00, w01, w10, w11;
         lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
 
-        // ---- fetch the I patch (into the J buffer) and the derivative patch
-        const int gx = v.pad_x + ipx, gy = v.pad_y + ipy;          // padded-plane coordinates, gx >= 1
+        // ---- fetch the I patch (into the J buffer) and the derivative patch of this warp's tile
+        const int gx = v.pad_x + ipx + 32 * tx, gy = v.pad_y + ipy + 32 * ty;      // padded-plane coordinates, gx >= 1
         __syncwarp();
         if (lane == 0) {
-            mbar_expect_tx(bar, 48 * 32 + 36 * 4 * 32);
+            mbar_expect_tx(bar, (48 + 36 * 4) * KLT4_ROWS);
             tma_load_3d(sJ_a, maps + (size_t)(2 * level) * 128, gx & ~15, gy, slot_i, bar);
             tma_load_3d(sD_a, maps + (size_t)(2 * level + 1) * 128, gx & ~3, gy, slot_i, bar);
         }
         mbar_wait(bar, parity); parity ^= 1;
 
-        // ---- template in registers: 4 row steps x 8 pixels per lane
-        int Ix[4][8], Iy[4][8];
+        // ---- template in registers: JB row bands x 8 pixels per lane
+        int Ix[cfg::JB][8], Iy[cfg::JB][8];
         int pA11 = 0, pA12 = 0, pA22 = 0, pc1 = 0, pc2 = 0;
         {
             const int wt = pack_s16x2(w00, w01), wb = pack_s16x2(w10, w11);
@@ -508,27 +543,27 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
             const int sh = (gx & 3) * 8;
             const uint32_t* dw = dbase + (gx & 3);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const row8 ra = load_row8(jw + j * 8 * KLT3_JP, sh), rb = load_row8(jw + (j * 8 + 1) * KLT3_JP, sh);
-                int tx[9], ty[9], bx[9], by[9];
+            for (int j = 0; j < cfg::JB; ++j) {
+                const row8 ra = load_row8(jw + j * 8 * KLT4_JP, sh), rb = load_row8(jw + (j * 8 + 1) * KLT4_JP, sh);
+                int tx_[9], ty_[9], bx[9], by[9];
 #pragma unroll
                 for (int q = 0; q < 9; ++q) {
-                    const unsigned dt = dw[j * 8 * KLT3_DP + q], db = dw[(j * 8 + 1) * KLT3_DP + q];
-                    tx[q] = (int)(short)(dt & 0xffff); ty[q] = (int)dt >> 16;
+                    const unsigned dt = dw[j * 8 * KLT4_DP + q], db = dw[(j * 8 + 1) * KLT4_DP + q];
+                    tx_[q] = (int)(short)(dt & 0xffff); ty_[q] = (int)dt >> 16;
                     bx[q] = (int)(short)(db & 0xffff); by[q] = (int)db >> 16;
                 }
-                const bool row_masked = (8 * j + 7 >= WH) && (8 * j + g >= WH);
+                const bool row_masked = (8 * j + 7 >= cfg::LH) && (8 * j + g >= th);
                 int iv[8];
                 iv[0] = sample8<0>(wt, wb, ra, rb); iv[1] = sample8<1>(wt, wb, ra, rb); iv[2] = sample8<2>(wt, wb, ra, rb);
                 iv[3] = sample8<3>(wt, wb, ra, rb); iv[4] = sample8<4>(wt, wb, ra, rb); iv[5] = sample8<5>(wt, wb, ra, rb);
                 iv[6] = sample8<6>(wt, wb, ra, rb); iv[7] = sample8<7>(wt, wb, ra, rb);
 #pragma unroll
                 for (int pp = 0; pp < 8; ++pp) {
-                    int ixv = (tx[pp] * w00 + tx[pp + 1] * w01 + bx[pp] * w10 + bx[pp + 1] * w11 + (1 << 13)) >> 14;
-                    int iyv = (ty[pp] * w00 + ty[pp + 1] * w01 + by[pp] * w10 + by[pp + 1] * w11 + (1 << 13)) >> 14;
-                    if ((8 * j + 7 >= WH) || (24 + pp >= WW)) {      // compile-time: only overhanging rows / columns
+                    int ixv = (tx_[pp] * w00 + tx_[pp + 1] * w01 + bx[pp] * w10 + bx[pp + 1] * w11 + (1 << 13)) >> 14;
+                    int iyv = (ty_[pp] * w00 + ty_[pp + 1] * w01 + by[pp] * w10 + by[pp + 1] * w11 + (1 << 13)) >> 14;
+                    if ((8 * j + 7 >= cfg::LH) || (24 + pp >= cfg::LW)) {      // compile-time: only rows / columns some tile masks
                         bool masked = row_masked;
-                        if (24 + pp >= WW) masked = masked || (8 * k + pp >= WW);
+                        if (24 + pp >= cfg::LW) masked = masked || (8 * k + pp >= tw);
                         if (masked) { ixv = 0; iyv = 0; }
                     }
                     Ix[j][pp] = ixv; Iy[j][pp] = iyv;
@@ -537,10 +572,11 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
                 }
             }
         }
-        const long long sA11 = warp_sum_exact(pA11), sA12 = warp_sum_exact(pA12), sA22 = warp_sum_exact(pA22);
-        const long long sc1 = warp_sum_exact(pc1), sc2 = warp_sum_exact(pc2);
-        const float A11 = __fmul_rn(__ll2float_rn(sA11), FLT_SCALE), A12 = __fmul_rn(__ll2float_rn(sA12), FLT_SCALE),
-                    A22 = __fmul_rn(__ll2float_rn(sA22), FLT_SCALE);
+        long long sT[5] = { warp_sum_exact(pA11), warp_sum_exact(pA12), warp_sum_exact(pA22), warp_sum_exact(pc1), warp_sum_exact(pc2) };
+        cta_sum<cfg::NT, 5>(sT, red, phase, warp, lane);
+        const long long sc1 = sT[3], sc2 = sT[4];
+        const float A11 = __fmul_rn(__ll2float_rn(sT[0]), FLT_SCALE), A12 = __fmul_rn(__ll2float_rn(sT[1]), FLT_SCALE),
+                    A22 = __fmul_rn(__ll2float_rn(sT[2]), FLT_SCALE);
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
         const float dA = __fsub_rn(A11, A22);
         const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
@@ -567,12 +603,12 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
                     status = 0;
                     break;
                 }
-                const int jx = v.pad_x + inx, jy = v.pad_y + iny;
+                const int jx = v.pad_x + inx + 32 * tx, jy = v.pad_y + iny + 32 * ty;
                 if ((jx & ~15) != cur_x0 || jy != cur_y) {
                     __syncwarp();                                  // every lane is done with the previous patch
                     cur_x0 = jx & ~15; cur_y = jy;
                     if (lane == 0) {
-                        mbar_expect_tx(bar, 48 * 32);
+                        mbar_expect_tx(bar, 48 * KLT4_ROWS);
                         tma_load_3d(sJ_a, maps + (size_t)(2 * level) * 128, cur_x0, cur_y, slot_j, bar);
                     }
                     mbar_wait(bar, parity); parity ^= 1;
@@ -583,8 +619,8 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
                 const int sh = (jx & 3) * 8;
                 int pb1 = 0, pb2 = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const row8 ra = load_row8(jw + j * 8 * KLT3_JP, sh), rb = load_row8(jw + (j * 8 + 1) * KLT3_JP, sh);
+                for (int j = 0; j < cfg::JB; ++j) {
+                    const row8 ra = load_row8(jw + j * 8 * KLT4_JP, sh), rb = load_row8(jw + (j * 8 + 1) * KLT4_JP, sh);
                     int jv;
                     jv = sample8<0>(wt, wb, ra, rb); pb1 += jv * Ix[j][0]; pb2 += jv * Iy[j][0];
                     jv = sample8<1>(wt, wb, ra, rb); pb1 += jv * Ix[j][1]; pb2 += jv * Iy[j][1];
@@ -595,7 +631,9 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
                     jv = sample8<6>(wt, wb, ra, rb); pb1 += jv * Ix[j][6]; pb2 += jv * Iy[j][6];
                     jv = sample8<7>(wt, wb, ra, rb); pb1 += jv * Ix[j][7]; pb2 += jv * Iy[j][7];
                 }
-                const long long sb1 = warp_sum_exact(pb1) - sc1, sb2 = warp_sum_exact(pb2) - sc2;
+                long long sB[2] = { warp_sum_exact(pb1), warp_sum_exact(pb2) };
+                cta_sum<cfg::NT, 2>(sB, red, phase, warp, lane);
+                const long long sb1 = sB[0] - sc1, sb2 = sB[1] - sc2;
                 const float b1 = __fmul_rn(__ll2float_rn(sb1), FLT_SCALE), b2 = __fmul_rn(__ll2float_rn(sb2), FLT_SCALE);
                 const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
                 const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
@@ -621,37 +659,37 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
     }
 }
 
-// grid: (ceil(cap / KLT3_WARPS), jobs); dynamic smem = KLT3_WARPS * KLT3_WARP_BYTES
+// grid: (cap, jobs); block = one warp per window tile; dynamic smem = tiles * KLT4_WARP_BYTES
 // passes: 0 = forward (one or two targets), 1 = backward of target 0, 2 = backward of target 1 (fb only); one
 // inlined instance of the tracker serves all passes (keeps the code inside the instruction cache).
-template <int WW, int WH>
-__global__ void __launch_bounds__(KLT3_WARPS * 32, KLT4_MIN_BLOCKS) k_klt_track_v4(klt_args a)
+template <int WW, int WH, int MINB>
+__global__ void __launch_bounds__(klt4_cfg<WW, WH>::NT * 32, MINB) k_klt_track_v4(klt_args a)
 {
+    typedef klt4_cfg<WW, WH> cfg;
     extern __shared__ __align__(128) uint8_t smem3[];
+    __shared__ long long s_red[cfg::NT > 1 ? 2 * cfg::NT * 5 : 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int job = a.job_list ? a.job_list[blockIdx.y] : blockIdx.y;
     const int slot_src = a.prev_slot[job];
     if (slot_src < 0) return;                                  // job folded into another job's second target
-    const int i = blockIdx.x * KLT3_WARPS + warp;
+    const int i = blockIdx.x;
     const int in_row = a.pts_row ? a.pts_row[job] : job;
     if (i >= min(a.count[in_row], a.cap)) return;
-    uint8_t* sJ = smem3 + (size_t)warp * KLT3_WARP_BYTES;
-    uint8_t* sD = sJ + KLT3_SJ_BYTES;
-    const uint32_t bar = smem_u32(sD + KLT3_SD_BYTES);
+    uint8_t* sJ = smem3 + (size_t)warp * KLT4_WARP_BYTES;
+    uint8_t* sD = sJ + KLT4_SJ_BYTES;
+    const uint32_t bar = smem_u32(sD + KLT4_SD_BYTES);
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // the spill rows are read (never used) by masked pixels; give them defined contents
-    ((uint32_t*)(sJ + 48 * 32))[lane] = 0;
-    ((uint32_t*)(sD + 144 * 32))[lane] = 0; ((uint32_t*)(sD + 144 * 32))[lane + 4] = 0;
     __syncwarp();
     uint32_t parity = 0;
+    int phase = 0;
     // Per-warp bookkeeping lives in the 128-byte scratch line behind the barrier (warp-uniform values, written by
     // every lane with the same data, read back as broadcasts): it would otherwise sit in registers across the
     // whole inlined tracker and push the kernel past 128 registers (4 CTAs per SM).
     //   w[4] slot_src  w[5] slot_t0  w[6] slot_t1  w[7] ntgt  w[8..9] p0  w[10..12] f0  w[13..15] f1  w[16] job1
-    volatile int* w = (volatile int*)(sD + KLT3_SD_BYTES);
+    volatile int* w = (volatile int*)(sD + KLT4_SD_BYTES);
     volatile float* wf = (volatile float*)w;
     {
         const int job1 = a.out_job2 ? a.out_job2[job] : -1;
@@ -661,9 +699,18 @@ __global__ void __launch_bounds__(KLT3_WARPS * 32, KLT4_MIN_BLOCKS) k_klt_track_
     }
     __syncwarp();
     const bool use_init = (a.flags & ZS_LK_USE_INITIAL_FLOW) != 0;
+    const bool writer = lane == 0 && (cfg::NT == 1 || warp == 0);
     const int passes = a.fb ? 1 + w[7] : 1;
 #pragma unroll 1
     for (int pass = 0; pass < passes; ++pass) {
+        const int job1 = w[16];
+        const size_t o0 = (size_t)job * a.cap + i, o1 = (size_t)(job1 >= 0 ? job1 : job) * a.cap + i;
+        // a point whose forward track failed is dropped whatever the backward call returns (keypoint_tracker.cpp:180:
+        // status && status_back && ...), and nothing else of the backward call is visible: skip it
+        if (pass > 0 && !w[9 + 3 * pass]) {
+            if (writer) a.keep[pass == 1 ? o0 : o1] = 0;
+            continue;
+        }
         // pass 0: forward from p0 (one or two targets); pass 1 / 2: backward of target 0 / 1 from its forward result,
         // images swapped, no initial flow (keypoint_tracker.cpp:156-170)
         const int si = pass == 0 ? w[4] : w[4 + pass], sj0 = pass == 0 ? w[5] : w[4], sj1 = w[6];
@@ -672,23 +719,21 @@ __global__ void __launch_bounds__(KLT3_WARPS * 32, KLT4_MIN_BLOCKS) k_klt_track_
         const bool ui = use_init && pass == 0;
         if (ui) init = a.next_pts[(size_t)job * a.cap + i];
         lk_state r0, r1; float err;
-        lk_track_point_v4<WW, WH>(a, si, sj0, sj1, pass == 0 ? w[7] : 1, from, init, ui, lane, sJ, sD, bar, parity, r0, r1, err);
-        const int job1 = w[16];
-        const size_t o0 = (size_t)job * a.cap + i, o1 = (size_t)(job1 >= 0 ? job1 : job) * a.cap + i;
+        lk_track_point_v4<WW, WH>(a, si, sj0, sj1, pass == 0 ? w[7] : 1, from, init, ui, warp, lane, sJ, sD, bar, parity, s_red,
+                                  phase, r0, r1, err);
         if (pass == 0) {
             __syncwarp();
             wf[10] = r0.outx; wf[11] = r0.outy; w[12] = r0.status; wf[13] = r1.outx; wf[14] = r1.outy; w[15] = r1.status;
             __syncwarp();
-            if (lane == 0) {
+            if (writer) {
                 a.next_pts[o0] = make_float2(r0.outx, r0.outy); a.status[o0] = (uint8_t)r0.status; a.err[o0] = err;
                 if (job1 >= 0) { a.next_pts[o1] = make_float2(r1.outx, r1.outy); a.status[o1] = (uint8_t)r1.status; a.err[o1] = err; }
             }
-        } else if (lane == 0) {
+        } else if (writer) {
             // cv::norm(Point2f) -> sqrt((double)dx*dx + (double)dy*dy) < klt_threshold (keypoint_tracker.cpp:180)
             const float dx = __fsub_rn(r0.outx, wf[8]), dy = __fsub_rn(r0.outy, wf[9]);
             const double nrm = sqrt((double)dx * (double)dx + (double)dy * (double)dy);
-            const int fs = w[9 + 3 * pass];
-            a.keep[pass == 1 ? o0 : o1] = (uint8_t)(fs && r0.status && nrm < a.fb_thr);
+            a.keep[pass == 1 ? o0 : o1] = (uint8_t)(r0.status && nrm < a.fb_thr);
         }
     }
 }
@@ -731,6 +776,13 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) k_klt_track(klt_args a)
     }
 }
 
+// windows the TMA-staged tiled kernel is instantiated for (everything else runs the generic shared-memory kernel)
+bool zs_klt_tiled_window(const zs_context* ctx, const zs_pyramid* p, int win_w, int win_h)
+{
+    if (!p->v.tmaps || ctx->sw.klt_no_tma || win_w != win_h) return false;
+    return win_w == 15 || win_w == 21 || win_w == 31 || win_w == 63;
+}
+
 zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_slot, const int* d_next_slot,
                         const float* d_prev_pts, float* d_next_pts, const int* d_count, const int* d_pts_row, int jobs, int cap,
                         const zs_lk_params* prm, uint8_t* d_status, float* d_err, int fb, double fb_thr, uint8_t* d_keep,
@@ -758,16 +810,30 @@ zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_
         a.eps2_lo = nextafterf((float)(a.eps2 * (1.0 - 1e-6)), 0.f);
         a.eps2_hi = nextafterf((float)(a.eps2 * (1.0 + 1e-6)), 3.0e38f);
     }
-    // TMA-staged kernel for the reference's default window
-    if (a.win_w == 31 && a.win_h == 31 && a.v.tmaps && !getenv("ZS_KLT_NO_TMA")) {
-        const size_t smem3 = (size_t)KLT3_WARPS * KLT3_WARP_BYTES;
+    // TMA-staged tiled kernel: the reference's default 31x31, the shipped 63x63 (tumvi.yaml:45), 21x21 (OpenCV's default), 15x15
+    if (zs_klt_tiled_window(ctx, p, a.win_w, a.win_h)) {
         // with a job list only the jobs that still own work get blocks (folded jobs would launch cap empty CTAs each)
         if (d_job_list && n_list > 0) a.job_list = d_job_list;
-        k_klt_track_v4<31, 31><<<dim3(zs_div_up(cap, KLT3_WARPS), a.job_list ? n_list : jobs), KLT3_WARPS * 32, smem3, ctx->stream>>>(a);
+        const dim3 grid(cap, a.job_list ? n_list : jobs);
+#define KLT4_LAUNCH(W_, H_, MB_)                                                                                               \
+        do {                                                                                                                   \
+            const size_t sm = (size_t)klt4_cfg<W_, H_>::NT * KLT4_WARP_BYTES;                                                  \
+            k_klt_track_v4<W_, H_, MB_><<<grid, klt4_cfg<W_, H_>::NT * 32, sm, ctx->stream>>>(a);                              \
+        } while (0)
+        if (a.win_w == 31) KLT4_LAUNCH(31, 31, 24);
+        else if (a.win_w == 63) {
+            // resident CTAs (of four warps) per SM: 6 = 80 registers with spills, 5 = 96, 4 = 128 and no spills
+            if (ctx->sw.klt_blocks63 == 4) KLT4_LAUNCH(63, 63, 4);
+            else if (ctx->sw.klt_blocks63 == 6) KLT4_LAUNCH(63, 63, 6);
+            else KLT4_LAUNCH(63, 63, 5);
+        }
+        else if (a.win_w == 21) KLT4_LAUNCH(21, 21, 24);
+        else KLT4_LAUNCH(15, 15, 24);
+#undef KLT4_LAUNCH
         ZS_LAUNCH_CHECK(ctx);
         return ZS_OK;
     }
-    ZS_REQUIRE(!d_out_job2, "second targets need the TMA-staged 31x31 kernel");
+    ZS_REQUIRE(!d_out_job2, "second targets need the TMA-staged tiled kernel");
     // specialised register-template kernels for the common window sizes
     {
         const dim3 grid2(zs_div_up(cap, KLT2_WARPS), jobs);

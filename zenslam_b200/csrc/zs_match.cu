@@ -241,13 +241,10 @@ __global__ void __launch_bounds__(256) k_f32_to_u8(const float* __restrict__ src
 // Train-side splitting: a block sweeps `chunk` train rows.  Large maps are cut into 2048-row chunks; small problems are
 // cut too when the grid would otherwise leave the machine short of warps (the kernel is latency-bound per warp).
 #define HAMMING_SPLIT_CHUNK 2048
-static int g_hamming_split_override = -1;
-
-static int hamming_splits(int pairs, int cap_q, int cap_t)
+static int hamming_splits(const zs_context* ctx, int pairs, int cap_q, int cap_t)
 {
-    if (g_hamming_split_override < 0) { const char* e = getenv("ZS_HAMMING_SPLITS"); g_hamming_split_override = e ? atoi(e) : 0; }
     if (cap_t > 2 * HAMMING_SPLIT_CHUNK) return zs_div_up(cap_t, HAMMING_SPLIT_CHUNK);
-    if (g_hamming_split_override > 0) return g_hamming_split_override;
+    if (ctx->sw.hamming_splits > 0) return ctx->sw.hamming_splits;
     const long long blocks = (long long)zs_div_up(cap_q, 128) * pairs;
     int sp = (int)((148LL * 32 + blocks - 1) / blocks);
     const int max_sp = cap_t / 256 > 0 ? cap_t / 256 : 1;
@@ -256,19 +253,18 @@ static int hamming_splits(int pairs, int cap_q, int cap_t)
 }
 static int hamming_chunk(int cap_t, int splits) { return splits > 1 ? (zs_div_up(cap_t, splits) + 127) / 128 * 128 : 0x7fffffff; }
 // ints of scratch the partial top-2 of one direction need (0 when the train side is not split)
-static size_t hamming_part_ints(int pairs, int cap_q, int cap_t)
+static size_t hamming_part_ints(const zs_context* ctx, int pairs, int cap_q, int cap_t)
 {
-    const int sp = hamming_splits(pairs, cap_q, cap_t);
+    const int sp = hamming_splits(ctx, pairs, cap_q, cap_t);
     return sp > 1 ? 4 * (size_t)pairs * cap_q * sp : 0;
 }
 
 static zs_status hamming_top2(zs_context* ctx, const uint8_t* q, const int* nq, size_t qs, const uint8_t* t, const int* nt,
                               size_t ts, int pairs, int cap_q, int cap_t, int* idx, int* dist, void* part)
 {
-    const int splits = hamming_splits(pairs, cap_q, cap_t);
+    const int splits = hamming_splits(ctx, pairs, cap_q, cap_t);
     const int chunk = cap_t > 2 * HAMMING_SPLIT_CHUNK ? HAMMING_SPLIT_CHUNK : hamming_chunk(cap_t, splits);
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv("ZS_HAMMING_VARIANT"); variant = e ? atoi(e) : 0; }
+    const int variant = ctx->sw.hamming_variant;
 #define HAM_LAUNCH(HQ_, CSA_)                                                                                                   \
     k_hamming_top2<HQ_, CSA_><<<dim3(zs_div_up(cap_q, HAMMING_THREADS * HQ_), splits, pairs), HAMMING_THREADS, 0, ctx->stream>>>( \
         q, nq, qs, t, nt, ts, idx, dist, 2 * cap_q, chunk, splits, cap_q, (int4*)part)
@@ -298,7 +294,7 @@ extern "C" zs_status zs_match_hamming_knn2(zs_context* ctx, const uint8_t* d_q, 
                "descriptor arrays must be 16-byte aligned");
     if (pairs == 0) return ZS_OK;
     void* s;
-    zs_status st = zs_scratch(ctx, sizeof(int) * (4 * (size_t)cap_q * pairs + hamming_part_ints(pairs, cap_q, cap_t)), &s);
+    zs_status st = zs_scratch(ctx, sizeof(int) * (4 * (size_t)cap_q * pairs + hamming_part_ints(ctx, pairs, cap_q, cap_t)), &s);
     if (st != ZS_OK) return st;
     int* ti = (int*)s; int* td = ti + 2 * (size_t)cap_q * pairs;
     st = hamming_top2(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, cap_t, ti, td, td + 2 * (size_t)cap_q * pairs);
@@ -319,7 +315,7 @@ extern "C" zs_status zs_match_hamming_cross(zs_context* ctx, const uint8_t* d_q,
     if (pairs == 0) return ZS_OK;
     void* s;
     zs_status st = zs_scratch(ctx, sizeof(int) * (4 * ((size_t)cap_q + cap_t) * pairs +
-                                                  std::max(hamming_part_ints(pairs, cap_q, cap_t), hamming_part_ints(pairs, cap_t, cap_q))), &s);
+                                                  std::max(hamming_part_ints(ctx, pairs, cap_q, cap_t), hamming_part_ints(ctx, pairs, cap_t, cap_q))), &s);
     if (st != ZS_OK) return st;
     int* fi = (int*)s; int* fd = fi + 2 * (size_t)cap_q * pairs;
     int* bi = fd + 2 * (size_t)cap_q * pairs; int* bd = bi + 2 * (size_t)cap_t * pairs;
@@ -371,7 +367,7 @@ static zs_status l2_top2(zs_context* ctx, const uint8_t* q8, const int* nq, cons
 {
     // 128-dim (SIFT) rows take the tcgen05 path; ZS_L2_NO_TENSOR=1 selects the CUDA-core dp4a kernel instead
     // (used by tools/bench_l2.py and the tests to cross-check the two implementations)
-    if (dim == 128 && !getenv("ZS_L2_NO_TENSOR")) return zs_l2_tensor_top2(ctx, q8, nq, t8, nt, pairs, cap_q, cap_t, dim, idx, dist, part);
+    if (dim == 128 && !ctx->sw.l2_no_tensor) return zs_l2_tensor_top2(ctx, q8, nq, t8, nt, pairs, cap_q, cap_t, dim, idx, dist, part);
     const dim3 grid(zs_div_up(cap_q, MATCH_THREADS), pairs);
 #define L2_CASE(NW)                                                                                          \
     case NW:                                                                                                 \

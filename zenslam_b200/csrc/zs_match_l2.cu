@@ -549,10 +549,10 @@ zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, c
     if (st != ZS_OK) return st;
     if ((st = l2_make_map(&mt, t8, (size_t)pairs * cap_t)) != ZS_OK) return st;
     const int q_tiles = zs_div_up(cap_q, L2TC_M), t_tiles = zs_div_up(cap_t, L2TC_N);
-    if (!getenv("ZS_L2_ONE_TILE")) {
+    if (!ctx->sw.l2_one_tile) {
         // persistent kernel: enough CTAs for two waves of 2 CTAs per SM, otherwise as many train tiles per CTA as possible
         int splits = (int)((4LL * ctx->sm_count + (long long)q_tiles * pairs - 1) / ((long long)q_tiles * pairs));
-        if (const char* es = getenv("ZS_L2_SPLITS")) splits = atoi(es);
+        if (ctx->sw.l2_splits > 0) splits = ctx->sw.l2_splits;
         splits = splits < 1 ? 1 : splits > t_tiles ? t_tiles : splits;
         l2p_args b;
         b.nq = nq; b.nt = nt; b.cap_q = cap_q; b.cap_t = cap_t;
@@ -572,8 +572,7 @@ zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, c
             ZS_CUDA(cudaFuncSetAttribute(k_l2_tc_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_p = true;
         }
-        const char* eg = getenv("ZS_L2_EPI_GROUPS");             // 1, 2 or 4 epilogue warps per TMEM lane quarter
-        const int cgsel = eg ? atoi(eg) : 2;
+        const int cgsel = ctx->sw.l2_epi_groups > 0 ? ctx->sw.l2_epi_groups : 2;   // 1, 2 or 4 epilogue warps per TMEM lane quarter
         const dim3 grid(q_tiles, b.splits, pairs);
         if (cgsel == 1) k_l2_tc_persist<1><<<grid, 64 + 128, smem, ctx->stream>>>(mq, mt, b);
         else if (cgsel == 2) k_l2_tc_persist<2><<<grid, 64 + 256, smem, ctx->stream>>>(mq, mt, b);

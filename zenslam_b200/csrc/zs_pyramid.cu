@@ -297,7 +297,7 @@ extern "C" zs_status zs_pyramid_build(zs_context* ctx, zs_pyramid* p, int first,
     // for 2 with the flat pad items), 32 images 79 vs 82 us (whole step equal), 64: 135 vs 121, 128: 247 vs 199, 256: 468 vs
     // 357 -- with many images in flight the three separate streaming passes win, with few the launch count does.
     // ZS_PYR_SPLIT / ZS_PYR_FUSED force one or the other.
-    const int force = getenv("ZS_PYR_SPLIT") ? 1 : getenv("ZS_PYR_FUSED") ? 2 : 0;
+    const int force = ctx->sw.pyr_force;
     const bool split = force == 1 || (force == 0 && count > 16);
     for (int l = 0; l < v.levels; ++l) {
         const int w = v.w[l], h = v.h[l];

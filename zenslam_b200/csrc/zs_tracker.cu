@@ -347,7 +347,7 @@ extern "C" zs_status zs_tracker_create(zs_context* ctx, const zs_tracker_options
         free(hs);
         if (e != cudaSuccess) { cudaFree(t->dev); zs_pyramid_destroy(t->pyr); free(t); return zs_cuda_fail(e, "tracker tables", __FILE__, __LINE__); }
     }
-    t->graph_ok = !getenv("ZS_FE_NO_GRAPH");
+    t->graph_ok = !ctx->sw.fe_no_graph;
     *out = t;
     return ZS_OK;
 }

@@ -26,7 +26,7 @@ class StereoFrontend:
         self._opt = FrontendOptions(width, height, batch, o.detection.cell_size[0], o.detection.cell_size[1],
                                     o.detection.fast_threshold, o.tracking.klt_window_size[0], o.tracking.klt_window_size[1],
                                     o.tracking.klt_max_level, o.tracking.klt_threshold, o.matcher_ratio, max_iters, epsilon,
-                                    min_eig_threshold)
+                                    min_eig_threshold, 1 if o.detection.algorithm == "PARALLEL_GRID" else 0)
         h = C.c_void_p()
         check(lib().zs_frontend_create(ctx._h, C.byref(self._opt), C.byref(h)))
         self._h = h

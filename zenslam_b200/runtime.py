@@ -89,6 +89,10 @@ class Context:
     def launches(self) -> int:
         return int(lib().zs_context_launch_count(self._h))
 
+    def reload_switches(self):
+        """re-read the ZS_* A/B switches from the environment (they are read once, at context creation)"""
+        check(lib().zs_context_reload_switches(self._h))
+
     def empty(self, shape, dtype):
         torch = _torch()
         return torch.empty(shape, dtype=dtype, device="cuda:%d" % self.device)
