@@ -36,7 +36,7 @@ struct zs_pyr_view {
 struct zs_switches {
     bool fe_no_graph, klt_no_tma, klt_no_share, lk_no_cache, fast_v1, l2_no_tensor, l2_one_tile, fast_pretest;
     int pyr_force;               // 0 = by batch size, 1 = ZS_PYR_SPLIT, 2 = ZS_PYR_FUSED
-    int hamming_splits, hamming_variant, l2_splits, l2_epi_groups, klt_blocks63;   // 0 = default
+    int hamming_splits, hamming_variant, l2_splits, l2_epi_groups;   // 0 = default
 };
 void zs_read_switches(zs_switches* s);
 

@@ -64,7 +64,6 @@ void zs_read_switches(zs_switches* s)
     s->pyr_force = on("ZS_PYR_SPLIT") ? 1 : on("ZS_PYR_FUSED") ? 2 : 0;
     s->hamming_splits = num("ZS_HAMMING_SPLITS"); s->hamming_variant = num("ZS_HAMMING_VARIANT");
     s->l2_splits = num("ZS_L2_SPLITS"); s->l2_epi_groups = num("ZS_L2_EPI_GROUPS");
-    s->klt_blocks63 = num("ZS_KLT_BLOCKS63");
 }
 
 static thread_local char g_err[512] = "";

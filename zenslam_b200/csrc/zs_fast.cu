@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(FG2_THREADS) k_fast_grid_v2(fast_grid_args a)
     uint32_t* sO = sE + CH * PW;                                    // [CH][PW]
     uint8_t* sS = (uint8_t*)(sO + CH * PW);                         // score tile [CH][TW]
     int* sBest = (int*)(sS + CH * TW);                              // [NC]
-    uint8_t* sRaw = (uint8_t*)(sBest + NC);                  // raw strip [CH][TW + 16]
+    uint8_t* sRaw = (uint8_t*)(sBest + ((NC + 3) & ~3));     // raw strip [CH][TW + 16], 16-byte aligned (uint4 staging)
     constexpr int RP = TW + 16;
 
     const int img = blockIdx.z, gy = blockIdx.y, cell0 = blockIdx.x * NC;
@@ -271,7 +271,7 @@ template <int CW, int CH, int NC>
 static size_t fast_grid_v2_smem()
 {
     constexpr int TW = NC * CW, PW = TW / 2 + 4;
-    return (size_t)2 * CH * PW * 4 + (size_t)CH * TW + NC * 4 + (size_t)CH * (TW + 16);
+    return (size_t)2 * CH * PW * 4 + (size_t)CH * TW + ((NC + 3) & ~3) * 4 + (size_t)CH * (TW + 16);
 }
 
 // Compaction in cell row-major order: one block per image, block-wide exclusive scan over the cells.

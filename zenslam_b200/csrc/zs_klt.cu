@@ -821,12 +821,9 @@ zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_
             k_klt_track_v4<W_, H_, MB_><<<grid, klt4_cfg<W_, H_>::NT * 32, sm, ctx->stream>>>(a);                              \
         } while (0)
         if (a.win_w == 31) KLT4_LAUNCH(31, 31, 24);
-        else if (a.win_w == 63) {
-            // resident CTAs (of four warps) per SM: 6 = 80 registers with spills, 5 = 96, 4 = 128 and no spills
-            if (ctx->sw.klt_blocks63 == 4) KLT4_LAUNCH(63, 63, 4);
-            else if (ctx->sw.klt_blocks63 == 6) KLT4_LAUNCH(63, 63, 6);
-            else KLT4_LAUNCH(63, 63, 5);
-        }
+        // four-warp CTAs: 4 per SM = 128 registers, no spills: 16.4 ms per 128-frame TUMVI batch (1024x1024, 225 points per
+        // image); 5 per SM (96 registers, 240 B of spills): 16.6 ms; 6 (80 registers, 324 B): 20.1 ms
+        else if (a.win_w == 63) KLT4_LAUNCH(63, 63, 4);
         else if (a.win_w == 21) KLT4_LAUNCH(21, 21, 24);
         else KLT4_LAUNCH(15, 15, 24);
 #undef KLT4_LAUNCH

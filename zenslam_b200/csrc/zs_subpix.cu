@@ -6,15 +6,19 @@
 // One warp per point.  Per iteration the (2w+3)^2 float patch around the current estimate is produced in shared
 // memory exactly as OpenCV's 8u->32f getRectSubPix does it -- inside the image that is a per-row recurrence
 // (lane = patch row), at the image border the replicate-border bilinear form (lanes stride over the patch) --
-// and the five double-precision sums of the normal equations are accumulated by five lanes, each walking the
-// window in raster order, so that every rounding happens in the same order as on the CPU: results are
-// bit-identical to OpenCV built without IPP (the oracle pins that), not merely within tolerance.
+// and the five double-precision sums of the normal equations are accumulated by five lanes, each adding its terms in
+// raster order, so that every rounding happens in the same order as on the CPU: results are bit-identical to OpenCV
+// built without IPP (the oracle pins that), not merely within tolerance.  The TERMS are order-free, so all 32 lanes
+// compute them first (one window pixel per lane and step) and park them in shared memory; only the 121 dependent
+// additions per sum stay serial (the first version had five lanes do everything: 10 ms per 57 k points at tumvi.yaml's
+// settings, 5/32 lane utilisation).
 #include <math.h>
 
 #include "zs_common.cuh"
 
 #define SUBPIX_MAX_WIN 7                       // half window; the reference uses 5
 #define SUBPIX_WARPS 4
+#define SUBPIX_NPX ((2 * SUBPIX_MAX_WIN + 1) * (2 * SUBPIX_MAX_WIN + 1))
 
 struct subpix_args {
     zs_pyr_view v;
@@ -28,6 +32,7 @@ struct subpix_args {
 __global__ void __launch_bounds__(SUBPIX_WARPS * 32) k_corner_subpix(subpix_args a)
 {
     __shared__ float s_sub[SUBPIX_WARPS][(2 * SUBPIX_MAX_WIN + 3) * (2 * SUBPIX_MAX_WIN + 3)];
+    __shared__ double s_term[SUBPIX_WARPS][5 * SUBPIX_NPX];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int img = blockIdx.y, i = blockIdx.x * SUBPIX_WARPS + warp;
     if (i >= min(a.count[img], a.cap)) return;
@@ -81,30 +86,28 @@ __global__ void __launch_bounds__(SUBPIX_WARPS * 32) k_corner_subpix(subpix_args
             }
         }
         __syncwarp();
-        // ---- normal equations: lanes 0..4 each own one sum and walk the window in raster order
+        // ---- normal equations.  Terms: every lane, one window pixel per step; sums: lanes 0..4, raster order
+        const int npx = ww * wh;
+        double* tm = s_term[warp];
+        for (int e = lane; e < npx; e += 32) {
+            const int r = e / ww, j = e - r * ww;
+            const float* sp = sub + (r + 1) * pw + 1;
+            const double m = (double)__fmul_rn(a.ey[r], a.ex[j]);
+            const double tgx = (double)__fsub_rn(sp[j + 1], sp[j - 1]);
+            const double tgy = (double)__fsub_rn(sp[j + pw], sp[j - pw]);
+            const double px = (double)(j - a.win_w), py = (double)(r - a.win_h);
+            const double gxx = __dmul_rn(__dmul_rn(tgx, tgx), m), gxy = __dmul_rn(__dmul_rn(tgx, tgy), m),
+                         gyy = __dmul_rn(__dmul_rn(tgy, tgy), m);
+            tm[e] = gxx; tm[npx + e] = gxy; tm[2 * npx + e] = gyy;
+            tm[3 * npx + e] = __dadd_rn(__dmul_rn(gxx, px), __dmul_rn(gxy, py));
+            tm[4 * npx + e] = __dadd_rn(__dmul_rn(gxy, px), __dmul_rn(gyy, py));
+        }
+        __syncwarp();
         double acc = 0;
         if (lane < 5) {
-            const float* sp = sub + pw + 1;
-            for (int r = 0; r < wh; ++r, sp += pw) {
-                const double py = (double)(r - a.win_h);
-                const float vy = a.ey[r];
-                for (int j = 0; j < ww; ++j) {
-                    const double m = (double)__fmul_rn(vy, a.ex[j]);
-                    const double tgx = (double)__fsub_rn(sp[j + 1], sp[j - 1]);
-                    const double tgy = (double)__fsub_rn(sp[j + pw], sp[j - pw]);
-                    const double px = (double)(j - a.win_w);
-                    double term;
-                    if (lane == 0) term = __dmul_rn(__dmul_rn(tgx, tgx), m);
-                    else if (lane == 1) term = __dmul_rn(__dmul_rn(tgx, tgy), m);
-                    else if (lane == 2) term = __dmul_rn(__dmul_rn(tgy, tgy), m);
-                    else {
-                        const double gxx = __dmul_rn(__dmul_rn(tgx, tgx), m), gxy = __dmul_rn(__dmul_rn(tgx, tgy), m),
-                                     gyy = __dmul_rn(__dmul_rn(tgy, tgy), m);
-                        term = lane == 3 ? __dadd_rn(__dmul_rn(gxx, px), __dmul_rn(gxy, py)) : __dadd_rn(__dmul_rn(gxy, px), __dmul_rn(gyy, py));
-                    }
-                    acc = __dadd_rn(acc, term);
-                }
-            }
+            const double* t = tm + lane * npx;
+#pragma unroll 4
+            for (int e = 0; e < npx; ++e) acc = __dadd_rn(acc, t[e]);
         }
         const double sa = __shfl_sync(0xffffffffu, acc, 0), sb = __shfl_sync(0xffffffffu, acc, 1), sc = __shfl_sync(0xffffffffu, acc, 2),
                      bb1 = __shfl_sync(0xffffffffu, acc, 3), bb2 = __shfl_sync(0xffffffffu, acc, 4);
