@@ -304,6 +304,21 @@ ZS_API zs_status zs_knn_match_host(zs_context* ctx, const void* q, int nq, const
 ZS_API zs_status zs_assign_landmarks_host(zs_context* ctx, const uint8_t* keypoint_desc, int n, const uint8_t* landmark_desc,
                                           int m, double max_descriptor_distance, int* landmark_row, float* distance);
 
+/* utils::match_keypoints3d (zenslam_core/source/matching/matching_utils.cpp:132-216, and the overload with frustum culling
+ * :218-343), SURVEY 8 a9 / f2: the landmarks within `radius` of the camera (same radius_search quirk as above: the first
+ * `count` landmarks in insertion order), moved into the camera frame (pose_of_camera0_in_world.inv(): R row-major 3x3, t[3]),
+ * kept when z > 0 (and, with image_width > 0, when they project inside the image +- frustum_margin), matched by
+ * cv::BFMatcher(NORM_HAMMING, crossCheck = true).match(landmarks, keypoints) and gated by the reprojection error
+ * ||project(P, X) - kp.pt|| < threshold (P row-major 3x4).  keypoints: the caller passes map::values_unmatched(points3d_world)
+ * -- the keypoints whose index is not a landmark index -- in key order.  Outputs (sized min(n_landmarks, n_keypoints)):
+ * landmark_index / keypoint_index = DMatch::queryIdx / trainIdx as the reference re-keys them, error = DMatch::distance. */
+ZS_API zs_status zs_match_keypoints3d_host(zs_context* ctx, const int* landmark_index, const double* landmark_xyz,
+                                           const uint8_t* landmark_desc, int n_landmarks, const int* keypoint_index,
+                                           const float* keypoint_xy, const uint8_t* keypoint_desc, int n_keypoints,
+                                           const double* R, const double* t, const double* P, double radius, double threshold,
+                                           int image_width, int image_height, double frustum_margin, int* out_landmark_index,
+                                           int* out_keypoint_index, float* out_error, int* n_out);
+
 /* ---- stereo triangulation with its gates: triangulator::triangulate_keypoints ----------------------------------
  * (zenslam_core/source/mapping/triangulator.cpp:39-132, filter_epipolar :152-188; cv::triangulatePoints behind
  * utils::triangulate_points, mapping/triangulation_utils.cpp:135-160).  SURVEY 8(f3).  n matched pairs (same keypoint
@@ -332,8 +347,9 @@ ZS_API zs_status zs_triangulate_keypoints_host(zs_context* ctx, const double* P0
  * the other camera lacks, sequential keypoint indices (keypoint::index_next).  Algorithm GRID or PARALLEL_GRID, feature
  * FAST, descriptor ORB.  Host-side pieces of the reference's flow: the landmark projection behind the initial flow (its
  * result comes in through zs_tracker_set_predictions) and the RANSAC that estimates F for filter_epipolar (the gate itself
- * is zs_tracker_filter_epipolar).  assign_landmark_indices (keypoint_tracker.cpp:55,71) is not applied: the tracker behaves
- * like track() with an empty landmark map.  Results: both maps in key (index) order. */
+ * is zs_tracker_filter_epipolar).  assign_landmark_indices (keypoint_tracker.cpp:55,71,199-291) runs inside the step, between
+ * each detection and its map add, against a landmark store kept on the device (zs_tracker_landmarks_add_host; empty store =
+ * the reference's early return).  Results: both maps in key (index) order. */
 typedef struct zs_tracker zs_tracker;
 typedef struct {
     int width, height;
@@ -344,6 +360,9 @@ typedef struct {
     int first_index;                               /* keypoint::index_next when the sequence starts */
     int sequences;                                 /* independent stereo sequences tracked in lock-step; 0 = 1 */
     int parallel_grid;                             /* detection.algorithm PARALLEL_GRID: cornerSubPix on the new corners */
+    int landmark_capacity;                         /* landmarks per sequence the device store can hold; 0 = no landmark association */
+    double landmark_match_radius;                  /* tracking.landmark_match_radius (50.0); <= 0: every landmark is a candidate */
+    double landmark_match_distance;                /* tracking.landmark_match_distance (32.0) */
 } zs_tracker_options;
 typedef struct {                                   /* HOST pointers, S = sequences; any may be NULL */
     int cap;                                       /* row length of the arrays below, >= zs_tracker_capacity() */
@@ -360,6 +379,17 @@ ZS_API int zs_tracker_sequences(const zs_tracker* t);
  * OPTFLOW_USE_INITIAL_FLOW.  Keypoints without a prediction start from their own position.  Consumed by the next call. */
 ZS_API zs_status zs_tracker_set_predictions(zs_tracker* t, int sequence, int camera, const int* index, const float* xy,
                                             int n);
+/* The landmark map of `sequence` (system.points3d) as assign_landmark_indices reads it: `system.points3d += pose * points3d`
+ * (slam_thread.cpp:210; map::operator+=(const map&), types/map.h:222-236): landmarks whose index the store already holds are
+ * skipped, the others are appended in the order given (the reference iterates a std::map: pass them in ascending index order).
+ * xyz = world coordinates [n][3], desc [n][32].  Returns ZS_ERR_CAPACITY when the store would exceed landmark_capacity.
+ * zs_tracker_set_camera_center: frame_0.pose.translation() for the next step's radius search (keypoint_tracker.cpp:56,72,213);
+ * default (0, 0, 0).  One reference quirk is reproduced: point3d_cloud::radius_search counts the landmarks within the radius
+ * and then returns the FIRST `count` landmarks in insertion order (types/point3d_cloud.cpp:56-64), so those are the candidates. */
+ZS_API zs_status zs_tracker_landmarks_add_host(zs_tracker* t, int sequence, const int* index, const double* xyz,
+                                               const uint8_t* desc, int n, int* n_added);
+ZS_API int zs_tracker_landmarks_size(const zs_tracker* t, int sequence);
+ZS_API zs_status zs_tracker_set_camera_center(zs_tracker* t, int sequence, const double* center);
 /* left / right: the new frame of every sequence, [S][height][pitch] with `stride` bytes between sequences (0 = pitch * height) */
 ZS_API zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, const uint8_t* right, size_t pitch,
                                        size_t stride, const zs_tracker_results* res);
@@ -367,6 +397,10 @@ ZS_API zs_status zs_tracker_track_host(zs_tracker* t, const uint8_t* left, const
  * copy of the current maps to the host as a separate call -- for callers that keep frames resident or pipeline transfers */
 ZS_API zs_status zs_tracker_track(zs_tracker* t, const uint8_t* d_left, const uint8_t* d_right, size_t pitch, size_t stride);
 ZS_API zs_status zs_tracker_download(zs_tracker* t, const zs_tracker_results* res);
+/* Capacity: a step in which a map would exceed zs_tracker_capacity() keeps the first `capacity` keypoints of that map (the
+ * rest are dropped; keypoint::index_next still advances past them) and the download / wait that returns THAT step reports
+ * ZS_ERR_CAPACITY after filling the results -- the step counts as consumed.  Later steps report it again only if they
+ * overflow themselves. */
 /* filter_epipolar (keypoint_tracker.cpp:293-341) on the maps of the last step of `sequence`, F (row-major 3x3) from the
  * caller -- the reference estimates it with cv::findFundamentalMat RANSAC on the matched points, which stays on the CPU:
  * both maps keep only the keypoints present in both whose |pt0^T F pt1| < threshold.  The filtered maps are what the next

@@ -1,0 +1,185 @@
+"""GPU: landmark association -- keypoint_tracker::assign_landmark_indices inside the stateful device flow
+(keypoint_tracker.cpp:55,71,199-291) and utils::match_keypoints3d (matching_utils.cpp:132-343) -- against the CPU
+restatement oracle/landmarks.py (whose Hamming matcher is pinned to cv2 elsewhere)."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import landmarks as olm
+from zenslam_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from zenslam_b200.runtime import Context
+    c = Context()
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("radius", [50.0, 0.0])
+def test_device_tracker_with_landmark_map(ctx, radius):
+    """zs_tracker with a non-empty landmark store against the keypoint_tracker.track mirror whose assign_landmark_indices is
+    the oracle's: identical index sets, positions, responses and descriptors in both cameras on every frame.  The landmark
+    map grows every frame like system.points3d (slam_thread.cpp:210), holds descriptors of keypoints the NEXT frame will
+    detect (so detections do take landmark indices), indices the maps already hold (so map.add skips them), landmarks
+    outside the radius and re-submitted indices (so `+=` skips them); the camera centre moves."""
+    from zenslam_b200 import detection_options, keypoint, slam_options, tracking_options
+    from zenslam_b200.detection import keypoint_detector_grid
+    from zenslam_b200.keypoint_tracker import device_keypoint_tracker, keypoint_tracker, stereo_frame
+    from zenslam_b200.tracking import create_cuda_pyr_lk
+    w, h, frames = 376, 240, 7
+    seq, _ = syn.stereo_sequence(w, h, frames, 3100, subpixel=True)
+    opts = slam_options(matcher="KNN", detection=detection_options(),
+                        tracking=tracking_options(filter_epipolar=False, landmark_match_radius=radius, landmark_match_distance=32.0))
+    rng = np.random.default_rng(31)
+    det = keypoint_detector_grid(opts.detection, ctx)
+
+    def new_landmarks(t, maps):
+        """landmarks to add before frame t is tracked: descriptors of what a full-grid detection finds in frame t (left and
+        right), keyed partly by fresh landmark indices and partly by indices the current maps hold"""
+        saved = keypoint.index_next
+        cand = det.detect_keypoints(seq[t, 0], {})[::3] + det.detect_keypoints(seq[t, 1], {})[1::4]
+        keypoint.index_next = saved
+        held = sorted(set(maps[0]) | set(maps[1]))
+        idx, desc = [], []
+        for j, k in enumerate(cand):
+            if held and j % 5 == 0:
+                idx.append(int(held[(7 * j) % len(held)]))
+            else:
+                idx.append(500000 + 1000 * t + j)
+            desc.append(k.descriptor)
+        xyz = rng.normal(0.0, 35.0, (len(idx), 3))                   # some beyond the 50 m radius
+        return canon(np.array(idx, np.int64), xyz, np.stack(desc))
+
+    def canon(idx, xyz, desc):
+        """what `+=` sees: a std::map holds every index once (first one wins here) and is iterated in key order"""
+        _, first = np.unique(idx, return_index=True)
+        return idx[first], xyz[first], desc[first]
+
+    # ---- the mirror: CUDA detector / pyr_lk seams + the oracle's assign_landmark_indices
+    cloud = olm.landmark_cloud()
+    state = {"center": np.zeros(3)}
+    assigned_total = [0]
+
+    def assign(detected):
+        if not detected:
+            return
+        got = olm.assign_landmark_indices(np.stack([k.descriptor for k in detected]), cloud, state["center"], radius, 32.0)
+        for k, li in zip(detected, got):
+            if li >= 0:
+                k.index = int(li); assigned_total[0] += 1
+
+    keypoint.index_next = 0
+    host = keypoint_tracker(opts, ctx, create_cuda_pyr_lk(ctx), assign_landmarks=assign)
+    prev = stereo_frame((seq[0, 0], seq[0, 1]))
+    want, adds = [], []
+    maps = ({}, {})
+    for t in range(frames):
+        if t >= 2:
+            lm = new_landmarks(t, maps)
+            if t == 4:                                                # re-submit a few known indices with other data: += skips them
+                lm = canon(np.concatenate([cloud.index[:5], lm[0]]), np.concatenate([cloud.xyz[:5] + 1.0, lm[1]]),
+                           np.concatenate([cloud.desc[:5] ^ 255, lm[2]]))
+            adds.append((t, lm, cloud.add(*lm)))
+        state["center"] = np.array([0.8 * t, -0.5 * t, 0.3 * t])
+        cur = stereo_frame((seq[t, 0], seq[t, 1]))
+        k0, k1 = host.track(prev, cur)
+        want.append((k0, k1, keypoint.index_next))
+        prev = dataclasses.replace(cur, keypoints=(k0, k1))
+        maps = (k0, k1)
+    assert assigned_total[0] > 40, assigned_total                     # the association really fires
+    if radius > 0:
+        assert cloud.radius_count(state["center"], radius) < len(cloud)   # ... and the radius really cuts
+
+    # ---- the device tracker
+    keypoint.index_next = 0
+    dev_trk = device_keypoint_tracker(opts, ctx, w, h, landmark_capacity=4096)
+    ai = 0
+    for t in range(frames):
+        if ai < len(adds) and adds[ai][0] == t:
+            assert dev_trk.add_landmarks(*adds[ai][1]) == adds[ai][2]
+            ai += 1
+        dev_trk.set_camera_center([0.8 * t, -0.5 * t, 0.3 * t])
+        g0, g1 = dev_trk.track(seq[t, 0], seq[t, 1])
+        for cam, (g, r) in enumerate(((g0, want[t][0]), (g1, want[t][1]))):
+            assert list(g) == sorted(r), (t, cam, len(g), len(r), sorted(set(g) ^ set(r))[:10])
+            for i in g:
+                assert g[i].pt == r[i].pt and g[i].response == r[i].response and np.array_equal(g[i].descriptor, r[i].descriptor), (t, cam, i)
+        assert keypoint.index_next == want[t][2]
+    assert dev_trk.landmarks_size() == len(cloud)
+    assert any(i >= 500000 for i in g0) and any(i >= 500000 for i in g1)      # landmark indices live in the maps
+    dev_trk.close()
+
+
+def test_device_tracker_empty_landmark_store_equals_plain_tracker(ctx):
+    """points3d.empty() -> assign_landmark_indices returns at once (keypoint_tracker.cpp:208): a tracker with an empty
+    landmark store must produce exactly what the tracker without one produces"""
+    from zenslam_b200 import detection_options, keypoint, slam_options, tracking_options
+    from zenslam_b200.keypoint_tracker import device_keypoint_tracker
+    w, h, frames = 376, 240, 4
+    seq, _ = syn.stereo_sequence(w, h, frames, 3200, subpixel=True)
+    opts = slam_options(detection=detection_options(), tracking=tracking_options(filter_epipolar=False))
+    out = []
+    for lm_cap in (0, 1024):
+        keypoint.index_next = 0
+        trk = device_keypoint_tracker(opts, ctx, w, h, landmark_capacity=lm_cap)
+        out.append([trk.track(seq[t, 0], seq[t, 1]) for t in range(frames)])
+        trk.close()
+    for t in range(frames):
+        for cam in range(2):
+            a, b = out[0][t][cam], out[1][t][cam]
+            assert list(a) == list(b)
+            assert all(a[i].pt == b[i].pt and np.array_equal(a[i].descriptor, b[i].descriptor) for i in a)
+
+
+def _scene(rng, m, n_kp):
+    """a cloud in front of / around a camera, keypoints that are noisy projections of some landmarks + strays"""
+    from zenslam_b200 import keypoint
+    ang = 0.3
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    t = np.array([2.0, -1.0, 0.5])
+    K = np.array([[420.0, 0, 376.0], [0, 420.0, 240.0], [0, 0, 1.0]])
+    P = np.hstack([K, np.zeros((3, 1))])
+    cam = np.stack([rng.uniform(-12, 12, m), rng.uniform(-8, 8, m), rng.uniform(-5, 40, m)], 1)
+    xyz = cam @ R.T + t                                       # world = R cam + t
+    desc = rng.integers(0, 256, (m, 32), dtype=np.uint8)
+    index = rng.permutation(np.arange(1000, 1000 + 3 * m))[:m].astype(np.int64)
+    kps = {}
+    pick = rng.choice(m, n_kp, replace=False)
+    for j, i in enumerate(pick):
+        z = max(cam[i, 2], 0.5)
+        uv = (K @ (cam[i] / z))[:2] + rng.normal(0, [0.4, 3.0][j % 2], 2)      # half of them beyond a 2 px gate
+        d = desc[i].copy()
+        d[rng.integers(0, 32, 3)] ^= np.uint8(1 << int(rng.integers(0, 8)))    # a few flipped bits
+        # a fifth of the keypoints carry a landmark's index: values_unmatched drops them
+        ki = int(index[(i + 1) % m]) if j % 5 == 0 else 900000 + j
+        kps[ki] = keypoint(pt=(float(np.float32(uv[0])), float(np.float32(uv[1]))), index=ki, descriptor=d)
+    return index, xyz, desc, kps, R, t, P
+
+
+@pytest.mark.parametrize("frustum", [False, True])
+@pytest.mark.parametrize("m,n_kp,radius", [(3000, 900, 30.0), (200, 150, 1000.0), (50, 40, 5.0)])
+def test_match_keypoints3d_vs_oracle(ctx, m, n_kp, radius, frustum):
+    from zenslam_b200.matching import match_keypoints3d
+    rng = np.random.default_rng(m + int(frustum))
+    index, xyz, desc, kps, R, t, P = _scene(rng, m, n_kp)
+    cloud = olm.landmark_cloud()
+    order = np.argsort(index, kind="stable")
+    cloud.add(index[order], xyz[order], desc[order])
+    size, margin = ((752, 480), 50.0) if frustum else (None, None)
+    keys = sorted(kps)
+    ol, ok_, oe = olm.match_keypoints3d(cloud, keys, np.array([kps[k].pt for k in keys], np.float32),
+                                        np.stack([kps[k].descriptor for k in keys]), R, t, P, radius, 2.0, size, margin)
+    got = match_keypoints3d(ctx, cloud.index, cloud.xyz, cloud.desc, kps, R, t, P, radius, 2.0, size, margin if frustum else 50.0)
+    assert [g.queryIdx for g in got] == ol.tolist() and [g.trainIdx for g in got] == ok_.tolist()
+    # the reference inverts the pose numerically (cv::Affine3d::inv): the error is a float comparison, tolerance 1e-4 px
+    assert np.allclose([g.distance for g in got], oe, rtol=0, atol=1e-4)
+    if m >= 200:
+        assert len(got) > 10
+    assert match_keypoints3d(ctx, cloud.index, cloud.xyz, cloud.desc, {}, R, t, P, radius, 2.0) == []
+    assert match_keypoints3d(ctx, [], np.zeros((0, 3)), np.zeros((0, 32), np.uint8), kps, R, t, P, radius, 2.0) == []

@@ -107,3 +107,34 @@ def test_pyramid_and_preprocessing_live():
     assert np.array_equal(gray, oracle.bgr2gray(bgr))
     assert np.array_equal(cv2.createCLAHE(4.0).apply(gray), oracle.clahe(gray, 4.0))
     assert np.array_equal(cv2.resize(img, (277, 209), interpolation=cv2.INTER_LINEAR_EXACT), oracle.resize_linear_exact(img, 277, 209))
+
+
+@pytest.mark.parametrize("radius", [0.0, 40.0])
+def test_assign_landmark_indices_live(radius):
+    """oracle/landmarks.py against keypoint_tracker::assign_landmark_indices (keypoint_tracker.cpp:199-291) restated directly
+    over cv2.BFMatcher(NORM_HAMMING, crossCheck=True), including the reference's radius_search (first `count` landmarks)"""
+    from oracle import landmarks as olm
+    rng = np.random.default_rng(800)
+    m, n = 700, 300
+    cloud = olm.landmark_cloud()
+    idx = rng.permutation(np.arange(10, 10 + 2 * m))[:m]
+    idx.sort()
+    desc = rng.integers(0, 256, (m, 32), dtype=np.uint8)
+    xyz = rng.normal(0, 30, (m, 3))
+    assert cloud.add(idx, xyz, desc) == m and cloud.add(idx[:9], xyz[:9], desc[:9]) == 0
+    q = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    src = rng.choice(m, 200, replace=False)
+    q[:200] = desc[src]
+    q[:200, :3] ^= rng.integers(0, 256, (200, 3), dtype=np.uint8)            # some within 32 bits, some not
+    center = np.array([3.0, -2.0, 1.0])
+    got = olm.assign_landmark_indices(q, cloud, center, radius, 32.0)
+    cand = m
+    if radius > 0:
+        d = xyz - center
+        cand = int(np.count_nonzero(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2] < radius * radius))
+        assert 0 < cand < m
+    want = np.full(n, -1, np.int64)
+    for mt in cv2.BFMatcher(cv2.NORM_HAMMING, True).match(q, desc[:cand]):
+        if mt.distance <= 32.0:
+            want[mt.queryIdx] = idx[mt.trainIdx]
+    assert np.array_equal(got, want) and (got >= 0).sum() > 30

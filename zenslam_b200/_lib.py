@@ -34,7 +34,8 @@ class TriangulationParams(C.Structure):
 class TrackerOptions(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("cell_w", C.c_int), ("cell_h", C.c_int), ("fast_threshold", C.c_int),
                 ("klt_win_w", C.c_int), ("klt_win_h", C.c_int), ("klt_max_level", C.c_int), ("klt_threshold", C.c_double),
-                ("capacity", C.c_int), ("first_index", C.c_int), ("sequences", C.c_int), ("parallel_grid", C.c_int)]
+                ("capacity", C.c_int), ("first_index", C.c_int), ("sequences", C.c_int), ("parallel_grid", C.c_int),
+                ("landmark_capacity", C.c_int), ("landmark_match_radius", C.c_double), ("landmark_match_distance", C.c_double)]
 
 
 class TrackerResults(C.Structure):
@@ -126,6 +127,10 @@ SIGNATURES = {
     "zs_tracker_capacity": (I, [P]),
     "zs_tracker_sequences": (I, [P]),
     "zs_tracker_set_predictions": (I, [P, I, I, P, P, I]),
+    "zs_tracker_landmarks_add_host": (I, [P, I, P, P, P, I, C.POINTER(I)]),
+    "zs_tracker_landmarks_size": (I, [P, I]),
+    "zs_tracker_set_camera_center": (I, [P, I, P]),
+    "zs_match_keypoints3d_host": (I, [P, P, P, P, I, P, P, P, I, P, P, P, D, D, I, I, D, P, P, P, C.POINTER(I)]),
     "zs_tracker_track_host": (I, [P, P, P, Z, Z, C.POINTER(TrackerResults)]),
     "zs_tracker_track": (I, [P, P, P, Z, Z]),
     "zs_tracker_download": (I, [P, C.POINTER(TrackerResults)]),

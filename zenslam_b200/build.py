@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libzenslam_cuda.so")
 
-SOURCES = ["zs_context.cu", "zs_pyramid.cu", "zs_fast.cu", "zs_orb.cu", "zs_orb_detect.cu", "zs_match.cu", "zs_match_l2.cu",
+SOURCES = ["zs_context.cu", "zs_landmarks.cu", "zs_pyramid.cu", "zs_fast.cu", "zs_orb.cu", "zs_orb_detect.cu", "zs_match.cu", "zs_match_l2.cu",
            "zs_klt.cu", "zs_subpix.cu", "zs_preproc.cu", "zs_triangulate.cu", "zs_host.cu", "zs_frontend.cu", "zs_tracker.cu"]
 
 NVCC_FLAGS = [

@@ -122,6 +122,8 @@ typedef CUresult (*zs_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint
 zs_encode_tiled_fn zs_get_encode_tiled();
 
 // internal launchers (defined in the per-stage .cu files)
+zs_status zs_lm_radius_count(zs_context* ctx, const double* d_xyz, const int* d_n, int cap, const double* d_center, double radius,
+                             int sequences, int* d_nt);
 bool zs_klt_tiled_window(const zs_context* ctx, const zs_pyramid* p, int win_w, int win_h);
 zs_status zs_launch_orb_blur(zs_context* ctx, const zs_pyramid* p, int first, int count);
 zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_slot, const int* d_next_slot,

@@ -13,9 +13,17 @@
 // merge of the sorted runs per frame.  New keypoints take sequential indices from a per-sequence device-side counter in
 // detection order (left image first), exactly like keypoint::index_next.  Sequences never interact: a block (or a KLT job,
 // or a detector image) belongs to one sequence.  Not done here (host-side in the reference too): the landmark projection
-// behind the initial flow (its result comes in through zs_tracker_set_predictions), assign_landmark_indices,
-// filter_epipolar's RANSAC.
+// behind the initial flow (its result comes in through zs_tracker_set_predictions) and filter_epipolar's RANSAC.
+//
+// assign_landmark_indices (:55,71,199-291) runs between each detection and its map add when the tracker was created with a
+// landmark store (landmark_capacity > 0): radius pre-filter around the camera centre (zs_landmarks.cu), cross-checked Hamming
+// match of the detected keypoints against the candidate landmarks (zs_match.cu), distance gate, and a map add that skips the
+// landmark indices the map already holds.  Landmark indices are arbitrary keys, so in that mode each map is re-sorted right
+// after its detection add (rank by binary search over its at most four ascending runs) and every search sees a sorted map.
 #include <stdlib.h>
+
+#include <unordered_set>
+#include <vector>
 
 #include "zs_common.cuh"
 
@@ -56,6 +64,15 @@ struct zs_tracker {
     int* marks;                  // [S][2][2] map sizes before the appends that start a new sorted run (see k_trk_sort)
     int* next_index;             // [S] device copies of keypoint::index_next
     int* overflow;               // set when a map would exceed cap
+    // landmark association: per-sequence landmark store in insertion order (system.points3d), [S][lm_cap] rows; 0 = off
+    int lm_cap;
+    double* lm_xyz; int* lm_index; uint8_t* lm_desc; int* lm_n; double* lm_center; int* lm_nt;
+    int* lm_match; float* lm_dist;   // [S][cells]: cross-checked landmark row of every detected keypoint (-1: none), distance
+    int* lm_runs;                    // [S][2][5]: boundaries of the ascending runs of a map before its mid-frame sort
+    trk_maps tmp;                    // scratch generation the mid-frame sorts write into
+    int lm_bucket, g_bucket[2];      // train-side row count the matcher is launched with (power of two >= the fullest store)
+    std::vector<std::unordered_set<int>>* lm_seen;   // indices each store holds: the host side of map::operator+=
+    std::vector<int>* lm_host_n;
     // CUDA graph of the per-frame launch sequence (pyramids ... sort), one per frame parity; uploads and result copies
     // stay outside.  Captured the second time a parity comes round (the first run sizes the context scratch).
     bool graph_ok; cudaGraphExec_t gexec[2]; void* g_scratch[2]; uint64_t g_launches[2]; int runs[2];
@@ -273,6 +290,128 @@ __global__ void __launch_bounds__(TRK_THREADS) k_trk_sort(trk_maps cur, trk_maps
     if (threadIdx.x == 0) *o.n = n;
 }
 
+// ---- landmark association ------------------------------------------------------------------------------------
+// map.add(detected) after assign_landmark_indices (keypoint_tracker.cpp:55-57, 71-73, 283-287).  The detector stamps every
+// new keypoint with index_next++ (keypoint_detector_grid.cpp:142-147); a keypoint whose cross-checked landmark match has
+// distance <= landmark_match_distance then takes the landmark's index, and add() skips it when the map already holds
+// that index.  Appends two ascending runs: the keypoints that keep their fresh index, then the accepted landmark-indexed
+// ones ranked by index; records the run boundaries for k_trk_sort_runs.  grid: S
+__global__ void __launch_bounds__(TRK_THREADS) k_trk_append_detected_lm(trk_maps cur, int cam, int cells, const float* __restrict__ dxy,
+                                                                        const float* __restrict__ dresp, const uint8_t* __restrict__ ddesc,
+                                                                        const int* __restrict__ dn, const int* __restrict__ lm_match,
+                                                                        const float* __restrict__ lm_dist, const int* __restrict__ lm_index,
+                                                                        int lm_cap, double max_dist, int* __restrict__ next_index,
+                                                                        int* __restrict__ overflow, const int* __restrict__ marks,
+                                                                        int* __restrict__ runs, int* __restrict__ stage_key,
+                                                                        int* __restrict__ stage_src)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int seq = blockIdx.x, cap = cur.cap;
+    const trk_map m = cur.at(seq, cam);
+    const float* xy = dxy + (size_t)seq * cells * 2; const float* rs = dresp + (size_t)seq * cells;
+    const uint8_t* ds = ddesc + (size_t)seq * cells * 32;
+    const int* mt = lm_match + (size_t)seq * cells; const float* md = lm_dist + (size_t)seq * cells;
+    const int* li = lm_index + (size_t)seq * lm_cap;
+    int* skey = stage_key + (size_t)seq * cap; int* ssrc = stage_src + (size_t)seq * cap;
+    const int n = min(*m.n, cap), k = min(dn[seq], cells), first = next_index[seq];
+    // the map so far: left = its temporal tracks; right = [temporal tracks | keypoints tracked over from the left camera]
+    const int b1 = cam == 0 ? n : min(max(marks[4 * seq + 2], 0), n);
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < k; base += TRK_THREADS) {               // fresh indices, detection order
+        const int i = base + threadIdx.x;
+        bool f = false;
+        if (i < k) { const int r = mt[i]; f = !(r >= 0 && (double)md[i] <= max_dist); }
+        const int o = n + trk_scan_step(f, warp_sums, &carry);
+        if (f && o < cap) {
+            m.idx[o] = first + i; m.xy[2 * o] = xy[2 * i]; m.xy[2 * o + 1] = xy[2 * i + 1]; m.resp[o] = rs[i];
+            trk_copy_desc(m.desc + (size_t)o * 32, ds + (size_t)i * 32);
+        }
+    }
+    const int nA = carry;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < k; base += TRK_THREADS) {               // landmark indices the map does not hold yet
+        const int i = base + threadIdx.x;
+        bool f = false;
+        int key = -1;
+        if (i < k) {
+            const int r = mt[i];
+            if (r >= 0 && (double)md[i] <= max_dist) {
+                key = li[r];
+                int lo = trk_lower_bound(m.idx, 0, b1, key);
+                bool have = lo < b1 && m.idx[lo] == key;
+                if (!have) { lo = trk_lower_bound(m.idx, b1, n, key); have = lo < n && m.idx[lo] == key; }
+                f = !have;
+            }
+        }
+        const int o = trk_scan_step(f, warp_sums, &carry);
+        if (f && o < cap) { skey[o] = key; ssrc[o] = i; }
+    }
+    const int nB = min(carry, cap);
+    __syncthreads();
+    for (int j = threadIdx.x; j < nB; j += TRK_THREADS) {             // ranked by index (a mutual match: keys are unique)
+        const int key = skey[j], i = ssrc[j];
+        int r = 0;
+        for (int q = 0; q < nB; ++q) r += skey[q] < key ? 1 : 0;
+        const int o = n + nA + r;
+        if (o < cap) {
+            m.idx[o] = key; m.xy[2 * o] = xy[2 * i]; m.xy[2 * o + 1] = xy[2 * i + 1]; m.resp[o] = rs[i];
+            trk_copy_desc(m.desc + (size_t)o * 32, ds + (size_t)i * 32);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int total = n + nA + nB;
+        if (total > cap) *overflow = 1;
+        *m.n = min(total, cap);
+        next_index[seq] = first + k;
+        int* rb = runs + ((size_t)seq * 2 + cam) * 5;
+        rb[0] = 0; rb[1] = b1; rb[2] = n; rb[3] = min(n + nA, cap); rb[4] = min(total, cap);
+    }
+}
+
+// one camera's map of every sequence sorted by index into `out`: an element's rank is its offset in its own ascending run
+// plus a lower-bound search in the (at most three) other runs.  grid: S
+__global__ void __launch_bounds__(TRK_THREADS) k_trk_sort_runs(trk_maps cur, trk_maps out, int cam, const int* __restrict__ runs)
+{
+    const int seq = blockIdx.x, cap = cur.cap;
+    const trk_map m = cur.at(seq, cam), o = out.at(seq, cam);
+    const int n = min(*m.n, cap);
+    const int* rb = runs + ((size_t)seq * 2 + cam) * 5;
+    int start[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) start[q] = min(max(rb[q], 0), n);
+    for (int i = threadIdx.x; i < n; i += TRK_THREADS) {
+        const int key = m.idx[i];
+        const int run = i < start[1] ? 0 : i < start[2] ? 1 : i < start[3] ? 2 : 3;
+        int r = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r += q == run ? i - start[q] : trk_lower_bound(m.idx, start[q], start[q + 1], key) - start[q];
+        o.idx[r] = key; o.xy[2 * r] = m.xy[2 * i]; o.xy[2 * r + 1] = m.xy[2 * i + 1]; o.resp[r] = m.resp[i];
+        trk_copy_desc(o.desc + (size_t)r * 32, m.desc + (size_t)i * 32);
+    }
+    if (threadIdx.x == 0) *o.n = n;
+}
+
+// the sorted map back into the working generation; a sorted right map is one run for the final k_trk_sort.  grid: S
+__global__ void __launch_bounds__(TRK_THREADS) k_trk_copy_map(trk_maps src, trk_maps dst, int cam, int* __restrict__ marks)
+{
+    const int seq = blockIdx.x, cap = src.cap;
+    const trk_map s = src.at(seq, cam), d = dst.at(seq, cam);
+    const int n = min(*s.n, cap);
+    for (int i = threadIdx.x; i < n; i += TRK_THREADS) {
+        d.idx[i] = s.idx[i]; d.xy[2 * i] = s.xy[2 * i]; d.xy[2 * i + 1] = s.xy[2 * i + 1]; d.resp[i] = s.resp[i];
+        trk_copy_desc(d.desc + (size_t)i * 32, s.desc + (size_t)i * 32);
+    }
+    if (threadIdx.x == 0) {
+        *d.n = n;
+        if (cam == 1) { marks[4 * seq + 2] = n; marks[4 * seq + 3] = n; }
+    }
+}
+
 static inline size_t trk_al(size_t v) { return (v + 255) / 256 * 256; }
 
 extern "C" zs_status zs_tracker_create(zs_context* ctx, const zs_tracker_options* opt, zs_tracker** out)
@@ -294,8 +433,11 @@ extern "C" zs_status zs_tracker_create(zs_context* ctx, const zs_tracker_options
     if (st != ZS_OK) { free(t); return st; }
     const size_t S = t->S, cap = t->cap, cells = t->cells, R = 2 * S;      // R map rows per generation
     size_t off = 0;
-    size_t o_map[2][5];                                  // prev, cur: idx | xy | resp | desc | n, each [S][2][cap]
-    for (int m = 0; m < 2; ++m) {
+    ZS_REQUIRE(opt->landmark_capacity >= 0 && opt->landmark_capacity <= (1 << 22), "landmark_capacity outside 0..4M");
+    t->lm_cap = opt->landmark_capacity > 0 ? (opt->landmark_capacity + 127) / 128 * 128 : 0;
+    const int gens = t->lm_cap > 0 ? 3 : 2;
+    size_t o_map[3][5];                                  // prev, cur (, tmp): idx | xy | resp | desc | n, each [S][2][cap]
+    for (int m = 0; m < gens; ++m) {
         o_map[m][0] = off; off += trk_al(sizeof(int) * R * cap);
         o_map[m][1] = off; off += trk_al(sizeof(float) * 2 * R * cap);
         o_map[m][2] = off; off += trk_al(sizeof(float) * R * cap);
@@ -309,14 +451,18 @@ extern "C" zs_status zs_tracker_create(zs_context* ctx, const zs_tracker_options
     TCARVE(det_n, sizeof(int) * S) TCARVE(det_desc, 32 * S * cells) TCARVE(sel, sizeof(int) * S * cap) TCARVE(sel_n, sizeof(int) * S)
     TCARVE(sel_pts, sizeof(float) * 2 * S * cap) TCARVE(next_index, sizeof(int) * S) TCARVE(overflow, 256) TCARVE(marks, sizeof(int) * 4 * S)
     TCARVE(pred_idx, sizeof(int) * R * cap) TCARVE(pred_xy, sizeof(float) * 2 * R * cap) TCARVE(pred_n, sizeof(int) * R)
+    const size_t LM = t->lm_cap;
+    TCARVE(lm_xyz, sizeof(double) * 3 * S * LM) TCARVE(lm_index, sizeof(int) * S * LM) TCARVE(lm_desc, 32 * S * LM) TCARVE(lm_n, sizeof(int) * S)
+    TCARVE(lm_center, sizeof(double) * 3 * S) TCARVE(lm_nt, sizeof(int) * S) TCARVE(lm_match, sizeof(int) * S * cells)
+    TCARVE(lm_dist, sizeof(float) * S * cells) TCARVE(lm_runs, sizeof(int) * 10 * S)
 #undef TCARVE
     cudaError_t e = cudaMalloc((void**)&t->dev, off);
     if (e != cudaSuccess) { zs_pyramid_destroy(t->pyr); free(t); return zs_cuda_fail(e, "cudaMalloc(tracker)", __FILE__, __LINE__); }
     t->dev_bytes = off;
     e = cudaMemsetAsync(t->dev, 0, off, ctx->stream);
     if (e != cudaSuccess) { cudaFree(t->dev); zs_pyramid_destroy(t->pyr); free(t); return zs_cuda_fail(e, "cudaMemset(tracker)", __FILE__, __LINE__); }
-    for (int m = 0; m < 2; ++m) {
-        trk_maps& g = m == 0 ? t->prev : t->cur;
+    for (int m = 0; m < gens; ++m) {
+        trk_maps& g = m == 0 ? t->prev : m == 1 ? t->cur : t->tmp;
         g.idx = (int*)(t->dev + o_map[m][0]); g.xy = (float*)(t->dev + o_map[m][1]); g.resp = (float*)(t->dev + o_map[m][2]);
         g.desc = t->dev + o_map[m][3]; g.n = (int*)(t->dev + o_map[m][4]); g.cap = t->cap;
     }
@@ -325,7 +471,14 @@ extern "C" zs_status zs_tracker_create(zs_context* ctx, const zs_tracker_options
     TBIND(raw_xy, float) TBIND(raw_resp, float) TBIND(raw_n, int) TBIND(det_xy, float) TBIND(det_resp, float) TBIND(det_n, int)
     TBIND(det_desc, uint8_t) TBIND(sel, int) TBIND(sel_n, int) TBIND(sel_pts, float) TBIND(next_index, int) TBIND(overflow, int)
     TBIND(marks, int) TBIND(pred_idx, int) TBIND(pred_xy, float) TBIND(pred_n, int)
+    TBIND(lm_xyz, double) TBIND(lm_index, int) TBIND(lm_desc, uint8_t) TBIND(lm_n, int) TBIND(lm_center, double) TBIND(lm_nt, int)
+    TBIND(lm_match, int) TBIND(lm_dist, float) TBIND(lm_runs, int)
 #undef TBIND
+    if (t->lm_cap > 0) {
+        t->lm_seen = new std::vector<std::unordered_set<int>>(S);
+        t->lm_host_n = new std::vector<int>(S, 0);
+        t->lm_bucket = t->lm_cap < 2048 ? t->lm_cap : 2048;
+    }
     {
         // slot(parity, camera, sequence) = (parity * 2 + camera) * S + sequence: the S images of one camera and parity are
         // contiguous slots, which is what the batched pyramid / detector / descriptor calls address
@@ -370,6 +523,8 @@ extern "C" void zs_tracker_destroy(zs_tracker* t)
     }
     if (t->pyr) zs_pyramid_destroy(t->pyr);
     if (t->dev) cudaFree(t->dev);
+    delete t->lm_seen;
+    delete t->lm_host_n;
     free(t);
 }
 
@@ -393,6 +548,68 @@ extern "C" zs_status zs_tracker_set_predictions(zs_tracker* t, int sequence, int
     return ZS_OK;
 }
 
+extern "C" zs_status zs_tracker_landmarks_add_host(zs_tracker* t, int sequence, const int* index, const double* xyz, const uint8_t* desc,
+                                                   int n, int* n_added)
+{
+    ZS_REQUIRE(t && sequence >= 0 && sequence < t->S, "bad argument");
+    ZS_REQUIRE(t->lm_cap > 0, "the tracker was created without a landmark store (landmark_capacity = 0)");
+    ZS_REQUIRE(n >= 0 && (n == 0 || (index && xyz && desc)), "bad landmark list");
+    if (n_added) *n_added = 0;
+    if (n == 0) return ZS_OK;
+    zs_context* ctx = t->ctx;
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    // map::operator+=(const map&) (types/map.h:222-236): only indices the map does not hold yet are added, in the order given
+    std::unordered_set<int>& seen = (*t->lm_seen)[sequence];
+    std::vector<int> rows;
+    rows.reserve(n);
+    for (int i = 0; i < n; ++i) if (seen.find(index[i]) == seen.end()) { seen.insert(index[i]); rows.push_back(i); }
+    const int have = (*t->lm_host_n)[sequence], add = (int)rows.size();
+    if (have + add > t->lm_cap) {
+        for (int i : rows) seen.erase(index[i]);
+        zs_set_error("landmark store of sequence %d would hold %d landmarks, landmark_capacity is %d", sequence, have + add, t->lm_cap);
+        return ZS_ERR_CAPACITY;
+    }
+    if (add == 0) return ZS_OK;
+    void* pin;
+    zs_status st = zs_pinned(ctx, (size_t)add * (24 + 4 + 32), &pin);
+    if (st != ZS_OK) return st;
+    double* hx = (double*)pin; int* hi = (int*)(hx + 3 * (size_t)add); uint8_t* hd = (uint8_t*)(hi + add);
+    for (int j = 0; j < add; ++j) {
+        const int i = rows[j];
+        hx[3 * j] = xyz[3 * i]; hx[3 * j + 1] = xyz[3 * i + 1]; hx[3 * j + 2] = xyz[3 * i + 2];
+        hi[j] = index[i];
+        memcpy(hd + (size_t)j * 32, desc + (size_t)i * 32, 32);
+    }
+    const size_t row0 = (size_t)sequence * t->lm_cap + have;
+    const int total = have + add;
+    ZS_CUDA(cudaMemcpyAsync(t->lm_xyz + row0 * 3, hx, sizeof(double) * 3 * add, cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(t->lm_index + row0, hi, sizeof(int) * add, cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(t->lm_desc + row0 * 32, hd, (size_t)add * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(t->lm_n + sequence, &total, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    (*t->lm_host_n)[sequence] = total;
+    // the matcher's train-side grid covers lm_bucket rows: grow it in powers of two (a change re-captures the step's graphs)
+    while (t->lm_bucket < total) t->lm_bucket = t->lm_bucket * 2 < t->lm_cap ? t->lm_bucket * 2 : t->lm_cap;
+    if (n_added) *n_added = add;
+    return ZS_OK;
+}
+
+extern "C" int zs_tracker_landmarks_size(const zs_tracker* t, int sequence)
+{
+    return (t && t->lm_cap > 0 && sequence >= 0 && sequence < t->S) ? (*t->lm_host_n)[sequence] : 0;
+}
+
+extern "C" zs_status zs_tracker_set_camera_center(zs_tracker* t, int sequence, const double* center)
+{
+    ZS_REQUIRE(t && center && sequence >= 0 && sequence < t->S, "bad argument");
+    ZS_REQUIRE(t->lm_cap > 0, "the tracker was created without a landmark store (landmark_capacity = 0)");
+    zs_context* ctx = t->ctx;
+    ZS_CUDA(cudaSetDevice(ctx->device));
+    ZS_CUDA(cudaMemcpyAsync(t->lm_center + 3 * (size_t)sequence, center, sizeof(double) * 3, cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZS_OK;
+}
+
 // detection of one camera of every sequence behind the occupancy of its current map (keypoint_tracker.cpp:53-57 / 69-73)
 static zs_status trk_detect(zs_tracker* t, int cam, int first_slot, int* d_mark)
 {
@@ -409,6 +626,25 @@ static zs_status trk_detect(zs_tracker* t, int cam, int first_slot, int* d_mark)
         return st;
     if ((st = zs_orb_compute(ctx, t->pyr, first_slot, t->S, t->raw_xy, t->raw_resp, nullptr, t->raw_n, t->cells, t->det_xy, t->det_resp,
                              nullptr, t->det_n, t->det_desc)) != ZS_OK) return st;
+    if (t->lm_cap > 0) {
+        // assign_landmark_indices(detected, system.points3d, frame_0.pose.translation(), landmark_match_radius,
+        // landmark_match_distance) (keypoint_tracker.cpp:55,71): candidates = radius search, then
+        // cv::BFMatcher(NORM_HAMMING, true).match(detected, candidates); an empty store matches nothing (:208)
+        if ((st = zs_lm_radius_count(ctx, t->lm_xyz, t->lm_n, t->lm_cap, t->lm_center, o.landmark_match_radius, t->S, t->lm_nt)) != ZS_OK)
+            return st;
+        if ((st = zs_match_hamming_cross(ctx, t->det_desc, t->det_n, (size_t)t->cells * 32, t->lm_desc, t->lm_nt, (size_t)t->lm_cap * 32, t->S,
+                                         t->cells, t->lm_bucket, t->lm_match, t->lm_dist)) != ZS_OK) return st;
+        k_trk_append_detected_lm<<<t->S, TRK_THREADS, 0, ctx->stream>>>(t->cur, cam, t->cells, t->det_xy, t->det_resp, t->det_desc, t->det_n,
+                                                                        t->lm_match, t->lm_dist, t->lm_index, t->lm_cap,
+                                                                        o.landmark_match_distance, t->next_index, t->overflow, t->marks,
+                                                                        t->lm_runs, t->sel, (int*)t->sel_pts);
+        ZS_LAUNCH_CHECK(ctx);
+        k_trk_sort_runs<<<t->S, TRK_THREADS, 0, ctx->stream>>>(t->cur, t->tmp, cam, t->lm_runs);
+        ZS_LAUNCH_CHECK(ctx);
+        k_trk_copy_map<<<t->S, TRK_THREADS, 0, ctx->stream>>>(t->tmp, t->cur, cam, t->marks);
+        ZS_LAUNCH_CHECK(ctx);
+        return ZS_OK;
+    }
     k_trk_append_detected<<<t->S, TRK_THREADS, 0, ctx->stream>>>(t->cur, cam, t->cells, t->det_xy, t->det_resp, t->det_desc, t->det_n,
                                                                  t->next_index, t->overflow, d_mark);
     ZS_LAUNCH_CHECK(ctx);
@@ -439,6 +675,10 @@ static zs_status trk_frame_body(zs_tracker* t, int par)
     const int S = t->S, cap = t->cap, first_l = (par * 2) * S, first_r = (par * 2 + 1) * S;
     const int* sl = t->slots + 6 * S * par;
     zs_status st;
+    // the overflow flag belongs to ONE step: it is cleared here and reported (ZS_ERR_CAPACITY) by the download / wait of this
+    // step only -- a map that shrinks again stops failing.  A step that overflowed has truncated maps (keypoints past the
+    // capacity are dropped, keypoint::index_next still advances past them).
+    ZS_CUDA(cudaMemsetAsync(t->overflow, 0, sizeof(int), ctx->stream));
     if ((st = zs_pyramid_build(ctx, t->pyr, first_l, 2 * S)) != ZS_OK) return st;      // left and right slots are adjacent
     zs_lk_params prm;
     prm.win_w = o.klt_win_w; prm.win_h = o.klt_win_h; prm.max_level = o.klt_max_level; prm.max_iters = 99; prm.epsilon = 0.001;
@@ -474,7 +714,9 @@ static zs_status trk_frame(zs_tracker* t, int par)
 {
     zs_context* ctx = t->ctx;
     if (!t->graph_ok || t->runs[par]++ == 0) return trk_frame_body(t, par);
-    if (t->gexec[par] && t->g_scratch[par] != ctx->scratch) { cudaGraphExecDestroy(t->gexec[par]); t->gexec[par] = nullptr; }
+    if (t->gexec[par] && (t->g_scratch[par] != ctx->scratch || t->g_bucket[par] != t->lm_bucket)) {
+        cudaGraphExecDestroy(t->gexec[par]); t->gexec[par] = nullptr;        // the captured launches bake scratch pointers and grid sizes in
+    }
     if (!t->gexec[par]) {
         void* scratch_before = ctx->scratch;
         const uint64_t l0 = ctx->launches;
@@ -498,6 +740,7 @@ static zs_status trk_frame(zs_tracker* t, int par)
         t->g_launches[par] = ctx->launches - l0;
         ctx->launches = l0;
         t->g_scratch[par] = ctx->scratch;
+        t->g_bucket[par] = t->lm_bucket;
     }
     ZS_CUDA(cudaGraphLaunch(t->gexec[par], ctx->stream));
     ctx->launches += t->g_launches[par];

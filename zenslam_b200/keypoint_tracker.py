@@ -111,7 +111,7 @@ class device_keypoint_tracker:
     the host)."""
 
     def __init__(self, options: slam_options, ctx, width: int, height: int, first_index: int = 0, capacity: int = 0,
-                 sequences: int = 1):
+                 sequences: int = 1, landmark_capacity: int = 0):
         import ctypes as C
 
         from ._lib import TrackerOptions, check, lib
@@ -123,7 +123,8 @@ class device_keypoint_tracker:
         self._ctx, self.width, self.height, self.sequences = ctx, width, height, sequences
         o = TrackerOptions(width, height, det.cell_size[0], det.cell_size[1], det.fast_threshold, trk.klt_window_size[0],
                            trk.klt_window_size[1], trk.klt_max_level, trk.klt_threshold, capacity, first_index, sequences,
-                           1 if det.algorithm == "PARALLEL_GRID" else 0)
+                           1 if det.algorithm == "PARALLEL_GRID" else 0, landmark_capacity, trk.landmark_match_radius,
+                           trk.landmark_match_distance)
         h = C.c_void_p()
         check(lib().zs_tracker_create(ctx._h, C.byref(o), C.byref(h)))
         self._h = h
@@ -154,6 +155,38 @@ class device_keypoint_tracker:
         idx = np.array(keys, np.int32); xy = np.array([predictions[k] for k in keys], np.float32).reshape(-1, 2)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         check(lib().zs_tracker_set_predictions(self._h, sequence, camera, p(idx), p(xy), len(keys)))
+
+    def add_landmarks(self, index, xyz, descriptors, sequence: int = 0) -> int:
+        """`system.points3d += ...` (slam_thread.cpp:210): landmarks whose index the device store already holds are skipped,
+        the others appended in the order given.  index (n,) int, xyz (n, 3) world coordinates, descriptors (n, 32) u8.
+        -> number of landmarks added.  Needs landmark_capacity > 0 at construction."""
+        import ctypes as C
+
+        import numpy as np
+
+        from ._lib import check, lib
+        idx = np.ascontiguousarray(index, np.int32); xyz = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)
+        desc = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        assert len(idx) == len(xyz) == len(desc)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        added = C.c_int(0)
+        check(lib().zs_tracker_landmarks_add_host(self._h, sequence, p(idx), p(xyz), p(desc), len(idx), C.byref(added)))
+        return added.value
+
+    def landmarks_size(self, sequence: int = 0) -> int:
+        from ._lib import lib
+        return int(lib().zs_tracker_landmarks_size(self._h, sequence))
+
+    def set_camera_center(self, center, sequence: int = 0):
+        """frame_0.pose.translation(): centre of the radius search of the next step's assign_landmark_indices
+        (keypoint_tracker.cpp:56,72,213)"""
+        import ctypes as C
+
+        import numpy as np
+
+        from ._lib import check, lib
+        c = np.ascontiguousarray(center, np.float64).reshape(3)
+        check(lib().zs_tracker_set_camera_center(self._h, sequence, c.ctypes.data_as(C.c_void_p)))
 
     def track_all(self, left, right):
         """left / right: (sequences, H, W) u8 -> [(keypoints_0, keypoints_1)] per sequence (keypoint_map each); the

@@ -88,3 +88,31 @@ def assign_landmark_indices(ctx: Context, keypoints: list, landmark_descriptors:
             keypoints[i].index = int(landmark_indices[int(lm[j])])
             n += 1
     return n
+
+
+def match_keypoints3d(ctx: Context, landmark_index, landmark_xyz, landmark_desc, keypoints, R, t, projection, radius: float,
+                      threshold: float, image_size=None, frustum_margin: float = 50.0) -> list:
+    """utils::match_keypoints3d (zenslam_core/source/matching/matching_utils.cpp:132-216; with image_size the overload with
+    frustum culling, :218-343).  Landmarks in the cloud's insertion order (index (M,), xyz (M, 3) world, desc (M, 32));
+    `keypoints`: a map / list of keypoints -- the ones whose index is a landmark index are dropped here, like
+    keypoints.values_unmatched(points3d_world), the rest go in key order.  R, t = pose_of_camera0_in_world; projection 3x4.
+    -> [DMatch(queryIdx = landmark index, trainIdx = keypoint index, distance = reprojection error)]"""
+    lm_i = np.ascontiguousarray(landmark_index, np.int32); lm_x = np.ascontiguousarray(landmark_xyz, np.float64).reshape(-1, 3)
+    lm_d = np.ascontiguousarray(landmark_desc, np.uint8).reshape(-1, 32)
+    kps = [keypoints[k] for k in sorted(keypoints)] if isinstance(keypoints, dict) else sorted(keypoints, key=lambda k: k.index)
+    have = set(lm_i.tolist())
+    kps = [k for k in kps if k.index not in have]
+    if len(lm_i) == 0 or not kps:
+        return []
+    k_i = np.array([k.index for k in kps], np.int32); k_xy = np.array([k.pt for k in kps], np.float32).reshape(-1, 2)
+    k_d = np.ascontiguousarray(np.stack([k.descriptor for k in kps]), np.uint8)
+    Rm = np.ascontiguousarray(R, np.float64).reshape(3, 3); tv = np.ascontiguousarray(t, np.float64).reshape(3)
+    P = np.ascontiguousarray(projection, np.float64).reshape(3, 4)
+    cap = min(len(lm_i), len(kps))
+    o_l = np.empty(cap, np.int32); o_k = np.empty(cap, np.int32); o_e = np.empty(cap, np.float32)
+    n = C.c_int(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    w, h = (int(image_size[0]), int(image_size[1])) if image_size is not None else (0, 0)
+    check(lib().zs_match_keypoints3d_host(ctx._h, p(lm_i), p(lm_x), p(lm_d), len(lm_i), p(k_i), p(k_xy), p(k_d), len(kps), p(Rm), p(tv), p(P),
+                                          float(radius), float(threshold), w, h, float(frustum_margin), p(o_l), p(o_k), p(o_e), C.byref(n)))
+    return [DMatch(int(o_l[i]), int(o_k[i]), float(o_e[i])) for i in range(n.value)]

@@ -34,6 +34,7 @@ class tracking_options:
     klt_threshold: float = 1.0
     klt_min_tracked_ratio: float = 0.6
     landmark_match_distance: float = 32.0
+    landmark_match_radius: float = 50.0
     filter_epipolar: bool = True
     epipolar_threshold: float = 1.0
 
@@ -95,6 +96,7 @@ def parse_slam(node) -> slam_options:
     t.klt_threshold = _get(tn, "klt_threshold", t.klt_threshold, float)
     t.klt_min_tracked_ratio = _get(tn, "klt_min_tracked_ratio", t.klt_min_tracked_ratio, float)
     t.landmark_match_distance = _get(tn, "landmark_match_distance", t.landmark_match_distance, float)
+    t.landmark_match_radius = _get(tn, "landmark_match_radius", t.landmark_match_radius, float)
     t.filter_epipolar = _get(tn, "filter_epipolar", t.filter_epipolar, bool)
     t.epipolar_threshold = _get(tn, "epipolar_threshold", t.epipolar_threshold, float)
     return o
