@@ -26,7 +26,15 @@ cv::Ptr<cv::DescriptorMatcher> zenslam::cuda::bf_matcher::clone(const bool empty
 
 void zenslam::cuda::bf_matcher::knnMatchImpl(cv::InputArray query, std::vector<std::vector<cv::DMatch>>& matches, const int k, cv::InputArrayOfArrays masks, const bool compact_result)
 {
-    CV_Assert(masks.empty());                               // the reference never passes masks (matcher.cpp:65,79)
+    // The reference never passes a mask (matcher.cpp:65,79), but cv::DescriptorMatcher's (query, train, ...) forms forward
+    // to this function with std::vector<cv::Mat>(1, mask.getMat()): a NON-empty vector holding one EMPTY Mat.  Like
+    // cv::BFMatcher, accept that; a real mask is what this matcher does not implement (isMaskSupported() == false).
+    std::vector<cv::Mat> mask_list { };
+    masks.getMatVector(mask_list);
+
+    for (const auto& mask : mask_list)
+        CV_Assert(mask.empty());
+
     CV_Assert(k == 1 || (k == 2 && !_cross_check));         // the only forms the reference uses
     CV_Assert(trainDescCollection.size() == 1);             // match(query, train) form: one train image
 
