@@ -60,6 +60,10 @@ ZS_API const char* zs_last_error_string(void);
 ZS_API zs_status zs_context_create(int device, void* stream, zs_context** out);
 ZS_API void zs_context_destroy(zs_context* ctx);
 ZS_API zs_status zs_context_synchronize(zs_context* ctx);
+/* errors that kernels of stream-asynchronous entries found in their DATA (zs_match_l2_*: descriptors that are not integers
+ * in 0..255): waits for the stream, returns ZS_ERR_UNSUPPORTED with a message if one was raised since the last call, and
+ * clears it */
+ZS_API zs_status zs_context_async_error(zs_context* ctx);
 ZS_API void* zs_context_stream(zs_context* ctx);
 /* number of kernels this library has launched on the context since creation */
 ZS_API uint64_t zs_context_launch_count(const zs_context* ctx);
@@ -197,8 +201,11 @@ ZS_API zs_status zs_match_hamming_knn2(zs_context* ctx, const uint8_t* d_q, cons
 ZS_API zs_status zs_match_hamming_cross(zs_context* ctx, const uint8_t* d_q, const int* d_nq, size_t q_stride,
                                         const uint8_t* d_t, const int* d_nt, size_t t_stride, int pairs,
                                         int cap_q, int cap_t, int* d_idx, float* d_dist);
-/* L2 on integer-valued float descriptors (cv::SIFT, values 0..255): exact; runs the
- * -2 A.B^T contraction on the tcgen05 tensor cores in bf16.  dim must be a multiple of 64. */
+/* L2 on integer-valued float descriptors (cv::SIFT, values 0..255): exact.  128-d rows run the -2 A.B^T
+ * contraction on the tcgen05 tensor cores (kind::i8 on the u8-narrowed rows); other dims (multiples of 4, <= 128) a dp4a
+ * kernel.  The calls are stream-asynchronous and never wait for the device: rows holding anything but integers in 0..255
+ * make EVERY match of that call come back as -1 (d_pass 0) and raise a flag that zs_context_async_error() -- and the host
+ * entries zs_match_host / zs_knn_match_host -- report as ZS_ERR_UNSUPPORTED. */
 ZS_API zs_status zs_match_l2_knn2(zs_context* ctx, const float* d_q, const int* d_nq, size_t q_stride,
                                   const float* d_t, const int* d_nt, size_t t_stride, int pairs,
                                   int cap_q, int cap_t, int dim, double ratio,
@@ -206,6 +213,15 @@ ZS_API zs_status zs_match_l2_knn2(zs_context* ctx, const float* d_q, const int* 
 ZS_API zs_status zs_match_l2_cross(zs_context* ctx, const float* d_q, const int* d_nq, size_t q_stride,
                                    const float* d_t, const int* d_nt, size_t t_stride, int pairs,
                                    int cap_q, int cap_t, int dim, int* d_idx, float* d_dist);
+/* The same two matchers on u8 rows (cv::SIFT::create(..., descriptorType = CV_8U) output, or float rows narrowed where they
+ * are produced): dense [pairs][cap][dim] bytes, 16-byte aligned; no conversion pass and a quarter of the bytes to move.
+ * Same results as the float entries on the same values (cv::BFMatcher(NORM_L2) on CV_8U rows). */
+ZS_API zs_status zs_match_l2_knn2_u8(zs_context* ctx, const uint8_t* d_q, const int* d_nq, const uint8_t* d_t,
+                                     const int* d_nt, int pairs, int cap_q, int cap_t, int dim, double ratio,
+                                     int* d_idx, float* d_dist, uint8_t* d_pass);
+ZS_API zs_status zs_match_l2_cross_u8(zs_context* ctx, const uint8_t* d_q, const int* d_nq, const uint8_t* d_t,
+                                      const int* d_nt, int pairs, int cap_q, int cap_t, int dim,
+                                      int* d_idx, float* d_dist);
 
 /* ---- KLT: pyr_lk::calc_optical_flow_pyr_lk == cv::calcOpticalFlowPyrLK ----------------------
  * (zenslam_core/include/zenslam/tracking/pyr_lk.h:15-26; zenslam_core/source/tracking/pyr_lk.cpp:25)
@@ -284,7 +300,7 @@ ZS_API zs_status zs_detect_keypoints_simple_host(zs_context* ctx, const uint8_t*
                                                  float* x, float* y, float* response, uint8_t* desc, int cap,
                                                  int* n_out);
 /* matcher::match_keypoints descriptor stage: mode 0 = KNN (ratio), 1 = BRUTE (cross-check);
- * norm 0 = Hamming (32-byte rows), 1 = L2 (dim floats).  Outputs sized nq; *n_out matches. */
+ * norm 0 = Hamming (32-byte rows), 1 = L2 (dim floats), 2 = L2 on u8 rows (dim bytes).  Outputs sized nq; *n_out matches. */
 ZS_API zs_status zs_match_host(zs_context* ctx, const void* q, int nq, const void* t, int nt, int dim,
                                int norm, int mode, double ratio, int* query_idx, int* train_idx, float* distance,
                                int* n_out);

@@ -122,3 +122,36 @@ def match_keypoints3d(cloud: landmark_cloud, kp_index, kp_xy, kp_desc, R, t, pro
     err = np.sqrt(e[:, 0] * e[:, 0] + e[:, 1] * e[:, 1])
     ok = err < float(threshold)
     return cloud.index[rows][q[ok]], kp_index[un][tr[ok]], err[ok].astype(np.float32)
+
+
+def match_temporal(keys_0, pts_0, desc_0, keys_1, pts_1, desc_1, camera_matrix, threshold, find_essential_mat):
+    """utils::match_temporal (zenslam_core/source/matching/matching_utils.cpp:441-563) restated: unmatched keypoints of both
+    maps in key order (:453-483), fewer than five on either side -> nothing (:485-488), BFMatcher(NORM_HAMMING, crossCheck)
+    (:490-497), the caller's findEssentialMat (:512-519), then mask / epipolar error / distance <= 5 (:531-559).  The essential
+    matrix is read the way the reference reads it: e.at<float> on the CV_64F result (:519-528).
+    keys_* ascending int arrays, pts_* (n, 2) f32, desc_* (n, 32) u8 -> [(index_0, index_1, distance)]"""
+    import oracle
+    keys_0 = np.asarray(keys_0, np.int64); keys_1 = np.asarray(keys_1, np.int64)
+    s0, s1 = set(keys_0.tolist()), set(keys_1.tolist())
+    u0 = [i for i in np.argsort(keys_0, kind="stable") if int(keys_0[i]) not in s1]
+    u1 = [i for i in np.argsort(keys_1, kind="stable") if int(keys_1[i]) not in s0]
+    if len(u0) < 5 or len(u1) < 5:
+        return []
+    oq, ot, od = oracle.match_hamming_cross(np.asarray(desc_0, np.uint8)[u0], np.asarray(desc_1, np.uint8)[u1])
+    if len(oq) == 0:
+        return []
+    p0 = np.asarray(pts_0, np.float32)[[u0[a] for a in oq]]; p1 = np.asarray(pts_1, np.float32)[[u1[b] for b in ot]]
+    essential, mask = find_essential_mat(p0, p1)
+    e64 = np.ascontiguousarray(essential, np.float64).reshape(3, 3)
+    E = np.frombuffer(e64.tobytes(), np.float32).reshape(3, 6)[:, :3].astype(np.float64)
+    k_inv = np.linalg.inv(np.asarray(camera_matrix, np.float64).reshape(3, 3))
+    out = []
+    for j, m in enumerate(np.asarray(mask).ravel()[:len(oq)]):
+        if not m:
+            continue
+        a, b = np.append(p0[j].astype(np.float64), 1.0), np.append(p1[j].astype(np.float64), 1.0)
+        err = float((((b @ k_inv.T) @ E) @ k_inv) @ a)
+        if err > threshold or float(od[j]) > 5:
+            continue
+        out.append((int(keys_0[u0[oq[j]]]), int(keys_1[u1[ot[j]]]), float(od[j])))
+    return out

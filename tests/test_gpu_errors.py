@@ -42,6 +42,15 @@ def test_bad_arguments_return_status(ctx):
     o = _lib.FrontendOptions(752, 480, 0, 16, 16, 10, 31, 31, 3, 1.0, 0.8, 99, 0.001, 1e-4)
     assert L.zs_frontend_create(ctx._h, C.byref(o), C.byref(fe)) == ZS_ERR_INVALID                     # batch 0
     assert L.zs_status_string(ZS_ERR_INVALID) and L.zs_status_string(0)
+    # GRID with cells that can reach the reference's ORB::detect fallback for empty cells (keypoint_detector_grid.cpp:92-95)
+    # is refused, not approximated; PARALLEL_GRID (no fallback in the reference) and provably safe sizes are accepted
+    for cell, thr, parallel, want in ((80, 10, 0, ZS_ERR_UNSUPPORTED), (64, 25, 0, ZS_ERR_UNSUPPORTED), (64, 10, 0, 0), (80, 10, 1, 0)):
+        o = _lib.FrontendOptions(752, 480, 1, cell, cell, thr, 31, 31, 3, 1.0, 0.8, 99, 0.001, 1e-4, parallel)
+        assert L.zs_frontend_create(ctx._h, C.byref(o), C.byref(fe)) == want, (cell, thr, parallel)
+        if want == 0:
+            L.zs_frontend_destroy(fe)
+        else:
+            assert b"fallback" in L.zs_last_error_string()
 
 
 def test_empty_inputs_are_empty_outputs(ctx):

@@ -183,3 +183,42 @@ def test_match_keypoints3d_vs_oracle(ctx, m, n_kp, radius, frustum):
         assert len(got) > 10
     assert match_keypoints3d(ctx, cloud.index, cloud.xyz, cloud.desc, {}, R, t, P, radius, 2.0) == []
     assert match_keypoints3d(ctx, [], np.zeros((0, 3)), np.zeros((0, 32), np.uint8), kps, R, t, P, radius, 2.0) == []
+
+
+def test_match_temporal_vs_oracle(ctx):
+    """utils::match_temporal (matching_utils.cpp:441-563): unmatched selection, the five-keypoint floor, the cross-checked
+    Hamming match on the device and the mask / epipolar / distance <= 5 gate, with findEssentialMat supplied by the caller."""
+    from zenslam_b200 import keypoint
+    from zenslam_b200.matching import match_temporal
+    rng = np.random.default_rng(77)
+    n0, n1 = 400, 380
+    d0 = rng.integers(0, 256, (n0, 32), dtype=np.uint8)
+    d1 = rng.integers(0, 256, (n1, 32), dtype=np.uint8)
+    d1[:250] = d0[50:300]
+    flips = rng.integers(0, 9, 250)                                     # 0..8 flipped bits: some matches beyond distance 5
+    for i, f in enumerate(flips):
+        for b in rng.choice(256, f, replace=False):
+            d1[i, b // 8] ^= np.uint8(1 << (b % 8))
+    keys_0 = np.sort(rng.choice(5000, n0, replace=False)); keys_1 = np.sort(rng.choice(np.arange(5000, 9000), n1, replace=False))
+    keys_1[:40] = keys_0[300:340]                                       # shared indices: dropped from both sides
+    keys_1 = np.sort(keys_1)
+    p0 = rng.uniform(0, 700, (n0, 2)).astype(np.float32); p1 = rng.uniform(0, 700, (n1, 2)).astype(np.float32)
+    K = np.array([[450.0, 0, 376.0], [0, 450.0, 240.0], [0, 0, 1.0]])
+    E = np.array([[0.0, -0.2, 0.05], [0.2, 0.0, -1.0], [-0.05, 1.0, 0.0]])
+    seen = []
+
+    def fem(points_0, points_1):
+        seen.append((points_0.copy(), points_1.copy()))
+        mask = (np.arange(len(points_0)) % 4 != 1).astype(np.uint8)     # what RANSAC would hand back: some outliers
+        return E, mask
+
+    m0 = {int(k): keypoint(pt=(float(p0[i, 0]), float(p0[i, 1])), index=int(k), descriptor=d0[i]) for i, k in enumerate(keys_0)}
+    m1 = {int(k): keypoint(pt=(float(p1[i, 0]), float(p1[i, 1])), index=int(k), descriptor=d1[i]) for i, k in enumerate(keys_1)}
+    for thr in (1e30, 0.0):
+        got = match_temporal(ctx, m0, m1, K, thr, fem)
+        want = olm.match_temporal(keys_0, p0, d0, keys_1, p1, d1, K, thr, fem)
+        assert [(g.queryIdx, g.trainIdx, g.distance) for g in got] == want
+        assert np.array_equal(seen[-1][0], seen[-2][0]) and np.array_equal(seen[-1][1], seen[-2][1])
+    assert len(match_temporal(ctx, m0, m1, K, 1e30, fem)) > 20
+    few = {k: m0[k] for k in list(m0)[:4]}
+    assert match_temporal(ctx, few, m1, K, 1e30, fem) == [] and match_temporal(ctx, m1, few, K, 1e30, fem) == []

@@ -285,11 +285,54 @@ def test_l2_golden_sift(ctx, golden):
 
 def test_l2_rejects_non_integer(ctx):
     from zenslam_b200 import ZenslamCudaError
-    from zenslam_b200.runtime import match_l2_knn2
+    from zenslam_b200.runtime import match_l2_cross, match_l2_knn2
     q = np.random.default_rng(0).random((1, 8, 128), dtype=np.float32)
     n = dev(ctx, np.array([8], np.int32))
+    # the device entry never waits for the GPU: it reports through the data (no neighbour anywhere) ...
+    idx, dist, ps = match_l2_knn2(ctx, dev(ctx, q), n, dev(ctx, q), n, 0.8)
+    assert (idx.cpu().numpy() == -1).all() and not ps.cpu().numpy().any()
+    cidx, _ = match_l2_cross(ctx, dev(ctx, q), n, dev(ctx, q), n)
+    assert (cidx.cpu().numpy() == -1).all()
+    # ... and through the context's asynchronous error, which is raised once and then cleared
     with pytest.raises(ZenslamCudaError):
-        match_l2_knn2(ctx, dev(ctx, q), n, dev(ctx, q), n, 0.8)
+        ctx.async_error()
+    ctx.async_error()
+    # the host entries (what the C++ bf_matcher calls) return the status themselves
+    from zenslam_b200 import _lib
+    import ctypes as C
+    out_i = np.zeros((8, 2), np.int32); out_d = np.zeros((8, 2), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert _lib.lib().zs_knn_match_host(ctx._h, p(q[0]), 8, p(q[0]), 8, 128, 1, 2, 0, p(out_i), p(out_d)) == -5
+    ok = np.rint(q[0] * 200).astype(np.float32)
+    assert _lib.lib().zs_knn_match_host(ctx._h, p(ok), 8, p(ok), 8, 128, 1, 2, 0, p(out_i), p(out_d)) == 0
+    assert np.array_equal(out_i[:, 0], np.arange(8))
+
+
+@pytest.mark.parametrize("nq,nt,dim", [(2000, 1700, 128), (300, 517, 128), (90, 75, 64)])
+def test_l2_u8_rows_equal_float_rows(ctx, nq, nt, dim):
+    """zs_match_l2_*_u8 (no conversion pass) == the float entries on the same values == the oracle; also through the host entry
+    with norm 2"""
+    import ctypes as C
+
+    from zenslam_b200 import _lib
+    from zenslam_b200.runtime import match_l2_cross, match_l2_knn2
+    rng = np.random.default_rng(nq + dim)
+    q = rng.integers(0, 256, (nq, dim)).astype(np.uint8); t = rng.integers(0, 256, (nt, dim)).astype(np.uint8)
+    t[:40] = q[10:50]; t[41] = t[3]
+    dnq, dnt = dev(ctx, np.array([nq], np.int32)), dev(ctx, np.array([nt], np.int32))
+    oi, od = oracle.match_l2_knn2(q.astype(np.float32), t.astype(np.float32))
+    for cast in (np.uint8, np.float32):
+        idx, dist, ps = match_l2_knn2(ctx, dev(ctx, q[None].astype(cast)), dnq, dev(ctx, t[None].astype(cast)), dnt, 0.8)
+        assert np.array_equal(idx[0].cpu().numpy(), oi) and np.array_equal(dist[0].cpu().numpy(), od), cast
+        cidx, cdist = match_l2_cross(ctx, dev(ctx, q[None].astype(cast)), dnq, dev(ctx, t[None].astype(cast)), dnt)
+        oq, ot, odd = oracle.match_l2_cross(q.astype(np.float32), t.astype(np.float32))
+        keep = np.nonzero(cidx[0].cpu().numpy() >= 0)[0]
+        assert np.array_equal(keep, oq) and np.array_equal(cidx[0].cpu().numpy()[keep], ot) and np.array_equal(cdist[0].cpu().numpy()[keep], odd)
+    ctx.async_error()
+    out_i = np.zeros((nq, 2), np.int32); out_d = np.zeros((nq, 2), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert _lib.lib().zs_knn_match_host(ctx._h, p(q), nq, p(t), nt, dim, 2, 2, 0, p(out_i), p(out_d)) == 0
+    assert np.array_equal(out_i, oi) and np.array_equal(out_d, od)
 
 
 @pytest.mark.parametrize("nq,nt", [(2000, 2000), (517, 1033), (1, 300), (256, 128)])

@@ -76,6 +76,7 @@ SIGNATURES = {
     "zs_context_create": (I, [I, P, C.POINTER(P)]),
     "zs_context_destroy": (None, [P]),
     "zs_context_synchronize": (I, [P]),
+    "zs_context_async_error": (I, [P]),
     "zs_context_stream": (P, [P]),
     "zs_context_launch_count": (C.c_uint64, [P]),
     "zs_context_reload_switches": (I, [P]),
@@ -109,6 +110,8 @@ SIGNATURES = {
     "zs_match_hamming_cross": (I, [P, P, P, Z, P, P, Z, I, I, I, P, P]),
     "zs_match_l2_knn2": (I, [P, P, P, Z, P, P, Z, I, I, I, I, D, P, P, P]),
     "zs_match_l2_cross": (I, [P, P, P, Z, P, P, Z, I, I, I, I, P, P]),
+    "zs_match_l2_knn2_u8": (I, [P, P, P, P, P, I, I, I, I, D, P, P, P]),
+    "zs_match_l2_cross_u8": (I, [P, P, P, P, P, I, I, I, I, P, P]),
     "zs_klt_track": (I, [P, P, P, P, P, P, P, I, I, C.POINTER(LkParams), P, P]),
     "zs_klt_track_fb": (I, [P, P, P, P, P, P, P, I, I, C.POINTER(LkParams), D, P, P, P]),
     "zs_calc_optical_flow_pyr_lk_host": (I, [P, P, P, I, I, Z, P, P, I, P, P, C.POINTER(LkParams)]),

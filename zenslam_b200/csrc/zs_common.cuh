@@ -59,6 +59,9 @@ struct zs_context {
     // four distinct images, two of them already seen by the previous frame's calls)
     uint64_t lk_hash[ZS_LK_CACHE_SLOTS], lk_stamp[ZS_LK_CACHE_SLOTS], lk_clock;
     uint64_t lk_hits, lk_misses;
+    int* d_async_err;         // device flags raised by kernels of stream-asynchronous entries ([0]: L2 descriptors not integers in 0..255)
+    uint8_t* lk_copy[ZS_LK_CACHE_SLOTS];   // host copy (w*h, no pitch) of the frame each slot holds: a hash hit is confirmed byte for byte
+    size_t lk_copy_bytes[ZS_LK_CACHE_SLOTS];
 };
 
 struct zs_pyramid {

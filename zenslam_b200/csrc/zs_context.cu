@@ -142,7 +142,34 @@ zs_status zs_context_create(int device, void* stream, zs_context** out)
         if (e != cudaSuccess) { free(c); return zs_cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
         c->own_stream = true;
     }
+    {
+        cudaError_t e = cudaMalloc((void**)&c->d_async_err, 256);
+        if (e == cudaSuccess) e = cudaMemset(c->d_async_err, 0, 256);
+        if (e != cudaSuccess) {
+            if (c->own_stream) cudaStreamDestroy(c->stream);
+            free(c);
+            return zs_cuda_fail(e, "cudaMalloc(async error flags)", __FILE__, __LINE__);
+        }
+    }
     *out = c;
+    return ZS_OK;
+}
+
+// Errors that kernels of stream-asynchronous entries found in their DATA (not their arguments): waits for the stream, reports
+// and clears them.  [0]: zs_match_l2_* got descriptors that are not integers in 0..255.
+zs_status zs_context_async_error(zs_context* c)
+{
+    ZS_REQUIRE(c, "ctx is null");
+    ZS_CUDA(cudaSetDevice(c->device));
+    int flags[4] = { 0, 0, 0, 0 };
+    ZS_CUDA(cudaMemcpyAsync(flags, c->d_async_err, sizeof(flags), cudaMemcpyDeviceToHost, c->stream));
+    ZS_CUDA(cudaStreamSynchronize(c->stream));
+    if (flags[0]) {
+        ZS_CUDA(cudaMemsetAsync(c->d_async_err, 0, sizeof(flags), c->stream));
+        zs_set_error("L2 matching is exact only for integer-valued descriptors in 0..255 (cv::SIFT); got other values "
+                     "(every match of that call was reported as -1)");
+        return ZS_ERR_UNSUPPORTED;
+    }
     return ZS_OK;
 }
 
@@ -152,7 +179,9 @@ void zs_context_destroy(zs_context* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 2; ++i) if (c->host_pyr[i]) zs_pyramid_destroy(c->host_pyr[i]);
+    for (int i = 0; i < ZS_LK_CACHE_SLOTS; ++i) free(c->lk_copy[i]);
     if (c->host_orb) zs_orb_detector_destroy(c->host_orb);
+    if (c->d_async_err) cudaFree(c->d_async_err);
     if (c->scratch) cudaFree(c->scratch);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->own_stream) cudaStreamDestroy(c->stream);

@@ -92,6 +92,16 @@ extern "C" zs_status zs_frontend_create(zs_context* ctx, const zs_frontend_optio
     ZS_REQUIRE(ctx && opt && out, "null argument");
     ZS_REQUIRE(opt->width > 0 && opt->height > 0 && opt->batch > 0, "bad geometry");
     ZS_REQUIRE(opt->cell_w >= 7 && opt->cell_h >= 7, "cell size must be at least 7");
+    // GRID (not PARALLEL_GRID) sends a free cell where FAST finds nothing through cv::ORB::detect (keypoint_detector_grid.cpp:92-95),
+    // which is not implemented.  That detector has a search area only in cells of at least 63 x 63 px; on its level 0 it finds
+    // nothing FAST(threshold <= 20) has not found, and its level 1 needs a 76-px cell: inside these bounds the batched flow is
+    // exact, outside it is refused (the per-call host entry checks the actual cells instead, zs_host.cu)
+    if (!opt->parallel_grid && opt->cell_w >= 63 && opt->cell_h >= 63 && !(opt->cell_w < 76 && opt->cell_h < 76 && opt->fast_threshold <= 20)) {
+        zs_set_error("GRID with %d x %d px cells and FAST threshold %d can reach the reference's ORB::detect fallback for empty cells "
+                     "(keypoint_detector_grid.cpp:92-95), which is not implemented: use PARALLEL_GRID or cells <= 62 px",
+                     opt->cell_w, opt->cell_h, opt->fast_threshold);
+        return ZS_ERR_UNSUPPORTED;
+    }
     ZS_CUDA(cudaSetDevice(ctx->device));
     zs_frontend* fe = (zs_frontend*)calloc(1, sizeof(zs_frontend));
     fe->ctx = ctx; fe->opt = *opt; fe->B = opt->batch;

@@ -52,6 +52,16 @@ static uint64_t frame_hash(const uint8_t* img, int w, int h, size_t pitch)
     return hsh ? hsh : 1;                      // 0 marks an empty slot
 }
 
+// a hash match is only a candidate: the cached frame must equal the caller's byte for byte (a collision would
+// silently track against a stale pyramid)
+static bool frame_equals(const uint8_t* copy, const uint8_t* img, int w, int h, size_t pitch)
+{
+    if (!copy) return false;
+    for (int y = 0; y < h; ++y)
+        if (memcmp(copy + (size_t)y * w, img + (size_t)y * pitch, w) != 0) return false;
+    return true;
+}
+
 // the LK pyramid of the host mirrors: ZS_LK_CACHE_SLOTS slots, least-recently-used replacement
 static zs_status lk_pyramid(zs_context* ctx, int w, int h, const zs_lk_params* prm, zs_pyramid** out)
 {
@@ -71,7 +81,7 @@ static zs_status lk_slot(zs_context* ctx, zs_pyramid* p, const uint8_t* img, int
     int lru = -1;
     for (int s = 0; s < ZS_LK_CACHE_SLOTS; ++s) {
         if (s == avoid) continue;
-        if (!no_cache && ctx->lk_hash[s] == hsh) {
+        if (!no_cache && ctx->lk_hash[s] == hsh && frame_equals(ctx->lk_copy[s], img, w, h, pitch)) {
             ctx->lk_stamp[s] = ++ctx->lk_clock; ctx->lk_hits++;
             *slot = s;
             return ZS_OK;
@@ -83,6 +93,16 @@ static zs_status lk_slot(zs_context* ctx, zs_pyramid* p, const uint8_t* img, int
     zs_status st = zs_pyramid_upload(ctx, p, img, pitch, pitch * h, lru, 1, 1);
     if (st != ZS_OK) return st;
     if ((st = zs_pyramid_build(ctx, p, lru, 1)) != ZS_OK) return st;
+    if (!no_cache) {                            // retained so that a later hash match can be confirmed (a 64-bit hash alone can collide)
+        const size_t bytes = (size_t)w * h;
+        if (ctx->lk_copy_bytes[lru] < bytes) {
+            free(ctx->lk_copy[lru]);
+            ctx->lk_copy[lru] = (uint8_t*)malloc(bytes);
+            ctx->lk_copy_bytes[lru] = ctx->lk_copy[lru] ? bytes : 0;
+        }
+        if (!ctx->lk_copy[lru]) { zs_set_error("out of host memory for the LK frame cache"); return ZS_ERR_CUDA; }
+        for (int y = 0; y < h; ++y) memcpy(ctx->lk_copy[lru] + (size_t)y * w, img + (size_t)y * pitch, w);
+    }
     ctx->lk_hash[lru] = hsh; ctx->lk_stamp[lru] = ++ctx->lk_clock;
     *slot = lru;
     return ZS_OK;
@@ -324,10 +344,10 @@ extern "C" zs_status zs_match_host(zs_context* ctx, const void* q, int nq, const
     *n_out = 0;
     if (nq <= 0 || nt <= 0) return ZS_OK;     // matcher.cpp:55-56,120-123: empty in, empty out
     ZS_REQUIRE(q && t && query_idx && train_idx && distance, "null argument");
-    ZS_REQUIRE(norm == 0 || norm == 1, "norm must be 0 (Hamming) or 1 (L2)");
+    ZS_REQUIRE(norm == 0 || norm == 1 || norm == 2, "norm must be 0 (Hamming), 1 (L2, float rows) or 2 (L2, u8 rows)");
     ZS_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (KNN + ratio) or 1 (BRUTE cross-check)");
     ZS_CUDA(cudaSetDevice(ctx->device));
-    const size_t row = norm == 0 ? 32 : sizeof(float) * (size_t)dim;
+    const size_t row = norm == 0 ? 32 : norm == 2 ? (size_t)dim : sizeof(float) * (size_t)dim;
     if (norm == 0) ZS_REQUIRE(dim == 32 || dim == 256 || dim == 0, "Hamming descriptors are 32-byte rows");
     const size_t o_q = 256, o_t = o_q + al256(row * nq), o_idx = o_t + al256(row * nt), o_dist = o_idx + al256(sizeof(int) * 2 * nq),
                  o_pass = o_dist + al256(sizeof(float) * 2 * nq), total = o_pass + al256(nq);
@@ -345,7 +365,11 @@ extern "C" zs_status zs_match_host(zs_context* ctx, const void* q, int nq, const
         if (mode == 0) st = zs_match_hamming_knn2(ctx, base + o_q, d_nq, 0, base + o_t, d_nt, 0, 1, nq, nt, ratio, d_idx, d_dist, d_pass);
         else st = zs_match_hamming_cross(ctx, base + o_q, d_nq, 0, base + o_t, d_nt, 0, 1, nq, nt, d_idx, d_dist);
     } else {
-        if (mode == 0) st = zs_match_l2_knn2(ctx, (const float*)(base + o_q), d_nq, 0, (const float*)(base + o_t), d_nt, 0, 1, nq, nt, dim, ratio, d_idx, d_dist, d_pass);
+        if (norm == 2) {
+            if (mode == 0) st = zs_match_l2_knn2_u8(ctx, base + o_q, d_nq, base + o_t, d_nt, 1, nq, nt, dim, ratio, d_idx, d_dist, d_pass);
+            else st = zs_match_l2_cross_u8(ctx, base + o_q, d_nq, base + o_t, d_nt, 1, nq, nt, dim, d_idx, d_dist);
+        }
+        else if (mode == 0) st = zs_match_l2_knn2(ctx, (const float*)(base + o_q), d_nq, 0, (const float*)(base + o_t), d_nt, 0, 1, nq, nt, dim, ratio, d_idx, d_dist, d_pass);
         else st = zs_match_l2_cross(ctx, (const float*)(base + o_q), d_nq, 0, (const float*)(base + o_t), d_nt, 0, 1, nq, nt, dim, d_idx, d_dist);
     }
     if (st != ZS_OK) return st;
@@ -358,6 +382,7 @@ extern "C" zs_status zs_match_host(zs_context* ctx, const void* q, int nq, const
     ZS_CUDA(cudaMemcpyAsync(h_dist, d_dist, sizeof(float) * per * nq, cudaMemcpyDeviceToHost, ctx->stream));
     if (mode == 0) ZS_CUDA(cudaMemcpyAsync(h_pass, d_pass, nq, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (norm == 1 && (st = zs_context_async_error(ctx)) != ZS_OK) return st;     // float rows that were not integers in 0..255
     int m = 0;
     for (int i = 0; i < nq; ++i) {
         if (mode == 0) {
@@ -378,7 +403,7 @@ extern "C" zs_status zs_knn_match_host(zs_context* ctx, const void* q, int nq, c
     ZS_REQUIRE(ctx, "null argument");
     ZS_REQUIRE(k == 1 || k == 2, "k must be 1 or 2");
     ZS_REQUIRE(!cross_check || k == 1, "cross check requires k = 1 (cv::BFMatcher asserts the same)");
-    ZS_REQUIRE(norm == 0 || norm == 1, "norm must be 0 (Hamming) or 1 (L2)");
+    ZS_REQUIRE(norm == 0 || norm == 1 || norm == 2, "norm must be 0 (Hamming), 1 (L2, float rows) or 2 (L2, u8 rows)");
     if (nq <= 0) return ZS_OK;
     ZS_REQUIRE(idx && dist, "null argument");
     if (nt <= 0) {
@@ -388,7 +413,7 @@ extern "C" zs_status zs_knn_match_host(zs_context* ctx, const void* q, int nq, c
     ZS_REQUIRE(q && t, "null argument");
     if (norm == 0) ZS_REQUIRE(dim == 32 || dim == 256 || dim == 0, "Hamming descriptors are 32-byte rows");
     ZS_CUDA(cudaSetDevice(ctx->device));
-    const size_t row = norm == 0 ? 32 : sizeof(float) * (size_t)dim;
+    const size_t row = norm == 0 ? 32 : norm == 2 ? (size_t)dim : sizeof(float) * (size_t)dim;
     const size_t o_q = 256, o_t = o_q + al256(row * nq), o_idx = o_t + al256(row * nt), o_dist = o_idx + al256(sizeof(int) * 2 * nq),
                  total = o_dist + al256(sizeof(float) * 2 * nq);
     zs_async_buffer buf(ctx->stream);
@@ -403,12 +428,14 @@ extern "C" zs_status zs_knn_match_host(zs_context* ctx, const void* q, int nq, c
     zs_status st;
     if (cross_check) {
         st = norm == 0 ? zs_match_hamming_cross(ctx, base + o_q, d_nq, 0, base + o_t, d_nt, 0, 1, nq, nt, d_idx, d_dist)
-                       : zs_match_l2_cross(ctx, (const float*)(base + o_q), d_nq, 0, (const float*)(base + o_t), d_nt, 0, 1, nq, nt,
-                                           dim, d_idx, d_dist);
+             : norm == 2 ? zs_match_l2_cross_u8(ctx, base + o_q, d_nq, base + o_t, d_nt, 1, nq, nt, dim, d_idx, d_dist)
+                         : zs_match_l2_cross(ctx, (const float*)(base + o_q), d_nq, 0, (const float*)(base + o_t), d_nt, 0, 1, nq, nt,
+                                             dim, d_idx, d_dist);
     } else {
         st = norm == 0 ? zs_match_hamming_knn2(ctx, base + o_q, d_nq, 0, base + o_t, d_nt, 0, 1, nq, nt, 1.0, d_idx, d_dist, nullptr)
-                       : zs_match_l2_knn2(ctx, (const float*)(base + o_q), d_nq, 0, (const float*)(base + o_t), d_nt, 0, 1, nq, nt,
-                                          dim, 1.0, d_idx, d_dist, nullptr);
+             : norm == 2 ? zs_match_l2_knn2_u8(ctx, base + o_q, d_nq, base + o_t, d_nt, 1, nq, nt, dim, 1.0, d_idx, d_dist, nullptr)
+                         : zs_match_l2_knn2(ctx, (const float*)(base + o_q), d_nq, 0, (const float*)(base + o_t), d_nt, 0, 1, nq, nt,
+                                            dim, 1.0, d_idx, d_dist, nullptr);
     }
     if (st != ZS_OK) return st;
     void* pin;
@@ -418,6 +445,7 @@ extern "C" zs_status zs_knn_match_host(zs_context* ctx, const void* q, int nq, c
     ZS_CUDA(cudaMemcpyAsync(h_idx, d_idx, sizeof(int) * per * nq, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaMemcpyAsync(h_dist, d_dist, sizeof(float) * per * nq, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (norm == 1 && (st = zs_context_async_error(ctx)) != ZS_OK) return st;     // float rows that were not integers in 0..255
     for (int i = 0; i < nq; ++i)
         for (int j = 0; j < k; ++j) { idx[i * k + j] = h_idx[i * per + j]; dist[i * k + j] = h_dist[i * per + j]; }
     return ZS_OK;

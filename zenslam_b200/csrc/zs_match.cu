@@ -125,15 +125,17 @@ __global__ void __launch_bounds__(256) k_top2_merge(const int4* __restrict__ par
 }
 
 // knn2 epilogue: int distances -> float, ratio gate of matcher.cpp:70
+// bad (L2 only, may be null): device flag set when the descriptors were not integers in 0..255 -- every row then reports "no
+// neighbour" instead of a distance computed from wrapped bytes
 __global__ void k_knn2_finish(const int* __restrict__ idx_in, const int* __restrict__ dist_in, const int* __restrict__ nq,
                               int cap_q, double ratio, int l2, int* __restrict__ idx, float* __restrict__ dist,
-                              uint8_t* __restrict__ pass)
+                              uint8_t* __restrict__ pass, const int* __restrict__ bad)
 {
     const int pair = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cap_q) return;
     const size_t o = (size_t)pair * cap_q + i;
-    if (i >= nq[pair]) {
+    if (i >= nq[pair] || (bad && *bad)) {
         idx[2 * o] = idx[2 * o + 1] = -1; dist[2 * o] = dist[2 * o + 1] = 0.f;
         if (pass) pass[o] = 0;
         return;
@@ -149,14 +151,14 @@ __global__ void k_knn2_finish(const int* __restrict__ idx_in, const int* __restr
 // cross-check epilogue: keep (i, fwd[i]) iff bwd[fwd[i]] == i
 __global__ void k_cross_finish(const int* __restrict__ fwd_idx, const int* __restrict__ fwd_dist,
                                const int* __restrict__ bwd_idx, const int* __restrict__ nq, int cap_q, int cap_t, int l2,
-                               int* __restrict__ idx, float* __restrict__ dist)
+                               int* __restrict__ idx, float* __restrict__ dist, const int* __restrict__ bad)
 {
     const int pair = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cap_q) return;
     const size_t o = (size_t)pair * cap_q + i;
     int out = -1; float d = 0.f;
-    if (i < nq[pair]) {
+    if (i < nq[pair] && !(bad && *bad)) {
         const int f = fwd_idx[2 * o];
         if (f >= 0 && bwd_idx[2 * ((size_t)pair * cap_t + f)] == i) {
             out = f;
@@ -216,8 +218,11 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_l2u8_top2(
 
 // float (integer-valued, 0..255) -> u8, flagging anything else; four values per thread (dim is a multiple of 4 and rows
 // are 16-byte aligned whenever the caller's stride is a multiple of 4 floats, which the launcher checks)
+// norms (dim == 128 only, else null): a row is then exactly one warp of this kernel, which also leaves the row's squared
+// norm for the tensor-core kernel's epilogue -- one pass over the floats instead of a conversion and a norm kernel
 __global__ void __launch_bounds__(256) k_f32_to_u8(const float* __restrict__ src, const int* __restrict__ n, size_t src_stride, int cap,
-                                                   int dim, uint8_t* __restrict__ dst, int* __restrict__ bad, int vec)
+                                                   int dim, uint8_t* __restrict__ dst, int* __restrict__ bad, int vec,
+                                                   int* __restrict__ norms)
 {
     const int pair = blockIdx.y;
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -236,6 +241,10 @@ __global__ void __launch_bounds__(256) k_f32_to_u8(const float* __restrict__ src
     }
     if (wrong) atomicExch(bad, 1);
     *(uint32_t*)(dst + (size_t)pair * cap * dim + i) = out;
+    if (norms) {                                   // dim == 128: total is a multiple of 128 values = whole warps get here
+        const int s2 = __reduce_add_sync(0xffffffffu, (int)__dp4a(out, out, 0u));
+        if ((threadIdx.x & 31) == 0) norms[(size_t)pair * cap + i / 128] = s2;
+    }
 }
 
 // Train-side splitting: a block sweeps `chunk` train rows.  Large maps are cut into 2048-row chunks; small problems are
@@ -299,7 +308,7 @@ extern "C" zs_status zs_match_hamming_knn2(zs_context* ctx, const uint8_t* d_q, 
     int* ti = (int*)s; int* td = ti + 2 * (size_t)cap_q * pairs;
     st = hamming_top2(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, cap_t, ti, td, td + 2 * (size_t)cap_q * pairs);
     if (st != ZS_OK) return st;
-    k_knn2_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(ti, td, d_nq, cap_q, ratio, 0, d_idx, d_dist, d_pass);
+    k_knn2_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(ti, td, d_nq, cap_q, ratio, 0, d_idx, d_dist, d_pass, nullptr);
     ZS_LAUNCH_CHECK(ctx);
     return ZS_OK;
 }
@@ -324,50 +333,53 @@ extern "C" zs_status zs_match_hamming_cross(zs_context* ctx, const uint8_t* d_q,
     if (st != ZS_OK) return st;
     st = hamming_top2(ctx, d_t, d_nt, t_stride, d_q, d_nq, q_stride, pairs, cap_t, cap_q, bi, bd, part);
     if (st != ZS_OK) return st;
-    k_cross_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(fi, fd, bi, d_nq, cap_q, cap_t, 0, d_idx, d_dist);
+    k_cross_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(fi, fd, bi, d_nq, cap_q, cap_t, 0, d_idx, d_dist, nullptr);
     ZS_LAUNCH_CHECK(ctx);
     return ZS_OK;
 }
 
-// ---- L2 (integer-valued float descriptors) -----------------------------------------------------------
+// ---- L2 (integer-valued descriptors: cv::SIFT) ---------------------------------------------------------
+// qnorm / tnorm: squared row norms [pairs*cap] when the caller has them already (the f32 -> u8 pass leaves them), else null
 zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, const uint8_t* t8, const int* nt, int pairs,
-                            int cap_q, int cap_t, int dim, int* idx, int* dist, void* part);   // zs_match_l2.cu
+                            int cap_q, int cap_t, int dim, int* idx, int* dist, void* part, const int* qnorm, const int* tnorm);   // zs_match_l2.cu
 size_t zs_l2_tensor_part_ints(int pairs, int cap_q, int cap_t);                                  // ints of `part` scratch
 
+struct l2_operands { const uint8_t* q8; const uint8_t* t8; const int* qnorm; const int* tnorm; int* extra; const int* bad; };
+
+// Float rows -> u8 rows (+ squared norms for 128-d rows) in context scratch.  Nothing here waits for the device: values that
+// are not integers in 0..255 raise ctx->d_async_err[0], which the finish kernels turn into "no neighbour" rows and which
+// zs_context_async_error() / the host entries report as ZS_ERR_UNSUPPORTED.
 static zs_status l2_prepare(zs_context* ctx, const float* d_q, const int* d_nq, size_t q_stride, const float* d_t,
                             const int* d_nt, size_t t_stride, int pairs, int cap_q, int cap_t, int dim, size_t extra_ints,
-                            uint8_t** q8, uint8_t** t8, int** extra)
+                            l2_operands* op)
 {
     ZS_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 128, "dim must be a multiple of 4, at most 128");
     const size_t qb = ((size_t)pairs * cap_q * dim + 255) / 256 * 256, tb = ((size_t)pairs * cap_t * dim + 255) / 256 * 256;
+    const size_t nb = ((size_t)pairs * ((size_t)cap_q + cap_t) * sizeof(int) + 255) / 256 * 256;
     void* s;
-    zs_status st = zs_scratch(ctx, qb + tb + 256 + extra_ints * sizeof(int), &s);
+    zs_status st = zs_scratch(ctx, qb + tb + nb + extra_ints * sizeof(int), &s);
     if (st != ZS_OK) return st;
-    *q8 = (uint8_t*)s; *t8 = *q8 + qb;
-    int* bad = (int*)(*t8 + tb);
-    *extra = bad + 64;
-    ZS_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+    uint8_t* q8 = (uint8_t*)s; uint8_t* t8 = q8 + qb;
+    int* norms = (int*)(t8 + tb);
+    op->q8 = q8; op->t8 = t8; op->extra = (int*)((uint8_t*)norms + nb); op->bad = ctx->d_async_err;
+    const bool fuse = dim == 128;
+    op->qnorm = fuse ? norms : nullptr; op->tnorm = fuse ? norms + (size_t)pairs * cap_q : nullptr;
     const int vq = ((uintptr_t)d_q % 16 == 0 && q_stride % 4 == 0) ? 1 : 0, vt = ((uintptr_t)d_t % 16 == 0 && t_stride % 4 == 0) ? 1 : 0;
-    k_f32_to_u8<<<dim3(zs_div_up(zs_div_up(cap_q * dim, 4), 256), pairs), 256, 0, ctx->stream>>>(d_q, d_nq, q_stride, cap_q, dim, *q8, bad, vq);
+    k_f32_to_u8<<<dim3(zs_div_up(zs_div_up(cap_q * dim, 4), 256), pairs), 256, 0, ctx->stream>>>(d_q, d_nq, q_stride, cap_q, dim, q8, ctx->d_async_err, vq,
+                                                                                                   fuse ? norms : nullptr);
     ZS_LAUNCH_CHECK(ctx);
-    k_f32_to_u8<<<dim3(zs_div_up(zs_div_up(cap_t * dim, 4), 256), pairs), 256, 0, ctx->stream>>>(d_t, d_nt, t_stride, cap_t, dim, *t8, bad, vt);
+    k_f32_to_u8<<<dim3(zs_div_up(zs_div_up(cap_t * dim, 4), 256), pairs), 256, 0, ctx->stream>>>(d_t, d_nt, t_stride, cap_t, dim, t8, ctx->d_async_err, vt,
+                                                                                                   fuse ? norms + (size_t)pairs * cap_q : nullptr);
     ZS_LAUNCH_CHECK(ctx);
-    int h_bad = 0;
-    ZS_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    ZS_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (h_bad) {
-        zs_set_error("L2 matching is exact only for integer-valued descriptors in 0..255 (cv::SIFT); got other values");
-        return ZS_ERR_UNSUPPORTED;
-    }
     return ZS_OK;
 }
 
 static zs_status l2_top2(zs_context* ctx, const uint8_t* q8, const int* nq, const uint8_t* t8, const int* nt, int pairs,
-                         int cap_q, int cap_t, int dim, int* idx, int* dist, void* part)
+                         int cap_q, int cap_t, int dim, int* idx, int* dist, void* part, const int* qnorm, const int* tnorm)
 {
     // 128-dim (SIFT) rows take the tcgen05 path; ZS_L2_NO_TENSOR=1 selects the CUDA-core dp4a kernel instead
     // (used by tools/bench_l2.py and the tests to cross-check the two implementations)
-    if (dim == 128 && !ctx->sw.l2_no_tensor) return zs_l2_tensor_top2(ctx, q8, nq, t8, nt, pairs, cap_q, cap_t, dim, idx, dist, part);
+    if (dim == 128 && !ctx->sw.l2_no_tensor) return zs_l2_tensor_top2(ctx, q8, nq, t8, nt, pairs, cap_q, cap_t, dim, idx, dist, part, qnorm, tnorm);
     const dim3 grid(zs_div_up(cap_q, MATCH_THREADS), pairs);
 #define L2_CASE(NW)                                                                                          \
     case NW:                                                                                                 \
@@ -396,6 +408,40 @@ zs_status zs_l2_cuda_core_top2(zs_context* ctx, const uint8_t* q8, const int* nq
     return ZS_OK;
 }
 
+// the two matchers on prepared operands (u8 rows in device memory, dense [pairs][cap][dim])
+static zs_status l2_knn2_run(zs_context* ctx, const l2_operands& op, const int* d_nq, const int* d_nt, int pairs, int cap_q, int cap_t,
+                             int dim, double ratio, int* d_idx, float* d_dist, uint8_t* d_pass)
+{
+    int* ti = op.extra; int* td = ti + 2 * (size_t)cap_q * pairs;
+    void* part = td + 2 * (size_t)cap_q * pairs;          // 16-byte aligned: every piece before it is a multiple of 16 bytes
+    zs_status st = l2_top2(ctx, op.q8, d_nq, op.t8, d_nt, pairs, cap_q, cap_t, dim, ti, td, part, op.qnorm, op.tnorm);
+    if (st != ZS_OK) return st;
+    k_knn2_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(ti, td, d_nq, cap_q, ratio, 1, d_idx, d_dist, d_pass, op.bad);
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}
+
+static zs_status l2_cross_run(zs_context* ctx, const l2_operands& op, const int* d_nq, const int* d_nt, int pairs, int cap_q, int cap_t,
+                              int dim, int* d_idx, float* d_dist)
+{
+    int* fi = op.extra; int* fd = fi + 2 * (size_t)cap_q * pairs;
+    int* bi = fd + 2 * (size_t)cap_q * pairs; int* bd = bi + 2 * (size_t)cap_t * pairs;
+    void* part = bd + 2 * (size_t)cap_t * pairs;
+    zs_status st = l2_top2(ctx, op.q8, d_nq, op.t8, d_nt, pairs, cap_q, cap_t, dim, fi, fd, part, op.qnorm, op.tnorm);
+    if (st != ZS_OK) return st;
+    st = l2_top2(ctx, op.t8, d_nt, op.q8, d_nq, pairs, cap_t, cap_q, dim, bi, bd, part, op.tnorm, op.qnorm);
+    if (st != ZS_OK) return st;
+    k_cross_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(fi, fd, bi, d_nq, cap_q, cap_t, 1, d_idx, d_dist, op.bad);
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}
+
+static size_t l2_knn2_extra(int pairs, int cap_q, int cap_t) { return 4 * (size_t)cap_q * pairs + zs_l2_tensor_part_ints(pairs, cap_q, cap_t); }
+static size_t l2_cross_extra(int pairs, int cap_q, int cap_t)
+{
+    return 4 * ((size_t)cap_q + cap_t) * pairs + std::max(zs_l2_tensor_part_ints(pairs, cap_q, cap_t), zs_l2_tensor_part_ints(pairs, cap_t, cap_q));
+}
+
 extern "C" zs_status zs_match_l2_knn2(zs_context* ctx, const float* d_q, const int* d_nq, size_t q_stride, const float* d_t,
                                       const int* d_nt, size_t t_stride, int pairs, int cap_q, int cap_t, int dim,
                                       double ratio, int* d_idx, float* d_dist, uint8_t* d_pass)
@@ -403,17 +449,10 @@ extern "C" zs_status zs_match_l2_knn2(zs_context* ctx, const float* d_q, const i
     ZS_REQUIRE(ctx && d_q && d_nq && d_t && d_nt && d_idx && d_dist, "null argument");
     ZS_REQUIRE(pairs >= 0 && cap_q > 0 && cap_t > 0, "bad sizes");
     if (pairs == 0) return ZS_OK;
-    uint8_t *q8, *t8; int* ex;
-    zs_status st = l2_prepare(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, cap_t, dim,
-                              4 * (size_t)cap_q * pairs + zs_l2_tensor_part_ints(pairs, cap_q, cap_t), &q8, &t8, &ex);
+    l2_operands op;
+    zs_status st = l2_prepare(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, cap_t, dim, l2_knn2_extra(pairs, cap_q, cap_t), &op);
     if (st != ZS_OK) return st;
-    int* ti = ex; int* td = ti + 2 * (size_t)cap_q * pairs;
-    void* part = td + 2 * (size_t)cap_q * pairs;          // 16-byte aligned: every piece before it is a multiple of 16 bytes
-    st = l2_top2(ctx, q8, d_nq, t8, d_nt, pairs, cap_q, cap_t, dim, ti, td, part);
-    if (st != ZS_OK) return st;
-    k_knn2_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(ti, td, d_nq, cap_q, ratio, 1, d_idx, d_dist, d_pass);
-    ZS_LAUNCH_CHECK(ctx);
-    return ZS_OK;
+    return l2_knn2_run(ctx, op, d_nq, d_nt, pairs, cap_q, cap_t, dim, ratio, d_idx, d_dist, d_pass);
 }
 
 extern "C" zs_status zs_match_l2_cross(zs_context* ctx, const float* d_q, const int* d_nq, size_t q_stride, const float* d_t,
@@ -423,20 +462,46 @@ extern "C" zs_status zs_match_l2_cross(zs_context* ctx, const float* d_q, const 
     ZS_REQUIRE(ctx && d_q && d_nq && d_t && d_nt && d_idx && d_dist, "null argument");
     ZS_REQUIRE(pairs >= 0 && cap_q > 0 && cap_t > 0, "bad sizes");
     if (pairs == 0) return ZS_OK;
-    uint8_t *q8, *t8; int* ex;
-    zs_status st = l2_prepare(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, cap_t, dim,
-                              4 * ((size_t)cap_q + cap_t) * pairs + std::max(zs_l2_tensor_part_ints(pairs, cap_q, cap_t),
-                                                                             zs_l2_tensor_part_ints(pairs, cap_t, cap_q)),
-                              &q8, &t8, &ex);
+    l2_operands op;
+    zs_status st = l2_prepare(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, cap_t, dim, l2_cross_extra(pairs, cap_q, cap_t), &op);
     if (st != ZS_OK) return st;
-    int* fi = ex; int* fd = fi + 2 * (size_t)cap_q * pairs;
-    int* bi = fd + 2 * (size_t)cap_q * pairs; int* bd = bi + 2 * (size_t)cap_t * pairs;
-    void* part = bd + 2 * (size_t)cap_t * pairs;
-    st = l2_top2(ctx, q8, d_nq, t8, d_nt, pairs, cap_q, cap_t, dim, fi, fd, part);
+    return l2_cross_run(ctx, op, d_nq, d_nt, pairs, cap_q, cap_t, dim, d_idx, d_dist);
+}
+
+// u8 rows straight from the caller (cv::SIFT with descriptorType CV_8U, or float rows narrowed where they were produced): no
+// conversion pass, a quarter of the bytes on the way to the device.  Rows are dense [pairs][cap][dim], 16-byte aligned.
+static zs_status l2_u8_operands(zs_context* ctx, const uint8_t* d_q, const uint8_t* d_t, int dim, size_t extra_ints, l2_operands* op)
+{
+    ZS_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 128, "dim must be a multiple of 4, at most 128");
+    ZS_REQUIRE(((uintptr_t)d_q % 16) == 0 && ((uintptr_t)d_t % 16) == 0, "descriptor arrays must be 16-byte aligned");
+    void* s;
+    zs_status st = zs_scratch(ctx, extra_ints * sizeof(int), &s);
     if (st != ZS_OK) return st;
-    st = l2_top2(ctx, t8, d_nt, q8, d_nq, pairs, cap_t, cap_q, dim, bi, bd, part);
-    if (st != ZS_OK) return st;
-    k_cross_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(fi, fd, bi, d_nq, cap_q, cap_t, 1, d_idx, d_dist);
-    ZS_LAUNCH_CHECK(ctx);
+    op->q8 = d_q; op->t8 = d_t; op->qnorm = op->tnorm = nullptr; op->extra = (int*)s; op->bad = nullptr;
     return ZS_OK;
+}
+
+extern "C" zs_status zs_match_l2_knn2_u8(zs_context* ctx, const uint8_t* d_q, const int* d_nq, const uint8_t* d_t, const int* d_nt,
+                                         int pairs, int cap_q, int cap_t, int dim, double ratio, int* d_idx, float* d_dist,
+                                         uint8_t* d_pass)
+{
+    ZS_REQUIRE(ctx && d_q && d_nq && d_t && d_nt && d_idx && d_dist, "null argument");
+    ZS_REQUIRE(pairs >= 0 && cap_q > 0 && cap_t > 0, "bad sizes");
+    if (pairs == 0) return ZS_OK;
+    l2_operands op;
+    zs_status st = l2_u8_operands(ctx, d_q, d_t, dim, l2_knn2_extra(pairs, cap_q, cap_t), &op);
+    if (st != ZS_OK) return st;
+    return l2_knn2_run(ctx, op, d_nq, d_nt, pairs, cap_q, cap_t, dim, ratio, d_idx, d_dist, d_pass);
+}
+
+extern "C" zs_status zs_match_l2_cross_u8(zs_context* ctx, const uint8_t* d_q, const int* d_nq, const uint8_t* d_t, const int* d_nt,
+                                          int pairs, int cap_q, int cap_t, int dim, int* d_idx, float* d_dist)
+{
+    ZS_REQUIRE(ctx && d_q && d_nq && d_t && d_nt && d_idx && d_dist, "null argument");
+    ZS_REQUIRE(pairs >= 0 && cap_q > 0 && cap_t > 0, "bad sizes");
+    if (pairs == 0) return ZS_OK;
+    l2_operands op;
+    zs_status st = l2_u8_operands(ctx, d_q, d_t, dim, l2_cross_extra(pairs, cap_q, cap_t), &op);
+    if (st != ZS_OK) return st;
+    return l2_cross_run(ctx, op, d_nq, d_nt, pairs, cap_q, cap_t, dim, d_idx, d_dist);
 }

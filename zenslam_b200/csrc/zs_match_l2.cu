@@ -540,7 +540,7 @@ static zs_status l2_make_map(CUtensorMap* m, const uint8_t* base, size_t rows)
 // q8 / t8: [pairs][cap][128] u8 (16-byte aligned); idx / dist: [pairs][cap_q][2] (squared distances as int);
 // part: zs_l2_tensor_part_ints() ints of scratch for the per-split partial top-2
 zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, const uint8_t* t8, const int* nt, int pairs,
-                            int cap_q, int cap_t, int dim, int* idx, int* dist, void* part)
+                            int cap_q, int cap_t, int dim, int* idx, int* dist, void* part, const int* qnorm, const int* tnorm)
 {
     ZS_REQUIRE(dim == L2TC_K, "tensor-core L2 path needs 128-dimensional descriptors");
     ZS_REQUIRE(((uintptr_t)q8 % 16) == 0 && ((uintptr_t)t8 % 16) == 0, "descriptor arrays must be 16-byte aligned");
@@ -559,11 +559,15 @@ zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, c
         b.tpc = zs_div_up(t_tiles, splits); b.splits = zs_div_up(t_tiles, b.tpc);
         b.part = (int4*)part;
         int* norms = (int*)part + 4 * (size_t)pairs * cap_q * t_tiles;           // behind the (worst-case) partial area
-        b.qnorm = norms; b.tnorm = norms + (size_t)pairs * cap_q;
-        k_l2_row_norms<<<zs_div_up(pairs * cap_q, 8), 256, 0, ctx->stream>>>(q8, (size_t)pairs * cap_q, norms);
-        ZS_LAUNCH_CHECK(ctx);
-        k_l2_row_norms<<<zs_div_up(pairs * cap_t, 8), 256, 0, ctx->stream>>>(t8, (size_t)pairs * cap_t, norms + (size_t)pairs * cap_q);
-        ZS_LAUNCH_CHECK(ctx);
+        b.qnorm = qnorm ? qnorm : norms; b.tnorm = tnorm ? tnorm : norms + (size_t)pairs * cap_q;
+        if (!qnorm) {                          // u8 rows from the caller: the f32 -> u8 pass that leaves the norms did not run
+            k_l2_row_norms<<<zs_div_up(pairs * cap_q, 8), 256, 0, ctx->stream>>>(q8, (size_t)pairs * cap_q, norms);
+            ZS_LAUNCH_CHECK(ctx);
+        }
+        if (!tnorm) {
+            k_l2_row_norms<<<zs_div_up(pairs * cap_t, 8), 256, 0, ctx->stream>>>(t8, (size_t)pairs * cap_t, norms + (size_t)pairs * cap_q);
+            ZS_LAUNCH_CHECK(ctx);
+        }
         const size_t smem = 1024 + (size_t)(L2TC_M + L2P_BSTAGES * L2TC_N) * L2TC_K;
         static bool attr_p = false;
         if (!attr_p) {

@@ -419,6 +419,16 @@ extern "C" zs_status zs_tracker_create(zs_context* ctx, const zs_tracker_options
     ZS_REQUIRE(ctx && opt && out, "null argument");
     ZS_REQUIRE(opt->width > 0 && opt->height > 0 && opt->cell_w > 0 && opt->cell_h > 0, "bad geometry");
     ZS_REQUIRE((opt->width / opt->cell_w) * (opt->height / opt->cell_h) > 0, "cells larger than the image");
+    // GRID (not PARALLEL_GRID) sends a free cell where FAST finds nothing through cv::ORB::detect (keypoint_detector_grid.cpp:92-95),
+    // which is not implemented.  That detector has a search area only in cells of at least 63 x 63 px; on its level 0 it finds
+    // nothing FAST(threshold <= 20) has not found, and its level 1 needs a 76-px cell: inside these bounds the batched flow is
+    // exact, outside it is refused (the per-call host entry checks the actual cells instead, zs_host.cu)
+    if (!opt->parallel_grid && opt->cell_w >= 63 && opt->cell_h >= 63 && !(opt->cell_w < 76 && opt->cell_h < 76 && opt->fast_threshold <= 20)) {
+        zs_set_error("GRID with %d x %d px cells and FAST threshold %d can reach the reference's ORB::detect fallback for empty cells "
+                     "(keypoint_detector_grid.cpp:92-95), which is not implemented: use PARALLEL_GRID or cells <= 62 px",
+                     opt->cell_w, opt->cell_h, opt->fast_threshold);
+        return ZS_ERR_UNSUPPORTED;
+    }
     ZS_REQUIRE(opt->sequences >= 0 && opt->sequences <= 4096, "sequences outside 0..4096");
     ZS_CUDA(cudaSetDevice(ctx->device));
     zs_tracker* t = (zs_tracker*)calloc(1, sizeof(zs_tracker));

@@ -116,3 +116,50 @@ def match_keypoints3d(ctx: Context, landmark_index, landmark_xyz, landmark_desc,
     check(lib().zs_match_keypoints3d_host(ctx._h, p(lm_i), p(lm_x), p(lm_d), len(lm_i), p(k_i), p(k_xy), p(k_d), len(kps), p(Rm), p(tv), p(P),
                                           float(radius), float(threshold), w, h, float(frustum_margin), p(o_l), p(o_k), p(o_e), C.byref(n)))
     return [DMatch(int(o_l[i]), int(o_k[i]), float(o_e[i])) for i in range(n.value)]
+
+
+def _essential_as_the_reference_reads_it(essential) -> np.ndarray:
+    """utils::match_temporal reads the CV_64F matrix cv::findEssentialMat returns with e.at<float>(i, j)
+    (matching_utils.cpp:519-528): element (i, j) is the 32-bit float found at byte offset 24 i + 4 j of the double buffer.
+    Reproduced as written -- a drop-in must gate on the same numbers."""
+    e64 = np.ascontiguousarray(essential, np.float64).reshape(3, 3)
+    return np.frombuffer(e64.tobytes(), np.float32).reshape(3, 6)[:, :3].astype(np.float64)
+
+
+def match_temporal(ctx: Context, keypoints_map_0: dict, keypoints_map_1: dict, camera_matrix, threshold: float,
+                   find_essential_mat) -> list:
+    """utils::match_temporal (zenslam_core/source/matching/matching_utils.cpp:441-563; SURVEY 8 a9): the keypoints of either
+    map whose index the other map lacks, in key order; nothing when either side has fewer than five; cross-checked 1-NN
+    (cv::BFMatcher(NORM_HAMMING, true).match) on the device; then the caller's cv::findEssentialMat(points_0, points_1,
+    camera_matrix, RANSAC, 0.99, threshold, mask) -- a randomised CPU algorithm, out of scope like the other RANSAC gates --
+    passed in as `find_essential_mat(points_0, points_1) -> (E 3x3 float64, mask)`; a match survives when its mask is set,
+    pt_1^T K^-T E K^-1 pt_0 <= threshold and its descriptor distance <= 5.
+    -> [DMatch(keypoint index in map 0, keypoint index in map 1, descriptor distance)]"""
+    un_0 = [kp for _, kp in sorted(keypoints_map_0.items()) if kp.index not in keypoints_map_1]
+    un_1 = [kp for _, kp in sorted(keypoints_map_1.items()) if kp.index not in keypoints_map_0]
+    if len(un_0) < 5 or len(un_1) < 5:
+        return []
+    q = np.ascontiguousarray(np.stack([kp.descriptor for kp in un_0]), np.uint8)
+    t = np.ascontiguousarray(np.stack([kp.descriptor for kp in un_1]), np.uint8)
+    idx = np.empty(len(q), np.int32); dist = np.empty(len(q), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(lib().zs_knn_match_host(ctx._h, p(q), len(q), p(t), len(t), 32, 0, 1, 1, p(idx), p(dist)))
+    rows = [(i, int(idx[i]), float(dist[i])) for i in range(len(q)) if idx[i] >= 0]
+    if not rows:
+        return []
+    points_0 = np.array([un_0[a].pt for a, _, _ in rows], np.float32)
+    points_1 = np.array([un_1[b].pt for _, b, _ in rows], np.float32)
+    essential, mask = find_essential_mat(points_0, points_1)
+    E = _essential_as_the_reference_reads_it(essential)
+    k_inv = np.linalg.inv(np.asarray(camera_matrix, np.float64).reshape(3, 3))
+    out = []
+    for (a, b, d), m in zip(rows, np.asarray(mask).ravel()):          # std::views::zip stops at the shorter range
+        if not m:
+            continue
+        pt_0 = np.array([np.float64(np.float32(un_0[a].pt[0])), np.float64(np.float32(un_0[a].pt[1])), 1.0])
+        pt_1 = np.array([np.float64(np.float32(un_1[b].pt[0])), np.float64(np.float32(un_1[b].pt[1])), 1.0])
+        error = float((((pt_1 @ k_inv.T) @ E) @ k_inv) @ pt_0)
+        if error > threshold or d > 5:
+            continue
+        out.append(DMatch(un_0[a].index, un_1[b].index, d))
+    return out

@@ -85,6 +85,11 @@ class Context:
     def synchronize(self):
         check(lib().zs_context_synchronize(self._h))
 
+    def async_error(self):
+        """waits for the stream and raises if a kernel of a stream-asynchronous entry rejected its DATA (zs_match_l2_* on
+        descriptors that are not integers in 0..255)"""
+        check(lib().zs_context_async_error(self._h))
+
     @property
     def launches(self) -> int:
         return int(lib().zs_context_launch_count(self._h))
@@ -312,13 +317,18 @@ def match_hamming_cross(ctx: Context, q, nq, t, nt):
 
 
 def match_l2_knn2(ctx: Context, q, nq, t, nt, ratio=0.8):
-    """q (pairs, cap_q, dim) f32 integer-valued"""
+    """q (pairs, cap_q, dim) f32 integer-valued, or u8 (cv::SIFT with descriptorType CV_8U).  Stream-asynchronous: float rows
+    that are not integers in 0..255 come back as all -1 and make ctx.async_error() raise."""
     torch = _torch()
     pairs, cap_q, dim = q.shape
     cap_t = t.shape[1]
     idx = ctx.empty((pairs, cap_q, 2), torch.int32)
     dist = ctx.empty((pairs, cap_q, 2), torch.float32)
     ps = ctx.empty((pairs, cap_q), torch.uint8)
+    if q.dtype == torch.uint8:
+        check(lib().zs_match_l2_knn2_u8(ctx._h, _ptr(q), _ptr(nq), _ptr(t), _ptr(nt), pairs, cap_q, cap_t, dim, float(ratio),
+                                        _ptr(idx), _ptr(dist), _ptr(ps)))
+        return idx, dist, ps
     check(lib().zs_match_l2_knn2(ctx._h, _ptr(q), _ptr(nq), cap_q * dim, _ptr(t), _ptr(nt), cap_t * dim, pairs,
                                  cap_q, cap_t, dim, float(ratio), _ptr(idx), _ptr(dist), _ptr(ps)))
     return idx, dist, ps
@@ -330,6 +340,9 @@ def match_l2_cross(ctx: Context, q, nq, t, nt):
     cap_t = t.shape[1]
     idx = ctx.empty((pairs, cap_q), torch.int32)
     dist = ctx.empty((pairs, cap_q), torch.float32)
+    if q.dtype == torch.uint8:
+        check(lib().zs_match_l2_cross_u8(ctx._h, _ptr(q), _ptr(nq), _ptr(t), _ptr(nt), pairs, cap_q, cap_t, dim, _ptr(idx), _ptr(dist)))
+        return idx, dist
     check(lib().zs_match_l2_cross(ctx._h, _ptr(q), _ptr(nq), cap_q * dim, _ptr(t), _ptr(nt), cap_t * dim, pairs,
                                   cap_q, cap_t, dim, _ptr(idx), _ptr(dist)))
     return idx, dist
