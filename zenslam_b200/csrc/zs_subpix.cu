@@ -127,6 +127,196 @@ __global__ void __launch_bounds__(SUBPIX_WARPS * 32) k_corner_subpix(subpix_args
     if (lane == 0) a.xy[(size_t)img * a.cap + i] = make_float2(cix, ciy);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// v2: six points per warp.  The serial part of the algorithm -- 121 dependent double additions per sum, five sums per
+// point and iteration -- is what bounds v1 (one point per warp: five busy lanes, a latency-bound chain; ncu: 41 % issue
+// slots used, 13.5 resident warps per SM).  Here lane 5 g + s carries sum s of point slot g (g = 0..5), so the chain phase
+// advances thirty sums per instruction, and everything that is order-free is spread over all 32 lanes:
+//   * the getRectSubPix patch: inside the image the CPU's row recurrence has no carried dependency -- prev_j is a function
+//     of t_{j-1} alone -- so every patch pixel is computed on its own from four image pixels (same operations, same
+//     roundings);
+//   * the gradient products (gxx, gxy, gyy), two window rows of all six points at a time, parked in shared memory; the
+//     chain lanes read them back in raster order, lanes 3 and 4 forming gxx px + gxy py / gxy px + gyy py as v1 does.
+// A point slot that has converged takes the warp's next point at the next iteration (warp-local queue over a contiguous
+// range of (image, corner) items), so lanes do not idle behind the slowest of six.  Results are bit-identical to v1.
+// ------------------------------------------------------------------------------------------------------
+#define SPX_G 6
+#define SPX_ROWS 2                              // window rows of terms parked per chunk
+
+// exact u8 -> f32 on the ALU / FMA pipes (I2F issues on the quarter-rate XU pipe): 2^23 + v is exactly representable
+__device__ __forceinline__ float spx_u8f(unsigned v) { return __fsub_rn(__uint_as_float(0x4b000000u | v), 8388608.f); }
+
+__device__ __forceinline__ int spx_div(int e, int rcp) { return (int)(((unsigned)e * (unsigned)rcp) >> 16); }   // e / d for e < 1024, d <= 32, rcp = 65536 / d + 1
+
+__global__ void __launch_bounds__(SUBPIX_WARPS * 32) k_corner_subpix_v2(subpix_args a, int total_items, int items_per_warp)
+{
+    extern __shared__ __align__(16) uint8_t spx_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = a.v.w[0], h = a.v.h[0], pitch = a.v.pitch[0];
+    const int ww = 2 * a.win_w + 1, wh = 2 * a.win_h + 1, pw = ww + 2, ph = wh + 2, npatch = pw * ph;
+    const int chunk = SPX_ROWS * ww;                                        // terms per point and chunk
+    const size_t warp_bytes = (size_t)SPX_G * (3 * chunk * sizeof(double) + ((npatch * sizeof(float) + 7) & ~(size_t)7));
+    double* s_mask = (double*)spx_smem;                                     // [wh * ww]: (double)(ey[r] * ex[j]), shared by the CTA
+    const int mask_doubles = (ww * wh + 1) & ~1;
+    double* s_term = (double*)(spx_smem + mask_doubles * sizeof(double) + warp * warp_bytes);   // [G][3][chunk]
+    float* s_sub = (float*)(s_term + SPX_G * 3 * chunk);                    // [G][patch_stride]
+    const int patch_stride = (int)(((npatch * sizeof(float) + 7) & ~(size_t)7) / sizeof(float));
+    const int rcp_pw = 65536 / pw + 1, rcp_ww = 65536 / ww + 1;
+    const int g = lane / 5, s = lane - 5 * g;                               // lanes 30, 31: g = 6, helpers of the 32-wide phases only
+    const int leader = g < SPX_G ? 5 * g : 0;
+    const uint8_t* base = a.v.img[0] + (size_t)a.v.pad_y * pitch + a.v.pad_x;
+
+    for (int e = threadIdx.x; e < ww * wh; e += SUBPIX_WARPS * 32) {
+        const int r = spx_div(e, rcp_ww), j = e - r * ww;
+        s_mask[e] = (double)__fmul_rn(a.ey[r], a.ex[j]);
+    }
+    __syncthreads();
+
+    int next = (blockIdx.x * SUBPIX_WARPS + warp) * items_per_warp;
+    const int end = min(next + items_per_warp, total_items);
+    bool active = false;
+    int item = 0, iter = 0, slot = 0;
+    float cix = 0.f, ciy = 0.f, c0x = 0.f, c0y = 0.f;
+
+    for (;;) {
+        // ---- refill idle point slots from the warp's range (an item beyond its image's corner count is skipped)
+        for (int tries = 0; tries < 3; ++tries) {
+            const unsigned idle = __ballot_sync(0xffffffffu, !active && s == 0 && g < SPX_G);
+            if (!idle || next >= end) break;
+            const int mine = next + __popc(idle & ((1u << lane) - 1));
+            const int id = __shfl_sync(0xffffffffu, mine, leader);
+            next += __popc(idle);
+            if (!active && g < SPX_G && id < end) {
+                const int img = id / a.cap, i = id - img * a.cap;
+                if (i < min(a.count[img], a.cap)) {
+                    const float2 c = a.xy[id];
+                    item = id; slot = zs_slot(a.first, img, a.v.slots); cix = c0x = c.x; ciy = c0y = c.y; iter = 0; active = true;
+                }
+            }
+        }
+        const unsigned act = __ballot_sync(0xffffffffu, active && s == 0);        // bit 5 g = point slot g is iterating
+        if (!act) {
+            if (next >= end) break;                                              // the range is exhausted too
+            continue;                                                            // only skipped items so far: keep refilling
+        }
+
+        // ---- patches (getRectSubPix_8u32f), one point slot after the other, 32 lanes per patch
+        for (int gg = 0; gg < SPX_G; ++gg) {
+            if (!(act >> (5 * gg) & 1)) continue;
+            const float px = __shfl_sync(0xffffffffu, cix, 5 * gg), py = __shfl_sync(0xffffffffu, ciy, 5 * gg);
+            const uint8_t* src = base + (size_t)__shfl_sync(0xffffffffu, slot, 5 * gg) * a.v.slot_stride[0];
+            float* sub = s_sub + gg * patch_stride;
+            const float centerx = __fsub_rn(px, __fmul_rn((float)(pw - 1), 0.5f)), centery = __fsub_rn(py, __fmul_rn((float)(ph - 1), 0.5f));
+            const int ipx = __float2int_rd(centerx), ipy = __float2int_rd(centery);
+            if (0 <= ipx && ipx + pw < w && 0 <= ipy && ipy + ph < h) {
+                float fa = __fsub_rn(centerx, (float)ipx);
+                const float fb = __fsub_rn(centery, (float)ipy);
+                fa = fmaxf(fa, 0.0001f);
+                const float a12 = __fmul_rn(fa, __fsub_rn(1.f, fb)), a22 = __fmul_rn(fa, fb), b1 = __fsub_rn(1.f, fb), b2 = fb;
+                const double sc = (1. - (double)fa) / (double)fa;
+                const uint8_t* org = src + (ptrdiff_t)ipy * pitch + ipx;
+                for (int e = lane; e < npatch; e += 32) {
+                    const int r = spx_div(e, rcp_pw), j = e - r * pw;
+                    const uint8_t* p = org + (r * pitch + j);
+                    const float p0 = spx_u8f(p[0]), p1 = spx_u8f(p[pitch]);
+                    const float t = __fadd_rn(__fmul_rn(a12, spx_u8f(p[1])), __fmul_rn(a22, spx_u8f(p[1 + pitch])));
+                    float prev;
+                    if (j == 0) prev = __fmul_rn(__fsub_rn(1.f, fa), __fadd_rn(__fmul_rn(b1, p0), __fmul_rn(b2, p1)));
+                    else prev = (float)((double)__fadd_rn(__fmul_rn(a12, p0), __fmul_rn(a22, p1)) * sc);
+                    sub[e] = __fadd_rn(prev, t);
+                }
+            } else {
+                const float fa = __fsub_rn(centerx, (float)ipx), fb = __fsub_rn(centery, (float)ipy);
+                const float na = __fsub_rn(1.f, fa), nb = __fsub_rn(1.f, fb);
+                const float a11 = __fmul_rn(na, nb), a12 = __fmul_rn(fa, nb), a21 = __fmul_rn(na, fb), a22 = __fmul_rn(fa, fb);
+                for (int e = lane; e < npatch; e += 32) {
+                    const int r = spx_div(e, rcp_pw), j = e - r * pw;
+                    int y0 = ipy + r, y1 = y0 + 1, x0 = ipx + j, x1 = x0 + 1;
+                    y0 = min(max(y0, 0), h - 1); y1 = min(max(y1, 0), h - 1);
+                    const bool xin = x0 >= 0 && x1 <= w - 1;
+                    x0 = min(max(x0, 0), w - 1); x1 = min(max(x1, 0), w - 1);
+                    const uint8_t* r0 = src + (size_t)y0 * pitch; const uint8_t* r1 = src + (size_t)y1 * pitch;
+                    float val;
+                    if (xin)
+                        val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn((float)r0[x0], a11), __fmul_rn((float)r0[x1], a12)),
+                                                  __fmul_rn((float)r1[x0], a21)), __fmul_rn((float)r1[x1], a22));
+                    else
+                        val = __fadd_rn(__fmul_rn((float)r0[x0], nb), __fmul_rn((float)r1[x0], fb));
+                    sub[e] = val;
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- normal equations: SPX_ROWS window rows at a time -- products by all lanes, then thirty ordered sums in step
+        double acc = 0;
+        const double* tA = s_term + ((g < SPX_G ? g : 0) * 3 + (s < 3 ? s : s - 3)) * chunk;      // s = 3: gxx, s = 4: gxy
+        const double* tB = s_term + ((g < SPX_G ? g : 0) * 3 + (s < 3 ? s : s - 2)) * chunk;      // s = 3: gxy, s = 4: gyy
+        for (int r0 = 0; r0 < wh; r0 += SPX_ROWS) {
+            const int rows = min(SPX_ROWS, wh - r0), n = rows * ww;
+            const int rcp_n = 65536 / n + 1;
+            for (int idx = lane; idx < SPX_G * n; idx += 32) {
+                const int gg = spx_div(idx, rcp_n), e = idx - gg * n;
+                if (!(act >> (5 * gg) & 1)) continue;
+                const int rr = spx_div(e, rcp_ww), j = e - rr * ww, r = r0 + rr;
+                const float* sp = s_sub + gg * patch_stride + (r + 1) * pw + 1 + j;
+                const double m = s_mask[r * ww + j];
+                const double tgx = (double)__fsub_rn(sp[1], sp[-1]);
+                const double tgy = (double)__fsub_rn(sp[pw], sp[-pw]);
+                double* tm = s_term + gg * 3 * chunk + e;
+                tm[0] = __dmul_rn(__dmul_rn(tgx, tgx), m);
+                tm[chunk] = __dmul_rn(__dmul_rn(tgx, tgy), m);
+                tm[2 * chunk] = __dmul_rn(__dmul_rn(tgy, tgy), m);
+            }
+            __syncwarp();
+            if (active && g < SPX_G) {
+                int e = 0;
+                for (int rr = 0; rr < rows; ++rr) {
+                    const double py = (double)(r0 + rr - a.win_h);
+                    double px = -(double)a.win_w;                               // j - win_w as a running double: small integers, exact
+                    for (int j = 0; j < ww; ++j, ++e) {
+                        const double va = tA[e];
+                        double v = va;
+                        if (s >= 3) v = __dadd_rn(__dmul_rn(va, px), __dmul_rn(tB[e], py));
+                        acc = __dadd_rn(acc, v);
+                        px = __dadd_rn(px, 1.0);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- 2x2 solve and update, every lane of a point slot on the same numbers
+        const double sa = __shfl_sync(0xffffffffu, acc, leader), sb = __shfl_sync(0xffffffffu, acc, leader + 1),
+                     scc = __shfl_sync(0xffffffffu, acc, leader + 2), bb1 = __shfl_sync(0xffffffffu, acc, leader + 3),
+                     bb2 = __shfl_sync(0xffffffffu, acc, leader + 4);
+        if (active && g < SPX_G) {
+            bool done = false;
+            const double det = __dsub_rn(__dmul_rn(sa, scc), __dmul_rn(sb, sb));
+            if (fabs(det) <= 2.220446049250313e-16 * 2.220446049250313e-16) done = true;
+            else {
+                const double scale = __ddiv_rn(1.0, det);
+                const float nx = (float)__dsub_rn(__dadd_rn((double)cix, __dmul_rn(__dmul_rn(scc, scale), bb1)), __dmul_rn(__dmul_rn(sb, scale), bb2));
+                const float ny = (float)__dadd_rn(__dsub_rn((double)ciy, __dmul_rn(__dmul_rn(sb, scale), bb1)), __dmul_rn(__dmul_rn(sa, scale), bb2));
+                const float ex = __fsub_rn(nx, cix), ey = __fsub_rn(ny, ciy);
+                const double err = (double)__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                // an update that would leave the image is dropped (cv2 4.13 behaviour, pinned by the oracle fixtures)
+                if (nx < 0.f || nx >= (float)w || ny < 0.f || ny >= (float)h) done = true;
+                else {
+                    cix = nx; ciy = ny;
+                    if (!(++iter < a.max_iters && err > a.eps2)) done = true;
+                }
+            }
+            if (done) {
+                // too far from the start = poor convergence: keep the input
+                if (fabsf(__fsub_rn(cix, c0x)) > (float)a.win_w || fabsf(__fsub_rn(ciy, c0y)) > (float)a.win_h) { cix = c0x; ciy = c0y; }
+                if (s == 0) a.xy[item] = make_float2(cix, ciy);
+                active = false;
+            }
+        }
+    }
+}
+
 extern "C" zs_status zs_corner_subpix(zs_context* ctx, const zs_pyramid* p, int first, int count, float* d_xy, const int* d_count,
                                       int cap, int win_w, int win_h, int max_iters, double epsilon)
 {
@@ -142,7 +332,24 @@ extern "C" zs_status zs_corner_subpix(zs_context* ctx, const zs_pyramid* p, int 
     // OpenCV: float y = (float)(i - win)/win; float vy = std::exp(-y*y)  (expf on the host)
     for (int i = 0; i < 2 * win_w + 1; ++i) { const float x = (float)(i - win_w) / win_w; a.ex[i] = expf(-x * x); }
     for (int i = 0; i < 2 * win_h + 1; ++i) { const float y = (float)(i - win_h) / win_h; a.ey[i] = expf(-y * y); }
-    k_corner_subpix<<<dim3(zs_div_up(cap, SUBPIX_WARPS), count), SUBPIX_WARPS * 32, 0, ctx->stream>>>(a);
+    if (ctx->sw.subpix_v1) {
+        k_corner_subpix<<<dim3(zs_div_up(cap, SUBPIX_WARPS), count), SUBPIX_WARPS * 32, 0, ctx->stream>>>(a);
+        ZS_LAUNCH_CHECK(ctx);
+        return ZS_OK;
+    }
+    // six points per warp; a warp's range of (image, corner) items is sized so that one wave of resident warps covers the call
+    const long long total = (long long)count * cap;
+    ZS_REQUIRE(total < (1LL << 31), "count * cap too large");
+    const int ww = 2 * win_w + 1, wh = 2 * win_h + 1, npatch = (ww + 2) * (wh + 2);
+    const size_t warp_bytes = (size_t)SPX_G * (3 * SPX_ROWS * ww * sizeof(double) + ((npatch * sizeof(float) + 7) & ~(size_t)7));
+    const size_t smem = warp_bytes * SUBPIX_WARPS + (size_t)((ww * wh + 1) & ~1) * sizeof(double);
+    const int resident_warps = ctx->sm_count * 24;
+    int ipw = (int)((total + resident_warps - 1) / resident_warps);
+    ipw = (ipw + SPX_G - 1) / SPX_G * SPX_G;
+    ipw = ipw < SPX_G ? SPX_G : ipw;
+    const int warps = (int)((total + ipw - 1) / ipw);
+    if (smem > 48 * 1024) ZS_CUDA(cudaFuncSetAttribute(k_corner_subpix_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_corner_subpix_v2<<<zs_div_up(warps, SUBPIX_WARPS), SUBPIX_WARPS * 32, smem, ctx->stream>>>(a, (int)total, ipw);
     ZS_LAUNCH_CHECK(ctx);
     return ZS_OK;
 }
