@@ -466,7 +466,11 @@ def measure_frontend(args, rank, world, local_rank, ctx, light=False):
                        "fb_keep_fraction": keep_frac, "distinct_batches": nb,
                        "l2": "inputs larger than L2: one batch's pyramids are %.0f MB, %d distinct batches cycled"
                              % (2 * B * 3.2 * (W * H) / (752.0 * 480.0), nb),
-                       "parallelism": "independent sequences per GPU, no collective"},
+                       "parallelism": "independent sequences per GPU, no collective",
+                       "note": "the contract's metric: every cell of every frame is detected again and every keypoint goes through all "
+                               "four forward/backward KLT jobs (SURVEY C2) -- more work per frame than the reference's stateful flow "
+                               "(occupancy-aware detection, stereo tracks only of what the other camera lacks), which is measured as "
+                               "extra.tracker; the per-frame seam calls the reference's slam_thread would make are extra.seams_e2e"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": fe.h2d_bytes, "d2h_bytes_per_step": fe.d2h_bytes,
                     "ms_per_step": e2e_ms / K, "call": "zs_frontend_submit_host/zs_frontend_wait (2 batches in flight)",
                     "blocking_call_value": e2e_sync_value},
