@@ -29,6 +29,8 @@ struct klt_args {
     float eps2_lo, eps2_hi;  // float band around eps2 inside which the double comparison is evaluated
     uint8_t* status; float* err;
     int fb; double fb_thr; uint8_t* keep;
+    // persistent launch of the tiled kernel: CTAs take (job, point) items from this counter until n_items are gone
+    int* work; int n_items, n_jobs_listed;
 };
 
 __device__ __forceinline__ long long warp_sum_ll(long long v)
@@ -662,35 +664,22 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
 // grid: (cap, jobs); block = one warp per window tile; dynamic smem = tiles * KLT4_WARP_BYTES
 // passes: 0 = forward (one or two targets), 1 = backward of target 0, 2 = backward of target 1 (fb only); one
 // inlined instance of the tracker serves all passes (keeps the code inside the instruction cache).
-template <int WW, int WH, int MINB>
-__global__ void __launch_bounds__(klt4_cfg<WW, WH>::NT * 32, MINB) k_klt_track_v4(klt_args a)
+template <int WW, int WH>
+__device__ __forceinline__ void klt4_item(const klt_args& a, int job, int i, int warp, int lane, uint8_t* sJ, uint8_t* sD, uint32_t bar,
+                                          uint32_t& parity, long long* s_red, int& phase)
 {
     typedef klt4_cfg<WW, WH> cfg;
-    extern __shared__ __align__(128) uint8_t smem3[];
-    __shared__ long long s_red[cfg::NT > 1 ? 2 * cfg::NT * 5 : 1];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int job = a.job_list ? a.job_list[blockIdx.y] : blockIdx.y;
     const int slot_src = a.prev_slot[job];
     if (slot_src < 0) return;                                  // job folded into another job's second target
-    const int i = blockIdx.x;
     const int in_row = a.pts_row ? a.pts_row[job] : job;
     if (i >= min(a.count[in_row], a.cap)) return;
-    uint8_t* sJ = smem3 + (size_t)warp * KLT4_WARP_BYTES;
-    uint8_t* sD = sJ + KLT4_SJ_BYTES;
-    const uint32_t bar = smem_u32(sD + KLT4_SD_BYTES);
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    uint32_t parity = 0;
-    int phase = 0;
     // Per-warp bookkeeping lives in the 128-byte scratch line behind the barrier (warp-uniform values, written by
     // every lane with the same data, read back as broadcasts): it would otherwise sit in registers across the
     // whole inlined tracker and push the kernel past 128 registers (4 CTAs per SM).
     //   w[4] slot_src  w[5] slot_t0  w[6] slot_t1  w[7] ntgt  w[8..9] p0  w[10..12] f0  w[13..15] f1  w[16] job1
     volatile int* w = (volatile int*)(sD + KLT4_SD_BYTES);
     volatile float* wf = (volatile float*)w;
+    __syncwarp();
     {
         const int job1 = a.out_job2 ? a.out_job2[job] : -1;
         w[4] = slot_src; w[5] = a.next_slot[job]; w[6] = job1 >= 0 ? a.next_slot2[job] : -1; w[7] = job1 >= 0 ? 2 : 1; w[16] = job1;
@@ -735,6 +724,54 @@ __global__ void __launch_bounds__(klt4_cfg<WW, WH>::NT * 32, MINB) k_klt_track_v
             const double nrm = sqrt((double)dx * (double)dx + (double)dy * (double)dy);
             a.keep[pass == 1 ? o0 : o1] = (uint8_t)(r0.status && nrm < a.fb_thr);
         }
+    }
+}
+
+// block = one warp per window tile; dynamic smem = tiles * KLT4_WARP_BYTES
+// passes: 0 = forward (one or two targets), 1 = backward of target 0, 2 = backward of target 1 (fb only); one
+// inlined instance of the tracker serves all passes (keeps the code inside the instruction cache).
+// Launch forms: grid (cap, jobs) with one (point, job) item per CTA (a.work == nullptr), or a PERSISTENT grid of
+// sm_count x MINB CTAs that take items from an atomic counter, point index fastest (neighbouring CTAs then work on the same
+// image pair): no CTA relaunch gap between the ~160 items a CTA slot serves per 128-frame batch, no empty CTAs for the
+// points beyond an image's corner count.
+template <int WW, int WH, int MINB>
+__global__ void __launch_bounds__(klt4_cfg<WW, WH>::NT * 32, MINB) k_klt_track_v4(klt_args a)
+{
+    typedef klt4_cfg<WW, WH> cfg;
+    extern __shared__ __align__(128) uint8_t smem3[];
+    __shared__ long long s_red[cfg::NT > 1 ? 2 * cfg::NT * 5 : 1];
+    __shared__ int s_item;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* sJ = smem3 + (size_t)warp * KLT4_WARP_BYTES;
+    uint8_t* sD = sJ + KLT4_SJ_BYTES;
+    const uint32_t bar = smem_u32(sD + KLT4_SD_BYTES);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t parity = 0;
+    int phase = 0;
+    const bool persistent = a.work != nullptr;
+    for (;;) {                                                 // ONE inlined instance of the tracker serves both launch forms
+        int jl = blockIdx.y, i = blockIdx.x;
+        if (persistent) {
+            int item;
+            if (cfg::NT == 1) {
+                item = 0;
+                if (lane == 0) item = atomicAdd(a.work, 1);
+                item = __shfl_sync(0xffffffffu, item, 0);
+            } else {
+                __syncthreads();                               // every warp has read the previous item
+                if (threadIdx.x == 0) s_item = atomicAdd(a.work, 1);
+                __syncthreads();
+                item = s_item;
+            }
+            if (item >= a.n_items) break;
+            jl = item / a.cap; i = item - jl * a.cap;
+        }
+        klt4_item<WW, WH>(a, a.job_list ? a.job_list[jl] : jl, i, warp, lane, sJ, sD, bar, parity, s_red, phase);
+        if (!persistent) break;
     }
 }
 
@@ -814,10 +851,24 @@ zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_
     if (zs_klt_tiled_window(ctx, p, a.win_w, a.win_h)) {
         // with a job list only the jobs that still own work get blocks (folded jobs would launch cap empty CTAs each)
         if (d_job_list && n_list > 0) a.job_list = d_job_list;
-        const dim3 grid(cap, a.job_list ? n_list : jobs);
+        const int listed = a.job_list ? n_list : jobs;
+        const long long items = (long long)listed * cap;
+        a.work = nullptr; a.n_items = 0; a.n_jobs_listed = listed;
+        // persistent form when there are many waves of CTAs to run (ZS_KLT_NO_PERSIST: always one CTA per item).  Measured at
+        // C2, 128 frames per batch (160 items per CTA slot): KLT 12.01 -> 11.85 ms; at 1 - 16 frames per batch no difference,
+        // so small launches keep the plain grid and skip the counter reset
+        const bool persist = !ctx->sw.klt_no_persist && items < (1LL << 31) && items > 4LL * ctx->sm_count * 24;
+        if (persist) {
+            a.work = ctx->d_async_err + 32;                    // a device int of the context, zeroed in stream order before the launch
+            a.n_items = (int)items;
+            ZS_CUDA(cudaMemsetAsync(a.work, 0, sizeof(int), ctx->stream));
+        }
 #define KLT4_LAUNCH(W_, H_, MB_)                                                                                               \
         do {                                                                                                                   \
             const size_t sm = (size_t)klt4_cfg<W_, H_>::NT * KLT4_WARP_BYTES;                                                  \
+            const long long resident = (long long)ctx->sm_count * MB_;                                                         \
+            const dim3 grid = (persist && items > resident) ? dim3((unsigned)resident, 1) : dim3(cap, listed);                 \
+            if (!(persist && items > resident)) a.work = nullptr;                                                              \
             k_klt_track_v4<W_, H_, MB_><<<grid, klt4_cfg<W_, H_>::NT * 32, sm, ctx->stream>>>(a);                              \
         } while (0)
         if (a.win_w == 31) KLT4_LAUNCH(31, 31, 24);

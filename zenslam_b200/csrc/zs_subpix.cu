@@ -155,11 +155,14 @@ __global__ void __launch_bounds__(SUBPIX_WARPS * 32) k_corner_subpix_v2(subpix_a
     const int w = a.v.w[0], h = a.v.h[0], pitch = a.v.pitch[0];
     const int ww = 2 * a.win_w + 1, wh = 2 * a.win_h + 1, pw = ww + 2, ph = wh + 2, npatch = pw * ph;
     const int chunk = SPX_ROWS * ww;                                        // terms per point and chunk
-    const size_t warp_bytes = (size_t)SPX_G * (3 * chunk * sizeof(double) + ((npatch * sizeof(float) + 7) & ~(size_t)7));
+    const size_t warp_bytes = (size_t)SPX_G * (5 * chunk * sizeof(double) + ((npatch * sizeof(float) + 7) & ~(size_t)7));
     double* s_mask = (double*)spx_smem;                                     // [wh * ww]: (double)(ey[r] * ex[j]), shared by the CTA
     const int mask_doubles = (ww * wh + 1) & ~1;
-    double* s_term = (double*)(spx_smem + mask_doubles * sizeof(double) + warp * warp_bytes);   // [G][3][chunk]
-    float* s_sub = (float*)(s_term + SPX_G * 3 * chunk);                    // [G][patch_stride]
+    double* s_pxd = s_mask + mask_doubles;                                  // [ww]: (double)(j - win_w);  [wh]: (double)(r - win_h)
+    double* s_pyd = s_pxd + ww;
+    const int table_doubles = (mask_doubles + ww + wh + 1) & ~1;
+    double* s_term = (double*)(spx_smem + table_doubles * sizeof(double) + warp * warp_bytes);  // [G][5][chunk]
+    float* s_sub = (float*)(s_term + SPX_G * 5 * chunk);                    // [G][patch_stride]
     const int patch_stride = (int)(((npatch * sizeof(float) + 7) & ~(size_t)7) / sizeof(float));
     const int rcp_pw = 65536 / pw + 1, rcp_ww = 65536 / ww + 1;
     const int g = lane / 5, s = lane - 5 * g;                               // lanes 30, 31: g = 6, helpers of the 32-wide phases only
@@ -170,6 +173,7 @@ __global__ void __launch_bounds__(SUBPIX_WARPS * 32) k_corner_subpix_v2(subpix_a
         const int r = spx_div(e, rcp_ww), j = e - r * ww;
         s_mask[e] = (double)__fmul_rn(a.ey[r], a.ex[j]);
     }
+    for (int e = threadIdx.x; e < ww + wh; e += SUBPIX_WARPS * 32) s_pxd[e] = e < ww ? (double)(e - a.win_w) : (double)(e - ww - a.win_h);
     __syncthreads();
 
     int next = (blockIdx.x * SUBPIX_WARPS + warp) * items_per_warp;
@@ -200,20 +204,25 @@ __global__ void __launch_bounds__(SUBPIX_WARPS * 32) k_corner_subpix_v2(subpix_a
             continue;                                                            // only skipped items so far: keep refilling
         }
 
-        // ---- patches (getRectSubPix_8u32f), one point slot after the other, 32 lanes per patch
+        // ---- patches (getRectSubPix_8u32f).  The per-point part -- integer origin, fractions, the double (1 - a) / a of the row
+        // recurrence -- is computed by every point slot for itself at once; the pixels then take all 32 lanes, slot after slot
+        const float my_cx = __fsub_rn(cix, __fmul_rn((float)(pw - 1), 0.5f)), my_cy = __fsub_rn(ciy, __fmul_rn((float)(ph - 1), 0.5f));
+        const int my_ipx = __float2int_rd(my_cx), my_ipy = __float2int_rd(my_cy);
+        const bool my_inside = 0 <= my_ipx && my_ipx + pw < w && 0 <= my_ipy && my_ipy + ph < h;
+        float my_fa = __fsub_rn(my_cx, (float)my_ipx);
+        const float my_fb = __fsub_rn(my_cy, (float)my_ipy);
+        if (my_inside) my_fa = fmaxf(my_fa, 0.0001f);
+        const double my_sc = (1. - (double)my_fa) / (double)my_fa;              // used by the inside form only (fa >= 1e-4 there)
+        const unsigned inside = __ballot_sync(0xffffffffu, my_inside);
         for (int gg = 0; gg < SPX_G; ++gg) {
             if (!(act >> (5 * gg) & 1)) continue;
-            const float px = __shfl_sync(0xffffffffu, cix, 5 * gg), py = __shfl_sync(0xffffffffu, ciy, 5 * gg);
+            const int ipx = __shfl_sync(0xffffffffu, my_ipx, 5 * gg), ipy = __shfl_sync(0xffffffffu, my_ipy, 5 * gg);
+            const float fa = __shfl_sync(0xffffffffu, my_fa, 5 * gg), fb = __shfl_sync(0xffffffffu, my_fb, 5 * gg);
             const uint8_t* src = base + (size_t)__shfl_sync(0xffffffffu, slot, 5 * gg) * a.v.slot_stride[0];
             float* sub = s_sub + gg * patch_stride;
-            const float centerx = __fsub_rn(px, __fmul_rn((float)(pw - 1), 0.5f)), centery = __fsub_rn(py, __fmul_rn((float)(ph - 1), 0.5f));
-            const int ipx = __float2int_rd(centerx), ipy = __float2int_rd(centery);
-            if (0 <= ipx && ipx + pw < w && 0 <= ipy && ipy + ph < h) {
-                float fa = __fsub_rn(centerx, (float)ipx);
-                const float fb = __fsub_rn(centery, (float)ipy);
-                fa = fmaxf(fa, 0.0001f);
+            if (inside >> (5 * gg) & 1) {
+                const double sc = __shfl_sync(0xffffffffu, my_sc, 5 * gg);
                 const float a12 = __fmul_rn(fa, __fsub_rn(1.f, fb)), a22 = __fmul_rn(fa, fb), b1 = __fsub_rn(1.f, fb), b2 = fb;
-                const double sc = (1. - (double)fa) / (double)fa;
                 const uint8_t* org = src + (ptrdiff_t)ipy * pitch + ipx;
                 for (int e = lane; e < npatch; e += 32) {
                     const int r = spx_div(e, rcp_pw), j = e - r * pw;
@@ -226,7 +235,6 @@ __global__ void __launch_bounds__(SUBPIX_WARPS * 32) k_corner_subpix_v2(subpix_a
                     sub[e] = __fadd_rn(prev, t);
                 }
             } else {
-                const float fa = __fsub_rn(centerx, (float)ipx), fb = __fsub_rn(centery, (float)ipy);
                 const float na = __fsub_rn(1.f, fa), nb = __fsub_rn(1.f, fb);
                 const float a11 = __fmul_rn(na, nb), a12 = __fmul_rn(fa, nb), a21 = __fmul_rn(na, fb), a22 = __fmul_rn(fa, fb);
                 for (int e = lane; e < npatch; e += 32) {
@@ -250,8 +258,7 @@ __global__ void __launch_bounds__(SUBPIX_WARPS * 32) k_corner_subpix_v2(subpix_a
 
         // ---- normal equations: SPX_ROWS window rows at a time -- products by all lanes, then thirty ordered sums in step
         double acc = 0;
-        const double* tA = s_term + ((g < SPX_G ? g : 0) * 3 + (s < 3 ? s : s - 3)) * chunk;      // s = 3: gxx, s = 4: gxy
-        const double* tB = s_term + ((g < SPX_G ? g : 0) * 3 + (s < 3 ? s : s - 2)) * chunk;      // s = 3: gxy, s = 4: gyy
+        const double* ts = s_term + ((g < SPX_G ? g : 0) * 5 + s) * chunk;                  // this lane's sum: terms of point slot g, row s
         for (int r0 = 0; r0 < wh; r0 += SPX_ROWS) {
             const int rows = min(SPX_ROWS, wh - r0), n = rows * ww;
             const int rcp_n = 65536 / n + 1;
@@ -263,25 +270,18 @@ __global__ void __launch_bounds__(SUBPIX_WARPS * 32) k_corner_subpix_v2(subpix_a
                 const double m = s_mask[r * ww + j];
                 const double tgx = (double)__fsub_rn(sp[1], sp[-1]);
                 const double tgy = (double)__fsub_rn(sp[pw], sp[-pw]);
-                double* tm = s_term + gg * 3 * chunk + e;
-                tm[0] = __dmul_rn(__dmul_rn(tgx, tgx), m);
-                tm[chunk] = __dmul_rn(__dmul_rn(tgx, tgy), m);
-                tm[2 * chunk] = __dmul_rn(__dmul_rn(tgy, tgy), m);
+                const double gxx = __dmul_rn(__dmul_rn(tgx, tgx), m), gxy = __dmul_rn(__dmul_rn(tgx, tgy), m),
+                             gyy = __dmul_rn(__dmul_rn(tgy, tgy), m);
+                const double px = s_pxd[j], py = s_pyd[r];
+                double* tm = s_term + gg * 5 * chunk + e;
+                tm[0] = gxx; tm[chunk] = gxy; tm[2 * chunk] = gyy;
+                tm[3 * chunk] = __dadd_rn(__dmul_rn(gxx, px), __dmul_rn(gxy, py));
+                tm[4 * chunk] = __dadd_rn(__dmul_rn(gxy, px), __dmul_rn(gyy, py));
             }
             __syncwarp();
             if (active && g < SPX_G) {
-                int e = 0;
-                for (int rr = 0; rr < rows; ++rr) {
-                    const double py = (double)(r0 + rr - a.win_h);
-                    double px = -(double)a.win_w;                               // j - win_w as a running double: small integers, exact
-                    for (int j = 0; j < ww; ++j, ++e) {
-                        const double va = tA[e];
-                        double v = va;
-                        if (s >= 3) v = __dadd_rn(__dmul_rn(va, px), __dmul_rn(tB[e], py));
-                        acc = __dadd_rn(acc, v);
-                        px = __dadd_rn(px, 1.0);
-                    }
-                }
+#pragma unroll 4
+                for (int e = 0; e < n; ++e) acc = __dadd_rn(acc, ts[e]);
             }
             __syncwarp();
         }
@@ -341,8 +341,8 @@ extern "C" zs_status zs_corner_subpix(zs_context* ctx, const zs_pyramid* p, int 
     const long long total = (long long)count * cap;
     ZS_REQUIRE(total < (1LL << 31), "count * cap too large");
     const int ww = 2 * win_w + 1, wh = 2 * win_h + 1, npatch = (ww + 2) * (wh + 2);
-    const size_t warp_bytes = (size_t)SPX_G * (3 * SPX_ROWS * ww * sizeof(double) + ((npatch * sizeof(float) + 7) & ~(size_t)7));
-    const size_t smem = warp_bytes * SUBPIX_WARPS + (size_t)((ww * wh + 1) & ~1) * sizeof(double);
+    const size_t warp_bytes = (size_t)SPX_G * (5 * SPX_ROWS * ww * sizeof(double) + ((npatch * sizeof(float) + 7) & ~(size_t)7));
+    const size_t smem = warp_bytes * SUBPIX_WARPS + (size_t)(((((ww * wh + 1) & ~1) + ww + wh) + 1) & ~1) * sizeof(double);
     const int resident_warps = ctx->sm_count * 24;
     int ipw = (int)((total + resident_warps - 1) / resident_warps);
     ipw = (ipw + SPX_G - 1) / SPX_G * SPX_G;
