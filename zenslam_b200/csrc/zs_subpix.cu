@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(SUBPIX_WARPS * 32) k_corner_subpix_v2(subpix_a
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = a.v.w[0], h = a.v.h[0], pitch = a.v.pitch[0];
     const int ww = 2 * a.win_w + 1, wh = 2 * a.win_h + 1, pw = ww + 2, ph = wh + 2, npatch = pw * ph;
-    const int chunk = SPX_ROWS * ww;                                        // terms per point and chunk
+    const int chunk = (SPX_ROWS * ww) | 1;                                  // row stride of the term arrays: terms per point and chunk,
+                                                                            // made odd so that the thirty chain lanes spread over all banks
     const size_t warp_bytes = (size_t)SPX_G * (5 * chunk * sizeof(double) + ((npatch * sizeof(float) + 7) & ~(size_t)7));
     double* s_mask = (double*)spx_smem;                                     // [wh * ww]: (double)(ey[r] * ex[j]), shared by the CTA
     const int mask_doubles = (ww * wh + 1) & ~1;
@@ -341,14 +342,17 @@ extern "C" zs_status zs_corner_subpix(zs_context* ctx, const zs_pyramid* p, int 
     const long long total = (long long)count * cap;
     ZS_REQUIRE(total < (1LL << 31), "count * cap too large");
     const int ww = 2 * win_w + 1, wh = 2 * win_h + 1, npatch = (ww + 2) * (wh + 2);
-    const size_t warp_bytes = (size_t)SPX_G * (5 * SPX_ROWS * ww * sizeof(double) + ((npatch * sizeof(float) + 7) & ~(size_t)7));
+    const size_t warp_bytes = (size_t)SPX_G * (5 * ((SPX_ROWS * ww) | 1) * sizeof(double) + ((npatch * sizeof(float) + 7) & ~(size_t)7));
     const size_t smem = warp_bytes * SUBPIX_WARPS + (size_t)(((((ww * wh + 1) & ~1) + ww + wh) + 1) & ~1) * sizeof(double);
-    const int resident_warps = ctx->sm_count * 24;
+    if (smem > 48 * 1024) ZS_CUDA(cudaFuncSetAttribute(k_corner_subpix_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // one wave: the kernel is latency-bound per warp (a warp runs its points to convergence), so a second, partly filled
+    // wave would cost as much as the first (measured: 822 CTAs on 740 resident slots = 1.20 instead of 1.02 ms)
+    int ctas_per_sm = 0;
+    ZS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_corner_subpix_v2, SUBPIX_WARPS * 32, smem));
+    const long long resident_warps = (long long)ctx->sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 1) * SUBPIX_WARPS;
     int ipw = (int)((total + resident_warps - 1) / resident_warps);
-    ipw = (ipw + SPX_G - 1) / SPX_G * SPX_G;
     ipw = ipw < SPX_G ? SPX_G : ipw;
     const int warps = (int)((total + ipw - 1) / ipw);
-    if (smem > 48 * 1024) ZS_CUDA(cudaFuncSetAttribute(k_corner_subpix_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_corner_subpix_v2<<<zs_div_up(warps, SUBPIX_WARPS), SUBPIX_WARPS * 32, smem, ctx->stream>>>(a, (int)total, ipw);
     ZS_LAUNCH_CHECK(ctx);
     return ZS_OK;
