@@ -781,11 +781,20 @@ def measure_c3(args, rank, world, ctx, light=False):
     return None
 
 
+def klt_capture_file():
+    """the committed ncu --set full capture of the KLT launch of the default workload: newest round first"""
+    for name in ("r2_klt_traffic.json", "r1_klt_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return p
+    return os.path.join(ROOT, "profiles", "r1_klt_traffic.json")
+
+
 def klt_traffic(batch):
     """dram__bytes_read.sum + dram__bytes_write.sum of one KLT launch from the committed ncu capture (taken at batch
     128; scaled linearly with the batch, which is exact for the compulsory part), or None"""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_klt_traffic.json")))
+        t = json.load(open(klt_capture_file()))
         return (t["dram_bytes_read"] + t["dram_bytes_write"]) * batch / t["batch_stereo_frames"]
     except Exception:
         return None
@@ -797,7 +806,7 @@ def klt_issue(batch, klt_ms, clocks):
     workload (smsp__inst_executed.sum at batch 128, linear in the batch); the time is this run's."""
     try:
         import torch
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_klt_traffic.json")))
+        t = json.load(open(klt_capture_file()))
         inst = t["warp_instructions"] * batch / t["batch_stereo_frames"]
         sms = torch.cuda.get_device_properties(0).multi_processor_count
         mhz = (clocks or {}).get("sm_mhz") or 1965.0

@@ -60,7 +60,8 @@ struct zs_context {
     uint64_t lk_hash[ZS_LK_CACHE_SLOTS], lk_stamp[ZS_LK_CACHE_SLOTS], lk_clock;
     uint64_t lk_hits, lk_misses;
     int* d_async_err;         // device flags raised by kernels of stream-asynchronous entries ([0]: L2 descriptors not integers in 0..255)
-    uint8_t* lk_copy[ZS_LK_CACHE_SLOTS];   // host copy (w*h, no pitch) of the frame each slot holds: a hash hit is confirmed byte for byte
+    int* d_klt_work;          // work counter of the persistent KLT launch (same allocation; reset in stream order before each launch)
+    uint8_t* lk_copy[ZS_LK_CACHE_SLOTS];   // sampled rows of the frame each slot holds: a hash hit is confirmed against them (zs_host.cu)
     size_t lk_copy_bytes[ZS_LK_CACHE_SLOTS];
 };
 

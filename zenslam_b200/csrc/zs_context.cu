@@ -150,6 +150,7 @@ zs_status zs_context_create(int device, void* stream, zs_context** out)
             free(c);
             return zs_cuda_fail(e, "cudaMalloc(async error flags)", __FILE__, __LINE__);
         }
+        c->d_klt_work = c->d_async_err + 32;
     }
     *out = c;
     return ZS_OK;

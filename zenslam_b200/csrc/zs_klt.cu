@@ -859,7 +859,7 @@ zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_
         // so small launches keep the plain grid and skip the counter reset
         const bool persist = !ctx->sw.klt_no_persist && items < (1LL << 31) && items > 4LL * ctx->sm_count * 24;
         if (persist) {
-            a.work = ctx->d_async_err + 32;                    // a device int of the context, zeroed in stream order before the launch
+            a.work = ctx->d_klt_work;                          // a device int of the context, zeroed in stream order before the launch
             a.n_items = (int)items;
             ZS_CUDA(cudaMemsetAsync(a.work, 0, sizeof(int), ctx->stream));
         }
