@@ -138,3 +138,67 @@ def test_assign_landmark_indices_live(radius):
         if mt.distance <= 32.0:
             want[mt.queryIdx] = idx[mt.trainIdx]
     assert np.array_equal(got, want) and (got >= 0).sum() > 30
+
+
+def test_match_temporal_live():
+    """oracle/landmarks.py::match_temporal against utils::match_temporal (matching_utils.cpp:441-563) restated directly over
+    cv2.BFMatcher(NORM_HAMMING, crossCheck=True) and cv2.findEssentialMat -- including the reference's e.at<float> reading of
+    the CV_64F essential matrix"""
+    from oracle import landmarks as olm
+    rng = np.random.default_rng(811)
+    n0, n1 = 260, 240
+    K = np.array([[450.0, 0, 376.0], [0, 450.0, 240.0], [0, 0, 1.0]])
+    # a rigid scene seen from two poses, so that findEssentialMat has inliers
+    X = np.stack([rng.uniform(-4, 4, n0), rng.uniform(-3, 3, n0), rng.uniform(4, 12, n0)], 1)
+    ang = 0.05
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    t = np.array([0.3, 0.02, 0.05])
+    p0 = (X / X[:, 2:]) @ K.T
+    X1 = X @ R.T + t
+    p1_all = (X1 / X1[:, 2:]) @ K.T
+    pts_0 = p0[:, :2].astype(np.float32)
+    d0 = rng.integers(0, 256, (n0, 32), dtype=np.uint8)
+    perm = rng.permutation(n0)[:n1]
+    pts_1 = (p1_all[perm, :2] + rng.normal(0, 0.2, (n1, 2))).astype(np.float32)
+    d1 = d0[perm].copy()
+    d1[::3, 5] ^= 1                                                     # distance 1 .. and some beyond 5:
+    d1[1::7, :2] ^= 255
+    keys_0 = np.arange(100, 100 + n0); keys_1 = np.arange(5000, 5000 + n1)
+    keys_1[:20] = keys_0[perm[:20]]                                     # shared indices drop out of both sides
+    order = np.argsort(keys_1, kind="stable"); keys_1, pts_1, d1 = keys_1[order], pts_1[order], d1[order]
+    s0, s1 = set(keys_0.tolist()), set(keys_1.tolist())
+    u0 = [i for i in range(n0) if int(keys_0[i]) not in s1]; u1 = [i for i in range(n1) if int(keys_1[i]) not in s0]
+    Ki = np.linalg.inv(K)
+    # threshold 1.0: what the reference passes -- with the float reading of E the epipolar gate then rejects practically
+    # everything (the reference's own behaviour); 1e30: every match reaches the mask / distance gates
+    for thr in (1.0, 1e30):
+        state = {}
+
+        def fem(a, b):
+            cv2.setRNGSeed(7)
+            E, mask = cv2.findEssentialMat(a, b, K, cv2.RANSAC, 0.99, thr)
+            state["E"], state["mask"] = E, mask
+            return E, mask
+
+        got = olm.match_temporal(keys_0, pts_0, d0, keys_1, pts_1, d1, K, thr, fem)
+        # the restatement over cv2
+        matches = cv2.BFMatcher(cv2.NORM_HAMMING, True).match(d0[u0], d1[u1])
+        a = np.array([pts_0[u0[m.queryIdx]] for m in matches], np.float32); b = np.array([pts_1[u1[m.trainIdx]] for m in matches], np.float32)
+        cv2.setRNGSeed(7)
+        E, mask = cv2.findEssentialMat(a, b, K, cv2.RANSAC, 0.99, thr)
+        Ef = np.frombuffer(np.ascontiguousarray(E, np.float64).tobytes(), np.float32).reshape(3, 6)[:, :3].astype(np.float64)
+        want = []
+        for k, (m, msk) in enumerate(zip(matches, mask.ravel())):
+            if not msk:
+                continue
+            pl = np.array([a[k][0], a[k][1], 1.0], np.float64); pr = np.array([b[k][0], b[k][1], 1.0], np.float64)
+            err = float((((pr @ Ki.T) @ Ef) @ Ki) @ pl)
+            if err > thr or m.distance > 5:
+                continue
+            want.append((int(keys_0[u0[m.queryIdx]]), int(keys_1[u1[m.trainIdx]]), float(m.distance)))
+        assert np.array_equal(state["E"], E) and np.array_equal(state["mask"], mask)
+        assert got == want
+        if thr > 1.0:
+            assert len(got) > 20 and any(m.distance > 5 for m in matches)
+    fem = lambda a, b: (np.eye(3), np.ones(len(a), np.uint8))
+    assert olm.match_temporal(keys_0[:4], pts_0[:4], d0[:4], keys_1, pts_1, d1, K, 1.0, fem) == []
