@@ -293,7 +293,11 @@ def test_l2_rejects_non_integer(ctx):
     assert (idx.cpu().numpy() == -1).all() and not ps.cpu().numpy().any()
     cidx, _ = match_l2_cross(ctx, dev(ctx, q), n, dev(ctx, q), n)
     assert (cidx.cpu().numpy() == -1).all()
-    # ... and through the context's asynchronous error, which is raised once and then cleared
+    # a later call with valid rows is not affected by the earlier bad one ...
+    good = np.rint(q * 200).astype(np.float32)
+    gidx, _, _ = match_l2_knn2(ctx, dev(ctx, good), n, dev(ctx, good), n, 0.8)
+    assert np.array_equal(gidx.cpu().numpy()[0, :, 0], np.arange(8))
+    # ... and the bad one is still reported through the context's asynchronous error, once
     with pytest.raises(ZenslamCudaError):
         ctx.async_error()
     ctx.async_error()

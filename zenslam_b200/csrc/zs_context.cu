@@ -157,7 +157,8 @@ zs_status zs_context_create(int device, void* stream, zs_context** out)
 }
 
 // Errors that kernels of stream-asynchronous entries found in their DATA (not their arguments): waits for the stream, reports
-// and clears them.  [0]: zs_match_l2_* got descriptors that are not integers in 0..255.
+// and clears them.  [0] / [1]: zs_match_l2_* got descriptors that are not integers in 0..255 ([0] belongs to the call in flight
+// and blanks its results, [1] stays until it is reported here: a later valid call is not affected by an earlier bad one).
 zs_status zs_context_async_error(zs_context* c)
 {
     ZS_REQUIRE(c, "ctx is null");
@@ -165,7 +166,7 @@ zs_status zs_context_async_error(zs_context* c)
     int flags[4] = { 0, 0, 0, 0 };
     ZS_CUDA(cudaMemcpyAsync(flags, c->d_async_err, sizeof(flags), cudaMemcpyDeviceToHost, c->stream));
     ZS_CUDA(cudaStreamSynchronize(c->stream));
-    if (flags[0]) {
+    if (flags[1]) {                                          // [1] is the sticky copy of the per-call flag [0]
         ZS_CUDA(cudaMemsetAsync(c->d_async_err, 0, sizeof(flags), c->stream));
         zs_set_error("L2 matching is exact only for integer-valued descriptors in 0..255 (cv::SIFT); got other values "
                      "(every match of that call was reported as -1)");

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256) k_f32_to_u8(const float* __restrict__ src
         wrong |= ((float)r != v[k] || r < 0 || r > 255);
         out |= (uint32_t)(r & 255) << (8 * k);
     }
-    if (wrong) atomicExch(bad, 1);
+    if (wrong) { atomicExch(bad, 1); atomicExch(bad + 1, 1); }     // [0]: this call (reset when the next one starts); [1]: sticky, for zs_context_async_error
     *(uint32_t*)(dst + (size_t)pair * cap * dim + i) = out;
     if (norms) {                                   // dim == 128: total is a multiple of 128 values = whole warps get here
         const int s2 = __reduce_add_sync(0xffffffffu, (int)__dp4a(out, out, 0u));
@@ -362,6 +362,7 @@ static zs_status l2_prepare(zs_context* ctx, const float* d_q, const int* d_nq, 
     uint8_t* q8 = (uint8_t*)s; uint8_t* t8 = q8 + qb;
     int* norms = (int*)(t8 + tb);
     op->q8 = q8; op->t8 = t8; op->extra = (int*)((uint8_t*)norms + nb); op->bad = ctx->d_async_err;
+    ZS_CUDA(cudaMemsetAsync(ctx->d_async_err, 0, sizeof(int), ctx->stream));   // the per-call flag; the sticky one stays
     const bool fuse = dim == 128;
     op->qnorm = fuse ? norms : nullptr; op->tnorm = fuse ? norms + (size_t)pairs * cap_q : nullptr;
     const int vq = ((uintptr_t)d_q % 16 == 0 && q_stride % 4 == 0) ? 1 : 0, vt = ((uintptr_t)d_t % 16 == 0 && t_stride % 4 == 0) ? 1 : 0;
