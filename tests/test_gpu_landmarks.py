@@ -222,3 +222,58 @@ def test_match_temporal_vs_oracle(ctx):
     assert len(match_temporal(ctx, m0, m1, K, 1e30, fem)) > 20
     few = {k: m0[k] for k in list(m0)[:4]}
     assert match_temporal(ctx, few, m1, K, 1e30, fem) == [] and match_temporal(ctx, m1, few, K, 1e30, fem) == []
+
+
+def test_match_keylines_and_keyline_landmarks_vs_cv2_restatement(ctx):
+    """utils::match_keylines (matching_utils.cpp:345-439) and the keyline landmark association (keyline_tracker.cpp:135-163):
+    the device Hamming matcher + the reference's gates against a restatement over the oracle matcher and, where cv2 imports,
+    cv2.computeCorrespondEpilines itself"""
+    from zenslam_b200 import keyline
+    from zenslam_b200.matching import _epilines, assign_keyline_landmark_indices, match_keylines
+    rng = np.random.default_rng(91)
+    n0, n1 = 180, 170
+    F = np.array([[0.0, 0.0, 0.0], [0.0, 0.0, -0.013], [0.0, 0.013, 0.0]])                        # rectified pair: horizontal epipolar lines
+    d0 = rng.integers(0, 256, (n0, 32), dtype=np.uint8)
+    perm = rng.permutation(n0)[:n1]
+    d1 = d0[perm].copy(); d1[::4, 3] ^= 9
+    def mk(i, d, s, e):
+        return keyline(startPointX=float(s[0]), startPointY=float(s[1]), endPointX=float(e[0]), endPointY=float(e[1]),
+                       pt=(float(np.float32(0.5) * np.float32(s[0] + e[0])), float(np.float32(0.5) * np.float32(s[1] + e[1]))), index=i, descriptor=d)
+    s0 = rng.uniform(50, 700, (n0, 2)).astype(np.float32); e0 = s0 + rng.uniform(-40, 40, (n0, 2)).astype(np.float32)
+    # image-1 lines: the same lines shifted along x (epipolar-consistent for this F up to noise), some pushed off their epiline
+    shift = np.stack([rng.uniform(-30, -5, n1), rng.normal(0, 0.3, n1)], 1).astype(np.float32)
+    shift[::5, 1] += 6.0
+    s1 = s0[perm] + shift; e1 = e0[perm] + shift
+    m0 = {10 + i: mk(10 + i, d0[i], s0[i], e0[i]) for i in range(n0)}
+    m1 = {900 + i: mk(900 + i, d1[i], s1[i], e1[i]) for i in range(n1)}
+    got = match_keylines(ctx, m0, m1, F, 2.0)
+    oq, ot, od = oracle.match_hamming_cross(d0, d1)
+    try:
+        import cv2
+    except Exception:
+        cv2 = None
+    want = []
+    for a, b, d in zip(oq, ot, od):
+        p0 = np.array([s0[a], e0[a], m0[10 + a].pt], np.float32); p1 = np.array([s1[b], e1[b], m1[900 + b].pt], np.float32)
+        if cv2 is not None:
+            l1 = cv2.computeCorrespondEpilines(p0.reshape(-1, 1, 2), 1, F).reshape(-1, 3)
+            l0 = cv2.computeCorrespondEpilines(p1.reshape(-1, 1, 2), 2, F).reshape(-1, 3)
+            assert np.allclose(l1, _epilines(p0, 1, F), rtol=0, atol=1e-5) and np.allclose(l0, _epilines(p1, 2, F), rtol=0, atol=1e-5)
+        else:
+            l1, l0 = _epilines(p0, 1, F), _epilines(p1, 2, F)
+        err0 = np.abs(l0[:, 0] * p0[:, 0] + l0[:, 1] * p0[:, 1] + l0[:, 2]) / np.sqrt(l0[:, 0] ** 2 + l0[:, 1] ** 2)
+        err1 = np.abs(l1[:, 0] * p1[:, 0] + l1[:, 1] * p1[:, 1] + l1[:, 2]) / np.sqrt(l1[:, 0] ** 2 + l1[:, 1] ** 2)
+        worst = float(max(err0.max(), err1.max()))
+        assert abs(worst - 2.0) > 1e-3, "a pair sits on the threshold: change the seed"     # float order differences stay below this
+        if worst <= 2.0:
+            want.append((10 + int(a), 900 + int(b), float(d)))
+    assert [(g.queryIdx, g.trainIdx, g.distance) for g in got] == want
+    assert 20 < len(got) < len(oq)                                          # the gate really cut something
+    # keyline landmarks: 1-NN without cross check, distance gate
+    lm_desc = rng.integers(0, 256, (400, 32), dtype=np.uint8); lm_desc[:60] = d0[:60]; lm_desc[:60, 0] ^= 1
+    lm_idx = np.arange(7000, 7400)
+    kls = [mk(i, d0[i], s0[i], e0[i]) for i in range(n0)]
+    n = assign_keyline_landmark_indices(ctx, kls, lm_desc, lm_idx, 32.0)
+    oi, odist = oracle.match_hamming_knn2(d0, lm_desc)
+    want_idx = [int(lm_idx[oi[i, 0]]) if odist[i, 0] <= 32 else i for i in range(n0)]
+    assert [k.index for k in kls] == want_idx and n == sum(1 for i in range(n0) if odist[i, 0] <= 32) and n >= 60

@@ -6,7 +6,7 @@ There is no CPU fallback: importing works anywhere, but creating a Context witho
 """
 from ._lib import LK_GET_MIN_EIGENVALS, LK_USE_INITIAL_FLOW, ZenslamCudaError, lib  # noqa: F401
 from .options import detection_options, slam_options, tracking_options  # noqa: F401
-from .types import DMatch, keypoint  # noqa: F401
+from .types import DMatch, keyline, keypoint  # noqa: F401
 
 __all__ = ["lib", "ZenslamCudaError", "slam_options", "detection_options", "tracking_options", "keypoint", "DMatch",
            "LK_GET_MIN_EIGENVALS", "LK_USE_INITIAL_FLOW"]

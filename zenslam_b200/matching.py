@@ -163,3 +163,79 @@ def match_temporal(ctx: Context, keypoints_map_0: dict, keypoints_map_1: dict, c
             continue
         out.append(DMatch(un_0[a].index, un_1[b].index, d))
     return out
+
+
+def _epilines(points, which_image: int, fundamental) -> np.ndarray:
+    """cv::computeCorrespondEpilines for CV_32F points (calib3d fundam.cpp): l = F p (which_image 1) or F^T p (2), accumulated
+    in double, scaled by 1 / sqrt(a^2 + b^2) (1 when that is 0), stored as float32"""
+    F = np.asarray(fundamental, np.float64).reshape(3, 3)
+    if which_image == 2:
+        F = F.T
+    p = np.asarray(points, np.float32).reshape(-1, 2).astype(np.float64)
+    a = F[0, 0] * p[:, 0] + F[0, 1] * p[:, 1] + F[0, 2]
+    b = F[1, 0] * p[:, 0] + F[1, 1] * p[:, 1] + F[1, 2]
+    c = F[2, 0] * p[:, 0] + F[2, 1] * p[:, 1] + F[2, 2]
+    nu = a * a + b * b
+    nu = np.where(nu != 0, 1.0 / np.sqrt(np.where(nu != 0, nu, 1.0)), 1.0)
+    return np.stack([a * nu, b * nu, c * nu], 1).astype(np.float32)
+
+
+def match_keylines(ctx: Context, keylines_map_0: dict, keylines_map_1: dict, fundamental, epipolar_threshold: float) -> list:
+    """utils::match_keylines (zenslam_core/source/matching/matching_utils.cpp:345-439; SURVEY 8 a9): every keyline of either
+    map in key order, cross-checked Hamming 1-NN of their 32-byte LBD descriptors on the device
+    (cv::BFMatcher(NORM_HAMMING, true).match), then the epipolar gate on both endpoints and the midpoint: point-to-epiline
+    distance in BOTH images <= epipolar_threshold, in float like the reference's expression.  Keyline detection and
+    description (LSD / LBD) stay on the host (out of scope).  -> [DMatch(keyline index 0, keyline index 1, distance)]"""
+    kl0 = [kl for _, kl in sorted(keylines_map_0.items())]
+    kl1 = [kl for _, kl in sorted(keylines_map_1.items())]
+    if not kl0 or not kl1:
+        return []
+    q = np.ascontiguousarray(np.stack([k.descriptor for k in kl0]), np.uint8).reshape(len(kl0), -1)
+    t = np.ascontiguousarray(np.stack([k.descriptor for k in kl1]), np.uint8).reshape(len(kl1), -1)
+    idx = np.empty(len(q), np.int32); dist = np.empty(len(q), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(lib().zs_knn_match_host(ctx._h, p(q), len(q), p(t), len(t), 32, 0, 1, 1, p(idx), p(dist)))
+    f32 = np.float32
+    out = []
+    for i in range(len(q)):
+        if idx[i] < 0:
+            continue
+        a, b = kl0[i], kl1[int(idx[i])]
+        pts0 = np.array([(a.startPointX, a.startPointY), (a.endPointX, a.endPointY), a.pt], f32)
+        pts1 = np.array([(b.startPointX, b.startPointY), (b.endPointX, b.endPointY), b.pt], f32)
+        lines1 = _epilines(pts0, 1, fundamental)             # epilines of image-0 points, in image 1
+        lines0 = _epilines(pts1, 2, fundamental)             # epilines of image-1 points, in image 0
+        good = True
+        for k in range(3):
+            e0 = abs(f32(f32(f32(lines0[k, 0] * pts0[k, 0]) + f32(lines0[k, 1] * pts0[k, 1])) + lines0[k, 2])) / \
+                np.sqrt(f32(f32(lines0[k, 0] * lines0[k, 0]) + f32(lines0[k, 1] * lines0[k, 1])))
+            e1 = abs(f32(f32(f32(lines1[k, 0] * pts1[k, 0]) + f32(lines1[k, 1] * pts1[k, 1])) + lines1[k, 2])) / \
+                np.sqrt(f32(f32(lines1[k, 0] * lines1[k, 0]) + f32(lines1[k, 1] * lines1[k, 1])))
+            if float(e0) > epipolar_threshold or float(e1) > epipolar_threshold:
+                good = False
+                break
+        if good:
+            out.append(DMatch(a.index, b.index, float(dist[i])))
+    return out
+
+
+def assign_keyline_landmark_indices(ctx: Context, keylines: list, landmark_descriptors, landmark_indices,
+                                    max_descriptor_distance: float) -> int:
+    """keyline_tracker's landmark association (zenslam_core/source/tracking/keyline_tracker.cpp:135-163): 1-NN WITHOUT cross
+    check (cv::BFMatcher(NORM_HAMMING, false).match) of the keylines that carry a descriptor against the landmark
+    descriptors; distance <= max_descriptor_distance renames the keyline to the landmark's index.  Mutates `keylines`;
+    returns the number of renamed keylines."""
+    rows = [i for i, kl in enumerate(keylines) if kl.descriptor is not None and len(kl.descriptor)]
+    if not rows or landmark_descriptors is None or len(landmark_descriptors) == 0:
+        return 0
+    q = np.ascontiguousarray(np.stack([keylines[i].descriptor for i in rows]), np.uint8).reshape(len(rows), -1)
+    t = np.ascontiguousarray(landmark_descriptors, np.uint8).reshape(-1, 32)
+    idx = np.empty(len(q), np.int32); dist = np.empty(len(q), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(lib().zs_knn_match_host(ctx._h, p(q), len(q), p(t), len(t), 32, 0, 1, 0, p(idx), p(dist)))
+    n = 0
+    for j, i in enumerate(rows):
+        if idx[j] >= 0 and float(dist[j]) <= max_descriptor_distance:
+            keylines[i].index = int(landmark_indices[int(idx[j])])
+            n += 1
+    return n
