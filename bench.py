@@ -283,7 +283,10 @@ def measure_frontend(args, rank, world, local_rank, ctx, light=False):
 
     # distinct batches cycled through the run: consecutive chunks of one long synthetic sequence per rank
     nb = min(args.batches, K + Wm)
-    seq = make_sequence(nb * B, 20000 + 97 * rank)                       # (nb*B, 2, H, W)
+    # every rank runs the SAME synthetic sequence: KLT iteration counts depend on the data (ranks with different sequences
+    # differed by 2.8 % in step time at N = 8, profiles/r2_bench_n8_distinct_sequences.json), and weak scaling is defined on
+    # identical per-GPU work -- the max-over-ranks time then measures the system, not the luck of the seeds
+    seq = make_sequence(nb * B, 20000)                                   # (nb*B, 2, H, W)
     left = torch.from_numpy(np.ascontiguousarray(seq[:, 0])).reshape(nb, B, H, W)
     right = torch.from_numpy(np.ascontiguousarray(seq[:, 1])).reshape(nb, B, H, W)
     left_pin, right_pin = left.pin_memory(), right.pin_memory()
@@ -466,7 +469,7 @@ def measure_frontend(args, rank, world, local_rank, ctx, light=False):
                        "fb_keep_fraction": keep_frac, "distinct_batches": nb,
                        "l2": "inputs larger than L2: one batch's pyramids are %.0f MB, %d distinct batches cycled"
                              % (2 * B * 3.2 * (W * H) / (752.0 * 480.0), nb),
-                       "parallelism": "independent sequences per GPU, no collective",
+                       "parallelism": "one independent sequence per GPU (the same synthetic content on every rank: identical per-GPU work), no collective",
                        "note": "the contract's metric: every cell of every frame is detected again and every keypoint goes through all "
                                "four forward/backward KLT jobs (SURVEY C2) -- more work per frame than the reference's stateful flow "
                                "(occupancy-aware detection, stereo tracks only of what the other camera lacks), which is measured as "
@@ -653,7 +656,7 @@ def measure_c3(args, rank, world, ctx, light=False):
     B = 64 if args.batch in (0, 128) else args.batch
     K, Wm = args.steps, max(3, args.warmup)
     nb = 3                                                           # 3 x 131 MB of float descriptors > the 126 MB L2
-    host = [torch.from_numpy(c3_descriptors(B, 31000 + 97 * rank + i)).pin_memory() for i in range(nb)]
+    host = [torch.from_numpy(c3_descriptors(B, 31000 + i)).pin_memory() for i in range(nb)]
     dev = [h.cuda(non_blocking=True) for h in host]
     n = torch.full((B,), C3_N, dtype=torch.int32, device="cuda")
     stream = torch.cuda.current_stream()

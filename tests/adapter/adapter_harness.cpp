@@ -299,7 +299,8 @@ try
         out.put_i32("match.refuses_mask", ref);
     }
 
-    // ---------------------------------------------------------------- the stateful tracker
+    // ---------------------------------------------------------------- the stateful tracker (second run: with a landmark store)
+    for (int with_landmarks = 0; with_landmarks < 2; ++with_landmarks)
     {
         zenslam::detection_options detection { };
         detection.cell_size      = cv::Size(cell, cell);
@@ -309,17 +310,37 @@ try
         tracking.klt_max_level   = max_level;
 
         zenslam::keypoint::index_next = 0;
-        zenslam::cuda::stereo_tracker tracker { detection, tracking, cv::Size(w, h) };
+        zenslam::cuda::stereo_tracker tracker { detection, tracking, cv::Size(w, h), with_landmarks ? 4096 : 0 };
+        const std::string             prefix = with_landmarks ? "trk_lm." : "trk.";
+
+        if (with_landmarks)
+        {
+            // system.points3d: (index, world position, descriptor) rows from the test; assign_landmark_indices then renames
+            // the detections of every frame whose descriptor matches one within landmark_match_distance
+            const auto& li = in.at("lm_index");
+            const auto& lx = in.at("lm_xyz");
+            const auto& ld = in.at("lm_desc");
+            std::map<size_t, std::pair<cv::Point3d, cv::Mat>> landmarks;
+            for (size_t i = 0; i < li.dim(0); ++i)
+            {
+                cv::Mat row(1, 32, CV_8UC1);
+                std::memcpy(row.ptr<uchar>(0), ld.as<uchar>() + 32 * i, 32);
+                landmarks[static_cast<size_t>(li.as<int>()[i])] = { cv::Point3d(lx.as<double>()[3 * i], lx.as<double>()[3 * i + 1], lx.as<double>()[3 * i + 2]), row };
+            }
+            const std::vector<int> added { tracker.add_landmarks(landmarks), tracker.add_landmarks(landmarks) };   // the second call adds nothing
+            out.put_i32("trk_lm.added", added);
+            tracker.set_camera_center(cv::Point3d(1.0, -2.0, 0.5));
+        }
 
         for (int t = 0; t < frames; ++t)
         {
             const cv::Mat left(h, w, CV_8UC1, const_cast<uchar*>(image(t, 0)));
             const cv::Mat right = padded_level0(image(t, 1), w, h, 8, 3).front();     // different pitches: the adapter equalises them
             const auto    maps  = tracker.track(left, right);
-            dump_map(out, "trk." + std::to_string(t) + ".0", maps[0]);
-            dump_map(out, "trk." + std::to_string(t) + ".1", maps[1]);
+            dump_map(out, prefix + std::to_string(t) + ".0", maps[0]);
+            dump_map(out, prefix + std::to_string(t) + ".1", maps[1]);
             const std::vector<int> next_index { static_cast<int>(zenslam::keypoint::index_next) };
-            out.put_i32("trk." + std::to_string(t) + ".index_next", next_index);
+            out.put_i32(prefix + std::to_string(t) + ".index_next", next_index);
         }
     }
 

@@ -62,6 +62,15 @@ namespace cv
     using Point2d = Point_<double>;
     using Point   = Point_<int>;
 
+    template <typename T> struct Point3_
+    {
+        T x { }, y { }, z { };
+        Point3_() = default;
+        Point3_(T x_, T y_, T z_) : x(x_), y(y_), z(z_) { }
+    };
+    using Point3d = Point3_<double>;
+    using Point3f = Point3_<float>;
+
     template <typename T> struct Size_
     {
         T width { }, height { };

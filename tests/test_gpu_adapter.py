@@ -33,7 +33,7 @@ def write_arrays(path, arrays):
     with open(path, "wb") as f:
         for name, a in arrays.items():
             a = np.ascontiguousarray(a)
-            code = {np.dtype(np.uint8): "u1", np.dtype(np.int32): "i4", np.dtype(np.float32): "f4"}[a.dtype]
+            code = {np.dtype(np.uint8): "u1", np.dtype(np.int32): "i4", np.dtype(np.float32): "f4", np.dtype(np.float64): "f8"}[a.dtype]
             f.write(("%s %s %d %s\n" % (name, code, a.ndim, " ".join(str(d) for d in a.shape))).encode())
             f.write(a.tobytes())
             f.write(b"\n")
@@ -87,8 +87,20 @@ def inputs():
     qf = rng.integers(0, 120, (150, 128)).astype(np.float32)
     tf = rng.integers(0, 120, (170, 128)).astype(np.float32)
     tf[:60] = qf[30:90]
+    # landmarks for the stateful flow: descriptors of corners the tracker will detect in frames 1 and 2 (a few bits flipped),
+    # positions some of which lie beyond the 50 m radius
+    lm_desc = []
+    for f in (1, 2):
+        xf, yf, _ = oracle.grid_detect(seq[f, 0], (CELL, CELL), THR)
+        _, df = oracle.orb_compute(seq[f, 0], xf, yf)
+        lm_desc.append(df[::2])
+    lm_desc = np.concatenate(lm_desc).copy()
+    lm_desc[:, 7] ^= 3
+    lm_index = (700000 + 3 * np.arange(len(lm_desc))).astype(np.int32)
+    lm_xyz = rng.normal(0.0, 30.0, (len(lm_desc), 3))
     return {"dims": np.array([W, H, FRAMES, CELL, THR, WIN, LEVEL], np.int32), "frames": seq, "lk_points": pts, "lk_initial": init,
-            "existing": ex, "match_q": q, "match_t": t, "match_qf": qf, "match_tf": tf}
+            "existing": ex, "match_q": q, "match_t": t, "match_qf": qf, "match_tf": tf,
+            "lm_index": lm_index, "lm_xyz": lm_xyz, "lm_desc": lm_desc}
 
 
 @pytest.fixture(scope="module")
@@ -214,23 +226,34 @@ def test_descriptor_matcher_forwarding_equals_oracle(results, inputs):
     assert int(results["match.refuses_mask"].ravel()[0]) == 1
 
 
-def test_stereo_tracker_class_equals_python_device_tracker(results, inputs, ctx):
+@pytest.mark.parametrize("with_landmarks", [False, True])
+def test_stereo_tracker_class_equals_python_device_tracker(results, inputs, ctx, with_landmarks):
+    """zenslam::cuda::stereo_tracker::track (+ add_landmarks / set_camera_center: assign_landmark_indices inside the step)
+    against the python device tracker, which tests/test_gpu_landmarks.py ties to the oracle's assign_landmark_indices"""
     from zenslam_b200 import detection_options, keypoint, slam_options, tracking_options
     from zenslam_b200.keypoint_tracker import device_keypoint_tracker
     seq = inputs["frames"]
     opts = slam_options(detection=detection_options(cell_size=(CELL, CELL), fast_threshold=THR),
                         tracking=tracking_options(klt_window_size=(WIN, WIN), klt_max_level=LEVEL, filter_epipolar=False))
     keypoint.index_next = 0
-    trk = device_keypoint_tracker(opts, ctx, W, H)
+    trk = device_keypoint_tracker(opts, ctx, W, H, landmark_capacity=4096 if with_landmarks else 0)
+    pre = "trk_lm" if with_landmarks else "trk"
+    if with_landmarks:
+        n_lm = len(inputs["lm_index"])
+        assert trk.add_landmarks(inputs["lm_index"], inputs["lm_xyz"], inputs["lm_desc"]) == n_lm
+        assert results["trk_lm.added"].ravel().tolist() == [n_lm, 0]
+        trk.set_camera_center([1.0, -2.0, 0.5])
     for t in range(FRAMES):
         maps = trk.track(seq[t, 0], seq[t, 1])
         for cam in range(2):
-            f, i, d = (results["trk.%d.%d.%s" % (t, cam, s)] for s in ("f", "i", "desc"))
+            f, i, d = (results["%s.%d.%d.%s" % (pre, t, cam, s)] for s in ("f", "i", "desc"))
             want = maps[cam]
             assert i[:, 0].tolist() == list(want), (t, cam)
             assert np.array_equal(f[:, :2], np.array([want[k].pt for k in want], np.float32)), (t, cam)
             assert np.array_equal(f[:, 2], np.array([want[k].response for k in want], np.float32)), (t, cam)
             assert np.array_equal(d, np.stack([want[k].descriptor for k in want])), (t, cam)
-        assert int(results["trk.%d.index_next" % t].ravel()[0]) == keypoint.index_next
-    assert len(results["trk.%d.0.f" % (FRAMES - 1)]) > 200
+        assert int(results["%s.%d.index_next" % (pre, t)].ravel()[0]) == keypoint.index_next
+    last = results["%s.%d.0.i" % (pre, FRAMES - 1)][:, 0]
+    assert len(last) > 200
+    assert bool((last >= 700000).any()) == with_landmarks           # landmark indices live in the maps exactly when a store exists
     trk.close()

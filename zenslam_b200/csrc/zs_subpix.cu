@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(SUBPIX_WARPS * 32) k_corner_subpix(subpix_args
 // range of (image, corner) items), so lanes do not idle behind the slowest of six.  Results are bit-identical to v1.
 // ------------------------------------------------------------------------------------------------------
 #define SPX_G 6
-#define SPX_ROWS 2                              // window rows of terms parked per chunk
+#define SPX_ROWS 2                              // window rows of terms parked per chunk (the term loop below assumes 2)
 
 // exact u8 -> f32 on the ALU / FMA pipes (I2F issues on the quarter-rate XU pipe): 2^23 + v is exactly representable
 __device__ __forceinline__ float spx_u8f(unsigned v) { return __fsub_rn(__uint_as_float(0x4b000000u | v), 8388608.f); }
@@ -262,11 +262,14 @@ __global__ void __launch_bounds__(SUBPIX_WARPS * 32) k_corner_subpix_v2(subpix_a
         const double* ts = s_term + ((g < SPX_G ? g : 0) * 5 + s) * chunk;                  // this lane's sum: terms of point slot g, row s
         for (int r0 = 0; r0 < wh; r0 += SPX_ROWS) {
             const int rows = min(SPX_ROWS, wh - r0), n = rows * ww;
-            const int rcp_n = 65536 / n + 1;
-            for (int idx = lane; idx < SPX_G * n; idx += 32) {
-                const int gg = spx_div(idx, rcp_n), e = idx - gg * n;
+            // element idx = gg * n + e walks the six slots' terms 32 at a time: (gg, e) advance without divisions
+            int gg = spx_div(lane, 65536 / n + 1), e = lane - gg * n;
+            for (int idx = lane; idx < SPX_G * n; idx += 32, e += 32) {
+                while (e >= n) { e -= n; ++gg; }
                 if (!(act >> (5 * gg) & 1)) continue;
-                const int rr = spx_div(e, rcp_ww), j = e - rr * ww, r = r0 + rr;
+                int rr = 0, j = e;
+                if (j >= ww) { j -= ww; rr = 1; }                            // SPX_ROWS == 2
+                const int r = r0 + rr;
                 const float* sp = s_sub + gg * patch_stride + (r + 1) * pw + 1 + j;
                 const double m = s_mask[r * ww + j];
                 const double tgx = (double)__fsub_rn(sp[1], sp[-1]);

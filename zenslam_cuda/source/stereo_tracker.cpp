@@ -5,7 +5,7 @@
 
 #include "context.h"
 
-zenslam::cuda::stereo_tracker::stereo_tracker(const detection_options& detection, const tracking_options& tracking, const cv::Size image_size)
+zenslam::cuda::stereo_tracker::stereo_tracker(const detection_options& detection, const tracking_options& tracking, const cv::Size image_size, const int landmark_capacity)
 {
     if (detection.algorithm == detection_algorithm::SIMPLE || detection.feature_detector != feature_type::FAST || detection.descriptor != descriptor_type::ORB)
         throw std::invalid_argument("stereo_tracker: algorithm GRID or PARALLEL_GRID with feature FAST and descriptor ORB runs on the GPU");
@@ -27,6 +27,9 @@ zenslam::cuda::stereo_tracker::stereo_tracker(const detection_options& detection
     tracker_options.first_index    = static_cast<int>(keypoint::index_next);
     tracker_options.sequences      = 1;
     tracker_options.parallel_grid  = detection.algorithm == detection_algorithm::PARALLEL_GRID ? 1 : 0;
+    tracker_options.landmark_capacity       = landmark_capacity;
+    tracker_options.landmark_match_radius   = tracking.landmark_match_radius;
+    tracker_options.landmark_match_distance = tracking.landmark_match_distance;
 
     std::scoped_lock lock { detail::context_mutex() };
 
@@ -60,6 +63,41 @@ void zenslam::cuda::stereo_tracker::set_predictions(const int camera, const std:
     std::scoped_lock lock { detail::context_mutex() };
 
     detail::check(zs_tracker_set_predictions(_tracker, 0, camera, index.data(), xy.data(), static_cast<int>(index.size())), "zs_tracker_set_predictions");
+}
+
+auto zenslam::cuda::stereo_tracker::add_landmarks(const std::map<size_t, std::pair<cv::Point3d, cv::Mat>>& landmarks) -> int
+{
+    std::vector<int>    index { };
+    std::vector<double> xyz { };
+    std::vector<uchar>  descriptors { };
+
+    for (const auto& [key, landmark] : landmarks)      // ascending key order, as map::operator+=(const map&) iterates
+    {
+        const auto& [point, descriptor] = landmark;
+
+        CV_Assert(descriptor.type() == CV_8UC1 && descriptor.rows == 1 && descriptor.cols == 32);
+
+        index.push_back(static_cast<int>(key));
+        xyz.insert(xyz.end(), { point.x, point.y, point.z });
+        descriptors.insert(descriptors.end(), descriptor.ptr<uchar>(0), descriptor.ptr<uchar>(0) + 32);
+    }
+
+    int added = 0;
+
+    std::scoped_lock lock { detail::context_mutex() };
+
+    detail::check(zs_tracker_landmarks_add_host(_tracker, 0, index.data(), xyz.data(), descriptors.data(), static_cast<int>(index.size()), &added), "zs_tracker_landmarks_add_host");
+
+    return added;
+}
+
+void zenslam::cuda::stereo_tracker::set_camera_center(const cv::Point3d& center)
+{
+    const double xyz[3] = { center.x, center.y, center.z };
+
+    std::scoped_lock lock { detail::context_mutex() };
+
+    detail::check(zs_tracker_set_camera_center(_tracker, 0, xyz), "zs_tracker_set_camera_center");
 }
 
 namespace
