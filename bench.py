@@ -275,7 +275,7 @@ def measure_frontend(args, rank, world, local_rank, ctx, light=False):
     from zenslam_b200 import detection_options, slam_options, tracking_options
     from zenslam_b200.frontend import StereoFrontend
 
-    B, K, Wm = args.batch, args.steps, args.warmup
+    B, K, Wm = args.batch, args.steps, max(3, args.warmup)          # never fewer than three warm-up steps (timing rules)
     opts = slam_options(matcher="KNN", matcher_ratio=RATIO,
                         detection=detection_options(cell_size=CELL, fast_threshold=FAST_T, algorithm=CFG["alg"]),
                         tracking=tracking_options(klt_window_size=WIN, klt_max_level=MAX_LEVEL, klt_threshold=KLT_THR))
