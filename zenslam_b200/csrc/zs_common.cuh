@@ -29,12 +29,15 @@ struct zs_pyr_view {
     // 48x33x1 box; [2*l+1] = derivative plane as u32 elements with a 36x33x1 box (TMA box origins must be 16-byte
     // aligned): one box = the patch of one 32x32 window tile.  Coordinates are padded-plane coordinates.
     const void* tmaps;
+    // [3] TMA descriptors of the level-0 image plane as u32 elements for the grid-FAST strips (zs_fast.cu): boxes of
+    // (16 cells x 16 px + 16) x 16 rows, (4 x 32 + 16) x 32 rows and (64 + 16) x 64 rows; null when they could not be built
+    const void* fast_maps;
 };
 
 // A/B switches: environment variables read ONCE when a context is created -- never on a launch
 // path -- and again only when zs_context_reload_switches is called (the tests / benches flip them between runs).
 struct zs_switches {
-    bool fe_no_graph, klt_no_tma, klt_no_share, lk_no_cache, fast_v1, l2_no_tensor, l2_one_tile, fast_pretest, subpix_v1, klt_no_persist;
+    bool fe_no_graph, klt_no_tma, klt_no_share, lk_no_cache, fast_v1, l2_no_tensor, l2_one_tile, fast_pretest, subpix_v1, klt_no_persist, fast_no_tma;
     int pyr_force;               // 0 = by batch size, 1 = ZS_PYR_SPLIT, 2 = ZS_PYR_FUSED
     int hamming_splits, hamming_variant, l2_splits, l2_epi_groups;   // 0 = default
 };
@@ -71,7 +74,7 @@ struct zs_pyramid {
     zs_pyr_view v;
     void* block;        // one allocation backing every plane
     size_t block_bytes;
-    void* tmaps_dev;    // device copy of the CUtensorMap array
+    void* tmaps_dev;    // device copy of the CUtensorMap array (2 per level, then the 3 grid-FAST maps)
 };
 
 void zs_set_error(const char* fmt, ...);

@@ -26,10 +26,10 @@ zs_encode_tiled_fn zs_get_encode_tiled()
 static zs_status make_tensor_maps(zs_pyramid* p)
 {
     zs_pyr_view& v = p->v;
-    v.tmaps = nullptr; p->tmaps_dev = nullptr;
+    v.tmaps = nullptr; v.fast_maps = nullptr; p->tmaps_dev = nullptr;
     zs_encode_tiled_fn enc = zs_get_encode_tiled();
     if (!enc) { zs_set_error("cuTensorMapEncodeTiled is not available from this driver"); return ZS_ERR_CUDA; }
-    CUtensorMap maps[2 * ZS_MAX_LEVELS];
+    CUtensorMap maps[2 * ZS_MAX_LEVELS + 3];
     for (int l = 0; l < v.levels; ++l) {
         const cuuint64_t rows = (cuuint64_t)(v.h[l] + 2 * v.pad_y);
         const cuuint64_t dims[3] = { (cuuint64_t)v.pitch[l], rows, (cuuint64_t)v.slots };
@@ -47,10 +47,30 @@ static zs_status make_tensor_maps(zs_pyramid* p)
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { zs_set_error("cuTensorMapEncodeTiled(deriv level %d) failed: %d", l, (int)r); return ZS_ERR_CUDA; }
     }
-    ZS_CUDA(cudaMalloc(&p->tmaps_dev, sizeof(CUtensorMap) * 2 * ZS_MAX_LEVELS));
+    // grid-FAST strips of level 0 (zs_fast.cu, k_fast_grid_v2): the same plane as u32 elements, one box = one block's strip
+    // of cells plus 16 bytes of slack; kept behind the per-level maps
+    bool fast_ok = (v.pitch[0] % 16) == 0 && (v.slot_stride[0] % 16) == 0;
+    {
+        const cuuint64_t rows = (cuuint64_t)(v.h[0] + 2 * v.pad_y);
+        const cuuint64_t dims[3] = { (cuuint64_t)v.pitch[0] / 4, rows, (cuuint64_t)v.slots };
+        const cuuint64_t st[2] = { (cuuint64_t)v.pitch[0], (cuuint64_t)v.slot_stride[0] };
+        const cuuint32_t es[3] = { 1, 1, 1 };
+        const cuuint32_t boxes[3][3] = { { (16 * 16 + 16) / 4, 16, 1 }, { (4 * 32 + 16) / 4, 32, 1 }, { (64 + 16) / 4, 64, 1 } };
+        for (int k = 0; k < 3 && fast_ok; ++k) {
+            const CUresult r = enc(&maps[2 * ZS_MAX_LEVELS + k], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, v.img[0], dims, st, boxes[k], es,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) fast_ok = false;       // e.g. an image lower than a 64-row box: the kernels keep their vector loads
+        }
+    }
+    ZS_CUDA(cudaMalloc(&p->tmaps_dev, sizeof(CUtensorMap) * (2 * ZS_MAX_LEVELS + 3)));
     ZS_CUDA(cudaMemcpyAsync(p->tmaps_dev, maps, sizeof(CUtensorMap) * 2 * v.levels, cudaMemcpyHostToDevice, p->ctx->stream));
+    if (fast_ok)
+        ZS_CUDA(cudaMemcpyAsync((CUtensorMap*)p->tmaps_dev + 2 * ZS_MAX_LEVELS, maps + 2 * ZS_MAX_LEVELS, sizeof(CUtensorMap) * 3,
+                                cudaMemcpyHostToDevice, p->ctx->stream));
     ZS_CUDA(cudaStreamSynchronize(p->ctx->stream));        // `maps` is on this stack frame
     v.tmaps = p->tmaps_dev;
+    v.fast_maps = fast_ok ? (const void*)((CUtensorMap*)p->tmaps_dev + 2 * ZS_MAX_LEVELS) : nullptr;
     return ZS_OK;
 }
 
@@ -59,7 +79,7 @@ void zs_read_switches(zs_switches* s)
     auto on = [](const char* n) { return getenv(n) != nullptr; };
     auto num = [](const char* n) { const char* e = getenv(n); return e ? atoi(e) : 0; };
     s->fe_no_graph = on("ZS_FE_NO_GRAPH"); s->klt_no_tma = on("ZS_KLT_NO_TMA"); s->klt_no_share = on("ZS_KLT_NO_SHARE");
-    s->lk_no_cache = on("ZS_LK_NO_CACHE"); s->fast_v1 = on("ZS_FAST_V1"); s->subpix_v1 = on("ZS_SUBPIX_V1"); s->klt_no_persist = on("ZS_KLT_NO_PERSIST"); s->l2_no_tensor = on("ZS_L2_NO_TENSOR");
+    s->lk_no_cache = on("ZS_LK_NO_CACHE"); s->fast_v1 = on("ZS_FAST_V1"); s->subpix_v1 = on("ZS_SUBPIX_V1"); s->fast_no_tma = on("ZS_FAST_NO_TMA"); s->klt_no_persist = on("ZS_KLT_NO_PERSIST"); s->l2_no_tensor = on("ZS_L2_NO_TENSOR");
     s->l2_one_tile = on("ZS_L2_ONE_TILE"); s->fast_pretest = on("ZS_FAST_PRETEST");
     s->pyr_force = on("ZS_PYR_SPLIT") ? 1 : on("ZS_PYR_FUSED") ? 2 : 0;
     s->hamming_splits = num("ZS_HAMMING_SPLITS"); s->hamming_variant = num("ZS_HAMMING_VARIANT");

@@ -22,6 +22,7 @@ struct fast_grid_args {
     const uint8_t* occupied;     // [count][gh*gw] or null
     // per-cell candidates: [count][gh*gw]
     int* cand;                   // packed: (score << 20) | (y_in_cell << 10) | x_in_cell, or -1
+    const void* strip_map;       // k_fast_grid_v2: TMA descriptor of this variant's strip box, or null (vector loads)
 };
 
 // grid: (ceil(cells / FAST_WARPS), count); dynamic smem = FAST_WARPS * (tile + score tile + corner list)
@@ -157,6 +158,20 @@ __device__ __forceinline__ unsigned ring_window9(const unsigned p[16])
     return MAX9 ? __vminu2(u, w) : __vmaxu2(u, w);
 }
 
+// TMA: one elected thread asks for the block's whole strip -- CH rows of NC cells plus 16 bytes of slack, a (TW + 16) / 4 x CH x 1
+// box of u32 elements of the padded level-0 plane -- and every thread waits on the mbarrier; no load instruction, address
+// arithmetic or register is spent on staging.  (Columns beyond the image's last cell then hold plane bytes instead of zeros;
+// they only feed cells this block does not own.)
+__device__ __forceinline__ uint32_t fg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fg_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
 template <int CW, int CH, int NC>
 __global__ void __launch_bounds__(FG2_THREADS) k_fast_grid_v2(fast_grid_args a)
 {
@@ -167,13 +182,15 @@ __global__ void __launch_bounds__(FG2_THREADS) k_fast_grid_v2(fast_grid_args a)
     constexpr int ROWP = NC * PPR;         // pairs per strip row
     constexpr int TOTAL = ROWP * IH;
     static_assert(CW % 4 == 0 && CW >= 8 && CH >= 7, "cell shape");
-    extern __shared__ __align__(16) uint8_t fsm[];
-    uint32_t* sE = (uint32_t*)fsm;                                  // [CH][PW]
+    constexpr int RP = TW + 16;
+    static_assert((CH * RP) % 128 == 0, "raw strip keeps the arrays behind it aligned");
+    extern __shared__ __align__(128) uint8_t fsm[];
+    __shared__ __align__(8) uint64_t s_bar;
+    uint8_t* sRaw = fsm;                                            // raw strip [CH][TW + 16]: the TMA box (128-byte aligned)
+    uint32_t* sE = (uint32_t*)(sRaw + CH * RP);                     // [CH][PW]
     uint32_t* sO = sE + CH * PW;                                    // [CH][PW]
     uint8_t* sS = (uint8_t*)(sO + CH * PW);                         // score tile [CH][TW]
     int* sBest = (int*)(sS + CH * TW);                              // [NC]
-    uint8_t* sRaw = (uint8_t*)(sBest + ((NC + 3) & ~3));     // raw strip [CH][TW + 16], 16-byte aligned (uint4 staging)
-    constexpr int RP = TW + 16;
 
     const int img = blockIdx.z, gy = blockIdx.y, cell0 = blockIdx.x * NC;
     const int ncell = min(NC, a.gw - cell0);
@@ -183,16 +200,31 @@ __global__ void __launch_bounds__(FG2_THREADS) k_fast_grid_v2(fast_grid_args a)
     const uint8_t* src = a.v.img[0] + (size_t)slot * a.v.slot_stride[0] + (size_t)(a.v.pad_y + gy * CH) * pitch + a.v.pad_x + cell0 * CW;
     const int valid_w = ncell * CW;               // pixels of this strip that belong to cells
 
-    // ---- stage the raw strip: 16-byte loads (interiors are 16-byte aligned: pad_x, pitch and CW*NC are multiples of 16)
-    for (int i = tid; i < CH * (RP / 16); i += FG2_THREADS) {
-        const int r = i / (RP / 16), c = (i - r * (RP / 16)) * 16;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (c < valid_w) v = *(const uint4*)(src + (size_t)r * pitch + c);
-        *(uint4*)(sRaw + r * RP + c) = v;
+    // ---- stage the raw strip: one TMA box, or 16-byte loads (interiors are 16-byte aligned: pad_x, pitch and CW*NC are
+    // multiples of 16)
+    const bool tma = a.strip_map != nullptr;
+    if (tma) {
+        const uint32_t bar = fg_smem_u32(&s_bar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(CH * RP) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(fg_smem_u32(sRaw)), "l"(a.strip_map), "r"((a.v.pad_x + cell0 * CW) >> 2), "r"(a.v.pad_y + gy * CH),
+                           "r"(slot), "r"(bar) : "memory");
+        }
+    } else {
+        for (int i = tid; i < CH * (RP / 16); i += FG2_THREADS) {
+            const int r = i / (RP / 16), c = (i - r * (RP / 16)) * 16;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (c < valid_w) v = *(const uint4*)(src + (size_t)r * pitch + c);
+            *(uint4*)(sRaw + r * RP + c) = v;
+        }
     }
     for (int i = tid; i < CH * TW / 4; i += FG2_THREADS) ((uint32_t*)sS)[i] = 0;
     if (tid < NC) sBest[tid] = 0;
-    __syncthreads();
+    __syncthreads();                                               // (also orders the barrier's initialisation before the waits)
+    if (tma) fg_mbar_wait(fg_smem_u32(&s_bar), 0);
     // ---- expand into the pair planes: word j of E = (p[2j], p[2j+1]), of O = (p[2j+1], p[2j+2]) as u16x2
     for (int i = tid; i < CH * (TW / 4 + 1); i += FG2_THREADS) {
         const int r = i / (TW / 4 + 1), q = i - r * (TW / 4 + 1);
@@ -327,17 +359,21 @@ extern "C" zs_status zs_fast_grid_detect(zs_context* ctx, const zs_pyramid* p, i
     if (st != ZS_OK) return st;
     fast_grid_args a;
     a.v = p->v; a.first = first; a.count = count; a.cw = cell_w; a.ch = cell_h; a.gw = gw; a.gh = gh;
-    a.threshold = threshold; a.occupied = d_occupied; a.cand = (int*)scratch;
+    a.threshold = threshold; a.occupied = d_occupied; a.cand = (int*)scratch; a.strip_map = nullptr;
     if (!ctx->sw.fast_v1 && ((cell_w == 16 && cell_h == 16) || (cell_w == 32 && cell_h == 32) || (cell_w == 64 && cell_h == 64))) {
+        const char* maps = (ctx->sw.fast_no_tma || !p->v.fast_maps) ? nullptr : (const char*)p->v.fast_maps;
         if (cell_w == 16) {
+            a.strip_map = maps;
             const size_t smem = fast_grid_v2_smem<16, 16, 16>();
             k_fast_grid_v2<16, 16, 16><<<dim3(zs_div_up(gw, 16), gh, count), FG2_THREADS, smem, ctx->stream>>>(a);
         } else if (cell_w == 64) {
             // the shipped configuration (tumvi.yaml:38: cell_size [64, 64]): one 64x64 cell per block, 28 KB of planes
+            a.strip_map = maps ? maps + 2 * 128 : nullptr;
             const size_t smem = fast_grid_v2_smem<64, 64, 1>();
             k_fast_grid_v2<64, 64, 1><<<dim3(gw, gh, count), FG2_THREADS, smem, ctx->stream>>>(a);
         } else {
             // 4 cells (128 px) per block keep the pair planes at 26 KB, so 8 blocks fit an SM instead of 2
+            a.strip_map = maps ? maps + 1 * 128 : nullptr;
             const size_t smem = fast_grid_v2_smem<32, 32, 4>();
             k_fast_grid_v2<32, 32, 4><<<dim3(zs_div_up(gw, 4), gh, count), FG2_THREADS, smem, ctx->stream>>>(a);
         }
