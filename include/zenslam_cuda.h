@@ -341,7 +341,10 @@ ZS_API zs_status zs_match_keypoints3d_host(zs_context* ctx, const int* landmark_
  * index in both cameras; the matching by index is host bookkeeping).  P0 / P1: 3x4 projection matrices, F: 3x3
  * fundamental matrix (calibration.fundamental_matrix[0]; NULL = no epipolar filter), t: translation of camera 1 in
  * camera 0 -- all HOST pointers, row-major doubles.  Outputs: xyz [n][3] doubles (every pair, like points3d_all),
- * keep [n] (the pairs that survive every gate), optional diag [n][4] = epipolar error, reprojection errors, angle. */
+ * keep [n] (the pairs that survive every gate), optional diag [n][4] = epipolar error, reprojection errors, angle.
+ * Parity is TOLERANCE-based here, unlike the integer rows of the path: FP64 one-sided Jacobi SVD on the device vs OpenCV's on
+ * the host -- points within 1e-5 relative of cv::triangulatePoints (>= 98 % identical floats), keep flags identical except
+ * within 1e-6 of a gate threshold (tests/test_gpu_frontend.py::test_triangulator_mirror_tolerance_1e5_relative). */
 typedef struct {
     int filter_epipolar;             /* triangulation.filter_epipolar */
     double epipolar_threshold;       /* triangulation.epipolar_threshold (0.01) */

@@ -727,10 +727,12 @@ def test_frontend_full_size_configs(ctx, w, h, cell, name):
     assert np.abs(flow + d.astype(np.float32)).max() < 0.05
 
 
-def test_triangulator_mirror(ctx, golden):
+def test_triangulator_mirror_tolerance_1e5_relative(ctx, golden):
     """SURVEY 8(f3): epipolar gate + cv::triangulatePoints + reprojection/depth/parallax gates on the device, against the
     cv2 fixture and the oracle.  Floating point: the 3-D points must agree to float rounding (they are ratios of
-    float-rounded SVD outputs), the keep decisions everywhere except within 1e-6 of a threshold."""
+    float-rounded SVD outputs), the keep decisions everywhere except within 1e-6 of a threshold.
+    TOLERANCE (this is the one tolerance-based row of the path): 3-D points within 1e-5 relative of cv::triangulatePoints,
+    >= 98 % of them the very same floats; gate inputs within rtol 1e-5; keep flags identical outside a 1e-6 margin."""
     from zenslam_b200 import keypoint
     from zenslam_b200.triangulation import triangulation_options, triangulator
     g = golden("triangulate")
