@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(SUBPIX_WARPS * 32) k_corner_subpix(subpix_args
 //   * the getRectSubPix patch: inside the image the CPU's row recurrence has no carried dependency -- prev_j is a function
 //     of t_{j-1} alone -- so every patch pixel is computed on its own from four image pixels (same operations, same
 //     roundings);
-//   * the gradient products (gxx, gxy, gyy), two window rows of all six points at a time, parked in shared memory; the
-//     chain lanes read them back in raster order, lanes 3 and 4 forming gxx px + gxy py / gxy px + gyy py as v1 does.
+//   * the five terms of every window pixel (gxx, gxy, gyy, gxx px + gxy py, gxy px + gyy py -- the very expressions v1
+//     evaluates), two window rows of all six points at a time, parked in shared memory (row stride odd, so that the thirty
+//     chain lanes spread over the banks); the chain lanes then only load and add, in raster order.
 // A point slot that has converged takes the warp's next point at the next iteration (warp-local queue over a contiguous
 // range of (image, corner) items), so lanes do not idle behind the slowest of six.  Results are bit-identical to v1.
 // ------------------------------------------------------------------------------------------------------
