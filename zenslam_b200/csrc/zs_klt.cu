@@ -664,11 +664,223 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
 // grid: (cap, jobs); block = one warp per window tile; dynamic smem = tiles * KLT4_WARP_BYTES
 // passes: 0 = forward (one or two targets), 1 = backward of target 0, 2 = backward of target 1 (fb only); one
 // inlined instance of the tracker serves all passes (keeps the code inside the instruction cache).
+// ------------------------------------------------------------------------------------------------------
+// v5: TWO window tiles per warp (63x63 windows: 2 x 2 tiles of 32 x 32 = two warps per feature, warp w owning the tile
+// row w).  In v4 every one of the four warps of a feature repeats the scalar part of each Gauss-Newton step -- bounds and
+// refetch tests, weights, reductions, the 2x2 solve, the convergence tests: 38 % of an iteration's instructions -- on
+// identical numbers.  With two tiles per warp that part runs twice per feature instead of four times, the two tiles'
+// pixel loops are independent instruction streams the scheduler can interleave, and the two tiles' lane partials share
+// their REDUX (the 16-bit halves of two partials still cannot overflow).  The price is registers: both tiles' gradient
+// templates live in registers (128 of them), so a CTA of two warps needs ~200 registers per thread and five CTAs fit an SM.
+// Arithmetic and results are identical to v4.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long warp_sum_exact2(int pa, int pb)
+{
+    const int lo = (pa & 0xffff) + (pb & 0xffff), hi = (pa >> 16) + (pb >> 16);
+    const int slo = __reduce_add_sync(0xffffffffu, lo);
+    const int shi = __reduce_add_sync(0xffffffffu, hi);
+    return ((long long)shi << 16) + (long long)slo;
+}
+
 template <int WW, int WH>
-__device__ __forceinline__ void klt4_item(const klt_args& a, int job, int i, int warp, int lane, uint8_t* sJ, uint8_t* sD, uint32_t bar,
+__device__ __forceinline__ void lk_track_point_v5(const klt_args& a, int slot_i, int slot_j0, int slot_j1, int ntgt,
+                                                  float2 prev, float2 init, bool use_init, int warp, int lane, uint8_t* tiles,
+                                                  uint32_t bar, uint32_t& parity, long long* red, int& phase,
+                                                  lk_state& t0, lk_state& t1, float& err)
+{
+    typedef klt4_cfg<WW, WH> cfg;
+    static_assert(cfg::TX == 2 && cfg::TY == 2, "two tiles per warp: 2 x 2 tile windows");
+    constexpr int TPW = 2, NW = 2;                           // tiles per warp (the tile row of warp `warp`), warps per CTA
+    constexpr int TILE_BYTES = KLT4_SJ_BYTES + KLT4_SD_BYTES;
+    const zs_pyr_view& v = a.v;
+    const float hwx = (float)(WW - 1) * 0.5f, hwy = (float)(WH - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (float)(1 << 20);
+    t0.status = 1; t1.status = 1; t0.outx = t0.outy = t1.outx = t1.outy = 0.f; err = 0.f;
+    const int top = min(a.max_level, v.levels - 1);
+    const int k = lane & 3, g = lane >> 2;
+    const int ty = warp;                                     // tile row; tile column = t (compile-time in the unrolled loops)
+    const int th = (ty == cfg::TY - 1) ? cfg::LH : 32;
+    const uint32_t tiles_a = smem_u32(tiles);
+    const char* maps = (const char*)v.tmaps;
+    const uint32_t* jbase = (const uint32_t*)tiles + g * KLT4_JP + 2 * k;
+    const uint32_t* dbase = (const uint32_t*)(tiles + KLT4_SJ_BYTES) + g * KLT4_DP + 8 * k;
+
+    for (int level = top; level >= 0; --level) {
+        const int cols = v.w[level], rows = v.h[level];
+        const float scale = 1.f / (float)(1 << level);
+        float px = __fmul_rn(prev.x, scale), py = __fmul_rn(prev.y, scale);
+        if (level == top) {
+            if (use_init) { t0.outx = __fmul_rn(init.x, scale); t0.outy = __fmul_rn(init.y, scale); }
+            else { t0.outx = px; t0.outy = py; }
+            t1.outx = px; t1.outy = py;
+        } else {
+            t0.outx = __fmul_rn(t0.outx, 2.f); t0.outy = __fmul_rn(t0.outy, 2.f);
+            t1.outx = __fmul_rn(t1.outx, 2.f); t1.outy = __fmul_rn(t1.outy, 2.f);
+        }
+        px = __fsub_rn(px, hwx); py = __fsub_rn(py, hwy);
+        const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
+        if (ipx < -WW || ipx >= cols || ipy < -WH || ipy >= rows) {
+            if (level == 0) { t0.status = 0; t1.status = 0; err = 0.f; }
+            continue;
+        }
+        int w00, w01, w10, w11;
+        lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
+
+        // ---- fetch the I patches (into the J buffers) and the derivative patches of this warp's two tiles
+        const int gx = v.pad_x + ipx, gy = v.pad_y + ipy + 32 * ty;          // tile column t adds 32 t to gx: same alignment residue
+        __syncwarp();
+        if (lane == 0) {
+            mbar_expect_tx(bar, TPW * (48 + 36 * 4) * KLT4_ROWS);
+#pragma unroll
+            for (int t = 0; t < TPW; ++t) {
+                tma_load_3d(tiles_a + t * TILE_BYTES, maps + (size_t)(2 * level) * 128, (gx + 32 * t) & ~15, gy, slot_i, bar);
+                tma_load_3d(tiles_a + t * TILE_BYTES + KLT4_SJ_BYTES, maps + (size_t)(2 * level + 1) * 128, (gx + 32 * t) & ~3, gy, slot_i, bar);
+            }
+        }
+        mbar_wait(bar, parity); parity ^= 1;
+
+        // ---- templates in registers: 2 tiles x 4 row bands x 8 pixels per lane
+        int Ix[TPW][4][8], Iy[TPW][4][8];
+        long long sT[5];
+        {
+            int pA11[TPW], pA12[TPW], pA22[TPW], pc1[TPW], pc2[TPW];
+            const int wt = pack_s16x2(w00, w01), wb = pack_s16x2(w10, w11);
+            const int sh = (gx & 3) * 8;
+#pragma unroll
+            for (int t = 0; t < TPW; ++t) {
+                pA11[t] = pA12[t] = pA22[t] = pc1[t] = pc2[t] = 0;
+                const uint32_t* jw = jbase + t * (TILE_BYTES / 4) + ((gx & 15) >> 2);
+                const uint32_t* dw = dbase + t * (TILE_BYTES / 4) + (gx & 3);
+                constexpr int dummy = 0; (void)dummy;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const row8 ra = load_row8(jw + j * 8 * KLT4_JP, sh), rb = load_row8(jw + (j * 8 + 1) * KLT4_JP, sh);
+                    int tx_[9], ty_[9], bx[9], by[9];
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const unsigned dt = dw[j * 8 * KLT4_DP + q], db = dw[(j * 8 + 1) * KLT4_DP + q];
+                        tx_[q] = (int)(short)(dt & 0xffff); ty_[q] = (int)dt >> 16;
+                        bx[q] = (int)(short)(db & 0xffff); by[q] = (int)db >> 16;
+                    }
+                    const bool row_masked = (8 * j + 7 >= cfg::LH) && (8 * j + g >= th);
+                    int iv[8];
+                    iv[0] = sample8<0>(wt, wb, ra, rb); iv[1] = sample8<1>(wt, wb, ra, rb); iv[2] = sample8<2>(wt, wb, ra, rb);
+                    iv[3] = sample8<3>(wt, wb, ra, rb); iv[4] = sample8<4>(wt, wb, ra, rb); iv[5] = sample8<5>(wt, wb, ra, rb);
+                    iv[6] = sample8<6>(wt, wb, ra, rb); iv[7] = sample8<7>(wt, wb, ra, rb);
+#pragma unroll
+                    for (int pp = 0; pp < 8; ++pp) {
+                        int ixv = (tx_[pp] * w00 + tx_[pp + 1] * w01 + bx[pp] * w10 + bx[pp + 1] * w11 + (1 << 13)) >> 14;
+                        int iyv = (ty_[pp] * w00 + ty_[pp + 1] * w01 + by[pp] * w10 + by[pp + 1] * w11 + (1 << 13)) >> 14;
+                        // tile column t is the last one for t == 1: its column 31 (pixel 7 of k == 3) lies outside a 63-wide window
+                        const bool col_masked = (t == cfg::TX - 1) && (24 + pp >= cfg::LW) && (8 * k + pp >= cfg::LW);
+                        if ((8 * j + 7 >= cfg::LH) || ((t == cfg::TX - 1) && (24 + pp >= cfg::LW))) {
+                            if (row_masked || col_masked) { ixv = 0; iyv = 0; }
+                        }
+                        Ix[t][j][pp] = ixv; Iy[t][j][pp] = iyv;
+                        pA11[t] += ixv * ixv; pA12[t] += ixv * iyv; pA22[t] += iyv * iyv;
+                        pc1[t] += iv[pp] * ixv; pc2[t] += iv[pp] * iyv;
+                    }
+                }
+            }
+            sT[0] = warp_sum_exact2(pA11[0], pA11[1]); sT[1] = warp_sum_exact2(pA12[0], pA12[1]); sT[2] = warp_sum_exact2(pA22[0], pA22[1]);
+            sT[3] = warp_sum_exact2(pc1[0], pc1[1]); sT[4] = warp_sum_exact2(pc2[0], pc2[1]);
+        }
+        cta_sum<NW, 5>(sT, red, phase, warp, lane);
+        const long long sc1 = sT[3], sc2 = sT[4];
+        const float A11 = __fmul_rn(__ll2float_rn(sT[0]), FLT_SCALE), A12 = __fmul_rn(__ll2float_rn(sT[1]), FLT_SCALE),
+                    A22 = __fmul_rn(__ll2float_rn(sT[2]), FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dA = __fsub_rn(A11, A22);
+        const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * WW * WH));
+        if (a.flags & ZS_LK_GET_MIN_EIGENVALS) err = minEig;
+        if ((double)minEig < a.min_eig || D < 1.1920929e-07f) {
+            if (level == 0) { t0.status = 0; t1.status = 0; }
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+
+#pragma unroll 1
+        for (int tg = 0; tg < ntgt; ++tg) {
+            const int slot_j = tg ? slot_j1 : slot_j0;
+            float outx = tg ? t1.outx : t0.outx, outy = tg ? t1.outy : t0.outy;
+            int status = 1;
+            float nx = __fsub_rn(outx, hwx), ny = __fsub_rn(outy, hwy);
+            float pdx = 0.f, pdy = 0.f;
+            int cur_x0 = 0x7fffffff, cur_y = 0x7fffffff;       // origin of the J patches now in shared memory (tile column 0)
+            for (int it = 0; it < a.max_iters; ++it) {
+                const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
+                if (inx < -WW || inx >= cols || iny < -WH || iny >= rows) {
+                    status = 0;
+                    break;
+                }
+                const int jx = v.pad_x + inx, jy = v.pad_y + iny + 32 * ty;
+                if ((jx & ~15) != cur_x0 || jy != cur_y) {
+                    __syncwarp();                                  // every lane is done with the previous patches
+                    cur_x0 = jx & ~15; cur_y = jy;
+                    if (lane == 0) {
+                        mbar_expect_tx(bar, TPW * 48 * KLT4_ROWS);
+#pragma unroll
+                        for (int t = 0; t < TPW; ++t)
+                            tma_load_3d(tiles_a + t * TILE_BYTES, maps + (size_t)(2 * level) * 128, cur_x0 + 32 * t, cur_y, slot_j, bar);
+                    }
+                    mbar_wait(bar, parity); parity ^= 1;
+                }
+                lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
+                const int wt = pack_s16x2(w00, w01), wb = pack_s16x2(w10, w11);
+                const int sh = (jx & 3) * 8;
+                int pb1[TPW], pb2[TPW];
+#pragma unroll
+                for (int t = 0; t < TPW; ++t) {
+                    pb1[t] = 0; pb2[t] = 0;
+                    const uint32_t* jw = jbase + t * (TILE_BYTES / 4) + ((jx & 15) >> 2);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const row8 ra = load_row8(jw + j * 8 * KLT4_JP, sh), rb = load_row8(jw + (j * 8 + 1) * KLT4_JP, sh);
+                        int jv;
+                        jv = sample8<0>(wt, wb, ra, rb); pb1[t] += jv * Ix[t][j][0]; pb2[t] += jv * Iy[t][j][0];
+                        jv = sample8<1>(wt, wb, ra, rb); pb1[t] += jv * Ix[t][j][1]; pb2[t] += jv * Iy[t][j][1];
+                        jv = sample8<2>(wt, wb, ra, rb); pb1[t] += jv * Ix[t][j][2]; pb2[t] += jv * Iy[t][j][2];
+                        jv = sample8<3>(wt, wb, ra, rb); pb1[t] += jv * Ix[t][j][3]; pb2[t] += jv * Iy[t][j][3];
+                        jv = sample8<4>(wt, wb, ra, rb); pb1[t] += jv * Ix[t][j][4]; pb2[t] += jv * Iy[t][j][4];
+                        jv = sample8<5>(wt, wb, ra, rb); pb1[t] += jv * Ix[t][j][5]; pb2[t] += jv * Iy[t][j][5];
+                        jv = sample8<6>(wt, wb, ra, rb); pb1[t] += jv * Ix[t][j][6]; pb2[t] += jv * Iy[t][j][6];
+                        jv = sample8<7>(wt, wb, ra, rb); pb1[t] += jv * Ix[t][j][7]; pb2[t] += jv * Iy[t][j][7];
+                    }
+                }
+                long long sB[2] = { warp_sum_exact2(pb1[0], pb1[1]), warp_sum_exact2(pb2[0], pb2[1]) };
+                cta_sum<NW, 2>(sB, red, phase, warp, lane);
+                const long long sb1 = sB[0] - sc1, sb2 = sB[1] - sc2;
+                const float b1 = __fmul_rn(__ll2float_rn(sb1), FLT_SCALE), b2 = __fmul_rn(__ll2float_rn(sb2), FLT_SCALE);
+                const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+                const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+                nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
+                outx = __fadd_rn(nx, hwx); outy = __fadd_rn(ny, hwy);
+                const float ss = fmaf(dx, dx, __fmul_rn(dy, dy));
+                bool conv = ss <= a.eps2_lo;
+                if (!conv && ss < a.eps2_hi) conv = (double)dx * (double)dx + (double)dy * (double)dy <= a.eps2;
+                if (conv) break;
+                if (it > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f) {
+                    outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f)); outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
+                    break;
+                }
+                pdx = dx; pdy = dy;
+            }
+            if (tg) { t1.outx = outx; t1.outy = outy; if (level == 0 && !status) t1.status = 0; }
+            else { t0.outx = outx; t0.outy = outy; if (level == 0 && !status) t0.status = 0; }
+        }
+    }
+}
+
+
+// TPW = window tiles per warp: 1 (one warp per tile, lk_track_point_v4) or 2 (lk_track_point_v5); sJ = the warp's first tile
+// buffer, scratch = its 128-byte bookkeeping line (which also holds the mbarrier)
+template <int WW, int WH, int TPW>
+__device__ __forceinline__ void klt4_item(const klt_args& a, int job, int i, int warp, int lane, uint8_t* sJ, uint8_t* scratch, uint32_t bar,
                                           uint32_t& parity, long long* s_red, int& phase)
 {
     typedef klt4_cfg<WW, WH> cfg;
+    uint8_t* sD = sJ + KLT4_SJ_BYTES;
     const int slot_src = a.prev_slot[job];
     if (slot_src < 0) return;                                  // job folded into another job's second target
     const int in_row = a.pts_row ? a.pts_row[job] : job;
@@ -677,7 +889,7 @@ __device__ __forceinline__ void klt4_item(const klt_args& a, int job, int i, int
     // every lane with the same data, read back as broadcasts): it would otherwise sit in registers across the
     // whole inlined tracker and push the kernel past 128 registers (4 CTAs per SM).
     //   w[4] slot_src  w[5] slot_t0  w[6] slot_t1  w[7] ntgt  w[8..9] p0  w[10..12] f0  w[13..15] f1  w[16] job1
-    volatile int* w = (volatile int*)(sD + KLT4_SD_BYTES);
+    volatile int* w = (volatile int*)scratch;
     volatile float* wf = (volatile float*)w;
     __syncwarp();
     {
@@ -688,7 +900,7 @@ __device__ __forceinline__ void klt4_item(const klt_args& a, int job, int i, int
     }
     __syncwarp();
     const bool use_init = (a.flags & ZS_LK_USE_INITIAL_FLOW) != 0;
-    const bool writer = lane == 0 && (cfg::NT == 1 || warp == 0);
+    const bool writer = lane == 0 && (cfg::NT / TPW == 1 || warp == 0);
     const int passes = a.fb ? 1 + w[7] : 1;
 #pragma unroll 1
     for (int pass = 0; pass < passes; ++pass) {
@@ -708,8 +920,12 @@ __device__ __forceinline__ void klt4_item(const klt_args& a, int job, int i, int
         const bool ui = use_init && pass == 0;
         if (ui) init = a.next_pts[(size_t)job * a.cap + i];
         lk_state r0, r1; float err;
-        lk_track_point_v4<WW, WH>(a, si, sj0, sj1, pass == 0 ? w[7] : 1, from, init, ui, warp, lane, sJ, sD, bar, parity, s_red,
-                                  phase, r0, r1, err);
+        if constexpr (TPW == 1)
+            lk_track_point_v4<WW, WH>(a, si, sj0, sj1, pass == 0 ? w[7] : 1, from, init, ui, warp, lane, sJ, sD, bar, parity, s_red,
+                                      phase, r0, r1, err);
+        else
+            lk_track_point_v5<WW, WH>(a, si, sj0, sj1, pass == 0 ? w[7] : 1, from, init, ui, warp, lane, sJ, bar, parity, s_red,
+                                      phase, r0, r1, err);
         if (pass == 0) {
             __syncwarp();
             wf[10] = r0.outx; wf[11] = r0.outy; w[12] = r0.status; wf[13] = r1.outx; wf[14] = r1.outy; w[15] = r1.status;
@@ -734,17 +950,19 @@ __device__ __forceinline__ void klt4_item(const klt_args& a, int job, int i, int
 // sm_count x MINB CTAs that take items from an atomic counter, point index fastest (neighbouring CTAs then work on the same
 // image pair): no CTA relaunch gap between the ~160 items a CTA slot serves per 128-frame batch, no empty CTAs for the
 // points beyond an image's corner count.
-template <int WW, int WH, int MINB>
-__global__ void __launch_bounds__(klt4_cfg<WW, WH>::NT * 32, MINB) k_klt_track_v4(klt_args a)
+template <int WW, int WH, int MINB, int TPW = 1>
+__global__ void __launch_bounds__(klt4_cfg<WW, WH>::NT / TPW * 32, MINB) k_klt_track_v4(klt_args a)
 {
     typedef klt4_cfg<WW, WH> cfg;
+    constexpr int NW = cfg::NT / TPW;                          // warps per CTA
+    constexpr int WARP_BYTES = TPW * (KLT4_SJ_BYTES + KLT4_SD_BYTES) + 128;
     extern __shared__ __align__(128) uint8_t smem3[];
-    __shared__ long long s_red[cfg::NT > 1 ? 2 * cfg::NT * 5 : 1];
+    __shared__ long long s_red[NW > 1 ? 2 * cfg::NT * 5 : 1];
     __shared__ int s_item;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* sJ = smem3 + (size_t)warp * KLT4_WARP_BYTES;
-    uint8_t* sD = sJ + KLT4_SJ_BYTES;
-    const uint32_t bar = smem_u32(sD + KLT4_SD_BYTES);
+    uint8_t* sJ = smem3 + (size_t)warp * WARP_BYTES;
+    uint8_t* scratch = sJ + TPW * (KLT4_SJ_BYTES + KLT4_SD_BYTES);
+    const uint32_t bar = smem_u32(scratch);
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -757,7 +975,7 @@ __global__ void __launch_bounds__(klt4_cfg<WW, WH>::NT * 32, MINB) k_klt_track_v
         int jl = blockIdx.y, i = blockIdx.x;
         if (persistent) {
             int item;
-            if (cfg::NT == 1) {
+            if (NW == 1) {
                 item = 0;
                 if (lane == 0) item = atomicAdd(a.work, 1);
                 item = __shfl_sync(0xffffffffu, item, 0);
@@ -770,7 +988,7 @@ __global__ void __launch_bounds__(klt4_cfg<WW, WH>::NT * 32, MINB) k_klt_track_v
             if (item >= a.n_items) break;
             jl = item / a.cap; i = item - jl * a.cap;
         }
-        klt4_item<WW, WH>(a, a.job_list ? a.job_list[jl] : jl, i, warp, lane, sJ, sD, bar, parity, s_red, phase);
+        klt4_item<WW, WH, TPW>(a, a.job_list ? a.job_list[jl] : jl, i, warp, lane, sJ, scratch, bar, parity, s_red, phase);
         if (!persistent) break;
     }
 }
@@ -863,21 +1081,30 @@ zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_
             a.n_items = (int)items;
             ZS_CUDA(cudaMemsetAsync(a.work, 0, sizeof(int), ctx->stream));
         }
-#define KLT4_LAUNCH(W_, H_, MB_)                                                                                               \
+#define KLT4_LAUNCH_T(W_, H_, MB_, TPW_)                                                                                       \
         do {                                                                                                                   \
-            const size_t sm = (size_t)klt4_cfg<W_, H_>::NT * KLT4_WARP_BYTES;                                                  \
+            const int nw = klt4_cfg<W_, H_>::NT / TPW_;                                                                         \
+            const size_t sm = (size_t)nw * (TPW_ * (KLT4_SJ_BYTES + KLT4_SD_BYTES) + 128);                                     \
             const long long resident = (long long)ctx->sm_count * MB_;                                                         \
             const dim3 grid = (persist && items > resident) ? dim3((unsigned)resident, 1) : dim3(cap, listed);                 \
             if (!(persist && items > resident)) a.work = nullptr;                                                              \
-            k_klt_track_v4<W_, H_, MB_><<<grid, klt4_cfg<W_, H_>::NT * 32, sm, ctx->stream>>>(a);                              \
+            if (sm > 48 * 1024) ZS_CUDA(cudaFuncSetAttribute(k_klt_track_v4<W_, H_, MB_, TPW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+            k_klt_track_v4<W_, H_, MB_, TPW_><<<grid, nw * 32, sm, ctx->stream>>>(a);                                           \
         } while (0)
+#define KLT4_LAUNCH(W_, H_, MB_) KLT4_LAUNCH_T(W_, H_, MB_, 1)
         if (a.win_w == 31) KLT4_LAUNCH(31, 31, 24);
-        // four-warp CTAs: 4 per SM = 128 registers, no spills: 16.4 ms per 128-frame TUMVI batch (1024x1024, 225 points per
-        // image); 5 per SM (96 registers, 240 B of spills): 16.6 ms; 6 (80 registers, 324 B): 20.1 ms
+        // (four-warp CTAs: 4 per SM = 128 registers: 16.4 - 16.5 ms; 5 per SM (96 registers, 240 B of spills): 16.6 ms; 6 (80
+        // registers, 324 B): 20.1 ms)
+        // 63x63 (tumvi.yaml:45): two tiles per warp, two-warp CTAs, six per SM (lk_track_point_v5; 168 registers, 240 B of
+        // spills): 15.8 ms per 128-frame TUMVI batch (1024x1024, 225 points per image).  Measured alternatives: 4 CTAs per SM
+        // (224 registers, no spills) 16.3 ms, 5: 17.5 ms, 7 / 8 (128 registers, 468 B of spills): 20.5 / 19.1 ms; the four-warp
+        // form (ZS_KLT63_FOUR_WARPS; one tile per warp, 128 registers, 4 CTAs per SM): 16.5 ms
+        else if (a.win_w == 63 && !ctx->sw.klt63_four_warps) KLT4_LAUNCH_T(63, 63, 6, 2);
         else if (a.win_w == 63) KLT4_LAUNCH(63, 63, 4);
         else if (a.win_w == 21) KLT4_LAUNCH(21, 21, 24);
         else KLT4_LAUNCH(15, 15, 24);
 #undef KLT4_LAUNCH
+#undef KLT4_LAUNCH_T
         ZS_LAUNCH_CHECK(ctx);
         return ZS_OK;
     }
