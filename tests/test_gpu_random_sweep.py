@@ -79,9 +79,11 @@ def test_detect_describe_match_random(ctx, seed):
 
 
 @pytest.mark.parametrize("seed", range(24))
-def test_klt_random(ctx, seed):
+def test_klt_random(ctx, switches, seed):
     from zenslam_b200 import LK_GET_MIN_EIGENVALS, LK_USE_INITIAL_FLOW
     from zenslam_b200.runtime import LK, Pyramid, klt_track
+    if seed % 4 == 3:
+        switches.set(ctx, "ZS_KLT_PERSIST_MIN", 1)                       # the persistent launch form on a small problem
     rng = np.random.default_rng(200 + seed)
     win = [(31, 31), (21, 21), (15, 15), (9, 9), (31, 31), (25, 13), (31, 31), (41, 41)][seed % 8]
     ml = int(rng.integers(0, 5))
@@ -109,6 +111,51 @@ def test_klt_random(ctx, seed):
     ob, osb, _ = oracle.lk_track(PB, PA, o1, None, win, ml)
     assert np.array_equal(st[:n], os_) and np.array_equal(p1[:n], o1) and np.array_equal(err[:n], oe), (win, ml, w, h)
     assert np.array_equal(keep[:n].astype(bool), oracle.fb_check(pts, ob, os_, osb, 1.0))
+    p.close()
+
+
+@pytest.mark.parametrize("form", ["two_tiles", "four_warps", "two_tiles_persistent", "four_warps_persistent"])
+@pytest.mark.parametrize("seed", range(6))
+def test_klt_random_63(ctx, switches, seed, form):
+    """63 x 63 windows (tumvi.yaml:45) on random frames against the oracle, through both tiled forms of the tracker -- two
+    tiles per warp (the default) and one tile per warp (ZS_KLT63_FOUR_WARPS) -- each also in its persistent launch form: frames
+    smaller than the window at the coarse levels, points outside the frame, integer positions, initial flow, several jobs in
+    one launch (so that the persistent form has items to distribute)."""
+    from zenslam_b200 import LK_GET_MIN_EIGENVALS, LK_USE_INITIAL_FLOW
+    from zenslam_b200.runtime import LK, Pyramid, klt_track
+    if form.startswith("four_warps"):
+        switches.set(ctx, "ZS_KLT63_FOUR_WARPS")
+    if form.endswith("persistent"):
+        switches.set(ctx, "ZS_KLT_PERSIST_MIN", 1)                       # small launches do not take the persistent form by themselves
+    rng = np.random.default_rng(900 + seed)
+    win, ml = (63, 63), int(rng.integers(0, 5))
+    w, h = int(rng.integers(130, 700)), int(rng.integers(130, 520))
+    base = syn.base_texture(w, h, int(rng.integers(1, 1 << 30)))
+    dx, dy = rng.uniform(-9, 9, 2)
+    A = syn.crop(base, w, h, 0, 0); B = syn.crop(base, w, h, float(dx), float(dy))
+    if seed % 3 == 1:
+        A = A.copy(); A[h // 4:h // 2, w // 4:w // 2] = 77               # textureless block: min-eigenvalue rejections
+    jobs = 3 if seed % 2 else 1
+    n = int(rng.integers(40, 700))
+    pts = np.stack([rng.uniform(-40, w + 40, (jobs, n)), rng.uniform(-40, h + 40, (jobs, n))], -1).astype(np.float32)
+    pts[:, : n // 4] = np.rint(pts[:, : n // 4])
+    init = (pts + rng.uniform(-15, 15, pts.shape)).astype(np.float32) if seed % 2 == 0 else None
+    p = Pyramid(ctx, w, h, 2, win, ml)
+    p.upload(np.stack([A, B]), 0); p.build(0, 2)
+    flags = LK_GET_MIN_EIGENVALS | (LK_USE_INITIAL_FLOW if init is not None else 0)
+    lk = LK(win, ml, 99, 0.001, flags, 1e-4)
+    prev_slot = dev(ctx, np.array([0, 1, 0][:jobs], np.int32)); next_slot = dev(ctx, np.array([1, 0, 1][:jobs], np.int32))
+    cnt = np.array([n, n - 7, n // 2][:jobs], np.int32)
+    out = klt_track(p, prev_slot, next_slot, dev(ctx, pts), dev(ctx, cnt), lk, None if init is None else dev(ctx, init.copy()), 2.0)
+    p1, st, err, keep = [o.cpu().numpy() for o in out]
+    PA, PB = oracle.Pyramid(A, win, ml), oracle.Pyramid(B, win, ml)
+    for j in range(jobs):
+        P0, P1 = (PA, PB) if j != 1 else (PB, PA)
+        m = int(cnt[j])
+        o1, os_, oe = oracle.lk_track(P0, P1, pts[j, :m], None if init is None else init[j, :m], win, ml, flags=flags)
+        ob, osb, _ = oracle.lk_track(P1, P0, o1, None, win, ml)
+        assert np.array_equal(st[j, :m], os_) and np.array_equal(p1[j, :m], o1) and np.array_equal(err[j, :m], oe), (form, j, ml, w, h)
+        assert np.array_equal(keep[j, :m].astype(bool), oracle.fb_check(pts[j, :m], ob, os_, osb, 2.0)), (form, j)
     p.close()
 
 

@@ -40,6 +40,7 @@ struct zs_switches {
     bool fe_no_graph, klt_no_tma, klt_no_share, lk_no_cache, fast_v1, l2_no_tensor, l2_one_tile, fast_pretest, subpix_v1, klt_no_persist, fast_no_tma, klt63_four_warps;
     int pyr_force;               // 0 = by batch size, 1 = ZS_PYR_SPLIT, 2 = ZS_PYR_FUSED
     int hamming_splits, hamming_variant, l2_splits, l2_epi_groups;   // 0 = default
+    int klt_persist_min;         // ZS_KLT_PERSIST_MIN: launches with at least this many (job, point) items take the persistent form (0 = default)
 };
 void zs_read_switches(zs_switches* s);
 

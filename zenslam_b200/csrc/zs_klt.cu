@@ -1075,7 +1075,8 @@ zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_
         // persistent form when there are many waves of CTAs to run (ZS_KLT_NO_PERSIST: always one CTA per item).  Measured at
         // C2, 128 frames per batch (160 items per CTA slot): KLT 12.01 -> 11.85 ms; at 1 - 16 frames per batch no difference,
         // so small launches keep the plain grid and skip the counter reset
-        const bool persist = !ctx->sw.klt_no_persist && items < (1LL << 31) && items > 4LL * ctx->sm_count * 24;
+        const long long persist_min = ctx->sw.klt_persist_min > 0 ? ctx->sw.klt_persist_min : 4LL * ctx->sm_count * 24 + 1;
+        const bool persist = !ctx->sw.klt_no_persist && items < (1LL << 31) && items >= persist_min;
         if (persist) {
             a.work = ctx->d_klt_work;                          // a device int of the context, zeroed in stream order before the launch
             a.n_items = (int)items;
@@ -1086,8 +1087,8 @@ zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_
             const int nw = klt4_cfg<W_, H_>::NT / TPW_;                                                                         \
             const size_t sm = (size_t)nw * (TPW_ * (KLT4_SJ_BYTES + KLT4_SD_BYTES) + 128);                                     \
             const long long resident = (long long)ctx->sm_count * MB_;                                                         \
-            const dim3 grid = (persist && items > resident) ? dim3((unsigned)resident, 1) : dim3(cap, listed);                 \
-            if (!(persist && items > resident)) a.work = nullptr;                                                              \
+            const dim3 grid = persist ? dim3((unsigned)(items < resident ? items : resident), 1) : dim3(cap, listed);          \
+            if (!persist) a.work = nullptr;                                                                                    \
             if (sm > 48 * 1024) ZS_CUDA(cudaFuncSetAttribute(k_klt_track_v4<W_, H_, MB_, TPW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
             k_klt_track_v4<W_, H_, MB_, TPW_><<<grid, nw * 32, sm, ctx->stream>>>(a);                                           \
         } while (0)
