@@ -30,6 +30,7 @@
 
 #include "zenslam_cuda/bf_matcher.h"
 #include "zenslam_cuda/keypoint_detector_cuda.h"
+#include "zenslam_cuda/processing.h"
 #include "zenslam_cuda/pyr_lk.h"
 #include "zenslam_cuda/pyr_lk_factory.h"
 #include "zenslam_cuda/stereo_tracker.h"
@@ -342,6 +343,47 @@ try
             const std::vector<int> next_index { static_cast<int>(zenslam::keypoint::index_next) };
             out.put_i32(prefix + std::to_string(t) + ".index_next", next_index);
         }
+    }
+
+    // ---------------------------------------------------------------- processor::process (image path) and the triangulator's core
+    {
+        const auto& bgr = in.at("pp_bgr");                      // [h][w][3]
+        const int   ph = static_cast<int>(bgr.dim(0)), pwid = static_cast<int>(bgr.dim(1));
+        // a BGR frame inside a wider buffer (row step != 3 * width), CV_32FC1 maps as cv::initUndistortRectifyMap writes them
+        cv::Mat buffer(ph, pwid + 5, CV_8UC3, cv::Scalar(9));
+        cv::Mat color = buffer(cv::Rect(2, 0, pwid, ph));
+        for (int y = 0; y < ph; ++y) std::memcpy(color.ptr<uchar>(y), bgr.as<uchar>() + static_cast<size_t>(y) * pwid * 3, static_cast<size_t>(pwid) * 3);
+        const cv::Mat map_x(ph, pwid, CV_32FC1, const_cast<float*>(in.at("pp_map_x").as<float>()));
+        const cv::Mat map_y(ph, pwid, CV_32FC1, const_cast<float*>(in.at("pp_map_y").as<float>()));
+
+        const cv::Mat plain = zenslam::cuda::process_image(color, false, 4.0, cv::Mat(), cv::Mat());
+        const cv::Mat full  = zenslam::cuda::process_image(color, true, 4.0, map_x, map_y);
+        CV_Assert(plain.isContinuous() && full.isContinuous());
+        out.put("pp.plain", "u1", { static_cast<size_t>(ph), static_cast<size_t>(pwid) }, plain.data);
+        out.put("pp.full", "u1", { static_cast<size_t>(ph), static_cast<size_t>(pwid) }, full.data);
+
+        const auto& tp = in.at("tri_P");                        // [2][3][4], then F [3][3], t [3]
+        cv::Matx34d P0, P1;
+        cv::Matx33d F;
+        cv::Vec3d   t;
+        for (int i = 0; i < 12; ++i) { P0.val[i] = tp.as<double>()[i]; P1.val[i] = tp.as<double>()[12 + i]; }
+        for (int i = 0; i < 9; ++i) F.val[i] = in.at("tri_F").as<double>()[i];
+        for (int i = 0; i < 3; ++i) t.val[i] = in.at("tri_t").as<double>()[i];
+        const auto&              a0 = in.at("tri_pts0");
+        const auto&              a1 = in.at("tri_pts1");
+        std::vector<cv::Point2f> p0(a0.dim(0)), p1(a0.dim(0));
+        for (size_t i = 0; i < p0.size(); ++i)
+        {
+            p0[i] = { a0.as<float>()[2 * i], a0.as<float>()[2 * i + 1] };
+            p1[i] = { a1.as<float>()[2 * i], a1.as<float>()[2 * i + 1] };
+        }
+        std::vector<cv::Point3d> points3d;
+        std::vector<uchar>       keep;
+        zenslam::cuda::triangulate_points(P0, P1, &F, t, p0, p1, { }, points3d, keep);
+        out.put("tri.xyz", "f8", { points3d.size(), 3 }, reinterpret_cast<const double*>(points3d.data()));
+        out.put_u8("tri.keep", keep);
+        zenslam::cuda::triangulate_points(P0, P1, nullptr, t, p0, p1, { }, points3d, keep);
+        out.put_u8("tri.keep_no_epipolar", keep);
     }
 
     std::cout << "adapter_harness: ok\n";

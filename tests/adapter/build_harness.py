@@ -16,7 +16,7 @@ REF_INC = "/root/reference/zenslam_core/include"
 OUT = os.path.join(HERE, "_build")
 EXE = os.path.join(OUT, "adapter_harness")
 ADAPTER = os.path.join(ROOT, "zenslam_cuda")
-SOURCES = ["context.cpp", "pyr_lk.cpp", "pyr_lk_factory.cpp", "keypoint_detector_cuda.cpp", "bf_matcher.cpp", "stereo_tracker.cpp"]
+SOURCES = ["context.cpp", "pyr_lk.cpp", "pyr_lk_factory.cpp", "keypoint_detector_cuda.cpp", "bf_matcher.cpp", "stereo_tracker.cpp", "processing.cpp"]
 
 
 def available() -> bool:

@@ -23,6 +23,7 @@ using uchar = unsigned char;
 #define CV_32F 5
 #define CV_8UC1 0
 #define CV_32FC1 5
+#define CV_8UC3 16
 
 namespace cv
 {
@@ -96,6 +97,8 @@ namespace cv
         const T& operator()(int r, int c) const { return val[r * N + c]; }
     };
     using Matx33d = Matx<double, 3, 3>;
+    using Matx34d = Matx<double, 3, 4>;
+    using Vec3d   = Matx<double, 3, 1>;
 
     struct TermCriteria
     {
@@ -122,7 +125,7 @@ namespace cv
         operator size_t() const { return v; }
     };
 
-    // 2-D, single-channel (CV_8UC1 / CV_32FC1) matrix: shared buffer + (data, step) view, so ROIs, row() and rowRange() alias
+    // 2-D matrix of CV_8UC1 / CV_32FC1 / CV_8UC3 elements: shared buffer + (data, step) view, so ROIs, row() and rowRange() alias
     // the parent's memory exactly like OpenCV's headers do
     class Mat
     {
@@ -150,7 +153,7 @@ namespace cv
         {
             for (int r = 0; r < rows; ++r)
             {
-                if (_type == CV_8UC1) std::memset(data + r * step.v, static_cast<int>(s[0]), cols);
+                if (_type == CV_8UC1 || _type == CV_8UC3) std::memset(data + r * step.v, static_cast<int>(s[0]), cols * elem(_type));
                 else for (int c = 0; c < cols; ++c) reinterpret_cast<float*>(data + r * step.v)[c] = static_cast<float>(s[0]);
             }
         }
@@ -190,7 +193,7 @@ namespace cv
         template <typename T> [[nodiscard]] const T& at(int r, int c) const { return ptr<T>(r)[c]; }
 
     private:
-        static size_t elem(int type_) { return type_ == CV_32FC1 ? 4 : 1; }
+        static size_t elem(int type_) { return type_ == CV_32FC1 ? 4 : type_ == CV_8UC3 ? 3 : 1; }
         int                                 _type { };
         std::shared_ptr<std::vector<uchar>> _buffer { };
     };

@@ -12,7 +12,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_INC = "/root/reference/zenslam_core/include"
 
-SOURCES = ["context.cpp", "pyr_lk.cpp", "pyr_lk_factory.cpp", "keypoint_detector_cuda.cpp", "bf_matcher.cpp", "stereo_tracker.cpp"]
+SOURCES = ["context.cpp", "pyr_lk.cpp", "pyr_lk_factory.cpp", "keypoint_detector_cuda.cpp", "bf_matcher.cpp", "stereo_tracker.cpp", "processing.cpp"]
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_INC), reason="reference headers not present")

@@ -98,9 +98,19 @@ def inputs():
     lm_desc[:, 7] ^= 3
     lm_index = (700000 + 3 * np.arange(len(lm_desc))).astype(np.int32)
     lm_xyz = rng.normal(0.0, 30.0, (len(lm_desc), 3))
+    # processor::process: a BGR frame + rectification maps that leave the frame here and there
+    g = seq[0, 0]
+    bgr = np.stack([g, np.roll(g, 3, 1), 255 - g // 2], -1).astype(np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    map_x = (xx + 3.5 * np.sin(yy / 37.0) - 4.0).astype(np.float32); map_y = (yy * 1.01 + 2.0 * np.cos(xx / 53.0) - 1.5).astype(np.float32)
+    # the triangulator's core: the committed cv2 fixture's geometry
+    tg = np.load(os.path.join(ROOT, "tests", "golden", "triangulate.npz"))
     return {"dims": np.array([W, H, FRAMES, CELL, THR, WIN, LEVEL], np.int32), "frames": seq, "lk_points": pts, "lk_initial": init,
             "existing": ex, "match_q": q, "match_t": t, "match_qf": qf, "match_tf": tf,
-            "lm_index": lm_index, "lm_xyz": lm_xyz, "lm_desc": lm_desc}
+            "lm_index": lm_index, "lm_xyz": lm_xyz, "lm_desc": lm_desc,
+            "pp_bgr": bgr, "pp_map_x": map_x, "pp_map_y": map_y,
+            "tri_P": np.stack([tg["P0"], tg["P1"]]).astype(np.float64), "tri_F": tg["F"].astype(np.float64), "tri_t": tg["t"].astype(np.float64).reshape(3),
+            "tri_pts0": tg["pts0"].astype(np.float32), "tri_pts1": tg["pts1"].astype(np.float32)}
 
 
 @pytest.fixture(scope="module")
@@ -257,3 +267,27 @@ def test_stereo_tracker_class_equals_python_device_tracker(results, inputs, ctx,
     assert len(last) > 200
     assert bool((last >= 700000).any()) == with_landmarks           # landmark indices live in the maps exactly when a store exists
     trk.close()
+
+
+def test_process_image_and_triangulation_equal_oracle(results, inputs):
+    """zenslam::cuda::process_image (processor.cpp:25-55: BGR2GRAY, CLAHE 4.0, remap) bit-exact against the oracle, and
+    zenslam::cuda::triangulate_points (triangulator.cpp:39-132) against the oracle within the stated float tolerance"""
+    bgr = inputs["pp_bgr"]
+    gray = oracle.bgr2gray(bgr)
+    assert np.array_equal(results["pp.plain"], gray)
+    want = oracle.remap_linear(oracle.clahe(gray, 4.0), inputs["pp_map_x"], inputs["pp_map_y"])
+    assert np.array_equal(results["pp.full"], want)
+    assert (want == 0).any() and not np.array_equal(want, gray)           # the maps really leave the frame / move pixels
+    P = inputs["tri_P"]
+    oxyz, okeep, odiag = oracle.triangulate_keypoints(P[0], P[1], inputs["tri_F"], inputs["tri_t"], inputs["tri_pts0"], inputs["tri_pts1"])
+    xyz = results["tri.xyz"]
+    scale = np.maximum(np.abs(oxyz).max(1, keepdims=True), 1e-6)
+    assert (np.abs(xyz - oxyz) / scale).max() < 1e-5
+    n0 = np.linalg.norm(oxyz, axis=1)
+    margin = np.min(np.stack([np.abs(np.abs(odiag[:, 0]) - 0.01), np.abs(n0 - 1.0), np.abs(n0 - 50.0), np.abs(odiag[:, 1] - 1.0),
+                              np.abs(odiag[:, 2] - 1.0), np.abs(odiag[:, 3] - 0.25), np.abs(oxyz[:, 2])]), 0)
+    safe = margin > 1e-6
+    keep = results["tri.keep"].ravel().astype(bool)
+    assert safe.mean() > 0.99 and np.array_equal(keep[safe], okeep[safe]) and keep.sum() > 20
+    wide = results["tri.keep_no_epipolar"].ravel().astype(bool)
+    assert (wide | ~keep).all() and wide.sum() >= keep.sum()              # without the epipolar filter: a superset
