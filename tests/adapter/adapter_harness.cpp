@@ -18,6 +18,7 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <opencv2/core.hpp>
@@ -356,8 +357,21 @@ try
         const cv::Mat map_x(ph, pwid, CV_32FC1, const_cast<float*>(in.at("pp_map_x").as<float>()));
         const cv::Mat map_y(ph, pwid, CV_32FC1, const_cast<float*>(in.at("pp_map_y").as<float>()));
 
-        const cv::Mat plain = zenslam::cuda::process_image(color, false, 4.0, cv::Mat(), cv::Mat());
-        const cv::Mat full  = zenslam::cuda::process_image(color, true, 4.0, map_x, map_y);
+        // two threads at once, as processor::process converts the two camera images (processor.cpp:25-55)
+        cv::Mat plain, full;
+        {
+            std::jthread thread_0 { [&] { plain = zenslam::cuda::process_image(color, false, 4.0, cv::Mat(), cv::Mat()); } };
+            std::jthread thread_1 { [&] { full = zenslam::cuda::process_image(color, true, 4.0, map_x, map_y); } };
+        }
+        for (int repeat = 0; repeat < 8; ++repeat)
+        {
+            cv::Mat again_0, again_1;
+            {
+                std::jthread thread_0 { [&] { again_0 = zenslam::cuda::process_image(color, false, 4.0, cv::Mat(), cv::Mat()); } };
+                std::jthread thread_1 { [&] { again_1 = zenslam::cuda::process_image(color, true, 4.0, map_x, map_y); } };
+            }
+            CV_Assert(std::memcmp(again_0.data, plain.data, static_cast<size_t>(ph) * pwid) == 0 && std::memcmp(again_1.data, full.data, static_cast<size_t>(ph) * pwid) == 0);
+        }
         CV_Assert(plain.isContinuous() && full.isContinuous());
         out.put("pp.plain", "u1", { static_cast<size_t>(ph), static_cast<size_t>(pwid) }, plain.data);
         out.put("pp.full", "u1", { static_cast<size_t>(ph), static_cast<size_t>(pwid) }, full.data);

@@ -1,5 +1,6 @@
 #include "context.h"
 
+#include <condition_variable>
 #include <cstdlib>
 #include <string>
 
@@ -36,6 +37,60 @@ auto zenslam::cuda::detail::context() -> zs_context*
 {
     static holder instance { };
     return instance.ctx;
+}
+
+namespace
+{
+    // two pre-processing contexts (one per camera image thread of processor::process), created on first use
+    struct preprocessing_pool
+    {
+        static constexpr int    size = 2;
+        holder*                 contexts[size] = { nullptr, nullptr };
+        bool                    busy[size]     = { false, false };
+        std::mutex              mutex { };
+        std::condition_variable released { };
+
+        ~preprocessing_pool()
+        {
+            for (auto* context : contexts)
+                delete context;
+        }
+    };
+
+    auto pool() -> preprocessing_pool&
+    {
+        static preprocessing_pool instance { };
+        return instance;
+    }
+}
+
+zenslam::cuda::detail::preprocessing_lease::preprocessing_lease()
+{
+    auto& p = pool();
+
+    std::unique_lock lock { p.mutex };
+
+    p.released.wait(lock, [&p] { return !p.busy[0] || !p.busy[1]; });
+
+    _slot         = p.busy[0] ? 1 : 0;
+    p.busy[_slot] = true;
+
+    if (p.contexts[_slot] == nullptr)
+        p.contexts[_slot] = new holder { };
+
+    _context = p.contexts[_slot]->ctx;
+}
+
+zenslam::cuda::detail::preprocessing_lease::~preprocessing_lease()
+{
+    auto& p = pool();
+
+    {
+        std::scoped_lock lock { p.mutex };
+        p.busy[_slot] = false;
+    }
+
+    p.released.notify_one();
 }
 
 auto zenslam::cuda::detail::context_mutex() -> std::mutex&

@@ -23,13 +23,17 @@ auto zenslam::cuda::process_image(const cv::Mat& image, const bool clahe_enabled
 
     cv::Mat undistorted(image.rows, image.cols, CV_8UC1);
 
-    std::scoped_lock lock { detail::context_mutex() };
+    // processor::process runs this for both cameras on two threads at once: each call takes its own context
+    const detail::preprocessing_lease lease { };
+
+    if (lease.get() == nullptr)
+        CV_Error(cv::Error::StsError, "zenslam::cuda::process_image: no sm_100 device (there is no CPU fallback in this backend)");
 
     detail::check
     (
         zs_process_image_host
         (
-            detail::context(),
+            lease.get(),
             image.data,
             channels,
             image.cols,
