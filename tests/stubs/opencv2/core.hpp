@@ -187,6 +187,14 @@ namespace cv
         [[nodiscard]] Mat rowRange(int r0, int r1) const { return (*this)(Rect(0, r0, cols, r1 - r0)); }
         [[nodiscard]] Mat row(int r) const { return rowRange(r, r + 1); }
 
+        // cv::Mat::ones(size, type) * 255 (keypoint_detector_simple.cpp:41): the product of the all-ones expression is a filled Mat
+        struct ones_expr { int rows, cols, type; };
+        static ones_expr ones(Size size_, int type_) { return { size_.height, size_.width, type_ }; }
+        Mat(const ones_expr& e) { create(e.rows, e.cols, e.type); setTo(Scalar(1)); }
+        friend Mat operator*(const ones_expr& e, double v) { return Mat(e.rows, e.cols, e.type, Scalar(v)); }
+
+        template <typename M> void copyTo(M& dst) const { dst = clone(); }
+
         template <typename T> [[nodiscard]] T*       ptr(int r = 0) { return reinterpret_cast<T*>(data + r * step.v); }
         template <typename T> [[nodiscard]] const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + r * step.v); }
         template <typename T> [[nodiscard]] T&       at(int r, int c) { return ptr<T>(r)[c]; }
@@ -196,6 +204,14 @@ namespace cv
         static size_t elem(int type_) { return type_ == CV_32FC1 ? 4 : type_ == CV_8UC3 ? 3 : 1; }
         int                                 _type { };
         std::shared_ptr<std::vector<uchar>> _buffer { };
+    };
+
+    // cv::UMat as the reference uses it (keypoint_detector_parallel.cpp:178-180): a Mat that lives somewhere else
+    class UMat : public Mat
+    {
+    public:
+        UMat() = default;
+        UMat& operator=(const Mat& m) { static_cast<Mat&>(*this) = m; return *this; }
     };
 
     struct KeyPoint
@@ -263,6 +279,17 @@ namespace cv
     using InputArray         = const _InputArray&;
     using InputArrayOfArrays = const _InputArray&;
     inline _InputArray noArray() { return _InputArray(); }
+
+    // cv::OutputArray bound to a cv::Mat the callee assigns
+    class _OutputArray
+    {
+    public:
+        _OutputArray(Mat& m) : _m(&m) { }
+        void assign(const Mat& m) const { *_m = m; }
+    private:
+        Mat* _m;
+    };
+    using OutputArray = const _OutputArray&;
 }
 
 #define CV_Error(code, msg) cv::error(code, msg, "", __FILE__, __LINE__)

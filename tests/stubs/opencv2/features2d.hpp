@@ -9,6 +9,45 @@
 
 namespace cv
 {
+    // cv::Feature2D and the detectors / describers the reference constructs (keypoint_detector_grid.cpp:12-36).  Declarations
+    // only: the adapter never calls them; oracle/ref_glue/opencv_over_oracle.cpp implements them over the C oracle so that the
+    // reference's own detector sources can be compiled and run (oracle/_ref).
+    class Feature2D
+    {
+    public:
+        virtual ~Feature2D() = default;
+        virtual void detect(InputArray image, std::vector<KeyPoint>& keypoints, InputArray mask = noArray());
+        virtual void compute(InputArray image, std::vector<KeyPoint>& keypoints, OutputArray descriptors);
+    };
+
+    class FastFeatureDetector : public Feature2D
+    {
+    public:
+        static Ptr<FastFeatureDetector> create(int threshold = 10, bool nonmaxSuppression = true);
+        void detect(InputArray image, std::vector<KeyPoint>& keypoints, InputArray mask = noArray()) override;
+    private:
+        int _threshold { 10 };
+    };
+
+    class ORB : public Feature2D
+    {
+    public:
+        enum ScoreType { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+        static Ptr<ORB> create(int nfeatures = 500, float scaleFactor = 1.2f, int nlevels = 8, int edgeThreshold = 31, int firstLevel = 0,
+                               int WTA_K = 2, ScoreType scoreType = HARRIS_SCORE, int patchSize = 31, int fastThreshold = 20);
+        void detect(InputArray image, std::vector<KeyPoint>& keypoints, InputArray mask = noArray()) override;
+        void compute(InputArray image, std::vector<KeyPoint>& keypoints, OutputArray descriptors) override;
+    private:
+        int   _nfeatures { 500 }, _nlevels { 8 }, _edge { 31 }, _patch { 31 }, _fast_threshold { 20 };
+        float _scale { 1.2f };
+    };
+
+    class SIFT : public Feature2D
+    {
+    public:
+        static Ptr<SIFT> create();
+    };
+
     class DescriptorMatcher
     {
     public:

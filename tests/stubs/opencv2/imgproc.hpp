@@ -4,6 +4,9 @@
 
 namespace cv
 {
+    // implemented over the C oracle in oracle/ref_glue/opencv_over_oracle.cpp (the adapter does not call it)
+    void cornerSubPix(InputArray image, std::vector<Point2f>& corners, Size winSize, Size zeroZone, TermCriteria criteria);
+
     // filled disc (thickness < 0) on a CV_8UC1 image, clipped: pixels with dx^2 + dy^2 <= r^2 around the centre (a cv::Point: the caller's Point2f
     // converts with cvRound) -- the set OpenCV's filled midpoint circle covers for the radii zenslam uses (cell / 2 = 8 .. 32);
     // tests/test_gpu_adapter.py compares the resulting detections with the python mirror, whose mask is pinned to cv2.circle

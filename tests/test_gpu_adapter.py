@@ -79,6 +79,8 @@ def inputs():
     init = pts + rng.normal(0, 1.5, pts.shape).astype(np.float32)
     # existing keypoints: every third grid corner of the left frame (their cells are occupied / their discs masked)
     ex = np.stack([np.arange(len(kept))[::3] + 7.0, x[kept][::3] + 0.25, y[kept][::3] + 0.5], 1).astype(np.float32)
+    # ... and two that were tracked just outside the frame: C++ truncation puts them into column / row 0 (keypoint_detector_grid.cpp:51-52)
+    ex = np.concatenate([ex, np.array([[9001.0, -5.5, 40.0], [9002.0, 100.0, -3.2]], np.float32)])
     q = rng.integers(0, 256, (300, 32), dtype=np.uint8)
     t = rng.integers(0, 256, (260, 32), dtype=np.uint8)
     t[:120] = q[40:160]
@@ -154,7 +156,7 @@ def _occupancy(ex):
     gw, gh = W // CELL, H // CELL
     occ = np.zeros((gh, gw), np.uint8)
     for _, x, y in ex:
-        gx, gy = int(x) // CELL, int(y) // CELL
+        gx, gy = int(int(x) / CELL), int(int(y) / CELL)                  # C++: both the cast and the division truncate toward zero
         if 0 <= gx < gw and 0 <= gy < gh:
             occ[gy, gx] = 1
     return occ

@@ -157,7 +157,7 @@ def test_keypoint_tracker_track_flow_vs_oracle(ctx):
             h, w = image.shape
             occ = np.zeros((h // ch, w // cw), np.uint8)
             for kp in (existing.values() if existing else []):
-                gx, gy = int(kp.pt[0]) // cw, int(kp.pt[1]) // ch
+                gx, gy = int(int(kp.pt[0]) / cw), int(int(kp.pt[1]) / ch)   # C++ truncation (toward zero) twice
                 if 0 <= gx < occ.shape[1] and 0 <= gy < occ.shape[0]:
                     occ[gy, gx] = 1
             x, y, s = oracle.grid_detect(image, (cw, ch), self.opt.fast_threshold, occ)

@@ -28,6 +28,12 @@ def _require_fast_orb(options: detection_options):
         raise NotImplementedError("the CUDA detector implements feature FAST + descriptor ORB (the reference default)")
 
 
+def _c_div(a: int, b: int) -> int:
+    """integer division as C++ does it (toward zero), not Python's floor"""
+    q = abs(a) // b
+    return q if a >= 0 else -q
+
+
 def _emit(xs, ys, resp, desc) -> list:
     out = []
     for i in range(len(xs)):        # keypoint_detector_grid.cpp:142-147: sequential global indices
@@ -59,7 +65,9 @@ class keypoint_detector_grid(keypoint_detector):
             occ = np.zeros((gh, gw), np.uint8)
             values = keypoints_existing.values() if hasattr(keypoints_existing, "values") else keypoints_existing
             for kp in values:
-                gx, gy = int(kp.pt[0]) // cw, int(kp.pt[1]) // ch
+                # C++ semantics: the float truncates toward zero, and so does the integer division -- a keypoint tracked to
+                # x in (-cell, 0) lands in column 0 (checked against the reference's own code: tests/test_oracle_vs_reference_glue.py)
+                gx, gy = _c_div(int(kp.pt[0]), cw), _c_div(int(kp.pt[1]), ch)
                 if 0 <= gx < gw and 0 <= gy < gh:
                     occ[gy, gx] = 1
         cells = gw * gh
