@@ -65,6 +65,9 @@ struct zs_context {
     uint64_t lk_hits, lk_misses;
     int* d_async_err;         // device flags raised by kernels of stream-asynchronous entries ([0]: L2 descriptors not integers in 0..255)
     int* d_klt_work;          // work counter of the persistent KLT launch (same allocation; reset in stream order before each launch)
+    // two pinned frame buffers of the single-image host entries (zs_host.cu: pageable frame -> pinned, row chunk by row chunk,
+    // each chunk's DMA running behind the host copy of the next one)
+    uint8_t* frame_pin[2]; size_t frame_pin_bytes[2]; int frame_pin_next;
     uint8_t* lk_copy[ZS_LK_CACHE_SLOTS];   // sampled rows of the frame each slot holds: a hash hit is confirmed against them (zs_host.cu)
     size_t lk_copy_bytes[ZS_LK_CACHE_SLOTS];
 };

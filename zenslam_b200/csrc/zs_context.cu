@@ -202,6 +202,7 @@ void zs_context_destroy(zs_context* c)
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 2; ++i) if (c->host_pyr[i]) zs_pyramid_destroy(c->host_pyr[i]);
     for (int i = 0; i < ZS_LK_CACHE_SLOTS; ++i) free(c->lk_copy[i]);
+    for (int i = 0; i < 2; ++i) if (c->frame_pin[i]) cudaFreeHost(c->frame_pin[i]);
     if (c->host_orb) zs_orb_detector_destroy(c->host_orb);
     if (c->d_async_err) cudaFree(c->d_async_err);
     if (c->scratch) cudaFree(c->scratch);

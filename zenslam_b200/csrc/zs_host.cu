@@ -4,6 +4,9 @@
 #include <stdlib.h>
 
 #include "zs_common.cuh"
+#if defined(__x86_64__)
+#include <nmmintrin.h>
+#endif
 
 static zs_status host_pyramid(zs_context* ctx, int which, int w, int h, int slots, int win_w, int win_h, int max_level,
                               zs_pyramid** out)
@@ -25,10 +28,45 @@ static zs_status host_pyramid(zs_context* ctx, int which, int w, int h, int slot
 
 static inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
-// 64-bit content hash of a frame (four interleaved multiply-xorshift lanes over 8-byte words; ~20 us for 752 x 480).
-// It keys the device-side pyramid cache below: a frame whose bytes were seen before keeps its slot, so its upload and
-// pyramid build are skipped.  The key is the content, not the pointer -- buffers are recycled between frames.
-static uint64_t frame_hash(const uint8_t* img, int w, int h, size_t pitch)
+// One pageable host frame into level 0 of a pyramid slot, for the detector entries (whose kernels wait for the frame): the
+// frame goes through one of two pinned buffers of the context in four row chunks, each chunk's DMA running while the host
+// copies the next one, and the call returns with the last DMA still in flight -- 25 us less per 752 x 480 detection call than
+// cudaMemcpy2DAsync from the pageable buffer (tools/bench_seams.py: 0.355 -> 0.304 ms for the two calls of a stereo frame).
+// Every host entry ends with a stream synchronisation, so a buffer is never reused while a DMA reads it.
+static zs_status upload_frame(zs_context* ctx, zs_pyramid* p, const uint8_t* img, size_t pitch, int slot)
+{
+    const int w = p->width, h = p->height;
+    const int b = ctx->frame_pin_next; ctx->frame_pin_next ^= 1;
+    const size_t bytes = (size_t)w * h;
+    if (ctx->frame_pin_bytes[b] < bytes) {
+        ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->frame_pin[b]) ZS_CUDA(cudaFreeHost(ctx->frame_pin[b]));
+        ctx->frame_pin[b] = nullptr; ctx->frame_pin_bytes[b] = 0;
+        ZS_CUDA(cudaMallocHost((void**)&ctx->frame_pin[b], bytes));
+        ctx->frame_pin_bytes[b] = bytes;
+    }
+    uint8_t* pin = ctx->frame_pin[b];
+    uint8_t* dst; size_t dpitch, dstride;
+    zs_status st = zs_pyramid_level0(p, slot, &dst, &dpitch, &dstride);
+    if (st != ZS_OK) return st;
+    const int chunks = h >= 64 ? 4 : 1;
+    for (int c = 0; c < chunks; ++c) {
+        const int y0 = (int)((long long)h * c / chunks), y1 = (int)((long long)h * (c + 1) / chunks);
+        if (pitch == (size_t)w) memcpy(pin + (size_t)y0 * w, img + (size_t)y0 * pitch, (size_t)(y1 - y0) * w);
+        else for (int y = y0; y < y1; ++y) memcpy(pin + (size_t)y * w, img + (size_t)y * pitch, w);
+        ZS_CUDA(cudaMemcpy2DAsync(dst + (size_t)y0 * dpitch, dpitch, pin + (size_t)y0 * w, w, w, y1 - y0, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    }
+    return ZS_OK;
+}
+
+
+// 64-bit content hash of a frame.  It keys the device-side pyramid cache below: a frame whose bytes were seen before keeps
+// its slot, so its upload and pyramid build are skipped.  The key is the content, not the pointer -- buffers are recycled
+// between frames.  Every LK call hashes both of its frames in full, so the hash is on the critical path of the per-frame
+// seam calls: four interleaved CRC32C lanes (one `crc32` per 8 bytes, 8 bytes per cycle: the speed of reading the frame,
+// ~25 us for 752 x 480 from DRAM) where the CPU has SSE4.2, four multiply-xorshift lanes (~50 us) elsewhere.
+static uint64_t frame_hash_scalar(const uint8_t* img, int w, int h, size_t pitch)
 {
     const uint64_t K = 0x9E3779B97F4A7C15ull;
     uint64_t a = K ^ (uint64_t)w, b = K * 3 ^ (uint64_t)h, c = K * 5, d = K * 7;
@@ -50,6 +88,37 @@ static uint64_t frame_hash(const uint8_t* img, int w, int h, size_t pitch)
     uint64_t hsh = a ^ (b * K) ^ ((c * K) >> 7) ^ (d << 3);
     hsh ^= hsh >> 31; hsh *= K; hsh ^= hsh >> 29;
     return hsh ? hsh : 1;                      // 0 marks an empty slot
+}
+
+#if defined(__x86_64__)
+__attribute__((target("sse4.2"))) static uint64_t frame_hash_crc(const uint8_t* img, int w, int h, size_t pitch)
+{
+    const uint64_t K = 0x9E3779B97F4A7C15ull;
+    uint64_t a = (uint32_t)w, b = (uint32_t)h, c = 0x243F6A88u, d = 0x85A308D3u;
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* r = img + (size_t)y * pitch;
+        int x = 0;
+        for (; x + 32 <= w; x += 32) {
+            uint64_t v[4];
+            memcpy(v, r + x, 32);
+            a = _mm_crc32_u64(a, v[0]); b = _mm_crc32_u64(b, v[1]); c = _mm_crc32_u64(c, v[2]); d = _mm_crc32_u64(d, v[3]);
+        }
+        for (; x < w; ++x) a = _mm_crc32_u8((uint32_t)a, r[x]);
+        d = _mm_crc32_u32((uint32_t)d, (uint32_t)y);      // the row number: equal rows in a different order differ
+    }
+    uint64_t hsh = ((a | (b << 32)) * K) ^ (c | (d << 32));
+    hsh ^= hsh >> 31; hsh *= K; hsh ^= hsh >> 29;
+    return hsh ? hsh : 1;
+}
+#endif
+
+static uint64_t frame_hash(const uint8_t* img, int w, int h, size_t pitch)
+{
+#if defined(__x86_64__)
+    static const bool crc = __builtin_cpu_supports("sse4.2");
+    if (crc) return frame_hash_crc(img, w, h, pitch);
+#endif
+    return frame_hash_scalar(img, w, h, pitch);
 }
 
 // A hash match is only a candidate (a collision of the 64-bit hash would silently track against a stale pyramid):
@@ -95,6 +164,8 @@ static zs_status lk_slot(zs_context* ctx, zs_pyramid* p, const uint8_t* img, int
     }
     ctx->lk_misses++;
     ctx->lk_hash[lru] = 0;                      // not valid until both calls below have been queued
+    // (plain pageable copy here: through upload_frame's pinned chunks an LK call with a new frame was 7 us SLOWER -- the
+    // driver's own staging of this copy already overlaps the hashing of the call's second frame)
     zs_status st = zs_pyramid_upload(ctx, p, img, pitch, pitch * h, lru, 1, 1);
     if (st != ZS_OK) return st;
     if ((st = zs_pyramid_build(ctx, p, lru, 1)) != ZS_OK) return st;
@@ -129,25 +200,31 @@ extern "C" zs_status zs_calc_optical_flow_pyr_lk_host(zs_context* ctx, const uin
     int slot_prev = 0, slot_next = 1;
     if ((st = lk_slot(ctx, p, prev_img, width, height, pitch, -1, &slot_prev)) != ZS_OK) return st;
     if ((st = lk_slot(ctx, p, next_img, width, height, pitch, slot_prev, &slot_next)) != ZS_OK) return st;
-    // scratch: [slots(2) count(1)] | prev n*2 f | next n*2 f | err n f | status n
+    // device scratch and pinned staging share one layout: [slots(2) count(1)] | prev n*2 f | next n*2 f | err n f | status n.
+    // One H2D copy brings the header and the points (the initial flow too, when it is used), one D2H copy returns next / err /
+    // status: the seven small pageable copies this call used to make cost as much as its kernel.  The KLT kernel itself uses
+    // no context scratch, so one block serves the whole call
     const size_t o_prev = 256, o_next = o_prev + al256(sizeof(float) * 2 * n), o_err = o_next + al256(sizeof(float) * 2 * n),
                  o_st = o_err + al256(sizeof(float) * n), total = o_st + al256(n);
-    // the KLT kernel itself uses no context scratch, so one block serves the whole call
-    void* s;
+    void *s, *pin;
     if ((st = zs_scratch(ctx, total, &s)) != ZS_OK) return st;
+    if ((st = zs_pinned(ctx, total, &pin)) != ZS_OK) return st;
     uint8_t* base = (uint8_t*)s;
+    uint8_t* hb = (uint8_t*)pin;
+    const bool init = (prm->flags & ZS_LK_USE_INITIAL_FLOW) != 0;
     const int hdr[3] = { slot_prev, slot_next, n };
-    ZS_CUDA(cudaMemcpyAsync(base, hdr, sizeof(hdr), cudaMemcpyHostToDevice, ctx->stream));
-    ZS_CUDA(cudaMemcpyAsync(base + o_prev, prev_pts, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
-    if (prm->flags & ZS_LK_USE_INITIAL_FLOW)
-        ZS_CUDA(cudaMemcpyAsync(base + o_next, next_pts, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    memcpy(hb, hdr, sizeof(hdr));
+    memcpy(hb + o_prev, prev_pts, sizeof(float) * 2 * n);
+    if (init) memcpy(hb + o_next, next_pts, sizeof(float) * 2 * n);
+    ZS_CUDA(cudaMemcpyAsync(base, hb, init ? o_err : o_next, cudaMemcpyHostToDevice, ctx->stream));
     st = zs_klt_track(ctx, p, (const int*)base, (const int*)base + 1, (const float*)(base + o_prev), (float*)(base + o_next),
                       (const int*)base + 2, 1, n, prm, base + o_st, (float*)(base + o_err));
     if (st != ZS_OK) return st;
-    ZS_CUDA(cudaMemcpyAsync(next_pts, base + o_next, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
-    ZS_CUDA(cudaMemcpyAsync(status, base + o_st, n, cudaMemcpyDeviceToHost, ctx->stream));
-    ZS_CUDA(cudaMemcpyAsync(err, base + o_err, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(hb + o_next, base + o_next, total - o_next, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(next_pts, hb + o_next, sizeof(float) * 2 * n);
+    memcpy(status, hb + o_st, n);
+    memcpy(err, hb + o_err, sizeof(float) * n);
     return ZS_OK;
 }
 
@@ -179,29 +256,34 @@ extern "C" zs_status zs_track_keypoints_host(zs_context* ctx, const uint8_t* img
     int slot_0 = 0, slot_1 = 1;
     if ((st = lk_slot(ctx, p, img_0, width, height, pitch, -1, &slot_0)) != ZS_OK) return st;
     if ((st = lk_slot(ctx, p, img_1, width, height, pitch, slot_0, &slot_1)) != ZS_OK) return st;
+    // one layout for the device scratch and the pinned staging, one copy in, one copy out (see zs_calc_optical_flow_pyr_lk_host)
     const size_t o_prev = 256, o_next = o_prev + al256(sizeof(float) * 2 * n), o_err = o_next + al256(sizeof(float) * 2 * n),
                  o_st = o_err + al256(sizeof(float) * n), o_keep = o_st + al256(n), total = o_keep + al256(n);
-    void* s;
+    void *s, *pin;
     if ((st = zs_scratch(ctx, total, &s)) != ZS_OK) return st;
+    if ((st = zs_pinned(ctx, total, &pin)) != ZS_OK) return st;
     uint8_t* base = (uint8_t*)s;
+    uint8_t* hb = (uint8_t*)pin;
     const int hdr[3] = { slot_0, slot_1, n };
-    ZS_CUDA(cudaMemcpyAsync(base, hdr, sizeof(hdr), cudaMemcpyHostToDevice, ctx->stream));
-    ZS_CUDA(cudaMemcpyAsync(base + o_prev, points_0, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    memcpy(hb, hdr, sizeof(hdr));
+    memcpy(hb + o_prev, points_0, sizeof(float) * 2 * n);
     zs_lk_params q = *prm;
     if (predicted_1) {
         q.flags |= ZS_LK_USE_INITIAL_FLOW;
-        ZS_CUDA(cudaMemcpyAsync(base + o_next, predicted_1, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+        memcpy(hb + o_next, predicted_1, sizeof(float) * 2 * n);
     } else {
         q.flags &= ~ZS_LK_USE_INITIAL_FLOW;
     }
+    ZS_CUDA(cudaMemcpyAsync(base, hb, predicted_1 ? o_err : o_next, cudaMemcpyHostToDevice, ctx->stream));
     st = zs_klt_track_fb(ctx, p, (const int*)base, (const int*)base + 1, (const float*)(base + o_prev), (float*)(base + o_next),
                          (const int*)base + 2, 1, n, &q, klt_threshold, base + o_st, (float*)(base + o_err), base + o_keep);
     if (st != ZS_OK) return st;
-    ZS_CUDA(cudaMemcpyAsync(points_1, base + o_next, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (status) ZS_CUDA(cudaMemcpyAsync(status, base + o_st, n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (err) ZS_CUDA(cudaMemcpyAsync(err, base + o_err, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    ZS_CUDA(cudaMemcpyAsync(keep, base + o_keep, n, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA(cudaMemcpyAsync(hb + o_next, base + o_next, total - o_next, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(points_1, hb + o_next, sizeof(float) * 2 * n);
+    if (status) memcpy(status, hb + o_st, n);
+    if (err) memcpy(err, hb + o_err, sizeof(float) * n);
+    memcpy(keep, hb + o_keep, n);
     return ZS_OK;
 }
 
@@ -218,13 +300,19 @@ static zs_status detect_grid_host(zs_context* ctx, const uint8_t* img, int width
     zs_pyramid* p;
     zs_status st = host_pyramid(ctx, 1, width, height, 1, 16, 16, 0, &p);
     if (st != ZS_OK) return st;
-    if ((st = zs_pyramid_upload(ctx, p, img, pitch, pitch * height, 0, 1, 1)) != ZS_OK) return st;
+    if ((st = upload_frame(ctx, p, img, pitch, 0)) != ZS_OK) return st;
     if ((st = zs_pyramid_build(ctx, p, 0, 1)) != ZS_OK) return st;      // fills the reflect padding ORB's blur reads
     // This call's buffers come from cudaMallocAsync rather than the context scratch, because the detection
     // kernels use that scratch themselves.
+    // Everything the caller gets back -- both counts, keypoints, responses, descriptors -- is one contiguous tail of the
+    // buffer, fetched at full capacity by ONE copy into pinned staging (63 KB at 752 x 480 / 16-px cells) and trimmed to the
+    // count on the host: reading the count first and the rows afterwards cost a second round trip and four pageable copies.
     const size_t o_occ = 0, o_xy0 = al256(cells), o_r0 = o_xy0 + al256(sizeof(float) * 2 * cells),
-                 o_n0 = o_r0 + al256(sizeof(float) * cells), o_xy = o_n0 + 256, o_r = o_xy + al256(sizeof(float) * 2 * cells),
-                 o_n = o_r + al256(sizeof(float) * cells), o_desc = o_n + 256, total = o_desc + al256((size_t)cells * 32);
+                 o_n0 = o_r0 + al256(sizeof(float) * cells), o_n = o_n0 + 256, o_xy = o_n + 256,
+                 o_r = o_xy + al256(sizeof(float) * 2 * cells), o_desc = o_r + al256(sizeof(float) * cells),
+                 total = o_desc + al256((size_t)cells * 32);
+    void* pin;
+    if ((st = zs_pinned(ctx, total - o_n0, &pin)) != ZS_OK) return st;
     zs_async_buffer buf(ctx->stream);
     ZS_CUDA(cudaMallocAsync((void**)&buf.p, total, ctx->stream));
     uint8_t* base = buf.p;
@@ -240,10 +328,10 @@ static zs_status detect_grid_host(zs_context* ctx, const uint8_t* img, int width
                             (const int*)(base + o_n0), cells, (float*)(base + o_xy), (float*)(base + o_r), nullptr,
                             (int*)(base + o_n), base + o_desc);
     if (st != ZS_OK) return st;
-    int n = 0, n_raw = 0;
-    ZS_CUDA(cudaMemcpyAsync(&n, base + o_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    ZS_CUDA(cudaMemcpyAsync(&n_raw, base + o_n0, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    const uint8_t* tail = (const uint8_t*)pin;                    // host image of the buffer from o_n0 on
+    ZS_CUDA(cudaMemcpyAsync(pin, base + o_n0, total - o_n0, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int n = *(const int*)(tail + (o_n - o_n0)), n_raw = *(const int*)tail;
     if (!subpix && cell_w >= 63 && cell_h >= 63) {
         // GRID only (PARALLEL_GRID has no such step): a free cell where FAST finds nothing goes through _describer->detect
         // (keypoint_detector_grid.cpp:92-95) -- the 8-level ORB detector, which CAN return a keypoint once the cell is wider
@@ -258,14 +346,10 @@ static zs_status detect_grid_host(zs_context* ctx, const uint8_t* img, int width
         }
     }
     if (n > 0) {
-        void* pin;
-        if ((st = zs_pinned(ctx, sizeof(float) * 2 * n, &pin)) != ZS_OK) return st;
-        ZS_CUDA(cudaMemcpyAsync(pin, base + o_xy, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
-        ZS_CUDA(cudaMemcpyAsync(response, base + o_r, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
-        ZS_CUDA(cudaMemcpyAsync(desc, base + o_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
-        ZS_CUDA(cudaStreamSynchronize(ctx->stream));
-        const float* xy = (const float*)pin;
+        const float* xy = (const float*)(tail + (o_xy - o_n0));
         for (int i = 0; i < n; ++i) { x[i] = xy[2 * i]; y[i] = xy[2 * i + 1]; }
+        memcpy(response, tail + (o_r - o_n0), sizeof(float) * n);
+        memcpy(desc, tail + (o_desc - o_n0), (size_t)n * 32);
     }
     *n_out = n;
     return ZS_OK;
@@ -298,7 +382,7 @@ extern "C" zs_status zs_detect_keypoints_simple_host(zs_context* ctx, const uint
     zs_pyramid* p;
     zs_status st = host_pyramid(ctx, 1, width, height, 1, 16, 16, 0, &p);
     if (st != ZS_OK) return st;
-    if ((st = zs_pyramid_upload(ctx, p, img, pitch, pitch * height, 0, 1, 1)) != ZS_OK) return st;
+    if ((st = upload_frame(ctx, p, img, pitch, 0)) != ZS_OK) return st;
     if ((st = zs_pyramid_build(ctx, p, 0, 1)) != ZS_OK) return st;
     const size_t plane = al256((size_t)width * height);
     const size_t o_mask = 0, o_xy0 = plane, o_r0 = o_xy0 + al256(sizeof(float) * 2 * cap), o_n0 = o_r0 + al256(sizeof(float) * cap),
