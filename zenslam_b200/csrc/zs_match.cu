@@ -27,21 +27,40 @@ __device__ __forceinline__ void top2_update(top2& t, int d, int j)
 // grid: (ceil(cap_q / 128), splits, pairs).  With splits > 1 (large rectangular problems: new keypoints against the
 // landmark map, keypoint_tracker.cpp:199-291) block y sweeps train rows [y*chunk, (y+1)*chunk) and writes a partial
 // top-2 (int4 i0,i1,d0,d1) per (query, split); k_top2_merge folds the partials in ascending split order.
-// popcount of a 256-bit XOR with 4 POPC instead of 8: POPC issues at a quarter of the LOP3 rate on sm_100 (the kernel
-// was POPC-bound: 1.28 G POPC per 128-pair batch at ~16 per clock per SM), so the eight words are first reduced with
-// carry-save adders (LOP3 0x96 = a^b^c, 0xe8 = majority) to one word each of weight 1, 2, 4 and 8.
-__device__ __forceinline__ int hamming256(const uint4& qa, const uint4& qb, const uint4& a, const uint4& b)
+// The running (best, second) of a query as packed keys (distance << 22 | train row): distances are at most 256 and a
+// launch has fewer than 2^22 train rows (checked by the launcher), so a key orders by distance first and train row second --
+// the smaller train row wins a tie, OpenCV's rule -- and the update is three VIMNMX instead of a compare /
+// select chain of eight.
+#define HAMMING_ROW_BITS 22
+#define HAMMING_NONE 0x7fffffff
+struct top2k { int k0, k1; };
+__device__ __forceinline__ void top2k_update(top2k& t, int key)
+{
+    const int hi = max(t.k0, key);
+    t.k0 = min(t.k0, key);
+    t.k1 = min(t.k1, hi);
+}
+
+// Key of one (query, train row) distance.  Popcount of a 256-bit XOR with 4 POPC instead of 8: POPC issues at a quarter of
+// the LOP3 rate on sm_100 (the first kernel was POPC-bound: 1.28 G POPC per 128-pair batch at ~16 per clock per SM), so seven
+// of the eight words go through four full adders (LOP3 0x96 = a^b^c, 0xe8 = majority) and leave one word of weight 1 (plus
+// the eighth word, counted as it is), one of weight 2 and one of weight 4.  Round 1 folded the eighth word and the carries
+// through three more half adders into (ones, twos, fours, eights): the same four POPC for six more LOP3, on the ALU pipe
+// that bounds the kernel (ncu: ALU 85 %, XU 52 %).  The weights and the row index are applied by IMADs (FMA pipe, idle).
+__device__ __forceinline__ int hamming_key(const uint4& qa, const uint4& qb, const uint4& a, const uint4& b, int row)
 {
     const unsigned w0 = qa.x ^ a.x, w1 = qa.y ^ a.y, w2 = qa.z ^ a.z, w3 = qa.w ^ a.w;
     const unsigned w4 = qb.x ^ b.x, w5 = qb.y ^ b.y, w6 = qb.z ^ b.z, w7 = qb.w ^ b.w;
     const unsigned s1 = w0 ^ w1 ^ w2, c1 = (w0 & w1) | (w2 & (w0 | w1));
     const unsigned s2 = w3 ^ w4 ^ w5, c2 = (w3 & w4) | (w5 & (w3 | w4));
     const unsigned s3 = s1 ^ s2 ^ w6, c3 = (s1 & s2) | (w6 & (s1 | s2));
-    const unsigned ones = s3 ^ w7, c4 = s3 & w7;
     const unsigned s5 = c1 ^ c2 ^ c3, c5 = (c1 & c2) | (c3 & (c1 | c2));
-    const unsigned twos = s5 ^ c4, c6 = s5 & c4;
-    const unsigned fours = c5 ^ c6, eights = c5 & c6;
-    return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
+    int key = row;
+    key = __popc(s3) * (1 << HAMMING_ROW_BITS) + key;
+    key = __popc(w7) * (1 << HAMMING_ROW_BITS) + key;
+    key = __popc(s5) * (2 << HAMMING_ROW_BITS) + key;
+    key = __popc(c5) * (4 << HAMMING_ROW_BITS) + key;
+    return key;
 }
 
 // Each thread owns HQ query descriptors in registers (8 x u32 each): one pair of broadcast 128-bit shared loads of a train
@@ -66,13 +85,13 @@ __global__ void __launch_bounds__(HAMMING_THREADS) k_hamming_top2(
     const uint4* tp = (const uint4*)(t + (size_t)pair * t_stride);
     // query k of this thread is row q0 + k*HAMMING_THREADS + threadIdx.x (consecutive threads read consecutive rows)
     uint4 qa[HQ], qb[HQ];
-    top2 best[HQ];
+    top2k best[HQ];
 #pragma unroll
     for (int k = 0; k < HQ; ++k) {
         const int qi = q0 + k * HAMMING_THREADS + threadIdx.x;
         qa[k] = make_uint4(0, 0, 0, 0); qb[k] = qa[k];
         if (qi < n_q) { qa[k] = qp[2 * qi]; qb[k] = qp[2 * qi + 1]; }
-        best[k].d0 = best[k].d1 = 0x7fffffff; best[k].i0 = best[k].i1 = -1;
+        best[k].k0 = best[k].k1 = HAMMING_NONE;
     }
     for (int base = t_begin; base < t_end; base += MATCH_TILE) {
         const int m = min(MATCH_TILE, t_end - base);
@@ -84,11 +103,12 @@ __global__ void __launch_bounds__(HAMMING_THREADS) k_hamming_top2(
             const uint4 a = tile[2 * j], b = tile[2 * j + 1];
 #pragma unroll
             for (int k = 0; k < HQ; ++k) {
-                int d;
-                if (CSA) d = hamming256(qa[k], qb[k], a, b);
-                else d = __popc(qa[k].x ^ a.x) + __popc(qa[k].y ^ a.y) + __popc(qa[k].z ^ a.z) + __popc(qa[k].w ^ a.w) +
-                         __popc(qb[k].x ^ b.x) + __popc(qb[k].y ^ b.y) + __popc(qb[k].z ^ b.z) + __popc(qb[k].w ^ b.w);
-                top2_update(best[k], d, base + j);
+                int key;
+                if (CSA) key = hamming_key(qa[k], qb[k], a, b, base + j);
+                else key = (__popc(qa[k].x ^ a.x) + __popc(qa[k].y ^ a.y) + __popc(qa[k].z ^ a.z) + __popc(qa[k].w ^ a.w) +
+                            __popc(qb[k].x ^ b.x) + __popc(qb[k].y ^ b.y) + __popc(qb[k].z ^ b.z) + __popc(qb[k].w ^ b.w)) *
+                               (1 << HAMMING_ROW_BITS) + (base + j);
+                top2k_update(best[k], key);
             }
         }
     }
@@ -96,12 +116,15 @@ __global__ void __launch_bounds__(HAMMING_THREADS) k_hamming_top2(
     for (int k = 0; k < HQ; ++k) {
         const int qi = q0 + k * HAMMING_THREADS + threadIdx.x;
         if (qi >= n_q) continue;
+        const int k0 = best[k].k0, k1 = best[k].k1;
+        const int i0 = k0 == HAMMING_NONE ? -1 : k0 & ((1 << HAMMING_ROW_BITS) - 1), d0 = k0 == HAMMING_NONE ? HAMMING_NONE : k0 >> HAMMING_ROW_BITS;
+        const int i1 = k1 == HAMMING_NONE ? -1 : k1 & ((1 << HAMMING_ROW_BITS) - 1), d1 = k1 == HAMMING_NONE ? HAMMING_NONE : k1 >> HAMMING_ROW_BITS;
         if (splits > 1) {
-            part[((size_t)pair * cap_q + qi) * splits + blockIdx.y] = make_int4(best[k].i0, best[k].i1, best[k].d0, best[k].d1);
+            part[((size_t)pair * cap_q + qi) * splits + blockIdx.y] = make_int4(i0, i1, d0, d1);
         } else {
             int* oi = o_idx + (size_t)pair * out_stride + 2 * qi;
             int* od = o_dist + (size_t)pair * out_stride + 2 * qi;
-            oi[0] = best[k].i0; oi[1] = best[k].i1; od[0] = best[k].d0; od[1] = best[k].d1;
+            oi[0] = i0; oi[1] = i1; od[0] = d0; od[1] = d1;
         }
     }
 }
@@ -271,6 +294,7 @@ static size_t hamming_part_ints(const zs_context* ctx, int pairs, int cap_q, int
 static zs_status hamming_top2(zs_context* ctx, const uint8_t* q, const int* nq, size_t qs, const uint8_t* t, const int* nt,
                               size_t ts, int pairs, int cap_q, int cap_t, int* idx, int* dist, void* part)
 {
+    ZS_REQUIRE(cap_t < (1 << HAMMING_ROW_BITS), "more than 2^22 train rows per pair");
     const int splits = hamming_splits(ctx, pairs, cap_q, cap_t);
     const int chunk = cap_t > 2 * HAMMING_SPLIT_CHUNK ? HAMMING_SPLIT_CHUNK : hamming_chunk(cap_t, splits);
     const int variant = ctx->sw.hamming_variant;
