@@ -265,6 +265,47 @@ def test_hamming_batch_ragged_vs_oracle(ctx):
         assert np.array_equal(cdist[k, keep], odd.astype(np.float32))
 
 
+@pytest.mark.parametrize("variant,splits", [(0, 0), (0, 3), (2, 0), (3, 2), (4, 0), (5, 0), (5, 5)])
+def test_hamming_kernel_variants_vs_oracle(ctx, monkeypatch, variant, splits):
+    """every instantiation of k_hamming_top2 behind ZS_HAMMING_VARIANT (queries per thread x carry-save / plain popcount) and
+    train-side split counts, packed (distance << 22 | row) keys included: ragged batch with duplicate rows and 16-bit
+    descriptors (tie floods) against the oracle's stable top-2 / cross-check"""
+    from zenslam_b200.runtime import match_hamming_cross, match_hamming_knn2
+    if variant:
+        monkeypatch.setenv("ZS_HAMMING_VARIANT", str(variant))
+    if splits:
+        monkeypatch.setenv("ZS_HAMMING_SPLITS", str(splits))
+    ctx.reload_switches()
+    try:
+        rng = np.random.default_rng(50 + variant)
+        sizes = [(700, 900), (0, 50), (37, 0), (1, 1), (300, 1411), (129, 128), (513, 2)]
+        qs = [rng.integers(0, 256, (a, 32), dtype=np.uint8) for a, _ in sizes]
+        ts = [rng.integers(0, 256, (b, 32), dtype=np.uint8) for _, b in sizes]
+        ts[0][:40] = qs[0][100:140]; ts[0][500] = ts[0][3]; ts[0][899] = ts[0][3]
+        qs[4][:, 2:] = 0; ts[4][:, 2:] = 0
+        ts[6][1] = ts[6][0]                                          # two identical train rows: best and second tie on every query
+        cap_q, cap_t = 700, 1411
+        dq, dt = dev(ctx, _pad(qs, cap_q, np.uint8)), dev(ctx, _pad(ts, cap_t, np.uint8))
+        nq = dev(ctx, np.array([a for a, _ in sizes], np.int32)); nt = dev(ctx, np.array([b for _, b in sizes], np.int32))
+        idx, dist, ps = match_hamming_knn2(ctx, dq, nq, dt, nt, 0.8)
+        cidx, cdist = match_hamming_cross(ctx, dq, nq, dt, nt)
+        idx, dist, ps, cidx, cdist = [a.cpu().numpy() for a in (idx, dist, ps, cidx, cdist)]
+        for k, (a, b) in enumerate(sizes):
+            oi, od = oracle.match_hamming_knn2(qs[k], ts[k])
+            assert np.array_equal(idx[k, :a], oi), (variant, splits, k)
+            assert np.array_equal(dist[k, :a][oi >= 0], od.astype(np.float32)[oi >= 0])
+            rq, _, _ = oracle.ratio_test(oi, od.astype(np.float32), 0.8)
+            assert np.array_equal(np.nonzero(ps[k, :a])[0], rq)
+            oq, ot, odd = oracle.match_hamming_cross(qs[k], ts[k])
+            keep = np.nonzero(cidx[k, :a] >= 0)[0]
+            assert np.array_equal(keep, oq) and np.array_equal(cidx[k, keep], ot)
+            assert np.array_equal(cdist[k, keep], odd.astype(np.float32))
+    finally:
+        monkeypatch.delenv("ZS_HAMMING_VARIANT", raising=False)
+        monkeypatch.delenv("ZS_HAMMING_SPLITS", raising=False)
+        ctx.reload_switches()
+
+
 def test_l2_golden_sift(ctx, golden):
     from zenslam_b200.runtime import match_l2_cross, match_l2_knn2
     g = golden("match")
