@@ -114,17 +114,23 @@ def test_klt_random(ctx, switches, seed):
     p.close()
 
 
-@pytest.mark.parametrize("form", ["two_tiles", "four_warps", "two_tiles_persistent", "four_warps_persistent"])
+@pytest.mark.parametrize("form", ["two_tiles", "four_warps", "two_tiles_persistent", "four_warps_persistent",
+                                  "packed6", "packed7_persistent", "unpacked", "unpacked_persistent"])
 @pytest.mark.parametrize("seed", range(6))
 def test_klt_random_63(ctx, switches, seed, form):
-    """63 x 63 windows (tumvi.yaml:45) on random frames against the oracle, through both tiled forms of the tracker -- two
-    tiles per warp (the default) and one tile per warp (ZS_KLT63_FOUR_WARPS) -- each also in its persistent launch form: frames
+    """63 x 63 windows (tumvi.yaml:45) on random frames against the oracle, through the tiled forms of the tracker -- two
+    tiles per warp with the packed template (the default; also at 6 / 7 CTAs per SM), two tiles per warp with one register per
+    pixel (ZS_KLT63_UNPACKED) and one tile per warp (ZS_KLT63_FOUR_WARPS) -- each also in its persistent launch form: frames
     smaller than the window at the coarse levels, points outside the frame, integer positions, initial flow, several jobs in
     one launch (so that the persistent form has items to distribute)."""
     from zenslam_b200 import LK_GET_MIN_EIGENVALS, LK_USE_INITIAL_FLOW
     from zenslam_b200.runtime import LK, Pyramid, klt_track
     if form.startswith("four_warps"):
         switches.set(ctx, "ZS_KLT63_FOUR_WARPS")
+    if form.startswith("packed"):                                        # the packed-template two-tile kernel at 6 / 7 CTAs per SM (default: 8)
+        switches.set(ctx, "ZS_KLT63_PACKED", form[6])
+    if form.startswith("unpacked"):                                      # register-per-pixel template (the round-2 form before the packed one)
+        switches.set(ctx, "ZS_KLT63_UNPACKED")
     if form.endswith("persistent"):
         switches.set(ctx, "ZS_KLT_PERSIST_MIN", 1)                       # small launches do not take the persistent form by themselves
     rng = np.random.default_rng(900 + seed)

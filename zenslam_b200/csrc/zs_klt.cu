@@ -483,7 +483,7 @@ __device__ __forceinline__ void cta_sum(long long (&v)[N], long long* red, int& 
 // (stereo L->R of frame k and temporal L_k -> L_{k+1}) share it and only the Gauss-Newton loops run twice.
 struct lk_state { float outx, outy; int status; };
 
-template <int WW, int WH>
+template <int WW, int WH, int PK>
 __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i, int slot_j0, int slot_j1, int ntgt,
                                                   float2 prev, float2 init, bool use_init, int warp, int lane, uint8_t* sJ,
                                                   uint8_t* sD, uint32_t bar, uint32_t& parity, long long* red, int& phase,
@@ -537,7 +537,7 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
         mbar_wait(bar, parity); parity ^= 1;
 
         // ---- template in registers: JB row bands x 8 pixels per lane
-        int Ix[cfg::JB][8], Iy[cfg::JB][8];
+        int Ix[cfg::JB][PK != 0 ? 4 : 8], Iy[cfg::JB][PK != 0 ? 4 : 8];      // PK: s16 x 2 words of pixel pairs (see lk_track_point_v5)
         int pA11 = 0, pA12 = 0, pA22 = 0, pc1 = 0, pc2 = 0;
         {
             const int wt = pack_s16x2(w00, w01), wb = pack_s16x2(w10, w11);
@@ -568,7 +568,10 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
                         if (24 + pp >= cfg::LW) masked = masked || (8 * k + pp >= tw);
                         if (masked) { ixv = 0; iyv = 0; }
                     }
-                    Ix[j][pp] = ixv; Iy[j][pp] = iyv;
+                    if constexpr (PK != 0) {
+                        if (pp & 1) { Ix[j][pp >> 1] |= ixv << 16; Iy[j][pp >> 1] |= iyv << 16; }
+                        else { Ix[j][pp >> 1] = ixv & 0xffff; Iy[j][pp >> 1] = iyv & 0xffff; }
+                    } else { Ix[j][pp] = ixv; Iy[j][pp] = iyv; }
                     pA11 += ixv * ixv; pA12 += ixv * iyv; pA22 += iyv * iyv;
                     pc1 += iv[pp] * ixv; pc2 += iv[pp] * iyv;
                 }
@@ -620,6 +623,27 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
                 const uint32_t* jw = jbase + ((jx & 15) >> 2);
                 const int sh = (jx & 3) * 8;
                 int pb1 = 0, pb2 = 0;
+                if constexpr (PK != 0) {
+                    int xl = 0, xh = 0, yl = 0, yh = 0;
+#pragma unroll
+                    for (int j = 0; j < cfg::JB; ++j) {
+                        const row8 ra = load_row8(jw + j * 8 * KLT4_JP, sh), rb = load_row8(jw + (j * 8 + 1) * KLT4_JP, sh);
+                        unsigned bp;
+                        bp = __byte_perm(sample8<0>(wt, wb, ra, rb), sample8<1>(wt, wb, ra, rb), 0x5140);
+                        xl = dp2a_lo_su(Ix[j][0], bp, xl); xh = dp2a_hi_su(Ix[j][0], bp, xh);
+                        yl = dp2a_lo_su(Iy[j][0], bp, yl); yh = dp2a_hi_su(Iy[j][0], bp, yh);
+                        bp = __byte_perm(sample8<2>(wt, wb, ra, rb), sample8<3>(wt, wb, ra, rb), 0x5140);
+                        xl = dp2a_lo_su(Ix[j][1], bp, xl); xh = dp2a_hi_su(Ix[j][1], bp, xh);
+                        yl = dp2a_lo_su(Iy[j][1], bp, yl); yh = dp2a_hi_su(Iy[j][1], bp, yh);
+                        bp = __byte_perm(sample8<4>(wt, wb, ra, rb), sample8<5>(wt, wb, ra, rb), 0x5140);
+                        xl = dp2a_lo_su(Ix[j][2], bp, xl); xh = dp2a_hi_su(Ix[j][2], bp, xh);
+                        yl = dp2a_lo_su(Iy[j][2], bp, yl); yh = dp2a_hi_su(Iy[j][2], bp, yh);
+                        bp = __byte_perm(sample8<6>(wt, wb, ra, rb), sample8<7>(wt, wb, ra, rb), 0x5140);
+                        xl = dp2a_lo_su(Ix[j][3], bp, xl); xh = dp2a_hi_su(Ix[j][3], bp, xh);
+                        yl = dp2a_lo_su(Iy[j][3], bp, yl); yh = dp2a_hi_su(Iy[j][3], bp, yh);
+                    }
+                    pb1 = xl + (xh << 8); pb2 = yl + (yh << 8);
+                } else {
 #pragma unroll
                 for (int j = 0; j < cfg::JB; ++j) {
                     const row8 ra = load_row8(jw + j * 8 * KLT4_JP, sh), rb = load_row8(jw + (j * 8 + 1) * KLT4_JP, sh);
@@ -632,6 +656,7 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
                     jv = sample8<5>(wt, wb, ra, rb); pb1 += jv * Ix[j][5]; pb2 += jv * Iy[j][5];
                     jv = sample8<6>(wt, wb, ra, rb); pb1 += jv * Ix[j][6]; pb2 += jv * Iy[j][6];
                     jv = sample8<7>(wt, wb, ra, rb); pb1 += jv * Ix[j][7]; pb2 += jv * Iy[j][7];
+                }
                 }
                 long long sB[2] = { warp_sum_exact(pb1), warp_sum_exact(pb2) };
                 cta_sum<cfg::NT, 2>(sB, red, phase, warp, lane);
@@ -682,7 +707,11 @@ __device__ __forceinline__ long long warp_sum_exact2(int pa, int pb)
     return ((long long)shi << 16) + (long long)slo;
 }
 
-template <int WW, int WH>
+// PK = packed template: the gradients of a lane's pixel PAIRS as s16 x 2 words (half the template registers).  The products
+// then come from IDP.2A as well: jv < 2^13 is split into its two bytes, a PRMT puts (lo_p, lo_q, hi_p, hi_q) of a pixel pair
+// into one word, and IDP.2A.LO / .HI accumulate sum(lo * I) and sum(hi * I) -- sum(jv * I) = lo-sum + 256 hi-sum exactly.
+// 4 IDP + 1 PRMT per pixel pair instead of 4 IMAD: 4 more instructions per 8-pixel band, 64 registers fewer per thread.
+template <int WW, int WH, int PK>
 __device__ __forceinline__ void lk_track_point_v5(const klt_args& a, int slot_i, int slot_j0, int slot_j1, int ntgt,
                                                   float2 prev, float2 init, bool use_init, int warp, int lane, uint8_t* tiles,
                                                   uint32_t bar, uint32_t& parity, long long* red, int& phase,
@@ -740,9 +769,71 @@ __device__ __forceinline__ void lk_track_point_v5(const klt_args& a, int slot_i,
         mbar_wait(bar, parity); parity ^= 1;
 
         // ---- templates in registers: 2 tiles x 4 row bands x 8 pixels per lane
-        int Ix[TPW][4][8], Iy[TPW][4][8];
+        int Ix[TPW][4][PK != 0 ? 4 : 8], Iy[TPW][4][PK != 0 ? 4 : 8];
         long long sT[5];
-        {
+        if constexpr (PK == 2) {
+            // ROLLED template pass (round 2, late).  Unrolled over 2 tiles x 4 bands the template section is 1 920 instructions
+            // (30 KB) of straight-line code that every warp streams through once per level: with sixteen warps per SM at
+            // different places in it the instruction cache thrashes (ncu: `no_instruction` 1.25 warps per issue, 65 % of those
+            // samples in this section).  Here ONE band body runs eight times; a band's packed gradients (8 words per lane) are
+            // parked in the derivative rows the band has just consumed (rows 8j .. 8j+7 of its tile, dead from then on; row
+            // 8j+8 is still needed by the next band and stays) and loaded back into registers, where the Gauss-Newton loops
+            // want them, by sixteen 128-bit loads afterwards.  Both tiles' lane partials share one 32-bit word: 64 pixels x
+            // 4080 x 8160 < 2^31.
+            int pA11 = 0, pA12 = 0, pA22 = 0, pc1 = 0, pc2 = 0;
+            const int wt = pack_s16x2(w00, w01), wb = pack_s16x2(w10, w11);
+            const int sh = (gx & 3) * 8;
+            const uint32_t* jw = jbase + ((gx & 15) >> 2);
+            const uint32_t* dw = dbase + (gx & 3);
+            uint32_t* park = (uint32_t*)(tiles + KLT4_SJ_BYTES) + 4 * lane;
+#pragma unroll 1
+            for (int tj = 0; tj < TPW * 4; ++tj) {
+                const int t = tj >> 2, j = tj & 3;
+                const row8 ra = load_row8(jw, sh), rb = load_row8(jw + KLT4_JP, sh);
+                int tx_[9], ty_[9], bx[9], by[9];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    const unsigned dt = dw[q], db = dw[KLT4_DP + q];
+                    tx_[q] = (int)(short)(dt & 0xffff); ty_[q] = (int)dt >> 16;
+                    bx[q] = (int)(short)(db & 0xffff); by[q] = (int)db >> 16;
+                }
+                const bool row_masked = (8 * j + 7 >= cfg::LH) && (8 * j + g >= th);
+                int iv[8];
+                iv[0] = sample8<0>(wt, wb, ra, rb); iv[1] = sample8<1>(wt, wb, ra, rb); iv[2] = sample8<2>(wt, wb, ra, rb);
+                iv[3] = sample8<3>(wt, wb, ra, rb); iv[4] = sample8<4>(wt, wb, ra, rb); iv[5] = sample8<5>(wt, wb, ra, rb);
+                iv[6] = sample8<6>(wt, wb, ra, rb); iv[7] = sample8<7>(wt, wb, ra, rb);
+                unsigned gxp[4], gyp[4];
+#pragma unroll
+                for (int pp = 0; pp < 8; ++pp) {
+                    int ixv = (tx_[pp] * w00 + tx_[pp + 1] * w01 + bx[pp] * w10 + bx[pp + 1] * w11 + (1 << 13)) >> 14;
+                    int iyv = (ty_[pp] * w00 + ty_[pp + 1] * w01 + by[pp] * w10 + by[pp + 1] * w11 + (1 << 13)) >> 14;
+                    bool masked = row_masked;
+                    if (24 + pp >= cfg::LW) masked = masked || (t == cfg::TX - 1 && 8 * k + pp >= cfg::LW);
+                    if (masked) { ixv = 0; iyv = 0; }
+                    if (pp & 1) { gxp[pp >> 1] |= (unsigned)ixv << 16; gyp[pp >> 1] |= (unsigned)iyv << 16; }
+                    else { gxp[pp >> 1] = ixv & 0xffff; gyp[pp >> 1] = iyv & 0xffff; }
+                    pA11 += ixv * ixv; pA12 += ixv * iyv; pA22 += iyv * iyv;
+                    pc1 += iv[pp] * ixv; pc2 += iv[pp] * iyv;
+                }
+                __syncwarp();                                  // every lane has read this band's derivative rows
+                uint32_t* st = park + t * (TILE_BYTES / 4) + j * (8 * KLT4_DP);
+                *(uint4*)st = make_uint4(gxp[0], gxp[1], gxp[2], gxp[3]);
+                *(uint4*)(st + 128) = make_uint4(gyp[0], gyp[1], gyp[2], gyp[3]);
+                jw += 8 * KLT4_JP; dw += 8 * KLT4_DP;
+                if (j == 3) { jw += TILE_BYTES / 4 - 32 * KLT4_JP; dw += TILE_BYTES / 4 - 32 * KLT4_DP; }
+            }
+#pragma unroll
+            for (int t = 0; t < TPW; ++t)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t* st = park + t * (TILE_BYTES / 4) + j * (8 * KLT4_DP);
+                    const uint4 gx4 = *(const uint4*)st, gy4 = *(const uint4*)(st + 128);
+                    Ix[t][j][0] = gx4.x; Ix[t][j][1] = gx4.y; Ix[t][j][2] = gx4.z; Ix[t][j][3] = gx4.w;
+                    Iy[t][j][0] = gy4.x; Iy[t][j][1] = gy4.y; Iy[t][j][2] = gy4.z; Iy[t][j][3] = gy4.w;
+                }
+            sT[0] = warp_sum_exact(pA11); sT[1] = warp_sum_exact(pA12); sT[2] = warp_sum_exact(pA22);
+            sT[3] = warp_sum_exact(pc1); sT[4] = warp_sum_exact(pc2);
+        } else {
             int pA11[TPW], pA12[TPW], pA22[TPW], pc1[TPW], pc2[TPW];
             const int wt = pack_s16x2(w00, w01), wb = pack_s16x2(w10, w11);
             const int sh = (gx & 3) * 8;
@@ -776,7 +867,10 @@ __device__ __forceinline__ void lk_track_point_v5(const klt_args& a, int slot_i,
                         if ((8 * j + 7 >= cfg::LH) || ((t == cfg::TX - 1) && (24 + pp >= cfg::LW))) {
                             if (row_masked || col_masked) { ixv = 0; iyv = 0; }
                         }
-                        Ix[t][j][pp] = ixv; Iy[t][j][pp] = iyv;
+                        if constexpr (PK != 0) {
+                            if (pp & 1) { Ix[t][j][pp >> 1] |= ixv << 16; Iy[t][j][pp >> 1] |= iyv << 16; }
+                            else { Ix[t][j][pp >> 1] = ixv & 0xffff; Iy[t][j][pp >> 1] = iyv & 0xffff; }
+                        } else { Ix[t][j][pp] = ixv; Iy[t][j][pp] = iyv; }
                         pA11[t] += ixv * ixv; pA12[t] += ixv * iyv; pA22[t] += iyv * iyv;
                         pc1[t] += iv[pp] * ixv; pc2[t] += iv[pp] * iyv;
                     }
@@ -834,6 +928,27 @@ __device__ __forceinline__ void lk_track_point_v5(const klt_args& a, int slot_i,
                 for (int t = 0; t < TPW; ++t) {
                     pb1[t] = 0; pb2[t] = 0;
                     const uint32_t* jw = jbase + t * (TILE_BYTES / 4) + ((jx & 15) >> 2);
+                    if constexpr (PK != 0) {
+                        int xl = 0, xh = 0, yl = 0, yh = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const row8 ra = load_row8(jw + j * 8 * KLT4_JP, sh), rb = load_row8(jw + (j * 8 + 1) * KLT4_JP, sh);
+                            unsigned bp;
+                            bp = __byte_perm(sample8<0>(wt, wb, ra, rb), sample8<1>(wt, wb, ra, rb), 0x5140);
+                            xl = dp2a_lo_su(Ix[t][j][0], bp, xl); xh = dp2a_hi_su(Ix[t][j][0], bp, xh);
+                            yl = dp2a_lo_su(Iy[t][j][0], bp, yl); yh = dp2a_hi_su(Iy[t][j][0], bp, yh);
+                            bp = __byte_perm(sample8<2>(wt, wb, ra, rb), sample8<3>(wt, wb, ra, rb), 0x5140);
+                            xl = dp2a_lo_su(Ix[t][j][1], bp, xl); xh = dp2a_hi_su(Ix[t][j][1], bp, xh);
+                            yl = dp2a_lo_su(Iy[t][j][1], bp, yl); yh = dp2a_hi_su(Iy[t][j][1], bp, yh);
+                            bp = __byte_perm(sample8<4>(wt, wb, ra, rb), sample8<5>(wt, wb, ra, rb), 0x5140);
+                            xl = dp2a_lo_su(Ix[t][j][2], bp, xl); xh = dp2a_hi_su(Ix[t][j][2], bp, xh);
+                            yl = dp2a_lo_su(Iy[t][j][2], bp, yl); yh = dp2a_hi_su(Iy[t][j][2], bp, yh);
+                            bp = __byte_perm(sample8<6>(wt, wb, ra, rb), sample8<7>(wt, wb, ra, rb), 0x5140);
+                            xl = dp2a_lo_su(Ix[t][j][3], bp, xl); xh = dp2a_hi_su(Ix[t][j][3], bp, xh);
+                            yl = dp2a_lo_su(Iy[t][j][3], bp, yl); yh = dp2a_hi_su(Iy[t][j][3], bp, yh);
+                        }
+                        pb1[t] = xl + (xh << 8); pb2[t] = yl + (yh << 8);
+                    } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const row8 ra = load_row8(jw + j * 8 * KLT4_JP, sh), rb = load_row8(jw + (j * 8 + 1) * KLT4_JP, sh);
@@ -846,6 +961,7 @@ __device__ __forceinline__ void lk_track_point_v5(const klt_args& a, int slot_i,
                         jv = sample8<5>(wt, wb, ra, rb); pb1[t] += jv * Ix[t][j][5]; pb2[t] += jv * Iy[t][j][5];
                         jv = sample8<6>(wt, wb, ra, rb); pb1[t] += jv * Ix[t][j][6]; pb2[t] += jv * Iy[t][j][6];
                         jv = sample8<7>(wt, wb, ra, rb); pb1[t] += jv * Ix[t][j][7]; pb2[t] += jv * Iy[t][j][7];
+                    }
                     }
                 }
                 long long sB[2] = { warp_sum_exact2(pb1[0], pb1[1]), warp_sum_exact2(pb2[0], pb2[1]) };
@@ -875,7 +991,7 @@ __device__ __forceinline__ void lk_track_point_v5(const klt_args& a, int slot_i,
 
 // TPW = window tiles per warp: 1 (one warp per tile, lk_track_point_v4) or 2 (lk_track_point_v5); sJ = the warp's first tile
 // buffer, scratch = its 128-byte bookkeeping line (which also holds the mbarrier)
-template <int WW, int WH, int TPW>
+template <int WW, int WH, int TPW, int PK>
 __device__ __forceinline__ void klt4_item(const klt_args& a, int job, int i, int warp, int lane, uint8_t* sJ, uint8_t* scratch, uint32_t bar,
                                           uint32_t& parity, long long* s_red, int& phase)
 {
@@ -921,10 +1037,10 @@ __device__ __forceinline__ void klt4_item(const klt_args& a, int job, int i, int
         if (ui) init = a.next_pts[(size_t)job * a.cap + i];
         lk_state r0, r1; float err;
         if constexpr (TPW == 1)
-            lk_track_point_v4<WW, WH>(a, si, sj0, sj1, pass == 0 ? w[7] : 1, from, init, ui, warp, lane, sJ, sD, bar, parity, s_red,
+            lk_track_point_v4<WW, WH, PK>(a, si, sj0, sj1, pass == 0 ? w[7] : 1, from, init, ui, warp, lane, sJ, sD, bar, parity, s_red,
                                       phase, r0, r1, err);
         else
-            lk_track_point_v5<WW, WH>(a, si, sj0, sj1, pass == 0 ? w[7] : 1, from, init, ui, warp, lane, sJ, bar, parity, s_red,
+            lk_track_point_v5<WW, WH, PK>(a, si, sj0, sj1, pass == 0 ? w[7] : 1, from, init, ui, warp, lane, sJ, bar, parity, s_red,
                                       phase, r0, r1, err);
         if (pass == 0) {
             __syncwarp();
@@ -950,7 +1066,7 @@ __device__ __forceinline__ void klt4_item(const klt_args& a, int job, int i, int
 // sm_count x MINB CTAs that take items from an atomic counter, point index fastest (neighbouring CTAs then work on the same
 // image pair): no CTA relaunch gap between the ~160 items a CTA slot serves per 128-frame batch, no empty CTAs for the
 // points beyond an image's corner count.
-template <int WW, int WH, int MINB, int TPW = 1>
+template <int WW, int WH, int MINB, int TPW = 1, int PK = 0>
 __global__ void __launch_bounds__(klt4_cfg<WW, WH>::NT / TPW * 32, MINB) k_klt_track_v4(klt_args a)
 {
     typedef klt4_cfg<WW, WH> cfg;
@@ -988,7 +1104,7 @@ __global__ void __launch_bounds__(klt4_cfg<WW, WH>::NT / TPW * 32, MINB) k_klt_t
             if (item >= a.n_items) break;
             jl = item / a.cap; i = item - jl * a.cap;
         }
-        klt4_item<WW, WH, TPW>(a, a.job_list ? a.job_list[jl] : jl, i, warp, lane, sJ, scratch, bar, parity, s_red, phase);
+        klt4_item<WW, WH, TPW, PK>(a, a.job_list ? a.job_list[jl] : jl, i, warp, lane, sJ, scratch, bar, parity, s_red, phase);
         if (!persistent) break;
     }
 }
@@ -1082,29 +1198,44 @@ zs_status zs_klt_launch(zs_context* ctx, const zs_pyramid* p, const int* d_prev_
             a.n_items = (int)items;
             ZS_CUDA(cudaMemsetAsync(a.work, 0, sizeof(int), ctx->stream));
         }
-#define KLT4_LAUNCH_T(W_, H_, MB_, TPW_)                                                                                       \
+#define KLT4_LAUNCH_T(W_, H_, MB_, TPW_) KLT4_LAUNCH_P(W_, H_, MB_, TPW_, 0)
+#define KLT4_LAUNCH_P(W_, H_, MB_, TPW_, PK_)                                                                                     \
         do {                                                                                                                   \
             const int nw = klt4_cfg<W_, H_>::NT / TPW_;                                                                         \
             const size_t sm = (size_t)nw * (TPW_ * (KLT4_SJ_BYTES + KLT4_SD_BYTES) + 128);                                     \
             const long long resident = (long long)ctx->sm_count * MB_;                                                         \
             const dim3 grid = persist ? dim3((unsigned)(items < resident ? items : resident), 1) : dim3(cap, listed);          \
             if (!persist) a.work = nullptr;                                                                                    \
-            if (sm > 48 * 1024) ZS_CUDA(cudaFuncSetAttribute(k_klt_track_v4<W_, H_, MB_, TPW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-            k_klt_track_v4<W_, H_, MB_, TPW_><<<grid, nw * 32, sm, ctx->stream>>>(a);                                           \
+            if (sm > 48 * 1024) ZS_CUDA(cudaFuncSetAttribute(k_klt_track_v4<W_, H_, MB_, TPW_, PK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+            k_klt_track_v4<W_, H_, MB_, TPW_, PK_><<<grid, nw * 32, sm, ctx->stream>>>(a);                                      \
         } while (0)
 #define KLT4_LAUNCH(W_, H_, MB_) KLT4_LAUNCH_T(W_, H_, MB_, 1)
-        if (a.win_w == 31) KLT4_LAUNCH(31, 31, 24);
+        // (packed template, ZS_KLT31_PACKED = CTAs per SM: 78 / 72 registers and no spills, but 390 instead of 378 instructions per
+        // iteration, all of the extra ones on the ALU pipe: 24 CTAs 11.86 ms, 28: 11.93 ms, 32 (64 registers): 12.22 ms against
+        // 11.85 ms -- the 31x31 kernel is bound by issue slots, not by resident warps; profiles/r2_klt_packed_template.txt)
+        if (a.win_w == 31 && ctx->sw.klt31_packed == 24) KLT4_LAUNCH_P(31, 31, 24, 1, 1);
+        else if (a.win_w == 31 && ctx->sw.klt31_packed == 28) KLT4_LAUNCH_P(31, 31, 28, 1, 1);
+        else if (a.win_w == 31) KLT4_LAUNCH(31, 31, 24);
         // (four-warp CTAs: 4 per SM = 128 registers: 16.4 - 16.5 ms; 5 per SM (96 registers, 240 B of spills): 16.6 ms; 6 (80
         // registers, 324 B): 20.1 ms)
         // 63x63 (tumvi.yaml:45): two tiles per warp, two-warp CTAs, six per SM (lk_track_point_v5; 168 registers, 240 B of
         // spills): 15.8 ms per 128-frame TUMVI batch (1024x1024, 225 points per image).  Measured alternatives: 4 CTAs per SM
         // (224 registers, no spills) 16.3 ms, 5: 17.5 ms, 7 / 8 (128 registers, 468 B of spills): 20.5 / 19.1 ms; the four-warp
         // form (ZS_KLT63_FOUR_WARPS; one tile per warp, 128 registers, 4 CTAs per SM): 16.5 ms
+        // Round 2, late: the PACKED template (gradients of pixel pairs as s16 x 2, products by IDP.2A on the bytes of jv) halves
+        // the template registers: 128 registers with 36 B of spills at EIGHT CTAs per SM (the limit of shared memory) instead of
+        // 168 at six: 15.89 -> 14.95 ms (6 CTAs, 158 registers, no spills: 15.48; 7: 15.56).  ZS_KLT63_UNPACKED restores the
+        // register-per-pixel template, ZS_KLT63_PACKED = 6 / 7 the other occupancies.
+        else if (a.win_w == 63 && !ctx->sw.klt63_four_warps && !ctx->sw.klt63_unpacked && ctx->sw.klt63_packed == 6) KLT4_LAUNCH_P(63, 63, 6, 2, 1);
+        else if (a.win_w == 63 && !ctx->sw.klt63_four_warps && !ctx->sw.klt63_unpacked && ctx->sw.klt63_packed == 7) KLT4_LAUNCH_P(63, 63, 7, 2, 1);
+        else if (a.win_w == 63 && !ctx->sw.klt63_four_warps && !ctx->sw.klt63_unpacked && ctx->sw.klt63_packed == 8) KLT4_LAUNCH_P(63, 63, 8, 2, 1);
+        else if (a.win_w == 63 && !ctx->sw.klt63_four_warps && !ctx->sw.klt63_unpacked) KLT4_LAUNCH_P(63, 63, 8, 2, 2);
         else if (a.win_w == 63 && !ctx->sw.klt63_four_warps) KLT4_LAUNCH_T(63, 63, 6, 2);
         else if (a.win_w == 63) KLT4_LAUNCH(63, 63, 4);
         else if (a.win_w == 21) KLT4_LAUNCH(21, 21, 24);
         else KLT4_LAUNCH(15, 15, 24);
 #undef KLT4_LAUNCH
+#undef KLT4_LAUNCH_P
 #undef KLT4_LAUNCH_T
         ZS_LAUNCH_CHECK(ctx);
         return ZS_OK;
