@@ -452,6 +452,8 @@ __device__ __forceinline__ int sample8(int wt, int wb, const row8& a, const row8
     int acc;
     if ((P & 3) < 2) acc = dp2a_lo_su(wt, ta, dp2a_lo_su(wb, tb, 1 << 8));
     else acc = dp2a_hi_su(wt, ta, dp2a_hi_su(wb, tb, 1 << 8));
+    // (the shift as IMAD.HI by 2^23 would move it from the ALU to the FMA pipe, but IMAD.HI issues far slower than SHF: KLT 11.86
+    // -> 13.64 ms at C2, 13.87 -> 15.55 ms at TUMVI; gpurun_out/r5i)
     return acc >> 9;
 }
 
@@ -537,7 +539,7 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
         mbar_wait(bar, parity); parity ^= 1;
 
         // ---- template in registers: JB row bands x 8 pixels per lane
-        int Ix[cfg::JB][PK != 0 ? 4 : 8], Iy[cfg::JB][PK != 0 ? 4 : 8];      // PK: s16 x 2 words of pixel pairs (see lk_track_point_v5)
+        int Ix[cfg::JB][PK == 1 ? 4 : 8], Iy[cfg::JB][PK == 1 ? 4 : 8];      // PK: s16 x 2 words of pixel pairs (see lk_track_point_v5)
         int pA11 = 0, pA12 = 0, pA22 = 0, pc1 = 0, pc2 = 0;
         {
             const int wt = pack_s16x2(w00, w01), wb = pack_s16x2(w10, w11);
@@ -568,7 +570,7 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
                         if (24 + pp >= cfg::LW) masked = masked || (8 * k + pp >= tw);
                         if (masked) { ixv = 0; iyv = 0; }
                     }
-                    if constexpr (PK != 0) {
+                    if constexpr (PK == 1) {
                         if (pp & 1) { Ix[j][pp >> 1] |= ixv << 16; Iy[j][pp >> 1] |= iyv << 16; }
                         else { Ix[j][pp >> 1] = ixv & 0xffff; Iy[j][pp >> 1] = iyv & 0xffff; }
                     } else { Ix[j][pp] = ixv; Iy[j][pp] = iyv; }
@@ -623,7 +625,7 @@ __device__ __forceinline__ void lk_track_point_v4(const klt_args& a, int slot_i,
                 const uint32_t* jw = jbase + ((jx & 15) >> 2);
                 const int sh = (jx & 3) * 8;
                 int pb1 = 0, pb2 = 0;
-                if constexpr (PK != 0) {
+                if constexpr (PK == 1) {
                     int xl = 0, xh = 0, yl = 0, yh = 0;
 #pragma unroll
                     for (int j = 0; j < cfg::JB; ++j) {
@@ -771,7 +773,7 @@ __device__ __forceinline__ void lk_track_point_v5(const klt_args& a, int slot_i,
         // ---- templates in registers: 2 tiles x 4 row bands x 8 pixels per lane
         int Ix[TPW][4][PK != 0 ? 4 : 8], Iy[TPW][4][PK != 0 ? 4 : 8];
         long long sT[5];
-        if constexpr (PK == 2) {
+        if constexpr (PK >= 2) {
             // ROLLED template pass (round 2, late).  Unrolled over 2 tiles x 4 bands the template section is 1 920 instructions
             // (30 KB) of straight-line code that every warp streams through once per level: with sixteen warps per SM at
             // different places in it the instruction cache thrashes (ncu: `no_instruction` 1.25 warps per issue, 65 % of those
