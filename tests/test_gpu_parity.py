@@ -485,14 +485,18 @@ def test_klt_multi_job_752(ctx):
         assert okeep.mean() > 0.5 if n > 100 else True
 
 
-@pytest.mark.parametrize("groups", [1, 2, 4])
+@pytest.mark.parametrize("groups", [1, 2, 4, "2_chains"])
 def test_l2_tensor_core_ragged_pairs_vs_oracle_and_cuda_core(ctx, switches, groups):
     """several pairs of different sizes in one launch (tile tails, pairs with an empty side, counts that are not
     multiples of the 128-row tiles, low-entropy rows full of distance ties), checked against the oracle and against
     the CUDA-core dp4a kernel, for 1 / 2 / 4 epilogue warps per TMEM lane quarter (the column groups of a tile are
-    folded with an explicit index tie-break)"""
+    folded with an explicit index tie-break); two warps per quarter is the default and drains a chunk with two min3 trees,
+    "2_chains" (ZS_L2_CHAINS) is the same grouping with the four serial (best, second) chains the others use"""
     from zenslam_b200.runtime import match_l2_cross, match_l2_knn2
-    switches.set(ctx, "ZS_L2_EPI_GROUPS", groups)
+    if groups == "2_chains":
+        switches.set(ctx, "ZS_L2_CHAINS")
+    else:
+        switches.set(ctx, "ZS_L2_EPI_GROUPS", groups)
     rng = np.random.default_rng(99)
     sizes = [(300, 129), (1, 1), (128, 128), (257, 511), (0, 40), (40, 0), (130, 2), (320, 500)]
     cap_q, cap_t = 320, 512

@@ -294,12 +294,51 @@ __device__ __forceinline__ int l2_min3(int a, int b, int c)
     asm("min.s32 %0, %1, %2;\n\tmin.s32 %0, %0, %3;" : "=&r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+__device__ __forceinline__ unsigned l2_min3u(unsigned a, unsigned b, unsigned c)
+{
+    unsigned d;
+    asm("min.u32 %0, %1, %2;\n\tmin.u32 %0, %0, %3;" : "=&r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// smallest of N keys as four independent min3 chains (N = 16 or 32)
+template <int N>
+__device__ __forceinline__ int l2_tree_min(const int (&k)[N])
+{
+    int m[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int* g = &k[q * (N / 4)];
+        int v = l2_min3(g[0], g[1], g[2]);
+#pragma unroll
+        for (int j = 3; j + 1 < N / 4; j += 2) v = l2_min3(v, g[j], g[j + 1]);
+        if ((N / 4) % 2 == 0) v = min(v, g[N / 4 - 1]);
+        m[q] = v;
+    }
+    return min(l2_min3(m[0], m[1], m[2]), m[3]);
+}
+// smallest of the N values (unsigned)(k - base): with base = smallest key + 1 the smallest key itself wraps to 2^32 - 1 and
+// the result is (second smallest key) - base
+template <int N>
+__device__ __forceinline__ unsigned l2_tree_min_rebased(const int (&k)[N], unsigned base)
+{
+    unsigned m[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int* g = &k[q * (N / 4)];
+        unsigned v = l2_min3u((unsigned)g[0] - base, (unsigned)g[1] - base, (unsigned)g[2] - base);
+#pragma unroll
+        for (int j = 3; j + 1 < N / 4; j += 2) v = l2_min3u(v, (unsigned)g[j] - base, (unsigned)g[j + 1] - base);
+        if ((N / 4) % 2 == 0) v = min(v, (unsigned)g[N / 4 - 1] - base);
+        m[q] = v;
+    }
+    return min(l2_min3u(m[0], m[1], m[2]), m[3]);
+}
 // CG = epilogue warps per TMEM lane quarter (the 128 accumulator columns of a tile are split into CG groups of
 // 128/CG); threads = 64 + 128 CG.  One epilogue warp per scheduler (CG = 1) leaves the drain latency-bound -- a
 // warp cannot issue its dependent min/max chain back to back -- so the MMA issuer idles on acc_empty; with CG = 2 or
 // 4 every scheduler interleaves 4 to 8 epilogue warps (2 CTAs per SM) and the drain approaches the issue rate.
 // grid: (ceil(cap_q/128), splits, pairs); dynamic smem: 1024 slack + 16 KB A + L2P_BSTAGES x 16 KB B
-template <int CG>
+template <int CG, bool TREE = false>
 __global__ void __launch_bounds__(64 + 128 * CG, 2) k_l2_tc_persist(const __grid_constant__ CUtensorMap map_q,
                                                                      const __grid_constant__ CUtensorMap map_t, l2p_args a)
 {
@@ -434,7 +473,23 @@ __global__ void __launch_bounds__(64 + 128 * CG, 2) k_l2_tc_persist(const __grid
                     if (lane == 0) l2_mbar_arrive(BAR(3 + 2 * NB + st));
                 }
                 const int4* tn4 = (const int4*)&tn[c0];
-                if (c0 + CW <= ncol) {
+                if (TREE && c0 + CW <= ncol) {
+                    // the chunk's two smallest keys by two min3 trees (keys are unique: the column sits in their low bits): the
+                    // smallest, then the smallest of the keys re-based on it as unsigned numbers (ptxas fuses most of the
+                    // subtractions into VIADDMNMX) -- tree-shaped dependencies and ~2.1 operations per element instead of 2.5
+                    // on four serial chains
+                    int kk[CW];
+#pragma unroll
+                    for (int j4 = 0; j4 < CW / 4; ++j4) {
+                        const int4 t4 = tn4[j4];
+                        kk[4 * j4] = t4.x - 256 * (int)v[4 * j4]; kk[4 * j4 + 1] = t4.y - 256 * (int)v[4 * j4 + 1];
+                        kk[4 * j4 + 2] = t4.z - 256 * (int)v[4 * j4 + 2]; kk[4 * j4 + 3] = t4.w - 256 * (int)v[4 * j4 + 3];
+                    }
+                    const int m0 = l2_tree_min<CW>(kk);
+                    const unsigned base = (unsigned)m0 + 1u;
+                    const int m1 = (int)(l2_tree_min_rebased<CW>(kk, base) + base);
+                    c1k[0] = l2_min3(c1k[0], m1, max(c0k[0], m0)); c0k[0] = min(c0k[0], m0);
+                } else if (c0 + CW <= ncol) {
 #pragma unroll
                     for (int j4 = 0; j4 < CW / 4; ++j4) {
                         const int4 t4 = tn4[j4];
@@ -574,11 +629,15 @@ zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, c
             ZS_CUDA(cudaFuncSetAttribute(k_l2_tc_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ZS_CUDA(cudaFuncSetAttribute(k_l2_tc_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ZS_CUDA(cudaFuncSetAttribute(k_l2_tc_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ZS_CUDA(cudaFuncSetAttribute((k_l2_tc_persist<2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_p = true;
         }
         const int cgsel = ctx->sw.l2_epi_groups > 0 ? ctx->sw.l2_epi_groups : 2;   // 1, 2 or 4 epilogue warps per TMEM lane quarter
         const dim3 grid(q_tiles, b.splits, pairs);
-        if (cgsel == 1) k_l2_tc_persist<1><<<grid, 64 + 128, smem, ctx->stream>>>(mq, mt, b);
+        // default: two epilogue warps per lane quarter, chunk top-2 by two min3 trees (whole 64-pair call 0.1329 -> 0.1283 ms against
+        // the four serial chains, ZS_L2_CHAINS; the other groupings keep the chains)
+        if (cgsel == 2 && !ctx->sw.l2_chains) k_l2_tc_persist<2, true><<<grid, 64 + 256, smem, ctx->stream>>>(mq, mt, b);
+        else if (cgsel == 1) k_l2_tc_persist<1><<<grid, 64 + 128, smem, ctx->stream>>>(mq, mt, b);
         else if (cgsel == 2) k_l2_tc_persist<2><<<grid, 64 + 256, smem, ctx->stream>>>(mq, mt, b);
         else k_l2_tc_persist<4><<<grid, 64 + 512, smem, ctx->stream>>>(mq, mt, b);
         ZS_LAUNCH_CHECK(ctx);
