@@ -487,13 +487,13 @@ def measure_frontend(args, rank, world, local_rank, ctx, light=False):
                                      "timed region; the timed region replays one CUDA graph per batch"},
             "roofline": {"kernel": "k_klt_track (fused forward+backward LK, 4 pairs x B frames per launch)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": klt_traffic(B) if CFG["name"] == "C2" else None,
+                         "frac": achieved / peak if peak else None, "traffic": klt_traffic(B) if CFG["name"] in ("C2", "TUMVI") else None,
                          "algorithmic_bytes_per_launch": klt_bytes, "avg_launch_ms": stage_ms["klt"],
                          "peak_source": peak_src,
-                         "note": "KLT is instruction-issue bound (ncu: 85 % issue-active, DRAM 1.3 % of peak), not HBM bound "
-                                 "(SURVEY 8d); the compulsory-bytes figure is reported as the contract asks, see DESIGN.md"},
+                         "note": "KLT is instruction-issue bound (ncu: 86 % issue-active at C2, 76 % at TUMVI; DRAM 1.3 % / 3 % of peak), "
+                                 "not HBM bound (SURVEY 8d); the compulsory-bytes figure is reported as the contract asks, see DESIGN.md"},
         }
-        issue = klt_issue(B, stage_ms["klt"], clocks) if CFG["name"] == "C2" else None
+        issue = klt_issue(B, stage_ms["klt"], clocks) if CFG["name"] in ("C2", "TUMVI") else None
         if issue:
             line["roofline"]["issue"] = issue
         if sustained:
@@ -558,7 +558,9 @@ def extras(args, ctx):
             return {k: ln[k] for k in ("value", "unit", "ms_per_step", "steps", "e2e", "stage_ms_per_step", "stage_roofline",
                                        "gpu_launches")} | {"workload": ln["config"]["workload"], "batch_stereo_frames": a.batch,
                                                            "keypoints_per_image": ln["config"]["keypoints_per_image"],
-                                                           "roofline_klt_frac": ln["roofline"]["frac"]}
+                                                           "roofline_klt_frac": ln["roofline"]["frac"]} | (
+                    {"roofline_klt_issue": ln["roofline"]["issue"], "roofline_klt_traffic": ln["roofline"]["traffic"]}
+                    if "issue" in ln["roofline"] else {})
         return run
 
     def c3():
@@ -838,7 +840,9 @@ def measure_c3(args, rank, world, ctx, light=False):
 
 
 def klt_capture_file():
-    """the committed ncu --set full capture of the KLT launch of the default workload: newest round first"""
+    """the committed ncu --set full capture of the KLT launch of the default workload (or of the TUMVI one): newest round first"""
+    if CFG["name"] == "TUMVI":
+        return os.path.join(ROOT, "profiles", "r2_klt63_traffic.json")
     for name in ("r2_klt_traffic.json", "r1_klt_traffic.json"):
         p = os.path.join(ROOT, "profiles", name)
         if os.path.exists(p):
