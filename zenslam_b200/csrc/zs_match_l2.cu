@@ -629,17 +629,19 @@ zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, c
             ZS_CUDA(cudaFuncSetAttribute(k_l2_tc_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ZS_CUDA(cudaFuncSetAttribute(k_l2_tc_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ZS_CUDA(cudaFuncSetAttribute(k_l2_tc_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ZS_CUDA(cudaFuncSetAttribute((k_l2_tc_persist<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ZS_CUDA(cudaFuncSetAttribute((k_l2_tc_persist<2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ZS_CUDA(cudaFuncSetAttribute((k_l2_tc_persist<4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_p = true;
         }
         const int cgsel = ctx->sw.l2_epi_groups > 0 ? ctx->sw.l2_epi_groups : 2;   // 1, 2 or 4 epilogue warps per TMEM lane quarter
         const dim3 grid(q_tiles, b.splits, pairs);
         // default: two epilogue warps per lane quarter, chunk top-2 by two min3 trees (whole 64-pair call 0.1329 -> 0.1283 ms against
-        // the four serial chains, ZS_L2_CHAINS; the other groupings keep the chains)
-        if (cgsel == 2 && !ctx->sw.l2_chains) k_l2_tc_persist<2, true><<<grid, 64 + 256, smem, ctx->stream>>>(mq, mt, b);
-        else if (cgsel == 1) k_l2_tc_persist<1><<<grid, 64 + 128, smem, ctx->stream>>>(mq, mt, b);
-        else if (cgsel == 2) k_l2_tc_persist<2><<<grid, 64 + 256, smem, ctx->stream>>>(mq, mt, b);
-        else k_l2_tc_persist<4><<<grid, 64 + 512, smem, ctx->stream>>>(mq, mt, b);
+        // the four serial chains, ZS_L2_CHAINS)
+        const bool tree = !ctx->sw.l2_chains;
+        if (cgsel == 1) { if (tree) k_l2_tc_persist<1, true><<<grid, 64 + 128, smem, ctx->stream>>>(mq, mt, b); else k_l2_tc_persist<1><<<grid, 64 + 128, smem, ctx->stream>>>(mq, mt, b); }
+        else if (cgsel == 2) { if (tree) k_l2_tc_persist<2, true><<<grid, 64 + 256, smem, ctx->stream>>>(mq, mt, b); else k_l2_tc_persist<2><<<grid, 64 + 256, smem, ctx->stream>>>(mq, mt, b); }
+        else { if (tree) k_l2_tc_persist<4, true><<<grid, 64 + 512, smem, ctx->stream>>>(mq, mt, b); else k_l2_tc_persist<4><<<grid, 64 + 512, smem, ctx->stream>>>(mq, mt, b); }
         ZS_LAUNCH_CHECK(ctx);
         k_l2p_merge<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(b, idx, dist);
         ZS_LAUNCH_CHECK(ctx);
