@@ -80,7 +80,7 @@ void zs_read_switches(zs_switches* s)
     auto num = [](const char* n) { const char* e = getenv(n); return e ? atoi(e) : 0; };
     s->fe_no_graph = on("ZS_FE_NO_GRAPH"); s->klt_no_tma = on("ZS_KLT_NO_TMA"); s->klt_no_share = on("ZS_KLT_NO_SHARE");
     s->lk_no_cache = on("ZS_LK_NO_CACHE"); s->fast_v1 = on("ZS_FAST_V1"); s->subpix_v1 = on("ZS_SUBPIX_V1"); s->fast_no_tma = on("ZS_FAST_NO_TMA"); s->klt63_four_warps = on("ZS_KLT63_FOUR_WARPS"); s->klt63_unpacked = on("ZS_KLT63_UNPACKED"); s->klt_persist_min = num("ZS_KLT_PERSIST_MIN"); s->klt63_packed = num("ZS_KLT63_PACKED"); s->klt31_packed = num("ZS_KLT31_PACKED"); s->klt_no_persist = on("ZS_KLT_NO_PERSIST"); s->l2_no_tensor = on("ZS_L2_NO_TENSOR");
-    s->l2_one_tile = on("ZS_L2_ONE_TILE"); s->l2_chains = on("ZS_L2_CHAINS"); s->fast_pretest = on("ZS_FAST_PRETEST");
+    s->l2_one_tile = on("ZS_L2_ONE_TILE"); s->l2_chains = on("ZS_L2_CHAINS"); s->hamming_no_tensor = on("ZS_HAMMING_NO_TENSOR"); s->hamming_tensor_min = num("ZS_HAMMING_TENSOR_MIN"); s->fast_pretest = on("ZS_FAST_PRETEST");
     s->pyr_force = on("ZS_PYR_SPLIT") ? 1 : on("ZS_PYR_FUSED") ? 2 : 0;
     s->hamming_splits = num("ZS_HAMMING_SPLITS"); s->hamming_variant = num("ZS_HAMMING_VARIANT");
     s->l2_splits = num("ZS_L2_SPLITS"); s->l2_epi_groups = num("ZS_L2_EPI_GROUPS");

@@ -283,10 +283,64 @@ static int hamming_splits(const zs_context* ctx, int pairs, int cap_q, int cap_t
     sp = sp < 1 ? 1 : sp > 8 ? 8 : sp;
     return sp > max_sp ? max_sp : sp;
 }
+// ---- Hamming on the tensor cores (late round 2).  For 0 / 1 vectors |a - b|^2 = |a| + |b| - 2 a.b is the Hamming distance, so the
+// 256-bit descriptors, expanded to one byte per bit, go through the tcgen05 kind::i8 kernel of the L2 matcher (zs_match_l2.cu,
+// two 128-byte K halves per row) with their bit counts as the "norms": same exact integers, same tie rule (smaller train row).
+// Taken for problems large enough to pay for the expansion pass (ZS_HAMMING_TENSOR_MIN distances per call, default 2^24;
+// ZS_HAMMING_NO_TENSOR keeps the CUDA-core kernel).
+zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, const uint8_t* t8, const int* nt, int pairs,
+                            int cap_q, int cap_t, int dim, int* idx, int* dist, void* part, const int* qnorm, const int* tnorm);   // zs_match_l2.cu
+size_t zs_l2_tensor_part_ints(int pairs, int cap_q, int cap_t);
+
+// one warp per descriptor row: lane l expands byte l into eight 0 / 1 bytes; rows at or beyond the pair's count become zeros
+__global__ void __launch_bounds__(256) k_bits_expand(const uint8_t* __restrict__ d, const int* __restrict__ n, size_t pair_stride, int cap,
+                                                     size_t rows, uint8_t* __restrict__ out, int* __restrict__ norms)
+{
+    const size_t r = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int pair = (int)(r / cap), i = (int)(r - (size_t)pair * cap);
+    unsigned b = 0;
+    if (i < min(n[pair], cap)) b = d[(size_t)pair * pair_stride + (size_t)i * 32 + lane];
+    uint2 o;
+    o.x = (b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21);
+    o.y = ((b >> 4) & 1u) | ((b & 32u) << 3) | ((b & 64u) << 10) | ((b & 128u) << 17);
+    *(uint2*)(out + r * 256 + 8 * lane) = o;
+    const int c = __reduce_add_sync(0xffffffffu, __popc(b));
+    if (lane == 0) norms[r] = c;
+}
+
+static bool hamming_use_tensor(const zs_context* ctx, int pairs, int cap_q, int cap_t)
+{
+    if (ctx->sw.hamming_no_tensor) return false;
+    const long long min_work = ctx->sw.hamming_tensor_min > 0 ? ctx->sw.hamming_tensor_min : (1LL << 24);
+    return (long long)pairs * cap_q * cap_t >= min_work;
+}
+// ints of scratch behind `part` for the tensor path: partial top-2 + both expanded sides + their bit counts (+ alignment slack)
+static size_t hamming_tensor_ints(int pairs, int cap_q, int cap_t)
+{
+    return zs_l2_tensor_part_ints(pairs, cap_q, cap_t) + 64 * (size_t)pairs * ((size_t)cap_q + cap_t) + (size_t)pairs * ((size_t)cap_q + cap_t) + 256;
+}
+static zs_status hamming_top2_tensor(zs_context* ctx, const uint8_t* q, const int* nq, size_t qs, const uint8_t* t, const int* nt, size_t ts,
+                                     int pairs, int cap_q, int cap_t, int* idx, int* dist, void* part)
+{
+    const size_t rq = (size_t)pairs * cap_q, rt = (size_t)pairs * cap_t;
+    uint8_t* base = (uint8_t*)(((uintptr_t)part + 127) & ~(uintptr_t)127);
+    uint8_t* q8 = base; uint8_t* t8 = q8 + rq * 256;
+    int* qn = (int*)(t8 + rt * 256); int* tn = qn + rq;
+    void* l2part = (void*)(((uintptr_t)(tn + rt) + 15) & ~(uintptr_t)15);
+    k_bits_expand<<<(unsigned)zs_div_up(rq, 8), 256, 0, ctx->stream>>>(q, nq, qs, cap_q, rq, q8, qn);
+    ZS_LAUNCH_CHECK(ctx);
+    k_bits_expand<<<(unsigned)zs_div_up(rt, 8), 256, 0, ctx->stream>>>(t, nt, ts, cap_t, rt, t8, tn);
+    ZS_LAUNCH_CHECK(ctx);
+    return zs_l2_tensor_top2(ctx, q8, nq, t8, nt, pairs, cap_q, cap_t, 256, idx, dist, l2part, qn, tn);
+}
+
 static int hamming_chunk(int cap_t, int splits) { return splits > 1 ? (zs_div_up(cap_t, splits) + 127) / 128 * 128 : 0x7fffffff; }
 // ints of scratch the partial top-2 of one direction need (0 when the train side is not split)
 static size_t hamming_part_ints(const zs_context* ctx, int pairs, int cap_q, int cap_t)
 {
+    if (hamming_use_tensor(ctx, pairs, cap_q, cap_t)) return hamming_tensor_ints(pairs, cap_q, cap_t);
     const int sp = hamming_splits(ctx, pairs, cap_q, cap_t);
     return sp > 1 ? 4 * (size_t)pairs * cap_q * sp : 0;
 }
@@ -295,6 +349,7 @@ static zs_status hamming_top2(zs_context* ctx, const uint8_t* q, const int* nq, 
                               size_t ts, int pairs, int cap_q, int cap_t, int* idx, int* dist, void* part)
 {
     ZS_REQUIRE(cap_t < (1 << HAMMING_ROW_BITS), "more than 2^22 train rows per pair");
+    if (hamming_use_tensor(ctx, pairs, cap_q, cap_t)) return hamming_top2_tensor(ctx, q, nq, qs, t, nt, ts, pairs, cap_q, cap_t, idx, dist, part);
     const int splits = hamming_splits(ctx, pairs, cap_q, cap_t);
     const int chunk = cap_t > 2 * HAMMING_SPLIT_CHUNK ? HAMMING_SPLIT_CHUNK : hamming_chunk(cap_t, splits);
     const int variant = ctx->sw.hamming_variant;

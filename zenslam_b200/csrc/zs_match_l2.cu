@@ -338,7 +338,10 @@ __device__ __forceinline__ unsigned l2_tree_min_rebased(const int (&k)[N], unsig
 // warp cannot issue its dependent min/max chain back to back -- so the MMA issuer idles on acc_empty; with CG = 2 or
 // 4 every scheduler interleaves 4 to 8 epilogue warps (2 CTAs per SM) and the drain approaches the issue rate.
 // grid: (ceil(cap_q/128), splits, pairs); dynamic smem: 1024 slack + 16 KB A + L2P_BSTAGES x 16 KB B
-template <int CG, bool TREE = false>
+// KH = 128-byte K halves per descriptor row: 1 = 128-d u8 rows (SIFT), 2 = 256-d rows -- binary descriptors (ORB) expanded to
+// one 0 / 1 byte per bit, for which |a - b|^2 IS the Hamming distance: the query tile then holds two swizzled 16 KB halves, a
+// train tile passes through the operand ring as two stages, and the second half's four MMAs accumulate onto the first's.
+template <int CG, bool TREE = false, int KH = 1>
 __global__ void __launch_bounds__(64 + 128 * CG, 2) k_l2_tc_persist(const __grid_constant__ CUtensorMap map_q,
                                                                      const __grid_constant__ CUtensorMap map_t, l2p_args a)
 {
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(64 + 128 * CG, 2) k_l2_tc_persist(const __grid
     const int ntile = min(a.tpc, tiles_total - tile_begin);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* sm = (uint8_t*)(((uintptr_t)l2_smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = sm; uint8_t* sB0 = sm + L2TC_M * L2TC_K;
+    uint8_t* sA = sm; uint8_t* sB0 = sm + KH * L2TC_M * L2TC_K;
     const uint32_t bar0 = l2_smem_u32(&s_bar[0]);
 #define BAR(i) (bar0 + 8u * (uint32_t)(i))
 
@@ -377,37 +380,44 @@ __global__ void __launch_bounds__(64 + 128 * CG, 2) k_l2_tc_persist(const __grid
 
     if (warp == 0) {
         if (lane == 0) {
-            l2_mbar_expect_tx(BAR(0), L2TC_M * L2TC_K);
-            l2_tma_load_2d(l2_smem_u32(sA), &map_q, 0, pair * a.cap_q + q0, BAR(0));
-            for (int i = 0; i < ntile; ++i) {
-                const int sb = i % NB, pb = (i / NB) & 1;
+            l2_mbar_expect_tx(BAR(0), KH * L2TC_M * L2TC_K);
+#pragma unroll
+            for (int h = 0; h < KH; ++h)
+                l2_tma_load_2d(l2_smem_u32(sA + h * (L2TC_M * L2TC_K)), &map_q, h * L2TC_K, pair * a.cap_q + q0, BAR(0));
+            for (int r = 0; r < ntile * KH; ++r) {                               // ring item r = (train tile r / KH, K half r % KH)
+                const int sb = r % NB, pb = (r / NB) & 1;
                 l2_mbar_wait_backoff<L2P_SLEEP_TMA>(BAR(1 + NB + sb), pb ^ 1);   // stage free (passes at once the first time round)
                 l2_mbar_expect_tx(BAR(1 + sb), L2TC_N * L2TC_K);
-                l2_tma_load_2d(l2_smem_u32(sB0 + sb * (L2TC_N * L2TC_K)), &map_t, 0, pair * a.cap_t + (tile_begin + i) * L2TC_N, BAR(1 + sb));
+                l2_tma_load_2d(l2_smem_u32(sB0 + sb * (L2TC_N * L2TC_K)), &map_t, (r % KH) * L2TC_K,
+                               pair * a.cap_t + (tile_begin + r / KH) * L2TC_N, BAR(1 + sb));
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
             l2_mbar_wait(BAR(0), 0);
-            const uint64_t da = l2_smem_desc(l2_smem_u32(sA));
             for (int i = 0; i < ntile; ++i) {
                 const int st = i & 1, ph = (i >> 1) & 1;          // accumulator ring (2 deep)
-                const int sb = i % NB, pb = (i / NB) & 1;         // operand ring (NB deep: covers the TMA round trip)
-                l2_mbar_wait_backoff<L2P_SLEEP_MMA>(BAR(1 + sb), pb);            // train tile landed
                 l2_mbar_wait_backoff<L2P_SLEEP_MMA>(BAR(3 + 2 * NB + st), ph ^ 1);   // accumulator drained
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t db = l2_smem_desc(l2_smem_u32(sB0 + sb * (L2TC_N * L2TC_K)));
                 const uint32_t d = tmem + (uint32_t)(st * L2TC_N);
 #pragma unroll
-                for (int k = 0; k < L2TC_K / 32; ++k) {
-                    const uint64_t dak = da + (uint64_t)(2 * k), dbk = db + (uint64_t)(2 * k);
-                    const uint32_t acc = k > 0 ? 1u : 0u;
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-                                 ::"r"(d), "l"(dak), "l"(dbk), "r"(L2TC_IDESC), "r"(acc) : "memory");
+                for (int h = 0; h < KH; ++h) {
+                    const int r = i * KH + h;
+                    const int sb = r % NB, pb = (r / NB) & 1;     // operand ring (NB deep: covers the TMA round trip)
+                    l2_mbar_wait_backoff<L2P_SLEEP_MMA>(BAR(1 + sb), pb);        // this half of the train tile landed
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t da = l2_smem_desc(l2_smem_u32(sA + h * (L2TC_M * L2TC_K)));
+                    const uint64_t db = l2_smem_desc(l2_smem_u32(sB0 + sb * (L2TC_N * L2TC_K)));
+#pragma unroll
+                    for (int k = 0; k < L2TC_K / 32; ++k) {
+                        const uint64_t dak = da + (uint64_t)(2 * k), dbk = db + (uint64_t)(2 * k);
+                        const uint32_t acc = (h > 0 || k > 0) ? 1u : 0u;
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                                     ::"r"(d), "l"(dak), "l"(dbk), "r"(L2TC_IDESC), "r"(acc) : "memory");
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(1 + NB + sb)) : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(1 + NB + sb)) : "memory");
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(1 + 2 * NB + st)) : "memory");
             }
         }
@@ -579,12 +589,12 @@ __global__ void __launch_bounds__(256) k_l2p_merge(l2p_args a, int* __restrict__
     o_idx[o] = best.i0; o_idx[o + 1] = best.i1; o_dist[o] = best.d0; o_dist[o + 1] = best.d1;
 }
 
-static zs_status l2_make_map(CUtensorMap* m, const uint8_t* base, size_t rows)
+static zs_status l2_make_map(CUtensorMap* m, const uint8_t* base, size_t rows, int row_bytes = L2TC_K)
 {
     zs_encode_tiled_fn enc = zs_get_encode_tiled();
     if (!enc) { zs_set_error("cuTensorMapEncodeTiled is not available from this driver"); return ZS_ERR_CUDA; }
-    const cuuint64_t dims[2] = { L2TC_K, (cuuint64_t)rows };
-    const cuuint64_t strides[1] = { L2TC_K };
+    const cuuint64_t dims[2] = { (cuuint64_t)row_bytes, (cuuint64_t)rows };
+    const cuuint64_t strides[1] = { (cuuint64_t)row_bytes };
     const cuuint32_t box[2] = { L2TC_K, L2TC_M }, es[2] = { 1, 1 };
     const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -597,13 +607,34 @@ static zs_status l2_make_map(CUtensorMap* m, const uint8_t* base, size_t rows)
 zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, const uint8_t* t8, const int* nt, int pairs,
                             int cap_q, int cap_t, int dim, int* idx, int* dist, void* part, const int* qnorm, const int* tnorm)
 {
-    ZS_REQUIRE(dim == L2TC_K, "tensor-core L2 path needs 128-dimensional descriptors");
+    ZS_REQUIRE(dim == L2TC_K || dim == 2 * L2TC_K, "tensor-core path needs 128- or 256-byte descriptor rows");
     ZS_REQUIRE(((uintptr_t)q8 % 16) == 0 && ((uintptr_t)t8 % 16) == 0, "descriptor arrays must be 16-byte aligned");
     CUtensorMap mq, mt;
-    zs_status st = l2_make_map(&mq, q8, (size_t)pairs * cap_q);
+    zs_status st = l2_make_map(&mq, q8, (size_t)pairs * cap_q, dim);
     if (st != ZS_OK) return st;
-    if ((st = l2_make_map(&mt, t8, (size_t)pairs * cap_t)) != ZS_OK) return st;
+    if ((st = l2_make_map(&mt, t8, (size_t)pairs * cap_t, dim)) != ZS_OK) return st;
     const int q_tiles = zs_div_up(cap_q, L2TC_M), t_tiles = zs_div_up(cap_t, L2TC_N);
+    if (dim == 2 * L2TC_K) {
+        // 256-byte rows (expanded binary descriptors): two K halves; the caller always supplies the norms (bit counts)
+        ZS_REQUIRE(qnorm && tnorm, "256-byte rows need their norms");
+        int splits = (int)((4LL * ctx->sm_count + (long long)q_tiles * pairs - 1) / ((long long)q_tiles * pairs));
+        splits = splits < 1 ? 1 : splits > t_tiles ? t_tiles : splits;
+        l2p_args b;
+        b.nq = nq; b.nt = nt; b.cap_q = cap_q; b.cap_t = cap_t;
+        b.tpc = zs_div_up(t_tiles, splits); b.splits = zs_div_up(t_tiles, b.tpc);
+        b.part = (int4*)part; b.qnorm = qnorm; b.tnorm = tnorm;
+        const size_t smem = 1024 + (size_t)(2 * L2TC_M + L2P_BSTAGES * L2TC_N) * L2TC_K;
+        static bool attr_h = false;
+        if (!attr_h) {
+            ZS_CUDA(cudaFuncSetAttribute((k_l2_tc_persist<2, true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_h = true;
+        }
+        k_l2_tc_persist<2, true, 2><<<dim3(q_tiles, b.splits, pairs), 64 + 256, smem, ctx->stream>>>(mq, mt, b);
+        ZS_LAUNCH_CHECK(ctx);
+        k_l2p_merge<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(b, idx, dist);
+        ZS_LAUNCH_CHECK(ctx);
+        return ZS_OK;
+    }
     if (!ctx->sw.l2_one_tile) {
         // persistent kernel: enough CTAs for two waves of 2 CTAs per SM, otherwise as many train tiles per CTA as possible
         int splits = (int)((4LL * ctx->sm_count + (long long)q_tiles * pairs - 1) / ((long long)q_tiles * pairs));
