@@ -461,6 +461,11 @@ def measure_frontend(args, rank, world, local_rank, ctx, light=False):
                               "achieved_gbs": (B * b / (stage_ms[k] * 1e-3) / 1e9) if stage_ms[k] > 0 else None,
                               "frac_of_hbm_peak": (B * b / (stage_ms[k] * 1e-3) / 1e9 / peak) if stage_ms[k] > 0 else None}
                           for k, b in stage_bytes.items()}
+        if stage_ms["match"] > 0:
+            # the match stage is a contraction, not a stream: B x N x N x 256-bit Hamming distances, on the tcgen05 kind::i8 kernel
+            # (bits expanded to bytes) when the call is large enough, else on the CUDA cores (ZS_HAMMING_NO_TENSOR forces those)
+            stage_roofline["match"]["giga_distances_per_s"] = B * kp_mean * kp_mean / (stage_ms["match"] * 1e-3) / 1e9
+            stage_roofline["match"]["tera_ops_per_s"] = 2.0 * 256 * B * kp_mean * kp_mean / (stage_ms["match"] * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -238,8 +238,16 @@ def test_hamming_golden(ctx, golden, nm, qk, tk):
     assert np.array_equal(cdist[keep], g[f"cv_cross_{nm}_d"])
 
 
-def test_hamming_batch_ragged_vs_oracle(ctx):
+@pytest.mark.parametrize("path", ["cuda_core", "tensor"])
+def test_hamming_batch_ragged_vs_oracle(ctx, switches, path):
+    """ragged batch (empty sides, one row, tile tails, duplicates, 16-bit descriptors) through both Hamming paths: the CUDA-core
+    kernel and the tcgen05 kind::i8 kernel fed with the descriptors expanded to one byte per bit (forced here: by default
+    only calls of at least 12 M distances take it)"""
     from zenslam_b200.runtime import match_hamming_cross, match_hamming_knn2
+    if path == "tensor":
+        switches.set(ctx, "ZS_HAMMING_TENSOR_MIN", 1)
+    else:
+        switches.set(ctx, "ZS_HAMMING_NO_TENSOR")
     rng = np.random.default_rng(5)
     sizes = [(1100, 1000), (0, 50), (37, 0), (1, 1), (300, 1411), (129, 128)]
     qs = [rng.integers(0, 256, (a, 32), dtype=np.uint8) for a, _ in sizes]
@@ -265,19 +273,23 @@ def test_hamming_batch_ragged_vs_oracle(ctx):
         assert np.array_equal(cdist[k, keep], odd.astype(np.float32))
 
 
-@pytest.mark.parametrize("variant,splits", [(0, 0), (0, 3), (2, 0), (3, 2), (4, 0), (5, 0), (5, 5)])
+@pytest.mark.parametrize("variant,splits", [(0, 0), (0, 3), (2, 0), (3, 2), (4, 0), (5, 0), (5, 5), (-1, 0)])
 def test_hamming_kernel_variants_vs_oracle(ctx, monkeypatch, variant, splits):
     """every instantiation of k_hamming_top2 behind ZS_HAMMING_VARIANT (queries per thread x carry-save / plain popcount) and
-    train-side split counts, packed (distance << 22 | row) keys included: ragged batch with duplicate rows and 16-bit
+    train-side split counts, packed (distance << 22 | row) keys included, and (variant -1) the tensor-core path: ragged batch with duplicate rows and 16-bit
     descriptors (tie floods) against the oracle's stable top-2 / cross-check"""
     from zenslam_b200.runtime import match_hamming_cross, match_hamming_knn2
-    if variant:
+    if variant > 0:
         monkeypatch.setenv("ZS_HAMMING_VARIANT", str(variant))
+    if variant == -1:
+        monkeypatch.setenv("ZS_HAMMING_TENSOR_MIN", "1")             # the tensor-core path (bits expanded to bytes), whatever the size
+    else:
+        monkeypatch.setenv("ZS_HAMMING_NO_TENSOR", "1")
     if splits:
         monkeypatch.setenv("ZS_HAMMING_SPLITS", str(splits))
     ctx.reload_switches()
     try:
-        rng = np.random.default_rng(50 + variant)
+        rng = np.random.default_rng(50 + abs(variant))
         sizes = [(700, 900), (0, 50), (37, 0), (1, 1), (300, 1411), (129, 128), (513, 2)]
         qs = [rng.integers(0, 256, (a, 32), dtype=np.uint8) for a, _ in sizes]
         ts = [rng.integers(0, 256, (b, 32), dtype=np.uint8) for _, b in sizes]
@@ -303,6 +315,8 @@ def test_hamming_kernel_variants_vs_oracle(ctx, monkeypatch, variant, splits):
     finally:
         monkeypatch.delenv("ZS_HAMMING_VARIANT", raising=False)
         monkeypatch.delenv("ZS_HAMMING_SPLITS", raising=False)
+        monkeypatch.delenv("ZS_HAMMING_TENSOR_MIN", raising=False)
+        monkeypatch.delenv("ZS_HAMMING_NO_TENSOR", raising=False)
         ctx.reload_switches()
 
 

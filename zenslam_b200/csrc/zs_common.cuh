@@ -40,7 +40,7 @@ struct zs_switches {
     bool fe_no_graph, klt_no_tma, klt_no_share, lk_no_cache, fast_v1, l2_no_tensor, l2_one_tile, fast_pretest, subpix_v1, klt_no_persist, fast_no_tma, klt63_four_warps, klt63_unpacked, l2_chains, hamming_no_tensor;
     int pyr_force;               // 0 = by batch size, 1 = ZS_PYR_SPLIT, 2 = ZS_PYR_FUSED
     int hamming_splits, hamming_variant, l2_splits, l2_epi_groups;   // 0 = default
-    long long hamming_tensor_min; // ZS_HAMMING_TENSOR_MIN: distances per call from which Hamming matching takes the tensor-core path (0 = default 2^24)
+    long long hamming_tensor_min; // ZS_HAMMING_TENSOR_MIN: distances per call from which Hamming matching takes the tensor-core path (0 = default 12 M)
     int klt31_packed;            // ZS_KLT31_PACKED: 24 / 28 = packed-template form of the 31x31 kernel at that many CTAs per SM (experiment)
     int klt63_packed;            // ZS_KLT63_PACKED: 6 / 7 = the packed-template two-tile 63x63 kernel at that many CTAs per SM (default 8)
     int klt_persist_min;         // ZS_KLT_PERSIST_MIN: launches with at least this many (job, point) items take the persistent form (0 = default)

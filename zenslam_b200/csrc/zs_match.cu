@@ -286,7 +286,7 @@ static int hamming_splits(const zs_context* ctx, int pairs, int cap_q, int cap_t
 // ---- Hamming on the tensor cores (late round 2).  For 0 / 1 vectors |a - b|^2 = |a| + |b| - 2 a.b is the Hamming distance, so the
 // 256-bit descriptors, expanded to one byte per bit, go through the tcgen05 kind::i8 kernel of the L2 matcher (zs_match_l2.cu,
 // two 128-byte K halves per row) with their bit counts as the "norms": same exact integers, same tie rule (smaller train row).
-// Taken for problems large enough to pay for the expansion pass (ZS_HAMMING_TENSOR_MIN distances per call, default 2^24;
+// Taken for problems large enough to pay for the expansion pass (ZS_HAMMING_TENSOR_MIN distances per call, default 12 M;
 // ZS_HAMMING_NO_TENSOR keeps the CUDA-core kernel).
 zs_status zs_l2_tensor_top2(zs_context* ctx, const uint8_t* q8, const int* nq, const uint8_t* t8, const int* nt, int pairs,
                             int cap_q, int cap_t, int dim, int* idx, int* dist, void* part, const int* qnorm, const int* tnorm);   // zs_match_l2.cu
@@ -313,7 +313,9 @@ __global__ void __launch_bounds__(256) k_bits_expand(const uint8_t* __restrict__
 static bool hamming_use_tensor(const zs_context* ctx, int pairs, int cap_q, int cap_t)
 {
     if (ctx->sw.hamming_no_tensor) return false;
-    const long long min_work = ctx->sw.hamming_tensor_min > 0 ? ctx->sw.hamming_tensor_min : (1LL << 24);
+    // measured crossover (profiles/r2_hamming_tensor.txt): below ~2^23.5 distances a call is launch-bound either way (32 - 38 us)
+    // and the CUDA-core kernel's two launches beat the tensor path's five
+    const long long min_work = ctx->sw.hamming_tensor_min > 0 ? ctx->sw.hamming_tensor_min : 12000000LL;
     return (long long)pairs * cap_q * cap_t >= min_work;
 }
 // ints of scratch behind `part` for the tensor path: partial top-2 + both expanded sides + their bit counts (+ alignment slack)
@@ -321,19 +323,28 @@ static size_t hamming_tensor_ints(int pairs, int cap_q, int cap_t)
 {
     return zs_l2_tensor_part_ints(pairs, cap_q, cap_t) + 64 * (size_t)pairs * ((size_t)cap_q + cap_t) + (size_t)pairs * ((size_t)cap_q + cap_t) + 256;
 }
+// both sides expanded behind `part`: [q8 | t8 | bit counts of q | of t | partial top-2 of the tensor kernel]
+struct ham_expanded { uint8_t* q8; uint8_t* t8; int* qn; int* tn; void* l2part; };
+static zs_status hamming_expand(zs_context* ctx, const uint8_t* q, const int* nq, size_t qs, const uint8_t* t, const int* nt, size_t ts,
+                                int pairs, int cap_q, int cap_t, void* part, ham_expanded* e)
+{
+    const size_t rq = (size_t)pairs * cap_q, rt = (size_t)pairs * cap_t;
+    e->q8 = (uint8_t*)(((uintptr_t)part + 127) & ~(uintptr_t)127); e->t8 = e->q8 + rq * 256;
+    e->qn = (int*)(e->t8 + rt * 256); e->tn = e->qn + rq;
+    e->l2part = (void*)(((uintptr_t)(e->tn + rt) + 15) & ~(uintptr_t)15);
+    k_bits_expand<<<(unsigned)zs_div_up(rq, 8), 256, 0, ctx->stream>>>(q, nq, qs, cap_q, rq, e->q8, e->qn);
+    ZS_LAUNCH_CHECK(ctx);
+    k_bits_expand<<<(unsigned)zs_div_up(rt, 8), 256, 0, ctx->stream>>>(t, nt, ts, cap_t, rt, e->t8, e->tn);
+    ZS_LAUNCH_CHECK(ctx);
+    return ZS_OK;
+}
 static zs_status hamming_top2_tensor(zs_context* ctx, const uint8_t* q, const int* nq, size_t qs, const uint8_t* t, const int* nt, size_t ts,
                                      int pairs, int cap_q, int cap_t, int* idx, int* dist, void* part)
 {
-    const size_t rq = (size_t)pairs * cap_q, rt = (size_t)pairs * cap_t;
-    uint8_t* base = (uint8_t*)(((uintptr_t)part + 127) & ~(uintptr_t)127);
-    uint8_t* q8 = base; uint8_t* t8 = q8 + rq * 256;
-    int* qn = (int*)(t8 + rt * 256); int* tn = qn + rq;
-    void* l2part = (void*)(((uintptr_t)(tn + rt) + 15) & ~(uintptr_t)15);
-    k_bits_expand<<<(unsigned)zs_div_up(rq, 8), 256, 0, ctx->stream>>>(q, nq, qs, cap_q, rq, q8, qn);
-    ZS_LAUNCH_CHECK(ctx);
-    k_bits_expand<<<(unsigned)zs_div_up(rt, 8), 256, 0, ctx->stream>>>(t, nt, ts, cap_t, rt, t8, tn);
-    ZS_LAUNCH_CHECK(ctx);
-    return zs_l2_tensor_top2(ctx, q8, nq, t8, nt, pairs, cap_q, cap_t, 256, idx, dist, l2part, qn, tn);
+    ham_expanded e;
+    zs_status st = hamming_expand(ctx, q, nq, qs, t, nt, ts, pairs, cap_q, cap_t, part, &e);
+    if (st != ZS_OK) return st;
+    return zs_l2_tensor_top2(ctx, e.q8, nq, e.t8, nt, pairs, cap_q, cap_t, 256, idx, dist, e.l2part, e.qn, e.tn);
 }
 
 static int hamming_chunk(int cap_t, int splits) { return splits > 1 ? (zs_div_up(cap_t, splits) + 127) / 128 * 128 : 0x7fffffff; }
@@ -408,10 +419,18 @@ extern "C" zs_status zs_match_hamming_cross(zs_context* ctx, const uint8_t* d_q,
     int* fi = (int*)s; int* fd = fi + 2 * (size_t)cap_q * pairs;
     int* bi = fd + 2 * (size_t)cap_q * pairs; int* bd = bi + 2 * (size_t)cap_t * pairs;
     void* part = bd + 2 * (size_t)cap_t * pairs;          // 16-byte aligned: every piece before it is a multiple of 16 bytes
-    st = hamming_top2(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, cap_t, fi, fd, part);
-    if (st != ZS_OK) return st;
-    st = hamming_top2(ctx, d_t, d_nt, t_stride, d_q, d_nq, q_stride, pairs, cap_t, cap_q, bi, bd, part);
-    if (st != ZS_OK) return st;
+    if (hamming_use_tensor(ctx, pairs, cap_q, cap_t)) {            // both directions from ONE expansion of the two sides
+        ZS_REQUIRE(cap_t < (1 << HAMMING_ROW_BITS) && cap_q < (1 << HAMMING_ROW_BITS), "more than 2^22 rows per pair");
+        ham_expanded e;
+        if ((st = hamming_expand(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, cap_t, part, &e)) != ZS_OK) return st;
+        if ((st = zs_l2_tensor_top2(ctx, e.q8, d_nq, e.t8, d_nt, pairs, cap_q, cap_t, 256, fi, fd, e.l2part, e.qn, e.tn)) != ZS_OK) return st;
+        if ((st = zs_l2_tensor_top2(ctx, e.t8, d_nt, e.q8, d_nq, pairs, cap_t, cap_q, 256, bi, bd, e.l2part, e.tn, e.qn)) != ZS_OK) return st;
+    } else {
+        st = hamming_top2(ctx, d_q, d_nq, q_stride, d_t, d_nt, t_stride, pairs, cap_q, cap_t, fi, fd, part);
+        if (st != ZS_OK) return st;
+        st = hamming_top2(ctx, d_t, d_nt, t_stride, d_q, d_nq, q_stride, pairs, cap_t, cap_q, bi, bd, part);
+        if (st != ZS_OK) return st;
+    }
     k_cross_finish<<<dim3(zs_div_up(cap_q, 256), pairs), 256, 0, ctx->stream>>>(fi, fd, bi, d_nq, cap_q, cap_t, 0, d_idx, d_dist, nullptr);
     ZS_LAUNCH_CHECK(ctx);
     return ZS_OK;
