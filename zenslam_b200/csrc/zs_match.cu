@@ -329,12 +329,13 @@ static zs_status hamming_expand(zs_context* ctx, const uint8_t* q, const int* nq
                                 int pairs, int cap_q, int cap_t, void* part, ham_expanded* e)
 {
     const size_t rq = (size_t)pairs * cap_q, rt = (size_t)pairs * cap_t;
+    ZS_REQUIRE(rq < (1u << 30) && rt < (1u << 30), "too many descriptor rows for one call");
     e->q8 = (uint8_t*)(((uintptr_t)part + 127) & ~(uintptr_t)127); e->t8 = e->q8 + rq * 256;
     e->qn = (int*)(e->t8 + rt * 256); e->tn = e->qn + rq;
     e->l2part = (void*)(((uintptr_t)(e->tn + rt) + 15) & ~(uintptr_t)15);
-    k_bits_expand<<<(unsigned)zs_div_up(rq, 8), 256, 0, ctx->stream>>>(q, nq, qs, cap_q, rq, e->q8, e->qn);
+    k_bits_expand<<<(unsigned)((rq + 7) / 8), 256, 0, ctx->stream>>>(q, nq, qs, cap_q, rq, e->q8, e->qn);
     ZS_LAUNCH_CHECK(ctx);
-    k_bits_expand<<<(unsigned)zs_div_up(rt, 8), 256, 0, ctx->stream>>>(t, nt, ts, cap_t, rt, e->t8, e->tn);
+    k_bits_expand<<<(unsigned)((rt + 7) / 8), 256, 0, ctx->stream>>>(t, nt, ts, cap_t, rt, e->t8, e->tn);
     ZS_LAUNCH_CHECK(ctx);
     return ZS_OK;
 }
