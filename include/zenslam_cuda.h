@@ -193,7 +193,10 @@ ZS_API zs_status zs_detect_keypoints_orb_host(zs_context* ctx, const uint8_t* im
  * knn2: per query the two nearest (ties -> smaller train index): d_idx [pairs][cap_q][2] (-1 = none),
  * d_dist [pairs][cap_q][2] (Hamming: popcount as float; L2: sqrtf of the exact integer distance),
  * d_pass [pairs][cap_q]: Lowe ratio gate of matcher.cpp:70 ((double)d0 < ratio*(double)d1, two neighbours).
- * cross: BFMatcher(crossCheck=true).match: d_idx [pairs][cap_q] = train index or -1, d_dist likewise. */
+ * cross: BFMatcher(crossCheck=true).match: d_idx [pairs][cap_q] = train index or -1, d_dist likewise.
+ * Hamming calls of at least 12 M distances (pairs * cap_q * cap_t) run on the tcgen05 tensor cores too: the descriptors are
+ * expanded to one 0 / 1 byte per bit, for which the squared L2 distance IS the Hamming distance, and go through the kind::i8
+ * kernel of the L2 matcher (same exact integers, same tie rule); smaller calls use the CUDA-core kernel. */
 ZS_API zs_status zs_match_hamming_knn2(zs_context* ctx, const uint8_t* d_q, const int* d_nq, size_t q_stride,
                                        const uint8_t* d_t, const int* d_nt, size_t t_stride, int pairs,
                                        int cap_q, int cap_t, double ratio,
